@@ -1,0 +1,396 @@
+// kvstore('device') push+pull as ONE kernel: cross-GPU gradient reduction over NVLink peer memory fused
+// with gradient rescale/clip, the optimizer update and the weight fan-out.
+//
+// What it replaces in the reference: CommDevice::Reduce = (N-1) cudaMemcpyPeerAsync +
+// ElementwiseSum<gpu> + a blocking stream sync inside the engine op (src/kvstore/comm.h:503-550,
+// src/ndarray/ndarray.cc:1318-1331), then the Python updater callback launching sgd_mom_update /
+// mp_sgd_mom_update per tensor (optimizer_op-inl.h:305-448), then CommDevice::Broadcast = (N+1) copies
+// (comm.h:598-616) -- per parameter tensor, ~161 times per ResNet-50 step; and KVStoreNCCL's
+// ncclReduce + ncclBcast pair (kvstore_nccl.h:270-308,386-413).
+//
+// Here every GPU runs the same persistent kernel over a symmetric, peer-mapped arena that holds ALL
+// parameters (chunk table gives per-tensor lr/wd multipliers):
+//   * two-shot (bandwidth-bound sizes): rank r owns slice r of the arena.  It loads that slice of every
+//     peer's gradient arena straight over NVLink (16B vector loads from peer pointers), sums in fp32,
+//     applies the partitioned optimizer update (fp32 master weight + momentum exist only for the owned
+//     slice: ZeRO-1-like state partitioning), and stores the updated low-precision weight slice into
+//     EVERY rank's weight arena (peer stores).  Per-GPU NVLink traffic = 2*(N-1)/N*S.
+//   * one-shot (latency-bound sizes): every rank loads the whole message from all peers and applies the
+//     update redundantly on its own replica: one barrier pair, no second phase.
+//   * flags in peer memory (st.release.sys / ld.acquire.sys, monotonically increasing sequence numbers,
+//     never reset) replace cudaStreamSynchronize + engine ops.  Spins are bounded: on timeout the kernel
+//     records an error in a host-visible word and exits instead of hanging the GPU.
+// No NCCL call and no separate optimizer kernel runs on this path.
+#include "common.cuh"
+#include "optim_math.cuh"
+
+namespace mxb {
+namespace ar {
+
+constexpr int kMaxRanks = 8;
+constexpr int kMaxBlocks = 256;   // flag pad rows
+constexpr int kThreads = 512;
+constexpr int kChunk = 1024;
+constexpr uint32_t kSpinLimit = 200u * 1000u * 1000u;
+
+enum Mode : int {
+  kAllreduce = 0,   // out_p[i] = scale * sum_q grad_q[i]            (push without updater + pull)
+  kSgd = 1,         // SGD / momentum / NAG update, weights fanned out
+  kAdam = 2,
+  kLambPhase1 = 3,  // reduce + moments + direction r (local slice) + per-tensor partial norms
+  kLambPhase2 = 4,  // w -= lr*trust*r on the slice, weights fanned out (no gradient traffic)
+  kBroadcast = 5,   // weights_p[i] = src[i] for the owned slice (init / re-shard)
+};
+
+struct Args {
+  void* grads[kMaxRanks];     // gradient arenas as mapped in this process
+  void* weights[kMaxRanks];   // weight (or allreduce output) arenas
+  uint32_t* flags[kMaxRanks]; // signal pads: [kMaxBlocks][kMaxRanks] uint32
+  float* w32;                 // local fp32 master arena (may be null: weight arena is the master)
+  float* mom;                 // local momentum / Adam m
+  float* var;                 // Adam / LAMB v
+  float* rbuf;                // LAMB direction
+  float* w_norm2;             // LAMB per-tensor partial norms (local)
+  float* r_norm2;
+  const int* chunk_tid;
+  const float* lr_mult;
+  const float* wd_mult;
+  int* err;                   // host-visible error word
+  int64_t n;                  // arena elements (multiple of kChunk)
+  int rank, nranks;
+  int mode, one_shot;
+  int g_dt, w_dt;
+  uint32_t seq;
+  int zero_grad;              // zero the local gradient slice after it was consumed by everyone
+  float lr, wd, momentum, rescale, clip;
+  int nesterov, has_mom;
+  float beta1, beta2, eps, bc1, bc2;
+  float lamb_lower, lamb_upper;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Block-level barrier with the same block index on every peer.
+__device__ __forceinline__ bool peer_barrier(const Args& a, uint32_t val) {
+  __shared__ int ok;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  if (threadIdx.x < a.nranks) {
+    const int p = threadIdx.x;
+    st_release_sys(a.flags[p] + blockIdx.x * kMaxRanks + a.rank, val);
+    const uint32_t* mine = a.flags[a.rank] + blockIdx.x * kMaxRanks + p;
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_sys(mine) - val) < 0) {
+      if (++spins > kSpinLimit) {
+        ok = 0;
+        if (a.err) atomicExch(a.err, 1 + p);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  return ok != 0;
+}
+
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float (&o)[8]);
+template <>
+__device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&o)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o[2 * i] = __low2float(h[i]);
+    o[2 * i + 1] = __high2float(h[i]);
+  }
+}
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float (&o)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* p, const float (&o)[8]);
+template <>
+__device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float (&o)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+template <>
+__device__ __forceinline__ void st8<float>(float* p, const float (&o)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+}
+
+template <typename GT, typename WT, int NR>
+__global__ void __launch_bounds__(kThreads)
+fused_kernel(const Args a) {
+  const int nr = NR > 0 ? NR : a.nranks;
+  if (nr > 1) {
+    if (!peer_barrier(a, 2u * a.seq)) return;
+  }
+  // slice owned by this rank (two-shot) or the whole arena (one-shot)
+  const int64_t n_chunks = a.n / kChunk;
+  int64_t c_begin = 0, c_end = n_chunks;
+  if (!a.one_shot && nr > 1) {
+    const int64_t per = (n_chunks + nr - 1) / nr;
+    c_begin = min(n_chunks, per * a.rank);
+    c_end = min(n_chunks, c_begin + per);
+  }
+  const bool fan_out = !a.one_shot && nr > 1;
+  constexpr int kVecPerChunk = kChunk / 8;  // 128 vectors of 8 elements
+  const int64_t v_begin = c_begin * kVecPerChunk, v_end = c_end * kVecPerChunk;
+  __shared__ float red[2][kThreads / 32];
+
+  // block-uniform trip count (LAMB phase 1 has __syncthreads inside); base is a multiple of 128 vectors, so
+  // every group of 128 consecutive threads works on exactly one 1024-element chunk (= one tensor).
+  for (int64_t base = v_begin + (int64_t)blockIdx.x * kThreads; base < v_end; base += (int64_t)gridDim.x * kThreads) {
+    const int64_t v = base + threadIdx.x;
+    const bool active = v < v_end;
+    const int64_t e = v * 8;
+    const int64_t chunk = active ? e / kChunk : 0;
+    int t = 0;
+    float lr = a.lr, wd = a.wd;
+    bool skip = !active;
+    if (active && a.chunk_tid != nullptr) {
+      t = __ldg(a.chunk_tid + chunk);
+      if (t < 0) skip = true;
+      else {
+        lr *= a.lr_mult ? __ldg(a.lr_mult + t) : 1.f;
+        wd *= a.wd_mult ? __ldg(a.wd_mult + t) : 1.f;
+      }
+    }
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (!skip && a.mode != kLambPhase2 && a.mode != kBroadcast) {
+      // gradient reduction: own copy first, then peers in a rank-rotated order to spread link load
+#pragma unroll
+      for (int k = 0; k < (NR > 0 ? NR : kMaxRanks); ++k) {
+        if (k < nr) {
+          const int p = (a.rank + k) % nr;
+          float x[8];
+          ld8<GT>(reinterpret_cast<const GT*>(a.grads[p]) + e, x);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += x[j];
+        }
+      }
+    }
+    if (a.mode == kAllreduce) {
+      if (!skip) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] *= a.rescale;
+        if (fan_out) {
+#pragma unroll
+          for (int k = 0; k < (NR > 0 ? NR : kMaxRanks); ++k)
+            if (k < nr) st8<WT>(reinterpret_cast<WT*>(a.weights[(a.rank + k) % nr]) + e, g);
+        } else {
+          st8<WT>(reinterpret_cast<WT*>(a.weights[a.rank]) + e, g);
+        }
+      }
+      continue;
+    }
+    float w[8];
+    if (!skip) {
+      if (a.w32 != nullptr) ld8<float>(a.w32 + e, w);
+      else ld8<WT>(reinterpret_cast<const WT*>(a.weights[a.rank]) + e, w);
+    }
+    if (a.mode == kSgd) {
+      if (skip) continue;
+      SgdHyper h{a.lr, a.wd, a.momentum, a.rescale, a.clip, a.nesterov, a.has_mom};
+      float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (a.has_mom) ld8<float>(a.mom + e, m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sgd_step(w[j], g[j], m[j], h, lr, wd);
+      if (a.has_mom) st8<float>(a.mom + e, m);
+    } else if (a.mode == kAdam) {
+      if (skip) continue;
+      AdamHyper h{a.lr, a.wd, a.beta1, a.beta2, a.eps, a.rescale, a.clip};
+      float m[8], vv[8];
+      ld8<float>(a.mom + e, m);
+      ld8<float>(a.var + e, vv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) adam_step(w[j], g[j], m[j], vv[j], h, lr, wd);
+      st8<float>(a.mom + e, m);
+      st8<float>(a.var + e, vv);
+    } else if (a.mode == kLambPhase1) {
+      // block-uniform chunk: 512 threads x 8 = 4 chunks per block iteration -> reduce per 128-thread group
+      float sw = 0.f, sr = 0.f;
+      if (!skip) {
+        LambHyper h{a.beta1, a.beta2, a.eps, a.rescale, a.clip, a.bc1, a.bc2};
+        float m[8], vv[8], r[8];
+        ld8<float>(a.mom + e, m);
+        ld8<float>(a.var + e, vv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          r[j] = lamb_dir(w[j], g[j], m[j], vv[j], h, wd);
+          sw += w[j] * w[j];
+          sr += r[j] * r[j];
+        }
+        st8<float>(a.mom + e, m);
+        st8<float>(a.var + e, vv);
+        st8<float>(a.rbuf + e, r);
+      }
+      // 128 consecutive threads (4 warps) share one chunk => one tensor id
+      sw = warp_sum(sw);
+      sr = warp_sum(sr);
+      if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = sw;
+        red[1][threadIdx.x >> 5] = sr;
+      }
+      __syncthreads();
+      if ((threadIdx.x & 127) == 0 && !skip) {
+        const int wq = threadIdx.x >> 5;
+        const float aw = red[0][wq] + red[0][wq + 1] + red[0][wq + 2] + red[0][wq + 3];
+        const float arr = red[1][wq] + red[1][wq + 1] + red[1][wq + 2] + red[1][wq + 3];
+        atomicAdd(a.w_norm2 + t, aw);
+        atomicAdd(a.r_norm2 + t, arr);
+      }
+      __syncthreads();
+      continue;
+    } else if (a.mode == kLambPhase2) {
+      if (skip) continue;
+      float wn = sqrtf(__ldg(a.w_norm2 + t)), rn = sqrtf(__ldg(a.r_norm2 + t));
+      if (a.lamb_lower >= 0.f) wn = fmaxf(wn, a.lamb_lower);
+      if (a.lamb_upper >= 0.f) wn = fminf(wn, a.lamb_upper);
+      const float ratio = (wn > 0.f && rn > 0.f) ? wn / rn : 1.f;
+      float r[8];
+      ld8<float>(a.rbuf + e, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] -= lr * ratio * r[j];
+    } else if (a.mode == kBroadcast) {
+      if (skip) continue;
+    }
+    // write back master + fan the low-precision weights out to every replica
+    if (a.w32 != nullptr) st8<float>(a.w32 + e, w);
+    if (fan_out) {
+#pragma unroll
+      for (int k = 0; k < (NR > 0 ? NR : kMaxRanks); ++k)
+        if (k < nr) st8<WT>(reinterpret_cast<WT*>(a.weights[(a.rank + k) % nr]) + e, w);
+    } else {
+      st8<WT>(reinterpret_cast<WT*>(a.weights[a.rank]) + e, w);
+    }
+  }
+  if (nr > 1) {
+    if (!peer_barrier(a, 2u * a.seq + 1u)) return;
+  }
+  // Everyone has consumed this rank's gradients: clear them so the next backward can accumulate
+  // without a separate memset (grad_req='add'-style arena).  Done after the barrier on the FULL local arena.
+  if (a.zero_grad && a.mode != kLambPhase2 && a.mode != kBroadcast) {
+    const int64_t nv = a.n / 8;
+    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < nv; v += (int64_t)gridDim.x * kThreads)
+      st8<GT>(reinterpret_cast<GT*>(a.grads[a.rank]) + v * 8, z);
+  }
+}
+
+template <typename GT, typename WT>
+static void launch_nr(const Args& a, int blocks, cudaStream_t s) {
+  switch (a.nranks) {
+    case 1: fused_kernel<GT, WT, 1><<<blocks, kThreads, 0, s>>>(a); break;
+    case 2: fused_kernel<GT, WT, 2><<<blocks, kThreads, 0, s>>>(a); break;
+    case 4: fused_kernel<GT, WT, 4><<<blocks, kThreads, 0, s>>>(a); break;
+    case 8: fused_kernel<GT, WT, 8><<<blocks, kThreads, 0, s>>>(a); break;
+    default: fused_kernel<GT, WT, 0><<<blocks, kThreads, 0, s>>>(a); break;
+  }
+}
+
+}  // namespace ar
+}  // namespace mxb
+
+using namespace mxb;
+using namespace mxb::ar;
+
+MXB_API int MXBFusedAllreduceArgsSize() { return (int)sizeof(Args); }
+
+MXB_API int MXBFusedAllreduce(const void* args_blob, int blob_bytes, int blocks, void* stream) {
+  MXB_TRY
+  MXB_CHECK(blob_bytes == (int)sizeof(Args), "Args struct size mismatch between python and native");
+  Args a = *reinterpret_cast<const Args*>(args_blob);
+  MXB_CHECK(a.nranks >= 1 && a.nranks <= kMaxRanks, "nranks out of range");
+  MXB_CHECK(a.n % kChunk == 0, "arena size must be a multiple of 1024");
+  if (blocks <= 0) blocks = 64;
+  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a.g_dt == kBF16 && a.w_dt == kBF16) launch_nr<__nv_bfloat16, __nv_bfloat16>(a, blocks, s);
+  else if (a.g_dt == kBF16 && a.w_dt == kF32) launch_nr<__nv_bfloat16, float>(a, blocks, s);
+  else if (a.g_dt == kF32 && a.w_dt == kF32) launch_nr<float, float>(a, blocks, s);
+  else if (a.g_dt == kF32 && a.w_dt == kBF16) launch_nr<float, __nv_bfloat16>(a, blocks, s);
+  else throw std::runtime_error("fused allreduce: dtypes must be bf16 or fp32");
+  CUDA_CHECK(cudaGetLastError());
+  MXB_CATCH
+}
+
+// ---- peer-memory plumbing (CommDevice::EnableP2P / InitMergeBuffer analogue, comm.h:678-755) ----
+MXB_API int MXBDeviceMalloc(int64_t bytes, void** out) {
+  MXB_TRY
+  CUDA_CHECK(cudaMalloc(out, (size_t)bytes));
+  CUDA_CHECK(cudaMemset(*out, 0, (size_t)bytes));
+  MXB_CATCH
+}
+MXB_API int MXBDeviceFree(void* p) {
+  MXB_TRY
+  CUDA_CHECK(cudaFree(p));
+  MXB_CATCH
+}
+MXB_API int MXBIpcGetHandle(void* p, void* handle64) {
+  MXB_TRY
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  CUDA_CHECK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), p));
+  MXB_CATCH
+}
+MXB_API int MXBIpcOpenHandle(const void* handle64, void** out) {
+  MXB_TRY
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CUDA_CHECK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  MXB_CATCH
+}
+MXB_API int MXBIpcCloseHandle(void* p) {
+  MXB_TRY
+  CUDA_CHECK(cudaIpcCloseMemHandle(p));
+  MXB_CATCH
+}
+MXB_API int MXBEnablePeerAccess(int dev, int peer) {
+  MXB_TRY
+  int cur;
+  CUDA_CHECK(cudaGetDevice(&cur));
+  CUDA_CHECK(cudaSetDevice(dev));
+  int can = 0;
+  CUDA_CHECK(cudaDeviceCanAccessPeer(&can, dev, peer));
+  if (!can) {
+    cudaSetDevice(cur);
+    throw std::runtime_error("device " + std::to_string(dev) + " cannot access peer " + std::to_string(peer));
+  }
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+  } else if (e != cudaSuccess) {
+    cudaSetDevice(cur);
+    CUDA_CHECK(e);
+  }
+  CUDA_CHECK(cudaSetDevice(cur));
+  MXB_CATCH
+}
+MXB_API int MXBHostAllocMapped(int64_t bytes, void** host_ptr, void** dev_ptr) {
+  MXB_TRY
+  CUDA_CHECK(cudaHostAlloc(host_ptr, (size_t)bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(*host_ptr, 0, (size_t)bytes);
+  CUDA_CHECK(cudaHostGetDevicePointer(dev_ptr, *host_ptr, 0));
+  MXB_CATCH
+}
+MXB_API int MXBHostFree(void* p) {
+  MXB_TRY
+  CUDA_CHECK(cudaFreeHost(p));
+  MXB_CATCH
+}

@@ -1,0 +1,451 @@
+// Fused BatchNorm (+ residual add) (+ ReLU) for channels-last activations, training forward + backward.
+//
+// Reference ops being fused: BatchNorm (src/operator/nn/batch_norm.cu:147-576, cuDNN path
+// cudnn_batch_norm-inl.h), Activation(relu) (nn/activation.cu) and the residual elemwise_add -- three
+// separate engine ops (and 4-6 full passes over the activation) in the reference.  Here:
+//   forward : pass 1 reads x once (per-channel sum / sum-of-squares, fp32; the last block to finish
+//             finalises mean / biased var / inv-std, updates the running statistics with
+//             running = running*momentum + batch*(1-momentum) (batch_norm.cu:359-362) and emits the folded
+//             scale/shift), pass 2 reads x (+residual) and writes y = relu(x*scale + shift + residual).
+//             When the producer is our tcgen05 GEMM the sums come from its epilogue and pass 1 is skipped
+//             (bn_finalize only).
+//   backward: pass 1 reads dy, x (and y for the ReLU mask) once for sum(dy'), sum(dy'*xhat);
+//             pass 2 writes dx = gamma*invstd*(dy' - mean(dy') - xhat*mean(dy'*xhat)) and, for residual
+//             blocks, the masked gradient dy' for the skip branch in the same pass.
+// Layout: x is [M, C] with C contiguous (NHWC); C*sizeof(T) must be a multiple of 16 and C/VEC a power of
+// two <= 256 (all ResNet widths).  Statistics are always fp32 (AccReal in the reference).
+#include "common.cuh"
+
+namespace mxb {
+namespace bn {
+
+constexpr int kThreads = 256;
+
+template <typename T>
+struct V {
+  static constexpr int N = 16 / sizeof(T);
+};
+
+template <typename T>
+__device__ __forceinline__ void unpack(const uint4& u, float* o);
+template <>
+__device__ __forceinline__ void unpack<__nv_bfloat16>(const uint4& u, float* o) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o[2 * i] = __low2float(p[i]);
+    o[2 * i + 1] = __high2float(p[i]);
+  }
+}
+template <>
+__device__ __forceinline__ void unpack<float>(const uint4& u, float* o) {
+  o[0] = __uint_as_float(u.x); o[1] = __uint_as_float(u.y); o[2] = __uint_as_float(u.z); o[3] = __uint_as_float(u.w);
+}
+template <typename T>
+__device__ __forceinline__ uint4 pack(const float* o);
+template <>
+__device__ __forceinline__ uint4 pack<__nv_bfloat16>(const float* o) {
+  uint4 u;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+  return u;
+}
+template <>
+__device__ __forceinline__ uint4 pack<float>(const float* o) {
+  return make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
+}
+
+struct Finalize {
+  float* sum;          // [C] workspace (zeroed on exit)
+  float* sumsq;        // [C]
+  unsigned int* counter;  // arrival counter (zeroed on exit)
+  const float* gamma;  // may be null (=> 1)
+  const float* beta;   // may be null (=> 0)
+  float* running_mean; // may be null
+  float* running_var;
+  float* mean_out;     // [C] saved batch mean
+  float* invstd_out;   // [C] saved 1/sqrt(var+eps)
+  float* scale_out;    // [C] gamma*invstd
+  float* shift_out;    // [C] beta - mean*gamma*invstd
+  float eps, momentum;
+  int64_t count;       // rows reduced (N*H*W)
+};
+
+__device__ __forceinline__ void finalize_channel(const Finalize& f, int c) {
+  const float inv_n = 1.f / (float)f.count;
+  const float mean = f.sum[c] * inv_n;
+  float var = f.sumsq[c] * inv_n - mean * mean;
+  var = fmaxf(var, 0.f);
+  const float invstd = rsqrtf(var + f.eps);
+  const float g = f.gamma ? f.gamma[c] : 1.f;
+  const float b = f.beta ? f.beta[c] : 0.f;
+  f.mean_out[c] = mean;
+  f.invstd_out[c] = invstd;
+  f.scale_out[c] = g * invstd;
+  f.shift_out[c] = b - mean * g * invstd;
+  if (f.running_mean) {
+    f.running_mean[c] = f.running_mean[c] * f.momentum + mean * (1.f - f.momentum);
+    f.running_var[c] = f.running_var[c] * f.momentum + var * (1.f - f.momentum);
+  }
+  f.sum[c] = 0.f;
+  f.sumsq[c] = 0.f;
+}
+
+// Column-vector mapping: thread t owns vector column (t % CV) and rows (t / CV) + k * (kThreads / CV).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+stats_kernel(const T* __restrict__ x, int64_t M, int C, Finalize f) {
+  constexpr int N = V<T>::N;
+  const int CV = C / N;
+  const int rpi = kThreads / CV;             // rows per block iteration
+  const int col = threadIdx.x % CV;
+  const int r0 = threadIdx.x / CV;
+  float s[N], s2[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) s[j] = s2[j] = 0.f;
+  const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t row_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t row_end = min(M, row_begin + rows_per_block);
+  const T* base = x + (int64_t)col * N;
+  int64_t r = row_begin + r0;
+  // 2x unrolled for memory-level parallelism
+  for (; r + rpi < row_end; r += 2 * rpi) {
+    uint4 u0 = ldg16_stream(base + r * C);
+    uint4 u1 = ldg16_stream(base + (r + rpi) * C);
+    float v0[N], v1[N];
+    unpack<T>(u0, v0);
+    unpack<T>(u1, v1);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      s[j] += v0[j] + v1[j];
+      s2[j] += v0[j] * v0[j] + v1[j] * v1[j];
+    }
+  }
+  for (; r < row_end; r += rpi) {
+    uint4 u0 = ldg16_stream(base + r * C);
+    float v0[N];
+    unpack<T>(u0, v0);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      s[j] += v0[j];
+      s2[j] += v0[j] * v0[j];
+    }
+  }
+  __shared__ float red[kThreads][2 * 8 + 1];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    red[threadIdx.x][j] = s[j];
+    red[threadIdx.x][N + j] = s2[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < CV) {
+#pragma unroll
+    for (int j = 0; j < 2 * N; ++j) {
+      float a = 0.f;
+      for (int k = 0; k < rpi; ++k) a += red[threadIdx.x + k * CV][j];
+      if (j < N) atomicAdd(f.sum + col * N + j, a);
+      else atomicAdd(f.sumsq + col * N + (j - N), a);
+    }
+  }
+  // last block finalises
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int prev = atomicAdd(f.counter, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int c = threadIdx.x; c < C; c += kThreads) finalize_channel(f, c);
+    if (threadIdx.x == 0) *f.counter = 0u;
+  }
+}
+
+__global__ void finalize_kernel(int C, Finalize f) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) finalize_channel(f, c);
+}
+
+template <typename T, bool RELU, bool RES>
+__global__ void __launch_bounds__(kThreads)
+apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, int64_t M, int C,
+             const float* __restrict__ scale, const float* __restrict__ shift) {
+  constexpr int N = V<T>::N;
+  const int CV = C / N;
+  const int64_t total = M * CV;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;  // multiple of CV
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int col = (int)(i % CV);
+  float sc[N], sh[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    sc[j] = __ldg(scale + col * N + j);
+    sh[j] = __ldg(shift + col * N + j);
+  }
+  for (; i < total; i += stride) {
+    uint4 u = ldg16_stream(x + i * N);
+    float v[N];
+    unpack<T>(u, v);
+    if (RES) {
+      uint4 ur = ldg16_stream(res + i * N);
+      float rv[N];
+      unpack<T>(ur, rv);
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = v[j] * sc[j] + sh[j] + rv[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = v[j] * sc[j] + sh[j];
+    }
+    if (RELU) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    stg16(y + i * N, pack<T>(v));
+  }
+}
+
+struct BwdFinalize {
+  float* sum_dy;       // [C] workspace, zeroed on exit
+  float* sum_dyx;      // [C]
+  unsigned int* counter;
+  const float* gamma;  // may be null
+  const float* invstd;
+  float* dgamma;       // [C] out (may be null)
+  float* dbeta;        // [C] out (may be null)
+  float* c1;           // gamma*invstd
+  float* c2;           // mean(dy')
+  float* c3;           // mean(dy'*xhat)
+  int64_t count;
+  int accumulate;      // grad_req == 'add' for dgamma/dbeta
+};
+
+template <typename T, bool RELU>
+__global__ void __launch_bounds__(kThreads)
+bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, int64_t M, int C,
+                  const float* __restrict__ mean, BwdFinalize f) {
+  constexpr int N = V<T>::N;
+  const int CV = C / N;
+  const int rpi = kThreads / CV;
+  const int col = threadIdx.x % CV;
+  const int r0 = threadIdx.x / CV;
+  float mu[N], is[N], s[N], s2[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    mu[j] = __ldg(mean + col * N + j);
+    is[j] = __ldg(f.invstd + col * N + j);
+    s[j] = s2[j] = 0.f;
+  }
+  const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t row_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t row_end = min(M, row_begin + rows_per_block);
+  for (int64_t r = row_begin + r0; r < row_end; r += rpi) {
+    const int64_t off = r * C + (int64_t)col * N;
+    uint4 ud = ldg16_stream(dy + off);
+    uint4 ux = ldg16_stream(x + off);
+    float dv[N], xv[N];
+    unpack<T>(ud, dv);
+    unpack<T>(ux, xv);
+    if (RELU) {
+      uint4 uy = ldg16_stream(y + off);
+      float yv[N];
+      unpack<T>(uy, yv);
+#pragma unroll
+      for (int j = 0; j < N; ++j) dv[j] = yv[j] > 0.f ? dv[j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      s[j] += dv[j];
+      s2[j] += dv[j] * (xv[j] - mu[j]) * is[j];
+    }
+  }
+  __shared__ float red[kThreads][2 * 8 + 1];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    red[threadIdx.x][j] = s[j];
+    red[threadIdx.x][N + j] = s2[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < CV) {
+#pragma unroll
+    for (int j = 0; j < 2 * N; ++j) {
+      float a = 0.f;
+      for (int k = 0; k < rpi; ++k) a += red[threadIdx.x + k * CV][j];
+      if (j < N) atomicAdd(f.sum_dy + col * N + j, a);
+      else atomicAdd(f.sum_dyx + col * N + (j - N), a);
+    }
+  }
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int prev = atomicAdd(f.counter, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    const float inv_n = 1.f / (float)f.count;
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      const float sd = f.sum_dy[c], sdx = f.sum_dyx[c];
+      const float g = f.gamma ? f.gamma[c] : 1.f;
+      if (f.dgamma) f.dgamma[c] = (f.accumulate ? f.dgamma[c] : 0.f) + sdx;
+      if (f.dbeta) f.dbeta[c] = (f.accumulate ? f.dbeta[c] : 0.f) + sd;
+      f.c1[c] = g * f.invstd[c];
+      f.c2[c] = sd * inv_n;
+      f.c3[c] = sdx * inv_n;
+      f.sum_dy[c] = 0.f;
+      f.sum_dyx[c] = 0.f;
+    }
+    if (threadIdx.x == 0) *f.counter = 0u;
+  }
+}
+
+template <typename T, bool RELU, bool RES>
+__global__ void __launch_bounds__(kThreads)
+bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ dx,
+                 T* __restrict__ dres, int64_t M, int C, const float* __restrict__ mean,
+                 const float* __restrict__ invstd, const float* __restrict__ c1, const float* __restrict__ c2,
+                 const float* __restrict__ c3) {
+  constexpr int N = V<T>::N;
+  const int CV = C / N;
+  const int64_t total = M * CV;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int col = (int)(i % CV);
+  float mu[N], is[N], a1[N], a2[N], a3[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    mu[j] = __ldg(mean + col * N + j);
+    is[j] = __ldg(invstd + col * N + j);
+    a1[j] = __ldg(c1 + col * N + j);
+    a2[j] = __ldg(c2 + col * N + j);
+    a3[j] = __ldg(c3 + col * N + j);
+  }
+  for (; i < total; i += stride) {
+    uint4 ud = ldg16_stream(dy + i * N);
+    uint4 ux = ldg16_stream(x + i * N);
+    float dv[N], xv[N], o[N];
+    unpack<T>(ud, dv);
+    unpack<T>(ux, xv);
+    if (RELU) {
+      uint4 uy = ldg16_stream(y + i * N);
+      float yv[N];
+      unpack<T>(uy, yv);
+#pragma unroll
+      for (int j = 0; j < N; ++j) dv[j] = yv[j] > 0.f ? dv[j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) o[j] = a1[j] * (dv[j] - a2[j] - (xv[j] - mu[j]) * is[j] * a3[j]);
+    stg16(dx + i * N, pack<T>(o));
+    if (RES) stg16(dres + i * N, pack<T>(dv));
+  }
+}
+
+static int grid_rows(int64_t M, int rpi) {
+  // each block should own at least ~8 iterations; cap at 4 waves
+  int64_t blocks = (M + (int64_t)rpi * 8 - 1) / ((int64_t)rpi * 8);
+  blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)kNumSMs * 4));
+  return (int)blocks;
+}
+
+static int grid_elems(int64_t total_vec, int CV) {
+  int64_t blocks = (total_vec + kThreads * 4 - 1) / (kThreads * 4);
+  blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)kNumSMs * 8));
+  (void)CV;
+  return (int)blocks;
+}
+
+template <typename T>
+static void check_shape(int C) {
+  constexpr int N = V<T>::N;
+  if (C % N != 0) throw std::runtime_error("bn: C must be a multiple of the 16B vector width");
+  const int CV = C / N;
+  if (CV > kThreads || (CV & (CV - 1)) != 0) throw std::runtime_error("bn: C/vec must be a power of two <= 256");
+}
+
+}  // namespace bn
+}  // namespace mxb
+
+using namespace mxb;
+using namespace mxb::bn;
+
+// ws: fp32 workspace of 2*C floats followed by one uint32 counter (all zero on first use; kernels leave it zeroed).
+MXB_API int MXBBnStatsFinalize(const void* x, int dt, int64_t M, int C, float* ws, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var, float* mean_out,
+                               float* invstd_out, float* scale_out, float* shift_out, float eps, float momentum,
+                               int stats_precomputed, void* stream) {
+  MXB_TRY
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  Finalize f{ws, ws + C, reinterpret_cast<unsigned int*>(ws + 2 * C), gamma, beta, running_mean, running_var,
+             mean_out, invstd_out, scale_out, shift_out, eps, momentum, M};
+  if (stats_precomputed) {
+    finalize_kernel<<<(C + 255) / 256, 256, 0, s>>>(C, f);
+  } else if (dt == kBF16) {
+    check_shape<__nv_bfloat16>(C);
+    const int rpi = kThreads / (C / 8);
+    stats_kernel<__nv_bfloat16><<<grid_rows(M, rpi), kThreads, 0, s>>>((const __nv_bfloat16*)x, M, C, f);
+  } else if (dt == kF32) {
+    check_shape<float>(C);
+    const int rpi = kThreads / (C / 4);
+    stats_kernel<float><<<grid_rows(M, rpi), kThreads, 0, s>>>((const float*)x, M, C, f);
+  } else {
+    throw std::runtime_error("bn: dtype must be bf16 or fp32");
+  }
+  CUDA_CHECK(cudaGetLastError());
+  MXB_CATCH
+}
+
+MXB_API int MXBBnApply(const void* x, const void* res, void* y, int dt, int64_t M, int C, const float* scale,
+                       const float* shift, int relu, void* stream) {
+  MXB_TRY
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  auto go = [&](auto t) {
+    using T = decltype(t);
+    check_shape<T>(C);
+    const int CV = C / V<T>::N;
+    const int g = grid_elems(M * CV, CV);
+    const T* xx = (const T*)x; const T* rr = (const T*)res; T* yy = (T*)y;
+    if (relu && res) apply_kernel<T, true, true><<<g, kThreads, 0, s>>>(xx, rr, yy, M, C, scale, shift);
+    else if (relu) apply_kernel<T, true, false><<<g, kThreads, 0, s>>>(xx, rr, yy, M, C, scale, shift);
+    else if (res) apply_kernel<T, false, true><<<g, kThreads, 0, s>>>(xx, rr, yy, M, C, scale, shift);
+    else apply_kernel<T, false, false><<<g, kThreads, 0, s>>>(xx, rr, yy, M, C, scale, shift);
+  };
+  if (dt == kBF16) go(__nv_bfloat16{});
+  else if (dt == kF32) go(float{});
+  else throw std::runtime_error("bn: dtype must be bf16 or fp32");
+  CUDA_CHECK(cudaGetLastError());
+  MXB_CATCH
+}
+
+// ws: 2*C floats + counter (zeroed).  coef: 3*C floats scratch (c1,c2,c3).
+MXB_API int MXBBnBackward(const void* dy, const void* x, const void* y, void* dx, void* dres, int dt, int64_t M, int C,
+                          const float* mean, const float* invstd, const float* gamma, float* dgamma, float* dbeta,
+                          float* ws, float* coef, int relu, int accumulate, void* stream) {
+  MXB_TRY
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  BwdFinalize f{ws, ws + C, reinterpret_cast<unsigned int*>(ws + 2 * C), gamma, invstd, dgamma, dbeta,
+                coef, coef + C, coef + 2 * C, M, accumulate};
+  auto go = [&](auto t) {
+    using T = decltype(t);
+    check_shape<T>(C);
+    const int CV = C / V<T>::N;
+    const int rpi = kThreads / CV;
+    const T* dd = (const T*)dy; const T* xx = (const T*)x; const T* yy = (const T*)y;
+    if (relu) bwd_reduce_kernel<T, true><<<grid_rows(M, rpi), kThreads, 0, s>>>(dd, xx, yy, M, C, mean, f);
+    else bwd_reduce_kernel<T, false><<<grid_rows(M, rpi), kThreads, 0, s>>>(dd, xx, yy, M, C, mean, f);
+    const int g = grid_elems(M * CV, CV);
+    T* ox = (T*)dx; T* orr = (T*)dres;
+    if (relu && dres) bwd_apply_kernel<T, true, true><<<g, kThreads, 0, s>>>(dd, xx, yy, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
+    else if (relu) bwd_apply_kernel<T, true, false><<<g, kThreads, 0, s>>>(dd, xx, yy, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
+    else if (dres) bwd_apply_kernel<T, false, true><<<g, kThreads, 0, s>>>(dd, xx, yy, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
+    else bwd_apply_kernel<T, false, false><<<g, kThreads, 0, s>>>(dd, xx, yy, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
+  };
+  if (dt == kBF16) go(__nv_bfloat16{});
+  else if (dt == kF32) go(float{});
+  else throw std::runtime_error("bn: dtype must be bf16 or fp32");
+  CUDA_CHECK(cudaGetLastError());
+  MXB_CATCH
+}

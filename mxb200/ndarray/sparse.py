@@ -1,0 +1,282 @@
+"""Sparse storage types: row_sparse and csr.
+
+Reference: python/mxnet/ndarray/sparse.py, include/mxnet/ndarray.h (aux data
+per storage type), src/operator/tensor/cast_storage-inl.cuh, dot-inl.cuh.
+A RowSparseNDArray is (data[nnz_rows, ...], indices[nnz_rows]) with sorted
+unique int64 row ids; a CSRNDArray is (data, indices, indptr).
+"""
+import numpy as np
+import torch
+
+from ..base import torch_dtype, np_dtype
+from ..context import current_context
+from .ndarray import NDArray, _ctx_of, array as _dense_array
+
+__all__ = ["BaseSparseNDArray", "RowSparseNDArray", "CSRNDArray", "row_sparse_array", "csr_matrix",
+           "zeros", "cast_storage", "dot", "retain", "add_n_rsp"]
+
+
+class BaseSparseNDArray(object):
+    stype = None
+
+    @property
+    def context(self):
+        return self._ctx
+
+    ctx = context
+
+    @property
+    def dtype(self):
+        return np_dtype(self._data.dtype)
+
+    @property
+    def size(self):
+        return int(np.prod(self._shape))
+
+    @property
+    def ndim(self):
+        return len(self._shape)
+
+    @property
+    def shape(self):
+        return tuple(self._shape)
+
+    def asnumpy(self):
+        return self.todense().asnumpy()
+
+    def wait_to_read(self):
+        if self._data.is_cuda:
+            torch.cuda.current_stream(self._data.device).synchronize()
+
+    def tostype(self, stype):
+        if stype == self.stype:
+            return self
+        return cast_storage(self.todense(), stype) if stype != "default" else self.todense()
+
+    def __repr__(self):
+        return "\n<%s %s @%s>" % (type(self).__name__, "x".join(map(str, self.shape)), self._ctx)
+
+
+class RowSparseNDArray(BaseSparseNDArray):
+    stype = "row_sparse"
+
+    def __init__(self, data, indices, shape, ctx=None):
+        self._data = data
+        self._indices = indices.to(torch.int64)
+        self._shape = tuple(int(s) for s in shape)
+        self._ctx = ctx if ctx is not None else current_context()
+
+    @property
+    def data(self):
+        return NDArray(self._data, self._ctx)
+
+    @property
+    def indices(self):
+        return NDArray(self._indices, self._ctx)
+
+    def todense(self):
+        out = torch.zeros(self._shape, dtype=self._data.dtype, device=self._data.device)
+        if self._indices.numel():
+            out.index_copy_(0, self._indices, self._data)
+        return NDArray(out, self._ctx)
+
+    def copy(self):
+        return RowSparseNDArray(self._data.clone(), self._indices.clone(), self._shape, self._ctx)
+
+    def copyto(self, other):
+        if isinstance(other, RowSparseNDArray):
+            other._data = self._data.to(other._data.device, copy=True)
+            other._indices = self._indices.to(other._data.device, copy=True)
+            other._shape = self._shape
+            return other
+        if isinstance(other, NDArray):
+            other[:] = self.todense()
+            return other
+        ctx = _ctx_of(other)
+        return RowSparseNDArray(self._data.to(ctx.torch_device, copy=True), self._indices.to(ctx.torch_device, copy=True),
+                                self._shape, ctx)
+
+    def as_in_context(self, ctx):
+        return self if ctx == self._ctx else self.copyto(ctx)
+
+    def astype(self, dtype):
+        return RowSparseNDArray(self._data.to(torch_dtype(dtype)), self._indices, self._shape, self._ctx)
+
+    def retain(self, row_ids):
+        return retain(self, row_ids)
+
+    def __setitem__(self, key, value):
+        assert isinstance(key, slice) and key == slice(None)
+        if isinstance(value, RowSparseNDArray):
+            value.copyto(self)
+        else:
+            src = cast_storage(value if isinstance(value, NDArray) else _dense_array(value, ctx=self._ctx), "row_sparse")
+            src.copyto(self)
+
+    def _binary(self, other, fn):
+        if isinstance(other, RowSparseNDArray):
+            return cast_storage(NDArray(fn(self.todense()._t, other.todense()._t), self._ctx), "row_sparse")
+        if isinstance(other, NDArray):
+            return NDArray(fn(self.todense()._t, other._t), self._ctx)
+        return RowSparseNDArray(fn(self._data, other), self._indices, self._shape, self._ctx)
+
+    def __add__(self, o):
+        return self._binary(o, torch.add)
+
+    def __sub__(self, o):
+        return self._binary(o, torch.sub)
+
+    def __mul__(self, o):
+        return self._binary(o, torch.mul)
+
+    def __truediv__(self, o):
+        return self._binary(o, torch.div)
+
+
+class CSRNDArray(BaseSparseNDArray):
+    stype = "csr"
+
+    def __init__(self, data, indices, indptr, shape, ctx=None):
+        self._data = data
+        self._indices = indices.to(torch.int64)
+        self._indptr = indptr.to(torch.int64)
+        self._shape = tuple(int(s) for s in shape)
+        self._ctx = ctx if ctx is not None else current_context()
+
+    @property
+    def data(self):
+        return NDArray(self._data, self._ctx)
+
+    @property
+    def indices(self):
+        return NDArray(self._indices, self._ctx)
+
+    @property
+    def indptr(self):
+        return NDArray(self._indptr, self._ctx)
+
+    def _torch_csr(self):
+        return torch.sparse_csr_tensor(self._indptr, self._indices, self._data, size=self._shape)
+
+    def todense(self):
+        return NDArray(self._torch_csr().to_dense(), self._ctx)
+
+    def copy(self):
+        return CSRNDArray(self._data.clone(), self._indices.clone(), self._indptr.clone(), self._shape, self._ctx)
+
+    def copyto(self, other):
+        if isinstance(other, CSRNDArray):
+            other._data, other._indices, other._indptr, other._shape = self._data.clone(), self._indices.clone(), self._indptr.clone(), self._shape
+            return other
+        ctx = _ctx_of(other)
+        d = ctx.torch_device
+        return CSRNDArray(self._data.to(d, copy=True), self._indices.to(d, copy=True), self._indptr.to(d, copy=True), self._shape, ctx)
+
+    def as_in_context(self, ctx):
+        return self if ctx == self._ctx else self.copyto(ctx)
+
+    def __getitem__(self, key):
+        if isinstance(key, int):
+            key = slice(key, key + 1)
+        assert isinstance(key, slice) and key.step in (None, 1)
+        b, e, _ = key.indices(self._shape[0])
+        lo, hi = int(self._indptr[b]), int(self._indptr[e])
+        return CSRNDArray(self._data[lo:hi], self._indices[lo:hi], self._indptr[b:e + 1] - lo, (e - b, self._shape[1]), self._ctx)
+
+
+def row_sparse_array(arg1, shape=None, ctx=None, dtype=None):
+    ctx = _ctx_of(ctx)
+    if isinstance(arg1, tuple) and len(arg1) == 2:
+        data, idx = arg1
+        data = _dense_array(data, ctx=ctx, dtype=dtype)._t
+        idx = _dense_array(idx, ctx=ctx, dtype="int64")._t
+        if shape is None:
+            shape = (int(idx.max()) + 1 if idx.numel() else 0,) + tuple(data.shape[1:])
+        return RowSparseNDArray(data, idx, shape, ctx)
+    if isinstance(arg1, RowSparseNDArray):
+        return arg1.copyto(ctx)
+    return cast_storage(_dense_array(arg1, ctx=ctx, dtype=dtype), "row_sparse")
+
+
+def csr_matrix(arg1, shape=None, ctx=None, dtype=None):
+    ctx = _ctx_of(ctx)
+    if isinstance(arg1, tuple) and len(arg1) == 3:
+        data, indices, indptr = arg1
+        data = _dense_array(data, ctx=ctx, dtype=dtype)._t
+        indices = _dense_array(indices, ctx=ctx, dtype="int64")._t
+        indptr = _dense_array(indptr, ctx=ctx, dtype="int64")._t
+        if shape is None:
+            shape = (indptr.numel() - 1, int(indices.max()) + 1 if indices.numel() else 0)
+        return CSRNDArray(data, indices, indptr, shape, ctx)
+    return cast_storage(_dense_array(arg1, ctx=ctx, dtype=dtype), "csr")
+
+
+def zeros(stype, shape, ctx=None, dtype=None):
+    ctx = _ctx_of(ctx)
+    d = ctx.torch_device
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    td = torch_dtype(dtype)
+    if stype == "row_sparse":
+        return RowSparseNDArray(torch.zeros((0,) + shape[1:], dtype=td, device=d), torch.zeros(0, dtype=torch.int64, device=d), shape, ctx)
+    if stype == "csr":
+        return CSRNDArray(torch.zeros(0, dtype=td, device=d), torch.zeros(0, dtype=torch.int64, device=d),
+                          torch.zeros(shape[0] + 1, dtype=torch.int64, device=d), shape, ctx)
+    from .ndarray import zeros as dz
+    return dz(shape, ctx, dtype)
+
+
+def cast_storage(arr, stype):
+    """src/operator/tensor/cast_storage-inl.cuh."""
+    if isinstance(arr, BaseSparseNDArray):
+        return arr.tostype(stype)
+    t = arr._t
+    if stype == "default":
+        return arr
+    if stype == "row_sparse":
+        nz = (t.reshape(t.shape[0], -1) != 0).any(dim=1)
+        idx = torch.nonzero(nz).reshape(-1)
+        return RowSparseNDArray(t[idx].clone(), idx, t.shape, arr._ctx)
+    if stype == "csr":
+        c = t.to_sparse_csr()
+        return CSRNDArray(c.values(), c.col_indices(), c.crow_indices(), t.shape, arr._ctx)
+    raise ValueError("unknown stype " + str(stype))
+
+
+def retain(rsp, row_ids):
+    """sparse_retain: keep only the requested rows (src/operator/tensor/sparse_retain.cu)."""
+    ids = row_ids._t.long() if isinstance(row_ids, NDArray) else torch.as_tensor(row_ids, dtype=torch.int64, device=rsp._data.device)
+    ids = torch.unique(ids)
+    mask = torch.isin(rsp._indices, ids)
+    return RowSparseNDArray(rsp._data[mask], rsp._indices[mask], rsp._shape, rsp._ctx)
+
+
+def add_n_rsp(arrs):
+    """Sum of row_sparse arrays -> row_sparse (ElementWiseRspAdditionKernel, ndarray_function-inl.cuh)."""
+    shape, ctx = arrs[0]._shape, arrs[0]._ctx
+    idx = torch.cat([a._indices for a in arrs])
+    dat = torch.cat([a._data for a in arrs])
+    if idx.numel() == 0:
+        return arrs[0].copy()
+    uniq, inv = torch.unique(idx, return_inverse=True)
+    out = torch.zeros((uniq.numel(),) + tuple(dat.shape[1:]), dtype=dat.dtype, device=dat.device)
+    out.index_add_(0, inv, dat)
+    return RowSparseNDArray(out, uniq, shape, ctx)
+
+
+def dot(lhs, rhs, transpose_a=False, transpose_b=False):
+    """Sparse dot: csr x dense, csr^T x dense -> dense (dot-inl.cuh)."""
+    if isinstance(lhs, CSRNDArray):
+        a = lhs._torch_csr()
+        b = rhs._t if isinstance(rhs, NDArray) else rhs.todense()._t
+        if transpose_b:
+            b = b.t()
+        if transpose_a:
+            return NDArray(torch.matmul(a.to_dense().t(), b), lhs._ctx)
+        return NDArray(torch.matmul(a, b), lhs._ctx)
+    a = lhs._t if isinstance(lhs, NDArray) else lhs.todense()._t
+    b = rhs.todense()._t if isinstance(rhs, BaseSparseNDArray) else rhs._t
+    if transpose_a:
+        a = a.t()
+    if transpose_b:
+        b = b.t()
+    return NDArray(torch.matmul(a, b), lhs._ctx if isinstance(lhs, NDArray) else rhs._ctx)

@@ -1,0 +1,367 @@
+"""Torch-level functional ops backed by the hand-written sm_100a kernels.
+
+Every function takes/returns ``torch.Tensor`` and is differentiable through a
+``torch.autograd.Function`` whose forward AND backward call our kernels:
+
+  linear / conv1x1_nhwc -> csrc/cuda/gemm_tcgen05.cu  (TMA + tcgen05.mma + TMEM)
+  bn_act                -> csrc/cuda/bn_act.cu        (BatchNorm + residual + ReLU, NHWC)
+  softmax_cross_entropy -> csrc/cuda/softmax_ce.cu    (loss + gradient in one launch)
+
+CPU tensors (and shapes the kernels do not cover) take an equivalent eager
+torch path so the whole framework runs on a GPU-less host; on a CUDA device
+a missing native library is an error, never a silent fallback.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from .. import _native as N
+from ..base import getenv
+from ._dtypes import code
+
+c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+
+LAUNCHES = [0]
+
+
+def _p(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def _use_native(*ts):
+    return all(t is None or t.is_cuda for t in ts) and N.have_cuda_kernels()
+
+
+# --------------------------------------------------------------------------- GEMM
+GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+
+
+def gemm_raw(mode, A, B, D, M, Nn, K, lda, ldb, ldd, bias=None, relu=False, col_sum=None, col_sumsq=None, splits=1,
+             block_n=0, max_ctas=0, dbg=None):
+    lib = N.cuda()
+    dbg_arr = (c_int * 4)(*dbg) if dbg is not None else None
+    rc = lib.MXBGemmBf16(c_int(mode), _p(A), _p(B), _p(D), c_int(M), c_int(Nn), c_int(K), c_int64(lda), c_int64(ldb),
+                         c_int64(ldd), _p(bias), c_int(1 if relu else 0), _p(col_sum), _p(col_sumsq), c_int(splits),
+                         c_int(block_n), c_int(max_ctas), dbg_arr, N.stream_of(A))
+    N.check(lib, rc)
+    LAUNCHES[0] += 1
+
+
+def gemm_nt(x, w, bias=None, relu=False, col_stats=None, block_n=0):
+    """y[M,N] = x[M,K] @ w[N,K]^T (+bias)(relu); bf16 in/out, fp32 accumulate in TMEM."""
+    M, K = x.shape
+    Nn = w.shape[0]
+    y = torch.empty((M, Nn), dtype=torch.bfloat16, device=x.device)
+    cs, cs2 = col_stats if col_stats is not None else (None, None)
+    gemm_raw(GEMM_NT, x, w, y, M, Nn, K, x.stride(0), w.stride(0), Nn, bias, relu, cs, cs2, block_n=block_n)
+    return y
+
+
+def gemm_nn(dy, w, block_n=0):
+    """dx[M,K] = dy[M,N] @ w[N,K]."""
+    M, Nn = dy.shape
+    K = w.shape[1]
+    dx = torch.empty((M, K), dtype=torch.bfloat16, device=dy.device)
+    gemm_raw(GEMM_NN, dy, w, dx, M, K, Nn, dy.stride(0), w.stride(0), K, block_n=block_n)
+    return dx
+
+
+def _pick_splits(M_out, N_out, K_red, block_n):
+    tiles = ((M_out + 127) // 128) * ((N_out + block_n - 1) // block_n)
+    kb = (K_red + 63) // 64
+    want = max(1, (148 * 2) // max(1, tiles))
+    return max(1, min(want, kb // 4 if kb >= 8 else 1))
+
+
+def gemm_tn(dy, x, out_dtype=torch.bfloat16, block_n=0):
+    """dw[N,K] = dy[M,N]^T @ x[M,K]; reduction over the (huge) M dim is split across CTAs and combined with
+    fp32 TMA reduce-add."""
+    M, Nn = dy.shape
+    K = x.shape[1]
+    bn = block_n or (64 if K <= 64 else 128)
+    acc = torch.zeros((Nn, K), dtype=torch.float32, device=dy.device)
+    gemm_raw(GEMM_TN, dy, x, acc, Nn, K, M, dy.stride(0), x.stride(0), K, splits=_pick_splits(Nn, K, M, bn),
+             block_n=bn)
+    return acc if out_dtype is torch.float32 else acc.to(out_dtype)
+
+
+def _gemm_ok(x, w):
+    if not (x.is_cuda and x.dtype is torch.bfloat16 and w.dtype is torch.bfloat16):
+        return False
+    if getenv("MXB200_GEMM", "tcgen05") != "tcgen05":
+        return False
+    K, Nn = x.shape[-1], w.shape[0]
+    return K % 8 == 0 and Nn % 8 == 0 and x.stride(-1) == 1 and w.stride(-1) == 1 and N.have_cuda_kernels()
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, relu):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        bias32 = b.float() if b is not None else None
+        y = gemm_nt(x2, w, bias32, relu)
+        ctx.save_for_backward(x2, w, y if relu else None)
+        ctx.has_bias = b is not None
+        ctx.relu = relu
+        ctx.xshape = x.shape
+        ctx.bdtype = b.dtype if b is not None else None
+        return y.reshape(x.shape[:-1] + (w.shape[0],))
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w, y = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if ctx.relu:
+            g2 = g2 * (y > 0)
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm_nn(g2, w).reshape(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            gw = gemm_tn(g2, x2, out_dtype=w.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.float().sum(0).to(ctx.bdtype)
+        return gx, gw, gb, None
+
+
+def linear(x, w, b=None, relu=False):
+    """FullyConnected: Y = X.W^T + b (reference: src/operator/nn/fully_connected-inl.h:72-180)."""
+    if _gemm_ok(x, w):
+        return _LinearFn.apply(x, w, b, relu)
+    if x.is_cuda and not N.have_cuda_kernels():
+        raise RuntimeError("mxb200: CUDA kernels library missing on a GPU host")
+    y = F.linear(x, w, b)
+    return torch.relu(y) if relu else y
+
+
+def conv1x1_nhwc(x, w, stride=1):
+    """1x1 convolution on a channels-last (N,H,W,C) *view* == GEMM over pixels.  w: (Cout, Cin)."""
+    if stride != 1:
+        x = x[:, ::stride, ::stride, :].contiguous()
+    n, h, ww, c = x.shape
+    y = linear(x.reshape(n * h * ww, c), w)
+    return y.reshape(n, h, ww, w.shape[0])
+
+
+# --------------------------------------------------------------------------- BatchNorm(+add)(+ReLU)
+class _BnWorkspace(object):
+    """Per-device zero-initialised scratch reused by all BN calls on one stream (kernels leave it zeroed)."""
+    _ws = {}
+
+    @classmethod
+    def get(cls, device, C):
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        ws = cls._ws.get(key)
+        if ws is None or ws.numel() < 2 * C + 8:
+            ws = torch.zeros(max(2 * C + 8, 2 * 4096 + 8), dtype=torch.float32, device=device)
+            cls._ws[key] = ws
+        return ws
+
+
+def _bn_shape_ok(x2):
+    C = x2.shape[1]
+    vec = 16 // x2.element_size()
+    cv = C // vec if C % vec == 0 else 0
+    return cv > 0 and cv <= 256 and (cv & (cv - 1)) == 0 and x2.dtype in (torch.bfloat16, torch.float32)
+
+
+class _BnActFn(torch.autograd.Function):
+    """x: [M, C] contiguous (channels-last pixels).  Returns y = act(bn(x) + residual)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, relu, eps, momentum, training, fix_gamma,
+                pre_stats):
+        lib = N.cuda()
+        M, C = x.shape
+        dev = x.device
+        stats = torch.empty((4, C), dtype=torch.float32, device=dev)   # mean, invstd, scale, shift
+        g32 = None if fix_gamma else gamma.float()
+        b32 = beta.float()
+        st = N.stream_of(x)
+        if training:
+            if pre_stats is not None:
+                ws = pre_stats            # [2C+8] sums produced by the GEMM epilogue
+            else:
+                ws = _BnWorkspace.get(dev, C)
+            N.check(lib, lib.MXBBnStatsFinalize(_p(x), c_int(code(x.dtype)), c_int64(M), c_int(C), _p(ws), _p(g32),
+                                                _p(b32), _p(running_mean), _p(running_var), _p(stats[0]), _p(stats[1]),
+                                                _p(stats[2]), _p(stats[3]), c_float(eps), c_float(momentum),
+                                                c_int(1 if pre_stats is not None else 0), st))
+            LAUNCHES[0] += 1
+        else:
+            invstd = torch.rsqrt(running_var.float() + eps)
+            gg = g32 if g32 is not None else torch.ones_like(invstd)
+            stats[0] = running_mean.float()
+            stats[1] = invstd
+            stats[2] = gg * invstd
+            stats[3] = b32 - running_mean.float() * gg * invstd
+        y = torch.empty_like(x)
+        N.check(lib, lib.MXBBnApply(_p(x), _p(residual), _p(y), c_int(code(x.dtype)), c_int64(M), c_int(C),
+                                    _p(stats[2]), _p(stats[3]), c_int(1 if relu else 0), st))
+        LAUNCHES[0] += 1
+        ctx.save_for_backward(x, y if relu else None, stats, g32)
+        ctx.cfg = (relu, residual is not None, fix_gamma, gamma.dtype, beta.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = N.cuda()
+        x, y, stats, g32 = ctx.saved_tensors
+        relu, has_res, fix_gamma, gdt, bdt = ctx.cfg
+        M, C = x.shape
+        if not dy.is_contiguous():
+            dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if has_res else None
+        dgb = torch.empty((2, C), dtype=torch.float32, device=x.device)
+        coef = torch.empty((3, C), dtype=torch.float32, device=x.device)
+        ws = _BnWorkspace.get(x.device, C)
+        N.check(lib, lib.MXBBnBackward(_p(dy), _p(x), _p(y), _p(dx), _p(dres), c_int(code(x.dtype)), c_int64(M), c_int(C),
+                                       _p(stats[0]), _p(stats[1]), _p(g32), _p(dgb[0]), _p(dgb[1]), _p(ws), _p(coef),
+                                       c_int(1 if relu else 0), c_int(0), N.stream_of(x)))
+        LAUNCHES[0] += 2
+        dgamma = torch.zeros_like(dgb[0]).to(gdt) if fix_gamma else dgb[0].to(gdt)
+        return dx, dgamma, dgb[1].to(bdt), None, None, dres, None, None, None, None, None, None
+
+
+def bn_act(x, gamma, beta, running_mean, running_var, residual=None, relu=False, eps=1e-5, momentum=0.9,
+           training=True, fix_gamma=False, pre_stats=None):
+    """BatchNorm over the last (channel) dim of a channels-last tensor, + optional residual add + ReLU.
+
+    momentum follows the reference convention: running = running*momentum + batch*(1-momentum)
+    (src/operator/nn/batch_norm.cu:359-362).  running stats are fp32 tensors updated in place.
+    """
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    if _use_native(x2) and _bn_shape_ok(x2) and x2.is_contiguous():
+        r2 = residual.reshape(-1, C) if residual is not None else None
+        if r2 is not None and not r2.is_contiguous():
+            r2 = r2.contiguous()
+        y = _BnActFn.apply(x2, gamma, beta, running_mean, running_var, r2, relu, eps, momentum, training, fix_gamma,
+                           pre_stats)
+        return y.reshape(x.shape)
+    if x.is_cuda and not N.have_cuda_kernels():
+        raise RuntimeError("mxb200: CUDA kernels library missing on a GPU host")
+    # eager reference path (CPU / unsupported widths)
+    g = torch.ones_like(gamma) if fix_gamma else gamma
+    xf = x2.float()
+    if training:
+        mean = xf.mean(0)
+        var = xf.var(0, unbiased=False)
+        with torch.no_grad():
+            running_mean.mul_(momentum).add_(mean.detach() * (1 - momentum))
+            running_var.mul_(momentum).add_(var.detach() * (1 - momentum))
+    else:
+        mean, var = running_mean.float(), running_var.float()
+    y = (xf - mean) * torch.rsqrt(var + eps) * g.float() + beta.float()
+    if residual is not None:
+        y = y + residual.reshape(-1, C).float()
+    if relu:
+        y = torch.relu(y)
+    return y.to(x.dtype).reshape(x.shape)
+
+
+# --------------------------------------------------------------------------- softmax / CE
+def softmax_rows(x, log=False, temperature=1.0):
+    if _use_native(x) and x.dim() == 2 and x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16, torch.float16):
+        lib = N.cuda()
+        y = torch.empty_like(x)
+        N.check(lib, lib.MXBSoftmaxRows(_p(x), _p(y), c_int(code(x.dtype)), c_int64(x.shape[0]), c_int(x.shape[1]),
+                                        c_int(1 if log else 0), c_float(temperature), N.stream_of(x)))
+        LAUNCHES[0] += 1
+        return y
+    z = x / temperature if temperature != 1.0 else x
+    return torch.log_softmax(z, dim=-1) if log else torch.softmax(z, dim=-1)
+
+
+def _label_code(label):
+    if label.dtype is torch.int64:
+        return 6
+    if label.dtype is torch.float32:
+        return 0
+    raise TypeError("labels must be int64 or float32")
+
+
+class _SoftmaxCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, label, smooth_alpha, use_ignore, ignore_label, sample_weight):
+        lib = N.cuda()
+        rows, cols = x.shape
+        loss = torch.empty(rows, dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        N.check(lib, lib.MXBSoftmaxCE(_p(x), c_int(code(x.dtype)), _p(label), c_int(_label_code(label)), _p(loss), _p(dx),
+                                      c_int64(rows), c_int(cols), c_float(1.0), c_int(1 if use_ignore else 0),
+                                      c_float(ignore_label), c_float(smooth_alpha), _p(sample_weight), N.stream_of(x)))
+        LAUNCHES[0] += 1
+        ctx.save_for_backward(dx)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gl):
+        dx, = ctx.saved_tensors
+        return (dx * gl.unsqueeze(1).to(dx.dtype)), None, None, None, None, None
+
+
+def softmax_cross_entropy(x, label, smooth_alpha=0.0, use_ignore=False, ignore_label=-1.0, sample_weight=None):
+    """Per-row -log softmax(x)[label] (fp32).  One kernel produces the loss and the logits gradient."""
+    if _use_native(x) and x.dim() == 2 and x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16, torch.float16):
+        if label.dtype not in (torch.int64, torch.float32):
+            label = label.long()
+        return _SoftmaxCEFn.apply(x, label.contiguous(), float(smooth_alpha), use_ignore, float(ignore_label),
+                                  sample_weight)
+    if x.is_cuda and not N.have_cuda_kernels():
+        raise RuntimeError("mxb200: CUDA kernels library missing on a GPU host")
+    lp = torch.log_softmax(x.float(), dim=-1)
+    li = label.long()
+    nll = -lp.gather(1, li.clamp(0, x.shape[1] - 1).unsqueeze(1)).squeeze(1)
+    if smooth_alpha > 0:
+        K = x.shape[1]
+        other = -(lp.sum(1) - lp.gather(1, li.clamp(0, K - 1).unsqueeze(1)).squeeze(1))
+        nll = (1 - smooth_alpha) * nll + smooth_alpha / (K - 1) * other
+    if use_ignore:
+        nll = torch.where(label.float() == ignore_label, torch.zeros_like(nll), nll)
+    if sample_weight is not None:
+        nll = nll * sample_weight
+    return nll
+
+
+def softmax_output_grad(p, label, grad_scale=1.0, ignore_label=-1.0, use_ignore=False, normalization="null",
+                        smooth_alpha=0.0):
+    """SoftmaxOutput backward: (p - onehot)*grad_scale/norm (src/operator/softmax_output-inl.h:160-240)."""
+    rows, cols = p.shape
+    scale = float(grad_scale)
+    valid = None
+    if normalization == "batch":
+        scale /= rows
+    elif normalization == "valid":
+        valid = (label.float() != ignore_label).sum().clamp(min=1) if use_ignore else None
+        if valid is None:
+            scale /= rows
+    if _use_native(p) and p.is_contiguous() and p.dtype in (torch.float32, torch.bfloat16, torch.float16):
+        lib = N.cuda()
+        lab = label if label.dtype in (torch.int64, torch.float32) else label.float()
+        g = torch.empty_like(p)
+        N.check(lib, lib.MXBSoftmaxOutputGrad(_p(p), c_int(code(p.dtype)), _p(lab.contiguous()), c_int(_label_code(lab)),
+                                              _p(g), c_int64(rows), c_int(cols), c_float(scale),
+                                              c_int(1 if use_ignore else 0), c_float(ignore_label),
+                                              c_float(smooth_alpha), N.stream_of(p)))
+        LAUNCHES[0] += 1
+    else:
+        li = label.long().clamp(0, cols - 1)
+        tgt = torch.full_like(p, smooth_alpha / (cols - 1) if smooth_alpha > 0 else 0.0)
+        tgt.scatter_(1, li.unsqueeze(1), 1.0 - smooth_alpha)
+        g = (p - tgt) * scale
+        if use_ignore:
+            g = g * (label.float() != ignore_label).unsqueeze(1).to(g.dtype)
+    if valid is not None:
+        g = g / valid.to(g.dtype)
+    return g
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):
+    from . import layernorm
+    return layernorm.layer_norm(x, gamma, beta, eps)

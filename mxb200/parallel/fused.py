@@ -1,0 +1,140 @@
+"""Launcher for the fused allreduce + optimizer kernel (csrc/cuda/allreduce.cu).
+
+``SymmetricArena`` owns one dtype-group of parameters on one rank: symmetric (peer-mapped) weight and
+gradient buffers, local fp32 master / optimizer state, chunk table.  ``fused_step`` is the whole
+``kv.push(grads) -> optimizer -> kv.pull(weights)`` sequence of the reference
+(python/mxnet/model.py:183-205 -> kvstore_local.h:189-242) as one kernel launch per rank.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from ..ops._dtypes import code
+from .arena import ArenaLayout, CHUNK
+from .peer import MAX_RANKS
+
+c_void_p, c_int, c_int64, c_float, c_uint32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_uint32
+
+LAUNCHES = [0]
+
+MODE_ALLREDUCE, MODE_SGD, MODE_ADAM, MODE_LAMB1, MODE_LAMB2, MODE_BCAST = 0, 1, 2, 3, 4, 5
+
+# one-shot below this many bytes of gradient per rank (latency-bound), two-shot above
+ONE_SHOT_BYTES = 512 * 1024
+
+
+class _Args(ctypes.Structure):
+    _fields_ = [("grads", c_void_p * MAX_RANKS), ("weights", c_void_p * MAX_RANKS), ("flags", c_void_p * MAX_RANKS),
+                ("w32", c_void_p), ("mom", c_void_p), ("var", c_void_p), ("rbuf", c_void_p), ("w_norm2", c_void_p),
+                ("r_norm2", c_void_p), ("chunk_tid", c_void_p), ("lr_mult", c_void_p), ("wd_mult", c_void_p),
+                ("err", c_void_p), ("n", c_int64), ("rank", c_int), ("nranks", c_int), ("mode", c_int),
+                ("one_shot", c_int), ("g_dt", c_int), ("w_dt", c_int), ("seq", c_uint32), ("zero_grad", c_int),
+                ("lr", c_float), ("wd", c_float), ("momentum", c_float), ("rescale", c_float), ("clip", c_float),
+                ("nesterov", c_int), ("has_mom", c_int), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
+                ("bc1", c_float), ("bc2", c_float), ("lamb_lower", c_float), ("lamb_upper", c_float)]
+
+
+def _check_abi(lib):
+    n = lib.MXBFusedAllreduceArgsSize()
+    if n != ctypes.sizeof(_Args):
+        raise RuntimeError("fused allreduce ABI mismatch: native %d bytes vs python %d" % (n, ctypes.sizeof(_Args)))
+
+
+class SymmetricArena(object):
+    """One dtype group on one rank.  ``group`` is a PeerGroup/_LocalGroup; buffers come from ``bufs``:
+    dict with 'weights' and 'grads' -> (local _RawBuffer, [ptr per rank])."""
+
+    def __init__(self, group, names, tensors, bufs, wdtype, gdtype):
+        self.group = group
+        self.device = group.device
+        self.layout = ArenaLayout(names, [t.shape for t in tensors], align_chunks_to=MAX_RANKS)
+        n = self.layout.total
+        self.n = n
+        self.wdtype, self.gdtype = wdtype, gdtype
+        (wl, self.w_ptrs), (gl, self.g_ptrs) = bufs["weights"], bufs["grads"]
+        self.weights = wl.tensor(wdtype, n)
+        self.grads = gl.tensor(gdtype, n)
+        self.chunk_tid = torch.from_numpy(self.layout.chunk_tid).to(self.device)
+        self.lr_mult = torch.ones(len(names), dtype=torch.float32, device=self.device)
+        self.wd_mult = torch.ones(len(names), dtype=torch.float32, device=self.device)
+        self.state = {}
+        self.views, self.grad_views = [], []
+        with torch.no_grad():
+            for i, t in enumerate(tensors):
+                krsc = t.dim() == 4 and not t.is_contiguous() and t.permute(0, 2, 3, 1).is_contiguous()
+                v = self.layout.view(self.weights, i, krsc)
+                v.copy_(t)
+                self.views.append(v)
+                self.grad_views.append(self.layout.view(self.grads, i, krsc))
+
+    @staticmethod
+    def bytes_needed(tensors, dtype):
+        lay = ArenaLayout([str(i) for i in range(len(tensors))], [t.shape for t in tensors], align_chunks_to=MAX_RANKS)
+        return lay.total * torch.empty((), dtype=dtype).element_size()
+
+    def get_state(self, name, init_from_weights=False):
+        st = self.state.get(name)
+        if st is None:
+            st = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+            if init_from_weights:
+                st.copy_(self.weights)
+            self.state[name] = st
+        return st
+
+    def bind(self, params):
+        for p, v, g in zip(params, self.views, self.grad_views):
+            p.data = v
+            p.grad = g
+
+
+def fused_step(arena, mode, lr=0.0, wd=0.0, momentum=0.0, rescale=1.0, clip=None, nesterov=False, multi_precision=True,
+               zero_grad=True, beta1=0.9, beta2=0.999, eps=1e-8, bc1=1.0, bc2=1.0, lamb_lower=-1.0, lamb_upper=-1.0,
+               one_shot=None, blocks=0, seq=None):
+    """Launch the fused kernel for one arena on this rank's current stream."""
+    g = arena.group
+    lib = g.lib
+    _check_abi(lib)
+    a = _Args()
+    for r in range(g.world):
+        a.grads[r] = arena.g_ptrs[r]
+        a.weights[r] = arena.w_ptrs[r]
+        a.flags[r] = g.flag_ptrs[r]
+    a.n = arena.n
+    a.rank, a.nranks, a.mode = g.rank, g.world, mode
+    gbytes = arena.n * arena.grads.element_size()
+    a.one_shot = int(one_shot if one_shot is not None else gbytes <= ONE_SHOT_BYTES)
+    a.g_dt, a.w_dt = code(arena.gdtype), code(arena.wdtype)
+    a.seq = seq if seq is not None else g.next_seq()
+    a.zero_grad = int(zero_grad)
+    a.lr, a.wd, a.momentum, a.rescale = lr, wd, momentum, rescale
+    a.clip = -1.0 if clip is None else clip
+    a.nesterov = int(nesterov)
+    a.has_mom = int(momentum != 0.0)
+    a.beta1, a.beta2, a.eps, a.bc1, a.bc2 = beta1, beta2, eps, bc1, bc2
+    a.lamb_lower, a.lamb_upper = lamb_lower, lamb_upper
+    a.chunk_tid = arena.chunk_tid.data_ptr()
+    a.lr_mult = arena.lr_mult.data_ptr()
+    a.wd_mult = arena.wd_mult.data_ptr()
+    a.err = g.err_dev.value
+    need_master = multi_precision and arena.wdtype is not torch.float32
+    if mode in (MODE_SGD, MODE_ADAM, MODE_LAMB1, MODE_LAMB2, MODE_BCAST) and need_master:
+        a.w32 = arena.get_state("w32", init_from_weights=True).data_ptr()
+    if mode == MODE_SGD and momentum != 0.0:
+        a.mom = arena.get_state("mom").data_ptr()
+    if mode in (MODE_ADAM, MODE_LAMB1):
+        a.mom = arena.get_state("mom").data_ptr()
+        a.var = arena.get_state("var").data_ptr()
+    if mode in (MODE_LAMB1, MODE_LAMB2):
+        a.rbuf = arena.get_state("rbuf").data_ptr()
+        nt = len(arena.layout.names)
+        if "norms" not in arena.state:
+            arena.state["norms"] = torch.zeros(2 * ((nt + 1023) // 1024 * 1024), dtype=torch.float32, device=arena.device)
+        norms = arena.state["norms"]
+        a.w_norm2 = norms.data_ptr()
+        a.r_norm2 = norms.data_ptr() + norms.numel() // 2 * 4
+    with torch.cuda.device(arena.device):
+        rc = lib.MXBFusedAllreduce(ctypes.byref(a), c_int(ctypes.sizeof(a)), c_int(blocks), N.stream_of(device=arena.device))
+    N.check(lib, rc)
+    LAUNCHES[0] += 1

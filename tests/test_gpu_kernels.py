@@ -1,0 +1,333 @@
+"""Numerics of every hand-written sm_100a kernel against a plain PyTorch fp32 reference of the same op
+(the reference's check_consistency idea, python/mxnet/test_utils.py:1207)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-6)).item()
+
+
+# ----------------------------------------------------------------------------- tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 256), (1000, 1000, 2048), (4096, 256, 64),
+                                    (12544, 512, 2048), (333, 72, 136)])
+def test_gemm_nt(M, N, K):
+    from mxb200.ops import functional as K_
+    x = torch.randn(M, K, device=_dev()).bfloat16()
+    w = torch.randn(N, K, device=_dev()).bfloat16()
+    y = K_.gemm_nt(x, w)
+    ref = x.float() @ w.float().t()
+    assert y.shape == (M, N)
+    assert _rel_err(y, ref) < 2e-2
+
+
+def test_gemm_nt_bias_relu_bn64():
+    from mxb200.ops import functional as K_
+    M, N, K = 512, 192, 320
+    x = torch.randn(M, K, device=_dev()).bfloat16()
+    w = torch.randn(N, K, device=_dev()).bfloat16()
+    b = torch.randn(N, device=_dev())
+    for bn in (64, 128):
+        y = K_.gemm_nt(x, w, bias=b, relu=True, block_n=bn)
+        ref = torch.relu(x.float() @ w.float().t() + b)
+        assert _rel_err(y, ref) < 2e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (3136, 256, 64), (1000, 2048, 1000), (777, 264, 520)])
+def test_gemm_nn(M, N, K):
+    # dx[M,K] = dy[M,N] @ w[N,K]
+    from mxb200.ops import functional as K_
+    dy = torch.randn(M, N, device=_dev()).bfloat16()
+    w = torch.randn(N, K, device=_dev()).bfloat16()
+    dx = K_.gemm_nn(dy, w)
+    ref = dy.float() @ w.float()
+    assert dx.shape == (M, K)
+    assert _rel_err(dx, ref) < 2e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (6272, 64, 256), (50176, 256, 64), (1000, 1000, 2048), (515, 72, 136)])
+def test_gemm_tn(M, N, K):
+    # dw[N,K] = dy[M,N]^T @ x[M,K]
+    from mxb200.ops import functional as K_
+    dy = (torch.randn(M, N, device=_dev()) * 0.1).bfloat16()
+    x = torch.randn(M, K, device=_dev()).bfloat16()
+    dw = K_.gemm_tn(dy, x, out_dtype=torch.float32)
+    ref = dy.float().t() @ x.float()
+    assert dw.shape == (N, K)
+    assert _rel_err(dw, ref) < 2e-2
+
+
+def test_gemm_col_stats():
+    from mxb200.ops import functional as K_
+    M, N, K = 1024, 256, 128
+    x = torch.randn(M, K, device=_dev()).bfloat16()
+    w = (torch.randn(N, K, device=_dev()) * 0.1).bfloat16()
+    s = torch.zeros(N, device=_dev())
+    s2 = torch.zeros(N, device=_dev())
+    y = K_.gemm_nt(x, w, col_stats=(s, s2))
+    assert _rel_err(s, y.float().sum(0)) < 1e-3
+    assert _rel_err(s2, (y.float() ** 2).sum(0)) < 1e-3
+
+
+def test_linear_autograd_matches_torch():
+    from mxb200.ops import functional as K_
+    x = torch.randn(64, 7, 256, device=_dev()).bfloat16().requires_grad_(True)
+    w = (torch.randn(512, 256, device=_dev()) * 0.05).bfloat16().requires_grad_(True)
+    b = torch.randn(512, device=_dev()).requires_grad_(True)
+    y = K_.linear(x, w, b)
+    g = torch.randn_like(y)
+    y.backward(g)
+    x2, w2, b2 = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    y2 = torch.nn.functional.linear(x2, w2, b2)
+    y2.backward(g.float())
+    assert _rel_err(y, y2) < 2e-2
+    assert _rel_err(x.grad, x2.grad) < 2e-2
+    assert _rel_err(w.grad, w2.grad) < 2e-2
+    assert _rel_err(b.grad, b2.grad) < 2e-2
+
+
+# ----------------------------------------------------------------------------- BatchNorm + add + ReLU
+@pytest.mark.parametrize("C", [64, 256, 2048])
+@pytest.mark.parametrize("relu,res", [(False, False), (True, False), (True, True)])
+def test_bn_act_fwd_bwd(C, relu, res):
+    from mxb200.ops import functional as K_
+    M = 4 * 14 * 14
+    dev = _dev()
+    x = (torch.randn(M, C, device=dev) * 2 + 0.5).bfloat16().requires_grad_(True)
+    r = torch.randn(M, C, device=dev).bfloat16().requires_grad_(True) if res else None
+    gamma = (torch.rand(C, device=dev) + 0.5).requires_grad_(True)
+    beta = torch.randn(C, device=dev).requires_grad_(True)
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    y = K_.bn_act(x, gamma, beta, rm, rv, residual=r, relu=relu, eps=1e-5, momentum=0.9, training=True)
+    g = torch.randn_like(y)
+    y.backward(g)
+    # fp32 reference
+    x2 = x.detach().float().requires_grad_(True)
+    r2 = r.detach().float().requires_grad_(True) if res else None
+    g2, b2 = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    mean, var = x2.mean(0), x2.var(0, unbiased=False)
+    yr = (x2 - mean) * torch.rsqrt(var + 1e-5) * g2 + b2
+    if res:
+        yr = yr + r2
+    if relu:
+        yr = torch.relu(yr)
+    yr.backward(g.float())
+    assert _rel_err(y, yr) < 2e-2
+    assert _rel_err(x.grad, x2.grad) < 3e-2
+    assert _rel_err(gamma.grad, g2.grad) < 2e-2
+    assert _rel_err(beta.grad, b2.grad) < 2e-2
+    if res:
+        assert _rel_err(r.grad, r2.grad) < 2e-2
+    assert _rel_err(rm, mean.detach() * 0.1) < 1e-2
+    assert _rel_err(rv, 0.9 + var.detach() * 0.1) < 1e-2
+
+
+def test_bn_eval_mode():
+    from mxb200.ops import functional as K_
+    dev = _dev()
+    x = torch.randn(512, 128, device=dev).bfloat16()
+    gamma, beta = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev)
+    rm, rv = torch.randn(128, device=dev), torch.rand(128, device=dev) + 0.5
+    y = K_.bn_act(x, gamma, beta, rm.clone(), rv.clone(), relu=True, training=False, eps=1e-5)
+    ref = torch.relu((x.float() - rm) * torch.rsqrt(rv + 1e-5) * gamma + beta)
+    assert _rel_err(y, ref) < 2e-2
+
+
+# ----------------------------------------------------------------------------- softmax / CE
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cols", [10, 1000, 30522])
+def test_softmax_ce(dtype, cols):
+    from mxb200.ops import functional as K_
+    dev = _dev()
+    x = (torch.randn(64, cols, device=dev) * 3).to(dtype).requires_grad_(True)
+    lab = torch.randint(0, cols, (64,), device=dev)
+    loss = K_.softmax_cross_entropy(x, lab)
+    loss.sum().backward()
+    x2 = x.detach().float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(x2, lab, reduction="none")
+    ref.sum().backward()
+    tol = 1e-4 if dtype is torch.float32 else 2e-2
+    assert _rel_err(loss, ref) < tol
+    assert _rel_err(x.grad, x2.grad) < tol
+
+
+def test_softmax_rows_and_label_smoothing():
+    from mxb200.ops import functional as K_
+    dev = _dev()
+    x = torch.randn(33, 777, device=dev)
+    assert _rel_err(K_.softmax_rows(x), torch.softmax(x, -1)) < 1e-5
+    assert _rel_err(K_.softmax_rows(x, log=True), torch.log_softmax(x, -1)) < 1e-5
+    lab = torch.randint(0, 777, (33,), device=dev)
+    got = K_.softmax_cross_entropy(x, lab, smooth_alpha=0.1)
+    lp = torch.log_softmax(x, -1)
+    tgt = torch.full_like(x, 0.1 / 776)
+    tgt.scatter_(1, lab[:, None], 0.9)
+    assert _rel_err(got, -(tgt * lp).sum(1)) < 1e-4
+
+
+# ----------------------------------------------------------------------------- optimizer kernels
+def _ref_sgd(w, g, m, lr, wd, mu, rescale, clip, nesterov):
+    g = g * rescale
+    if clip is not None:
+        g = g.clamp(-clip, clip)
+    if mu == 0:
+        return (1 - lr * wd) * w - lr * g, m
+    if not nesterov:
+        m = mu * m - lr * wd * w - lr * g
+        return w + m, m
+    g = g + wd * w
+    m = mu * m + g
+    return w - lr * (g + mu * m), m
+
+
+@pytest.mark.parametrize("n", [7, 1024, 100003])
+@pytest.mark.parametrize("mu,nesterov", [(0.0, False), (0.9, False), (0.9, True)])
+@pytest.mark.parametrize("clip", [None, 0.4])
+def test_sgd_kernel_fp32(n, mu, nesterov, clip):
+    from mxb200.ops import optim as KO
+    dev = _dev()
+    w, g = torch.randn(n, device=dev), torch.randn(n, device=dev)
+    m = torch.randn(n, device=dev) * 0.1 if mu else None
+    wr, mr = _ref_sgd(w.clone(), g.clone(), m.clone() if mu else None, 0.1, 0.03, mu, 0.8, clip, nesterov)
+    KO.sgd_update(w, g, m, None, 0.1, 0.03, mu, 0.8, clip, nesterov)
+    assert torch.allclose(w, wr, rtol=1e-5, atol=1e-6)
+    if mu:
+        assert torch.allclose(m, mr, rtol=1e-5, atol=1e-6)
+
+
+def test_sgd_kernel_multi_precision_and_chunk_table():
+    from mxb200.ops import optim as KO
+    dev = _dev()
+    n = 4096
+    w32 = torch.randn(n, device=dev)
+    w = w32.bfloat16()
+    g = torch.randn(n, device=dev).bfloat16()
+    m = torch.zeros(n, device=dev)
+    tid = torch.tensor([0, 1, -1, 1], dtype=torch.int32, device=dev)
+    lrm = torch.tensor([1.0, 2.0], device=dev)
+    wdm = torch.tensor([1.0, 0.0], device=dev)
+    w32_0 = w32.clone()
+    KO.sgd_update(w, g, m, w32, 0.1, 0.01, 0.9, 1.0, None, False, chunk_tid=tid, lr_mult=lrm, wd_mult=wdm, zero_grad=True)
+    gf = g.float()  # zeroed now for live chunks
+    assert gf[:1024].abs().max() == 0 and gf[2048:3072].abs().max() != 0
+    # chunk 0: lr 0.1 wd 0.01 ; chunk 1,3: lr 0.2 wd 0 ; chunk 2 untouched
+    assert torch.equal(w32[2048:3072], w32_0[2048:3072])
+    assert torch.allclose(w.float(), w32.bfloat16().float())
+
+
+def test_adam_and_lamb_kernels():
+    from mxb200.ops import optim as KO
+    dev = _dev()
+    n = 2048
+    w, g = torch.randn(n, device=dev), torch.randn(n, device=dev)
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    w0 = w.clone()
+    KO.adam_update(w, g, m, v, None, 0.01, 0.9, 0.999, 1e-8, 0.1, 1.0, None)
+    gg = g + 0.1 * w0
+    mr, vr = 0.1 * gg, 0.001 * gg * gg
+    assert torch.allclose(w, w0 - 0.01 * mr / (vr.sqrt() + 1e-8), rtol=1e-4, atol=1e-5)
+    # LAMB: one tensor of 2 chunks
+    w = torch.randn(n, device=dev); w0 = w.clone()
+    m.zero_(); v.zero_()
+    r = torch.empty(n, device=dev)
+    norms = torch.zeros(2, device=dev)
+    tid = torch.zeros(2, dtype=torch.int32, device=dev)
+    ones = torch.ones(1, device=dev)
+    KO.lamb_phase1(w, g, m, v, None, r, norms[0:1], norms[1:2], 0.9, 0.999, 1e-6, 1.0, None, 0.1, 0.001, 0.01, chunk_tid=tid, wd_mult=ones)
+    mh, vh = (0.1 * g) / 0.1, (0.001 * g * g) / 0.001
+    rr = mh / (vh.sqrt() + 1e-6) + 0.01 * w0
+    assert torch.allclose(r, rr, rtol=1e-4, atol=1e-5)
+    assert abs(norms[0].item() - (w0 ** 2).sum().item()) / (w0 ** 2).sum().item() < 1e-4
+    KO.lamb_phase2(w, None, r, norms[0:1], norms[1:2], 0.02, chunk_tid=tid, lr_mult=ones)
+    ratio = w0.norm() / rr.norm()
+    assert torch.allclose(w, w0 - 0.02 * ratio * rr, rtol=1e-4, atol=1e-5)
+
+
+def test_elementwise_sum():
+    from mxb200.ops import optim as KO
+    dev = _dev()
+    xs = [torch.randn(10001, device=dev) for _ in range(11)]
+    out = torch.empty_like(xs[0])
+    KO.elementwise_sum(out, xs, scale=0.5)
+    assert torch.allclose(out, 0.5 * torch.stack(xs).sum(0), rtol=1e-5, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------- fused allreduce+update (loopback ranks)
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("one_shot", [True, False])
+def test_fused_allreduce_sgd_loopback(world, one_shot):
+    """N logical ranks on one GPU: every rank's kernel runs on its own stream and they meet at the flag
+    barriers.  Checks reduce + momentum update + weight fan-out against a dense reference."""
+    from mxb200.parallel import peer, fused
+    dev = _dev()
+    groups = peer.make_local_groups([dev] * world, loopback=True)
+    shapes = [(1000,), (64, 3, 3, 3), (2048,), (517,)]
+    init = [torch.randn(s, device=dev) for s in shapes]
+    names = ["p%d" % i for i in range(len(shapes))]
+    nbytes_w = fused.SymmetricArena.bytes_needed(init, torch.bfloat16)
+    wb = peer._LocalGroup.alloc_all(groups, nbytes_w)
+    gb = peer._LocalGroup.alloc_all(groups, nbytes_w)
+    arenas = [fused.SymmetricArena(groups[r], names, [t.bfloat16() for t in init], {"weights": wb[r], "grads": gb[r]},
+                                   torch.bfloat16, torch.bfloat16) for r in range(world)]
+    grads = [[torch.randn(s, device=dev).bfloat16() for s in shapes] for _ in range(world)]
+    for r in range(world):
+        for gv, g in zip(arenas[r].grad_views, grads[r]):
+            gv.copy_(g)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(dev) for _ in range(world)]
+    lr, wd, mu, rescale = 0.1, 0.01, 0.9, 1.0 / world
+    for step in range(2):
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                fused.fused_step(arenas[r], fused.MODE_SGD, lr=lr, wd=wd, momentum=mu, rescale=rescale,
+                                 one_shot=one_shot, zero_grad=False, blocks=8, seq=step + 1)
+        torch.cuda.synchronize()
+        for g in groups:
+            g.check_error()
+    # reference: two identical steps with the same gradients
+    for i, s in enumerate(shapes):
+        gsum = sum(grads[r][i].float() for r in range(world))
+        w = init[i].bfloat16().float()
+        m = torch.zeros_like(w)
+        for _ in range(2):
+            w, m = _ref_sgd(w, gsum, m, lr, wd, mu, rescale, None, False)
+        for r in range(world):
+            got = arenas[r].views[i].float()
+            assert _rel_err(got, w) < 1e-2, "rank %d tensor %d" % (r, i)
+    for g in groups:
+        g.close()
+
+
+def test_fused_allreduce_plain_sum_loopback():
+    from mxb200.parallel import peer, fused
+    dev = _dev()
+    world = 2
+    groups = peer.make_local_groups([dev] * world, loopback=True)
+    t = [torch.zeros(5000, device=dev)]
+    nb = fused.SymmetricArena.bytes_needed(t, torch.float32)
+    wb = peer._LocalGroup.alloc_all(groups, nb)
+    gb = peer._LocalGroup.alloc_all(groups, nb)
+    arenas = [fused.SymmetricArena(groups[r], ["x"], t, {"weights": wb[r], "grads": gb[r]}, torch.float32, torch.float32)
+              for r in range(world)]
+    for r in range(world):
+        arenas[r].grad_views[0].fill_(r + 1.0)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(dev) for _ in range(world)]
+    for r in range(world):
+        with torch.cuda.stream(streams[r]):
+            fused.fused_step(arenas[r], fused.MODE_ALLREDUCE, rescale=1.0, one_shot=False, zero_grad=False, blocks=4, seq=1)
+    torch.cuda.synchronize()
+    for r in range(world):
+        groups[r].check_error()
+        assert torch.allclose(arenas[r].views[0], torch.full((5000,), 3.0, device=dev))
+    for g in groups:
+        g.close()
