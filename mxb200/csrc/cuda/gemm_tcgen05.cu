@@ -346,6 +346,13 @@ static CUtensorMap make_map(const void* ptr, CUtensorMapDataType dt, int elem_by
   cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  // The driver entry point needs a current context; autograd's backward threads may not have touched the
+  // runtime yet (CUDA_ERROR_INVALID_CONTEXT otherwise).  cudaFree(0) binds the primary context once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    CUDA_CHECK(cudaFree(0));
+    ctx_bound = true;
+  }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) throw std::runtime_error("TMA: base pointer not 16B aligned");
   if ((strides[0] & 15) != 0) throw std::runtime_error("TMA: row stride must be a multiple of 16 bytes");
   CUresult r = get_encode()(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

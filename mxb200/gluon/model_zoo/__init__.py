@@ -1,0 +1,3 @@
+"""Predefined models (reference: python/mxnet/gluon/model_zoo/)."""
+from . import vision  # noqa: F401
+from .vision import get_model  # noqa: F401

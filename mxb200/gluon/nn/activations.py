@@ -1,0 +1,58 @@
+"""Activation layers (reference: python/mxnet/gluon/nn/activations.py)."""
+from ..block import HybridBlock
+from ... import initializer
+
+__all__ = ["LeakyReLU", "PReLU", "ELU", "SELU", "Swish", "GELU"]
+
+
+class LeakyReLU(HybridBlock):
+    def __init__(self, alpha, **kwargs):
+        assert alpha >= 0, "Slope coefficient for LeakyReLU must be no less than 0."
+        super(LeakyReLU, self).__init__(**kwargs)
+        self._alpha = alpha
+
+    def hybrid_forward(self, F, x):
+        return F.LeakyReLU(x, act_type="leaky", slope=self._alpha, name="fwd")
+
+    def __repr__(self):
+        return "{name}({alpha})".format(name=self.__class__.__name__, alpha=self._alpha)
+
+
+class PReLU(HybridBlock):
+    def __init__(self, alpha_initializer=initializer.Constant(0.25), **kwargs):
+        super(PReLU, self).__init__(**kwargs)
+        with self.name_scope():
+            self.alpha = self.params.get("alpha", shape=(1,), init=alpha_initializer)
+
+    def hybrid_forward(self, F, x, alpha):
+        return F.LeakyReLU(x, gamma=alpha, act_type="prelu", name="fwd")
+
+
+class ELU(HybridBlock):
+    def __init__(self, alpha=1.0, **kwargs):
+        super(ELU, self).__init__(**kwargs)
+        self._alpha = alpha
+
+    def hybrid_forward(self, F, x):
+        return F.LeakyReLU(x, act_type="elu", slope=self._alpha)
+
+
+class SELU(HybridBlock):
+    def hybrid_forward(self, F, x):
+        return F.LeakyReLU(x, act_type="selu", name="fwd")
+
+
+class GELU(HybridBlock):
+    """Gaussian Error Linear Unit (absent in the reference; needed by the BERT config)."""
+
+    def hybrid_forward(self, F, x):
+        return F.LeakyReLU(x, act_type="gelu", name="fwd")
+
+
+class Swish(HybridBlock):
+    def __init__(self, beta=1.0, **kwargs):
+        super(Swish, self).__init__(**kwargs)
+        self._beta = beta
+
+    def hybrid_forward(self, F, x):
+        return x * F.sigmoid(self._beta * x, name="fwd")

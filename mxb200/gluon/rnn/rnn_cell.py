@@ -1,0 +1,241 @@
+"""Recurrent cells (reference: python/mxnet/gluon/rnn/rnn_cell.py)."""
+from ..block import Block, HybridBlock
+from ...ndarray import zeros
+from ... import ndarray as nd
+
+__all__ = ["RecurrentCell", "HybridRecurrentCell", "RNNCell", "LSTMCell", "GRUCell", "SequentialRNNCell", "DropoutCell",
+           "ResidualCell", "BidirectionalCell"]
+
+
+class RecurrentCell(Block):
+    def __init__(self, prefix=None, params=None):
+        super(RecurrentCell, self).__init__(prefix=prefix, params=params)
+        self._modified = False
+        self.reset()
+
+    def reset(self):
+        self._init_counter = -1
+        self._counter = -1
+        for cell in self._children.values():
+            cell.reset()
+
+    def state_info(self, batch_size=0):
+        raise NotImplementedError()
+
+    def begin_state(self, batch_size=0, func=zeros, **kwargs):
+        states = []
+        for info in self.state_info(batch_size):
+            self._init_counter += 1
+            info = dict(info) if info is not None else {}
+            info.pop("__layout__", None)
+            info.update(kwargs)
+            states.append(func(**info))
+        return states
+
+    def unroll(self, length, inputs, begin_state=None, layout="NTC", merge_outputs=None, valid_length=None):
+        self.reset()
+        axis = layout.find("T")
+        if isinstance(inputs, nd.NDArray):
+            batch_size = inputs.shape[layout.find("N")]
+            seq = [x.squeeze(axis) for x in nd.split(inputs, num_outputs=length, axis=axis, squeeze_axis=False)] if length > 1 \
+                else [inputs.squeeze(axis)]
+        else:
+            seq = list(inputs)
+            batch_size = seq[0].shape[0]
+        if begin_state is None:
+            begin_state = self.begin_state(batch_size, ctx=seq[0].context, dtype=seq[0].dtype)
+        states = begin_state
+        outputs = []
+        for i in range(length):
+            output, states = self(seq[i], states)
+            outputs.append(output)
+        if merge_outputs is None or merge_outputs:
+            outputs = nd.stack(*outputs, axis=axis)
+        return outputs, states
+
+    def forward(self, inputs, states):
+        self._counter += 1
+        return super(RecurrentCell, self).forward(inputs, states)
+
+
+class HybridRecurrentCell(RecurrentCell, HybridBlock):
+    def __init__(self, prefix=None, params=None):
+        super(HybridRecurrentCell, self).__init__(prefix=prefix, params=params)
+
+    def forward(self, inputs, states):
+        self._counter += 1
+        ctx = inputs.context
+        try:
+            params = {i: j.data(ctx) for i, j in self._reg_params.items()}
+        except Exception:
+            self._deferred_infer(inputs, states)
+            params = {i: j.data(ctx) for i, j in self._reg_params.items()}
+        return self.hybrid_forward(nd, inputs, states, **params)
+
+    def hybrid_forward(self, F, x, *args, **kwargs):
+        raise NotImplementedError
+
+
+class _BaseCell(HybridRecurrentCell):
+    _ngates = 1
+
+    def __init__(self, hidden_size, i2h_weight_initializer=None, h2h_weight_initializer=None,
+                 i2h_bias_initializer="zeros", h2h_bias_initializer="zeros", input_size=0, prefix=None, params=None):
+        super(_BaseCell, self).__init__(prefix=prefix, params=params)
+        g = self._ngates
+        self._hidden_size, self._input_size = hidden_size, input_size
+        self.i2h_weight = self.params.get("i2h_weight", shape=(g * hidden_size, input_size), init=i2h_weight_initializer, allow_deferred_init=True)
+        self.h2h_weight = self.params.get("h2h_weight", shape=(g * hidden_size, hidden_size), init=h2h_weight_initializer, allow_deferred_init=True)
+        self.i2h_bias = self.params.get("i2h_bias", shape=(g * hidden_size,), init=i2h_bias_initializer, allow_deferred_init=True)
+        self.h2h_bias = self.params.get("h2h_bias", shape=(g * hidden_size,), init=h2h_bias_initializer, allow_deferred_init=True)
+
+    def _infer_param_shapes(self, x, *args):
+        self.i2h_weight.shape = (self._ngates * self._hidden_size, x.shape[-1])
+
+    def state_info(self, batch_size=0):
+        return [{"shape": (batch_size, self._hidden_size), "__layout__": "NC"}]
+
+
+class RNNCell(_BaseCell):
+    def __init__(self, hidden_size, activation="tanh", **kwargs):
+        super(RNNCell, self).__init__(hidden_size, **kwargs)
+        self._activation = activation
+
+    def _alias(self):
+        return "rnn"
+
+    def hybrid_forward(self, F, inputs, states, i2h_weight, h2h_weight, i2h_bias, h2h_bias):
+        i2h = F.FullyConnected(inputs, i2h_weight, i2h_bias, num_hidden=self._hidden_size)
+        h2h = F.FullyConnected(states[0], h2h_weight, h2h_bias, num_hidden=self._hidden_size)
+        output = F.Activation(i2h + h2h, act_type=self._activation)
+        return output, [output]
+
+
+class LSTMCell(_BaseCell):
+    _ngates = 4
+
+    def _alias(self):
+        return "lstm"
+
+    def state_info(self, batch_size=0):
+        return [{"shape": (batch_size, self._hidden_size), "__layout__": "NC"},
+                {"shape": (batch_size, self._hidden_size), "__layout__": "NC"}]
+
+    def hybrid_forward(self, F, inputs, states, i2h_weight, h2h_weight, i2h_bias, h2h_bias):
+        i2h = F.FullyConnected(inputs, i2h_weight, i2h_bias, num_hidden=self._hidden_size * 4)
+        h2h = F.FullyConnected(states[0], h2h_weight, h2h_bias, num_hidden=self._hidden_size * 4)
+        gates = i2h + h2h
+        s = F.split(gates, num_outputs=4, axis=1)
+        in_gate, forget_gate = F.sigmoid(s[0]), F.sigmoid(s[1])
+        in_transform, out_gate = F.tanh(s[2]), F.sigmoid(s[3])
+        next_c = forget_gate * states[1] + in_gate * in_transform
+        next_h = out_gate * F.tanh(next_c)
+        return next_h, [next_h, next_c]
+
+
+class GRUCell(_BaseCell):
+    _ngates = 3
+
+    def _alias(self):
+        return "gru"
+
+    def hybrid_forward(self, F, inputs, states, i2h_weight, h2h_weight, i2h_bias, h2h_bias):
+        prev = states[0]
+        i2h = F.FullyConnected(inputs, i2h_weight, i2h_bias, num_hidden=self._hidden_size * 3)
+        h2h = F.FullyConnected(prev, h2h_weight, h2h_bias, num_hidden=self._hidden_size * 3)
+        i2h_r, i2h_z, i2h = F.split(i2h, num_outputs=3, axis=1)
+        h2h_r, h2h_z, h2h = F.split(h2h, num_outputs=3, axis=1)
+        reset_gate = F.sigmoid(i2h_r + h2h_r)
+        update_gate = F.sigmoid(i2h_z + h2h_z)
+        next_h_tmp = F.tanh(i2h + reset_gate * h2h)
+        next_h = (1. - update_gate) * next_h_tmp + update_gate * prev
+        return next_h, [next_h]
+
+
+class SequentialRNNCell(RecurrentCell):
+    def add(self, cell):
+        self.register_child(cell)
+
+    def state_info(self, batch_size=0):
+        return sum([c.state_info(batch_size) for c in self._children.values()], [])
+
+    def begin_state(self, **kwargs):
+        return sum([c.begin_state(**kwargs) for c in self._children.values()], [])
+
+    def __call__(self, inputs, states):
+        self._counter += 1
+        next_states = []
+        p = 0
+        for cell in self._children.values():
+            n = len(cell.state_info())
+            state = states[p:p + n]
+            p += n
+            inputs, state = cell(inputs, state)
+            next_states.append(state)
+        return inputs, sum(next_states, [])
+
+    def __len__(self):
+        return len(self._children)
+
+    def __getitem__(self, i):
+        return list(self._children.values())[i]
+
+
+class DropoutCell(HybridRecurrentCell):
+    def __init__(self, rate, prefix=None, params=None):
+        super(DropoutCell, self).__init__(prefix, params)
+        self.rate = rate
+
+    def state_info(self, batch_size=0):
+        return []
+
+    def _alias(self):
+        return "dropout"
+
+    def hybrid_forward(self, F, inputs, states):
+        if self.rate > 0:
+            inputs = F.Dropout(inputs, p=self.rate)
+        return inputs, states
+
+
+class ResidualCell(RecurrentCell):
+    def __init__(self, base_cell):
+        super(ResidualCell, self).__init__(prefix=base_cell.prefix + "res_", params=None)
+        self.base_cell = base_cell
+
+    def state_info(self, batch_size=0):
+        return self.base_cell.state_info(batch_size)
+
+    def begin_state(self, **kwargs):
+        return self.base_cell.begin_state(**kwargs)
+
+    def __call__(self, inputs, states):
+        output, states = self.base_cell(inputs, states)
+        return output + inputs, states
+
+
+class BidirectionalCell(RecurrentCell):
+    def __init__(self, l_cell, r_cell, output_prefix="bi_"):
+        super(BidirectionalCell, self).__init__(prefix="", params=None)
+        self.l_cell, self.r_cell = l_cell, r_cell
+        self._output_prefix = output_prefix
+
+    def state_info(self, batch_size=0):
+        return self.l_cell.state_info(batch_size) + self.r_cell.state_info(batch_size)
+
+    def begin_state(self, **kwargs):
+        return self.l_cell.begin_state(**kwargs) + self.r_cell.begin_state(**kwargs)
+
+    def __call__(self, inputs, states):
+        raise NotImplementedError("Bidirectional cannot be stepped. Please use unroll")
+
+    def unroll(self, length, inputs, begin_state=None, layout="NTC", merge_outputs=None, valid_length=None):
+        axis = layout.find("T")
+        if begin_state is None:
+            bs = inputs.shape[layout.find("N")]
+            begin_state = self.begin_state(batch_size=bs, ctx=inputs.context)
+        nl = len(self.l_cell.state_info())
+        l_out, l_st = self.l_cell.unroll(length, inputs, begin_state[:nl], layout, merge_outputs=True)
+        r_out, r_st = self.r_cell.unroll(length, nd.flip(inputs, axis=axis), begin_state[nl:], layout, merge_outputs=True)
+        out = nd.concat(l_out, nd.flip(r_out, axis=axis), dim=2)
+        return out, l_st + r_st

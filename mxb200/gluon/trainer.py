@@ -1,0 +1,349 @@
+"""gluon.Trainer (reference: python/mxnet/gluon/trainer.py:62-423).
+
+Two execution paths behind one API:
+
+* **fused** (default on CUDA for SGD / NAG / Adam / LAMB with dense parameters on one GPU per process):
+  parameters and gradients are re-homed into symmetric arenas and ``step`` is ONE kernel launch per dtype
+  group that performs the cross-GPU gradient reduction (P2P over NVLink), rescale/clip, the optimizer
+  update with fp32 master weights and the weight fan-out (mxb200/parallel/trainer.py,
+  csrc/cuda/allreduce.cu).  This replaces _allreduce_grads + _update (trainer.py:304-374).
+* **generic**: the reference algorithm -- kvstore push/pull per parameter + per-context Updaters -- used on
+  CPU, with several contexts in one process, with sparse gradients or custom optimizers.
+"""
+import warnings
+
+import torch
+
+from .. import optimizer as opt
+from ..base import getenv
+from ..model import _create_kvstore
+from ..ndarray import NDArray, sparse as _sp
+from .parameter import ParameterDict, Parameter
+
+__all__ = ["Trainer"]
+
+
+class Trainer(object):
+    def __init__(self, params, optimizer, optimizer_params=None, kvstore="device", compression_params=None,
+                 update_on_kvstore=None):
+        if isinstance(params, (dict, ParameterDict)):
+            params = list(params.values())
+        if not isinstance(params, (list, tuple)):
+            raise ValueError("First argument must be a list or dict of Parameters, got %s." % (type(params)))
+        self._params = []
+        self._contains_sparse = False
+        self._param2idx = {}
+        for i, param in enumerate(params):
+            if not isinstance(param, Parameter):
+                raise ValueError("First argument must be a list or dict of Parameters, got list of %s." % (type(param)))
+            self._param2idx[param.name] = i
+            self._params.append(param)
+            param._trainer = self
+            if param._stype != "default" or param._grad_stype != "default":
+                self._contains_sparse = True
+        self._compression_params = compression_params
+        optimizer_params = optimizer_params if optimizer_params else {}
+        self._scale = float(optimizer_params.get("rescale_grad", 1.0))
+        self._contexts = self._check_contexts()
+        self._init_optimizer(optimizer, optimizer_params)
+        self._kvstore_params = {"kvstore": kvstore, "update_on_kvstore": update_on_kvstore}
+        self._kv_initialized = False
+        self._kvstore = None
+        self._update_on_kvstore = None
+        self._params_to_init = []
+        self._fused = None
+        self._reset_kvstore()
+
+    def _check_contexts(self):
+        contexts = None
+        for param in self._params:
+            ctx = param.list_ctx()
+            assert contexts is None or contexts == ctx, \
+                "All Parameters must be initialized on the same set of contexts, but Parameter %s is initialized on " \
+                "%s while previous Parameters are initialized on %s." % (param.name, str(ctx), str(contexts))
+            contexts = ctx
+        return contexts
+
+    def _init_optimizer(self, optimizer, optimizer_params):
+        param_dict = {i: param for i, param in enumerate(self._params)}
+        if isinstance(optimizer, opt.Optimizer):
+            assert not optimizer_params, "optimizer_params must be None if optimizer is an instance of Optimizer " \
+                                         "instead of str"
+            self._optimizer = optimizer
+            self._optimizer.param_dict = param_dict
+        else:
+            self._optimizer = opt.create(optimizer, param_dict=param_dict, **optimizer_params)
+        self._updaters = [opt.get_updater(self._optimizer) for _ in self._contexts]
+
+    def _reset_kvstore(self):
+        if self._kvstore and "dist" in self._kvstore.type:
+            raise RuntimeError("Cannot reset distributed KVStore.")
+        self._kv_initialized = False
+        self._kvstore = None
+        self._update_on_kvstore = None
+        self._params_to_init = [param for param in self._params]
+        if self._fused is not None:
+            self._unfuse()
+
+    # ---------------------------------------------------------------------------------- kvstore init
+    def _init_kvstore(self):
+        config = self._kvstore_params
+        if self._contains_sparse:
+            kvstore, update_on_kvstore = _create_kvstore(config["kvstore"], len(self._contexts), {})
+            if config["update_on_kvstore"] is False:
+                raise RuntimeError("Cannot set update_on_kvstore to False when sparse gradients and/or sparse "
+                                   "weights are present for Parameter.")
+            update_on_kvstore = True if kvstore else update_on_kvstore
+        else:
+            arg_arrays = {}
+            for param in self._params:
+                try:
+                    arg_arrays[param.name] = param.data(self._contexts[0])
+                except Exception:  # noqa: BLE001
+                    pass
+            kvstore, update_on_kvstore = _create_kvstore(config["kvstore"], len(self._contexts), arg_arrays)
+            if config["update_on_kvstore"] is not None:
+                update_on_kvstore = config["update_on_kvstore"]
+        if kvstore:
+            if self._compression_params:
+                kvstore.set_gradient_compression(self._compression_params)
+            if "dist" in kvstore.type:
+                update_on_kvstore = True if "async" in kvstore.type else update_on_kvstore
+            if update_on_kvstore:
+                kvstore.set_optimizer(self._optimizer)
+            self._kvstore = kvstore
+            self._update_on_kvstore = update_on_kvstore
+        else:
+            self._kvstore = None
+            self._update_on_kvstore = None
+        self._kv_initialized = True
+        self._maybe_fuse()
+
+    # ---------------------------------------------------------------------------------- fused path
+    def _fusable(self):
+        if not getenv("MXB200_FUSED_TRAINER", True):
+            return False
+        if self._contains_sparse or self._compression_params or len(self._contexts) != 1:
+            return False
+        if self._contexts[0].device_type != "gpu" or not torch.cuda.is_available():
+            return False
+        if type(self._optimizer) not in (opt.SGD, opt.NAG, opt.Adam, opt.LAMB):
+            return False
+        kv = self._kvstore
+        if kv is not None and "dist" in kv.type:
+            return False
+        for p in self._params:
+            if p._data is None:
+                return False
+        return True
+
+    def _maybe_fuse(self):
+        if self._fused is not None or not self._fusable():
+            return
+        from ..parallel.trainer import DeviceTrainer
+        ctx = self._contexts[0]
+        kv = self._kvstore
+        world = kv.num_workers if kv is not None else 1
+        rank = kv.rank if kv is not None else 0
+        train = [p for p in self._params if p.grad_req != "null"]
+        if not train:
+            return
+        named = [(p.name, p.data(ctx)._t.detach()) for p in train]
+        lr_mult = {p.name: p.lr_mult for p in train}
+        wd_mult = {p.name: p.wd_mult for p in train}
+        dt = DeviceTrainer(named, ctx.torch_device, rank=rank, world=world, lr_mult=lr_mult, wd_mult=wd_mult)
+        views = dt.params()
+        for p in train:
+            v = views[p.name]
+            d = p._data[0]
+            if d._grad_hook is not None:      # arena grads are cleared by the fused kernel itself
+                d._grad_hook.remove()
+                d._grad_hook = None
+            d._t = v
+            p._grad[0]._t = v.grad
+        if world > 1:
+            # non-trainable state (BN running stats): start from rank 0's values (kv.init semantics)
+            import torch.distributed as dist
+            for p in self._params:
+                if p.grad_req == "null":
+                    dist.broadcast(p._data[0]._t, src=0)
+            # weights: rank 0 wins
+            for ar in dt.arenas:
+                dist.broadcast(ar.weights, src=0)
+        self._fused = dt
+        self._params_to_init = []
+
+    def _unfuse(self):
+        dt, self._fused = self._fused, None
+        for p in self._params:
+            if p.grad_req == "null" or p._data is None:
+                continue
+            d = p._data[0]
+            t = d._t.detach().clone().contiguous() if d._t.is_contiguous() else d._t.detach().clone()
+            d._t = t
+            d._grad_req = None
+            d.attach_grad(p.grad_req)
+            p._grad[0]._t = d._t.grad
+        try:
+            dt.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def check_health(self):
+        """Raise if a fused collective timed out (a peer never arrived)."""
+        if self._fused is not None:
+            torch.cuda.synchronize(self._fused.device)
+            self._fused.check()
+
+    # ---------------------------------------------------------------------------------- properties
+    @property
+    def learning_rate(self):
+        if not isinstance(self._optimizer, opt.Optimizer):
+            raise UserWarning("Optimizer has to be defined before its learning rate can be accessed.")
+        return self._optimizer.learning_rate
+
+    def set_learning_rate(self, lr):
+        if not isinstance(self._optimizer, opt.Optimizer):
+            raise UserWarning("Optimizer has to be defined before its learning rate is mutated.")
+        self._optimizer.set_learning_rate(lr)
+
+    def _init_params(self):
+        assert self._kv_initialized, "Cannot initialize parameters in KVStore when KVStore is not initialized."
+        params_to_init = []
+        if self._kvstore:
+            for param in self._params_to_init:
+                if param._deferred_init:
+                    params_to_init.append(param)
+                else:
+                    param_arrays = param._check_and_get(param._data, list)
+                    idx = self._param2idx[param.name]
+                    self._kvstore.init(idx, param_arrays[0])
+                    if param._stype == "default":
+                        self._kvstore.pull(idx, param_arrays, priority=-idx)
+        self._params_to_init = params_to_init
+
+    def _row_sparse_pull(self, parameter, out, row_id):
+        if not self._kv_initialized:
+            self._init_kvstore()
+        if self._params_to_init:
+            self._init_params()
+        idx = self._param2idx[parameter.name]
+        self._kvstore.row_sparse_pull(idx, out=out, row_ids=row_id, priority=-idx)
+
+    # ---------------------------------------------------------------------------------- step
+    def step(self, batch_size, ignore_stale_grad=False):
+        """One optimisation step; gradients are normalised by 1/batch_size (trainer.py:254-280)."""
+        rescale_grad = self._scale / batch_size
+        if not self._kv_initialized:
+            self._init_kvstore()
+        if self._fused is not None:
+            self._fused_step(rescale_grad)
+            return
+        if self._params_to_init:
+            self._init_params()
+        self._optimizer.rescale_grad = rescale_grad
+        self._allreduce_grads()
+        self._update(ignore_stale_grad)
+
+    def _fused_step(self, rescale_grad):
+        o = self._optimizer
+        o.rescale_grad = rescale_grad
+        o.num_update += 1
+        lr = o.lr_scheduler(o.num_update) if o.lr_scheduler is not None else o.lr
+        kind = {opt.SGD: "sgd", opt.NAG: "nag", opt.Adam: "adam", opt.LAMB: "lamb"}[type(o)]
+        kw = {}
+        if kind in ("adam", "lamb"):
+            kw.update(beta1=o.beta1, beta2=o.beta2, eps=o.epsilon)
+        if kind == "lamb":
+            kw.update(bias_correction=o.bias_correction,
+                      lamb_bounds=(-1.0 if o.lower_bound is None else o.lower_bound,
+                                   -1.0 if o.upper_bound is None else o.upper_bound))
+        self._fused.step(kind, lr=lr, wd=o.wd, momentum=getattr(o, "momentum", 0.0), rescale=rescale_grad,
+                         clip=o.clip_gradient, multi_precision=o.multi_precision, **kw)
+
+    def allreduce_grads(self):
+        if not self._kv_initialized:
+            self._init_kvstore()
+        if self._fused is not None:
+            raise RuntimeError("allreduce_grads()/update() split is not available on the fused path; construct the "
+                               "Trainer with update_on_kvstore=False and set MXB200_FUSED_TRAINER=0, or call step().")
+        if self._params_to_init:
+            self._init_params()
+        assert not (self._kvstore and self._update_on_kvstore), \
+            "allreduce_grads() when parameters are updated on kvstore is not supported. Try setting " \
+            "`update_on_kvstore` to False when creating trainer."
+        self._allreduce_grads()
+
+    def _allreduce_grads(self):
+        if self._kvstore:
+            for i, param in enumerate(self._params):
+                if param.grad_req != "null":
+                    self._kvstore.push(i, param.list_grad(), priority=-i)
+                    if not self._update_on_kvstore:
+                        self._kvstore.pull(i, param.list_grad(), priority=-i, ignore_sparse=False)
+
+    def update(self, batch_size, ignore_stale_grad=False):
+        if not self._kv_initialized:
+            self._init_kvstore()
+        if self._params_to_init:
+            self._init_params()
+        assert not (self._kvstore and self._update_on_kvstore), \
+            "update() when parameters are updated on kvstore is not supported. Try setting `update_on_kvstore` to " \
+            "False when creating trainer."
+        self._optimizer.rescale_grad = self._scale / batch_size
+        self._update(ignore_stale_grad)
+
+    def _update(self, ignore_stale_grad=False):
+        for i, param in enumerate(self._params):
+            if param.grad_req == "null":
+                continue
+            if self._kvstore and self._update_on_kvstore:
+                if param._stype == "default":
+                    self._kvstore.pull(i, param.list_data(), priority=-i)
+                continue
+            for upd, arr, grad in zip(self._updaters, param.list_data(), param.list_grad()):
+                upd(i, grad, arr)
+
+    # ---------------------------------------------------------------------------------- states
+    def save_states(self, fname):
+        assert self._optimizer is not None
+        if not self._kv_initialized:
+            self._init_kvstore()
+        if self._fused is not None:
+            state = {"num_update": self._optimizer.num_update, "trainer_num_update": self._fused.num_update,
+                     "arenas": [{k: v.detach().cpu() for k, v in ar.state.items()} for ar in self._fused.arenas]}
+            torch.save(state, fname)
+            return
+        if self._params_to_init:
+            self._init_params()
+        if self._update_on_kvstore:
+            self._kvstore.save_optimizer_states(fname, dump_optimizer=True)
+        else:
+            with open(fname, "wb") as fout:
+                fout.write(self._updaters[0].get_states(dump_optimizer=True))
+
+    def load_states(self, fname):
+        if not self._kv_initialized:
+            self._init_kvstore()
+        if self._fused is not None:
+            state = torch.load(fname, map_location="cpu")
+            self._optimizer.num_update = state["num_update"]
+            self._fused.num_update = state["trainer_num_update"]
+            for ar, st in zip(self._fused.arenas, state["arenas"]):
+                for k, v in st.items():
+                    ar.get_state(k).copy_(v) if k != "norms" else None
+            return
+        if self._params_to_init:
+            self._init_params()
+        if self._update_on_kvstore:
+            self._kvstore.load_optimizer_states(fname)
+            self._optimizer = self._kvstore._updater.optimizer
+        else:
+            with open(fname, "rb") as f:
+                states = f.read()
+            for updater in self._updaters:
+                updater.set_states(states)
+                updater.optimizer = self._updaters[0].optimizer
+            self._optimizer = self._updaters[0].optimizer
+        param_dict = {i: param for i, param in enumerate(self._params)}
+        self._optimizer.param_dict = param_dict

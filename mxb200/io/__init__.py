@@ -1,0 +1,3 @@
+"""Data iterators (reference: python/mxnet/io/)."""
+from .io import *  # noqa: F401,F403
+from .io import DataDesc, DataBatch, DataIter  # noqa: F401

@@ -1,0 +1,370 @@
+"""KVStore: key-value store for data-parallel training (reference API: python/mxnet/kvstore.py:116-688,
+C++ include/mxnet/kvstore.h:60-446, src/kvstore/kvstore_local.h, comm.h).
+
+Semantics preserved: ``push`` = reduce the per-device values of a key (duplicates of a key
+in one call are summed) then either run the updater on the stored value or replace it; ``pull`` =
+broadcast the stored value into every output; ``init`` once per key; int or str keys but never mixed; keys
+initialised with ``exclude_update=True`` are numbered from ``MAX_ALLOWED_KEY_FOR_UPDATE+1`` and are
+*averaged* instead of optimised (the elastic fork's aux-state keys, kvstore_local.h:100-120,
+kvstore_dist_server.h:345-379).
+
+Store types (substring matched like src/kvstore/kvstore.cc:40-77):
+  local / local_update_cpu / local_allreduce_cpu : host reduce  (CommCPU, comm.h:103-441)
+  device / local_allreduce_device / nccl          : device reduce.  Inside one process the per-device values
+        are summed on the owner device with our ElementwiseSum kernel after P2P copies.  When the job runs one
+        process per GPU (torchrun / tools/launch.py) the store spans the processes: rank/num_workers come from
+        the process group and gluon.Trainer / Module route whole steps through the fused
+        allreduce+update kernel (mxb200/parallel/trainer.py) instead of per-key push/pull.
+  dist_sync / dist_device_sync / dist_async       : parameter-server path (kvstore/dist.py)
+"""
+import pickle
+
+import torch
+
+from ..base import MXNetError, getenv
+from ..ndarray import NDArray, sparse as _sp
+from ..ndarray.ndarray import zeros_like
+from .. import optimizer as opt
+from .compression import GradientCompression
+
+__all__ = ["KVStore", "KVStoreLocal", "create", "MAX_ALLOWED_KEY_FOR_UPDATE"]
+
+MAX_ALLOWED_KEY_FOR_UPDATE = 10000000
+
+
+def _as_list(x):
+    return list(x) if isinstance(x, (list, tuple)) else [x]
+
+
+def _key_value_lists(key, value):
+    """Normalise (key, value) into parallel lists: keys[i] <-> list of per-device arrays."""
+    if isinstance(key, (int, str)):
+        vals = _as_list(value)
+        return [key], [vals]
+    keys = list(key)
+    if len(keys) == 0:
+        return [], []
+    assert isinstance(value, (list, tuple)), "a list of keys needs a list of values"
+    if len(value) == len(keys) and not isinstance(value[0], (list, tuple)):
+        return keys, [[v] for v in value]
+    if len(value) == len(keys):
+        return keys, [list(v) for v in value]
+    # flat list: k values per key
+    assert len(value) % len(keys) == 0, "the number of values must be a multiple of the number of keys"
+    n = len(value) // len(keys)
+    return keys, [list(value[i * n:(i + 1) * n]) for i in range(len(keys))]
+
+
+class KVStore(object):
+    """Abstract interface (python/mxnet/kvstore.py).  Concrete: KVStoreLocal, KVStoreDist."""
+
+    def __init__(self, kv_type):
+        self._type = kv_type
+        self._updater = None
+        self._updater_func = None
+        self._str2int = {}
+        self._key_type = None
+        self._next_str_key = [0, MAX_ALLOWED_KEY_FOR_UPDATE + 1]
+        self._compression = None
+        self._barrier_before_exit = True
+
+    # identity -------------------------------------------------------------------------------------
+    @property
+    def type(self):
+        return self._type
+
+    @property
+    def rank(self):
+        return 0
+
+    @property
+    def num_workers(self):
+        return 1
+
+    # key typing -----------------------------------------------------------------------------------
+    def _set_key_type(self, key):
+        t = str if isinstance(key, str) else int
+        if self._key_type is None:
+            self._key_type = t
+        elif self._key_type is not t:
+            raise MXNetError("inconsistent types of keys detected: a store uses either int or str keys, not both")
+
+    def _int_key(self, key, create=False, exclude_update=False):
+        """str keys get dense integer ids; exclude-update (aux) keys live above MAX_ALLOWED_KEY_FOR_UPDATE."""
+        self._set_key_type(key)
+        if isinstance(key, int):
+            return key
+        if key not in self._str2int:
+            if not create:
+                raise MXNetError("key %s has not been initialized" % key)
+            slot = 1 if exclude_update else 0
+            self._str2int[key] = self._next_str_key[slot]
+            self._next_str_key[slot] += 1
+        return self._str2int[key]
+
+    # API ------------------------------------------------------------------------------------------
+    def init(self, key, value, exclude_update=False):
+        raise NotImplementedError
+
+    def push(self, key, value, priority=0):
+        raise NotImplementedError
+
+    def pull(self, key, out=None, priority=0, ignore_sparse=True):
+        raise NotImplementedError
+
+    def row_sparse_pull(self, key, out=None, priority=0, row_ids=None):
+        raise NotImplementedError
+
+    def set_gradient_compression(self, compression_params):
+        if ("device" not in self._type) and ("dist" not in self._type):
+            raise MXNetError("Gradient compression is not supported for this type of kvstore")
+        self._compression = GradientCompression(compression_params)
+
+    def set_optimizer(self, optimizer):
+        self._set_updater(opt.get_updater(optimizer))
+
+    def _set_updater(self, updater):
+        self._updater = updater
+        self._updater_func = updater
+
+    def save_optimizer_states(self, fname, dump_optimizer=False):
+        assert self._updater is not None, "Cannot save states for distributed training"
+        with open(fname, "wb") as fout:
+            fout.write(self._updater.get_states(dump_optimizer))
+
+    def load_optimizer_states(self, fname):
+        assert self._updater is not None, "Cannot load states for distributed training"
+        with open(fname, "rb") as f:
+            self._updater.set_states(f.read())
+
+    def _barrier(self):
+        pass
+
+    def _membership_change_barrier(self, env):
+        raise MXNetError("membership change barrier is only available for dist / multi-process kvstores "
+                         "(python/mxnet/kvstore.py:617-624)")
+
+    def _send_command_to_servers(self, head, body):
+        pass
+
+    def get_num_dead_node(self, node_id=0, timeout=60):
+        return 0
+
+
+class KVStoreLocal(KVStore):
+    """Single-process store: values of one key are one array per device (KVStoreLocal + CommCPU/CommDevice)."""
+
+    def __init__(self, kv_type="local"):
+        super(KVStoreLocal, self).__init__(kv_type)
+        self._store = {}
+        self._device_mode = ("device" in kv_type) or ("nccl" in kv_type)
+        self._residuals = {}
+
+    # reduce / broadcast (Comm) ----------------------------------------------------------------------
+    def _reduce(self, ikey, vals):
+        """Sum the per-device values.  Returns an array on the 'owner' device (CommDevice) or pinned/host
+        memory (CommCPU)."""
+        if any(isinstance(v, _sp.RowSparseNDArray) for v in vals):
+            tgt = self._store[ikey].context if ikey in self._store else vals[0].context
+            return _sp.add_n_rsp([v.as_in_context(tgt) for v in vals])
+        if len(vals) == 1:
+            return vals[0]
+        if self._compression is not None and self._device_mode:
+            return self._reduce_compressed(ikey, vals)
+        if self._device_mode and vals[0]._t.is_cuda:
+            owner = self._store[ikey]._t.device if ikey in self._store and self._store[ikey]._t.is_cuda else vals[0]._t.device
+            with torch.no_grad():
+                ts = [v._t if v._t.device == owner else v._t.to(owner, non_blocking=True) for v in vals]
+                out = torch.empty_like(ts[0])
+                if all(t.is_contiguous() for t in ts):
+                    from ..ops import optim as KO
+                    with torch.cuda.device(owner):
+                        KO.elementwise_sum(out, ts)
+                else:
+                    out = torch.stack(ts).sum(0)
+            return NDArray(out)
+        # host reduce
+        with torch.no_grad():
+            acc = vals[0]._t.detach().to("cpu", copy=True).float()
+            for v in vals[1:]:
+                acc += v._t.detach().to("cpu").float()
+        return NDArray(acc.to(vals[0]._t.dtype), vals[0].context if not vals[0]._t.is_cuda else None)
+
+    def _reduce_compressed(self, ikey, vals):
+        """2-bit quantise on the source device, move the small buffer, dequantise and sum at the owner
+        (CommDevice::ReduceCompressed, comm.h:552-596)."""
+        owner = vals[0]._t.device
+        acc = None
+        for i, v in enumerate(vals):
+            res = self._residuals.setdefault((ikey, i), torch.zeros_like(v._t, dtype=torch.float32))
+            q = self._compression.quantize(v._t, res)
+            d = self._compression.dequantize(q.to(owner), v._t.numel(), v._t.shape, owner)
+            acc = d if acc is None else acc + d
+        return NDArray(acc.to(vals[0]._t.dtype), vals[0].context)
+
+    # API --------------------------------------------------------------------------------------------
+    def init(self, key, value, exclude_update=False):
+        keys, vals = _key_value_lists(key, value)
+        for k, vlist in zip(keys, vals):
+            ik = self._int_key(k, create=True, exclude_update=exclude_update)
+            if ik in self._store:
+                raise MXNetError("duplicate init of key %s" % str(k))
+            v = vlist[0]
+            self._store[ik] = v.copy() if isinstance(v, (NDArray, _sp.BaseSparseNDArray)) else v
+
+    def _group(self, keys, vals):
+        """GroupKVPairs: duplicates of a key in one call are merged (kvstore_local.h:349-379)."""
+        grouped, order = {}, []
+        for k, vlist in zip(keys, vals):
+            ik = self._int_key(k)
+            if ik not in grouped:
+                grouped[ik] = []
+                order.append(ik)
+            grouped[ik].extend(vlist)
+        return [(ik, grouped[ik]) for ik in order]
+
+    def push(self, key, value, priority=0):
+        keys, vals = _key_value_lists(key, value)
+        for ik, vlist in self._group(keys, vals):
+            if ik not in self._store:
+                raise MXNetError("key %s has not been initialized" % str(ik))
+            merged = self._reduce(ik, vlist)
+            stored = self._store[ik]
+            if ik > MAX_ALLOWED_KEY_FOR_UPDATE:
+                # exclude-update (aux) key: average over contributing workers, never optimised
+                merged = merged / float(self.num_workers) if self.num_workers > 1 else merged
+                self._assign(stored, merged)
+            elif self._updater is not None:
+                if isinstance(merged, NDArray) and isinstance(stored, NDArray) and merged._t.device != stored._t.device:
+                    merged = NDArray(merged._t.to(stored._t.device), stored.context)
+                self._updater(self._orig_key(ik), merged, stored)
+            else:
+                self._assign(stored, merged)
+
+    def _orig_key(self, ik):
+        if self._key_type is str:
+            for k, v in self._str2int.items():
+                if v == ik:
+                    return k
+        return ik
+
+    @staticmethod
+    def _assign(stored, merged):
+        if isinstance(stored, _sp.RowSparseNDArray):
+            src = merged if isinstance(merged, _sp.RowSparseNDArray) else _sp.cast_storage(merged, "row_sparse")
+            src.copyto(stored)
+        elif isinstance(merged, _sp.BaseSparseNDArray):
+            stored[:] = merged.todense()
+        else:
+            with torch.no_grad():
+                stored._t.copy_(merged._t)
+
+    def pull(self, key, out=None, priority=0, ignore_sparse=True):
+        assert out is not None
+        keys, outs = _key_value_lists(key, out)
+        for k, olist in zip(keys, outs):
+            ik = self._int_key(k)
+            if ik not in self._store:
+                raise MXNetError("key %s has not been initialized" % str(k))
+            stored = self._store[ik]
+            if isinstance(stored, _sp.RowSparseNDArray):
+                if ignore_sparse:
+                    continue
+                raise MXNetError("pull with row_sparse stored value: use row_sparse_pull")
+            for o in olist:
+                if isinstance(o, _sp.BaseSparseNDArray):
+                    if not ignore_sparse:
+                        raise MXNetError("pull into a sparse output is not supported; use row_sparse_pull")
+                    continue
+                with torch.no_grad():
+                    o._t.copy_(stored._t, non_blocking=True)
+
+    def row_sparse_pull(self, key, out=None, priority=0, row_ids=None):
+        assert out is not None and row_ids is not None
+        keys, outs = _key_value_lists(key, out)
+        _k2, rids = _key_value_lists(key, row_ids)
+        from .utils import unique_rows
+        for k, olist, rlist in zip(keys, outs, rids):
+            ik = self._int_key(k)
+            stored = self._store[ik]
+            dense = stored.todense()._t if isinstance(stored, _sp.RowSparseNDArray) else stored._t
+            if len(rlist) == 1 and len(olist) > 1:
+                rlist = rlist * len(olist)
+            for o, rid in zip(olist, rlist):
+                ids = unique_rows(rid._t.to(dense.device))
+                data = dense.index_select(0, ids)
+                if isinstance(o, _sp.RowSparseNDArray):
+                    dev = o._data.device
+                    o._data, o._indices, o._shape = data.to(dev), ids.to(dev), tuple(dense.shape)
+                else:
+                    with torch.no_grad():
+                        o._t.zero_()
+                        o._t.index_copy_(0, ids.to(o._t.device), data.to(o._t.device))
+
+    def set_optimizer(self, optimizer):
+        self._set_updater(opt.get_updater(optimizer))
+
+
+class KVStoreDevice(KVStoreLocal):
+    """kvstore('device'/'nccl') when the job is one process per GPU: the store spans the process group.
+
+    ``push``/``pull`` of individual keys fall back to an allreduce of that key across ranks followed by the
+    local updater (every rank applies the identical update), which keeps the plain KVStore API usable; the
+    fast path is :meth:`fused_trainer`, which gluon.Trainer and Module use to run a whole step as one fused
+    kernel per dtype group."""
+
+    def __init__(self, kv_type="device"):
+        super(KVStoreDevice, self).__init__(kv_type)
+        import torch.distributed as dist
+        self._dist = dist
+        self._trainer = None
+
+    @property
+    def rank(self):
+        return self._dist.get_rank() if self._dist.is_initialized() else 0
+
+    @property
+    def num_workers(self):
+        return self._dist.get_world_size() if self._dist.is_initialized() else 1
+
+    def init(self, key, value, exclude_update=False):
+        super(KVStoreDevice, self).init(key, value, exclude_update)
+        if self.num_workers > 1:   # only rank 0's value is used (kvstore.py:116-158)
+            keys, _ = _key_value_lists(key, value)
+            for k in keys:
+                st = self._store[self._int_key(k)]
+                if isinstance(st, NDArray):
+                    self._dist.broadcast(st._t, src=0)
+
+    def _reduce(self, ikey, vals):
+        merged = super(KVStoreDevice, self)._reduce(ikey, vals)
+        if self.num_workers > 1 and isinstance(merged, NDArray):
+            t = merged._t.clone() if merged is vals[0] else merged._t
+            self._dist.all_reduce(t)
+            merged = NDArray(t, merged.context)
+        return merged
+
+    def _barrier(self):
+        if self.num_workers > 1:
+            self._dist.barrier()
+
+    def _membership_change_barrier(self, env):
+        from ..parallel import membership
+        return membership.process_group_membership_barrier(self, env)
+
+
+def create(name="local"):
+    """mx.kv.create (python/mxnet/kvstore.py:645-688; type parsing as in src/kvstore/kvstore.cc:40-77)."""
+    if not isinstance(name, str):
+        raise TypeError("name must be a string")
+    if "dist" in name:
+        from .dist import KVStoreDist
+        return KVStoreDist(name)
+    if "device" in name or "nccl" in name:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return KVStoreDevice(name)
+        return KVStoreLocal(name)
+    if name.startswith("local"):
+        return KVStoreLocal(name)
+    raise MXNetError("Unknown KVStore type \"%s\"" % name)

@@ -10,10 +10,23 @@ from .sparse import RowSparseNDArray, CSRNDArray, BaseSparseNDArray, cast_storag
 from .op import *  # noqa: F401,F403
 from .op import _REG as _OPS
 
+import functools as _functools
+
+
+def _strip_sym_kwargs(f):
+    """Ops accept (and ignore) the symbolic-only ``name=`` / ``attr=`` kwargs so HybridBlocks can pass them."""
+    @_functools.wraps(f)
+    def g(*a, **k):
+        k.pop("name", None)
+        k.pop("attr", None)
+        return f(*a, **k)
+    return g
+
+
 _this = _sys.modules[__name__]
-for _k, _v in _OPS.items():
-    if not hasattr(_this, _k) or _k in ("sum", "max", "min", "abs", "round", "slice"):
-        setattr(_this, _k, _v)
+for _k in list(_OPS.keys()):
+    _OPS[_k] = _strip_sym_kwargs(_OPS[_k])
+    setattr(_this, _k, _OPS[_k])
 # creation functions win over same-named elementwise ops
 zeros_like = ndarray.zeros_like
 ones_like = ndarray.ones_like
