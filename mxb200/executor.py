@@ -1,0 +1,171 @@
+"""Executor: a Symbol bound to argument / gradient / aux arrays on one context
+(reference: python/mxnet/executor.py, src/executor/graph_executor.cc).
+
+forward() evaluates the graph with the shared op registry under the autograd scope; backward() runs torch
+autograd from the outputs (loss ops such as SoftmaxOutput ignore head gradients exactly like the
+reference).  Memory planning / bulk segments of GraphExecutor are unnecessary here: torch's caching
+allocator and stream ordering play that role.
+"""
+import numpy as np
+import torch
+
+from .base import MXNetError
+from .context import Context, cpu
+from . import ndarray as nd
+from .ndarray import NDArray
+from . import autograd
+
+__all__ = ["Executor"]
+
+
+class Executor(object):
+    def __init__(self, symbol, ctx, args, args_grad=None, grad_req="write", aux_states=None, group2ctx=None):
+        self._symbol = symbol
+        self._ctx = ctx if isinstance(ctx, Context) else cpu()
+        self._group2ctx = group2ctx
+        arg_names = symbol.list_arguments()
+        aux_names = symbol.list_auxiliary_states()
+        if isinstance(args, dict):
+            self.arg_dict = {n: args[n] for n in arg_names}
+        else:
+            assert len(args) == len(arg_names), "Length of args does not match the number of arguments"
+            self.arg_dict = dict(zip(arg_names, args))
+        if aux_states is None:
+            aux_states = {}
+        if isinstance(aux_states, dict):
+            self.aux_dict = {n: aux_states[n] for n in aux_names}
+        else:
+            self.aux_dict = dict(zip(aux_names, aux_states))
+        if isinstance(grad_req, str):
+            self._grad_req = {n: grad_req for n in arg_names}
+        elif isinstance(grad_req, (list, tuple)):
+            self._grad_req = dict(zip(arg_names, grad_req))
+        else:
+            self._grad_req = {n: grad_req.get(n, "null") for n in arg_names}
+        if args_grad is None:
+            args_grad = {}
+        if not isinstance(args_grad, dict):
+            args_grad = dict(zip(arg_names, args_grad))
+        self.grad_dict = {}
+        for n in arg_names:
+            req = self._grad_req.get(n, "null")
+            if req == "null" or (args_grad.get(n) is None and n not in args_grad and False):
+                continue
+            a = self.arg_dict[n]
+            if not a._t.is_floating_point():
+                self._grad_req[n] = "null"
+                continue
+            a.attach_grad(req)
+            g = args_grad.get(n)
+            if g is not None:
+                a._t.grad = g._t
+                self.grad_dict[n] = g
+            else:
+                self.grad_dict[n] = NDArray(a._t.grad, a.context)
+        self.arg_arrays = [self.arg_dict[n] for n in arg_names]
+        self.grad_arrays = [self.grad_dict.get(n) for n in arg_names]
+        self.aux_arrays = [self.aux_dict[n] for n in aux_names]
+        self.outputs = []
+        self._output_names = symbol.list_outputs()
+        self._monitor_callback = None
+
+    @property
+    def output_dict(self):
+        return dict(zip(self._output_names, self.outputs))
+
+    @staticmethod
+    def simple_bind(symbol, ctx, grad_req="write", type_dict=None, group2ctx=None, shapes=None):
+        shapes = shapes or {}
+        type_dict = type_dict or {}
+        vshape, _out, vdtype, _ = symbol._infer(shapes, type_dict)
+        args, aux = {}, {}
+        for n in symbol.list_arguments():
+            if n not in vshape:
+                raise MXNetError("simple_bind: cannot infer shape of argument %s" % n)
+            args[n] = nd.zeros(vshape[n], ctx=ctx, dtype=type_dict.get(n, vdtype.get(n, "float32")))
+        for n in symbol.list_auxiliary_states():
+            aux[n] = nd.zeros(vshape[n], ctx=ctx, dtype="float32")
+        if isinstance(grad_req, str):
+            req = {n: ("null" if n in shapes and grad_req != "null" and False else grad_req) for n in args}
+        else:
+            req = grad_req
+        return Executor(symbol, ctx, args, None, req, aux, group2ctx)
+
+    def forward(self, is_train=False, **kwargs):
+        for name, array in kwargs.items():
+            if name not in self.arg_dict:
+                raise TypeError("Unknown argument %s" % name)
+            if not isinstance(array, NDArray):
+                array = nd.array(array, ctx=self._ctx)
+            if self.arg_dict[name].shape == array.shape:
+                self.arg_dict[name][:] = array
+            else:
+                raise ValueError("Shape not match! Argument %s, need: %s, received: %s" % (
+                    name, str(self.arg_dict[name].shape), str(array.shape)))
+        feed = dict(self.arg_dict)
+        feed.update(self.aux_dict)
+        if is_train:
+            with autograd.record(train_mode=True):
+                self.outputs = self._symbol.eval_nd(feed)
+        else:
+            with autograd.pause(train_mode=False):
+                self.outputs = self._symbol.eval_nd(feed)
+        if self._monitor_callback is not None:
+            for name, out in zip(self._output_names, self.outputs):
+                self._monitor_callback(name, out)
+        return self.outputs
+
+    def backward(self, out_grads=None, is_train=True):
+        if out_grads is None:
+            out_grads = []
+        elif isinstance(out_grads, NDArray):
+            out_grads = [out_grads]
+        elif isinstance(out_grads, dict):
+            out_grads = [out_grads[k] for k in self._output_names]
+        heads, hgrads = [], []
+        for i, o in enumerate(self.outputs):
+            if not o._t.requires_grad:
+                continue
+            heads.append(o)
+            hgrads.append(out_grads[i] if i < len(out_grads) else None)
+        if heads:
+            autograd.backward(heads, hgrads)
+        # keep grad handles pointing at the live tensors
+        for n, g in self.grad_dict.items():
+            live = self.arg_dict[n]._t.grad
+            if live is not None and live is not g._t:
+                g._t = live
+
+    def set_monitor_callback(self, callback):
+        self._monitor_callback = callback
+
+    def copy_params_from(self, arg_params, aux_params=None, allow_extra_params=False):
+        for name, array in arg_params.items():
+            if name in self.arg_dict:
+                dst = self.arg_dict[name]
+                with torch.no_grad():
+                    dst._t.copy_(array._t.to(dst._t.dtype))
+            elif not allow_extra_params:
+                raise ValueError("Find name \"%s\" that is not in the arguments" % name)
+        if aux_params is None:
+            return
+        for name, array in aux_params.items():
+            if name in self.aux_dict:
+                dst = self.aux_dict[name]
+                with torch.no_grad():
+                    dst._t.copy_(array._t.to(dst._t.dtype))
+            elif not allow_extra_params:
+                raise ValueError("Find name %s that is not in the auxiliary states" % name)
+
+    def reshape(self, partial_shaping=False, allow_up_sizing=False, **kwargs):
+        vshape, _o, vdtype, _ = self._symbol._infer(kwargs)
+        new_args, new_aux = {}, {}
+        for n, a in self.arg_dict.items():
+            shp = vshape.get(n, a.shape)
+            new_args[n] = a if tuple(shp) == a.shape else nd.zeros(shp, ctx=self._ctx, dtype=a.dtype)
+        for n, a in self.aux_dict.items():
+            new_aux[n] = a
+        return Executor(self._symbol, self._ctx, new_args, None, self._grad_req, new_aux, self._group2ctx)
+
+    def debug_str(self):
+        return self._symbol.tojson()

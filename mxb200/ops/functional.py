@@ -134,7 +134,7 @@ def linear(x, w, b=None, relu=False):
         return _LinearFn.apply(x, w, b, relu)
     if x.is_cuda and not N.have_cuda_kernels():
         raise RuntimeError("mxb200: CUDA kernels library missing on a GPU host")
-    y = F.linear(x, w, b)
+    y = F.linear(x, w.to(x.dtype) if w.dtype != x.dtype else w, b.to(x.dtype) if b is not None and b.dtype != x.dtype else b)
     return torch.relu(y) if relu else y
 
 

@@ -1,0 +1,655 @@
+"""Symbolic graph API (reference: python/mxnet/symbol/symbol.py, 3rdparty/tvm/nnvm graph IR + passes).
+
+A ``Symbol`` is a list of output entries of a small DAG of op nodes.  Ops are the same functions as in
+``mx.nd`` (one registry), so the graph is *executed* by running those functions in topological order on
+NDArrays (``eval_nd`` / ``Executor``) with torch autograd providing gradients -- replacing the reference's
+NNVM gradient / PlanMemory / bulk-exec passes (src/executor/graph_executor.cc).  Shape/type inference runs
+the graph on ``meta`` tensors after filling in parameter shapes with per-op rules (FullyConnected,
+Convolution, BatchNorm, ...), the counterpart of infer_shape_type.cc.  ``tojson`` writes the NNVM JSON layout
+(nodes / arg_nodes / node_row_ptr / heads) so ``-symbol.json`` checkpoints round-trip.
+"""
+import copy
+import json
+import threading
+
+import numpy as np
+import torch
+
+from ..base import MXNetError, torch_dtype, np_dtype, dtype_name
+from ..context import cpu, Context
+from .. import ndarray as nd
+from ..ndarray import NDArray
+from ..ndarray import op as _ndop
+from .. import autograd
+
+__all__ = ["Symbol", "var", "Variable", "Group", "load", "load_json", "zeros", "ones"]
+
+# ops that own parameters: op -> (list of (arg_name, is_aux)), created as variables when not passed explicitly
+_PARAM_ARGS = {
+    "FullyConnected": [("weight", False), ("bias", False)],
+    "Convolution": [("weight", False), ("bias", False)],
+    "Deconvolution": [("weight", False), ("bias", False)],
+    "BatchNorm": [("gamma", False), ("beta", False), ("moving_mean", True), ("moving_var", True)],
+    "LayerNorm": [("gamma", False), ("beta", False)],
+    "InstanceNorm": [("gamma", False), ("beta", False)],
+    "Embedding": [("weight", False)],
+    "LeakyReLU": [("gamma", False)],
+}
+_LABEL_OPS = {"SoftmaxOutput": "label", "Softmax": "label", "LinearRegressionOutput": "label",
+              "LogisticRegressionOutput": "label", "MAERegressionOutput": "label", "SVMOutput": "label"}
+_MULTI_OUT = {"split": "num_outputs", "SliceChannel": "num_outputs"}
+
+
+class _NameManager(object):
+    _tl = threading.local()
+
+    @classmethod
+    def get(cls, hint):
+        if not hasattr(cls._tl, "counter"):
+            cls._tl.counter = {}
+        c = cls._tl.counter
+        n = c.get(hint, 0)
+        c[hint] = n + 1
+        return "%s%d" % (hint, n)
+
+    @classmethod
+    def prefix(cls):
+        from ..gluon.block import _BlockScope
+        cur = getattr(_BlockScope._current, "value", None)
+        return cur._block.prefix if cur is not None else ""
+
+
+class _Node(object):
+    __slots__ = ("op", "name", "attrs", "inputs", "is_aux", "num_outputs", "var_attrs")
+
+    def __init__(self, op, name, attrs=None, inputs=None, num_outputs=1):
+        self.op = op            # None for variables
+        self.name = name
+        self.attrs = attrs or {}
+        self.inputs = inputs or []      # list of (node, out_index)
+        self.is_aux = False
+        self.num_outputs = num_outputs
+        self.var_attrs = {}
+
+
+class Symbol(object):
+    def __init__(self, outputs):
+        self._outputs = list(outputs)   # list of (node, index)
+
+    # ---- composition helpers -------------------------------------------------------------------
+    @property
+    def name(self):
+        if len(self._outputs) != 1:
+            return None
+        return self._outputs[0][0].name
+
+    def __repr__(self):
+        if len(self._outputs) == 1:
+            return "<Symbol %s>" % self.name
+        return "<Symbol group [%s]>" % ", ".join(n.name for n, _ in self._outputs)
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self._outputs)))
+
+    def __len__(self):
+        return len(self._outputs)
+
+    def __getitem__(self, index):
+        if isinstance(index, str):
+            names = self.list_outputs()
+            idx = [i for i, n in enumerate(names) if n == index]
+            if len(idx) != 1:
+                raise ValueError('There are multiple outputs with name "%s"' % index if idx else "Cannot find output %s" % index)
+            index = idx[0]
+        if isinstance(index, slice):
+            return Symbol(self._outputs[index])
+        return Symbol([self._outputs[index]])
+
+    def _topo(self):
+        order, seen = [], set()
+
+        def visit(node):
+            if id(node) in seen:
+                return
+            seen.add(id(node))
+            for inp, _ in node.inputs:
+                visit(inp)
+            order.append(node)
+        import sys
+        sys.setrecursionlimit(max(10000, sys.getrecursionlimit()))
+        for n, _ in self._outputs:
+            visit(n)
+        return order
+
+    def list_arguments(self):
+        return [n.name for n in self._topo() if n.op is None and not n.is_aux]
+
+    def list_auxiliary_states(self):
+        return [n.name for n in self._topo() if n.op is None and n.is_aux]
+
+    def list_inputs(self):
+        return [n.name for n in self._topo() if n.op is None]
+
+    def list_outputs(self):
+        out = []
+        for n, i in self._outputs:
+            if n.op is None:
+                out.append(n.name)
+            elif n.num_outputs > 1:
+                out.append("%s_output%d" % (n.name, i))
+            else:
+                out.append("%s_output" % n.name)
+        return out
+
+    def get_internals(self):
+        outs = []
+        for n in self._topo():
+            for i in range(n.num_outputs):
+                outs.append((n, i))
+        return Symbol(outs)
+
+    def get_children(self):
+        if len(self._outputs) != 1:
+            return None
+        inputs = self._outputs[0][0].inputs
+        return Symbol(inputs) if inputs else None
+
+    def attr(self, key):
+        n = self._outputs[0][0]
+        v = n.var_attrs.get(key, n.attrs.get(key))
+        return str(v) if v is not None else None
+
+    def list_attr(self):
+        n = self._outputs[0][0]
+        d = {k: str(v) for k, v in n.attrs.items()}
+        d.update({k: str(v) for k, v in n.var_attrs.items()})
+        return d
+
+    def attr_dict(self):
+        ret = {}
+        for n in self._topo():
+            d = {k: str(v) for k, v in n.attrs.items()}
+            d.update({k: str(v) for k, v in n.var_attrs.items()})
+            if d:
+                ret[n.name] = d
+        return ret
+
+    def _set_attr(self, **kwargs):
+        self._outputs[0][0].var_attrs.update(kwargs)
+
+    # ---- arithmetic ------------------------------------------------------------------------------
+    def _bin(self, other, op, scalar_op, rev=False):
+        if isinstance(other, Symbol):
+            a, b = (other, self) if rev else (self, other)
+            return _make_op(op, [a, b], {})
+        return _make_op(scalar_op, [self], {"scalar": float(other), "reverse": rev})
+
+    def __add__(self, o):
+        return self._bin(o, "broadcast_add", "_plus_scalar")
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self._bin(o, "broadcast_sub", "_minus_scalar")
+
+    def __rsub__(self, o):
+        return self._bin(o, "broadcast_sub", "_minus_scalar", rev=True)
+
+    def __mul__(self, o):
+        return self._bin(o, "broadcast_mul", "_mul_scalar")
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        return self._bin(o, "broadcast_div", "_div_scalar")
+
+    def __rtruediv__(self, o):
+        return self._bin(o, "broadcast_div", "_div_scalar", rev=True)
+
+    __div__, __rdiv__ = __truediv__, __rtruediv__
+
+    def __pow__(self, o):
+        return self._bin(o, "broadcast_power", "_power_scalar")
+
+    def __neg__(self):
+        return self * -1.0
+
+    def __gt__(self, o):
+        return self._bin(o, "broadcast_greater", "_greater_scalar")
+
+    def __lt__(self, o):
+        return self._bin(o, "broadcast_lesser", "_lesser_scalar")
+
+    def __eq__(self, o):
+        if isinstance(o, (Symbol, int, float)):
+            return self._bin(o, "broadcast_equal", "_equal_scalar")
+        return NotImplemented
+
+    __hash__ = object.__hash__
+
+    def __getattr__(self, name):
+        # method forms: sym.reshape(...), sym.sum(...), ...
+        if name.startswith("_"):
+            raise AttributeError(name)
+        from . import _lookup_op
+        fn = _lookup_op(name)
+        if fn is None:
+            raise AttributeError("Symbol has no attribute %r" % name)
+        return lambda *a, **k: fn(self, *a, **k)
+
+    def reshape(self, *shape, **kwargs):
+        if len(shape) == 1 and isinstance(shape[0], (list, tuple)):
+            shape = tuple(shape[0])
+        if not shape:
+            shape = tuple(kwargs["shape"])
+        return _make_op("reshape", [self], {"shape": tuple(shape)})
+
+    # ---- inference -------------------------------------------------------------------------------
+    def _infer(self, shapes, dtypes=None, partial=False):
+        """Returns ({var_name: shape}, [out shapes], {var_name: dtype}, [out dtypes])."""
+        shapes = {k: tuple(v) for k, v in shapes.items() if v is not None}
+        dtypes = dict(dtypes or {})
+        vals = {}
+        vshape, vdtype = {}, {}
+        order = self._topo()
+        for node in order:
+            if node.op is None:
+                shp = shapes.get(node.name)
+                if shp is None and "__shape__" in node.var_attrs:
+                    s = tuple(node.var_attrs["__shape__"])
+                    shp = s if all(d > 0 for d in s) else None
+                dt = dtypes.get(node.name, node.var_attrs.get("__dtype__", "float32"))
+                if shp is not None:
+                    vals[(id(node), 0)] = torch.empty(shp, dtype=torch_dtype(dt), device="meta")
+                    vshape[node.name] = shp
+                vdtype[node.name] = dt
+                continue
+            # fill parameter shapes from the data shape
+            _infer_param_shapes(node, vals, vshape, vdtype)
+            ins = []
+            missing = False
+            for inp, idx in node.inputs:
+                t = vals.get((id(inp), idx))
+                if t is None:
+                    missing = True
+                    break
+                ins.append(t)
+            if missing:
+                if partial:
+                    continue
+                unknown = [inp.name for inp, idx in node.inputs if (id(inp), idx) not in vals]
+                raise MXNetError("infer_shape: cannot infer shape of inputs %s of node %s" % (unknown, node.name))
+            outs = _run_node(node, ins, meta=True)
+            for i, o in enumerate(outs):
+                vals[(id(node), i)] = o
+        out_shapes, out_types = [], []
+        for n, i in self._outputs:
+            t = vals.get((id(n), i))
+            out_shapes.append(tuple(t.shape) if t is not None else None)
+            out_types.append(np_dtype(t.dtype) if t is not None else None)
+        return vshape, out_shapes, vdtype, out_types
+
+    def infer_shape(self, *args, **kwargs):
+        if args:
+            kwargs = dict(zip(self.list_arguments(), args))
+        vshape, out_shapes, _, _ = self._infer(kwargs)
+        arg_shapes = [vshape.get(n) for n in self.list_arguments()]
+        aux_shapes = [vshape.get(n) for n in self.list_auxiliary_states()]
+        return arg_shapes, out_shapes, aux_shapes
+
+    def infer_shape_partial(self, *args, **kwargs):
+        if args:
+            kwargs = dict(zip(self.list_arguments(), args))
+        vshape, _out, _, _ = self._infer(kwargs, partial=True)
+        return vshape
+
+    def infer_type(self, *args, **kwargs):
+        if args:
+            kwargs = dict(zip(self.list_arguments(), args))
+        names = self.list_arguments()
+        dt = {k: v for k, v in kwargs.items() if v is not None}
+        default = list(dt.values())[0] if dt else np.float32
+        arg_types = [np_dtype(torch_dtype(dt.get(n, default))) for n in names]
+        aux_types = [np.float32 for _ in self.list_auxiliary_states()]
+        return arg_types, [arg_types[0] if arg_types else np.float32 for _ in self._outputs], aux_types
+
+    # ---- execution ---------------------------------------------------------------------------------
+    def eval_nd(self, feed):
+        """Run the graph on NDArrays: feed maps variable name -> NDArray.  Returns list of outputs."""
+        vals = {}
+        for node in self._topo():
+            if node.op is None:
+                if node.name not in feed:
+                    raise MXNetError("eval: missing input %s" % node.name)
+                vals[(id(node), 0)] = feed[node.name]
+                continue
+            ins = [vals[(id(inp), idx)] for inp, idx in node.inputs]
+            outs = _run_node(node, ins, meta=False)
+            for i, o in enumerate(outs):
+                vals[(id(node), i)] = o
+        return [vals[(id(n), i)] for n, i in self._outputs]
+
+    def eval(self, ctx=None, **kwargs):
+        return self.eval_nd(kwargs)
+
+    def simple_bind(self, ctx, grad_req="write", type_dict=None, stype_dict=None, group2ctx=None, shared_arg_names=None,
+                    shared_exec=None, shared_buffer=None, **kwargs):
+        from ..executor import Executor
+        return Executor.simple_bind(self, ctx, grad_req, type_dict, group2ctx, kwargs)
+
+    def bind(self, ctx, args, args_grad=None, grad_req="write", aux_states=None, group2ctx=None, shared_exec=None):
+        from ..executor import Executor
+        return Executor(self, ctx, args, args_grad, grad_req, aux_states, group2ctx)
+
+    # ---- serialization --------------------------------------------------------------------------------
+    def tojson(self):
+        order = self._topo()
+        index = {id(n): i for i, n in enumerate(order)}
+        nodes, arg_nodes, row_ptr = [], [], [0]
+        for i, n in enumerate(order):
+            d = {"op": "null" if n.op is None else n.op, "name": n.name,
+                 "inputs": [[index[id(inp)], idx, 0] for inp, idx in n.inputs]}
+            attrs = {k: _attr_str(v) for k, v in n.attrs.items()}
+            attrs.update({k: _attr_str(v) for k, v in n.var_attrs.items()})
+            if n.op is None and n.is_aux:
+                attrs["__is_aux__"] = "1"
+            if attrs:
+                d["attrs"] = attrs
+            nodes.append(d)
+            if n.op is None:
+                arg_nodes.append(i)
+            row_ptr.append(row_ptr[-1] + n.num_outputs)
+        heads = [[index[id(n)], i, 0] for n, i in self._outputs]
+        return json.dumps({"nodes": nodes, "arg_nodes": arg_nodes, "node_row_ptr": row_ptr, "heads": heads,
+                           "attrs": {"mxnet_version": ["int", 10301], "framework": ["str", "mxb200"]}}, indent=2)
+
+    def save(self, fname):
+        with open(fname, "w") as f:
+            f.write(self.tojson())
+
+    def __deepcopy__(self, memo):
+        return load_json(self.tojson())
+
+    def __getstate__(self):
+        return {"json": self.tojson()}
+
+    def __setstate__(self, state):
+        self._outputs = load_json(state["json"])._outputs
+
+
+def _attr_str(v):
+    if isinstance(v, (tuple, list)):
+        return "(" + ", ".join(str(x) for x in v) + ")"
+    return str(v)
+
+
+def _parse_attr(s):
+    if not isinstance(s, str):
+        return s
+    t = s.strip()
+    if t in ("True", "true"):
+        return True
+    if t in ("False", "false"):
+        return False
+    if t == "None":
+        return None
+    if t.startswith("(") or t.startswith("["):
+        inner = t[1:-1].strip()
+        if not inner:
+            return ()
+        return tuple(_parse_attr(x) for x in inner.split(",") if x.strip() != "")
+    try:
+        return int(t)
+    except ValueError:
+        pass
+    try:
+        return float(t)
+    except ValueError:
+        return s
+
+
+def load_json(json_str):
+    g = json.loads(json_str)
+    nodes = []
+    for d in g["nodes"]:
+        attrs = d.get("attrs", d.get("attr", d.get("param", {}))) or {}
+        if d["op"] == "null":
+            n = _Node(None, d["name"])
+            n.is_aux = attrs.get("__is_aux__") == "1"
+            n.var_attrs = {k: _parse_attr(v) if k in ("__shape__",) else v for k, v in attrs.items() if k != "__is_aux__"}
+        else:
+            n = _Node(d["op"], d["name"], {k: _parse_attr(v) for k, v in attrs.items() if not k.startswith("__")})
+            n.var_attrs = {k: v for k, v in attrs.items() if k.startswith("__")}
+        nodes.append(n)
+    for n, d in zip(nodes, g["nodes"]):
+        n.inputs = [(nodes[i[0]], i[1]) for i in d["inputs"]]
+        if n.op in _MULTI_OUT:
+            n.num_outputs = int(n.attrs.get(_MULTI_OUT[n.op], 1))
+        # legacy graphs: aux inputs of BatchNorm are variables named *moving_*
+        if n.op == "BatchNorm":
+            for inp, _ in n.inputs[3:5]:
+                inp.is_aux = True
+    return Symbol([(nodes[h[0]], h[1]) for h in g["heads"]])
+
+
+def load(fname):
+    with open(fname) as f:
+        return load_json(f.read())
+
+
+def var(name, attr=None, shape=None, lr_mult=None, wd_mult=None, dtype=None, init=None, stype=None, **kwargs):
+    if not isinstance(name, str):
+        raise TypeError("Expect a string for variable `name`")
+    n = _Node(None, name)
+    a = dict(attr or {})
+    if shape is not None:
+        a["__shape__"] = tuple(shape)
+    if lr_mult is not None:
+        a["__lr_mult__"] = lr_mult
+    if wd_mult is not None:
+        a["__wd_mult__"] = wd_mult
+    if dtype is not None:
+        a["__dtype__"] = dtype_name(dtype)
+    if init is not None:
+        a["__init__"] = init if isinstance(init, str) else init.dumps()
+    for k, v in kwargs.items():
+        if k.startswith("__") and k.endswith("__"):
+            a[k] = str(v)
+    n.var_attrs = a
+    return Symbol([(n, 0)])
+
+
+Variable = var
+
+
+def Group(symbols):
+    outs = []
+    for s in symbols:
+        outs.extend(s._outputs)
+    return Symbol(outs)
+
+
+def zeros(shape, dtype=None, **kwargs):
+    return _make_op("_zeros", [], {"shape": tuple(shape), "dtype": dtype_name(dtype or "float32")})
+
+
+def ones(shape, dtype=None, **kwargs):
+    return _make_op("_ones", [], {"shape": tuple(shape), "dtype": dtype_name(dtype or "float32")})
+
+
+def _make_op(op, inputs, attrs, name=None, hint=None):
+    hint = hint or op.lower().lstrip("_")
+    name = _NameManager.prefix() + (name if name else _NameManager.get(hint))
+    nout = int(attrs.get(_MULTI_OUT[op], 1)) if op in _MULTI_OUT else 1
+    node = _Node(op, name, attrs, [s._outputs[0] for s in inputs], nout)
+    return Symbol([(node, i) for i in range(nout)]) if nout > 1 else Symbol([(node, 0)])
+
+
+def _create(op, args, kwargs):
+    """mx.sym.<op>(*args, **kwargs): Symbol inputs become graph edges, the rest become attributes; parameter
+    variables (weight/bias/gamma/...) and label variables are auto-created with the reference naming."""
+    name = kwargs.pop("name", None)
+    kwargs.pop("attr", None)
+    sym_kwargs = {k: v for k, v in kwargs.items() if isinstance(v, Symbol)}
+    attrs = {k: v for k, v in kwargs.items() if not isinstance(v, Symbol) and v is not None}
+    hint = op.lower().lstrip("_")
+    node_name = _NameManager.prefix() + (name if name else _NameManager.get(hint))
+    inputs = [a for a in args if isinstance(a, Symbol)]
+    pos_attrs = [a for a in args if not isinstance(a, Symbol) and a is not None]
+    if pos_attrs:
+        # positional non-symbol args (e.g. nd-style clip(x, a_min, a_max)) -> named by the nd op signature
+        import inspect
+        fn = _ndop.get(op)
+        if fn is not None:
+            params = [p for p in inspect.signature(fn).parameters.values() if p.kind in (p.POSITIONAL_OR_KEYWORD,)]
+            names = [p.name for p in params]
+            k = 0
+            for a, pname in zip(args, names):
+                if not isinstance(a, Symbol) and a is not None:
+                    attrs[pname] = a
+    order = []
+    if op in _PARAM_ARGS or op in _LABEL_OPS:
+        spec = [("data", False)] + _PARAM_ARGS.get(op, [])
+        if op in _LABEL_OPS:
+            spec = spec + [(_LABEL_OPS[op], False)]
+        provided = list(inputs)
+        for i, (aname, is_aux) in enumerate(spec):
+            if aname in sym_kwargs:
+                s = sym_kwargs[aname]
+            elif provided:
+                s = provided.pop(0)
+            else:
+                if aname == "bias" and attrs.get("no_bias", False):
+                    continue
+                if aname == "gamma" and op == "LeakyReLU" and attrs.get("act_type", "leaky") != "prelu":
+                    continue
+                if aname == "data":
+                    raise MXNetError("%s: missing data input" % op)
+                s = var("%s_%s" % (node_name, aname))
+                if is_aux:
+                    s._outputs[0][0].is_aux = True
+            if is_aux:
+                s._outputs[0][0].is_aux = True
+            order.append(s)
+    else:
+        order = inputs + [sym_kwargs[k] for k in sym_kwargs]
+        if sym_kwargs:
+            attrs["__kwarg_inputs__"] = tuple(sym_kwargs.keys())
+    nout = int(attrs.get(_MULTI_OUT[op], 1)) if op in _MULTI_OUT else 1
+    node = _Node(op, node_name, attrs, [s._outputs[0] for s in order], nout)
+    return Symbol([(node, i) for i in range(nout)]) if nout > 1 else Symbol([(node, 0)])
+
+
+_SCALAR_OPS = {
+    "_plus_scalar": lambda x, s, rev: x + s, "_minus_scalar": lambda x, s, rev: (s - x) if rev else (x - s),
+    "_mul_scalar": lambda x, s, rev: x * s, "_div_scalar": lambda x, s, rev: (s / x) if rev else (x / s),
+    "_power_scalar": lambda x, s, rev: (s ** x) if rev else (x ** s),
+    "_greater_scalar": lambda x, s, rev: x > s, "_lesser_scalar": lambda x, s, rev: x < s,
+    "_equal_scalar": lambda x, s, rev: x == s,
+}
+
+
+def _run_node(node, ins, meta):
+    """Execute one node.  meta=True: ins are meta tensors (shape inference); else NDArrays."""
+    op, attrs = node.op, dict(node.attrs)
+    kw_inputs = attrs.pop("__kwarg_inputs__", None)
+    if meta:
+        ins = [NDArray(t, cpu()) for t in ins]
+    if op in _SCALAR_OPS:
+        out = _SCALAR_OPS[op](ins[0], attrs["scalar"], attrs.get("reverse", False))
+    elif op == "_zeros":
+        out = nd.zeros(attrs["shape"], dtype=attrs.get("dtype"))
+    elif op == "_ones":
+        out = nd.ones(attrs["shape"], dtype=attrs.get("dtype"))
+    else:
+        fn = _ndop.get(op)
+        if fn is None:
+            raise MXNetError("operator %s is not registered" % op)
+        if op in _PARAM_ARGS or op in _LABEL_OPS:
+            spec = ["data"] + [a for a, _ in _PARAM_ARGS.get(op, [])]
+            if op in _LABEL_OPS:
+                spec.append(_LABEL_OPS[op])
+            present = []
+            for aname in spec:
+                if aname == "bias" and attrs.get("no_bias", False):
+                    continue
+                if aname == "gamma" and op == "LeakyReLU" and attrs.get("act_type", "leaky") != "prelu":
+                    continue
+                present.append(aname)
+            kwargs = dict(zip(present, ins))
+            data = kwargs.pop("data")
+            if meta and op in _LABEL_OPS:
+                kwargs.pop(_LABEL_OPS[op], None)
+                out = data if op not in ("SoftmaxOutput", "Softmax") else data
+            else:
+                out = fn(data, **kwargs, **attrs)
+        elif kw_inputs:
+            npos = len(ins) - len(kw_inputs)
+            out = fn(*ins[:npos], **dict(zip(kw_inputs, ins[npos:])), **attrs)
+        else:
+            out = fn(*ins, **attrs)
+    outs = list(out) if isinstance(out, (list, tuple)) else [out]
+    if meta:
+        return [o._t for o in outs]
+    return outs
+
+
+def _infer_param_shapes(node, vals, vshape, vdtype):
+    """Fill shapes of parameter/label variables feeding ``node`` from its data input (infer_shape rules)."""
+    op = node.op
+    if op not in _PARAM_ARGS and op not in _LABEL_OPS:
+        return
+    a = node.attrs
+    data = vals.get((id(node.inputs[0][0]), node.inputs[0][1])) if node.inputs else None
+    if data is None:
+        return
+    ds = tuple(data.shape)
+    spec = ["data"] + [x for x, _ in _PARAM_ARGS.get(op, [])]
+    if op in _LABEL_OPS:
+        spec.append(_LABEL_OPS[op])
+    present = []
+    for aname in spec:
+        if aname == "bias" and a.get("no_bias", False):
+            continue
+        if aname == "gamma" and op == "LeakyReLU" and a.get("act_type", "leaky") != "prelu":
+            continue
+        present.append(aname)
+
+    def rule(aname):
+        if op == "FullyConnected":
+            nh = int(a["num_hidden"])
+            inn = int(np.prod(ds[1:])) if a.get("flatten", True) else ds[-1]
+            return {"weight": (nh, inn), "bias": (nh,)}[aname]
+        if op == "Convolution":
+            k = tuple(a["kernel"]) if not isinstance(a["kernel"], int) else (a["kernel"],) * (len(ds) - 2)
+            nf, g = int(a["num_filter"]), int(a.get("num_group", 1))
+            return {"weight": (nf, ds[1] // g) + k, "bias": (nf,)}[aname]
+        if op == "Deconvolution":
+            k = tuple(a["kernel"]) if not isinstance(a["kernel"], int) else (a["kernel"],) * (len(ds) - 2)
+            nf, g = int(a["num_filter"]), int(a.get("num_group", 1))
+            return {"weight": (ds[1], nf // g) + k, "bias": (nf,)}[aname]
+        if op in ("BatchNorm", "InstanceNorm"):
+            return (ds[int(a.get("axis", 1))],)
+        if op == "LayerNorm":
+            return (ds[int(a.get("axis", -1))],)
+        if op == "Embedding":
+            return (int(a["input_dim"]), int(a["output_dim"]))
+        if op == "LeakyReLU":
+            return (ds[1],)
+        if aname == "label":
+            if op in ("SoftmaxOutput", "Softmax"):
+                if a.get("multi_output", False):
+                    return (ds[0],) + ds[2:]
+                return (ds[0],)
+            return ds
+        return None
+    for (inp, idx), aname in zip(node.inputs, present):
+        if inp.op is None and (id(inp), idx) not in vals and aname != "data":
+            shp = rule(aname)
+            if shp is not None:
+                dt = vdtype.get(inp.name, inp.var_attrs.get("__dtype__", "float32"))
+                if aname not in ("label",) and op not in ("BatchNorm",):
+                    dt = dtype_name(data.dtype) if inp.var_attrs.get("__dtype__") is None else dt
+                vals[(id(inp), idx)] = torch.empty(shp, dtype=torch_dtype(dt), device="meta")
+                vshape[inp.name] = tuple(shp)
+                vdtype[inp.name] = dt
