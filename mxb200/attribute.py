@@ -1,0 +1,32 @@
+"""Attribute scope (reference: python/mxnet/attribute.py)."""
+import threading
+
+
+class AttrScope(object):
+    _current = threading.local()
+
+    def __init__(self, **kwargs):
+        self._old_scope = None
+        for value in kwargs.values():
+            if not isinstance(value, str):
+                raise ValueError("Attributes need to be string")
+        self._attr = kwargs
+
+    def get(self, attr):
+        if self._attr:
+            ret = self._attr.copy()
+            if attr:
+                ret.update(attr)
+            return ret
+        return attr if attr else {}
+
+    def __enter__(self):
+        self._old_scope = getattr(AttrScope._current, "value", None)
+        attr = (self._old_scope._attr.copy() if self._old_scope else {})
+        attr.update(self._attr)
+        self._attr = attr
+        AttrScope._current.value = self
+        return self
+
+    def __exit__(self, *a):
+        AttrScope._current.value = self._old_scope

@@ -568,7 +568,7 @@ def array(source, ctx=None, dtype=None):
         if not isinstance(source, np.ndarray):
             dtype = np.float32
     td = torch_dtype(dtype)
-    t = torch.from_numpy(np.ascontiguousarray(a)).to(td)
+    t = torch.from_numpy(np.array(a, copy=True, order="C")).to(td)   # always own the memory (never alias numpy)
     if t.dim() == 0:
         t = t.reshape(1)
     return NDArray(_pin_if(t.to(ctx.torch_device), ctx), ctx)

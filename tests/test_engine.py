@@ -1,0 +1,96 @@
+"""Dependency engine: randomized read/write workloads must equal serial execution; waits, stop/start,
+exception propagation (reference tests: tests/cpp/engine/threaded_engine_test.cc:46-353, test_exc_handling.py)."""
+import random
+import threading
+import time
+
+import pytest
+
+import mxb200 as mx
+from mxb200.engine import Engine
+
+
+@pytest.mark.parametrize("kind", ["ThreadedEngine", "NaiveEngine"])
+def test_random_workload_equals_serial(kind):
+    eng = Engine(kind=kind, num_workers=4)
+    nvar, nops = 8, 300
+    rng = random.Random(7)
+    vars_ = [eng.new_variable() for _ in range(nvar)]
+    data = [0] * nvar
+    serial = [0] * nvar
+    lock = threading.Lock()
+    for i in range(nops):
+        reads = rng.sample(range(nvar), rng.randint(0, 3))
+        writes = rng.sample([v for v in range(nvar) if v not in reads], rng.randint(1, 2))
+        k = rng.randint(1, 5)
+        # serial oracle
+        s = sum(serial[r] for r in reads)
+        for w in writes:
+            serial[w] = serial[w] * 3 + s + k
+
+        def op(reads=reads, writes=writes, k=k):
+            s = sum(data[r] for r in reads)
+            time.sleep(0.0002 * (k % 3))
+            for w in writes:
+                data[w] = data[w] * 3 + s + k
+        eng.push(op, [vars_[r] for r in reads], [vars_[w] for w in writes])
+    eng.wait_all()
+    assert data == serial
+    assert eng.num_pending() == 0
+
+
+def test_wait_for_var_and_priority():
+    eng = Engine(num_workers=2)
+    v = eng.new_variable()
+    out = []
+    eng.push(lambda: (time.sleep(0.05), out.append(1)), [], [v])
+    eng.push(lambda: out.append(2), [], [v])
+    eng.wait_for_var(v)
+    assert out == [1, 2]
+
+
+def test_concurrent_readers_run_in_parallel():
+    eng = Engine(num_workers=4)
+    v = eng.new_variable()
+    active, peak = [0], [0]
+    lock = threading.Lock()
+
+    def reader():
+        with lock:
+            active[0] += 1
+            peak[0] = max(peak[0], active[0])
+        time.sleep(0.05)
+        with lock:
+            active[0] -= 1
+    for _ in range(4):
+        eng.push(reader, [v], [])
+    eng.wait_all()
+    assert peak[0] >= 2
+
+
+def test_exception_propagates_at_wait():
+    eng = Engine(num_workers=2)
+    v = eng.new_variable()
+
+    def boom():
+        raise ValueError("bad op")
+    eng.push(boom, [], [v])
+    with pytest.raises(ValueError):
+        eng.wait_all()
+    eng.push(lambda: None, [], [v])     # engine keeps working afterwards
+    eng.wait_all()
+
+
+def test_stop_start_drain():
+    eng = Engine(num_workers=2)
+    v = eng.new_variable()
+    hits = []
+    for i in range(10):
+        eng.push(lambda i=i: hits.append(i), [], [v])
+    eng.stop()                           # drains everything (elastic re-init)
+    assert hits == list(range(10))
+    eng.start()
+    eng.push(lambda: hits.append(99), [], [v])
+    eng.wait_all()
+    assert hits[-1] == 99
+    mx.nd.waitall()

@@ -1,0 +1,164 @@
+"""Symbol / Executor / Module (reference tests: test_symbol.py, test_executor.py, test_module.py, train/test_mlp.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import mxb200 as mx
+
+
+def _mlp():
+    data = mx.sym.var("data")
+    fc1 = mx.sym.FullyConnected(data, name="fc1", num_hidden=32)
+    act = mx.sym.Activation(fc1, name="relu1", act_type="relu")
+    fc2 = mx.sym.FullyConnected(act, name="fc2", num_hidden=4)
+    return mx.sym.SoftmaxOutput(fc2, name="softmax")
+
+
+def _toy(n=256, seed=0):
+    rng = np.random.RandomState(seed)
+    X = rng.randn(n, 10).astype(np.float32)
+    Y = (X @ rng.randn(10, 4)).argmax(1).astype(np.float32)
+    return X, Y
+
+
+def test_symbol_compose_infer_json(tmp_path):
+    net = _mlp()
+    assert net.list_arguments() == ["data", "fc1_weight", "fc1_bias", "fc2_weight", "fc2_bias", "softmax_label"]
+    assert net.list_outputs() == ["softmax_output"]
+    arg, out, aux = net.infer_shape(data=(8, 10))
+    assert arg == [(8, 10), (32, 10), (32,), (4, 32), (4,), (8,)] and out == [(8, 4)] and aux == []
+    f = str(tmp_path / "net-symbol.json")
+    net.save(f)
+    g = json.load(open(f))
+    assert {"nodes", "arg_nodes", "heads", "node_row_ptr"} <= set(g)
+    net2 = mx.sym.load(f)
+    assert net2.list_arguments() == net.list_arguments()
+    assert net2.infer_shape(data=(8, 10))[1] == [(8, 4)]
+    internals = net.get_internals()
+    assert "fc1_output" in internals.list_outputs()
+    conv = mx.sym.Convolution(mx.sym.var("x"), kernel=(3, 3), num_filter=8, pad=(1, 1), name="c")
+    bn = mx.sym.BatchNorm(conv, name="bn")
+    assert bn.list_auxiliary_states() == ["bn_moving_mean", "bn_moving_var"]
+    a, o, x = bn.infer_shape(x=(2, 3, 5, 5))
+    assert o == [(2, 8, 5, 5)] and x == [(8,), (8,)]
+    s = (mx.sym.var("a") + mx.sym.var("b") * 2.0 - 1.0)
+    r = s.eval_nd({"a": mx.nd.ones((2,)), "b": mx.nd.ones((2,))})[0]
+    np.testing.assert_allclose(r.asnumpy(), [2.0, 2.0])
+
+
+def test_executor_forward_backward_matches_numpy():
+    x, w = mx.sym.var("x"), mx.sym.var("w")
+    y = mx.sym.FullyConnected(x, weight=w, no_bias=True, num_hidden=3, name="fc")
+    loss = mx.sym.MakeLoss(mx.sym.sum(mx.sym.square(y)))
+    xv, wv = np.random.randn(4, 5).astype(np.float32), np.random.randn(3, 5).astype(np.float32)
+    ex = loss.bind(mx.cpu(), {"x": mx.nd.array(xv), "w": mx.nd.array(wv)}, grad_req={"x": "null", "w": "write"})
+    out = ex.forward(is_train=True)[0]
+    ex.backward()
+    np.testing.assert_allclose(out.asnumpy(), ((xv @ wv.T) ** 2).sum(), rtol=1e-4)
+    np.testing.assert_allclose(ex.grad_dict["w"].asnumpy(), 2 * (xv @ wv.T).T @ xv, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("ctxs", [[mx.cpu(0)], [mx.cpu(0), mx.cpu(1)]])
+@pytest.mark.parametrize("kv", ["local", "device"])
+def test_module_fit_converges_and_checkpoints(tmp_path, ctxs, kv):
+    X, Y = _toy()
+    it = mx.io.NDArrayIter(X, Y, batch_size=32, shuffle=True)
+    mod = mx.mod.Module(_mlp(), context=ctxs)
+    prefix = str(tmp_path / "mlp")
+    mod.fit(it, num_epoch=8, optimizer="sgd", optimizer_params={"learning_rate": 0.3, "momentum": 0.9}, kvstore=kv,
+            initializer=mx.init.Xavier(), epoch_end_callback=mx.callback.do_checkpoint(prefix),
+            batch_end_callback=mx.callback.Speedometer(32, 2))
+    acc = mod.score(it, "acc")[0][1]
+    assert acc > 0.85
+    assert os.path.exists(prefix + "-symbol.json") and os.path.exists(prefix + "-0008.params")
+    sym, arg, aux = mx.model.load_checkpoint(prefix, 8)
+    assert set(arg) == {"fc1_weight", "fc1_bias", "fc2_weight", "fc2_bias"}
+    m2 = mx.mod.Module.load(prefix, 8)
+    m2.bind(it.provide_data, it.provide_label, for_training=False)
+    assert m2.score(it, "acc")[0][1] == pytest.approx(acc)
+    pred = m2.predict(it)
+    assert pred.shape == (256, 4)
+
+
+def test_module_multi_device_equals_single_device():
+    X, Y = _toy(64)
+    outs = []
+    for ctxs in ([mx.cpu(0)], [mx.cpu(0), mx.cpu(1), mx.cpu(2), mx.cpu(3)]):
+        mx.random.seed(5)
+        np.random.seed(5)
+        it = mx.io.NDArrayIter(X, Y, batch_size=32)
+        mod = mx.mod.Module(_mlp(), context=ctxs)
+        mod.bind(it.provide_data, it.provide_label)
+        mod.init_params(mx.init.Constant(0.05))
+        mod.init_optimizer(kvstore="device", optimizer="sgd", optimizer_params={"learning_rate": 0.1})
+        for batch in it:
+            mod.forward_backward(batch)
+            mod.update()
+        outs.append(mod.get_params()[0]["fc2_weight"].asnumpy())
+    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-4, atol=1e-5)
+
+
+def test_module_save_load_optimizer_states_and_reshape(tmp_path):
+    X, Y = _toy(64)
+    it = mx.io.NDArrayIter(X, Y, batch_size=16)
+    mod = mx.mod.Module(_mlp())
+    mod.bind(it.provide_data, it.provide_label)
+    mod.init_params()
+    mod.init_optimizer(optimizer="sgd", optimizer_params={"learning_rate": 0.1, "momentum": 0.9})
+    b = next(iter(it))
+    mod.forward_backward(b)
+    mod.update()
+    prefix = str(tmp_path / "m")
+    mod.save_checkpoint(prefix, 1, save_optimizer_states=True)
+    assert os.path.exists(prefix + "-0001.states")
+    m2 = mx.mod.Module.load(prefix, 1, load_optimizer_states=True)
+    m2.bind(it.provide_data, it.provide_label)
+    m2.init_optimizer(optimizer="sgd", optimizer_params={"learning_rate": 0.1, "momentum": 0.9})
+    m2.forward_backward(b)
+    m2.update()
+    big = mx.io.DataBatch([mx.nd.array(np.random.randn(8, 10))], [mx.nd.zeros((8,))])
+    mod.forward(big, is_train=False)                  # triggers reshape to a new batch size
+    assert mod.get_outputs()[0].shape == (8, 4)
+
+
+def test_bucketing_and_sequential_modules():
+    def sym_gen(key):
+        data = mx.sym.var("data")
+        fc = mx.sym.FullyConnected(data, name="fc", num_hidden=4, flatten=True)
+        return mx.sym.SoftmaxOutput(fc, name="softmax"), ("data",), ("softmax_label",)
+    bm = mx.mod.BucketingModule(sym_gen, default_bucket_key=10)
+    bm.bind([("data", (8, 10))], [("softmax_label", (8,))])
+    bm.init_params()
+    bm.init_optimizer()
+    batch = mx.io.DataBatch([mx.nd.ones((8, 10))], [mx.nd.zeros((8,))], bucket_key=10,
+                            provide_data=[("data", (8, 10))], provide_label=[("softmax_label", (8,))])
+    bm.forward_backward(batch)
+    bm.update()
+    assert bm.get_outputs()[0].shape == (8, 4)
+    m1 = mx.mod.Module(mx.sym.FullyConnected(mx.sym.var("data"), num_hidden=6, name="a"), label_names=None)
+    m2 = mx.mod.Module(mx.sym.SoftmaxOutput(mx.sym.FullyConnected(mx.sym.var("data"), num_hidden=3, name="b"), name="softmax"))
+    seq = mx.mod.SequentialModule().add(m1).add(m2, take_labels=True, auto_wiring=True)
+    seq.bind([("data", (4, 5))], [("softmax_label", (4,))])
+    seq.init_params()
+    seq.init_optimizer()
+    seq.forward_backward(mx.io.DataBatch([mx.nd.ones((4, 5))], [mx.nd.zeros((4,))]))
+    seq.update()
+    assert seq.get_outputs()[0].shape == (4, 3)
+
+
+def test_hybridblock_export_and_symbolblock_import(tmp_path):
+    from mxb200.gluon import nn
+    net = nn.HybridSequential(prefix="net_")
+    with net.name_scope():
+        net.add(nn.Dense(8, activation="relu", in_units=5), nn.Dense(3, in_units=8))
+    net.initialize()
+    net.hybridize()
+    x = mx.nd.array(np.random.randn(2, 5))
+    y = net(x)
+    prefix = str(tmp_path / "exp")
+    net.export(prefix)
+    assert os.path.exists(prefix + "-symbol.json") and os.path.exists(prefix + "-0000.params")
+    blk = mx.gluon.SymbolBlock.imports(prefix + "-symbol.json", ["data"], prefix + "-0000.params")
+    np.testing.assert_allclose(blk(x).asnumpy(), y.asnumpy(), rtol=1e-5, atol=1e-6)
