@@ -60,6 +60,7 @@ struct Finalize {
   float* sum;          // [C] workspace (zeroed on exit)
   float* sumsq;        // [C]
   unsigned int* counter;  // arrival counter (zeroed on exit)
+  float* partials;     // [grid][2C] per-block partial sums (no atomics; reduced by the last block)
   const float* gamma;  // may be null (=> 1)
   const float* beta;   // may be null (=> 0)
   float* running_mean; // may be null
@@ -140,15 +141,16 @@ stats_kernel(const T* __restrict__ x, int64_t M, int C, Finalize f) {
   }
   __syncthreads();
   if (threadIdx.x < CV) {
+    float* mine = f.partials + (size_t)blockIdx.x * 2 * C;
 #pragma unroll
     for (int j = 0; j < 2 * N; ++j) {
       float a = 0.f;
       for (int k = 0; k < rpi; ++k) a += red[threadIdx.x + k * CV][j];
-      if (j < N) atomicAdd(f.sum + col * N + j, a);
-      else atomicAdd(f.sumsq + col * N + (j - N), a);
+      if (j < N) mine[col * N + j] = a;
+      else mine[C + col * N + (j - N)] = a;
     }
   }
-  // last block finalises
+  // last block reduces the per-block partials (coalesced across channels, deterministic order) and finalises
   __shared__ bool is_last;
   __threadfence();
   __syncthreads();
@@ -159,7 +161,16 @@ stats_kernel(const T* __restrict__ x, int64_t M, int C, Finalize f) {
   __syncthreads();
   if (is_last) {
     __threadfence();
-    for (int c = threadIdx.x; c < C; c += kThreads) finalize_channel(f, c);
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      float a = 0.f, b = 0.f;
+      for (unsigned int k = 0; k < gridDim.x; ++k) {
+        a += f.partials[(size_t)k * 2 * C + c];
+        b += f.partials[(size_t)k * 2 * C + C + c];
+      }
+      f.sum[c] = a;
+      f.sumsq[c] = b;
+      finalize_channel(f, c);
+    }
     if (threadIdx.x == 0) *f.counter = 0u;
   }
 }
@@ -171,8 +182,8 @@ __global__ void finalize_kernel(int C, Finalize f) {
 
 template <typename T, bool RELU, bool RES>
 __global__ void __launch_bounds__(kThreads)
-apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, int64_t M, int C,
-             const float* __restrict__ scale, const float* __restrict__ shift) {
+apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, uint8_t* __restrict__ mask,
+             int64_t M, int C, const float* __restrict__ scale, const float* __restrict__ shift) {
   constexpr int N = V<T>::N;
   const int CV = C / N;
   const int64_t total = M * CV;
@@ -200,8 +211,13 @@ apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__
       for (int j = 0; j < N; ++j) v[j] = v[j] * sc[j] + sh[j];
     }
     if (RELU) {
+      uint32_t bits = 0;
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = fmaxf(v[j], 0.f);
+      for (int j = 0; j < N; ++j) {
+        bits |= (v[j] > 0.f ? 1u : 0u) << j;
+        v[j] = fmaxf(v[j], 0.f);
+      }
+      if (mask != nullptr) mask[i] = (uint8_t)bits;   // 1 bit / element: what the backward needs instead of y
     }
     stg16(y + i * N, pack<T>(v));
   }
@@ -211,6 +227,7 @@ struct BwdFinalize {
   float* sum_dy;       // [C] workspace, zeroed on exit
   float* sum_dyx;      // [C]
   unsigned int* counter;
+  float* partials;     // [grid][2C]
   const float* gamma;  // may be null
   const float* invstd;
   float* dgamma;       // [C] out (may be null)
@@ -224,8 +241,8 @@ struct BwdFinalize {
 
 template <typename T, bool RELU>
 __global__ void __launch_bounds__(kThreads)
-bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, int64_t M, int C,
-                  const float* __restrict__ mean, BwdFinalize f) {
+bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8_t* __restrict__ mask, int64_t M,
+                  int C, const float* __restrict__ mean, BwdFinalize f) {
   constexpr int N = V<T>::N;
   const int CV = C / N;
   const int rpi = kThreads / CV;
@@ -249,11 +266,9 @@ bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
     unpack<T>(ud, dv);
     unpack<T>(ux, xv);
     if (RELU) {
-      uint4 uy = ldg16_stream(y + off);
-      float yv[N];
-      unpack<T>(uy, yv);
+      const uint32_t bits = mask[r * CV + col];
 #pragma unroll
-      for (int j = 0; j < N; ++j) dv[j] = yv[j] > 0.f ? dv[j] : 0.f;
+      for (int j = 0; j < N; ++j) dv[j] = ((bits >> j) & 1u) ? dv[j] : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < N; ++j) {
@@ -269,12 +284,13 @@ bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
   }
   __syncthreads();
   if (threadIdx.x < CV) {
+    float* mine = f.partials + (size_t)blockIdx.x * 2 * C;
 #pragma unroll
     for (int j = 0; j < 2 * N; ++j) {
       float a = 0.f;
       for (int k = 0; k < rpi; ++k) a += red[threadIdx.x + k * CV][j];
-      if (j < N) atomicAdd(f.sum_dy + col * N + j, a);
-      else atomicAdd(f.sum_dyx + col * N + (j - N), a);
+      if (j < N) mine[col * N + j] = a;
+      else mine[C + col * N + (j - N)] = a;
     }
   }
   __shared__ bool is_last;
@@ -287,6 +303,16 @@ bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
   __syncthreads();
   if (is_last) {
     __threadfence();
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      float a = 0.f, b = 0.f;
+      for (unsigned int k = 0; k < gridDim.x; ++k) {
+        a += f.partials[(size_t)k * 2 * C + c];
+        b += f.partials[(size_t)k * 2 * C + C + c];
+      }
+      f.sum_dy[c] = a;
+      f.sum_dyx[c] = b;
+    }
+    __syncthreads();
     const float inv_n = 1.f / (float)f.count;
     for (int c = threadIdx.x; c < C; c += kThreads) {
       const float sd = f.sum_dy[c], sdx = f.sum_dyx[c];
@@ -305,7 +331,7 @@ bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
 
 template <typename T, bool RELU, bool RES>
 __global__ void __launch_bounds__(kThreads)
-bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ dx,
+bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8_t* __restrict__ mask, T* __restrict__ dx,
                  T* __restrict__ dres, int64_t M, int C, const float* __restrict__ mean,
                  const float* __restrict__ invstd, const float* __restrict__ c1, const float* __restrict__ c2,
                  const float* __restrict__ c3) {
@@ -331,11 +357,9 @@ bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __r
     unpack<T>(ud, dv);
     unpack<T>(ux, xv);
     if (RELU) {
-      uint4 uy = ldg16_stream(y + i * N);
-      float yv[N];
-      unpack<T>(uy, yv);
+      const uint32_t bits = mask[i];
 #pragma unroll
-      for (int j = 0; j < N; ++j) dv[j] = yv[j] > 0.f ? dv[j] : 0.f;
+      for (int j = 0; j < N; ++j) dv[j] = ((bits >> j) & 1u) ? dv[j] : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < N; ++j) o[j] = a1[j] * (dv[j] - a2[j] - (xv[j] - mu[j]) * is[j] * a3[j]);
@@ -372,15 +396,20 @@ static void check_shape(int C) {
 using namespace mxb;
 using namespace mxb::bn;
 
-// ws: fp32 workspace of 2*C floats followed by one uint32 counter (all zero on first use; kernels leave it zeroed).
+// ws: fp32 workspace = [2*C sums | 1 counter (uint32) | pad to 2*C+8 | partials: grid_max * 2*C floats].
+// Everything the kernels touch in ws[0 .. 2C+8) is left zeroed on exit.  kMaxGrid bounds the partial area.
+static constexpr int kMaxGrid = kNumSMs * 4;
+
+MXB_API int MXBBnWorkspaceFloats(int C) { return 2 * C + 8 + kMaxGrid * 2 * C; }
+
 MXB_API int MXBBnStatsFinalize(const void* x, int dt, int64_t M, int C, float* ws, const float* gamma,
                                const float* beta, float* running_mean, float* running_var, float* mean_out,
                                float* invstd_out, float* scale_out, float* shift_out, float eps, float momentum,
                                int stats_precomputed, void* stream) {
   MXB_TRY
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  Finalize f{ws, ws + C, reinterpret_cast<unsigned int*>(ws + 2 * C), gamma, beta, running_mean, running_var,
-             mean_out, invstd_out, scale_out, shift_out, eps, momentum, M};
+  Finalize f{ws, ws + C, reinterpret_cast<unsigned int*>(ws + 2 * C), ws + 2 * C + 8, gamma, beta, running_mean,
+             running_var, mean_out, invstd_out, scale_out, shift_out, eps, momentum, M};
   if (stats_precomputed) {
     finalize_kernel<<<(C + 255) / 256, 256, 0, s>>>(C, f);
   } else if (dt == kBF16) {
@@ -398,8 +427,9 @@ MXB_API int MXBBnStatsFinalize(const void* x, int dt, int64_t M, int C, float* w
   MXB_CATCH
 }
 
-MXB_API int MXBBnApply(const void* x, const void* res, void* y, int dt, int64_t M, int C, const float* scale,
-                       const float* shift, int relu, void* stream) {
+// mask: [M * C/VEC] bytes (bit j of byte i = (y > 0) of element j of vector i); may be null.
+MXB_API int MXBBnApply(const void* x, const void* res, void* y, void* mask, int dt, int64_t M, int C,
+                       const float* scale, const float* shift, int relu, void* stream) {
   MXB_TRY
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   auto go = [&](auto t) {
@@ -407,11 +437,11 @@ MXB_API int MXBBnApply(const void* x, const void* res, void* y, int dt, int64_t 
     check_shape<T>(C);
     const int CV = C / V<T>::N;
     const int g = grid_elems(M * CV, CV);
-    const T* xx = (const T*)x; const T* rr = (const T*)res; T* yy = (T*)y;
-    if (relu && res) apply_kernel<T, true, true><<<g, kThreads, 0, s>>>(xx, rr, yy, M, C, scale, shift);
-    else if (relu) apply_kernel<T, true, false><<<g, kThreads, 0, s>>>(xx, rr, yy, M, C, scale, shift);
-    else if (res) apply_kernel<T, false, true><<<g, kThreads, 0, s>>>(xx, rr, yy, M, C, scale, shift);
-    else apply_kernel<T, false, false><<<g, kThreads, 0, s>>>(xx, rr, yy, M, C, scale, shift);
+    const T* xx = (const T*)x; const T* rr = (const T*)res; T* yy = (T*)y; uint8_t* mm = (uint8_t*)mask;
+    if (relu && res) apply_kernel<T, true, true><<<g, kThreads, 0, s>>>(xx, rr, yy, mm, M, C, scale, shift);
+    else if (relu) apply_kernel<T, true, false><<<g, kThreads, 0, s>>>(xx, rr, yy, mm, M, C, scale, shift);
+    else if (res) apply_kernel<T, false, true><<<g, kThreads, 0, s>>>(xx, rr, yy, mm, M, C, scale, shift);
+    else apply_kernel<T, false, false><<<g, kThreads, 0, s>>>(xx, rr, yy, mm, M, C, scale, shift);
   };
   if (dt == kBF16) go(__nv_bfloat16{});
   else if (dt == kF32) go(float{});
@@ -420,28 +450,29 @@ MXB_API int MXBBnApply(const void* x, const void* res, void* y, int dt, int64_t 
   MXB_CATCH
 }
 
-// ws: 2*C floats + counter (zeroed).  coef: 3*C floats scratch (c1,c2,c3).
-MXB_API int MXBBnBackward(const void* dy, const void* x, const void* y, void* dx, void* dres, int dt, int64_t M, int C,
-                          const float* mean, const float* invstd, const float* gamma, float* dgamma, float* dbeta,
-                          float* ws, float* coef, int relu, int accumulate, void* stream) {
+// ws as above.  coef: 3*C floats scratch (c1,c2,c3).  relu => mask must be the byte map written by MXBBnApply.
+// dgamma / dbeta: fp32, written (accumulate=0) or accumulated into (accumulate=1; e.g. straight into a gradient arena).
+MXB_API int MXBBnBackward(const void* dy, const void* x, const void* mask, void* dx, void* dres, int dt, int64_t M,
+                          int C, const float* mean, const float* invstd, const float* gamma, float* dgamma,
+                          float* dbeta, float* ws, float* coef, int relu, int accumulate, void* stream) {
   MXB_TRY
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  BwdFinalize f{ws, ws + C, reinterpret_cast<unsigned int*>(ws + 2 * C), gamma, invstd, dgamma, dbeta,
+  BwdFinalize f{ws, ws + C, reinterpret_cast<unsigned int*>(ws + 2 * C), ws + 2 * C + 8, gamma, invstd, dgamma, dbeta,
                 coef, coef + C, coef + 2 * C, M, accumulate};
   auto go = [&](auto t) {
     using T = decltype(t);
     check_shape<T>(C);
     const int CV = C / V<T>::N;
     const int rpi = kThreads / CV;
-    const T* dd = (const T*)dy; const T* xx = (const T*)x; const T* yy = (const T*)y;
-    if (relu) bwd_reduce_kernel<T, true><<<grid_rows(M, rpi), kThreads, 0, s>>>(dd, xx, yy, M, C, mean, f);
-    else bwd_reduce_kernel<T, false><<<grid_rows(M, rpi), kThreads, 0, s>>>(dd, xx, yy, M, C, mean, f);
+    const T* dd = (const T*)dy; const T* xx = (const T*)x; const uint8_t* mm = (const uint8_t*)mask;
+    if (relu) bwd_reduce_kernel<T, true><<<grid_rows(M, rpi), kThreads, 0, s>>>(dd, xx, mm, M, C, mean, f);
+    else bwd_reduce_kernel<T, false><<<grid_rows(M, rpi), kThreads, 0, s>>>(dd, xx, mm, M, C, mean, f);
     const int g = grid_elems(M * CV, CV);
     T* ox = (T*)dx; T* orr = (T*)dres;
-    if (relu && dres) bwd_apply_kernel<T, true, true><<<g, kThreads, 0, s>>>(dd, xx, yy, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
-    else if (relu) bwd_apply_kernel<T, true, false><<<g, kThreads, 0, s>>>(dd, xx, yy, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
-    else if (dres) bwd_apply_kernel<T, false, true><<<g, kThreads, 0, s>>>(dd, xx, yy, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
-    else bwd_apply_kernel<T, false, false><<<g, kThreads, 0, s>>>(dd, xx, yy, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
+    if (relu && dres) bwd_apply_kernel<T, true, true><<<g, kThreads, 0, s>>>(dd, xx, mm, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
+    else if (relu) bwd_apply_kernel<T, true, false><<<g, kThreads, 0, s>>>(dd, xx, mm, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
+    else if (dres) bwd_apply_kernel<T, false, true><<<g, kThreads, 0, s>>>(dd, xx, mm, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
+    else bwd_apply_kernel<T, false, false><<<g, kThreads, 0, s>>>(dd, xx, mm, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
   };
   if (dt == kBF16) go(__nv_bfloat16{});
   else if (dt == kF32) go(float{});

@@ -13,7 +13,9 @@
 //
 // Tile: BLOCK_M=128 x BLOCK_N in {64,128} x BLOCK_K=64 (one 128-byte swizzle atom of bf16), UMMA 128xBNx16,
 // cta_group::1.  Warp roles: warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
-// warps4-7 = epilogue (TMEM lane quarter = warp_idx % 4).
+// warps4-11 = epilogue (TMEM lane quarter = warp_idx % 4; the two warps of a quarter split the columns;
+// TMEM loads are batched, the staging buffer is double buffered so the TMA store of tile i overlaps the
+// epilogue of tile i+1, and per-column BatchNorm statistics are accumulated per CTA in shared memory).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -30,8 +32,9 @@ namespace gemm {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 384;      // 4 control warps + 8 epilogue warps
+constexpr int kEpiThreads = 256;   // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int kMaxStatCols = 2048; // per-CTA column-statistics accumulators kept in shared memory
 
 struct Params {
   int M, N, K;          // logical problem: D[M,N] = A[M,K] * B[N,K]^T   (K = reduction)
@@ -41,6 +44,8 @@ struct Params {
   int relu;
   float* col_sum;       // [N] fp32 accumulators (atomicAdd) or null : sum over rows of stored output
   float* col_sumsq;     // [N]
+  const __nv_bfloat16* addend;  // optional C[M,N] (row stride ldc): D = A*B + C  (residual-gradient fusion)
+  int64_t ldc;
   // debug overrides for descriptor fields (0 = use computed); lets one GPU run probe encodings
   int dbg_lbo_a, dbg_sbo_a, dbg_lbo_b, dbg_sbo_b;
 };
@@ -51,10 +56,12 @@ struct Smem {
   static constexpr int kBBytes = BN * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kDBytes = BLOCK_M * BN * (int)sizeof(OutT);
-  static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
-  static constexpr int kStagesRaw = (kBudget - kDBytes) / kStageBytes;
+  static constexpr int kDBufs = sizeof(OutT) == 2 ? 2 : 1;   // double-buffered staging for the streaming bf16 case
+  static constexpr int kStatBytes = 2 * kMaxStatCols * 4;
+  static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - kStatBytes;
+  static constexpr int kStagesRaw = (kBudget - kDBufs * kDBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kTotal = kStages * kStageBytes + kDBytes + 256 + 1024;
+  static constexpr int kTotal = kStages * kStageBytes + kDBufs * kDBytes + kStatBytes + 256 + 1024;
 };
 
 template <int BN, bool A_MN, bool B_MN, typename OutT, bool REDUCE>
@@ -71,8 +78,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * S::kABytes;
-  uint8_t* smem_d = smem + kStages * S::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_d + S::kDBytes);
+  uint8_t* smem_d0 = smem + kStages * S::kStageBytes;
+  float* colacc = reinterpret_cast<float*>(smem_d0 + S::kDBufs * S::kDBytes);   // [2][kMaxStatCols]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(colacc) + S::kStatBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
@@ -203,40 +211,87 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (4 warps, 128 threads) =====================
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;          // row of the tile owned by this thread
-    const int epi_tid = threadIdx.x - 128;  // 0..127
+    // ===================== epilogue (8 warps, 256 threads) =====================
+    constexpr int kColsPerWarp = BN / 2;          // two warps share a lane quarter, each owns half the columns
+    constexpr int kChunks = kColsPerWarp / 32;    // 32-column TMEM loads per warp
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;             // which half of the tile's columns
+    const int row = q * 32 + lane;                // row of the tile owned by this thread
+    const int epi_tid = threadIdx.x - 128;        // 0..255
+    const bool stats_smem = (p.col_sum != nullptr) && (p.N <= kMaxStatCols);
+    if (stats_smem) {
+      for (int i = epi_tid; i < 2 * kMaxStatCols; i += kEpiThreads) colacc[i] = 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     int it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
       int m_blk, n_blk, kb0, kb1;
       decode(w, m_blk, n_blk, kb0, kb1);
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      // staging buffer must be drained by the previous tile's TMA store before it is overwritten
-      if (epi_tid == 0) ptx::tma_wait_group_read<0>();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      uint8_t* smem_d = smem_d0 + (S::kDBufs == 2 ? (it & 1) * S::kDBytes : 0);
+      // the staging buffer about to be overwritten must have been drained by its previous TMA store
+      if (epi_tid == 0) {
+        if (S::kDBufs == 2) ptx::tma_wait_group_read<1>();
+        else ptx::tma_wait_group_read<0>();
+      }
+      // residual addend: issue the global loads before blocking on the accumulator
+      const int grow = m_blk * BLOCK_M + row;
+      uint4 cadd[kChunks * 4];
+      if (p.addend != nullptr) {
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const int col0 = n_blk * BN + half * kColsPerWarp + c * 32;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (grow < p.M && col0 + i * 8 < p.N)
+              cadd[c * 4 + i] = *reinterpret_cast<const uint4*>(p.addend + (int64_t)grow * p.ldc + col0 + i * 8);
+            else
+              cadd[c * 4 + i] = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       ptx::mbar_wait(&tmem_full[buf], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-      const bool row_valid = (m_blk * BLOCK_M + row) < p.M;
+      const uint32_t taddr = tmem_base + buf * BN + half * kColsPerWarp + ((uint32_t)(q * 32) << 16);
+      uint32_t r[kChunks][32];
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
-        ptx::tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 32;
+      for (int c = 0; c < kChunks; ++c) ptx::tmem_ld_32x32b_x32(taddr + c * 32, r[c]);
+      ptx::tmem_ld_wait();
+      // all TMEM reads of this warp are done: hand the accumulator back to the MMA warp as early as possible
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int cc = half * kChunks + c;              // 32-column chunk index within the tile
+        const int col0 = n_blk * BN + cc * 32;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
+          float x = __uint_as_float(r[c][j]);
           if (p.bias != nullptr && (col0 + j) < p.N) x += __ldg(p.bias + col0 + j);
-          if (p.relu) x = fmaxf(x, 0.f);
           v[j] = x;
         }
+        if (p.addend != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cadd[c * 4 + i]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              v[i * 8 + 2 * k] += __low2float(h[k]);
+              v[i * 8 + 2 * k + 1] += __high2float(h[k]);
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
         if constexpr (sizeof(OutT) == 2) {
-          // 32 bf16 = 64B = 4 x 16B chunks; box = c/2, logical chunk = (c%2)*4 + i
-          uint8_t* box = smem_d + (c >> 1) * (BLOCK_M * 128) + row * 128;
+          // 32 bf16 = 64B = 4 x 16B chunks; box = cc/2, logical 16B chunk = (cc%2)*4 + i, XOR-swizzled by row
+          uint8_t* box = smem_d + (cc >> 1) * (BLOCK_M * 128) + row * 128;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 pk;
@@ -248,12 +303,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             pk.y = *reinterpret_cast<uint32_t*>(&h1);
             pk.z = *reinterpret_cast<uint32_t*>(&h2);
             pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            const int chunk = ((c & 1) * 4 + i) ^ (row & 7);
+            const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
             *reinterpret_cast<uint4*>(box + chunk * 16) = pk;
           }
         } else {
-          // 32 fp32 = 128B = one full swizzled row of box c
-          uint8_t* box = smem_d + c * (BLOCK_M * 128) + row * 128;
+          // 32 fp32 = 128B = one full swizzled row of box cc
+          uint8_t* box = smem_d + cc * (BLOCK_M * 128) + row * 128;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             uint4 pk;
@@ -266,13 +321,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
-      // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
       // make generic-proxy smem writes visible to the async proxy, then one thread issues the TMA stores
       ptx::fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (p.col_sum != nullptr) {
         // per-column sum / sum-of-squares of the values as stored (rounded), for fused BatchNorm statistics.
         // thread t owns column t (t < BN); rows beyond M are zero because TMA zero-filled A.
@@ -281,18 +332,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int colg = n_blk * BN + epi_tid;
             if (colg < p.N) {
               const uint8_t* box = smem_d + (epi_tid >> 6) * (BLOCK_M * 128);
-              const int cc = epi_tid & 63;
+              const int cl = epi_tid & 63;
               float s = 0.f, s2 = 0.f;
 #pragma unroll 8
               for (int rr = 0; rr < BLOCK_M; ++rr) {
-                const int chunk = (cc >> 3) ^ (rr & 7);
+                const int chunk = (cl >> 3) ^ (rr & 7);
                 float x = __bfloat162float(
-                    *reinterpret_cast<const __nv_bfloat16*>(box + rr * 128 + chunk * 16 + (cc & 7) * 2));
+                    *reinterpret_cast<const __nv_bfloat16*>(box + rr * 128 + chunk * 16 + (cl & 7) * 2));
                 s += x;
                 s2 += x * x;
               }
-              atomicAdd(p.col_sum + colg, s);
-              atomicAdd(p.col_sumsq + colg, s2);
+              if (stats_smem) {   // one thread per column per tile: plain accumulate, flushed once at kernel end
+                colacc[colg] += s;
+                colacc[kMaxStatCols + colg] += s2;
+              } else {
+                atomicAdd(p.col_sum + colg, s);
+                atomicAdd(p.col_sumsq + colg, s2);
+              }
             }
           }
         }
@@ -307,7 +363,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         ptx::tma_commit_group();
       }
-      (void)row_valid;
+    }
+    if (stats_smem) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = epi_tid; c < p.N; c += kEpiThreads) {
+        const float a = colacc[c], b = colacc[kMaxStatCols + c];
+        if (a != 0.f || b != 0.f) {
+          atomicAdd(p.col_sum + c, a);
+          atomicAdd(p.col_sumsq + c, b);
+        }
+      }
     }
     if (epi_tid == 0) ptx::tma_wait_group<0>();
   }
@@ -364,8 +429,8 @@ static CUtensorMap make_map(const void* ptr, CUtensorMapDataType dt, int elem_by
 
 template <int BN, bool A_MN, bool B_MN, typename OutT, bool REDUCE>
 static void launch(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldd,
-                   const float* bias, int relu, float* col_sum, float* col_sumsq, int splits, int max_ctas,
-                   const int* dbg, cudaStream_t stream) {
+                   const float* bias, int relu, float* col_sum, float* col_sumsq, const void* addend, int64_t ldc,
+                   int splits, int max_ctas, const int* dbg, cudaStream_t stream) {
   using S = Smem<BN, OutT>;
   CUtensorMap tmA = A_MN ? make_map(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, M, lda, BLOCK_K, 64)
                          : make_map(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, BLOCK_M, BLOCK_K);
@@ -381,6 +446,9 @@ static void launch(const void* A, const void* B, void* D, int M, int N, int K, i
   p.kb_per_split = (nkb + splits - 1) / splits;
   p.num_splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;
   p.bias = bias; p.relu = relu; p.col_sum = col_sum; p.col_sumsq = col_sumsq;
+  p.addend = reinterpret_cast<const __nv_bfloat16*>(addend); p.ldc = ldc;
+  if (addend != nullptr && ((reinterpret_cast<uintptr_t>(addend) & 15) != 0 || (ldc % 8) != 0))
+    throw std::runtime_error("gemm: addend must be 16B aligned with a row stride multiple of 8");
   p.dbg_lbo_a = dbg ? dbg[0] : 0; p.dbg_sbo_a = dbg ? dbg[1] : 0; p.dbg_lbo_b = dbg ? dbg[2] : 0; p.dbg_sbo_b = dbg ? dbg[3] : 0;
   const int num_work = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN) * p.num_splits;
   int ctas = max_ctas > 0 ? max_ctas : kNumSMs;
@@ -401,21 +469,21 @@ using namespace mxb;
 //       2 = TN (A MN-major, B MN-major) -> fp32 out, TMA reduce-add (caller zero-fills D), split-K
 // A, B bf16.  lda/ldb/ldd are row strides (elements) of the *stored* 2D arrays.
 MXB_API int MXBGemmBf16(int mode, const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb,
-                        int64_t ldd, const float* bias, int relu, float* col_sum, float* col_sumsq, int splits,
-                        int block_n, int max_ctas, const int* dbg, void* stream) {
+                        int64_t ldd, const float* bias, int relu, float* col_sum, float* col_sumsq, const void* addend,
+                        int64_t ldc, int splits, int block_n, int max_ctas, const int* dbg, void* stream) {
   MXB_TRY
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   MXB_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
   const bool bn64 = (block_n == 64) || (block_n == 0 && N <= 64);
   if (mode == 0) {
-    if (bn64) gemm::launch<64, false, false, __nv_bfloat16, false>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, 1, max_ctas, dbg, s);
-    else gemm::launch<128, false, false, __nv_bfloat16, false>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, 1, max_ctas, dbg, s);
+    if (bn64) gemm::launch<64, false, false, __nv_bfloat16, false>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, 1, max_ctas, dbg, s);
+    else gemm::launch<128, false, false, __nv_bfloat16, false>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, 1, max_ctas, dbg, s);
   } else if (mode == 1) {
-    if (bn64) gemm::launch<64, false, true, __nv_bfloat16, false>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, 1, max_ctas, dbg, s);
-    else gemm::launch<128, false, true, __nv_bfloat16, false>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, 1, max_ctas, dbg, s);
+    if (bn64) gemm::launch<64, false, true, __nv_bfloat16, false>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, 1, max_ctas, dbg, s);
+    else gemm::launch<128, false, true, __nv_bfloat16, false>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, 1, max_ctas, dbg, s);
   } else if (mode == 2) {
-    if (bn64) gemm::launch<64, true, true, float, true>(A, B, D, M, N, K, lda, ldb, ldd, nullptr, 0, nullptr, nullptr, splits, max_ctas, dbg, s);
-    else gemm::launch<128, true, true, float, true>(A, B, D, M, N, K, lda, ldb, ldd, nullptr, 0, nullptr, nullptr, splits, max_ctas, dbg, s);
+    if (bn64) gemm::launch<64, true, true, float, true>(A, B, D, M, N, K, lda, ldb, ldd, nullptr, 0, nullptr, nullptr, nullptr, 0, splits, max_ctas, dbg, s);
+    else gemm::launch<128, true, true, float, true>(A, B, D, M, N, K, lda, ldb, ldd, nullptr, 0, nullptr, nullptr, nullptr, 0, splits, max_ctas, dbg, s);
   } else {
     throw std::runtime_error("MXBGemmBf16: bad mode");
   }

@@ -256,6 +256,9 @@ class FusedResNet(HybridBlock):
         training = autograd.is_training()
         P = {n: params[n]._t for n in self._pnames}
         A = {n: params[n]._t for n in self._anames}
+        G = {n: self._reg_params[n]._grad_sink for n in self._pnames if self._reg_params[n]._grad_sink is not None}
+        if not G or not autograd.is_recording():
+            G = None
         spec, eps, mom = self._spec, self._eps, self._momentum
         nchw = self._layout == "NCHW"
 
@@ -266,7 +269,7 @@ class FusedResNet(HybridBlock):
                 xt = xt.to(self._tdtype)
             if not xt.is_contiguous():
                 xt = xt.contiguous()
-            return _R.resnet_forward(spec, P, A, xt, training=training, eps=eps, momentum=mom)
+            return _R.resnet_forward(spec, P, A, xt, training=training, eps=eps, momentum=mom, G=G)
         return _op(run, x)
 
 

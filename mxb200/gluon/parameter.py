@@ -52,6 +52,7 @@ class Parameter(object):
         self._stype = stype
         self._grad_stype = grad_stype
         self._fresh_grad = False
+        self._grad_sink = None     # fp32 gradient-arena view when a fused Trainer owns this parameter
 
     def __repr__(self):
         return "Parameter {name} (shape={shape}, dtype={dtype})".format(name=self.name, shape=self.shape, dtype=self.dtype)
@@ -253,7 +254,7 @@ class Parameter(object):
 
     def _sync_grad(self):
         # torch may replace .grad; keep our NDArray handles pointing at the live tensor
-        if self._grad is None or self._data is None:
+        if self._grad is None or self._data is None or self._grad_sink is not None:
             return
         for i, d in enumerate(self._data):
             g = d._t.grad

@@ -159,8 +159,13 @@ class Trainer(object):
             if d._grad_hook is not None:      # arena grads are cleared by the fused kernel itself
                 d._grad_hook.remove()
                 d._grad_hook = None
+            sink = dt.grad_sinks[p.name]
+            with torch.no_grad():
+                if p._grad is not None and p._grad[0]._t is not None:
+                    sink.copy_(p._grad[0]._t)           # gradients of the step that triggered the lazy fusion
             d._t = v
-            p._grad[0]._t = v.grad
+            p._grad[0]._t = sink                        # fp32 arena view (what ``param.grad()`` shows)
+            p._grad_sink = dt.grad_sinks[p.name]
         if world > 1:
             # non-trainable state (BN running stats): start from rank 0's values (kv.init semantics)
             import torch.distributed as dist
@@ -176,6 +181,7 @@ class Trainer(object):
     def _unfuse(self):
         dt, self._fused = self._fused, None
         for p in self._params:
+            p._grad_sink = None
             if p.grad_req == "null" or p._data is None:
                 continue
             d = p._data[0]

@@ -37,19 +37,20 @@ def _use_native(*ts):
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
 
 
-def gemm_raw(mode, A, B, D, M, Nn, K, lda, ldb, ldd, bias=None, relu=False, col_sum=None, col_sumsq=None, splits=1,
-             block_n=0, max_ctas=0, dbg=None):
+def gemm_raw(mode, A, B, D, M, Nn, K, lda, ldb, ldd, bias=None, relu=False, col_sum=None, col_sumsq=None, addend=None,
+             ldc=0, splits=1, block_n=0, max_ctas=0, dbg=None):
     lib = N.cuda()
     dbg_arr = (c_int * 4)(*dbg) if dbg is not None else None
     rc = lib.MXBGemmBf16(c_int(mode), _p(A), _p(B), _p(D), c_int(M), c_int(Nn), c_int(K), c_int64(lda), c_int64(ldb),
-                         c_int64(ldd), _p(bias), c_int(1 if relu else 0), _p(col_sum), _p(col_sumsq), c_int(splits),
-                         c_int(block_n), c_int(max_ctas), dbg_arr, N.stream_of(A))
+                         c_int64(ldd), _p(bias), c_int(1 if relu else 0), _p(col_sum), _p(col_sumsq), _p(addend),
+                         c_int64(ldc), c_int(splits), c_int(block_n), c_int(max_ctas), dbg_arr, N.stream_of(A))
     N.check(lib, rc)
     LAUNCHES[0] += 1
 
 
 def gemm_nt(x, w, bias=None, relu=False, col_stats=None, block_n=0):
-    """y[M,N] = x[M,K] @ w[N,K]^T (+bias)(relu); bf16 in/out, fp32 accumulate in TMEM."""
+    """y[M,N] = x[M,K] @ w[N,K]^T (+bias)(relu); bf16 in/out, fp32 accumulate in TMEM.  ``col_stats`` =
+    (sum, sumsq) fp32 [N] accumulators that receive the per-column statistics of y (fused BatchNorm stats)."""
     M, K = x.shape
     Nn = w.shape[0]
     y = torch.empty((M, Nn), dtype=torch.bfloat16, device=x.device)
@@ -58,12 +59,13 @@ def gemm_nt(x, w, bias=None, relu=False, col_stats=None, block_n=0):
     return y
 
 
-def gemm_nn(dy, w, block_n=0):
-    """dx[M,K] = dy[M,N] @ w[N,K]."""
+def gemm_nn(dy, w, addend=None, block_n=0):
+    """dx[M,K] = dy[M,N] @ w[N,K] (+ addend[M,K]: the residual-branch gradient, added in the epilogue)."""
     M, Nn = dy.shape
     K = w.shape[1]
     dx = torch.empty((M, K), dtype=torch.bfloat16, device=dy.device)
-    gemm_raw(GEMM_NN, dy, w, dx, M, K, Nn, dy.stride(0), w.stride(0), K, block_n=block_n)
+    gemm_raw(GEMM_NN, dy, w, dx, M, K, Nn, dy.stride(0), w.stride(0), K, addend=addend,
+             ldc=addend.stride(0) if addend is not None else 0, block_n=block_n)
     return dx
 
 
@@ -74,15 +76,17 @@ def _pick_splits(M_out, N_out, K_red, block_n):
     return max(1, min(want, kb // 4 if kb >= 8 else 1))
 
 
-def gemm_tn(dy, x, out_dtype=torch.bfloat16, block_n=0):
+def gemm_tn(dy, x, out_dtype=torch.bfloat16, block_n=0, out=None):
     """dw[N,K] = dy[M,N]^T @ x[M,K]; reduction over the (huge) M dim is split across CTAs and combined with
-    fp32 TMA reduce-add."""
+    fp32 TMA reduce-add.  ``out``: fp32 [N,K] buffer that is ACCUMULATED into (e.g. a gradient-arena view)."""
     M, Nn = dy.shape
     K = x.shape[1]
     bn = block_n or (64 if K <= 64 else 128)
-    acc = torch.zeros((Nn, K), dtype=torch.float32, device=dy.device)
-    gemm_raw(GEMM_TN, dy, x, acc, Nn, K, M, dy.stride(0), x.stride(0), K, splits=_pick_splits(Nn, K, M, bn),
+    acc = out if out is not None else torch.zeros((Nn, K), dtype=torch.float32, device=dy.device)
+    gemm_raw(GEMM_TN, dy, x, acc, Nn, K, M, dy.stride(0), x.stride(0), acc.stride(0), splits=_pick_splits(Nn, K, M, bn),
              block_n=bn)
+    if out is not None:
+        return None
     return acc if out_dtype is torch.float32 else acc.to(out_dtype)
 
 
@@ -95,23 +99,41 @@ def _gemm_ok(x, w):
     return K % 8 == 0 and Nn % 8 == 0 and x.stride(-1) == 1 and w.stride(-1) == 1 and N.have_cuda_kernels()
 
 
+def _sink_ok(sink, shape):
+    return sink is not None and sink.dtype is torch.float32 and tuple(sink.shape) == tuple(shape) and sink.is_contiguous()
+
+
 class _LinearFn(torch.autograd.Function):
+    """y = x.W^T (+b)(relu).  Optional extras (all used by the fused ResNet):
+      * ``stats``   : fp32 workspace receiving column sum / sum-of-squares of y (BN statistics for free);
+      * ``sink_w`` / ``sink_b``: fp32 gradient-arena views; when given the weight / bias gradients are accumulated
+        straight into them by the kernels and autograd receives None for those inputs;
+      * ``passthrough``: also return x itself so that a residual branch can hang off the *output* of this op; the
+        gradient arriving on that second output is added inside the dgrad GEMM epilogue (no separate add kernel)."""
+
     @staticmethod
-    def forward(ctx, x, w, b, relu):
+    def forward(ctx, x, w, b, relu, stats, sink_w, sink_b, passthrough):
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         bias32 = b.float() if b is not None else None
-        y = gemm_nt(x2, w, bias32, relu)
+        Nn = w.shape[0]
+        cs = (stats[0:Nn], stats[Nn:2 * Nn]) if stats is not None else None
+        y = gemm_nt(x2, w, bias32, relu, col_stats=cs)
         ctx.save_for_backward(x2, w, y if relu else None)
         ctx.has_bias = b is not None
         ctx.relu = relu
         ctx.xshape = x.shape
         ctx.bdtype = b.dtype if b is not None else None
-        return y.reshape(x.shape[:-1] + (w.shape[0],))
+        ctx.sink_w = sink_w if _sink_ok(sink_w, w.shape) else None
+        ctx.sink_b = sink_b if (b is not None and _sink_ok(sink_b, b.shape)) else None
+        out = y.reshape(x.shape[:-1] + (Nn,))
+        if passthrough:
+            return out, x
+        return out
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, gskip=None):
         x2, w, y = ctx.saved_tensors
         g2 = gy.reshape(-1, gy.shape[-1])
         if ctx.relu:
@@ -120,46 +142,83 @@ class _LinearFn(torch.autograd.Function):
             g2 = g2.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = gemm_nn(g2, w).reshape(ctx.xshape)
-        if ctx.needs_input_grad[1]:
-            gw = gemm_tn(g2, x2, out_dtype=w.dtype)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g2.float().sum(0).to(ctx.bdtype)
-        return gx, gw, gb, None
+            add = None
+            if gskip is not None:
+                add = gskip.reshape(-1, gskip.shape[-1])
+                if not add.is_contiguous():
+                    add = add.contiguous()
+            gx = gemm_nn(g2, w, addend=add).reshape(ctx.xshape)
+        if ctx.needs_input_grad[1] or ctx.sink_w is not None:
+            if ctx.sink_w is not None:
+                gemm_tn(g2, x2, out=ctx.sink_w)
+            else:
+                gw = gemm_tn(g2, x2, out_dtype=w.dtype)
+        if ctx.has_bias and (ctx.needs_input_grad[2] or ctx.sink_b is not None):
+            gsum = g2.float().sum(0)
+            if ctx.sink_b is not None:
+                ctx.sink_b.add_(gsum)
+            else:
+                gb = gsum.to(ctx.bdtype)
+        return gx, gw, gb, None, None, None, None, None
 
 
-def linear(x, w, b=None, relu=False):
+def linear(x, w, b=None, relu=False, stats=None, sink_w=None, sink_b=None, passthrough=False):
     """FullyConnected: Y = X.W^T + b (reference: src/operator/nn/fully_connected-inl.h:72-180)."""
     if _gemm_ok(x, w):
-        return _LinearFn.apply(x, w, b, relu)
+        return _LinearFn.apply(x, w, b, relu, stats, sink_w, sink_b, passthrough)
     if x.is_cuda and not N.have_cuda_kernels():
         raise RuntimeError("mxb200: CUDA kernels library missing on a GPU host")
     y = F.linear(x, w.to(x.dtype) if w.dtype != x.dtype else w, b.to(x.dtype) if b is not None and b.dtype != x.dtype else b)
-    return torch.relu(y) if relu else y
+    y = torch.relu(y) if relu else y
+    return (y, x) if passthrough else y
 
 
-def conv1x1_nhwc(x, w, stride=1):
-    """1x1 convolution on a channels-last (N,H,W,C) *view* == GEMM over pixels.  w: (Cout, Cin)."""
+def conv1x1_nhwc(x, w, stride=1, stats=None, sink_w=None, passthrough=False):
+    """1x1 convolution on a channels-last (N,H,W,C) tensor == GEMM over pixels.  w: (Cout, Cin)."""
     if stride != 1:
         x = x[:, ::stride, ::stride, :].contiguous()
     n, h, ww, c = x.shape
-    y = linear(x.reshape(n * h * ww, c), w)
-    return y.reshape(n, h, ww, w.shape[0])
+    r = linear(x.reshape(n * h * ww, c), w, None, False, stats, sink_w, None, passthrough)
+    if passthrough:
+        y, xp = r
+        return y.reshape(n, h, ww, w.shape[0]), xp.reshape(n, h, ww, c)
+    return r.reshape(n, h, ww, w.shape[0])
 
 
 # --------------------------------------------------------------------------- BatchNorm(+add)(+ReLU)
 class _BnWorkspace(object):
-    """Per-device zero-initialised scratch reused by all BN calls on one stream (kernels leave it zeroed)."""
+    """Per-(device, stream) zero-initialised scratch shared by all BN calls (kernels leave the head zeroed):
+    [2C sums | counter | pad | per-block partials]."""
     _ws = {}
 
     @classmethod
     def get(cls, device, C):
+        lib = N.cuda()
         key = (device, torch.cuda.current_stream(device).cuda_stream)
+        need = lib.MXBBnWorkspaceFloats(c_int(max(C, 2048)))
         ws = cls._ws.get(key)
-        if ws is None or ws.numel() < 2 * C + 8:
-            ws = torch.zeros(max(2 * C + 8, 2 * 4096 + 8), dtype=torch.float32, device=device)
+        if ws is None or ws.numel() < need:
+            ws = torch.zeros(need, dtype=torch.float32, device=device)
             cls._ws[key] = ws
         return ws
+
+
+def fused_stats_workspace(x, w):
+    """Workspace for GEMM-epilogue BatchNorm statistics, or None when the producer will not be our GEMM / the BN
+    will not be our kernel (CPU, unsupported widths)."""
+    if not (_gemm_ok(x, w) and N.have_cuda_kernels()):
+        return None
+    C = w.shape[0]
+    vec = 8
+    cv = C // vec if C % vec == 0 else 0
+    if not (cv > 0 and cv <= 256 and (cv & (cv - 1)) == 0):
+        return None
+    return _BnWorkspace.get(x.device, C)
+
+
+def bn_stats_workspace(device, C):
+    """Workspace whose first 2C floats a producer GEMM may fill with column sums / sums of squares."""
+    return _BnWorkspace.get(torch.device(device), C)
 
 
 def _bn_shape_ok(x2):
@@ -174,7 +233,7 @@ class _BnActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, residual, relu, eps, momentum, training, fix_gamma,
-                pre_stats):
+                pre_stats, sink_g, sink_b):
         lib = N.cuda()
         M, C = x.shape
         dev = x.device
@@ -183,10 +242,7 @@ class _BnActFn(torch.autograd.Function):
         b32 = beta.float()
         st = N.stream_of(x)
         if training:
-            if pre_stats is not None:
-                ws = pre_stats            # [2C+8] sums produced by the GEMM epilogue
-            else:
-                ws = _BnWorkspace.get(dev, C)
+            ws = pre_stats if pre_stats is not None else _BnWorkspace.get(dev, C)
             N.check(lib, lib.MXBBnStatsFinalize(_p(x), c_int(code(x.dtype)), c_int64(M), c_int(C), _p(ws), _p(g32),
                                                 _p(b32), _p(running_mean), _p(running_var), _p(stats[0]), _p(stats[1]),
                                                 _p(stats[2]), _p(stats[3]), c_float(eps), c_float(momentum),
@@ -200,40 +256,56 @@ class _BnActFn(torch.autograd.Function):
             stats[2] = gg * invstd
             stats[3] = b32 - running_mean.float() * gg * invstd
         y = torch.empty_like(x)
-        N.check(lib, lib.MXBBnApply(_p(x), _p(residual), _p(y), c_int(code(x.dtype)), c_int64(M), c_int(C),
+        vec = 16 // x.element_size()
+        mask = torch.empty(M * (C // vec), dtype=torch.uint8, device=dev) if relu else None
+        N.check(lib, lib.MXBBnApply(_p(x), _p(residual), _p(y), _p(mask), c_int(code(x.dtype)), c_int64(M), c_int(C),
                                     _p(stats[2]), _p(stats[3]), c_int(1 if relu else 0), st))
         LAUNCHES[0] += 1
-        ctx.save_for_backward(x, y if relu else None, stats, g32)
+        ctx.save_for_backward(x, mask, stats, g32)
         ctx.cfg = (relu, residual is not None, fix_gamma, gamma.dtype, beta.dtype)
+        ctx.sink_g = sink_g if (not fix_gamma and _sink_ok(sink_g, gamma.shape)) else None
+        ctx.sink_b = sink_b if _sink_ok(sink_b, beta.shape) else None
         return y
 
     @staticmethod
     def backward(ctx, dy):
         lib = N.cuda()
-        x, y, stats, g32 = ctx.saved_tensors
+        x, mask, stats, g32 = ctx.saved_tensors
         relu, has_res, fix_gamma, gdt, bdt = ctx.cfg
         M, C = x.shape
         if not dy.is_contiguous():
             dy = dy.contiguous()
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
-        dgb = torch.empty((2, C), dtype=torch.float32, device=x.device)
         coef = torch.empty((3, C), dtype=torch.float32, device=x.device)
         ws = _BnWorkspace.get(x.device, C)
-        N.check(lib, lib.MXBBnBackward(_p(dy), _p(x), _p(y), _p(dx), _p(dres), c_int(code(x.dtype)), c_int64(M), c_int(C),
-                                       _p(stats[0]), _p(stats[1]), _p(g32), _p(dgb[0]), _p(dgb[1]), _p(ws), _p(coef),
-                                       c_int(1 if relu else 0), c_int(0), N.stream_of(x)))
+        direct = ctx.sink_b is not None and (fix_gamma or ctx.sink_g is not None)
+        if direct:
+            dg_ptr, db_ptr, acc = ctx.sink_g, ctx.sink_b, 1
+            dgb = None
+        else:
+            dgb = torch.empty((2, C), dtype=torch.float32, device=x.device)
+            dg_ptr, db_ptr, acc = dgb[0], dgb[1], 0
+        N.check(lib, lib.MXBBnBackward(_p(dy), _p(x), _p(mask), _p(dx), _p(dres), c_int(code(x.dtype)), c_int64(M),
+                                       c_int(C), _p(stats[0]), _p(stats[1]), _p(g32), _p(dg_ptr), _p(db_ptr), _p(ws),
+                                       _p(coef), c_int(1 if relu else 0), c_int(acc), N.stream_of(x)))
         LAUNCHES[0] += 2
-        dgamma = torch.zeros_like(dgb[0]).to(gdt) if fix_gamma else dgb[0].to(gdt)
-        return dx, dgamma, dgb[1].to(bdt), None, None, dres, None, None, None, None, None, None
+        if direct:
+            dgamma = dbeta = None
+        else:
+            dgamma = torch.zeros_like(dgb[0]).to(gdt) if fix_gamma else dgb[0].to(gdt)
+            dbeta = dgb[1].to(bdt)
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None, None, None
 
 
 def bn_act(x, gamma, beta, running_mean, running_var, residual=None, relu=False, eps=1e-5, momentum=0.9,
-           training=True, fix_gamma=False, pre_stats=None):
+           training=True, fix_gamma=False, pre_stats=None, sink_g=None, sink_b=None):
     """BatchNorm over the last (channel) dim of a channels-last tensor, + optional residual add + ReLU.
 
     momentum follows the reference convention: running = running*momentum + batch*(1-momentum)
     (src/operator/nn/batch_norm.cu:359-362).  running stats are fp32 tensors updated in place.
+    ``pre_stats``: workspace already holding sum / sum-of-squares of x (written by the producing GEMM's epilogue).
+    ``sink_g`` / ``sink_b``: fp32 gradient-arena views that receive dgamma / dbeta directly.
     """
     C = x.shape[-1]
     x2 = x.reshape(-1, C)
@@ -242,7 +314,7 @@ def bn_act(x, gamma, beta, running_mean, running_var, residual=None, relu=False,
         if r2 is not None and not r2.is_contiguous():
             r2 = r2.contiguous()
         y = _BnActFn.apply(x2, gamma, beta, running_mean, running_var, r2, relu, eps, momentum, training, fix_gamma,
-                           pre_stats)
+                           pre_stats, sink_g, sink_b)
         return y.reshape(x.shape)
     if x.is_cuda and not N.have_cuda_kernels():
         raise RuntimeError("mxb200: CUDA kernels library missing on a GPU host")
@@ -263,6 +335,46 @@ def bn_act(x, gamma, beta, running_mean, running_var, residual=None, relu=False,
     if relu:
         y = torch.relu(y)
     return y.to(x.dtype).reshape(x.shape)
+
+
+# --------------------------------------------------------------------------- max pooling (NHWC)
+class _MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, s, p):
+        lib = N.cuda()
+        n, h, w, c = x.shape
+        ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+        y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+        idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device)
+        N.check(lib, lib.MXBMaxPoolNhwcFwd(_p(x), _p(y), _p(idx), c_int(code(x.dtype)), c_int(n), c_int(h), c_int(w),
+                                           c_int(c), c_int(ho), c_int(wo), c_int(k), c_int(s), c_int(p), N.stream_of(x)))
+        LAUNCHES[0] += 1
+        ctx.save_for_backward(idx)
+        ctx.geo = (n, h, w, c, ho, wo, k, s, p)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = N.cuda()
+        idx, = ctx.saved_tensors
+        n, h, w, c, ho, wo, k, s, p = ctx.geo
+        if not dy.is_contiguous():
+            dy = dy.contiguous()
+        dx = torch.empty((n, h, w, c), dtype=dy.dtype, device=dy.device)
+        N.check(lib, lib.MXBMaxPoolNhwcBwd(_p(dy), _p(idx), _p(dx), c_int(code(dy.dtype)), c_int(n), c_int(h), c_int(w),
+                                           c_int(c), c_int(ho), c_int(wo), c_int(k), c_int(s), c_int(p), N.stream_of(dy)))
+        LAUNCHES[0] += 1
+        return dx, None, None, None
+
+
+def max_pool_nhwc(x, kernel=3, stride=2, pad=1):
+    """Max pooling on a channels-last [N,H,W,C] tensor (reference op: Pooling, src/operator/nn/pool.cuh)."""
+    vec = 16 // x.element_size()
+    if _use_native(x) and x.is_contiguous() and x.dtype in (torch.bfloat16, torch.float32) and x.shape[-1] % vec == 0:
+        return _MaxPoolFn.apply(x, kernel, stride, pad)
+    if x.is_cuda and not N.have_cuda_kernels():
+        raise RuntimeError("mxb200: CUDA kernels library missing on a GPU host")
+    return F.max_pool2d(x.permute(0, 3, 1, 2), kernel, stride, pad).permute(0, 2, 3, 1)
 
 
 # --------------------------------------------------------------------------- softmax / CE

@@ -31,19 +31,34 @@ class DeviceTrainer(object):
         self.names = [n for n, _ in named_params]
         lr_mult = lr_mult or {}
         wd_mult = wd_mult or {}
+        self.grad_sinks = {}
+        self._hooks = []
         for dtype, items in group_by_dtype(named_params).items():
             names = [n for n, _ in items]
             tensors = [t for _, t in items]
-            nbytes = fused.SymmetricArena.bytes_needed(tensors, dtype)
-            bufs = {"weights": group.alloc(nbytes), "grads": group.alloc(nbytes)}
-            ar = fused.SymmetricArena(group, names, tensors, bufs, dtype, grad_dtype or dtype)
+            # gradients are always accumulated in fp32 (better numerics than bf16 accumulation, and it lets the
+            # wgrad GEMM / BN backward kernels reduce straight into the arena); weights keep their own dtype
+            gdtype = grad_dtype or (torch.float32 if dtype in (torch.bfloat16, torch.float16) else dtype)
+            bufs = {"weights": group.alloc(fused.SymmetricArena.bytes_needed(tensors, dtype)),
+                    "grads": group.alloc(fused.SymmetricArena.bytes_needed(tensors, gdtype))}
+            ar = fused.SymmetricArena(group, names, tensors, bufs, dtype, gdtype)
             ar.lr_mult.copy_(torch.tensor([lr_mult.get(n, 1.0) for n in names], dtype=torch.float32))
             ar.wd_mult.copy_(torch.tensor([wd_mult.get(n, 1.0) for n in names], dtype=torch.float32))
             self.arenas.append(ar)
             for n, v, g in zip(names, ar.views, ar.grad_views):
                 v.requires_grad_(True)
-                v.grad = g
                 self.param_views[n] = v
+                self.grad_sinks[n] = g
+                if g.dtype == v.dtype:
+                    v.grad = g                      # autograd accumulates in place into the arena
+                else:
+                    # low-precision parameter, fp32 arena: ops that know about sinks write there directly; for
+                    # everything else (library convolutions) the freshly produced gradient is folded in here
+                    def _move(p, sink=g):
+                        if p.grad is not None:
+                            sink.add_(p.grad)
+                            p.grad = None
+                    self._hooks.append(v.register_post_accumulate_grad_hook(_move))
         self.num_update = 0
 
     def params(self):

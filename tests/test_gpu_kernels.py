@@ -331,3 +331,104 @@ def test_fused_allreduce_plain_sum_loopback():
         assert torch.allclose(arenas[r].views[0], torch.full((5000,), 3.0, device=dev))
     for g in groups:
         g.close()
+
+
+# ----------------------------------------------------------------------------- round-1b additions
+def test_gemm_nn_with_addend_and_tn_accumulate():
+    from mxb200.ops import functional as K_
+    dev = _dev()
+    M, N, K = 3000, 256, 64
+    dy = torch.randn(M, N, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.1).bfloat16()
+    add = torch.randn(M, K, device=dev).bfloat16()
+    dx = K_.gemm_nn(dy, w, addend=add)
+    assert _rel_err(dx, dy.float() @ w.float() + add.float()) < 2e-2
+    x = torch.randn(M, K, device=dev).bfloat16()
+    sink = torch.ones(N, K, device=dev)
+    K_.gemm_tn(dy, x, out=sink)
+    assert _rel_err(sink, 1.0 + dy.float().t() @ x.float()) < 2e-2
+
+
+@pytest.mark.parametrize("shape", [(2, 112, 112, 64), (3, 15, 17, 8), (1, 8, 8, 128)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_maxpool_nhwc(shape, dtype):
+    from mxb200.ops import functional as K_
+    x = torch.randn(shape, device=_dev()).to(dtype).requires_grad_(True)
+    y = K_.max_pool_nhwc(x, 3, 2, 1)
+    g = torch.randn_like(y)
+    y.backward(g)
+    x2 = x.detach().float().requires_grad_(True)
+    y2 = torch.nn.functional.max_pool2d(x2.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    y2.backward(g.float())
+    assert torch.equal(y.float(), y2.detach().to(dtype).float())
+    assert _rel_err(x.grad, x2.grad) < 1e-2
+
+
+def test_linear_sinks_stats_and_passthrough():
+    from mxb200.ops import functional as K_
+    dev = _dev()
+    x = torch.randn(512, 64, device=dev).bfloat16().requires_grad_(True)
+    w = (torch.randn(256, 64, device=dev) * 0.1).bfloat16().requires_grad_(True)
+    sink = torch.zeros(256, 64, device=dev)
+    ws = K_.fused_stats_workspace(x, w)
+    y, xp = K_.linear(x, w, None, False, ws, sink, None, True)
+    ref = x.detach().float() @ w.detach().float().t()
+    assert _rel_err(ws[0:256], y.float().sum(0)) < 1e-3 and _rel_err(ws[256:512], (y.float() ** 2).sum(0)) < 1e-3
+    ws[0:512].zero_()
+    g, gs = torch.randn_like(y), torch.randn_like(xp)
+    torch.autograd.backward([y, xp], [g, gs])
+    assert w.grad is None                                         # went to the sink instead
+    assert _rel_err(sink, g.float().t() @ x.detach().float()) < 2e-2
+    assert _rel_err(x.grad, g.float() @ w.detach().float() + gs.float()) < 2e-2
+    assert _rel_err(y, ref) < 2e-2
+
+
+def test_bn_with_gemm_stats_and_sinks():
+    from mxb200.ops import functional as K_
+    dev = _dev()
+    M, Cin, C = 2048, 64, 128
+    a = torch.randn(M, Cin, device=dev).bfloat16()
+    w = (torch.randn(C, Cin, device=dev) * 0.2).bfloat16()
+    gamma, beta = (torch.rand(C, device=dev) + 0.5).requires_grad_(True), torch.randn(C, device=dev).requires_grad_(True)
+    sg, sb = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    ws = K_.fused_stats_workspace(a, w)
+    x = K_.linear(a, w, None, False, ws)
+    xr = x.detach().clone().requires_grad_(True)
+    y = K_.bn_act(xr, gamma, beta, rm, rv, relu=True, pre_stats=ws, sink_g=sg, sink_b=sb)
+    g = torch.randn_like(y)
+    y.backward(g)
+    x2 = x.detach().float().requires_grad_(True)
+    g2, b2 = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    yr = torch.relu((x2 - x2.mean(0)) * torch.rsqrt(x2.var(0, unbiased=False) + 1e-5) * g2 + b2)
+    yr.backward(g.float())
+    assert _rel_err(y, yr) < 2e-2 and _rel_err(xr.grad, x2.grad) < 3e-2
+    assert gamma.grad is None and _rel_err(sg, g2.grad) < 2e-2 and _rel_err(sb, b2.grad) < 2e-2
+    assert float(ws[0:2 * C].abs().max()) == 0.0               # workspace handed back zeroed
+
+
+def test_gluon_fused_trainer_matches_unfused_on_gpu():
+    """Same ResNet-18 step through the fused arena path and through per-parameter updaters."""
+    import mxb200 as mx
+    from mxb200 import gluon, autograd
+    from mxb200.gluon.model_zoo import vision
+    import os
+    ctx = mx.gpu(0)
+    x = mx.nd.from_torch(torch.randn(8, 32, 32, 3, device="cuda").bfloat16(), ctx)
+    y = mx.nd.from_torch(torch.randint(0, 10, (8,), device="cuda"), ctx)
+    outs = []
+    for fused in ("1", "0"):
+        os.environ["MXB200_FUSED_TRAINER"] = fused
+        net = vision.get_resnet("v1b", 18, classes=10, thumbnail=True, ctx=ctx, dtype="bfloat16", layout="NHWC", seed=3)
+        tr = gluon.Trainer(net.collect_params(), "nag", {"learning_rate": 0.05, "momentum": 0.9, "wd": 1e-4,
+                                                         "multi_precision": True})
+        L = gluon.loss.SoftmaxCrossEntropyLoss()
+        for _ in range(3):
+            with autograd.record():
+                l = L(net(x), y)
+            l.backward()
+            tr.step(8)
+        outs.append([p.data().as_torch().float().clone() for p in net.collect_params().values()])
+    os.environ["MXB200_FUSED_TRAINER"] = "1"
+    for a, b in zip(*outs):
+        assert _rel_err(a, b) < 5e-2
