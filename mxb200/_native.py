@@ -36,7 +36,7 @@ def _load(kind, required):
                         raise MXNetError("native library %s missing and MXB200_NO_BUILD set" % path)
                 else:
                     B.build(kind)
-            lib = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL if kind == "host" else ctypes.RTLD_LOCAL)
+            lib = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)   # RTLD_GLOBAL breaks symbol binding next to libtorch
             lib.MXBGetLastError.restype = c_char_p
         except Exception as e:  # noqa: BLE001
             if required:

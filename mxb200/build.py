@@ -27,12 +27,16 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 
 NVCC = os.environ.get("NVCC", shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc")
-CXX = os.environ.get("CXX", "g++")
+# NOTE: deliberately NOT $CXX: this image exports CXX=/opt/gcc/bin/g++, a toolchain that links libstdc++ statically;
+# a second libstdc++ inside a dlopen'ed library next to libtorch's crashes in iostream / std::thread code.
+CXX = os.environ.get("MXB200_CXX") or ("/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++")
 
 CUDA_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--use_fast_math",
-              "-I", CSRC]
-HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-pthread", "-I", CSRC]
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v",
+              "--use_fast_math", "-I", CSRC]
+# hidden visibility: only the MXB_API entry points are exported
+HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-pthread", "-fvisibility=hidden",
+              "-fvisibility-inlines-hidden", "-I", CSRC]
 
 
 def _sources(kind):

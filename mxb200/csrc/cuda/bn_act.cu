@@ -396,11 +396,17 @@ static void check_shape(int C) {
 using namespace mxb;
 using namespace mxb::bn;
 
-// ws: fp32 workspace = [2*C sums | 1 counter (uint32) | pad to 2*C+8 | partials: grid_max * 2*C floats].
-// Everything the kernels touch in ws[0 .. 2C+8) is left zeroed on exit.  kMaxGrid bounds the partial area.
+// ws: fp32 workspace with a layout that does NOT depend on C (calls with different widths share it):
+//   ws[0]                      arrival counter (uint32)
+//   ws[8 .. 8+2C)              column sums | sums of squares (also where a producer GEMM deposits its statistics)
+//   ws[8+2*kMaxC .. )          per-block partials, kMaxGrid * 2C floats
+// ws[0 .. 8+2C) is left zeroed on exit.
 static constexpr int kMaxGrid = kNumSMs * 4;
+static constexpr int kMaxC = 4096;
+static constexpr int kSumOff = 8;
+static constexpr int kPartOff = 8 + 2 * kMaxC;
 
-MXB_API int MXBBnWorkspaceFloats(int C) { return 2 * C + 8 + kMaxGrid * 2 * C; }
+MXB_API int MXBBnWorkspaceFloats(int C) { return kPartOff + kMaxGrid * 2 * (C > kMaxC ? kMaxC : C); }
 
 MXB_API int MXBBnStatsFinalize(const void* x, int dt, int64_t M, int C, float* ws, const float* gamma,
                                const float* beta, float* running_mean, float* running_var, float* mean_out,
@@ -408,7 +414,8 @@ MXB_API int MXBBnStatsFinalize(const void* x, int dt, int64_t M, int C, float* w
                                int stats_precomputed, void* stream) {
   MXB_TRY
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  Finalize f{ws, ws + C, reinterpret_cast<unsigned int*>(ws + 2 * C), ws + 2 * C + 8, gamma, beta, running_mean,
+  MXB_CHECK(C <= kMaxC, "bn: at most 4096 channels");
+  Finalize f{ws + kSumOff, ws + kSumOff + C, reinterpret_cast<unsigned int*>(ws), ws + kPartOff, gamma, beta, running_mean,
              running_var, mean_out, invstd_out, scale_out, shift_out, eps, momentum, M};
   if (stats_precomputed) {
     finalize_kernel<<<(C + 255) / 256, 256, 0, s>>>(C, f);
@@ -457,8 +464,9 @@ MXB_API int MXBBnBackward(const void* dy, const void* x, const void* mask, void*
                           float* dbeta, float* ws, float* coef, int relu, int accumulate, void* stream) {
   MXB_TRY
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  BwdFinalize f{ws, ws + C, reinterpret_cast<unsigned int*>(ws + 2 * C), ws + 2 * C + 8, gamma, invstd, dgamma, dbeta,
-                coef, coef + C, coef + 2 * C, M, accumulate};
+  MXB_CHECK(C <= kMaxC, "bn: at most 4096 channels");
+  BwdFinalize f{ws + kSumOff, ws + kSumOff + C, reinterpret_cast<unsigned int*>(ws), ws + kPartOff, gamma, invstd, dgamma,
+                dbeta, coef, coef + C, coef + 2 * C, M, accumulate};
   auto go = [&](auto t) {
     using T = decltype(t);
     check_shape<T>(C);

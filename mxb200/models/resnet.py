@@ -141,7 +141,7 @@ def resnet_forward(spec, P, A, x, training=True, eps=1e-5, momentum=0.9, G=None,
     G (optional): name -> fp32 gradient-arena view; gradients of 1x1-conv / FC weights and BN gamma/beta are
     then written straight into the arena by the backward kernels."""
     if stem_pad is None:
-        stem_pad = int(getenv("MXB200_STEM_PAD", 8))
+        stem_pad = int(getenv("MXB200_STEM_PAD", 0))   # measured on B200: padding 3->8 channels is slower (2.7 vs 1.4 ms fwd)
     kw = dict(training=training, eps=eps, momentum=momentum)
     if spec.thumbnail:
         y = _stem_conv(x, P["conv0_weight"], 1, 1, stem_pad)

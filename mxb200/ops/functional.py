@@ -35,6 +35,7 @@ def _use_native(*ts):
 
 # --------------------------------------------------------------------------- GEMM
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+STATS_OFF = 8     # BN workspace layout: [counter | pad] [sums | sumsq] ... (csrc/cuda/bn_act.cu)
 
 
 def gemm_raw(mode, A, B, D, M, Nn, K, lda, ldb, ldd, bias=None, relu=False, col_sum=None, col_sumsq=None, addend=None,
@@ -118,7 +119,7 @@ class _LinearFn(torch.autograd.Function):
             x2 = x2.contiguous()
         bias32 = b.float() if b is not None else None
         Nn = w.shape[0]
-        cs = (stats[0:Nn], stats[Nn:2 * Nn]) if stats is not None else None
+        cs = (stats[STATS_OFF:STATS_OFF + Nn], stats[STATS_OFF + Nn:STATS_OFF + 2 * Nn]) if stats is not None else None
         y = gemm_nt(x2, w, bias32, relu, col_stats=cs)
         ctx.save_for_backward(x2, w, y if relu else None)
         ctx.has_bias = b is not None
@@ -195,7 +196,7 @@ class _BnWorkspace(object):
     def get(cls, device, C):
         lib = N.cuda()
         key = (device, torch.cuda.current_stream(device).cuda_stream)
-        need = lib.MXBBnWorkspaceFloats(c_int(max(C, 2048)))
+        need = lib.MXBBnWorkspaceFloats(c_int(4096))
         ws = cls._ws.get(key)
         if ws is None or ws.numel() < need:
             ws = torch.zeros(need, dtype=torch.float32, device=device)

@@ -373,8 +373,8 @@ def test_linear_sinks_stats_and_passthrough():
     ws = K_.fused_stats_workspace(x, w)
     y, xp = K_.linear(x, w, None, False, ws, sink, None, True)
     ref = x.detach().float() @ w.detach().float().t()
-    assert _rel_err(ws[0:256], y.float().sum(0)) < 1e-3 and _rel_err(ws[256:512], (y.float() ** 2).sum(0)) < 1e-3
-    ws[0:512].zero_()
+    assert _rel_err(ws[8:264], y.float().sum(0)) < 1e-3 and _rel_err(ws[264:520], (y.float() ** 2).sum(0)) < 1e-3
+    ws[0:520].zero_()
     g, gs = torch.randn_like(y), torch.randn_like(xp)
     torch.autograd.backward([y, xp], [g, gs])
     assert w.grad is None                                         # went to the sink instead
@@ -404,7 +404,7 @@ def test_bn_with_gemm_stats_and_sinks():
     yr.backward(g.float())
     assert _rel_err(y, yr) < 2e-2 and _rel_err(xr.grad, x2.grad) < 3e-2
     assert gamma.grad is None and _rel_err(sg, g2.grad) < 2e-2 and _rel_err(sb, b2.grad) < 2e-2
-    assert float(ws[0:2 * C].abs().max()) == 0.0               # workspace handed back zeroed
+    assert float(ws[0:8 + 2 * C].abs().max()) == 0.0               # workspace handed back zeroed
 
 
 def test_gluon_fused_trainer_matches_unfused_on_gpu():
