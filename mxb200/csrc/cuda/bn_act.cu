@@ -20,6 +20,7 @@ namespace mxb {
 namespace bn {
 
 constexpr int kThreads = 256;
+constexpr int kUnroll = 4;   // independent 16-byte loads in flight per thread and per stream
 
 template <typename T>
 struct V {
@@ -110,17 +111,20 @@ stats_kernel(const T* __restrict__ x, int64_t M, int C, Finalize f) {
   const int64_t row_end = min(M, row_begin + rows_per_block);
   const T* base = x + (int64_t)col * N;
   int64_t r = row_begin + r0;
-  // 2x unrolled for memory-level parallelism
-  for (; r + rpi < row_end; r += 2 * rpi) {
-    uint4 u0 = ldg16_stream(base + r * C);
-    uint4 u1 = ldg16_stream(base + (r + rpi) * C);
-    float v0[N], v1[N];
-    unpack<T>(u0, v0);
-    unpack<T>(u1, v1);
+  // kUnroll independent 16B loads in flight per thread: HBM3e needs ~40 KB in flight per SM to stream at full rate
+  for (; r + (kUnroll - 1) * rpi < row_end; r += kUnroll * rpi) {
+    uint4 u[kUnroll];
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      s[j] += v0[j] + v1[j];
-      s2[j] += v0[j] * v0[j] + v1[j] * v1[j];
+    for (int k = 0; k < kUnroll; ++k) u[k] = ldg16_stream(base + (r + k * rpi) * C);
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      float v[N];
+      unpack<T>(u[k], v);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        s[j] += v[j];
+        s2[j] = fmaf(v[j], v[j], s2[j]);
+      }
     }
   }
   for (; r < row_end; r += rpi) {
@@ -130,7 +134,7 @@ stats_kernel(const T* __restrict__ x, int64_t M, int C, Finalize f) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       s[j] += v0[j];
-      s2[j] += v0[j] * v0[j];
+      s2[j] = fmaf(v0[j], v0[j], s2[j]);
     }
   }
   __shared__ float red[kThreads][2 * 8 + 1];
@@ -196,19 +200,17 @@ apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__
     sc[j] = __ldg(scale + col * N + j);
     sh[j] = __ldg(shift + col * N + j);
   }
-  for (; i < total; i += stride) {
-    uint4 u = ldg16_stream(x + i * N);
+  auto body = [&](int64_t idx, const uint4& u, const uint4& ur) {
     float v[N];
     unpack<T>(u, v);
     if (RES) {
-      uint4 ur = ldg16_stream(res + i * N);
       float rv[N];
       unpack<T>(ur, rv);
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = v[j] * sc[j] + sh[j] + rv[j];
+      for (int j = 0; j < N; ++j) v[j] = fmaf(v[j], sc[j], sh[j]) + rv[j];
     } else {
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = v[j] * sc[j] + sh[j];
+      for (int j = 0; j < N; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
     }
     if (RELU) {
       uint32_t bits = 0;
@@ -217,9 +219,24 @@ apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__
         bits |= (v[j] > 0.f ? 1u : 0u) << j;
         v[j] = fmaxf(v[j], 0.f);
       }
-      if (mask != nullptr) mask[i] = (uint8_t)bits;   // 1 bit / element: what the backward needs instead of y
+      if (mask != nullptr) mask[idx] = (uint8_t)bits;   // 1 bit / element: what the backward needs instead of y
     }
-    stg16(y + i * N, pack<T>(v));
+    stg16(y + idx * N, pack<T>(v));
+  };
+  for (; i + (kUnroll - 1) * stride < total; i += kUnroll * stride) {
+    uint4 u[kUnroll], ur[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      u[k] = ldg16_stream(x + (i + k * stride) * N);
+      if (RES) ur[k] = ldg16_stream(res + (i + k * stride) * N);
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) body(i + k * stride, u[k], ur[k]);
+  }
+  for (; i < total; i += stride) {
+    uint4 u = ldg16_stream(x + i * N), ur = make_uint4(0, 0, 0, 0);
+    if (RES) ur = ldg16_stream(res + i * N);
+    body(i, u, ur);
   }
 }
 
@@ -258,24 +275,41 @@ bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8
   const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
   const int64_t row_begin = (int64_t)blockIdx.x * rows_per_block;
   const int64_t row_end = min(M, row_begin + rows_per_block);
-  for (int64_t r = row_begin + r0; r < row_end; r += rpi) {
-    const int64_t off = r * C + (int64_t)col * N;
-    uint4 ud = ldg16_stream(dy + off);
-    uint4 ux = ldg16_stream(x + off);
+  auto body = [&](const uint4& ud, const uint4& ux, uint32_t bits) {
     float dv[N], xv[N];
     unpack<T>(ud, dv);
     unpack<T>(ux, xv);
     if (RELU) {
-      const uint32_t bits = mask[r * CV + col];
 #pragma unroll
       for (int j = 0; j < N; ++j) dv[j] = ((bits >> j) & 1u) ? dv[j] : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       s[j] += dv[j];
-      s2[j] += dv[j] * (xv[j] - mu[j]) * is[j];
+      s2[j] = fmaf(dv[j], xv[j] - mu[j], s2[j]);   // invstd is applied once after the loop
     }
+  };
+  int64_t r = row_begin + r0;
+  for (; r + (kUnroll - 1) * rpi < row_end; r += kUnroll * rpi) {
+    uint4 ud[kUnroll], ux[kUnroll];
+    uint32_t bits[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      const int64_t off = (r + k * rpi) * C + (int64_t)col * N;
+      ud[k] = ldg16_stream(dy + off);
+      ux[k] = ldg16_stream(x + off);
+      bits[k] = RELU ? (uint32_t)__ldg(mask + (r + k * rpi) * CV + col) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) body(ud[k], ux[k], bits[k]);
   }
+  for (; r < row_end; r += rpi) {
+    const int64_t off = r * C + (int64_t)col * N;
+    const uint4 ud = ldg16_stream(dy + off), ux = ldg16_stream(x + off);
+    body(ud, ux, RELU ? (uint32_t)__ldg(mask + r * CV + col) : 0u);
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) s2[j] *= is[j];
   __shared__ float red[kThreads][2 * 8 + 1];
 #pragma unroll
   for (int j = 0; j < N; ++j) {
@@ -350,21 +384,40 @@ bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8_
     a2[j] = __ldg(c2 + col * N + j);
     a3[j] = __ldg(c3 + col * N + j);
   }
-  for (; i < total; i += stride) {
-    uint4 ud = ldg16_stream(dy + i * N);
-    uint4 ux = ldg16_stream(x + i * N);
+  float k1[N], k0[N];   // dx = a1*dv - a1*is*a3 * x + (a1*is*a3*mu - a1*a2)  -> two FMAs per element
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    k1[j] = -a1[j] * is[j] * a3[j];
+    k0[j] = -k1[j] * mu[j] - a1[j] * a2[j];
+  }
+  auto body = [&](int64_t idx, const uint4& ud, const uint4& ux, uint32_t bits) {
     float dv[N], xv[N], o[N];
     unpack<T>(ud, dv);
     unpack<T>(ux, xv);
     if (RELU) {
-      const uint32_t bits = mask[i];
 #pragma unroll
       for (int j = 0; j < N; ++j) dv[j] = ((bits >> j) & 1u) ? dv[j] : 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < N; ++j) o[j] = a1[j] * (dv[j] - a2[j] - (xv[j] - mu[j]) * is[j] * a3[j]);
-    stg16(dx + i * N, pack<T>(o));
-    if (RES) stg16(dres + i * N, pack<T>(dv));
+    for (int j = 0; j < N; ++j) o[j] = fmaf(a1[j], dv[j], fmaf(k1[j], xv[j], k0[j]));
+    stg16(dx + idx * N, pack<T>(o));
+    if (RES) stg16(dres + idx * N, pack<T>(dv));
+  };
+  for (; i + (kUnroll - 1) * stride < total; i += kUnroll * stride) {
+    uint4 ud[kUnroll], ux[kUnroll];
+    uint32_t bits[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      ud[k] = ldg16_stream(dy + (i + k * stride) * N);
+      ux[k] = ldg16_stream(x + (i + k * stride) * N);
+      bits[k] = RELU ? (uint32_t)__ldg(mask + i + k * stride) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) body(i + k * stride, ud[k], ux[k], bits[k]);
+  }
+  for (; i < total; i += stride) {
+    const uint4 ud = ldg16_stream(dy + i * N), ux = ldg16_stream(x + i * N);
+    body(i, ud, ux, RELU ? (uint32_t)__ldg(mask + i) : 0u);
   }
 }
 

@@ -32,14 +32,37 @@ namespace gemm {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 384;      // 4 control warps + 8 epilogue warps
-constexpr int kEpiThreads = 256;   // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int kThreads = 384;      // 4 control warps + 2 epilogue groups of 4 warps
+constexpr int kGroupThreads = 128; // one epilogue group = one warp per TMEM lane quarter
 constexpr int kMaxStatCols = 2048; // per-CTA column-statistics accumulators kept in shared memory
+constexpr int kSlabBytes = BLOCK_M * 128;  // one 128B-swizzled output box: 128 rows x 128 bytes
+
+// n / d for a launch-constant d without an integer divide (tile decode runs once per tile in every role).
+struct FastDiv {
+  uint32_t d, mul, shift;
+  __device__ __forceinline__ uint32_t div(uint32_t n) const {
+    return (uint32_t)(((uint64_t)__umulhi(n, mul) + n) >> shift);
+  }
+};
+
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.shift = s;
+  f.mul = (uint32_t)((((1ull << 32) * ((1ull << s) - d)) / d) + 1);
+  return f;
+}
 
 struct Params {
   int M, N, K;          // logical problem: D[M,N] = A[M,K] * B[N,K]^T   (K = reduction)
   int num_splits;       // split-K factor (>1 only with REDUCE epilogue)
   int kb_per_split;     // k-blocks per split
+  // rasterisation: groups of `gm` m-blocks; inside a group the m-block index runs fastest, so the tiles that share
+  // an A panel (same m-block, different n-block) are at most gm tiles apart and hit L2.
+  int gm, full_groups, tail_gm;
+  FastDiv d_split, d_group, d_gm, d_tail;
   const float* bias;    // [N] or null
   int relu;
   float* col_sum;       // [N] fp32 accumulators (atomicAdd) or null : sum over rows of stored output
@@ -55,14 +78,34 @@ struct Smem {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BN * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kDBytes = BLOCK_M * BN * (int)sizeof(OutT);
-  static constexpr int kDBufs = sizeof(OutT) == 2 ? 2 : 1;   // double-buffered staging for the streaming bf16 case
+  static constexpr int kSlabCols = 128 / (int)sizeof(OutT);      // 64 bf16 / 32 fp32 columns per staged slab
+  static constexpr int kSlabs = BN / kSlabCols;
+  static constexpr int kGroupBufs = 2;                           // staging slabs per epilogue group
+  static constexpr int kStagingBytes = 2 * kGroupBufs * kSlabBytes;
   static constexpr int kStatBytes = 2 * kMaxStatCols * 4;
-  static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - kStatBytes;
-  static constexpr int kStagesRaw = (kBudget - kDBufs * kDBytes) / kStageBytes;
+  static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - kStatBytes - kStagingBytes;
+  static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kTotal = kStages * kStageBytes + kDBufs * kDBytes + kStatBytes + 256 + 1024;
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kStatBytes + 256 + 1024;
+  static_assert(kStages >= 3, "smem budget too small for a 3-stage pipeline");
 };
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
 
 template <int BN, bool A_MN, bool B_MN, typename OutT, bool REDUCE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -71,15 +114,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   using S = Smem<BN, OutT>;
   constexpr int kStages = S::kStages;
   constexpr int kTmemCols = 2 * BN;  // double-buffered fp32 accumulators (power of two >= 32)
-  constexpr int kOutBoxCols = 128 / (int)sizeof(OutT);  // columns per 128B-swizzled output box
-  constexpr int kOutBoxes = BN / kOutBoxCols;
+  constexpr int kSlabCols = S::kSlabCols;
+  constexpr int kSlabs = S::kSlabs;
+  constexpr int kGroupBufs = S::kGroupBufs;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * S::kABytes;
   uint8_t* smem_d0 = smem + kStages * S::kStageBytes;
-  float* colacc = reinterpret_cast<float*>(smem_d0 + S::kDBufs * S::kDBytes);   // [2][kMaxStatCols]
+  float* colacc = reinterpret_cast<float*>(smem_d0 + S::kStagingBytes);   // [2][kMaxStatCols]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(colacc) + S::kStatBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
@@ -107,7 +151,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], kEpiThreads / 32);
+      ptx::mbar_init(&tmem_empty[i], kSlabs * 4);   // every slab of a tile is drained by the 4 warps of one group
     }
     ptx::fence_barrier_init();
   }
@@ -121,10 +165,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_base_slot;
 
   auto decode = [&](int w, int& m_blk, int& n_blk, int& kb0, int& kb1) {
-    int split = w % p.num_splits;
-    int tile = w / p.num_splits;
-    m_blk = tile / num_n;
-    n_blk = tile % num_n;
+    const uint32_t tile = p.d_split.div((uint32_t)w);
+    const int split = w - (int)tile * p.num_splits;
+    const uint32_t grp = p.d_group.div(tile);
+    const uint32_t within = tile - grp * p.d_group.d;
+    uint32_t nb, gm_eff;
+    if ((int)grp >= p.full_groups) {
+      nb = p.d_tail.div(within);
+      gm_eff = p.tail_gm;
+    } else {
+      nb = p.d_gm.div(within);
+      gm_eff = p.gm;
+    }
+    n_blk = (int)nb;
+    m_blk = (int)(grp * p.gm + (within - nb * gm_eff));
     kb0 = split * p.kb_per_split;
     kb1 = kb0 + p.kb_per_split;
     if (kb1 > num_kb_total) kb1 = num_kb_total;
@@ -211,162 +265,170 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (8 warps, 256 threads) =====================
-    constexpr int kColsPerWarp = BN / 2;          // two warps share a lane quarter, each owns half the columns
-    constexpr int kChunks = kColsPerWarp / 32;    // 32-column TMEM loads per warp
+    // ===================== epilogue: two independent groups of 4 warps =====================
+    // A tile's accumulator is drained slab by slab (slab = one 128B-wide swizzled output box: 64 bf16 or 32 fp32
+    // columns).  Slabs alternate between the two groups, each group owns kGroupBufs staging slabs and its own
+    // named barrier, and one thread per group issues the TMA stores -- so one group's TMEM->smem conversion
+    // overlaps the other group's store/statistics, and the per-thread code per slab is ~100 instructions.
+    const int g = (warp - 4) >> 2;                // epilogue group
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;             // which half of the tile's columns
     const int row = q * 32 + lane;                // row of the tile owned by this thread
+    const int gtid = (threadIdx.x - 128) & (kGroupThreads - 1);
     const int epi_tid = threadIdx.x - 128;        // 0..255
-    const bool stats_smem = (p.col_sum != nullptr) && (p.N <= kMaxStatCols);
+    const bool leader = (gtid == 0);
+    const int bar_id = 1 + g;
+    const uint32_t stage_base = ptx::smem_u32(smem_d0 + g * (kGroupBufs * kSlabBytes));
+    const uint32_t swz = (uint32_t)(row & 7);
+    const bool want_stats = (sizeof(OutT) == 2) && (p.col_sum != nullptr);
+    const bool stats_smem = want_stats && (p.N <= kMaxStatCols);
     if (stats_smem) {
-      for (int i = epi_tid; i < 2 * kMaxStatCols; i += kEpiThreads) colacc[i] = 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = epi_tid; i < 2 * kMaxStatCols; i += 2 * kGroupThreads) colacc[i] = 0.f;
+      named_bar_sync(3, 2 * kGroupThreads);
     }
     int it = 0;
+    uint32_t slab_seq = 0;   // slabs seen by this CTA (both groups count identically)
+    uint32_t my_cnt = 0;     // slabs processed by this group -> staging buffer rotation
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
       int m_blk, n_blk, kb0, kb1;
       decode(w, m_blk, n_blk, kb0, kb1);
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      uint8_t* smem_d = smem_d0 + (S::kDBufs == 2 ? (it & 1) * S::kDBytes : 0);
-      // the staging buffer about to be overwritten must have been drained by its previous TMA store
-      if (epi_tid == 0) {
-        if (S::kDBufs == 2) ptx::tma_wait_group_read<1>();
-        else ptx::tma_wait_group_read<0>();
-      }
-      // residual addend: issue the global loads before blocking on the accumulator
       const int grow = m_blk * BLOCK_M + row;
-      uint4 cadd[kChunks * 4];
-      if (p.addend != nullptr) {
+      bool acc_ready = false;
+#pragma unroll 1
+      for (int s = 0; s < kSlabs; ++s, ++slab_seq) {
+        if ((int)(slab_seq & 1) != g) continue;
+        const uint32_t sd = stage_base + (my_cnt % kGroupBufs) * kSlabBytes;
+        ++my_cnt;
+        const int col0 = n_blk * BN + s * kSlabCols;   // first global column of this slab
+        // residual addend: issue the global loads before blocking on the accumulator
+        uint4 cadd[sizeof(OutT) == 2 ? 8 : 1];
+        if constexpr (sizeof(OutT) == 2) {
+          if (p.addend != nullptr) {
+            const __nv_bfloat16* src = p.addend + (int64_t)grow * p.ldc + col0;
 #pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-          const int col0 = n_blk * BN + half * kColsPerWarp + c * 32;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (grow < p.M && col0 + i * 8 < p.N)
-              cadd[c * 4 + i] = *reinterpret_cast<const uint4*>(p.addend + (int64_t)grow * p.ldc + col0 + i * 8);
-            else
-              cadd[c * 4 + i] = make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < 8; ++i) {
+              if (grow < p.M && col0 + i * 8 < p.N) cadd[i] = *reinterpret_cast<const uint4*>(src + i * 8);
+              else cadd[i] = make_uint4(0, 0, 0, 0);
+            }
           }
         }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      ptx::mbar_wait(&tmem_full[buf], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * BN + half * kColsPerWarp + ((uint32_t)(q * 32) << 16);
-      uint32_t r[kChunks][32];
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) ptx::tmem_ld_32x32b_x32(taddr + c * 32, r[c]);
-      ptx::tmem_ld_wait();
-      // all TMEM reads of this warp are done: hand the accumulator back to the MMA warp as early as possible
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const int cc = half * kChunks + c;              // 32-column chunk index within the tile
-        const int col0 = n_blk * BN + cc * 32;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[c][j]);
-          if (p.bias != nullptr && (col0 + j) < p.N) x += __ldg(p.bias + col0 + j);
-          v[j] = x;
+        // the staging slab about to be overwritten must have been drained by its previous TMA store
+        if (leader) ptx::tma_wait_group_read<kGroupBufs - 1>();
+        named_bar_sync(bar_id, kGroupThreads);
+        if (!acc_ready) {
+          ptx::mbar_wait(&tmem_full[buf], acc_phase);
+          ptx::tc_fence_after();
+          acc_ready = true;
         }
-        if (p.addend != nullptr) {
+        const uint32_t taddr = tmem_base + buf * BN + s * kSlabCols + ((uint32_t)(q * 32) << 16);
+        uint32_t r[kSlabCols];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cadd[c * 4 + i]);
+        for (int c = 0; c < kSlabCols / 32; ++c) ptx::tmem_ld_32x32b_x32(taddr + c * 32, r + c * 32);
+        ptx::tmem_ld_wait();
+        // this warp is done with TMEM for this slab: release (the MMA warp waits for all kSlabs*4 arrivals)
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+        float v[kSlabCols];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              v[i * 8 + 2 * k] += __low2float(h[k]);
-              v[i * 8 + 2 * k + 1] += __high2float(h[k]);
+        for (int j = 0; j < kSlabCols; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < kSlabCols / 4; ++i) {
+            if (col0 + i * 4 < p.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+              v[i * 4 + 0] += b4.x; v[i * 4 + 1] += b4.y; v[i * 4 + 2] += b4.z; v[i * 4 + 3] += b4.w;
+            }
+          }
+        }
+        if constexpr (sizeof(OutT) == 2) {
+          if (p.addend != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cadd[i]);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                v[i * 8 + 2 * k] += __low2float(h[k]);
+                v[i * 8 + 2 * k + 1] += __high2float(h[k]);
+              }
             }
           }
         }
         if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          for (int j = 0; j < kSlabCols; ++j) v[j] = fmaxf(v[j], 0.f);
         }
+        const uint32_t rbase = sd + (uint32_t)row * 128u;
         if constexpr (sizeof(OutT) == 2) {
-          // 32 bf16 = 64B = 4 x 16B chunks; box = cc/2, logical 16B chunk = (cc%2)*4 + i, XOR-swizzled by row
-          uint8_t* box = smem_d + (cc >> 1) * (BLOCK_M * 128) + row * 128;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 pk;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i * 8 + 0], v[i * 8 + 1]);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i * 8 + 2], v[i * 8 + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i * 8 + 4], v[i * 8 + 5]);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i * 8 + 6], v[i * 8 + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&h0);
-            pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<uint32_t*>(&h2);
-            pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            const int chunk = ((cc & 1) * 4 + i) ^ (row & 7);
-            *reinterpret_cast<uint4*>(box + chunk * 16) = pk;
-          }
+          for (int i = 0; i < 8; ++i)   // 8 x 16B chunks = 64 bf16, XOR-swizzled by row (TMA SWIZZLE_128B)
+            st_shared_v4(rbase + (((uint32_t)i ^ swz) << 4), pack_bf16(v[i * 8 + 0], v[i * 8 + 1]),
+                         pack_bf16(v[i * 8 + 2], v[i * 8 + 3]), pack_bf16(v[i * 8 + 4], v[i * 8 + 5]),
+                         pack_bf16(v[i * 8 + 6], v[i * 8 + 7]));
         } else {
-          // 32 fp32 = 128B = one full swizzled row of box cc
-          uint8_t* box = smem_d + cc * (BLOCK_M * 128) + row * 128;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint4 pk;
-            pk.x = __float_as_uint(v[i * 4 + 0]);
-            pk.y = __float_as_uint(v[i * 4 + 1]);
-            pk.z = __float_as_uint(v[i * 4 + 2]);
-            pk.w = __float_as_uint(v[i * 4 + 3]);
-            const int chunk = i ^ (row & 7);
-            *reinterpret_cast<uint4*>(box + chunk * 16) = pk;
-          }
+          for (int i = 0; i < 8; ++i)   // 8 x 16B chunks = 32 fp32
+            st_shared_v4(rbase + (((uint32_t)i ^ swz) << 4), __float_as_uint(v[i * 4 + 0]),
+                         __float_as_uint(v[i * 4 + 1]), __float_as_uint(v[i * 4 + 2]), __float_as_uint(v[i * 4 + 3]));
         }
-      }
-      // make generic-proxy smem writes visible to the async proxy, then one thread issues the TMA stores
-      ptx::fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (p.col_sum != nullptr) {
-        // per-column sum / sum-of-squares of the values as stored (rounded), for fused BatchNorm statistics.
-        // thread t owns column t (t < BN); rows beyond M are zero because TMA zero-filled A.
+        // make generic-proxy smem writes visible to the async proxy, then one thread issues the TMA store
+        ptx::fence_proxy_async_smem();
+        named_bar_sync(bar_id, kGroupThreads);
+        if (leader) {
+          const void* src = smem_d0 + (sd - ptx::smem_u32(smem_d0));
+          if constexpr (REDUCE) ptx::tma_reduce_add_2d(&tmD, src, col0, m_blk * BLOCK_M);
+          else ptx::tma_store_2d(&tmD, src, col0, m_blk * BLOCK_M);
+          ptx::tma_commit_group();
+        }
         if constexpr (sizeof(OutT) == 2) {
-          if (epi_tid < BN) {
-            const int colg = n_blk * BN + epi_tid;
-            if (colg < p.N) {
-              const uint8_t* box = smem_d + (epi_tid >> 6) * (BLOCK_M * 128);
-              const int cl = epi_tid & 63;
-              float s = 0.f, s2 = 0.f;
-#pragma unroll 8
-              for (int rr = 0; rr < BLOCK_M; ++rr) {
-                const int chunk = (cl >> 3) ^ (rr & 7);
-                float x = __bfloat162float(
-                    *reinterpret_cast<const __nv_bfloat16*>(box + rr * 128 + chunk * 16 + (cl & 7) * 2));
-                s += x;
-                s2 += x * x;
+          if (want_stats) {
+            // per-column sum / sum-of-squares of the values as stored (rounded), for fused BatchNorm statistics.
+            // thread -> (8-column octet o, 8-row group rg); rows beyond M are zero because TMA zero-filled A.
+            const int o = gtid & 7, rg = gtid >> 3;
+            float s1[8], s2[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+              const uint4 u = ld_shared_v4(sd + (uint32_t)(rg * 8 + rr) * 128u + (((uint32_t)o ^ (uint32_t)rr) << 4));
+              const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float lo = __uint_as_float(wds[k] << 16), hi = __uint_as_float(wds[k] & 0xffff0000u);
+                s1[2 * k] += lo; s2[2 * k] = fmaf(lo, lo, s2[2 * k]);
+                s1[2 * k + 1] += hi; s2[2 * k + 1] = fmaf(hi, hi, s2[2 * k + 1]);
               }
-              if (stats_smem) {   // one thread per column per tile: plain accumulate, flushed once at kernel end
-                colacc[colg] += s;
-                colacc[kMaxStatCols + colg] += s2;
-              } else {
-                atomicAdd(p.col_sum + colg, s);
-                atomicAdd(p.col_sumsq + colg, s2);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {   // lanes with equal (lane & 7) hold the same octet: fold the 4 row groups
+              s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 8);
+              s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], 8);
+              s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 16);
+              s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], 16);
+            }
+            if (lane < 8) {
+              const int colg = col0 + o * 8;
+              if (colg < p.N) {   // N % 8 == 0 (TMA row-stride constraint) so an octet is all-in or all-out
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  if (stats_smem) {
+                    atomicAdd(&colacc[colg + k], s1[k]);
+                    atomicAdd(&colacc[kMaxStatCols + colg + k], s2[k]);
+                  } else {
+                    atomicAdd(p.col_sum + colg + k, s1[k]);
+                    atomicAdd(p.col_sumsq + colg + k, s2[k]);
+                  }
+                }
               }
             }
           }
         }
       }
-      if (epi_tid == 0) {
-#pragma unroll
-        for (int j = 0; j < kOutBoxes; ++j) {
-          if constexpr (REDUCE)
-            ptx::tma_reduce_add_2d(&tmD, smem_d + j * (BLOCK_M * 128), n_blk * BN + j * kOutBoxCols, m_blk * BLOCK_M);
-          else
-            ptx::tma_store_2d(&tmD, smem_d + j * (BLOCK_M * 128), n_blk * BN + j * kOutBoxCols, m_blk * BLOCK_M);
-        }
-        ptx::tma_commit_group();
-      }
     }
     if (stats_smem) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int c = epi_tid; c < p.N; c += kEpiThreads) {
+      named_bar_sync(3, 2 * kGroupThreads);
+      for (int c = epi_tid; c < p.N; c += 2 * kGroupThreads) {
         const float a = colacc[c], b = colacc[kMaxStatCols + c];
         if (a != 0.f || b != 0.f) {
           atomicAdd(p.col_sum + c, a);
@@ -374,7 +436,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-    if (epi_tid == 0) ptx::tma_wait_group<0>();
+    if (leader) ptx::tma_wait_group<0>();
   }
 
   ptx::tc_fence_before();
@@ -449,8 +511,20 @@ static void launch(const void* A, const void* B, void* D, int M, int N, int K, i
   p.addend = reinterpret_cast<const __nv_bfloat16*>(addend); p.ldc = ldc;
   if (addend != nullptr && ((reinterpret_cast<uintptr_t>(addend) & 15) != 0 || (ldc % 8) != 0))
     throw std::runtime_error("gemm: addend must be 16B aligned with a row stride multiple of 8");
+  if (bias != nullptr && ((reinterpret_cast<uintptr_t>(bias) & 15) != 0 || (N % 4) != 0))
+    throw std::runtime_error("gemm: bias must be 16B aligned and N a multiple of 4");
   p.dbg_lbo_a = dbg ? dbg[0] : 0; p.dbg_sbo_a = dbg ? dbg[1] : 0; p.dbg_lbo_b = dbg ? dbg[2] : 0; p.dbg_sbo_b = dbg ? dbg[3] : 0;
-  const int num_work = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN) * p.num_splits;
+  const int num_m = (M + BLOCK_M - 1) / BLOCK_M, num_n = (N + BN - 1) / BN;
+  p.gm = num_m < 16 ? num_m : 16;
+  p.full_groups = num_m / p.gm;
+  p.tail_gm = num_m - p.full_groups * p.gm;
+  p.d_split = make_fastdiv((uint32_t)p.num_splits);
+  p.d_group = make_fastdiv((uint32_t)(p.gm * num_n));
+  p.d_gm = make_fastdiv((uint32_t)p.gm);
+  p.d_tail = make_fastdiv((uint32_t)(p.tail_gm > 0 ? p.tail_gm : 1));
+  const int64_t num_work64 = (int64_t)num_m * num_n * p.num_splits;
+  if (num_work64 > (1ll << 30)) throw std::runtime_error("gemm: too many tiles");
+  const int num_work = (int)num_work64;
   int ctas = max_ctas > 0 ? max_ctas : kNumSMs;
   if (ctas > num_work) ctas = num_work;
   auto kern = gemm_kernel<BN, A_MN, B_MN, OutT, REDUCE>;
@@ -474,16 +548,33 @@ MXB_API int MXBGemmBf16(int mode, const void* A, const void* B, void* D, int M, 
   MXB_TRY
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   MXB_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
-  const bool bn64 = (block_n == 64) || (block_n == 0 && N <= 64);
+  // tile width: explicit, or the cheapest by a wave-quantisation estimate (a 256-wide tile costs 2 units, a 128-wide
+  // one 1.25: it moves 1.33x the operand bytes per flop through shared memory)
+  int bn = block_n;
+  if (bn != 64 && bn != 128 && bn != 256) {
+    if (N <= 64) bn = 64;
+    else if (N <= 128) bn = 128;
+    else {
+      const int64_t nm = (M + 127) / 128;
+      const int sp = (mode == 2 && splits > 1) ? splits : 1;
+      const int64_t t128 = nm * ((N + 127) / 128) * sp, t256 = nm * ((N + 255) / 256) * sp;
+      const double c128 = 1.25 * (double)((t128 + kNumSMs - 1) / kNumSMs), c256 = 2.0 * (double)((t256 + kNumSMs - 1) / kNumSMs);
+      bn = c256 <= c128 ? 256 : 128;
+    }
+  }
+#define MXB_GEMM_DISPATCH(AMN, BMN, OUT, RED, SPL)                                                                   \
+  do {                                                                                                                \
+    if (bn == 64) gemm::launch<64, AMN, BMN, OUT, RED>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
+    else if (bn == 128) gemm::launch<128, AMN, BMN, OUT, RED>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
+    else gemm::launch<256, AMN, BMN, OUT, RED>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
+  } while (0)
   if (mode == 0) {
-    if (bn64) gemm::launch<64, false, false, __nv_bfloat16, false>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, 1, max_ctas, dbg, s);
-    else gemm::launch<128, false, false, __nv_bfloat16, false>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, 1, max_ctas, dbg, s);
+    MXB_GEMM_DISPATCH(false, false, __nv_bfloat16, false, 1);
   } else if (mode == 1) {
-    if (bn64) gemm::launch<64, false, true, __nv_bfloat16, false>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, 1, max_ctas, dbg, s);
-    else gemm::launch<128, false, true, __nv_bfloat16, false>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, 1, max_ctas, dbg, s);
+    MXB_GEMM_DISPATCH(false, true, __nv_bfloat16, false, 1);
   } else if (mode == 2) {
-    if (bn64) gemm::launch<64, true, true, float, true>(A, B, D, M, N, K, lda, ldb, ldd, nullptr, 0, nullptr, nullptr, nullptr, 0, splits, max_ctas, dbg, s);
-    else gemm::launch<128, true, true, float, true>(A, B, D, M, N, K, lda, ldb, ldd, nullptr, 0, nullptr, nullptr, nullptr, 0, splits, max_ctas, dbg, s);
+    MXB_CHECK(bias == nullptr && relu == 0 && col_sum == nullptr && addend == nullptr, "TN mode has a plain reduce-add epilogue");
+    MXB_GEMM_DISPATCH(true, true, float, true, splits);
   } else {
     throw std::runtime_error("MXBGemmBf16: bad mode");
   }

@@ -42,6 +42,30 @@ def test_gemm_nt_bias_relu_bn64():
         assert _rel_err(y, ref) < 2e-2
 
 
+@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("M,N,K", [(20000, 256, 64), (2500, 520, 200), (4224, 1024, 256)])
+def test_gemm_all_modes_every_tile_width(M, N, K, bn):
+    """fwd (bias+relu, column stats), dgrad (+addend) and wgrad for each tile width incl. ragged M/N/K tails and more
+    tiles than CTAs (exercises the grouped rasterisation and the slab epilogue)."""
+    from mxb200.ops import functional as K_
+    x = torch.randn(M, K, device=_dev()).bfloat16()
+    w = (torch.randn(N, K, device=_dev()) * 0.1).bfloat16()
+    b = torch.randn(N, device=_dev())
+    y = K_.gemm_nt(x, w, bias=b, relu=True, block_n=bn)
+    assert _rel_err(y, torch.relu(x.float() @ w.float().t() + b)) < 2e-2
+    s, s2 = torch.zeros(N, device=_dev()), torch.zeros(N, device=_dev())
+    y = K_.gemm_nt(x, w, col_stats=(s, s2), block_n=bn)
+    assert _rel_err(y, x.float() @ w.float().t()) < 2e-2
+    assert _rel_err(s, y.float().sum(0)) < 2e-3
+    assert _rel_err(s2, (y.float() ** 2).sum(0)) < 2e-3
+    dy = (torch.randn(M, N, device=_dev()) * 0.1).bfloat16()
+    add = torch.randn(M, K, device=_dev()).bfloat16()
+    dx = K_.gemm_nn(dy, w, addend=add, block_n=bn)
+    assert _rel_err(dx, dy.float() @ w.float() + add.float()) < 2e-2
+    dw = K_.gemm_tn(dy, x, out_dtype=torch.float32, block_n=bn)
+    assert _rel_err(dw, dy.float().t() @ x.float()) < 2e-2
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 128, 64), (3136, 256, 64), (1000, 2048, 1000), (777, 264, 520)])
 def test_gemm_nn(M, N, K):
     # dx[M,K] = dy[M,N] @ w[N,K]

@@ -68,6 +68,24 @@ for (M, N, Kd) in shapes:
     results.append(row)
     del x, w, dy
 
+print("== GEMM tile-width sweep (block_n 128 vs 256, fwd with and without fused BN statistics)")
+sweep = []
+for (M, N, Kd) in [s for s in shapes if s[1] >= 256 and s[0] > 256]:
+    x = torch.randn(M, Kd, device=dev).bfloat16()
+    w = torch.randn(N, Kd, device=dev).bfloat16()
+    dy = torch.randn(M, N, device=dev).bfloat16()
+    st = (torch.zeros(N, device=dev), torch.zeros(N, device=dev))
+    row = {"M": M, "N": N, "K": Kd}
+    for bn in (128, 256):
+        row["fwd_bn%d" % bn] = timeit(lambda: K.gemm_nt(x, w, block_n=bn))
+        row["fwd_stats_bn%d" % bn] = timeit(lambda: K.gemm_nt(x, w, col_stats=st, block_n=bn))
+        if M != 8192:
+            row["dgrad_bn%d" % bn] = timeit(lambda: K.gemm_nn(dy, w, block_n=bn if Kd >= 256 else 0))
+    row["fwd_auto"] = timeit(lambda: K.gemm_nt(x, w))
+    print(" ".join("%s=%s" % (k, ("%.3f" % v) if isinstance(v, float) else v) for k, v in row.items()))
+    sweep.append(row)
+    del x, w, dy
+
 print("== BN(+add)+ReLU training fwd+bwd, NHWC bf16: ours vs torch eager (batch_norm + add + relu, channels_last)")
 bn_rows = []
 for (n, h, c, res) in [(256, 112, 64, False), (256, 56, 64, False), (256, 56, 256, True), (256, 28, 512, True),
@@ -109,4 +127,4 @@ for (n, h, c, res) in [(256, 112, 64, False), (256, 56, 64, False), (256, 56, 25
 
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/microbench.json", "w") as f:
-    json.dump({"peaks": PEAKS, "gemm": results, "bn": bn_rows}, f, indent=1)
+    json.dump({"peaks": PEAKS, "gemm": results, "gemm_block_n_sweep": sweep, "bn": bn_rows}, f, indent=1)
