@@ -14,6 +14,8 @@
 //             blocks, the masked gradient dy' for the skip branch in the same pass.
 // Layout: x is [M, C] with C contiguous (NHWC); C*sizeof(T) must be a multiple of 16 and C/VEC a power of
 // two <= 256 (all ResNet widths).  Statistics are always fp32 (AccReal in the reference).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mxb {
@@ -62,6 +64,7 @@ struct Finalize {
   float* sumsq;        // [C]
   unsigned int* counter;  // arrival counter (zeroed on exit)
   float* partials;     // [grid][2C] per-block partial sums (no atomics; reduced by the last block)
+  int use_atomics;     // wide layers: grid*2C partials would make the last block the bottleneck -> RED.ADD instead
   const float* gamma;  // may be null (=> 1)
   const float* beta;   // may be null (=> 0)
   float* running_mean; // may be null
@@ -74,10 +77,10 @@ struct Finalize {
   int64_t count;       // rows reduced (N*H*W)
 };
 
-__device__ __forceinline__ void finalize_channel(const Finalize& f, int c) {
+__device__ __forceinline__ void finalize_channel(const Finalize& f, int c, float sum, float sumsq) {
   const float inv_n = 1.f / (float)f.count;
-  const float mean = f.sum[c] * inv_n;
-  float var = f.sumsq[c] * inv_n - mean * mean;
+  const float mean = sum * inv_n;
+  float var = sumsq * inv_n - mean * mean;
   var = fmaxf(var, 0.f);
   const float invstd = rsqrtf(var + f.eps);
   const float g = f.gamma ? f.gamma[c] : 1.f;
@@ -150,8 +153,9 @@ stats_kernel(const T* __restrict__ x, int64_t M, int C, Finalize f) {
     for (int j = 0; j < 2 * N; ++j) {
       float a = 0.f;
       for (int k = 0; k < rpi; ++k) a += red[threadIdx.x + k * CV][j];
-      if (j < N) mine[col * N + j] = a;
-      else mine[C + col * N + (j - N)] = a;
+      const int idx = (j < N) ? (col * N + j) : (C + col * N + (j - N));
+      if (f.use_atomics) atomicAdd(f.sum + idx, a);   // sum | sumsq are contiguous: [0,C) and [C,2C)
+      else mine[idx] = a;
     }
   }
   // last block reduces the per-block partials (coalesced across channels, deterministic order) and finalises
@@ -167,13 +171,16 @@ stats_kernel(const T* __restrict__ x, int64_t M, int C, Finalize f) {
     __threadfence();
     for (int c = threadIdx.x; c < C; c += kThreads) {
       float a = 0.f, b = 0.f;
-      for (unsigned int k = 0; k < gridDim.x; ++k) {
-        a += f.partials[(size_t)k * 2 * C + c];
-        b += f.partials[(size_t)k * 2 * C + C + c];
+      if (f.use_atomics) {
+        a = __ldcg(f.sum + c);
+        b = __ldcg(f.sumsq + c);
+      } else {
+        for (unsigned int k = 0; k < gridDim.x; ++k) {
+          a += f.partials[(size_t)k * 2 * C + c];
+          b += f.partials[(size_t)k * 2 * C + C + c];
+        }
       }
-      f.sum[c] = a;
-      f.sumsq[c] = b;
-      finalize_channel(f, c);
+      finalize_channel(f, c, a, b);
     }
     if (threadIdx.x == 0) *f.counter = 0u;
   }
@@ -181,7 +188,7 @@ stats_kernel(const T* __restrict__ x, int64_t M, int C, Finalize f) {
 
 __global__ void finalize_kernel(int C, Finalize f) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) finalize_channel(f, c);
+  if (c < C) finalize_channel(f, c, f.sum[c], f.sumsq[c]);
 }
 
 template <typename T, bool RELU, bool RES>
@@ -254,6 +261,7 @@ struct BwdFinalize {
   float* c3;           // mean(dy'*xhat)
   int64_t count;
   int accumulate;      // grad_req == 'add' for dgamma/dbeta
+  int use_atomics;     // see Finalize::use_atomics
 };
 
 template <typename T, bool RELU>
@@ -323,8 +331,9 @@ bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8
     for (int j = 0; j < 2 * N; ++j) {
       float a = 0.f;
       for (int k = 0; k < rpi; ++k) a += red[threadIdx.x + k * CV][j];
-      if (j < N) mine[col * N + j] = a;
-      else mine[C + col * N + (j - N)] = a;
+      const int idx = (j < N) ? (col * N + j) : (C + col * N + (j - N));
+      if (f.use_atomics) atomicAdd(f.sum_dy + idx, a);   // sum_dy | sum_dyx are contiguous
+      else mine[idx] = a;
     }
   }
   __shared__ bool is_last;
@@ -337,19 +346,18 @@ bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8
   __syncthreads();
   if (is_last) {
     __threadfence();
-    for (int c = threadIdx.x; c < C; c += kThreads) {
-      float a = 0.f, b = 0.f;
-      for (unsigned int k = 0; k < gridDim.x; ++k) {
-        a += f.partials[(size_t)k * 2 * C + c];
-        b += f.partials[(size_t)k * 2 * C + C + c];
-      }
-      f.sum_dy[c] = a;
-      f.sum_dyx[c] = b;
-    }
-    __syncthreads();
     const float inv_n = 1.f / (float)f.count;
     for (int c = threadIdx.x; c < C; c += kThreads) {
-      const float sd = f.sum_dy[c], sdx = f.sum_dyx[c];
+      float sd = 0.f, sdx = 0.f;
+      if (f.use_atomics) {
+        sd = __ldcg(f.sum_dy + c);
+        sdx = __ldcg(f.sum_dyx + c);
+      } else {
+        for (unsigned int k = 0; k < gridDim.x; ++k) {
+          sd += f.partials[(size_t)k * 2 * C + c];
+          sdx += f.partials[(size_t)k * 2 * C + C + c];
+        }
+      }
       const float g = f.gamma ? f.gamma[c] : 1.f;
       if (f.dgamma) f.dgamma[c] = (f.accumulate ? f.dgamma[c] : 0.f) + sdx;
       if (f.dbeta) f.dbeta[c] = (f.accumulate ? f.dbeta[c] : 0.f) + sd;
@@ -459,6 +467,14 @@ static constexpr int kMaxC = 4096;
 static constexpr int kSumOff = 8;
 static constexpr int kPartOff = 8 + 2 * kMaxC;
 
+// a single block has to sum grid * 2C partials: fine up to a few hundred KB, a bottleneck beyond (measured: 0.6 ms
+// for C=2048) -> wide layers combine their block sums with fp32 RED.ADD instead (order-nondeterministic in the
+// last bits; MXB200_BN_DETERMINISTIC=1 forces the partials path)
+static int use_atomics_for(int C) {
+  static const bool det = [] { const char* e = getenv("MXB200_BN_DETERMINISTIC"); return e && e[0] == '1'; }();
+  return (!det && C >= 256) ? 1 : 0;
+}
+
 MXB_API int MXBBnWorkspaceFloats(int C) { return kPartOff + kMaxGrid * 2 * (C > kMaxC ? kMaxC : C); }
 
 MXB_API int MXBBnStatsFinalize(const void* x, int dt, int64_t M, int C, float* ws, const float* gamma,
@@ -468,8 +484,8 @@ MXB_API int MXBBnStatsFinalize(const void* x, int dt, int64_t M, int C, float* w
   MXB_TRY
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   MXB_CHECK(C <= kMaxC, "bn: at most 4096 channels");
-  Finalize f{ws + kSumOff, ws + kSumOff + C, reinterpret_cast<unsigned int*>(ws), ws + kPartOff, gamma, beta, running_mean,
-             running_var, mean_out, invstd_out, scale_out, shift_out, eps, momentum, M};
+  Finalize f{ws + kSumOff, ws + kSumOff + C, reinterpret_cast<unsigned int*>(ws), ws + kPartOff, use_atomics_for(C), gamma, beta,
+             running_mean, running_var, mean_out, invstd_out, scale_out, shift_out, eps, momentum, M};
   if (stats_precomputed) {
     finalize_kernel<<<(C + 255) / 256, 256, 0, s>>>(C, f);
   } else if (dt == kBF16) {
@@ -519,7 +535,7 @@ MXB_API int MXBBnBackward(const void* dy, const void* x, const void* mask, void*
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   MXB_CHECK(C <= kMaxC, "bn: at most 4096 channels");
   BwdFinalize f{ws + kSumOff, ws + kSumOff + C, reinterpret_cast<unsigned int*>(ws), ws + kPartOff, gamma, invstd, dgamma,
-                dbeta, coef, coef + C, coef + 2 * C, M, accumulate};
+                dbeta, coef, coef + C, coef + 2 * C, M, accumulate, use_atomics_for(C)};
   auto go = [&](auto t) {
     using T = decltype(t);
     check_shape<T>(C);

@@ -34,7 +34,7 @@ constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 384;      // 4 control warps + 2 epilogue groups of 4 warps
 constexpr int kGroupThreads = 128; // one epilogue group = one warp per TMEM lane quarter
-constexpr int kMaxStatCols = 2048; // per-CTA column-statistics accumulators kept in shared memory
+constexpr int kMaxStatCols = 1024; // per-CTA, per-epilogue-group column-statistics accumulators in shared memory
 constexpr int kSlabBytes = BLOCK_M * 128;  // one 128B-swizzled output box: 128 rows x 128 bytes
 
 // n / d for a launch-constant d without an integer divide (tile decode runs once per tile in every role).
@@ -82,7 +82,7 @@ struct Smem {
   static constexpr int kSlabs = BN / kSlabCols;
   static constexpr int kGroupBufs = 2;                           // staging slabs per epilogue group
   static constexpr int kStagingBytes = 2 * kGroupBufs * kSlabBytes;
-  static constexpr int kStatBytes = 2 * kMaxStatCols * 4;
+  static constexpr int kStatBytes = 2 /*groups*/ * 2 /*sum,sumsq*/ * kMaxStatCols * 4;
   static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - kStatBytes - kStagingBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -123,7 +123,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * S::kABytes;
   uint8_t* smem_d0 = smem + kStages * S::kStageBytes;
-  float* colacc = reinterpret_cast<float*>(smem_d0 + S::kStagingBytes);   // [2][kMaxStatCols]
+  float* colacc = reinterpret_cast<float*>(smem_d0 + S::kStagingBytes);   // [group][sum|sumsq][kMaxStatCols]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(colacc) + S::kStatBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
@@ -281,9 +281,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t swz = (uint32_t)(row & 7);
     const bool want_stats = (sizeof(OutT) == 2) && (p.col_sum != nullptr);
     const bool stats_smem = want_stats && (p.N <= kMaxStatCols);
+    float* myacc = colacc + g * (2 * kMaxStatCols);   // this group's private accumulators: no atomics needed
     if (stats_smem) {
-      for (int i = epi_tid; i < 2 * kMaxStatCols; i += 2 * kGroupThreads) colacc[i] = 0.f;
-      named_bar_sync(3, 2 * kGroupThreads);
+      for (int i = gtid; i < 2 * kMaxStatCols; i += kGroupThreads) myacc[i] = 0.f;
+      named_bar_sync(bar_id, kGroupThreads);
     }
     int it = 0;
     uint32_t slab_seq = 0;   // slabs seen by this CTA (both groups count identically)
@@ -384,52 +385,54 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if constexpr (sizeof(OutT) == 2) {
           if (want_stats) {
             // per-column sum / sum-of-squares of the values as stored (rounded), for fused BatchNorm statistics.
-            // thread -> (8-column octet o, 8-row group rg); rows beyond M are zero because TMA zero-filled A.
-            const int o = gtid & 7, rg = gtid >> 3;
-            float s1[8], s2[8];
+            // Warp wq of the group owns column octets {2wq, 2wq+1} of the slab over all 128 rows: lane -> (octet
+            // o, 8-row group rg); the row visited at step rr is rotated by rg so the 32 16-byte reads of a warp
+            // spread over all 8 swizzle positions (4 wavefronts = the 512-byte minimum).  Rows beyond M are zero
+            // because TMA zero-filled A.
+            const int wq = gtid >> 5;
+            const int o = 2 * wq + (lane & 1), rg = lane >> 1;
+            float acc[16];   // [0..8) column sums, [8..16) sums of squares of octet o
 #pragma unroll
-            for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+            for (int k = 0; k < 16; ++k) acc[k] = 0.f;
 #pragma unroll
             for (int rr = 0; rr < 8; ++rr) {
-              const uint4 u = ld_shared_v4(sd + (uint32_t)(rg * 8 + rr) * 128u + (((uint32_t)o ^ (uint32_t)rr) << 4));
+              const uint32_t r8 = (uint32_t)((rr + rg) & 7);
+              const uint4 u = ld_shared_v4(sd + (uint32_t)(rg * 8 + r8) * 128u + (((uint32_t)o ^ r8) << 4));
               const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const float lo = __uint_as_float(wds[k] << 16), hi = __uint_as_float(wds[k] & 0xffff0000u);
-                s1[2 * k] += lo; s2[2 * k] = fmaf(lo, lo, s2[2 * k]);
-                s1[2 * k + 1] += hi; s2[2 * k + 1] = fmaf(hi, hi, s2[2 * k + 1]);
+                acc[2 * k] += lo; acc[8 + 2 * k] = fmaf(lo, lo, acc[8 + 2 * k]);
+                acc[2 * k + 1] += hi; acc[8 + 2 * k + 1] = fmaf(hi, hi, acc[8 + 2 * k + 1]);
               }
             }
+            // butterfly that halves the live values at every step: 15 shuffles instead of 64; afterwards lane l
+            // holds value index ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1) of octet 2wq + (l&1)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {   // lanes with equal (lane & 7) hold the same octet: fold the 4 row groups
-              s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 8);
-              s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], 8);
-              s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 16);
-              s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], 16);
-            }
-            if (lane < 8) {
-              const int colg = col0 + o * 8;
-              if (colg < p.N) {   // N % 8 == 0 (TMA row-stride constraint) so an octet is all-in or all-out
+            for (int step = 0; step < 4; ++step) {
+              const int m = 16 >> step, half = 8 >> step;
+              const bool upper = (lane & m) != 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  if (stats_smem) {
-                    atomicAdd(&colacc[colg + k], s1[k]);
-                    atomicAdd(&colacc[kMaxStatCols + colg + k], s2[k]);
-                  } else {
-                    atomicAdd(p.col_sum + colg + k, s1[k]);
-                    atomicAdd(p.col_sumsq + colg + k, s2[k]);
-                  }
-                }
+              for (int i = 0; i < half; ++i) {
+                const float send = upper ? acc[i] : acc[i + half];
+                const float keep = upper ? acc[i + half] : acc[i];
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
               }
+            }
+            const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            const int colg = col0 + o * 8 + (vidx & 7);
+            if (colg < p.N) {
+              if (stats_smem) myacc[(vidx >> 3) * kMaxStatCols + colg] += acc[0];   // one owner lane per column: plain RMW
+              else atomicAdd((vidx >> 3) ? (p.col_sumsq + colg) : (p.col_sum + colg), acc[0]);
             }
           }
         }
       }
     }
     if (stats_smem) {
-      named_bar_sync(3, 2 * kGroupThreads);
-      for (int c = epi_tid; c < p.N; c += 2 * kGroupThreads) {
-        const float a = colacc[c], b = colacc[kMaxStatCols + c];
+      named_bar_sync(bar_id, kGroupThreads);
+      for (int c = gtid; c < p.N; c += kGroupThreads) {
+        const float a = myacc[c], b = myacc[kMaxStatCols + c];
         if (a != 0.f || b != 0.f) {
           atomicAdd(p.col_sum + c, a);
           atomicAdd(p.col_sumsq + c, b);
@@ -552,15 +555,13 @@ MXB_API int MXBGemmBf16(int mode, const void* A, const void* B, void* D, int M, 
   // one 1.25: it moves 1.33x the operand bytes per flop through shared memory)
   int bn = block_n;
   if (bn != 64 && bn != 128 && bn != 256) {
-    if (N <= 64) bn = 64;
-    else if (N <= 128) bn = 128;
-    else {
-      const int64_t nm = (M + 127) / 128;
-      const int sp = (mode == 2 && splits > 1) ? splits : 1;
-      const int64_t t128 = nm * ((N + 127) / 128) * sp, t256 = nm * ((N + 255) / 256) * sp;
-      const double c128 = 1.25 * (double)((t128 + kNumSMs - 1) / kNumSMs), c256 = 2.0 * (double)((t256 + kNumSMs - 1) / kNumSMs);
-      bn = c256 <= c128 ? 256 : 128;
-    }
+    // measured on B200 (profiles/microbench_*): the 256-wide tile wins whenever N > 128, even at worse wave
+    // quantisation (it moves 25% fewer operand bytes per flop through shared memory); tiny problems prefer more,
+    // narrower tiles so that more SMs take part
+    bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    const int64_t nm = (M + 127) / 128;
+    const int sp = (mode == 2 && splits > 1) ? splits : 1;
+    while (bn > 64 && nm * ((N + bn - 1) / bn) * sp < 100) bn >>= 1;
   }
 #define MXB_GEMM_DISPATCH(AMN, BMN, OUT, RED, SPL)                                                                   \
   do {                                                                                                                \

@@ -32,10 +32,29 @@ class GradientCompression(object):
     def compressed_size(n):
         return (n + 15) // 16
 
+    @staticmethod
+    def _native(t):
+        if not t.is_cuda:
+            return None
+        from .. import _native as N
+        return N.cuda() if N.have_cuda_kernels() else None
+
     def quantize(self, grad, residual):
         """grad (any float dtype), residual (fp32, updated in place) -> int32 words [ceil(n/16)]."""
         t = self.threshold
         n = grad.numel()
+        lib = self._native(grad)
+        if lib is not None and grad.dtype in (torch.float32, torch.bfloat16) and grad.is_contiguous() \
+                and residual.is_contiguous() and residual.dtype is torch.float32:
+            # one pass over grad + residual on the device (csrc/cuda/compress.cu)
+            from .. import _native as N
+            from ..ops._dtypes import code as _dt
+            from ..ops.functional import LAUNCHES
+            words = torch.empty(self.compressed_size(n), dtype=torch.int32, device=grad.device)
+            N.check(lib, lib.MXBQuantize2Bit(N.ptr(grad), N.c_int(_dt(grad.dtype)), N.ptr(residual), N.ptr(words),
+                                             N.c_int64(n), N.c_float(t), N.stream_of(grad)))
+            LAUNCHES[0] += 1
+            return words
         with torch.no_grad():
             residual.add_(grad.reshape(residual.shape).float())
             r = residual.reshape(-1)
@@ -55,8 +74,23 @@ class GradientCompression(object):
             words = torch.where(words >= 2 ** 31, words - 2 ** 32, words)
             return words.to(torch.int32)
 
-    def dequantize(self, words, n, shape, device=None):
+    def dequantize(self, words, n, shape, device=None, out=None):
+        """words -> fp32 tensor of ``shape``; with ``out`` (fp32, contiguous) the decoded values are ADDED into it
+        (how a server merges the compressed pushes of several workers)."""
         t = self.threshold
+        lib = self._native(words)
+        if lib is not None and words.dtype is torch.int32 and words.is_contiguous():
+            from .. import _native as N
+            from ..ops.functional import LAUNCHES
+            acc = out is not None
+            res = out if acc else torch.empty(n, dtype=torch.float32, device=words.device)
+            N.check(lib, lib.MXBDequantize2Bit(N.ptr(words), N.ptr(res), N.c_int64(n), N.c_float(t),
+                                               N.c_int(1 if acc else 0), N.stream_of(words)))
+            LAUNCHES[0] += 1
+            return res.reshape(shape)
+        if out is not None:
+            out.add_(self.dequantize(words, n, out.shape, device))
+            return out
         with torch.no_grad():
             w = words.to(torch.int64) & 0xFFFFFFFF
             bshift = torch.tensor([0, 8, 16, 24], device=w.device)

@@ -653,22 +653,23 @@ def FullyConnected(data, weight, bias=None, num_hidden=None, no_bias=False, flat
 
 @register
 def Activation(data, act_type="relu", out=None):
-    fn = {"relu": torch.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh,
-          "softrelu": F.softplus, "softsign": F.softsign, "gelu": F.gelu}[act_type]
-    return _out(_op(fn, data), out)
+    from ..ops.layernorm import bias_act
+
+    def _native(t):   # one fused elementwise kernel forward, one backward (csrc/cuda/layernorm.cu)
+        return bias_act(t, None, act_type)
+    if act_type == "softsign":
+        return _out(_op(F.softsign, data), out)
+    if act_type not in ("relu", "sigmoid", "tanh", "softrelu", "gelu"):
+        raise MXNetError("unknown act_type " + str(act_type))
+    return _out(_op(_native, data), out)
 
 
 @register
 def LeakyReLU(data, gamma=None, act_type="leaky", slope=0.25, lower_bound=0.125, upper_bound=0.334, out=None):
     def g(t, gm=None):
-        if act_type == "leaky":
-            return F.leaky_relu(t, slope)
-        if act_type == "elu":
-            return F.elu(t, slope)
-        if act_type == "selu":
-            return F.selu(t)
-        if act_type == "gelu":
-            return F.gelu(t)
+        if act_type in ("leaky", "elu", "selu", "gelu"):
+            from ..ops.layernorm import bias_act
+            return bias_act(t, None, act_type, slope)
         if act_type == "prelu":
             return F.prelu(t, gm.reshape(-1))
         if act_type == "rrelu":

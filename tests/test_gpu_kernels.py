@@ -432,27 +432,134 @@ def test_bn_with_gemm_stats_and_sinks():
 
 
 def test_gluon_fused_trainer_matches_unfused_on_gpu():
-    """Same ResNet-18 step through the fused arena path and through per-parameter updaters."""
+    """Fused arena Trainer (one allreduce+update kernel) vs per-parameter updaters.
+
+    Equivalence is checked on a well-conditioned MLP (a bf16 ResNet at batch 8 amplifies rounding noise so much
+    that two identical runs differ by >10% in their first gradients -- measured, see tools/diag_fused.py); the
+    ResNet-18 run checks that the fused path trains: same first loss, finite parameters, loss decreases."""
     import mxb200 as mx
     from mxb200 import gluon, autograd
+    from mxb200.gluon import nn
     from mxb200.gluon.model_zoo import vision
     import os
     ctx = mx.gpu(0)
-    x = mx.nd.from_torch(torch.randn(8, 32, 32, 3, device="cuda").bfloat16(), ctx)
-    y = mx.nd.from_torch(torch.randint(0, 10, (8,), device="cuda"), ctx)
+    torch.manual_seed(0)
+    xm = mx.nd.from_torch(torch.randn(64, 64, device="cuda").bfloat16(), ctx)
+    ym = mx.nd.from_torch(torch.randint(0, 10, (64,), device="cuda"), ctx)
     outs = []
-    for fused in ("1", "0"):
-        os.environ["MXB200_FUSED_TRAINER"] = fused
+    try:
+        for fused in ("1", "0"):
+            os.environ["MXB200_FUSED_TRAINER"] = fused
+            mx.random.seed(7)
+            net = nn.HybridSequential()
+            net.add(nn.Dense(128, activation="relu", in_units=64), nn.Dense(128, activation="relu", in_units=128),
+                    nn.Dense(16, in_units=128))
+            net.initialize(mx.init.Xavier(), ctx=ctx)
+            net.cast("bfloat16")
+            tr = gluon.Trainer(net.collect_params(), "nag", {"learning_rate": 0.05, "momentum": 0.9, "wd": 1e-4,
+                                                             "multi_precision": True})
+            L = gluon.loss.SoftmaxCrossEntropyLoss()
+            for _ in range(4):
+                with autograd.record():
+                    l = L(net(xm), ym)
+                l.backward()
+                tr.step(64)
+            outs.append([p.data().as_torch().float().clone() for p in net.collect_params().values()])
+        for a, b in zip(*outs):
+            assert _rel_err(a, b) < 2e-2
+        # the flagship family through the fused path
+        os.environ["MXB200_FUSED_TRAINER"] = "1"
+        x = mx.nd.from_torch(torch.randn(16, 32, 32, 3, device="cuda").bfloat16(), ctx)
+        y = mx.nd.from_torch(torch.randint(0, 10, (16,), device="cuda"), ctx)
         net = vision.get_resnet("v1b", 18, classes=10, thumbnail=True, ctx=ctx, dtype="bfloat16", layout="NHWC", seed=3)
-        tr = gluon.Trainer(net.collect_params(), "nag", {"learning_rate": 0.05, "momentum": 0.9, "wd": 1e-4,
+        tr = gluon.Trainer(net.collect_params(), "nag", {"learning_rate": 0.01, "momentum": 0.9, "wd": 1e-4,
                                                          "multi_precision": True})
         L = gluon.loss.SoftmaxCrossEntropyLoss()
-        for _ in range(3):
+        losses = []
+        for _ in range(8):
             with autograd.record():
                 l = L(net(x), y)
             l.backward()
-            tr.step(8)
-        outs.append([p.data().as_torch().float().clone() for p in net.collect_params().values()])
-    os.environ["MXB200_FUSED_TRAINER"] = "1"
-    for a, b in zip(*outs):
-        assert _rel_err(a, b) < 5e-2
+            tr.step(16)
+            losses.append(float(l.as_torch().detach().float().mean()))
+        assert all(math.isfinite(v) for v in losses)
+        assert losses[-1] < losses[0]          # memorising 16 images: the loss must go down
+        for p in net.collect_params().values():
+            assert bool(torch.isfinite(p.data().as_torch().float()).all())
+    finally:
+        os.environ["MXB200_FUSED_TRAINER"] = "1"
+
+
+# ----------------------------------------------------------------------------- LayerNorm / activations / 2-bit
+@pytest.mark.parametrize("C,dtype", [(768, torch.bfloat16), (1024, torch.bfloat16), (256, torch.float32), (2048, torch.bfloat16)])
+def test_layer_norm_fwd_bwd(C, dtype):
+    from mxb200.ops.layernorm import layer_norm
+    rows = 1000
+    x = torch.randn(rows, C, device=_dev()).to(dtype).requires_grad_(True)
+    g = (torch.rand(C, device=_dev()) + 0.5).requires_grad_(True)
+    b = torch.randn(C, device=_dev()).requires_grad_(True)
+    dy = torch.randn(rows, C, device=_dev()).to(dtype)
+    y = layer_norm(x, g, b, 1e-5)
+    y.backward(dy)
+    x32 = x.detach().float().requires_grad_(True)
+    g32, b32 = g.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(x32, (C,), g32, b32, 1e-5)
+    ref.backward(dy.float())
+    tol = 2e-2 if dtype is torch.bfloat16 else 1e-4
+    assert _rel_err(y, ref) < tol
+    assert _rel_err(x.grad, x32.grad) < tol
+    assert _rel_err(g.grad, g32.grad) < tol
+    assert _rel_err(b.grad, b32.grad) < tol
+
+
+def test_layer_norm_sinks_accumulate():
+    from mxb200.ops.layernorm import layer_norm
+    C, rows = 768, 512
+    x = torch.randn(rows, C, device=_dev()).bfloat16().requires_grad_(True)
+    g = torch.ones(C, device=_dev()).requires_grad_(True)
+    b = torch.zeros(C, device=_dev()).requires_grad_(True)
+    sg, sb = torch.full((C,), 2.0, device=_dev()), torch.full((C,), -1.0, device=_dev())
+    dy = torch.randn(rows, C, device=_dev()).bfloat16()
+    layer_norm(x, g, b, 1e-5, sink_g=sg, sink_b=sb).backward(dy)
+    x32 = x.detach().float().requires_grad_(True)
+    g32, b32 = g.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(x32, (C,), g32, b32, 1e-5).backward(dy.float())
+    assert g.grad is None and b.grad is None
+    assert _rel_err(sg - 2.0, g32.grad) < 2e-2 and _rel_err(sb + 1.0, b32.grad) < 2e-2
+
+
+@pytest.mark.parametrize("act", ["relu", "gelu", "gelu_tanh", "sigmoid", "tanh", "softrelu", "leaky", "elu", "selu", "silu"])
+def test_bias_act_fwd_bwd(act):
+    from mxb200.ops.layernorm import bias_act, _torch_act
+    rows, C = 333, 3072
+    x = torch.randn(rows, C, device=_dev()).bfloat16().requires_grad_(True)
+    b = torch.randn(C, device=_dev()).requires_grad_(True)
+    dy = torch.randn(rows, C, device=_dev()).bfloat16()
+    y = bias_act(x, b, act, 0.2)
+    y.backward(dy)
+    x32 = x.detach().float().requires_grad_(True)
+    b32 = b.detach().clone().requires_grad_(True)
+    ref = _torch_act(x32 + b32, act, 0.2)
+    ref.backward(dy.float())
+    assert _rel_err(y, ref) < 2e-2
+    assert _rel_err(x.grad, x32.grad) < 2e-2
+    assert _rel_err(b.grad, b32.grad) < 3e-2
+
+
+@pytest.mark.parametrize("n,dtype", [(16, torch.float32), (1000, torch.float32), (65537, torch.bfloat16)])
+def test_two_bit_compression_kernels_match_reference_format(n, dtype):
+    from mxb200.kvstore.compression import GradientCompression
+    gc = GradientCompression({"type": "2bit", "threshold": 0.5})
+    g = (torch.randn(n, device=_dev()) * 0.6).to(dtype)
+    res_dev = torch.randn(n, device=_dev()) * 0.1
+    res_cpu = res_dev.cpu().clone()
+    words = gc.quantize(g, res_dev)                       # CUDA kernel
+    words_ref = gc.quantize(g.cpu(), res_cpu)             # torch reference of the reference's wire format
+    assert torch.equal(words.cpu(), words_ref)
+    assert torch.allclose(res_dev.cpu(), res_cpu, atol=1e-6)
+    out = gc.dequantize(words, n, (n,))
+    out_ref = gc.dequantize(words_ref, n, (n,))
+    assert torch.equal(out.cpu(), out_ref)
+    acc = torch.ones(n, device=_dev())
+    gc.dequantize(words, n, (n,), out=acc)
+    assert torch.equal(acc.cpu(), out_ref + 1.0)

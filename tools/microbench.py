@@ -81,6 +81,8 @@ for (M, N, Kd) in [s for s in shapes if s[1] >= 256 and s[0] > 256]:
         row["fwd_stats_bn%d" % bn] = timeit(lambda: K.gemm_nt(x, w, col_stats=st, block_n=bn))
         if M != 8192:
             row["dgrad_bn%d" % bn] = timeit(lambda: K.gemm_nn(dy, w, block_n=bn if Kd >= 256 else 0))
+            if Kd >= 256:
+                row["wgrad_bn%d" % bn] = timeit(lambda: K.gemm_tn(dy, x, out_dtype=torch.float32, block_n=bn))
     row["fwd_auto"] = timeit(lambda: K.gemm_nt(x, w))
     print(" ".join("%s=%s" % (k, ("%.3f" % v) if isinstance(v, float) else v) for k, v in row.items()))
     sweep.append(row)
