@@ -22,6 +22,8 @@ namespace mxb {
 namespace bn {
 
 constexpr int kThreads = 256;
+constexpr int kSlabCV = 64;  // reduce kernels: a block covers at most 64 vector-columns (1 KB of a bf16 row); wider layers
+                             // are split into column slabs so that parallelism (blocks) and RED traffic (row-blocks x 2C) decouple
 constexpr int kUnroll = 4;   // independent 16-byte loads in flight per thread and per stream
 
 template <typename T>
@@ -103,9 +105,10 @@ __global__ void __launch_bounds__(kThreads)
 stats_kernel(const T* __restrict__ x, int64_t M, int C, Finalize f) {
   constexpr int N = V<T>::N;
   const int CV = C / N;
-  const int rpi = kThreads / CV;             // rows per block iteration
-  const int col = threadIdx.x % CV;
-  const int r0 = threadIdx.x / CV;
+  const int CVB = CV < kSlabCV ? CV : kSlabCV;   // vector-columns owned by this block (blockIdx.y = column slab)
+  const int rpi = kThreads / CVB;                // rows per block iteration
+  const int col = blockIdx.y * CVB + threadIdx.x % CVB;
+  const int r0 = threadIdx.x / CVB;
   float s[N], s2[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) s[j] = s2[j] = 0.f;
@@ -147,12 +150,12 @@ stats_kernel(const T* __restrict__ x, int64_t M, int C, Finalize f) {
     red[threadIdx.x][N + j] = s2[j];
   }
   __syncthreads();
-  if (threadIdx.x < CV) {
+  if (threadIdx.x < CVB) {
     float* mine = f.partials + (size_t)blockIdx.x * 2 * C;
 #pragma unroll
     for (int j = 0; j < 2 * N; ++j) {
       float a = 0.f;
-      for (int k = 0; k < rpi; ++k) a += red[threadIdx.x + k * CV][j];
+      for (int k = 0; k < rpi; ++k) a += red[threadIdx.x + k * CVB][j];
       const int idx = (j < N) ? (col * N + j) : (C + col * N + (j - N));
       if (f.use_atomics) atomicAdd(f.sum + idx, a);   // sum | sumsq are contiguous: [0,C) and [C,2C)
       else mine[idx] = a;
@@ -164,7 +167,7 @@ stats_kernel(const T* __restrict__ x, int64_t M, int C, Finalize f) {
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int prev = atomicAdd(f.counter, 1u);
-    is_last = (prev == gridDim.x - 1);
+    is_last = (prev == gridDim.x * gridDim.y - 1);
   }
   __syncthreads();
   if (is_last) {
@@ -270,9 +273,10 @@ bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8
                   int C, const float* __restrict__ mean, BwdFinalize f) {
   constexpr int N = V<T>::N;
   const int CV = C / N;
-  const int rpi = kThreads / CV;
-  const int col = threadIdx.x % CV;
-  const int r0 = threadIdx.x / CV;
+  const int CVB = CV < kSlabCV ? CV : kSlabCV;
+  const int rpi = kThreads / CVB;
+  const int col = blockIdx.y * CVB + threadIdx.x % CVB;
+  const int r0 = threadIdx.x / CVB;
   float mu[N], is[N], s[N], s2[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) {
@@ -325,12 +329,12 @@ bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8
     red[threadIdx.x][N + j] = s2[j];
   }
   __syncthreads();
-  if (threadIdx.x < CV) {
+  if (threadIdx.x < CVB) {
     float* mine = f.partials + (size_t)blockIdx.x * 2 * C;
 #pragma unroll
     for (int j = 0; j < 2 * N; ++j) {
       float a = 0.f;
-      for (int k = 0; k < rpi; ++k) a += red[threadIdx.x + k * CV][j];
+      for (int k = 0; k < rpi; ++k) a += red[threadIdx.x + k * CVB][j];
       const int idx = (j < N) ? (col * N + j) : (C + col * N + (j - N));
       if (f.use_atomics) atomicAdd(f.sum_dy + idx, a);   // sum_dy | sum_dyx are contiguous
       else mine[idx] = a;
@@ -341,7 +345,7 @@ bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int prev = atomicAdd(f.counter, 1u);
-    is_last = (prev == gridDim.x - 1);
+    is_last = (prev == gridDim.x * gridDim.y - 1);
   }
   __syncthreads();
   if (is_last) {
@@ -429,11 +433,17 @@ bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8_
   }
 }
 
-static int grid_rows(int64_t M, int rpi) {
-  // each block should own at least ~8 iterations; cap at 4 waves
-  int64_t blocks = (M + (int64_t)rpi * 8 - 1) / ((int64_t)rpi * 8);
-  blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)kNumSMs * 4));
-  return (int)blocks;
+template <typename T>
+static dim3 grid_rows(int64_t M, int C) {
+  const int CV = C / V<T>::N;
+  const int CVB = CV < kSlabCV ? CV : kSlabCV;
+  const int slabs = CV / CVB;
+  const int rpi = kThreads / CVB;
+  // one full wave of 4 resident blocks per SM in total; each block should own at least ~2 unrolled iterations
+  int64_t gx = (M + (int64_t)rpi * kUnroll * 2 - 1) / ((int64_t)rpi * kUnroll * 2);
+  const int64_t cap = std::max<int64_t>(1, (int64_t)kNumSMs * 4 / slabs);
+  gx = std::max<int64_t>(1, std::min<int64_t>(gx, cap));
+  return dim3((unsigned)gx, (unsigned)slabs, 1);
 }
 
 static int grid_elems(int64_t total_vec, int CV) {
@@ -490,12 +500,10 @@ MXB_API int MXBBnStatsFinalize(const void* x, int dt, int64_t M, int C, float* w
     finalize_kernel<<<(C + 255) / 256, 256, 0, s>>>(C, f);
   } else if (dt == kBF16) {
     check_shape<__nv_bfloat16>(C);
-    const int rpi = kThreads / (C / 8);
-    stats_kernel<__nv_bfloat16><<<grid_rows(M, rpi), kThreads, 0, s>>>((const __nv_bfloat16*)x, M, C, f);
+    stats_kernel<__nv_bfloat16><<<grid_rows<__nv_bfloat16>(M, C), kThreads, 0, s>>>((const __nv_bfloat16*)x, M, C, f);
   } else if (dt == kF32) {
     check_shape<float>(C);
-    const int rpi = kThreads / (C / 4);
-    stats_kernel<float><<<grid_rows(M, rpi), kThreads, 0, s>>>((const float*)x, M, C, f);
+    stats_kernel<float><<<grid_rows<float>(M, C), kThreads, 0, s>>>((const float*)x, M, C, f);
   } else {
     throw std::runtime_error("bn: dtype must be bf16 or fp32");
   }
@@ -540,10 +548,9 @@ MXB_API int MXBBnBackward(const void* dy, const void* x, const void* mask, void*
     using T = decltype(t);
     check_shape<T>(C);
     const int CV = C / V<T>::N;
-    const int rpi = kThreads / CV;
     const T* dd = (const T*)dy; const T* xx = (const T*)x; const uint8_t* mm = (const uint8_t*)mask;
-    if (relu) bwd_reduce_kernel<T, true><<<grid_rows(M, rpi), kThreads, 0, s>>>(dd, xx, mm, M, C, mean, f);
-    else bwd_reduce_kernel<T, false><<<grid_rows(M, rpi), kThreads, 0, s>>>(dd, xx, mm, M, C, mean, f);
+    if (relu) bwd_reduce_kernel<T, true><<<grid_rows<T>(M, C), kThreads, 0, s>>>(dd, xx, mm, M, C, mean, f);
+    else bwd_reduce_kernel<T, false><<<grid_rows<T>(M, C), kThreads, 0, s>>>(dd, xx, mm, M, C, mean, f);
     const int g = grid_elems(M * CV, CV);
     T* ox = (T*)dx; T* orr = (T*)dres;
     if (relu && dres) bwd_apply_kernel<T, true, true><<<g, kThreads, 0, s>>>(dd, xx, mm, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);

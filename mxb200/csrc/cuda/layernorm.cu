@@ -67,8 +67,9 @@ __device__ __forceinline__ void store8<float>(float* p, const float* o) {
 
 template <typename T, int VPT>
 __global__ void __launch_bounds__(kThreads)
-fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y,
-           float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, float eps) {
+fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ sum_out, const float* __restrict__ gamma,
+           const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+           int64_t rows, float eps) {
   constexpr int C = VPT * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float g[VPT][8], b[VPT][8];
@@ -86,6 +87,13 @@ fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
       load8<T>(x + r * C + (j * 32 + lane) * 8, v[j]);
+      if (res != nullptr) {   // y = LN(x + res): the sum is rounded to T and stored (it is what backward needs)
+        float rv[8];
+        load8<T>(res + r * C + (j * 32 + lane) * 8, rv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[j][k] = to_f(from_f<T>(v[j][k] + rv[k]));
+        store8<T>(sum_out + r * C + (j * 32 + lane) * 8, v[j]);
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) s += v[j][k];
     }
@@ -285,10 +293,10 @@ using namespace mxb::ln;
 MXB_API int MXBLayerNormWorkspaceFloats(int C) { return kMaxGrid * 2 * C; }
 
 template <typename T, int VPT>
-static void ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int64_t rows,
-                   float eps, cudaStream_t s) {
+static void ln_fwd(const void* x, const void* res, void* sum_out, const float* gamma, const float* beta, void* y,
+                   float* mean, float* rstd, int64_t rows, float eps, cudaStream_t s) {
   int grid = (int)std::min<int64_t>((rows + kWarps - 1) / kWarps, (int64_t)kNumSMs * 8);
-  fwd_kernel<T, VPT><<<grid, kThreads, 0, s>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, rows, eps);
+  fwd_kernel<T, VPT><<<grid, kThreads, 0, s>>>((const T*)x, (const T*)res, (T*)sum_out, gamma, beta, (T*)y, mean, rstd, rows, eps);
 }
 
 template <typename T, int VPT>
@@ -329,13 +337,16 @@ static void ln_bwd(const void* dy, const void* x, const float* gamma, const floa
     }                                                                                       \
   } while (0)
 
-// x,y: [rows, C] contiguous, C % 256 == 0 and C/256 in {1,2,3,4,6,8}; gamma/beta fp32 [C] (may be null)
-MXB_API int MXBLayerNormForward(const void* x, int dt, const float* gamma, const float* beta, void* y, float* mean,
-                                float* rstd, int64_t rows, int C, float eps, void* stream) {
+// x,y: [rows, C] contiguous, C % 256 == 0 and C/256 in {1,2,3,4,6,8}; gamma/beta fp32 [C] (may be null).
+// res (optional, same shape): y = LN(x + res) and sum_out receives x + res (the tensor backward differentiates).
+MXB_API int MXBLayerNormForward(const void* x, const void* res, void* sum_out, int dt, const float* gamma,
+                                const float* beta, void* y, float* mean, float* rstd, int64_t rows, int C, float eps,
+                                void* stream) {
   MXB_TRY
   MXB_CHECK(C % 256 == 0, "layernorm: C must be a multiple of 256");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  MXB_LN_DISPATCH(ln_fwd, x, gamma, beta, y, mean, rstd, rows, eps, s);
+  MXB_CHECK(res == nullptr || sum_out != nullptr, "layernorm: residual needs a sum output");
+  MXB_LN_DISPATCH(ln_fwd, x, res, sum_out, gamma, beta, y, mean, rstd, rows, eps, s);
   CUDA_CHECK(cudaGetLastError());
   MXB_CATCH
 }

@@ -143,12 +143,17 @@ def resnet_forward(spec, P, A, x, training=True, eps=1e-5, momentum=0.9, G=None,
     if stem_pad is None:
         stem_pad = int(getenv("MXB200_STEM_PAD", 0))   # measured on B200: padding 3->8 channels is slower (2.7 vs 1.4 ms fwd)
     kw = dict(training=training, eps=eps, momentum=momentum)
-    if spec.thumbnail:
-        y = _stem_conv(x, P["conv0_weight"], 1, 1, stem_pad)
-        y = _bn(y.contiguous(), P, A, G, "bn0", True, **kw)
+    st, pd = (1, 1) if spec.thumbnail else (2, 3)
+    w0 = P["conv0_weight"]
+    if K.stem_conv_ok(x, w0):
+        # stem as im2col + tcgen05 GEMM: BN statistics come out of the GEMM epilogue, dW goes straight to the arena
+        ws = K.fused_stats_workspace(x.reshape(-1, x.shape[-1]), w0.reshape(w0.shape[0], -1), force=True) if training else None
+        y = K.stem_conv_nhwc(x, w0, st, pd, stats=ws, sink_w=_sink(G, "conv0_weight"))
+        y = _bn(y, P, A, G, "bn0", True, pre_stats=ws, **kw)
     else:
-        y = _stem_conv(x, P["conv0_weight"], 2, 3, stem_pad)
+        y = _stem_conv(x, w0, st, pd, stem_pad)
         y = _bn(y.contiguous(), P, A, G, "bn0", True, **kw)
+    if not spec.thumbnail:
         y = K.max_pool_nhwc(y, 3, 2, 1)
     for s, (n, cout) in enumerate(zip(spec.layers, spec.channels[1:])):
         for b in range(n):

@@ -155,7 +155,7 @@ class _LinearFn(torch.autograd.Function):
             else:
                 gw = gemm_tn(g2, x2, out_dtype=w.dtype)
         if ctx.has_bias and (ctx.needs_input_grad[2] or ctx.sink_b is not None):
-            gsum = g2.float().sum(0)
+            gsum = g2.sum(0, dtype=torch.float32)
             if ctx.sink_b is not None:
                 ctx.sink_b.add_(gsum)
             else:
@@ -186,6 +186,61 @@ def conv1x1_nhwc(x, w, stride=1, stats=None, sink_w=None, passthrough=False):
     return r.reshape(n, h, ww, w.shape[0])
 
 
+class _StemConvFn(torch.autograd.Function):
+    """Small-channel k x k convolution (the ResNet stem) as im2col + tcgen05 GEMM (csrc/cuda/im2col.cu).
+    The input image gets no gradient (it is data)."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, pad, stats, sink_w):
+        n, h, ww, c = x.shape
+        o, _, kh, kw = w.shape
+        oh, ow = (h + 2 * pad - kh) // stride + 1, (ww + 2 * pad - kw) // stride + 1
+        k = kh * kw * c
+        kp = (k + 7) // 8 * 8
+        m = n * oh * ow
+        x = x.contiguous()
+        a = torch.empty((m, kp), dtype=torch.bfloat16, device=x.device)
+        lib = N.cuda()
+        N.check(lib, lib.MXBIm2colNHWC(_p(x), _p(a), c_int(n), c_int(h), c_int(ww), c_int(c), c_int(kh), c_int(kw),
+                                       c_int(stride), c_int(pad), c_int(oh), c_int(ow), c_int(kp), N.stream_of(x)))
+        LAUNCHES[0] += 1
+        wp = torch.zeros((o, kp), dtype=torch.bfloat16, device=x.device)
+        wp[:, :k] = w.permute(0, 2, 3, 1).reshape(o, k)        # (O, kh, kw, C) order == the patch order
+        cs = (stats[STATS_OFF:STATS_OFF + o], stats[STATS_OFF + o:STATS_OFF + 2 * o]) if stats is not None else None
+        y = gemm_nt(a, wp, col_stats=cs)
+        ctx.save_for_backward(a)
+        ctx.meta = (w.shape, w.dtype, k, kp, sink_w)
+        return y.view(n, oh, ow, o)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (a,) = ctx.saved_tensors
+        wshape, wdtype, k, kp, sink_w = ctx.meta
+        o, c, kh, kw = wshape
+        dy2 = dy.reshape(-1, o)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dwp = gemm_tn(dy2, a, out_dtype=torch.float32)                      # [O, Kp] fp32
+        dw = dwp[:, :k].reshape(o, kh, kw, c).permute(0, 3, 1, 2)           # view in (O, C, kh, kw) index order
+        if sink_w is not None:
+            sink_w.add_(dw)
+            return None, None, None, None, None, None
+        return None, dw.to(wdtype), None, None, None, None
+
+
+def stem_conv_nhwc(x, w, stride, pad, stats=None, sink_w=None):
+    """k x k convolution with very few input channels on an NHWC bf16 image.  ``stats``: BN workspace that receives
+    the per-channel sum / sum-of-squares of the output (GEMM epilogue)."""
+    return _StemConvFn.apply(x, w, stride, pad, stats, sink_w)
+
+
+def stem_conv_ok(x, w):
+    o, c, kh, kw = w.shape
+    return (x.is_cuda and x.dtype is torch.bfloat16 and w.dtype is torch.bfloat16 and not x.requires_grad
+            and c <= 4 and o % 8 == 0 and kh * kw * c <= 504 and N.have_cuda_kernels()
+            and getenv("MXB200_STEM", "im2col") == "im2col")
+
+
 # --------------------------------------------------------------------------- BatchNorm(+add)(+ReLU)
 class _BnWorkspace(object):
     """Per-(device, stream) zero-initialised scratch shared by all BN calls (kernels leave the head zeroed):
@@ -204,10 +259,10 @@ class _BnWorkspace(object):
         return ws
 
 
-def fused_stats_workspace(x, w):
+def fused_stats_workspace(x, w, force=False):
     """Workspace for GEMM-epilogue BatchNorm statistics, or None when the producer will not be our GEMM / the BN
-    will not be our kernel (CPU, unsupported widths)."""
-    if not (_gemm_ok(x, w) and N.have_cuda_kernels()):
+    will not be our kernel (CPU, unsupported widths).  ``force``: the caller guarantees a GEMM producer (stem)."""
+    if not ((force or _gemm_ok(x, w)) and N.have_cuda_kernels()):
         return None
     C = w.shape[0]
     vec = 8

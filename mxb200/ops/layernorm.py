@@ -29,20 +29,24 @@ def _ws(dev, C):
 
 class _LayerNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, sink_g, sink_b):
+    def forward(ctx, x, gamma, beta, eps, sink_g, sink_b, residual):
         C = x.shape[-1]
         x2 = x.contiguous().view(-1, C)
         rows = x2.shape[0]
         y = torch.empty_like(x2)
+        r2 = residual.contiguous().view(-1, C) if residual is not None else None
+        xs = torch.empty_like(x2) if r2 is not None else None
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
         g32 = gamma.float().contiguous() if gamma is not None else None
         b32 = beta.float().contiguous() if beta is not None else None
         lib = N.cuda()
-        N.check(lib, lib.MXBLayerNormForward(N.ptr(x2), N.c_int(_dt(x.dtype)), N.ptr(g32), N.ptr(b32), N.ptr(y), N.ptr(mean),
-                                             N.ptr(rstd), N.c_int64(rows), N.c_int(C), N.c_float(eps), N.stream_of(x2)))
+        N.check(lib, lib.MXBLayerNormForward(N.ptr(x2), N.ptr(r2), N.ptr(xs), N.c_int(_dt(x.dtype)), N.ptr(g32), N.ptr(b32),
+                                             N.ptr(y), N.ptr(mean), N.ptr(rstd), N.c_int64(rows), N.c_int(C),
+                                             N.c_float(eps), N.stream_of(x2)))
         LAUNCHES[0] += 1
-        ctx.save_for_backward(x2, g32, mean, rstd)
+        ctx.has_res = r2 is not None
+        ctx.save_for_backward(xs if r2 is not None else x2, g32, mean, rstd)
         ctx.shape = x.shape
         ctx.has = (gamma is not None, beta is not None)
         ctx.gdt = (gamma.dtype if gamma is not None else None, beta.dtype if beta is not None else None)
@@ -69,25 +73,28 @@ class _LayerNormFn(torch.autograd.Function):
                                               N.c_int64(rows), N.c_int(C), N.c_int(1 if use_sink else 0),
                                               N.stream_of(x2)))
         LAUNCHES[0] += 2
+        dxv = dx.view(ctx.shape)
+        dres = dxv if ctx.has_res else None           # d(x + r) flows unchanged to both addends
         if use_sink:
-            return dx.view(ctx.shape), None, None, None, None, None
-        return (dx.view(ctx.shape), dg.to(ctx.gdt[0]) if dg is not None else None,
-                db.to(ctx.gdt[1]) if db is not None else None, None, None, None)
+            return dxv, None, None, None, None, None, dres
+        return (dxv, dg.to(ctx.gdt[0]) if dg is not None else None,
+                db.to(ctx.gdt[1]) if db is not None else None, None, None, None, dres)
 
 
-def layer_norm(x, gamma, beta, eps=1e-5, sink_g=None, sink_b=None):
+def layer_norm(x, gamma, beta, eps=1e-5, sink_g=None, sink_b=None, residual=None):
+    """LayerNorm over the last dim; ``residual``: y = LN(x + residual) with the add fused into the same pass."""
     C = x.shape[-1]
-    if _native_ok(x) and C in _LN_WIDTHS:
-        return _LayerNormFn.apply(x, gamma, beta, float(eps), sink_g, sink_b)
-    if x.is_cuda and N.have_cuda_kernels() and x.dtype in (torch.bfloat16, torch.float32) and False:
-        raise RuntimeError("unreachable")
+    if _native_ok(x) and C in _LN_WIDTHS and (residual is None or residual.dtype is x.dtype):
+        return _LayerNormFn.apply(x, gamma, beta, float(eps), sink_g, sink_b, residual)
+    if residual is not None:
+        x = x + residual
     return F.layer_norm(x, (C,), gamma.to(x.dtype) if gamma is not None else None,
                         beta.to(x.dtype) if beta is not None else None, eps)
 
 
 class _BiasActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, bias, act, slope):
+    def forward(ctx, x, bias, act, slope, sink_b):
         C = x.shape[-1]
         x2 = x.contiguous().view(-1, C)
         b32 = bias.float().contiguous() if bias is not None else None
@@ -97,13 +104,13 @@ class _BiasActFn(torch.autograd.Function):
                                            N.c_int(C), N.c_int(act), N.c_float(slope), N.stream_of(x2)))
         LAUNCHES[0] += 1
         ctx.save_for_backward(x2, b32)
-        ctx.meta = (x.shape, act, slope, bias.dtype if bias is not None else None)
+        ctx.meta = (x.shape, act, slope, bias.dtype if bias is not None else None, sink_b)
         return y.view(x.shape)
 
     @staticmethod
     def backward(ctx, dy):
         x2, b32 = ctx.saved_tensors
-        shape, act, slope, bdt = ctx.meta
+        shape, act, slope, bdt, sink_b = ctx.meta
         C = x2.shape[-1]
         dy2 = dy.contiguous().view(-1, C)
         dx = torch.empty_like(x2)
@@ -112,8 +119,15 @@ class _BiasActFn(torch.autograd.Function):
                                             N.c_int64(x2.shape[0]), N.c_int(C), N.c_int(act), N.c_float(slope),
                                             N.stream_of(x2)))
         LAUNCHES[0] += 1
-        db = dx.float().sum(0).to(bdt) if b32 is not None else None
-        return dx.view(shape), db, None, None
+        db = None
+        if b32 is not None:
+            db = dx.sum(0, dtype=torch.float32)
+            if sink_b is not None:       # fp32 gradient-arena view: accumulate there, autograd gets nothing
+                sink_b.add_(db)
+                db = None
+            else:
+                db = db.to(bdt)
+        return dx.view(shape), db, None, None, None
 
 
 def _torch_act(x, act, slope):
@@ -140,11 +154,11 @@ def _torch_act(x, act, slope):
     raise ValueError("unknown activation %r" % (act,))
 
 
-def bias_act(x, bias=None, act="gelu", slope=0.25):
+def bias_act(x, bias=None, act="gelu", slope=0.25, sink_b=None):
     """y = act(x + bias) along the last dim in one pass (and one pass backward)."""
     if act not in ACT_CODES:
         raise ValueError("unknown activation %r" % (act,))
     C = x.shape[-1]
     if _native_ok(x) and C % 8 == 0 and x.numel() > 0:
-        return _BiasActFn.apply(x, bias, ACT_CODES[act], float(slope))
+        return _BiasActFn.apply(x, bias, ACT_CODES[act], float(slope), sink_b)
     return _torch_act(x + bias.to(x.dtype) if bias is not None else x, act, slope)

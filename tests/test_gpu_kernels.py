@@ -563,3 +563,82 @@ def test_two_bit_compression_kernels_match_reference_format(n, dtype):
     acc = torch.ones(n, device=_dev())
     gc.dequantize(words, n, (n,), out=acc)
     assert torch.equal(acc.cpu(), out_ref + 1.0)
+
+
+@pytest.mark.parametrize("shape,k,stride,pad", [((4, 64, 64, 3), 7, 2, 3), ((2, 32, 32, 3), 3, 1, 1), ((3, 37, 41, 3), 7, 2, 3)])
+def test_stem_conv_im2col_gemm(shape, k, stride, pad):
+    """Stem convolution as im2col + tcgen05 GEMM vs torch conv2d (fp32), forward, BN statistics and weight gradient."""
+    from mxb200.ops import functional as K_
+    n, h, w_, c = shape
+    x = torch.randn(shape, device=_dev()).bfloat16()
+    w = (torch.randn(64, k, k, c, device=_dev()) * 0.1).bfloat16().permute(0, 3, 1, 2).requires_grad_(True)
+    ws = K_._BnWorkspace.get(x.device, 64)
+    y = K_.stem_conv_nhwc(x, w, stride, pad, stats=ws)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.detach().float(), None, stride, pad).permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    assert _rel_err(y, ref) < 2e-2
+    off = K_.STATS_OFF
+    assert _rel_err(ws[off:off + 64], y.float().reshape(-1, 64).sum(0)) < 2e-3
+    ws[off:off + 128].zero_()
+    dy = (torch.randn_like(y.float()) * 0.1).bfloat16()
+    y.backward(dy)
+    w32 = w.detach().float().requires_grad_(True)
+    torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w32, None, stride, pad).backward(dy.float().permute(0, 3, 1, 2))
+    assert _rel_err(w.grad, w32.grad) < 2e-2
+    sink = torch.zeros(64, c, k, k, device=_dev())
+    w2 = w.detach().clone().requires_grad_(True)
+    K_.stem_conv_nhwc(x, w2, stride, pad, sink_w=sink).backward(dy)
+    assert w2.grad is None and _rel_err(sink, w32.grad) < 2e-2
+
+
+def test_layer_norm_fused_residual():
+    from mxb200.ops.layernorm import layer_norm
+    C, rows = 768, 640
+    x = torch.randn(rows, C, device=_dev()).bfloat16().requires_grad_(True)
+    r = torch.randn(rows, C, device=_dev()).bfloat16().requires_grad_(True)
+    g = (torch.rand(C, device=_dev()) + 0.5).requires_grad_(True)
+    b = torch.randn(C, device=_dev()).requires_grad_(True)
+    dy = torch.randn(rows, C, device=_dev()).bfloat16()
+    layer_norm(x, g, b, 1e-5, residual=r).backward(dy)
+    x32, r32 = x.detach().float().requires_grad_(True), r.detach().float().requires_grad_(True)
+    g32, b32 = g.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    torch.nn.functional.layer_norm((x32 + r32).bfloat16().float() + 0 * (x32 + r32), (C,), g32, b32, 1e-5).backward(dy.float())
+    assert _rel_err(x.grad, x32.grad) < 3e-2 and _rel_err(r.grad, r32.grad) < 3e-2
+    assert _rel_err(g.grad, g32.grad) < 3e-2 and _rel_err(b.grad, b32.grad) < 3e-2
+
+
+def test_bert_tiny_bf16_matches_fp32_and_trains_with_fused_lamb():
+    """BERT (2 layers, H=256) on the bf16 kernels vs the same weights in fp32; then 5 fused-LAMB steps through the
+    DeviceTrainer arena (wgrad / LN / bias gradients written straight into the fp32 arena) must reduce the loss."""
+    from mxb200.models import bert
+    from mxb200.parallel.trainer import DeviceTrainer
+    dev = _dev()
+    spec = bert.BertSpec(vocab=1000, hidden=256, layers=2, heads=4, intermediate=1024, max_pos=64, dropout=0.0)
+    P = bert.init_bert_params(spec, dtype=torch.bfloat16, device=dev, seed=1)
+    B, S, Mp = 8, 32, 8
+    g = torch.Generator(device="cpu").manual_seed(0)
+    ids = torch.randint(0, 1000, (B, S), generator=g).to(dev)
+    tt = torch.randint(0, 2, (B, S), generator=g).to(dev)
+    am = torch.ones(B, S, dtype=torch.long, device=dev)
+    mp = torch.randint(0, S, (B, Mp), generator=g).to(dev)
+    ml = torch.randint(0, 1000, (B, Mp), generator=g).to(dev)
+    nl = torch.randint(0, 2, (B,), generator=g).to(dev)
+
+    def run(params, G=None):
+        mlm, nsp = bert.bert_pretrain_forward(spec, params, ids, tt, am, mp, training=True, G=G)
+        return bert.bert_pretrain_loss(spec, mlm, nsp, ml, nl)
+
+    l_bf16 = run(P).item()
+    l_fp32 = run({k: v.float() for k, v in P.items()}).item()
+    assert abs(l_bf16 - l_fp32) / l_fp32 < 2e-2
+    tr = DeviceTrainer(list(P.items()), dev, 0, 1)
+    W = tr.params()
+    losses = []
+    for _ in range(5):
+        loss = run(W, tr.grad_sinks)
+        loss.backward()
+        tr.step("lamb", lr=2e-3, wd=0.01)
+        losses.append(loss.item())
+    tr.check()
+    assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0]
+    tr.close()

@@ -23,7 +23,7 @@ if what.startswith("gemm"):
         else:
             K.gemm_tn(dy, x, out_dtype=torch.float32)
 else:
-    M, C = 802816, 256
+    M, C = [int(v) for v in sys.argv[2:4]] if len(sys.argv) >= 4 else (802816, 256)
     x = torch.randn(M, C, device=dev).bfloat16().requires_grad_(True)
     r = torch.randn(M, C, device=dev).bfloat16().requires_grad_(True)
     g, b = torch.ones(C, device=dev, requires_grad=True), torch.zeros(C, device=dev, requires_grad=True)
