@@ -171,6 +171,19 @@ class KVStoreLocal(KVStore):
             return vals[0]
         if self._compression is not None and self._device_mode:
             return self._reduce_compressed(ikey, vals)
+        if self._device_mode and vals[0]._t.is_cuda and getenv("MXNET_KVSTORE_USETREE", False) and \
+                len({v._t.device for v in vals}) == len(vals) > 2:
+            # topology-aware tree reduce (CommDeviceTree, comm_tree.h; trees from kvstore/gpu_topology.py)
+            devs = tuple(v._t.device.index for v in vals)
+            tc = self._tree_comms.get(devs) if hasattr(self, "_tree_comms") else None
+            if tc is None:
+                from .gpu_topology import TreeComm
+                if not hasattr(self, "_tree_comms"):
+                    self._tree_comms = {}
+                tc = self._tree_comms[devs] = TreeComm(devs)
+            with torch.no_grad():
+                root = ikey % len(vals) if isinstance(ikey, int) else 0     # spread the roots over the devices
+                return NDArray(tc.reduce([v._t for v in vals], root))
         if self._device_mode and vals[0]._t.is_cuda:
             owner = self._store[ikey]._t.device if ikey in self._store and self._store[ikey]._t.is_cuda else vals[0]._t.device
             with torch.no_grad():

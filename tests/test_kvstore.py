@@ -172,3 +172,44 @@ def test_two_bit_compression_matches_numpy_oracle():
     import torch
     words = gc.quantize(torch.tensor([0.6, -0.7, 0.1, 0.0]), torch.zeros(4))
     assert gc.compressed_size(4) == 1 and (int(words[0]) & 0xFF) == 0xE0   # 11 10 00 00
+
+
+def test_gpu_topology_trees_and_tree_comm():
+    """Reference: tests/cpp/kvstore/gpu_topology_test.cc checks that every generated tree is a valid spanning tree;
+    plus a functional reduce/broadcast along the trees (on CPU tensors)."""
+    import numpy as np
+    import torch
+    from mxb200.kvstore import gpu_topology as T
+    # hybrid cube-mesh like DGX-1V (entries = number of NVLinks), a PCIe-only box and an asymmetric 6-GPU case
+    dgx1 = np.array([[0, 1, 1, 2, 2, 0, 0, 0], [1, 0, 2, 1, 0, 2, 0, 0], [1, 2, 0, 2, 0, 0, 1, 0], [2, 1, 2, 0, 0, 0, 0, 1],
+                     [2, 0, 0, 0, 0, 1, 1, 2], [0, 2, 0, 0, 1, 0, 2, 1], [0, 0, 1, 0, 1, 2, 0, 2], [0, 0, 0, 1, 2, 1, 2, 0]],
+                    dtype=np.float32)
+    flat = np.ones((4, 4), dtype=np.float32) - np.eye(4, dtype=np.float32)
+    rng = np.random.RandomState(0)
+    odd = rng.randint(0, 3, size=(6, 6)).astype(np.float32)
+    for W in (dgx1, flat, odd):
+        n = W.shape[0]
+        trees = T.compute_trees(W)
+        assert len(trees) == n
+        for root, levels in enumerate(trees):
+            edges = [e for lvl in levels for e in lvl]
+            assert len(edges) == n - 1
+            reached = {root}
+            for lvl in levels:                      # a parent must already be in the tree when its level runs
+                for p, c in lvl:
+                    assert p in reached and c not in reached
+                for p, c in lvl:
+                    reached.add(c)
+            assert reached == set(range(n))
+            assert len(levels) <= int(np.ceil(np.log2(n))) + 1
+        if W is dgx1:   # every hop of every tree rides an NVLink
+            Ws = np.maximum(W, W.T)
+            assert all(Ws[p, c] > 0 for levels in trees for lvl in levels for p, c in lvl)
+    tc = T.TreeComm(list(range(8)), W=dgx1)
+    xs = [torch.full((5,), float(i + 1)) for i in range(8)]
+    for root in (0, 3, 7):
+        assert torch.equal(tc.reduce(xs, root), torch.full((5,), 36.0))
+        outs = [torch.zeros(5) for _ in range(8)]
+        tc.broadcast(torch.full((5,), 2.5), outs, root)
+        assert all(torch.equal(o, torch.full((5,), 2.5)) for o in outs)
+    assert all(float(x[0]) == i + 1 for i, x in enumerate(xs))   # inputs untouched
