@@ -53,7 +53,8 @@ enum Role : int { kScheduler = 0, kServer = 1, kWorker = 2 };
 enum Group : int { kSchedulerGroup = 1, kServerGroup = 2, kWorkerGroup = 4 };  // ps/base.h:20-30
 enum Cmd : uint32_t {
   kEmpty = 0, kTerminate, kAddNode, kBarrier, kAck, kHeartbeat, kUpdateEnvVar, kMembershipChangeBarrier,  // message.h:123
-  kNodeTable, kBarrierDone, kUpdateEnvAck, kHello, kData, kDataResp, kCommand, kCommandResp
+  kNodeTable, kBarrierDone, kUpdateEnvAck, kHello, kData, kDataResp, kCommand, kCommandResp,
+  kAllGather, kAllGatherDone   // small-blob all-gather among workers through the scheduler (IPC handle exchange)
 };
 
 static constexpr uint32_t kMagic = 0x4d584232;  // "MXB2"
@@ -269,6 +270,24 @@ class Node {
     Send(1, h, kv, nullptr, 0);
     std::unique_lock<std::mutex> lk(mu_);
     cv_.wait(lk, [&] { return barrier_gen_ != gen || !running_ || terminated_; });
+  }
+
+  // All-gather of one small text blob per worker (in rank order) through the scheduler.  Used by the single-box
+  // elastic path to exchange CUDA IPC handles of the symmetric arenas after every membership change, when the
+  // worker set (and therefore any fixed communicator) has changed.  Blobs must not contain '\n'.
+  std::string AllGather(const std::string& blob) {
+    int gen;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      gen = gather_gen_;
+    }
+    Header h;
+    h.cmd = kAllGather;
+    h.head = kWorkerGroup;
+    Send(1, h, blob, nullptr, 0);
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return gather_gen_ != gen || !running_ || terminated_; });
+    return gather_result_;
   }
 
   // ------------------------------------------------------------------------------------------ data plane (worker)
@@ -526,6 +545,16 @@ class Node {
         cv_.notify_all();
         break;
       }
+      case kAllGather:
+        if (role_ == kScheduler) OnAllGather(h.sender, meta);
+        break;
+      case kAllGatherDone: {
+        std::lock_guard<std::mutex> lk(mu_);
+        gather_result_ = meta;
+        ++gather_gen_;
+        cv_.notify_all();
+        break;
+      }
       case kUpdateEnvVar:
         OnUpdateEnvVar(h, meta);
         break;
@@ -658,6 +687,27 @@ class Node {
     if (group & kServerGroup) v.insert(v.end(), server_ids_.begin(), server_ids_.end());
     if (group & kWorkerGroup) v.insert(v.end(), worker_ids_.begin(), worker_ids_.end());
     return v;
+  }
+
+  void OnAllGather(int sender, const std::string& blob) {
+    std::vector<int> members;
+    std::string all;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      gather_blobs_[sender] = blob;
+      if ((int)gather_blobs_.size() < GroupSize(kWorkerGroup)) return;
+      for (auto& kv : gather_blobs_) {   // std::map: ascending node id == ascending rank (id = 9 + 2*rank)
+        members.push_back(kv.first);
+        all += kv.second;
+        all += '\n';
+      }
+      gather_blobs_.clear();
+    }
+    for (int id : members) {
+      Header h;
+      h.cmd = kAllGatherDone;
+      Send(id, h, all, nullptr, 0);
+    }
   }
 
   void OnBarrier(int sender, int group, bool membership, const std::string& kv) {
@@ -947,6 +997,9 @@ class Node {
   std::vector<int> pending_release_;
   int pending_max_id_ = 0;
   std::string pending_kv_;
+  std::map<int, std::string> gather_blobs_;
+  std::string gather_result_;
+  int gather_gen_ = 0;
   std::vector<std::string> pending_added_, pending_removed_tags_;
   std::set<std::string> et_workers_;
   int update_acks_pending_ = 0;
@@ -1022,6 +1075,18 @@ MXB_API int MXBPsBarrier(void* h, int group) {
 MXB_API int MXBPsMembershipChangeBarrier(void* h, const char* kv) {
   MXB_TRY
   reinterpret_cast<Node*>(h)->MembershipChangeBarrier(kv ? kv : "");
+  MXB_CATCH
+}
+// out receives the '\n'-separated blobs of all workers in rank order (truncated to cap-1 bytes + NUL); *out_len = full length
+MXB_API int MXBPsAllGather(void* h, const char* blob, char* out, int cap, int* out_len) {
+  MXB_TRY
+  std::string r = reinterpret_cast<Node*>(h)->AllGather(blob ? blob : "");
+  *out_len = (int)r.size();
+  if (cap > 0) {
+    const int n = std::min((int)r.size(), cap - 1);
+    memcpy(out, r.data(), n);
+    out[n] = 0;
+  }
   MXB_CATCH
 }
 MXB_API int MXBPsNewRequest(void* h, int expected, int* ts) {

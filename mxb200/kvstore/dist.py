@@ -89,6 +89,17 @@ class PsNode(object):
         kv = "\n".join("%s\n%s" % (k, v) for k, v in env.items())
         N.check(self.lib, self.lib.MXBPsMembershipChangeBarrier(self.h, kv.encode()))
 
+    def allgather(self, blob):
+        """All-gather one small bytes blob per worker through the scheduler; returns the list in rank order."""
+        cap = 1 << 20
+        out = ctypes.create_string_buffer(cap)
+        n = c_int()
+        N.check(self.lib, self.lib.MXBPsAllGather(self.h, bytes(blob).hex().encode(), out, c_int(cap), ctypes.byref(n)))
+        if n.value >= cap:
+            raise MXNetError("allgather result too large")
+        parts = out.value.decode().split("\n")
+        return [bytes.fromhex(p) for p in parts if p != ""]
+
     def new_request(self, expected):
         ts = c_int()
         N.check(self.lib, self.lib.MXBPsNewRequest(self.h, c_int(expected), ctypes.byref(ts)))

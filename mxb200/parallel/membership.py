@@ -55,8 +55,93 @@ class ElasticGroup(object):
     def barrier(self):
         self.node.barrier(self._G_WORKER)
 
+    def allgather(self, blob):
+        return self.node.allgather(blob)
+
+    def peer_group(self, device):
+        """Symmetric-memory group over the CURRENT worker set (CUDA IPC handles exchanged through the scheduler)."""
+        from . import peer
+        return peer.PeerGroup("process", self.rank, self.world, device, exchange=peer.pslite_exchange(self.node))
+
     def close(self):
-        self.node.stop()
+        from ..kvstore.dist import K_STOP_SERVER
+        try:
+            info = self.node.info()
+            if not info["terminated"]:
+                self.node.barrier(self._G_WORKER)
+                if info["rank"] == 0 and info["num_servers"] > 0:
+                    self.node.send_command(K_STOP_SERVER, "")
+                self.node.barrier(self._G_ALL)
+        finally:
+            self.node.stop()
+
+
+class ElasticDeviceTrainer(object):
+    """The fused data-parallel trainer on a worker set that changes at epoch boundaries (single box, one process per
+    GPU).  Protocol per boundary (reference call stack: SURVEY.md 3.3; here the "servers" are the GPUs themselves):
+
+      survivors + leavers : gather_state (un-shard the ZeRO-1 optimizer state while everyone is still there)
+                            -> export private copies -> unmap the arenas
+      everyone            : ElasticGroup.membership_barrier (scheduler diffs the host file, removal before addition,
+                            launches newcomers, re-ranks densely; leavers exit inside)
+      survivors + newcomers: new PeerGroup over the new rank set -> new arenas -> import state
+                            -> every rank adopts rank 0's weights / optimizer state / aux (newcomers start from live
+                            state exactly like the reference's newcomers pull from the servers)
+    """
+
+    def __init__(self, egroup, named_params, device, aux=None, **trainer_kw):
+        import torch
+        self.eg = egroup
+        self.device = torch.device(device)
+        self.kw = trainer_kw
+        self.aux = list(aux or [])
+        self.tr = None
+        self._build([(n, t) for n, t in named_params], None)
+
+    def _build(self, named, state):
+        from .trainer import DeviceTrainer
+        pg = self.eg.peer_group(self.device)
+        self.tr = DeviceTrainer(named, self.device, self.eg.rank, self.eg.world, group=pg, **self.kw)
+        if state is not None:
+            self.tr.import_state(state)
+        self.tr.sync_from_rank0(self.eg.barrier)
+        self.tr.broadcast_from_rank0(self.aux, self.eg.barrier)
+
+    def params(self):
+        return self.tr.params()
+
+    @property
+    def grad_sinks(self):
+        return self.tr.grad_sinks
+
+    @property
+    def world(self):
+        return self.eg.world
+
+    @property
+    def rank(self):
+        return self.eg.rank
+
+    def step(self, *a, **kw):
+        return self.tr.step(*a, **kw)
+
+    def epoch_boundary(self, epoch):
+        """Call at the start of every epoch except a newcomer's first.  Returns (old_world, new_world)."""
+        import torch
+        self.tr.gather_state(self.eg.barrier)
+        state = self.tr.export_state()
+        named = [(n, d["weight"]) for n, d in state["params"].items()]
+        torch.cuda.synchronize(self.device)
+        self.eg.barrier()
+        self.tr.close()
+        old, new = self.eg.membership_barrier(epoch)       # leavers raise SystemExit here
+        self._build(named, state)
+        return old, new
+
+    def close(self):
+        if self.tr is not None:
+            self.tr.close()
+            self.tr = None
 
 
 def reinit_after_membership_change(trainer, old_world, new_world, lr_scheduler=None, global_batch=None):

@@ -190,3 +190,19 @@ def torch_dist_exchange():
         dist.all_gather_object(out, local_bytes)
         return out
     return ex
+
+
+def pslite_exchange(node):
+    """Handle exchange through the membership scheduler (csrc/host/pslite.cc kAllGather): works for a worker set
+    that changes at run time, which a fixed torch.distributed process group cannot follow."""
+
+    def ex(local_bytes):
+        import struct
+        rank = node.info()["rank"]
+        parts = node.allgather(struct.pack("<i", rank) + bytes(local_bytes))
+        parts = sorted(parts, key=lambda b: struct.unpack("<i", b[:4])[0])
+        ranks = [struct.unpack("<i", b[:4])[0] for b in parts]
+        if ranks != list(range(len(parts))):
+            raise MXNetError("handle exchange: ranks are not dense: %s" % (ranks,))
+        return [b[4:] for b in parts]
+    return ex

@@ -106,6 +106,150 @@ class DeviceTrainer(object):
         # tiny message (2 floats per tensor); per-tensor trust ratios need the global norms
         dist.all_reduce(ar.state["norms"])
 
+    # ------------------------------------------------------------------ state re-sharding (elastic membership)
+    _STATE_NAMES = ("w32", "mom", "var")
+
+    def _slice(self, ar, rank, world):
+        """Element range of the arena owned by ``rank`` in the two-shot kernel (csrc/cuda/allreduce.cu: per =
+        ceil(n_chunks / world) chunks of 1024 elements); one-shot arenas are replicated."""
+        from . import fused as F_
+        gbytes = ar.n * ar.grads.element_size()
+        if world == 1 or gbytes <= F_.ONE_SHOT_BYTES:
+            return 0, ar.n
+        n_chunks = ar.n // 1024
+        per = (n_chunks + world - 1) // world
+        lo = min(n_chunks, per * rank)
+        return lo * 1024, min(n_chunks, lo + per) * 1024
+
+    def gather_state(self, barrier):
+        """Make every rank hold the FULL optimizer state (fp32 master weights, momentum, second moment), which the
+        fused kernel keeps sharded ZeRO-1 style.  Staging area = the peer-mapped fp32 gradient arena (must be idle:
+        call between steps); ``barrier`` is a host-level barrier over the current ranks.  Needed before a
+        membership change: ranks that leave take their shard with them."""
+        from . import peer as P_
+        if self.world == 1:
+            return
+        for ar in self.arenas:
+            if ar.gdtype is not torch.float32:
+                continue
+            lo, hi = self._slice(ar, self.rank, self.world)
+            if (lo, hi) == (0, ar.n):
+                continue                       # replicated (one-shot) arena: nothing is sharded
+            for name in self._STATE_NAMES:
+                st = ar.state.get(name)
+                if st is None:
+                    continue
+                ar.grads[lo:hi].copy_(st[lo:hi])
+                torch.cuda.synchronize(self.device)
+                barrier()
+                for r in range(self.world):
+                    if r == self.rank:
+                        continue
+                    rlo, rhi = self._slice(ar, r, self.world)
+                    if rhi <= rlo:
+                        continue
+                    src = P_._RawBuffer(ar.g_ptrs[r], ar.n * 4, self.device, owner=False).tensor(torch.float32, ar.n)
+                    st[rlo:rhi].copy_(src[rlo:rhi])
+                torch.cuda.synchronize(self.device)
+                barrier()
+            ar.grads.zero_()
+        torch.cuda.synchronize(self.device)
+
+    def export_state(self):
+        """name -> dict(weight=tensor, <state>=fp32 tensor ...) as private copies (call after gather_state)."""
+        out = {"num_update": self.num_update, "params": {}}
+        for ar in self.arenas:
+            for i, n in enumerate(ar.layout.names):
+                d = {"weight": ar.views[i].detach().clone()}
+                for sname in self._STATE_NAMES:
+                    st = ar.state.get(sname)
+                    if st is not None:
+                        d[sname] = ar.layout.view(st, i, False).detach().clone()
+                out["params"][n] = d
+        return out
+
+    def import_state(self, state):
+        """Inverse of export_state on a (new) trainer over the same parameter set."""
+        self.num_update = int(state.get("num_update", 0))
+        with torch.no_grad():
+            for ar in self.arenas:
+                for i, n in enumerate(ar.layout.names):
+                    d = state["params"].get(n)
+                    if d is None:
+                        continue
+                    ar.views[i].copy_(d["weight"].reshape(ar.views[i].shape))
+                    for sname in self._STATE_NAMES:
+                        if sname in d:
+                            full = ar.get_state(sname, init_from_weights=(sname == "w32"))
+                            ar.layout.view(full, i, False).copy_(d[sname].reshape(-1).view_as(ar.layout.view(full, i, False)))
+
+    def sync_from_rank0(self, barrier):
+        """Every rank adopts rank 0's weights and optimizer state (how a newcomer obtains live state; the reference's
+        newcomers pull from the parameter servers, python/mxnet/module/module.py + kvstore_dist.h).  Uses peer reads of
+        rank 0's arenas: weights directly, state staged through its fp32 gradient arena."""
+        from . import peer as P_
+        if self.world == 1:
+            return
+        for ar in self.arenas:
+            esz = ar.weights.element_size()
+            torch.cuda.synchronize(self.device)
+            barrier()
+            if self.rank != 0:
+                src = P_._RawBuffer(ar.w_ptrs[0], ar.n * esz, self.device, owner=False).tensor(ar.wdtype, ar.n)
+                ar.weights.copy_(src)
+            # which state tensors exist is decided by rank 0 (the optimizer in use); all ranks walk the same list
+            for name in self._STATE_NAMES:
+                has = torch.tensor([1 if name in ar.state else 0], device=self.device, dtype=torch.float32)
+                if ar.gdtype is not torch.float32:
+                    continue
+                if self.rank == 0:
+                    ar.grads[:1].copy_(has)
+                torch.cuda.synchronize(self.device)
+                barrier()
+                g0 = P_._RawBuffer(ar.g_ptrs[0], ar.n * 4, self.device, owner=False).tensor(torch.float32, ar.n)
+                present = bool(g0[:1].item() > 0.5)
+                torch.cuda.synchronize(self.device)
+                barrier()
+                if not present:
+                    continue
+                if self.rank == 0:
+                    ar.grads.copy_(ar.state[name])
+                torch.cuda.synchronize(self.device)
+                barrier()
+                if self.rank != 0:
+                    ar.get_state(name).copy_(g0)
+                torch.cuda.synchronize(self.device)
+                barrier()
+            ar.grads.zero_()
+        torch.cuda.synchronize(self.device)
+        barrier()
+
+    def broadcast_from_rank0(self, tensors, barrier):
+        """Small fp32/any-dtype tensors (BatchNorm running statistics, counters): every rank adopts rank 0's values.
+        Staged through the first fp32 gradient arena in chunks."""
+        from . import peer as P_
+        if self.world == 1 or not tensors:
+            return
+        ar = next(a for a in self.arenas if a.gdtype is torch.float32)
+        g0 = P_._RawBuffer(ar.g_ptrs[0], ar.n * 4, self.device, owner=False).tensor(torch.float32, ar.n)
+        flat = torch.cat([t.detach().reshape(-1).float() for t in tensors])
+        for off in range(0, flat.numel(), ar.n):
+            m = min(ar.n, flat.numel() - off)
+            if self.rank == 0:
+                ar.grads[:m].copy_(flat[off:off + m])
+            torch.cuda.synchronize(self.device)
+            barrier()
+            if self.rank != 0:
+                flat[off:off + m].copy_(g0[:m])
+            torch.cuda.synchronize(self.device)
+            barrier()
+        ar.grads.zero_()
+        o = 0
+        with torch.no_grad():
+            for t in tensors:
+                t.copy_(flat[o:o + t.numel()].reshape(t.shape).to(t.dtype))
+                o += t.numel()
+
     def check(self):
         self.group.check_error()
 

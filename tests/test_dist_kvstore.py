@@ -64,3 +64,11 @@ def test_elastic_add_then_remove_worker(tmp_path):
     lines = [l.split() for l in lines if l]
     assert [(l[0], l[1], l[2]) for l in lines] == [("0", "ADDED", "local2"), ("1", "REMOVED", "local2")]
     assert int(lines[1][3]) > int(lines[0][3])
+
+
+def test_scheduler_allgather_three_workers(tmp_path):
+    """Small-blob all-gather through the scheduler (exchange of CUDA IPC handles when the worker set changes)."""
+    r = _launch(["-n", "3", "-s", "1", "--launcher", "local", sys.executable, os.path.join(ROOT, "tests", "allgather_worker.py")],
+                str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("OK") == 3
