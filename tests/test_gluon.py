@@ -214,3 +214,33 @@ def test_data_loader_and_samplers():
     assert len(batches) == 2
     s = gluon.data.SplitSampler(10, num_parts=2, part_index=1, shuffle=False)
     assert list(s) == [5, 6, 7, 8, 9]
+
+
+def test_gluon_bert_model_trains_on_cpu():
+    """BERTModel (gluon front-end of models/bert.py): parameters are gluon Parameters, LAMB through gluon.Trainer."""
+    import torch
+    import mxb200 as mx
+    from mxb200 import autograd, gluon
+    from mxb200.gluon.model_zoo import bert as zb
+    net = zb.BERTModel(vocab=200, hidden=256, layers=1, heads=4, intermediate=512, max_pos=16, dtype="float32", dropout=0.0)
+    net.initialize(ctx=mx.cpu())
+    assert "word_embed" in "".join(net.collect_params().keys())
+    B, S, Mp = 4, 8, 2
+    g = torch.Generator().manual_seed(0)
+    ids = mx.nd.array(torch.randint(0, 200, (B, S), generator=g).numpy())
+    mp = mx.nd.array(torch.randint(0, S, (B, Mp), generator=g).numpy())
+    lab = mx.nd.array(torch.randint(0, 200, (B * Mp,), generator=g).numpy())
+    tr = gluon.Trainer(net.collect_params(), "lamb", {"learning_rate": 5e-3})
+    L = gluon.loss.SoftmaxCrossEntropyLoss()
+    losses = []
+    for _ in range(6):
+        with autograd.record():
+            mlm, nsp = net(ids, None, None, mp)
+            loss = L(mlm, lab).mean()
+        loss.backward()
+        tr.step(1)
+        losses.append(float(loss.asnumpy().reshape(-1)[0]))
+    assert mlm.shape == (B * Mp, 200) and nsp.shape == (B, 8)
+    assert losses[-1] < losses[0]
+    enc = net(ids)
+    assert enc.shape == (B, S, 256)
