@@ -347,15 +347,25 @@ class KVStoreDevice(KVStoreLocal):
             for k in keys:
                 st = self._store[self._int_key(k)]
                 if isinstance(st, NDArray):
-                    self._dist.broadcast(st._t, src=0)
+                    self._collective(self._dist.broadcast, st._t, src=0)
 
     def _reduce(self, ikey, vals):
         merged = super(KVStoreDevice, self)._reduce(ikey, vals)
         if self.num_workers > 1 and isinstance(merged, NDArray):
             t = merged._t.clone() if merged is vals[0] else merged._t
-            self._dist.all_reduce(t)
+            self._collective(self._dist.all_reduce, t)
             merged = NDArray(t, merged.context)
         return merged
+
+    def _collective(self, fn, t, **kw):
+        """Run an in-place collective on ``t``; host tensors are staged through the rank's GPU when the process group
+        is NCCL-only (values initialised from mx.nd.zeros(shape) live on the CPU, like the reference's pinned copy)."""
+        if not t.is_cuda and torch.cuda.is_available() and self._dist.get_backend() == "nccl":
+            g = t.to(torch.device("cuda", torch.cuda.current_device()))
+            fn(g, **kw)
+            t.copy_(g)
+        else:
+            fn(t, **kw)
 
     def _barrier(self):
         if self.num_workers > 1:

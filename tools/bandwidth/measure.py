@@ -130,7 +130,7 @@ def run(args):
                 continue
             err = 0.0
             if args.test_results:
-                expect = -float(b) * world * (world + 1) / 2.0
+                expect = -float(b + 1) * world * (world + 1) / 2.0      # the warm-up iteration was applied as well
                 err = max(abs(float(tr.params()[n].flatten()[0]) - expect) / abs(expect) for n, _ in named[:4])
             res.append(Results(b, toc, size_mb * 2 * (n_total - 1) / max(n_total, 1) / (dms / 1e3) / 1e3, err, dms))
             if rank == 0:
