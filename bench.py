@@ -162,7 +162,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
+    def timed(fn, steps, after=None):
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -171,6 +171,8 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        if after is not None:
+            after()                                # e.g. consume the last outstanding device->host read
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -185,10 +187,34 @@ def main():
     def step_resident():
         train_step(res_x, res_y)
 
+    # ---- end-to-end arm: the public input pipeline (mx.io.DevicePrefetcher: pinned uint8 batch -> H2D on a copy stream
+    # -> normalise+cast kernel, one batch ahead of the compute) and a device->host read of every step's loss through a
+    # pinned ring (the read of step i is issued in step i and consumed while step i+1 is in flight, so the host never
+    # stalls the launch queue; every read completes inside the timed region)
+    def source():
+        while True:
+            yield host_img, host_lab
+    prefetch = iter(mx.io.DevicePrefetcher(source, ctx, mean=(123.68, 116.28, 103.53), std=(58.395, 57.12, 57.375),
+                                           dtype="bfloat16"))
+    ring = [(torch.zeros(1, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+    pending = []
+    seen = [0.0, 0]
+
+    def drain(keep):
+        while len(pending) > keep:
+            buf, ev = pending.pop(0)
+            ev.synchronize()
+            seen[0] = float(buf[0])
+            seen[1] += 1
+
     def step_e2e():
-        x, y = to_device_batch()
+        x, y = next(prefetch)
         loss = train_step(x, y)
-        loss_host.copy_(loss.as_torch().detach().float().mean().reshape(1), non_blocking=False)
+        drain(1)                                   # at most one read outstanding: its ring slot is free again
+        buf, ev = ring[(seen[1] + len(pending)) % 2]
+        buf.copy_(loss.as_torch().detach().float().mean().reshape(1), non_blocking=True)
+        ev.record()
+        pending.append((buf, ev))
 
     for _ in range(max(3, args.warmup)):
         step_resident()
@@ -199,8 +225,13 @@ def main():
     if not args.no_e2e:
         for _ in range(3):
             step_e2e()
-        ms2, _c2, _l2 = timed(step_e2e, args.steps)
+        drain(0)
+        n_before = seen[1]
+
+        ms2, _c2, _l2 = timed(step_e2e, args.steps, after=lambda: drain(0))
+        assert seen[1] - n_before == args.steps, "every timed step must have delivered its loss to the host"
         e2e = {"value": global_batch * args.steps / (ms2 / 1e3), "unit": "images/sec",
+               "pipeline": "mx.io.DevicePrefetcher (pinned uint8 -> H2D on copy stream -> normalise kernel) + per-step async loss readback",
                "h2d_bytes_per_step": int(host_img.numel() * host_img.element_size() + host_lab.numel() * 8) * world,
                "d2h_bytes_per_step": 4 * world, "ms_per_step": ms2 / args.steps}
     trainer.check_health()
@@ -217,7 +248,7 @@ def main():
                        "kvstore": "device (fused P2P allreduce+update kernel)",
                        "l2_policy": "working set per step (GBs of activations) >> 126 MB L2; inputs not re-used from L2",
                        "baseline_ref": "BASELINE.md ResNet-50 train fp32 1xV100 batch128 = 363.69 img/s"},
-            "clocks": clocks, "gpu_launches": launches, "final_loss": float(loss_host.item()) if e2e else None,
+            "clocks": clocks, "gpu_launches": launches, "final_loss": seen[0] if e2e else None,
         }
         if e2e:
             out["e2e"] = e2e

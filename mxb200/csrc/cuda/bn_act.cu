@@ -101,7 +101,7 @@ __device__ __forceinline__ void finalize_channel(const Finalize& f, int c, float
 
 // Column-vector mapping: thread t owns vector column (t % CV) and rows (t / CV) + k * (kThreads / CV).
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 stats_kernel(const T* __restrict__ x, int64_t M, int C, Finalize f) {
   constexpr int N = V<T>::N;
   const int CV = C / N;
@@ -195,7 +195,7 @@ __global__ void finalize_kernel(int C, Finalize f) {
 }
 
 template <typename T, bool RELU, bool RES>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, uint8_t* __restrict__ mask,
              int64_t M, int C, const float* __restrict__ scale, const float* __restrict__ shift) {
   constexpr int N = V<T>::N;
@@ -268,7 +268,7 @@ struct BwdFinalize {
 };
 
 template <typename T, bool RELU>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8_t* __restrict__ mask, int64_t M,
                   int C, const float* __restrict__ mean, BwdFinalize f) {
   constexpr int N = V<T>::N;
@@ -376,7 +376,7 @@ bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8
 }
 
 template <typename T, bool RELU, bool RES>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8_t* __restrict__ mask, T* __restrict__ dx,
                  T* __restrict__ dres, int64_t M, int C, const float* __restrict__ mean,
                  const float* __restrict__ invstd, const float* __restrict__ c1, const float* __restrict__ c2,

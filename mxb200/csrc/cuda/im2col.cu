@@ -42,42 +42,58 @@ struct Params {
   Div d_chunks, d_ohow, d_ow;
 };
 
+// One block = one (image, output row, tile of kTileW output columns).  Phase 1 stages the KH input rows that the tile
+// touches in shared memory (coalesced 2-byte loads, zero fill outside the image), phase 2 writes the patch rows with
+// 16-byte stores: thread -> fixed 16-byte chunk j of the patch (its 8 source offsets live in registers) and output
+// columns t0, t0 + rows_per_pass, ...  The input is read from global memory once per tile instead of ~KH*KW/stride^2
+// times through L1.
+constexpr int kTileW = 64;
+constexpr int kMaxStage = 8192;   // staged input elements per block (KH * ((kTileW-1)*stride + KW) * C)
+
 __global__ void __launch_bounds__(kThreads) im2col_kernel(const Params p) {
-  // per-k lookup table: dh | dw << 8 | c << 16 | valid << 24
-  __shared__ uint32_t tab[kMaxK];
-  for (int k = threadIdx.x; k < p.Kp; k += kThreads) {
-    uint32_t e = 0;
-    if (k < p.K) {
-      const int kh = k / (p.KW * p.C), r = k - kh * (p.KW * p.C);
-      const int kw = r / p.C, c = r - kw * p.C;
-      e = (uint32_t)kh | ((uint32_t)kw << 8) | ((uint32_t)c << 16) | (1u << 24);
-    }
-    tab[k] = e;
+  __shared__ unsigned short stage[kMaxStage];
+  const int tiles_w = (p.OW + kTileW - 1) / kTileW;
+  const int tile = blockIdx.x % tiles_w;
+  const int noh = blockIdx.x / tiles_w;
+  const int oh = noh % p.OH, n = noh / p.OH;
+  const int ow0 = tile * kTileW;
+  const int tw = min(kTileW, p.OW - ow0);
+  const int span = ((kTileW - 1) * p.stride + p.KW) * p.C;       // staged elements per kernel row
+  const int ih0 = oh * p.stride - p.pad, iw0 = ow0 * p.stride - p.pad;
+  const unsigned short* img = reinterpret_cast<const unsigned short*>(p.x) + (int64_t)n * p.H * p.W * p.C;
+  for (int i = threadIdx.x; i < p.KH * span; i += kThreads) {
+    const int kh = i / span, e = i - kh * span;
+    const int ih = ih0 + kh, iw = iw0 + e / p.C;
+    unsigned short v = 0;
+    if ((unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W) v = __ldg(img + ((int64_t)ih * p.W) * p.C + (int64_t)iw0 * p.C + e);
+    stage[i] = v;
   }
   __syncthreads();
-  const unsigned short* xs = reinterpret_cast<const unsigned short*>(p.x);
-  for (int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x; idx < p.total; idx += (int64_t)gridDim.x * kThreads) {
-    // idx < 2^32 is checked on the host
-    const uint32_t m = p.d_chunks.div((uint32_t)idx);
-    const uint32_t j = (uint32_t)idx - m * p.d_chunks.d;
-    const uint32_t n = p.d_ohow.div(m);
-    const uint32_t rem = m - n * p.d_ohow.d;
-    const uint32_t oh = p.d_ow.div(rem);
-    const uint32_t ow = rem - oh * p.d_ow.d;
-    const int ih0 = (int)oh * p.stride - p.pad, iw0 = (int)ow * p.stride - p.pad;
-    const unsigned short* img = xs + (int64_t)n * p.H * p.W * p.C;
+  const int rows_per_pass = kThreads / p.chunks;
+  const int j = threadIdx.x % p.chunks, t0 = threadIdx.x / p.chunks;
+  if (t0 >= rows_per_pass) return;
+  int off[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = j * 8 + e;
+    if (k < p.K) {
+      const int kh = k / (p.KW * p.C);
+      off[e] = kh * span + (k - kh * p.KW * p.C);
+    } else {
+      off[e] = -1;
+    }
+  }
+  const int64_t m0 = ((int64_t)n * p.OH + oh) * p.OW + ow0;
+  for (int t = t0; t < tw; t += rows_per_pass) {
+    const int base = t * p.stride * p.C;
     uint32_t w[4];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const uint32_t t = tab[j * 8 + e];
-      const int ih = ih0 + (int)(t & 0xff), iw = iw0 + (int)((t >> 8) & 0xff);
-      unsigned short v = 0;
-      if ((t >> 24) && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W)
-        v = __ldg(img + ((int64_t)ih * p.W + iw) * p.C + ((t >> 16) & 0xff));
-      if (e & 1) w[e >> 1] |= (uint32_t)v << 16;
+      const uint32_t v = off[e] >= 0 ? stage[off[e] + base] : 0u;
+      if (e & 1) w[e >> 1] |= v << 16;
       else w[e >> 1] = v;
     }
-    *reinterpret_cast<uint4*>(p.out + (int64_t)m * p.Kp + j * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(p.out + (m0 + t) * p.Kp + j * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -104,8 +120,11 @@ MXB_API int MXBIm2colNHWC(const void* x, void* out, int N, int H, int W, int C, 
   p.d_chunks = im2col::make_div((uint32_t)p.chunks);
   p.d_ohow = im2col::make_div((uint32_t)(OH * OW));
   p.d_ow = im2col::make_div((uint32_t)OW);
-  const int grid = grid_for(p.total, im2col::kThreads, 2, 16);
-  im2col::im2col_kernel<<<grid, im2col::kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  MXB_CHECK(KH * (((im2col::kTileW - 1) * stride + KW) * C) <= im2col::kMaxStage, "im2col: kernel window too large for the staging buffer");
+  MXB_CHECK(p.chunks <= im2col::kThreads, "im2col: patch too long");
+  const int64_t blocks = (int64_t)N * OH * ((OW + im2col::kTileW - 1) / im2col::kTileW);
+  MXB_CHECK(blocks < (1ll << 31), "im2col: grid too large");
+  im2col::im2col_kernel<<<(unsigned)blocks, im2col::kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   CUDA_CHECK(cudaGetLastError());
   MXB_CATCH
 }

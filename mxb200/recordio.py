@@ -71,6 +71,10 @@ class MXRecordIO(object):
         self.is_open = False
         self.pid = None
 
+    def tell(self):
+        """Byte offset of the next record (MXRecordIOWriterTell / ReaderTell in the reference C API)."""
+        return self.handle.tell()
+
     def reset(self):
         self.close()
         self.open()

@@ -642,3 +642,21 @@ def test_bert_tiny_bf16_matches_fp32_and_trains_with_fused_lamb():
     tr.check()
     assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0]
     tr.close()
+
+
+def test_device_prefetcher_normalises_on_device():
+    import mxb200 as mx
+    ctx = mx.gpu(0)
+    imgs = [torch.randint(0, 256, (4, 17, 19, 3), dtype=torch.uint8).pin_memory() for _ in range(4)]
+    labs = [torch.arange(4) + i for i in range(4)]
+    mean, std = (123.68, 116.28, 103.53), (58.395, 57.12, 57.375)
+    pf = mx.io.DevicePrefetcher(list(zip(imgs, labs)), ctx, mean=mean, std=std, dtype="bfloat16")
+    n = 0
+    for (x, y), im, lb in zip(pf, imgs, labs):
+        ref = (im.float() - torch.tensor(mean)) / torch.tensor(std)
+        xt = x.as_torch()
+        assert xt.dtype is torch.bfloat16 and xt.is_cuda
+        assert _rel_err(xt.cpu(), ref) < 1e-2
+        assert torch.equal(y.as_torch().cpu(), lb)
+        n += 1
+    assert n == 4

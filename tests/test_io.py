@@ -123,3 +123,16 @@ def test_metrics():
     custom = mx.metric.np(lambda l, p: float(np.abs(l - p).sum()))
     custom.update([mx.nd.array([1.0])], [mx.nd.array([3.0])])
     assert custom.get()[1] == 2.0
+
+
+def test_device_prefetcher_cpu_path():
+    import torch
+    import mxb200 as mx
+    imgs = [torch.randint(0, 256, (2, 4, 4, 3), dtype=torch.uint8) for _ in range(3)]
+    labs = [torch.tensor([i, i + 1]) for i in range(3)]
+    pf = mx.io.DevicePrefetcher(list(zip(imgs, labs)), mx.cpu(), mean=(1.0, 2.0, 3.0), std=(2.0, 2.0, 2.0), dtype="float32")
+    got = list(pf)
+    assert len(got) == 3
+    for (x, y), im, lb in zip(got, imgs, labs):
+        ref = (im.float() - torch.tensor([1.0, 2.0, 3.0])) / 2.0
+        assert torch.allclose(x.as_torch(), ref) and torch.equal(y.as_torch(), lb)
