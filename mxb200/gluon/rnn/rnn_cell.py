@@ -206,8 +206,8 @@ class ResidualCell(RecurrentCell):
     def state_info(self, batch_size=0):
         return self.base_cell.state_info(batch_size)
 
-    def begin_state(self, **kwargs):
-        return self.base_cell.begin_state(**kwargs)
+    def begin_state(self, batch_size=0, **kwargs):
+        return self.base_cell.begin_state(batch_size, **kwargs)
 
     def __call__(self, inputs, states):
         output, states = self.base_cell(inputs, states)
@@ -223,8 +223,8 @@ class BidirectionalCell(RecurrentCell):
     def state_info(self, batch_size=0):
         return self.l_cell.state_info(batch_size) + self.r_cell.state_info(batch_size)
 
-    def begin_state(self, **kwargs):
-        return self.l_cell.begin_state(**kwargs) + self.r_cell.begin_state(**kwargs)
+    def begin_state(self, batch_size=0, **kwargs):
+        return self.l_cell.begin_state(batch_size, **kwargs) + self.r_cell.begin_state(batch_size, **kwargs)
 
     def __call__(self, inputs, states):
         raise NotImplementedError("Bidirectional cannot be stepped. Please use unroll")
