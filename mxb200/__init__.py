@@ -33,6 +33,9 @@ _LAZY = {
 
 
 def __getattr__(name):
+    if name == "AttrScope":
+        from .attribute import AttrScope
+        return AttrScope
     target = _LAZY.get(name)
     if target is None:
         raise AttributeError("module 'mxb200' has no attribute %r" % name)

@@ -30,3 +30,9 @@ class AttrScope(object):
 
     def __exit__(self, *a):
         AttrScope._current.value = self._old_scope
+
+
+def current_attrs():
+    """Attributes of the innermost active ``AttrScope`` (empty dict outside any scope)."""
+    sc = getattr(AttrScope._current, "value", None)
+    return dict(sc._attr) if sc is not None else {}

@@ -106,10 +106,10 @@ class Executor(object):
         feed.update(self.aux_dict)
         if is_train:
             with autograd.record(train_mode=True):
-                self.outputs = self._symbol.eval_nd(feed)
+                self.outputs = self._symbol.eval_nd(feed, self._group2ctx)
         else:
             with autograd.pause(train_mode=False):
-                self.outputs = self._symbol.eval_nd(feed)
+                self.outputs = self._symbol.eval_nd(feed, self._group2ctx)
         if self._monitor_callback is not None:
             for name, out in zip(self._output_names, self.outputs):
                 self._monitor_callback(name, out)

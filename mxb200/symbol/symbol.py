@@ -314,8 +314,11 @@ class Symbol(object):
         return arg_types, [arg_types[0] if arg_types else np.float32 for _ in self._outputs], aux_types
 
     # ---- execution ---------------------------------------------------------------------------------
-    def eval_nd(self, feed):
-        """Run the graph on NDArrays: feed maps variable name -> NDArray.  Returns list of outputs."""
+    def eval_nd(self, feed, group2ctx=None):
+        """Run the graph on NDArrays: feed maps variable name -> NDArray.  Returns list of outputs.
+        ``group2ctx``: model parallelism by placement -- a node whose ``ctx_group`` attribute (AttrScope) is a key of
+        the map runs on that context; inputs coming from another device are copied there first (the reference inserts
+        _CrossDeviceCopy nodes for this: graph_executor.cc:1349-1353, nnvm place_device.cc)."""
         vals = {}
         for node in self._topo():
             if node.op is None:
@@ -324,6 +327,10 @@ class Symbol(object):
                 vals[(id(node), 0)] = feed[node.name]
                 continue
             ins = [vals[(id(inp), idx)] for inp, idx in node.inputs]
+            if group2ctx:
+                tgt = group2ctx.get(node.var_attrs.get("__ctx_group__"))
+                if tgt is not None:
+                    ins = [x.as_in_context(tgt) if hasattr(x, "as_in_context") and x.context != tgt else x for x in ins]
             outs = _run_node(node, ins, meta=False)
             for i, o in enumerate(outs):
                 vals[(id(node), i)] = o
@@ -455,6 +462,9 @@ def var(name, attr=None, shape=None, lr_mult=None, wd_mult=None, dtype=None, ini
     for k, v in kwargs.items():
         if k.startswith("__") and k.endswith("__"):
             a[k] = str(v)
+    from ..attribute import current_attrs
+    for k, v in current_attrs().items():        # e.g. AttrScope(ctx_group='dev1') -> __ctx_group__
+        a.setdefault("__%s__" % k, v)
     n.var_attrs = a
     return Symbol([(n, 0)])
 
@@ -482,6 +492,9 @@ def _make_op(op, inputs, attrs, name=None, hint=None):
     name = _NameManager.prefix() + (name if name else _NameManager.get(hint))
     nout = int(attrs.get(_MULTI_OUT[op], 1)) if op in _MULTI_OUT else 1
     node = _Node(op, name, attrs, [s._outputs[0] for s in inputs], nout)
+    from ..attribute import current_attrs
+    for k, v in current_attrs().items():
+        node.var_attrs["__%s__" % k] = v
     return Symbol([(node, i) for i in range(nout)]) if nout > 1 else Symbol([(node, 0)])
 
 
@@ -537,6 +550,9 @@ def _create(op, args, kwargs):
             attrs["__kwarg_inputs__"] = tuple(sym_kwargs.keys())
     nout = int(attrs.get(_MULTI_OUT[op], 1)) if op in _MULTI_OUT else 1
     node = _Node(op, node_name, attrs, [s._outputs[0] for s in order], nout)
+    from ..attribute import current_attrs
+    for k, v in current_attrs().items():
+        node.var_attrs["__%s__" % k] = v
     return Symbol([(node, i) for i in range(nout)]) if nout > 1 else Symbol([(node, 0)])
 
 

@@ -162,3 +162,18 @@ def test_hybridblock_export_and_symbolblock_import(tmp_path):
     assert os.path.exists(prefix + "-symbol.json") and os.path.exists(prefix + "-0000.params")
     blk = mx.gluon.SymbolBlock.imports(prefix + "-symbol.json", ["data"], prefix + "-0000.params")
     np.testing.assert_allclose(blk(x).asnumpy(), y.asnumpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_model_parallel_group2ctx_placement():
+    """ctx_group attribute + group2ctx at bind (reference: tests/python/unittest/test_model_parallel.py)."""
+    import mxb200 as mx
+    with mx.AttrScope(ctx_group="dev1"):
+        a = mx.sym.var("a")
+        b = a * 2
+    with mx.AttrScope(ctx_group="dev2"):
+        c = b + 1
+    ex = c.bind(mx.cpu(), {"a": mx.nd.ones((2,))}, group2ctx={"dev1": mx.cpu(0), "dev2": mx.cpu(1)})
+    out = ex.forward()[0]
+    assert out.asnumpy().tolist() == [3.0, 3.0] and out.context == mx.cpu(1)
+    c2 = mx.sym.load_json(c.tojson())                     # placement attributes survive serialisation
+    assert c2.bind(mx.cpu(), {"a": mx.nd.ones((2,))}, group2ctx={"dev2": mx.cpu(3)}).forward()[0].context == mx.cpu(3)
