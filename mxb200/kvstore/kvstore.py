@@ -251,6 +251,12 @@ class KVStoreLocal(KVStore):
                 if isinstance(merged, NDArray) and isinstance(stored, NDArray) and merged._t.device != stored._t.device:
                     merged = NDArray(merged._t.to(stored._t.device), stored.context)
                 self._updater(self._orig_key(ik), merged, stored)
+            elif (self._device_mode and isinstance(merged, NDArray) and isinstance(stored, NDArray) and merged._t.is_cuda
+                  and merged._t.shape == stored._t.shape):
+                # device kvstore without updater: the stored value BECOMES the merged device buffer (the reference does
+                # ``local = merged`` here, kvstore_local.h PushImpl) -- no round trip through host memory
+                own = all(merged is not v for v in vlist)
+                self._store[ik] = merged if own else NDArray(merged._t.clone(), merged.context)
             else:
                 self._assign(stored, merged)
 

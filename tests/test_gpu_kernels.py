@@ -660,3 +660,53 @@ def test_device_prefetcher_normalises_on_device():
         assert torch.equal(y.as_torch().cpu(), lb)
         n += 1
     assert n == 4
+
+
+def test_module_fit_symbolic_convnet_on_gpu():
+    """The generic (non-fused) path on the GPU: symbolic LeNet-ish net through Module.fit with kvstore='device',
+    NCHW fp32, checkpoint round trip."""
+    import numpy as np
+    import mxb200 as mx
+    rs = np.random.RandomState(0)
+    x = rs.rand(256, 1, 12, 12).astype("f")
+    y = (x.mean(axis=(1, 2, 3)) > 0.5).astype("f")
+    x[y == 1, :, :6, :] += 0.5
+    it = mx.io.NDArrayIter(x, y, batch_size=32, shuffle=True)
+    d = mx.sym.var("data")
+    n = mx.sym.Convolution(d, kernel=(3, 3), num_filter=8, name="c1")
+    n = mx.sym.BatchNorm(n, name="bn1")
+    n = mx.sym.Activation(n, act_type="relu")
+    n = mx.sym.Pooling(n, kernel=(2, 2), stride=(2, 2), pool_type="max")
+    n = mx.sym.FullyConnected(mx.sym.flatten(n), num_hidden=2, name="fc")
+    net = mx.sym.SoftmaxOutput(n, name="softmax")
+    mod = mx.mod.Module(net, context=[mx.gpu(0)])
+    mod.fit(it, num_epoch=6, optimizer="sgd", optimizer_params={"learning_rate": 0.1, "momentum": 0.9}, kvstore="device",
+            initializer=mx.init.Xavier())
+    acc = dict(mod.score(it, "acc"))["accuracy"]
+    assert acc > 0.9
+    arg, aux = mod.get_params()
+    assert all(np.isfinite(v.asnumpy()).all() for v in arg.values())
+    assert "bn1_moving_mean" in aux
+
+
+def test_gluon_generic_nchw_fp32_trainer_on_gpu():
+    """gluon model-zoo network (NCHW fp32, cuDNN/cuBLAS through torch) + Trainer('adam') + hybridize on the GPU."""
+    import mxb200 as mx
+    from mxb200 import autograd, gluon
+    from mxb200.gluon.model_zoo import vision
+    ctx = mx.gpu(0)
+    net = vision.get_model("resnet18_v1", classes=10)
+    net.initialize(mx.init.Xavier(), ctx=ctx)
+    net.hybridize()
+    tr = gluon.Trainer(net.collect_params(), "adam", {"learning_rate": 1e-3})
+    L = gluon.loss.SoftmaxCrossEntropyLoss()
+    x = mx.nd.from_torch(torch.randn(16, 3, 32, 32, device="cuda"), ctx)
+    y = mx.nd.from_torch(torch.randint(0, 10, (16,), device="cuda"), ctx)
+    losses = []
+    for _ in range(10):
+        with autograd.record():
+            loss = L(net(x), y)
+        loss.backward()
+        tr.step(16)
+        losses.append(float(loss.as_torch().detach().float().mean()))
+    assert losses[-1] < losses[0]
