@@ -20,7 +20,7 @@ from ....ndarray.ndarray import _op
 from .... import autograd
 from ....models import resnet as _R
 
-__all__ = ["ResNetV1", "ResNetV2", "BasicBlockV1", "BasicBlockV2", "BottleneckV1", "BottleneckV2", "FusedResNet",
+__all__ = ["resnet200_v1", "resnet269_v1", "resnet200_v2", "resnet269_v2", "ResNetV1", "ResNetV2", "BasicBlockV1", "BasicBlockV2", "BottleneckV1", "BottleneckV2", "FusedResNet",
            "resnet18_v1", "resnet34_v1", "resnet50_v1", "resnet101_v1", "resnet152_v1", "resnet18_v2", "resnet34_v2",
            "resnet50_v2", "resnet101_v2", "resnet152_v2", "resnet50_v1b", "resnet101_v1b", "resnet152_v1b",
            "get_resnet"]
@@ -277,7 +277,11 @@ _SPEC = {18: ("basic_block", [2, 2, 2, 2], [64, 64, 128, 256, 512]),
          34: ("basic_block", [3, 4, 6, 3], [64, 64, 128, 256, 512]),
          50: ("bottle_neck", [3, 4, 6, 3], [64, 256, 512, 1024, 2048]),
          101: ("bottle_neck", [3, 4, 23, 3], [64, 256, 512, 1024, 2048]),
-         152: ("bottle_neck", [3, 8, 36, 3], [64, 256, 512, 1024, 2048])}
+         152: ("bottle_neck", [3, 8, 36, 3], [64, 256, 512, 1024, 2048]),
+         # 200 / 269 layers: the deep ImageNet variants of the reference's symbol library
+         # (example/image-classification/symbols/resnet.py:171-179), used by tools/bandwidth/measure.py
+         200: ("bottle_neck", [3, 24, 36, 3], [64, 256, 512, 1024, 2048]),
+         269: ("bottle_neck", [3, 30, 48, 8], [64, 256, 512, 1024, 2048])}
 _NETS = [ResNetV1, ResNetV2]
 _BLOCKS = [{"basic_block": BasicBlockV1, "bottle_neck": BottleneckV1},
            {"basic_block": BasicBlockV2, "bottle_neck": BottleneckV2}]
@@ -313,3 +317,4 @@ def _mk(version, n):
 resnet18_v1, resnet34_v1, resnet50_v1, resnet101_v1, resnet152_v1 = [_mk(1, n) for n in (18, 34, 50, 101, 152)]
 resnet18_v2, resnet34_v2, resnet50_v2, resnet101_v2, resnet152_v2 = [_mk(2, n) for n in (18, 34, 50, 101, 152)]
 resnet50_v1b, resnet101_v1b, resnet152_v1b = [_mk("v1b", n) for n in (50, 101, 152)]
+resnet200_v1, resnet269_v1, resnet200_v2, resnet269_v2 = _mk(1, 200), _mk(1, 269), _mk(2, 200), _mk(2, 269)

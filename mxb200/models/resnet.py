@@ -31,6 +31,7 @@ RESNET_SPECS = {
     50: ("bottleneck", [3, 4, 6, 3], [64, 256, 512, 1024, 2048]),
     101: ("bottleneck", [3, 4, 23, 3], [64, 256, 512, 1024, 2048]),
     152: ("bottleneck", [3, 8, 36, 3], [64, 256, 512, 1024, 2048]),
+    200: ("bottleneck", [3, 24, 36, 3], [64, 256, 512, 1024, 2048]),
 }
 
 

@@ -82,7 +82,7 @@ def gemm_tn(dy, x, out_dtype=torch.bfloat16, block_n=0, out=None):
     fp32 TMA reduce-add.  ``out``: fp32 [N,K] buffer that is ACCUMULATED into (e.g. a gradient-arena view)."""
     M, Nn = dy.shape
     K = x.shape[1]
-    bn = block_n or (64 if K <= 64 else 128)
+    bn = block_n or (64 if K <= 64 else (128 if K < 256 else 256))   # measured: 256-wide tiles win for K >= 256 (profiles/)
     acc = out if out is not None else torch.zeros((Nn, K), dtype=torch.float32, device=dy.device)
     gemm_raw(GEMM_TN, dy, x, acc, Nn, K, M, dy.stride(0), x.stride(0), acc.stride(0), splits=_pick_splits(Nn, K, M, bn),
              block_n=bn)

@@ -90,6 +90,14 @@ def main():
                "fused_allreduce_update_ms": t_fused, "nccl_allreduce_plus_torch_update_ms": t_nccl,
                "nccl_allreduce_only_ms": t_ar,
                "fused_algbw_GBs": 4 * nelem / t_fused / 1e6}
+        # roofline of the fused step = its NVLink traffic at link bandwidth: every rank pulls (n-1)/n of the fp32
+        # gradients from its peers and pushes (n-1)/n of the updated bf16 weights back (two-shot); NVLink 5 gives
+        # 900 GB/s per direction per GPU, reads and writes travel in opposite directions
+        rd = 4.0 * nelem * (world - 1) / world
+        wr = 2.0 * nelem * (world - 1) / world
+        row["nvlink_read_bytes_per_rank"], row["nvlink_write_bytes_per_rank"] = rd, wr
+        row["roofline_ms_at_900GBs"] = max(rd, wr) / 900e9 * 1e3
+        row["fraction_of_nvlink_roofline"] = row["roofline_ms_at_900GBs"] / t_fused
         if rank == 0:
             print(json.dumps(row), flush=True)
         out.append(row)
