@@ -191,3 +191,66 @@ MXB_API int MXBMaxPoolNhwcBwd(const void* dy, const void* idx, void* dx, int dt,
   CUDA_CHECK(cudaGetLastError());
   MXB_CATCH
 }
+
+// ------------------------------------------------------------------ spatial sub-sampling x[:, ::s, ::s, :] (NHWC)
+// The strided 1x1 "downsample" convolutions of ResNet read every s-th pixel.  Forward = gather into a dense tensor (the
+// GEMM's A operand); backward writes the FULL input gradient in one pass (dy at the sampled pixels, zero elsewhere)
+// instead of a zero-fill kernel plus a strided scatter.  16-byte vectors, byte-granular (dtype agnostic).
+namespace mxb {
+namespace pool {
+
+__global__ void __launch_bounds__(kThreads)
+subsample_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int CV, int HO, int WO, int s) {
+  const int64_t total = (int64_t)N * HO * WO * CV;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+    const int c = (int)(i % CV);
+    int64_t r = i / CV;
+    const int wo = (int)(r % WO); r /= WO;
+    const int ho = (int)(r % HO);
+    const int n = (int)(r / HO);
+    y[i] = ldg16_stream(x + (((int64_t)n * H + (int64_t)ho * s) * W + (int64_t)wo * s) * CV + c);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+subsample_bwd_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, int N, int H, int W, int CV, int HO, int WO, int s) {
+  const int64_t total = (int64_t)N * H * W * CV;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+    const int c = (int)(i % CV);
+    int64_t r = i / CV;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (h % s == 0 && w % s == 0 && h / s < HO && w / s < WO)
+      v = ldg16_stream(dy + (((int64_t)n * HO + h / s) * WO + w / s) * CV + c);
+    dx[i] = v;
+  }
+}
+
+}  // namespace pool
+}  // namespace mxb
+
+// x: [N,H,W,C] contiguous with C*elem_bytes a multiple of 16; y: [N,HO,WO,C], HO = ceil(H/s), WO = ceil(W/s)
+MXB_API int MXBSubsampleNhwc(const void* src, void* dst, int elem_bytes, int N, int H, int W, int C, int s, int backward,
+                             void* stream) {
+  MXB_TRY
+  MXB_CHECK((C * elem_bytes) % 16 == 0, "subsample: C * sizeof(T) must be a multiple of 16");
+  MXB_CHECK(s >= 1, "subsample: stride >= 1");
+  const int CV = C * elem_bytes / 16;
+  const int HO = (H + s - 1) / s, WO = (W + s - 1) / s;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!backward) {
+    const int64_t total = (int64_t)N * HO * WO * CV;
+    if (total == 0) return 0;
+    pool::subsample_fwd_kernel<<<grid_for(total, pool::kThreads, 4, 16), pool::kThreads, 0, st>>>(
+        (const uint4*)src, (uint4*)dst, N, H, W, CV, HO, WO, s);
+  } else {
+    const int64_t total = (int64_t)N * H * W * CV;
+    if (total == 0) return 0;
+    pool::subsample_bwd_kernel<<<grid_for(total, pool::kThreads, 4, 16), pool::kThreads, 0, st>>>(
+        (const uint4*)src, (uint4*)dst, N, H, W, CV, HO, WO, s);
+  }
+  CUDA_CHECK(cudaGetLastError());
+  MXB_CATCH
+}

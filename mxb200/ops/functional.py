@@ -174,10 +174,46 @@ def linear(x, w, b=None, relu=False, stats=None, sink_w=None, sink_b=None, passt
     return (y, x) if passthrough else y
 
 
+class _SubsampleFn(torch.autograd.Function):
+    """x[:, ::s, ::s, :] on a contiguous NHWC tensor; the backward writes the whole input gradient in one pass
+    (csrc/cuda/pool.cu) instead of zero-fill + strided scatter."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        n, h, w, c = x.shape
+        ho, wo = (h + s - 1) // s, (w + s - 1) // s
+        y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+        lib = N.cuda()
+        N.check(lib, lib.MXBSubsampleNhwc(_p(x), _p(y), c_int(x.element_size()), c_int(n), c_int(h), c_int(w), c_int(c), c_int(s),
+                                          c_int(0), N.stream_of(x)))
+        LAUNCHES[0] += 1
+        ctx.meta = (x.shape, s)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (n, h, w, c), s = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty((n, h, w, c), dtype=dy.dtype, device=dy.device)
+        lib = N.cuda()
+        N.check(lib, lib.MXBSubsampleNhwc(_p(dy), _p(dx), c_int(dy.element_size()), c_int(n), c_int(h), c_int(w), c_int(c),
+                                          c_int(s), c_int(1), N.stream_of(dy)))
+        LAUNCHES[0] += 1
+        return dx, None
+
+
+def subsample_nhwc(x, s):
+    if s == 1:
+        return x
+    if _use_native(x) and x.dim() == 4 and x.is_contiguous() and (x.shape[-1] * x.element_size()) % 16 == 0:
+        return _SubsampleFn.apply(x, int(s))
+    return x[:, ::s, ::s, :].contiguous()
+
+
 def conv1x1_nhwc(x, w, stride=1, stats=None, sink_w=None, passthrough=False):
     """1x1 convolution on a channels-last (N,H,W,C) tensor == GEMM over pixels.  w: (Cout, Cin)."""
     if stride != 1:
-        x = x[:, ::stride, ::stride, :].contiguous()
+        x = subsample_nhwc(x, stride)
     n, h, ww, c = x.shape
     r = linear(x.reshape(n * h * ww, c), w, None, False, stats, sink_w, None, passthrough)
     if passthrough:

@@ -710,3 +710,17 @@ def test_gluon_generic_nchw_fp32_trainer_on_gpu():
         tr.step(16)
         losses.append(float(loss.as_torch().detach().float().mean()))
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("shape,s,dtype", [((4, 14, 14, 64), 2, torch.bfloat16), ((2, 7, 9, 8), 2, torch.float32), ((2, 8, 8, 16), 3, torch.bfloat16)])
+def test_subsample_nhwc_fwd_bwd(shape, s, dtype):
+    from mxb200.ops import functional as K_
+    x = torch.randn(shape, device=_dev()).to(dtype).requires_grad_(True)
+    y = K_.subsample_nhwc(x, s)
+    ref = x.detach()[:, ::s, ::s, :]
+    assert torch.equal(y, ref)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    x2 = x.detach().clone().requires_grad_(True)
+    x2[:, ::s, ::s, :].backward(dy)
+    assert torch.equal(x.grad, x2.grad)
