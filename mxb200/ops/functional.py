@@ -231,33 +231,34 @@ class _StemConvFn(torch.autograd.Function):
         n, h, ww, c = x.shape
         o, _, kh, kw = w.shape
         oh, ow = (h + 2 * pad - kh) // stride + 1, (ww + 2 * pad - kw) // stride + 1
-        k = kh * kw * c
-        kp = (k + 7) // 8 * 8
+        kwp = kw + (kw & 1)                 # patch layout (kh, kw padded to even, channel padded to 4)
+        kp = kh * kwp * 4
         m = n * oh * ow
         x = x.contiguous()
         a = torch.empty((m, kp), dtype=torch.bfloat16, device=x.device)
         lib = N.cuda()
         N.check(lib, lib.MXBIm2colNHWC(_p(x), _p(a), c_int(n), c_int(h), c_int(ww), c_int(c), c_int(kh), c_int(kw),
-                                       c_int(stride), c_int(pad), c_int(oh), c_int(ow), c_int(kp), N.stream_of(x)))
+                                       c_int(stride), c_int(pad), c_int(oh), c_int(ow), c_int(kwp), N.stream_of(x)))
         LAUNCHES[0] += 1
-        wp = torch.zeros((o, kp), dtype=torch.bfloat16, device=x.device)
-        wp[:, :k] = w.permute(0, 2, 3, 1).reshape(o, k)        # (O, kh, kw, C) order == the patch order
+        wp = torch.zeros((o, kh, kwp, 4), dtype=torch.bfloat16, device=x.device)
+        wp[:, :, :kw, :c] = w.permute(0, 2, 3, 1)              # (O, kh, kw, C) order == the patch order
+        wp = wp.view(o, kp)
         cs = (stats[STATS_OFF:STATS_OFF + o], stats[STATS_OFF + o:STATS_OFF + 2 * o]) if stats is not None else None
         y = gemm_nt(a, wp, col_stats=cs)
         ctx.save_for_backward(a)
-        ctx.meta = (w.shape, w.dtype, k, kp, sink_w)
+        ctx.meta = (w.shape, w.dtype, kwp, kp, sink_w)
         return y.view(n, oh, ow, o)
 
     @staticmethod
     def backward(ctx, dy):
         (a,) = ctx.saved_tensors
-        wshape, wdtype, k, kp, sink_w = ctx.meta
+        wshape, wdtype, kwp, kp, sink_w = ctx.meta
         o, c, kh, kw = wshape
         dy2 = dy.reshape(-1, o)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
         dwp = gemm_tn(dy2, a, out_dtype=torch.float32)                      # [O, Kp] fp32
-        dw = dwp[:, :k].reshape(o, kh, kw, c).permute(0, 3, 1, 2)           # view in (O, C, kh, kw) index order
+        dw = dwp.view(o, kh, kwp, 4)[:, :, :kw, :c].permute(0, 3, 1, 2)     # view in (O, C, kh, kw) index order
         if sink_w is not None:
             sink_w.add_(dw)
             return None, None, None, None, None, None
@@ -273,7 +274,7 @@ def stem_conv_nhwc(x, w, stride, pad, stats=None, sink_w=None):
 def stem_conv_ok(x, w):
     o, c, kh, kw = w.shape
     return (x.is_cuda and x.dtype is torch.bfloat16 and w.dtype is torch.bfloat16 and not x.requires_grad
-            and c <= 4 and o % 8 == 0 and kh * kw * c <= 504 and N.have_cuda_kernels()
+            and c <= 4 and o % 8 == 0 and kh * (kw + 1) * 4 <= 2048 and N.have_cuda_kernels()
             and getenv("MXB200_STEM", "im2col") == "im2col")
 
 

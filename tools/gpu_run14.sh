@@ -5,6 +5,7 @@ mkdir -p gpurun_out
 export MXB200_NO_BUILD=1
 R=$(pwd)
 nvidia-smi topo -m > gpurun_out/topo8.txt 2>&1
+timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "stem or subsample or prefetcher" > gpurun_out/t14_stem.log 2>&1; echo "pytest stem exit $?"; tail -3 gpurun_out/t14_stem.log
 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench14_n8.log 2>&1; echo "bench n8 exit $?"; grep '^{' gpurun_out/bench14_n8.log | cut -c1-330
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29532 tools/check_multigpu.py > gpurun_out/multigpu8.log 2>&1; echo "multigpu check exit $?"; grep '^{' gpurun_out/multigpu8.log | cut -c1-420
 rm -rf /tmp/elastic8 && mkdir -p /tmp/elastic8 && cd /tmp/elastic8
