@@ -136,11 +136,84 @@ def _conv1x1_bn(x, P, A, G, wname, bnname, relu, stride=1, residual=None, traini
     return (y, xp) if passthrough else y
 
 
+# ----------------------------------------------------------------------------- inference: BatchNorm folded away
+_FOLD_CACHE = {}
+
+
+def _folded(P, A, wname, bnname, eps):
+    """(w', shift): convolution weights with the BatchNorm scale folded in (w' = w * gamma / sqrt(var + eps) per output
+    channel) and the remaining per-channel shift, cached until any of the five tensors is modified in place."""
+    w, g, b = P[wname], P[bnname + "_gamma"], P[bnname + "_beta"]
+    m, v = A[bnname + "_running_mean"], A[bnname + "_running_var"]
+    key = (w.data_ptr(), g.data_ptr(), b.data_ptr(), m.data_ptr(), v.data_ptr())
+    ver = (w._version, g._version, b._version, m._version, v._version, float(eps))
+    hit = _FOLD_CACHE.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    with torch.no_grad():
+        scale = g.float() * torch.rsqrt(v.float() + eps)
+        shift = (b.float() - m.float() * scale).contiguous()
+        wf = (w.float() * scale.view(-1, *([1] * (w.dim() - 1)))).to(w.dtype)
+        if w.dim() == 4:
+            wf = wf.contiguous(memory_format=torch.channels_last)
+        else:
+            wf = wf.contiguous()
+    if len(_FOLD_CACHE) > 4096:
+        _FOLD_CACHE.clear()
+    _FOLD_CACHE[key] = (ver, wf, shift)
+    return wf, shift
+
+
+def _conv_bn_eval(x, P, A, wname, bnname, relu, stride=1, pad=0, residual=None, eps=1e-5):
+    """Inference Conv+BN(+residual)(+ReLU) as ONE kernel: the BN scale lives in the weights, the shift is the GEMM
+    bias, residual add and ReLU run in the GEMM epilogue (1x1) / in place after the library conv (kxk)."""
+    wf, shift = _folded(P, A, wname, bnname, eps)
+    if wf.dim() == 2:                                        # 1x1: tcgen05 GEMM
+        xs = K.subsample_nhwc(x, stride)
+        n, h, ww, c = xs.shape
+        y = K.gemm_bias_act(xs.reshape(n * h * ww, c), wf, shift, relu=relu,
+                            addend=residual.reshape(n * h * ww, -1) if residual is not None else None)
+        return y.view(n, h, ww, wf.shape[0])
+    if K.stem_conv_ok(x, wf):
+        y = K.stem_conv_nhwc(x, wf, stride, pad, bias=shift, relu=relu)
+        return y
+    y = F.conv2d(x.permute(0, 3, 1, 2), wf, shift.to(wf.dtype), stride, pad).permute(0, 2, 3, 1)
+    if residual is not None:
+        y = y + residual
+    return torch.relu_(y) if relu else y
+
+
+def _resnet_forward_eval(spec, P, A, x, eps):
+    st, pd = (1, 1) if spec.thumbnail else (2, 3)
+    y = _conv_bn_eval(x, P, A, "conv0_weight", "bn0", True, st, pd, eps=eps)
+    if not spec.thumbnail:
+        y = K.max_pool_nhwc(y.contiguous(), 3, 2, 1)
+    for s, (n, cout) in enumerate(zip(spec.layers, spec.channels[1:])):
+        for b in range(n):
+            pre = "stage%d_unit%d_" % (s + 1, b + 1)
+            stride = 2 if (b == 0 and s > 0) else 1
+            has_down = (pre + "down_weight") in P
+            res = _conv_bn_eval(y, P, A, pre + "down_weight", pre + "down_bn", False, stride, eps=eps) if has_down else y
+            if spec.block == "bottleneck":
+                s1, s2 = (stride, 1) if spec.version == "v1" else (1, stride)
+                o = _conv_bn_eval(y, P, A, pre + "conv1_weight", pre + "bn1", True, s1, eps=eps)
+                o = _conv_bn_eval(o, P, A, pre + "conv2_weight", pre + "bn2", True, s2, 1, eps=eps)
+                y = _conv_bn_eval(o.contiguous(), P, A, pre + "conv3_weight", pre + "bn3", True, 1, residual=res.contiguous(), eps=eps)
+            else:
+                o = _conv_bn_eval(y, P, A, pre + "conv1_weight", pre + "bn1", True, stride, 1, eps=eps)
+                y = _conv_bn_eval(o, P, A, pre + "conv2_weight", pre + "bn2", True, 1, 1, residual=res, eps=eps)
+    pooled = y.float().mean(dim=(1, 2)).to(y.dtype)
+    return K.linear(pooled, P["fc_weight"], P["fc_bias"])
+
+
 def resnet_forward(spec, P, A, x, training=True, eps=1e-5, momentum=0.9, G=None, stem_pad=None):
     """x: [N, H, W, C] channels-last.  Returns logits [N, classes] (bf16).
 
     G (optional): name -> fp32 gradient-arena view; gradients of 1x1-conv / FC weights and BN gamma/beta are
     then written straight into the arena by the backward kernels."""
+    if (not training and not torch.is_grad_enabled() and x.is_cuda and x.dtype is torch.bfloat16
+            and getenv("MXB200_FOLD_BN", True)):
+        return _resnet_forward_eval(spec, P, A, x, eps)
     if stem_pad is None:
         stem_pad = int(getenv("MXB200_STEM_PAD", 0))   # measured on B200: padding 3->8 channels is slower (2.7 vs 1.4 ms fwd)
     kw = dict(training=training, eps=eps, momentum=momentum)

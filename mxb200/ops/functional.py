@@ -49,6 +49,23 @@ def gemm_raw(mode, A, B, D, M, Nn, K, lda, ldb, ldd, bias=None, relu=False, col_
     LAUNCHES[0] += 1
 
 
+def gemm_bias_act(x, w, bias=None, relu=False, addend=None, block_n=0):
+    """Inference epilogue: y = relu(x.W^T + bias + addend) in one kernel (no autograd)."""
+    M, K = x.shape
+    Nn = w.shape[0]
+    if not (_gemm_ok(x, w) and (addend is None or (addend.is_contiguous() and addend.dtype is torch.bfloat16))):
+        y = F.linear(x, w, bias.to(x.dtype) if bias is not None else None)
+        if addend is not None:
+            y = y + addend
+        return torch.relu(y) if relu else y
+    if not x.is_contiguous():
+        x = x.contiguous()
+    y = torch.empty((M, Nn), dtype=torch.bfloat16, device=x.device)
+    gemm_raw(GEMM_NT, x, w, y, M, Nn, K, x.stride(0), w.stride(0), Nn, bias, relu, addend=addend,
+             ldc=addend.stride(0) if addend is not None else 0, block_n=block_n)
+    return y
+
+
 def gemm_nt(x, w, bias=None, relu=False, col_stats=None, block_n=0):
     """y[M,N] = x[M,K] @ w[N,K]^T (+bias)(relu); bf16 in/out, fp32 accumulate in TMEM.  ``col_stats`` =
     (sum, sumsq) fp32 [N] accumulators that receive the per-column statistics of y (fused BatchNorm stats)."""
@@ -227,7 +244,7 @@ class _StemConvFn(torch.autograd.Function):
     The input image gets no gradient (it is data)."""
 
     @staticmethod
-    def forward(ctx, x, w, stride, pad, stats, sink_w):
+    def forward(ctx, x, w, stride, pad, stats, sink_w, bias=None, relu=False):
         n, h, ww, c = x.shape
         o, _, kh, kw = w.shape
         oh, ow = (h + 2 * pad - kh) // stride + 1, (ww + 2 * pad - kw) // stride + 1
@@ -244,7 +261,7 @@ class _StemConvFn(torch.autograd.Function):
         wp[:, :, :kw, :c] = w.permute(0, 2, 3, 1)              # (O, kh, kw, C) order == the patch order
         wp = wp.view(o, kp)
         cs = (stats[STATS_OFF:STATS_OFF + o], stats[STATS_OFF + o:STATS_OFF + 2 * o]) if stats is not None else None
-        y = gemm_nt(a, wp, col_stats=cs)
+        y = gemm_nt(a, wp, bias=bias, relu=relu, col_stats=cs)
         ctx.save_for_backward(a)
         ctx.meta = (w.shape, w.dtype, kwp, kp, sink_w)
         return y.view(n, oh, ow, o)
@@ -261,14 +278,15 @@ class _StemConvFn(torch.autograd.Function):
         dw = dwp.view(o, kh, kwp, 4)[:, :, :kw, :c].permute(0, 3, 1, 2)     # view in (O, C, kh, kw) index order
         if sink_w is not None:
             sink_w.add_(dw)
-            return None, None, None, None, None, None
-        return None, dw.to(wdtype), None, None, None, None
+            return None, None, None, None, None, None, None, None
+        return None, dw.to(wdtype), None, None, None, None, None, None
 
 
-def stem_conv_nhwc(x, w, stride, pad, stats=None, sink_w=None):
+def stem_conv_nhwc(x, w, stride, pad, stats=None, sink_w=None, bias=None, relu=False):
     """k x k convolution with very few input channels on an NHWC bf16 image.  ``stats``: BN workspace that receives
-    the per-channel sum / sum-of-squares of the output (GEMM epilogue)."""
-    return _StemConvFn.apply(x, w, stride, pad, stats, sink_w)
+    the per-channel sum / sum-of-squares of the output (GEMM epilogue); ``bias`` / ``relu``: inference epilogue (not
+    differentiated)."""
+    return _StemConvFn.apply(x, w, stride, pad, stats, sink_w, bias, relu)
 
 
 def stem_conv_ok(x, w):

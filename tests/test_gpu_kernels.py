@@ -724,3 +724,34 @@ def test_subsample_nhwc_fwd_bwd(shape, s, dtype):
     x2 = x.detach().clone().requires_grad_(True)
     x2[:, ::s, ::s, :].backward(dy)
     assert torch.equal(x.grad, x2.grad)
+
+
+@pytest.mark.parametrize("layers,thumb,size", [(18, True, 32), (50, False, 64)])
+def test_resnet_inference_folded_bn_matches_unfolded(layers, thumb, size):
+    """Inference path with BatchNorm folded into the conv weights / GEMM bias (+ residual + ReLU in the GEMM epilogue)
+    against the generic eval path."""
+    import os
+    from mxb200.models import resnet as R
+    spec = R.ResNetSpec(layers, classes=16, thumbnail=thumb)
+    P, A = R.init_resnet_params(spec, dtype=torch.bfloat16, device=_dev(), seed=2)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for k in A:          # non-trivial running statistics
+        A[k].copy_((torch.rand(A[k].shape, generator=g) + 0.5).to(_dev()) if k.endswith("var") else (torch.randn(A[k].shape, generator=g) * 0.1).to(_dev()))
+    for k in P:
+        if k.endswith("_gamma"):
+            P[k].copy_((torch.rand(P[k].shape, generator=g) + 0.5).to(_dev()))
+        if k.endswith("_beta"):
+            P[k].copy_((torch.randn(P[k].shape, generator=g) * 0.1).to(_dev()))
+    x = torch.randn(4, size, size, 3, generator=g).to(_dev()).bfloat16()
+    with torch.no_grad():
+        y_fold = R.resnet_forward(spec, P, A, x, training=False)
+        os.environ["MXB200_FOLD_BN"] = "0"
+        try:
+            y_ref = R.resnet_forward(spec, P, A, x, training=False)
+        finally:
+            os.environ.pop("MXB200_FOLD_BN", None)
+        P["bn0_gamma"].mul_(2.0)              # in-place update must invalidate the fold cache
+        y_fold2 = R.resnet_forward(spec, P, A, x, training=False)
+    assert y_fold.shape == y_ref.shape == (4, 16)
+    assert _rel_err(y_fold, y_ref) < 6e-2
+    assert not torch.equal(y_fold2, y_fold)
