@@ -31,7 +31,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--batch", type=int, default=512,
+                    help="per-GPU batch (weak scaling); 512 x 8 GPUs = the global batch 4096 of the reference recipe "
+                         "(example/dynamic-training/run.sh:16)")
     ap.add_argument("--image", type=int, default=224)
     ap.add_argument("--classes", type=int, default=1000)
     ap.add_argument("--layers", type=int, default=50)

@@ -319,7 +319,14 @@ MXB_API int MXBFusedAllreduce(const void* args_blob, int blob_bytes, int blocks,
   Args a = *reinterpret_cast<const Args*>(args_blob);
   MXB_CHECK(a.nranks >= 1 && a.nranks <= kMaxRanks, "nranks out of range");
   MXB_CHECK(a.n % kChunk == 0, "arena size must be a multiple of 1024");
-  if (blocks <= 0) blocks = 64;
+  if (blocks <= 0) {
+    // one CTA per SM for large arenas (the step runs alone at the end of the iteration: measured 1.5 ms -> see
+    // profiles/ for LAMB on 110 M parameters with the previous fixed 64 CTAs); small arenas use fewer CTAs so the
+    // flag barrier stays cheap.  All CTAs must be co-resident (they pair up with the same CTA index on the peers).
+    const int64_t vec_per_rank = a.n / 8 / (a.nranks > 0 ? a.nranks : 1);
+    int64_t want = (vec_per_rank + kThreads * 4 - 1) / (kThreads * 4);
+    blocks = (int)(want < 8 ? 8 : (want > kNumSMs ? kNumSMs : want));
+  }
   if (blocks > kMaxBlocks) blocks = kMaxBlocks;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (a.g_dt == kBF16 && a.w_dt == kBF16) launch_nr<__nv_bfloat16, __nv_bfloat16>(a, blocks, s);

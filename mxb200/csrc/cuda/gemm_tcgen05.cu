@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -73,10 +74,10 @@ struct Params {
   int dbg_lbo_a, dbg_sbo_a, dbg_lbo_b, dbg_sbo_b;
 };
 
-template <int BN, typename OutT>
+template <int BN, typename OutT, int CTAS = 1>
 struct Smem {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kBBytes = BN * BLOCK_K * 2;
+  static constexpr int kBBytes = (BN / CTAS) * BLOCK_K * 2;   // CTA pair: each CTA stages half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSlabCols = 128 / (int)sizeof(OutT);      // 64 bf16 / 32 fp32 columns per staged slab
   static constexpr int kSlabs = BN / kSlabCols;
@@ -107,11 +108,20 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN, typename OutT, bool REDUCE>
+// CTAS == 2: a thread-block cluster of two CTAs (one TPC) owns a 256 x BN tile.  Each CTA stages 128 rows of A and BN/2
+// rows of B, the leader (cluster rank 0) issues tcgen05.mma.cta_group::2 (M = 256), the accumulator rows 0-127 live in
+// the leader's TMEM and rows 128-255 in the peer's, and each CTA drains / stores its own half.  Per SM this halves the
+// B-operand shared-memory traffic per flop (32 KB instead of 48 KB per 128x256x64 of work).
+template <int BN, bool A_MN, bool B_MN, typename OutT, bool REDUCE, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const Params p) {
-  using S = Smem<BN, OutT>;
+  using S = Smem<BN, OutT, CTAS>;
+  constexpr int kBRows = BN / CTAS;                 // B rows staged by this CTA
+  constexpr int kTileM = BLOCK_M * CTAS;            // rows of the output tile owned by the cluster
+  const uint32_t cta_rank = CTAS == 2 ? ptx::cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int cluster_id = (int)blockIdx.x / CTAS, num_clusters = (int)gridDim.x / CTAS;
   constexpr int kStages = S::kStages;
   constexpr int kTmemCols = 2 * BN;  // double-buffered fp32 accumulators (power of two >= 32)
   constexpr int kSlabCols = S::kSlabCols;
@@ -134,7 +144,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_m = (p.M + kTileM - 1) / kTileM;
   const int num_n = (p.N + BN - 1) / BN;
   const int num_kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_work = num_m * num_n * p.num_splits;
@@ -151,16 +161,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], kSlabs * 4);   // every slab of a tile is drained by the 4 warps of one group
+      ptx::mbar_init(&tmem_empty[i], CTAS * kSlabs * 4);   // every slab of a tile is drained by the 4 warps of one group (per CTA)
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_base_slot, kTmemCols);
-    ptx::tmem_relinquish();
+    if constexpr (CTAS == 2) {
+      ptx::tmem_alloc_2sm(tmem_base_slot, kTmemCols);   // collective over the pair: same warp id in both CTAs
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(tmem_base_slot, kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) ptx::cluster_sync();   // the peer's barriers must be initialised before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -189,30 +205,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      auto load = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+        if constexpr (CTAS == 2) ptx::tma_load_2d_2sm(dst, tm, bar, c0, c1);   // bytes credited to the leader's barrier
+        else ptx::tma_load_2d(dst, tm, bar, c0, c1);
+      };
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
         int m_blk, n_blk, kb0, kb1;
         decode(w, m_blk, n_blk, kb0, kb1);
+        const int m0 = m_blk * kTileM + (int)cta_rank * BLOCK_M;     // first A / output row of this CTA
+        const int n0 = n_blk * BN + (int)cta_rank * kBRows;          // first B row staged by this CTA
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+          if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], CTAS * S::kStageBytes);
           uint8_t* a_dst = smem_a + stage * S::kABytes;
           uint8_t* b_dst = smem_b + stage * S::kBBytes;
           if constexpr (A_MN) {
             // A stored [K, M]: boxes of [64 k][64 m]; chunk c covers m in [64c, 64c+64)
 #pragma unroll
             for (int c = 0; c < BLOCK_M / 64; ++c)
-              ptx::tma_load_2d(a_dst + c * (BLOCK_K * 128), &tmA, &full_bar[stage], m_blk * BLOCK_M + c * 64,
-                               kb * BLOCK_K);
+              load(a_dst + c * (BLOCK_K * 128), &tmA, &full_bar[stage], m0 + c * 64, kb * BLOCK_K);
           } else {
-            ptx::tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            load(a_dst, &tmA, &full_bar[stage], kb * BLOCK_K, m0);
           }
           if constexpr (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              ptx::tma_load_2d(b_dst + c * (BLOCK_K * 128), &tmB, &full_bar[stage], n_blk * BN + c * 64,
-                               kb * BLOCK_K);
+            for (int c = 0; c < kBRows / 64; ++c)
+              load(b_dst + c * (BLOCK_K * 128), &tmB, &full_bar[stage], n0 + c * 64, kb * BLOCK_K);
           } else {
-            ptx::tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BN);
+            load(b_dst, &tmB, &full_bar[stage], kb * BLOCK_K, n0);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -223,8 +243,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BN, true, A_MN, B_MN);
+    if (lane == 0 && is_leader) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, BN, true, A_MN, B_MN);
       // K-major: rows of 128B, 8-row groups 1024B apart (SBO); LBO unused (encoded as 16B).
       // MN-major: 64-element MN chunks LBO apart, 8-deep k groups 1024B apart (SBO).
       const uint32_t lbo_a = p.dbg_lbo_a ? p.dbg_lbo_a : (A_MN ? BLOCK_K * 128 : 16);
@@ -236,7 +256,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
         int m_blk, n_blk, kb0, kb1;
         decode(w, m_blk, n_blk, kb0, kb1);
         const int buf = it & 1;
@@ -253,15 +273,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             uint64_t adesc = ptx::make_smem_desc(a_addr + k * kstep_a, lbo_a, sbo_a);
             uint64_t bdesc = ptx::make_smem_desc(b_addr + k * kstep_b, lbo_b, sbo_b);
-            ptx::umma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CTAS == 2) ptx::umma_f16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else ptx::umma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (CTAS == 2) ptx::umma_commit_2sm(&empty_bar[stage], 3);
+          else ptx::umma_commit(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::umma_commit(&tmem_full[buf]);  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue (of both CTAs)
+        if constexpr (CTAS == 2) ptx::umma_commit_2sm(&tmem_full[buf], 3);
+        else ptx::umma_commit(&tmem_full[buf]);
       }
     }
   } else if (warp >= 4) {
@@ -289,12 +314,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int it = 0;
     uint32_t slab_seq = 0;   // slabs seen by this CTA (both groups count identically)
     uint32_t my_cnt = 0;     // slabs processed by this group -> staging buffer rotation
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+    for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
       int m_blk, n_blk, kb0, kb1;
       decode(w, m_blk, n_blk, kb0, kb1);
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int grow = m_blk * BLOCK_M + row;
+      const int m0 = m_blk * kTileM + (int)cta_rank * BLOCK_M;   // first output row of this CTA
+      const int grow = m0 + row;
       bool acc_ready = false;
 #pragma unroll 1
       for (int s = 0; s < kSlabs; ++s, ++slab_seq) {
@@ -330,7 +356,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // this warp is done with TMEM for this slab: release (the MMA warp waits for all kSlabs*4 arrivals)
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+        if (lane == 0) {
+          if constexpr (CTAS == 2) ptx::mbar_arrive_leader(&tmem_empty[buf]);   // the MMA issuer lives in the leader
+          else ptx::mbar_arrive(&tmem_empty[buf]);
+        }
         float v[kSlabCols];
 #pragma unroll
         for (int j = 0; j < kSlabCols; ++j) v[j] = __uint_as_float(r[j]);
@@ -378,8 +407,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         named_bar_sync(bar_id, kGroupThreads);
         if (leader) {
           const void* src = smem_d0 + (sd - ptx::smem_u32(smem_d0));
-          if constexpr (REDUCE) ptx::tma_reduce_add_2d(&tmD, src, col0, m_blk * BLOCK_M);
-          else ptx::tma_store_2d(&tmD, src, col0, m_blk * BLOCK_M);
+          if constexpr (REDUCE) ptx::tma_reduce_add_2d(&tmD, src, col0, m0);
+          else ptx::tma_store_2d(&tmD, src, col0, m0);
           ptx::tma_commit_group();
         }
         if constexpr (sizeof(OutT) == 2) {
@@ -444,9 +473,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) ptx::cluster_sync();   // the leader's MMAs read the peer's shared memory until the last tile
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (CTAS == 2) ptx::tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -492,15 +523,16 @@ static CUtensorMap make_map(const void* ptr, CUtensorMapDataType dt, int elem_by
   return m;
 }
 
-template <int BN, bool A_MN, bool B_MN, typename OutT, bool REDUCE>
+template <int BN, bool A_MN, bool B_MN, typename OutT, bool REDUCE, int CTAS = 1>
 static void launch(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldd,
                    const float* bias, int relu, float* col_sum, float* col_sumsq, const void* addend, int64_t ldc,
                    int splits, int max_ctas, const int* dbg, cudaStream_t stream) {
-  using S = Smem<BN, OutT>;
+  using S = Smem<BN, OutT, CTAS>;
+  constexpr int kBRows = BN / CTAS;
   CUtensorMap tmA = A_MN ? make_map(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, M, lda, BLOCK_K, 64)
                          : make_map(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, BLOCK_M, BLOCK_K);
   CUtensorMap tmB = B_MN ? make_map(B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, N, ldb, BLOCK_K, 64)
-                         : make_map(B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldb, BN, BLOCK_K);
+                         : make_map(B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldb, kBRows, BLOCK_K);
   CUtensorMap tmD = sizeof(OutT) == 2 ? make_map(D, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, ldd, BLOCK_M, 64)
                                       : make_map(D, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, ldd, BLOCK_M, 32);
   Params p;
@@ -517,7 +549,7 @@ static void launch(const void* A, const void* B, void* D, int M, int N, int K, i
   if (bias != nullptr && ((reinterpret_cast<uintptr_t>(bias) & 15) != 0 || (N % 4) != 0))
     throw std::runtime_error("gemm: bias must be 16B aligned and N a multiple of 4");
   p.dbg_lbo_a = dbg ? dbg[0] : 0; p.dbg_sbo_a = dbg ? dbg[1] : 0; p.dbg_lbo_b = dbg ? dbg[2] : 0; p.dbg_sbo_b = dbg ? dbg[3] : 0;
-  const int num_m = (M + BLOCK_M - 1) / BLOCK_M, num_n = (N + BN - 1) / BN;
+  const int num_m = (M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS), num_n = (N + BN - 1) / BN;
   p.gm = num_m < 16 ? num_m : 16;
   p.full_groups = num_m / p.gm;
   p.tail_gm = num_m - p.full_groups * p.gm;
@@ -528,11 +560,28 @@ static void launch(const void* A, const void* B, void* D, int M, int N, int K, i
   const int64_t num_work64 = (int64_t)num_m * num_n * p.num_splits;
   if (num_work64 > (1ll << 30)) throw std::runtime_error("gemm: too many tiles");
   const int num_work = (int)num_work64;
-  int ctas = max_ctas > 0 ? max_ctas : kNumSMs;
-  if (ctas > num_work) ctas = num_work;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, OutT, REDUCE>;
+  int clusters = (max_ctas > 0 ? max_ctas : kNumSMs) / CTAS;
+  if (clusters > num_work) clusters = num_work;
+  if (clusters < 1) clusters = 1;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, OutT, REDUCE, CTAS>;
   CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-  kern<<<ctas, kThreads, S::kTotal, stream>>>(tmA, tmB, tmD, p);
+  if constexpr (CTAS == 1) {
+    kern<<<clusters, kThreads, S::kTotal, stream>>>(tmA, tmB, tmD, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * CTAS), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = S::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, p));
+  }
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -563,9 +612,18 @@ MXB_API int MXBGemmBf16(int mode, const void* A, const void* B, void* D, int M, 
     const int sp = (mode == 2 && splits > 1) ? splits : 1;
     while (bn > 64 && nm * ((N + bn - 1) / bn) * sp < 100) bn >>= 1;
   }
+  // CTA pairs (cta_group::2): 256 x 256 tiles shared by two SMs; worth it when the problem is compute bound (deep K) and
+  // has enough 256-row tiles to fill the 74 clusters.  MXB200_GEMM_2CTA=0/1 forces it off/on.
+  static const int two_cta_env = [] { const char* e = getenv("MXB200_GEMM_2CTA"); return e ? atoi(e) : -1; }();
+  bool two_cta = false;
+  if (bn == 256 && mode != 2) {
+    const int64_t tiles2 = (((int64_t)M + 255) / 256) * (((int64_t)N + 255) / 256);
+    two_cta = two_cta_env == 1 || (two_cta_env != 0 && K >= 256 && tiles2 >= 74);
+  }
 #define MXB_GEMM_DISPATCH(AMN, BMN, OUT, RED, SPL)                                                                   \
   do {                                                                                                                \
-    if (bn == 64) gemm::launch<64, AMN, BMN, OUT, RED>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
+    if (two_cta) gemm::launch<256, AMN, BMN, OUT, RED, 2>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
+    else if (bn == 64) gemm::launch<64, AMN, BMN, OUT, RED>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
     else if (bn == 128) gemm::launch<128, AMN, BMN, OUT, RED>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
     else gemm::launch<256, AMN, BMN, OUT, RED>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
   } while (0)
