@@ -125,7 +125,7 @@ template <typename T, int VPT>
 __global__ void __launch_bounds__(kThreads)
 bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
            const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
-           float* __restrict__ partials /* [grid][2C] */, int64_t rows) {
+           float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows) {
   constexpr int C = VPT * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float g[VPT][8], dg[VPT][8], db[VPT][8];
@@ -164,11 +164,13 @@ bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __res
       store8<T>(dx + r * C + (j * 32 + lane) * 8, o);
     }
   }
-  // fold the 8 warps of the block (same lane -> same columns), then one coalesced partial row per block
+  // fold the 8 warps of the block (same lane -> same columns), then one fp32 RED per column and block into the
+  // (accumulating) outputs -- a second "sum the per-block partials" kernel cost as much as this one (19 us, latency bound)
   __shared__ float red[kWarps][32 * 8 + 1];
-  float* mine = partials + (size_t)blockIdx.x * 2 * C;
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
+    float* dst = which ? dbeta : dgamma;
+    if (dst == nullptr) continue;
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
       __syncthreads();
@@ -179,7 +181,7 @@ bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __res
         float a = 0.f;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) a += red[w][i];
-        mine[which * C + j * 256 + i] = a;
+        atomicAdd(dst + j * 256 + i, a);
       }
     }
   }
@@ -284,6 +286,52 @@ bias_act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const flo
   }
 }
 
+// out[c] += sum over rows of x[r, c]  (bias gradients of FullyConnected: db = colsum(dy); the reference runs a generic
+// reduce, fully_connected-inl.h:162-171).  Block = 32 vector-columns x 8 row lanes, 4 independent loads in flight per
+// thread, shared-memory fold over the row lanes, one fp32 RED per column and block.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t M, int C, int rows_per_block) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int vcol = blockIdx.y * 32 + tx;
+  const bool active = vcol * 8 < C;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(M, r_begin + rows_per_block);
+  if (active) {
+    int64_t r = r_begin + ty;
+    for (; r + 24 < r_end; r += 32) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8<T>(x + (r + 8 * u) * C + vcol * 8, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v[u][k];
+    }
+    for (; r < r_end; r += 8) {
+      float v[8];
+      load8<T>(x + r * C + vcol * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+  }
+  __shared__ float red[8][32 * 8 + 1];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[ty][tx * 8 + k] = acc[k];
+  __syncthreads();
+  const int c = threadIdx.x;                       // 256 threads <-> 256 columns of this block
+  const int col = blockIdx.y * 256 + c;
+  if (col < C) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += red[w][c];
+    atomicAdd(out + col, a);
+  }
+}
+
 }  // namespace ln
 }  // namespace mxb
 
@@ -303,10 +351,14 @@ template <typename T, int VPT>
 static void ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
                    float* dgamma, float* dbeta, float* ws, int64_t rows, int accumulate, cudaStream_t s) {
   constexpr int C = VPT * 256;
+  (void)ws;
   int grid = (int)std::min<int64_t>((rows + kWarps * 4 - 1) / (kWarps * 4), (int64_t)kMaxGrid);
   if (grid < 1) grid = 1;
-  bwd_kernel<T, VPT><<<grid, kThreads, 0, s>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, ws, rows);
-  reduce_partials_kernel<<<(2 * C + 255) / 256, 256, 0, s>>>(ws, grid, C, dgamma, dbeta, accumulate);
+  if (!accumulate) {
+    if (dgamma) CUDA_CHECK(cudaMemsetAsync(dgamma, 0, C * sizeof(float), s));
+    if (dbeta) CUDA_CHECK(cudaMemsetAsync(dbeta, 0, C * sizeof(float), s));
+  }
+  bwd_kernel<T, VPT><<<grid, kThreads, 0, s>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta, rows);
 }
 
 #define MXB_LN_DISPATCH(FN, ...)                                                            \
@@ -390,6 +442,22 @@ MXB_API int MXBBiasActBackward(const void* dy, const void* x, int dt, const floa
   if (dt == kBF16) bias_act_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, bias, (__nv_bfloat16*)dx, total8, C / 8, act, slope);
   else if (dt == kF32) bias_act_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)dy, (const float*)x, bias, (float*)dx, total8, C / 8, act, slope);
   else throw std::runtime_error("bias_act: dtype must be bf16 or fp32");
+  CUDA_CHECK(cudaGetLastError());
+  MXB_CATCH
+}
+
+// out (fp32 [C]) += column sums of x [rows, C]; C % 8 == 0.  Accumulates (zero ``out`` first for a plain sum).
+MXB_API int MXBColSumAccumulate(const void* x, int dt, float* out, int64_t rows, int C, void* stream) {
+  MXB_TRY
+  MXB_CHECK(C % 8 == 0, "colsum: C must be a multiple of 8");
+  if (rows == 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int rpb = 128;
+  while (rpb < 4096 && (rows + rpb - 1) / rpb * ((C + 255) / 256) > kNumSMs * 8) rpb *= 2;
+  dim3 grid((unsigned)((rows + rpb - 1) / rpb), (unsigned)((C + 255) / 256), 1);
+  if (dt == kBF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, out, rows, C, rpb);
+  else if (dt == kF32) colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)x, out, rows, C, rpb);
+  else throw std::runtime_error("colsum: dtype must be bf16 or fp32");
   CUDA_CHECK(cudaGetLastError());
   MXB_CATCH
 }

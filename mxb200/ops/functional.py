@@ -121,6 +121,24 @@ def _sink_ok(sink, shape):
     return sink is not None and sink.dtype is torch.float32 and tuple(sink.shape) == tuple(shape) and sink.is_contiguous()
 
 
+def colsum(x2, out=None):
+    """fp32 column sums of a contiguous [rows, C] tensor; ``out`` (fp32 [C]) is accumulated into (gradient-arena view)."""
+    C = x2.shape[-1]
+    if _use_native(x2) and x2.dim() == 2 and x2.is_contiguous() and C % 8 == 0 and x2.dtype in (torch.bfloat16, torch.float32) \
+            and (out is None or (out.dtype is torch.float32 and out.is_contiguous())):
+        res = out if out is not None else torch.zeros(C, dtype=torch.float32, device=x2.device)
+        lib = N.cuda()
+        N.check(lib, lib.MXBColSumAccumulate(_p(x2), c_int(code(x2.dtype)), _p(res), c_int64(x2.shape[0]), c_int(C),
+                                             N.stream_of(x2)))
+        LAUNCHES[0] += 1
+        return res
+    s_ = x2.sum(0, dtype=torch.float32)
+    if out is not None:
+        out.add_(s_)
+        return out
+    return s_
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x.W^T (+b)(relu).  Optional extras (all used by the fused ResNet):
       * ``stats``   : fp32 workspace receiving column sum / sum-of-squares of y (BN statistics for free);
@@ -172,11 +190,10 @@ class _LinearFn(torch.autograd.Function):
             else:
                 gw = gemm_tn(g2, x2, out_dtype=w.dtype)
         if ctx.has_bias and (ctx.needs_input_grad[2] or ctx.sink_b is not None):
-            gsum = g2.sum(0, dtype=torch.float32)
             if ctx.sink_b is not None:
-                ctx.sink_b.add_(gsum)
+                colsum(g2, out=ctx.sink_b)               # one kernel, straight into the fp32 gradient arena
             else:
-                gb = gsum.to(ctx.bdtype)
+                gb = colsum(g2).to(ctx.bdtype)
         return gx, gw, gb, None, None, None, None, None
 
 

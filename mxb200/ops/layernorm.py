@@ -72,7 +72,7 @@ class _LayerNormFn(torch.autograd.Function):
                                               N.ptr(rstd), N.ptr(dx), N.ptr(dg), N.ptr(db), N.ptr(_ws(x2.device, C)),
                                               N.c_int64(rows), N.c_int(C), N.c_int(1 if use_sink else 0),
                                               N.stream_of(x2)))
-        LAUNCHES[0] += 2
+        LAUNCHES[0] += 1
         dxv = dx.view(ctx.shape)
         dres = dxv if ctx.has_res else None           # d(x + r) flows unchanged to both addends
         if use_sink:
@@ -121,12 +121,11 @@ class _BiasActFn(torch.autograd.Function):
         LAUNCHES[0] += 1
         db = None
         if b32 is not None:
-            db = dx.sum(0, dtype=torch.float32)
+            from .functional import colsum
             if sink_b is not None:       # fp32 gradient-arena view: accumulate there, autograd gets nothing
-                sink_b.add_(db)
-                db = None
+                colsum(dx, out=sink_b)
             else:
-                db = db.to(bdt)
+                db = colsum(dx).to(bdt)
         return dx.view(shape), db, None, None, None
 
 

@@ -755,3 +755,13 @@ def test_resnet_inference_folded_bn_matches_unfolded(layers, thumb, size):
     assert y_fold.shape == y_ref.shape == (4, 16)
     assert _rel_err(y_fold, y_ref) < 6e-2
     assert not torch.equal(y_fold2, y_fold)
+
+
+@pytest.mark.parametrize("rows,C,dtype", [(8192, 768, torch.bfloat16), (1000, 3072, torch.bfloat16), (77, 1000, torch.float32), (5000, 8, torch.bfloat16)])
+def test_colsum_accumulate(rows, C, dtype):
+    from mxb200.ops import functional as K_
+    x = torch.randn(rows, C, device=_dev()).to(dtype)
+    out = torch.full((C,), 3.0, device=_dev())
+    K_.colsum(x, out=out)
+    assert _rel_err(out - 3.0, x.float().sum(0)) < 2e-3
+    assert _rel_err(K_.colsum(x), x.float().sum(0)) < 2e-3
