@@ -742,17 +742,23 @@ class Node {
       std::lock_guard<std::mutex> lk(mu_);
       dropped = dropped_ids_;
     }
+    bool self = false;
     for (int id : ids) {
       if (id > max_id || dropped.count(id)) continue;   // newcomers never see a response they did not ask for
       if (id == my_id_) {
-        std::lock_guard<std::mutex> lk(mu_);
-        ++barrier_gen_;
-        cv_.notify_all();
+        self = true;
         continue;
       }
       Header h;
       h.cmd = kBarrierDone;
       Send(id, h, "", nullptr, 0);
+    }
+    // Release this node LAST: its main thread may be sitting in the final barrier before Stop(); waking it first let
+    // it tear the sockets down while the loop above was still notifying the other nodes (rare shutdown hang).
+    if (self) {
+      std::lock_guard<std::mutex> lk(mu_);
+      ++barrier_gen_;
+      cv_.notify_all();
     }
   }
 

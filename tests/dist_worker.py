@@ -12,7 +12,24 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mxb200 as mx  # noqa: E402
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "default"
-kv = mx.kv.create("dist_sync")
+# "gpu": worker-side arrays live on cuda:0 (dist_device_sync: device gradients staged through pinned host buffers)
+ctx = mx.gpu(0) if mode == "gpu" else mx.cpu()
+_nd = mx.nd
+
+
+class _OnCtx(object):
+    """mx.nd factory functions that allocate on ``ctx``."""
+
+    def __getattr__(self, name):
+        f = getattr(_nd, name)
+        if name in ("ones", "zeros", "array"):
+            return lambda *a, **k: f(*a, ctx=ctx, **k)
+        return f
+
+
+if mode == "gpu":
+    mx.nd = _OnCtx()
+kv = mx.kv.create("dist_device_sync" if mode == "gpu" else "dist_sync")
 rank, n = kv.rank, kv.num_workers
 shape = (3, 4)
 rate = 2.0

@@ -765,3 +765,17 @@ def test_colsum_accumulate(rows, C, dtype):
     K_.colsum(x, out=out)
     assert _rel_err(out - 3.0, x.float().sum(0)) < 2e-3
     assert _rel_err(K_.colsum(x), x.float().sum(0)) < 2e-3
+
+
+def test_dist_device_sync_with_gpu_workers(tmp_path):
+    """Parameter-server kvstore with the workers' arrays on the GPU (2 workers share cuda:0, 1 server): push/pull,
+    big-array sharding, exclude-update keys and row_sparse_pull through the TCP van."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "launch.py"), "-n", "2", "-s", "1", "--launcher", "local",
+                        sys.executable, os.path.join(root, "tests", "dist_worker.py"), "gpu"], cwd=str(tmp_path), timeout=300,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("OK") == 2
