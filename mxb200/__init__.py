@@ -28,7 +28,8 @@ _LAZY = {
     "parallel": ".parallel", "models": ".models", "ops": ".ops", "executor": ".executor", "rtc": ".rtc",
     "kvstore_server": ".kvstore_server", "contrib": ".contrib", "visualization": ".visualization", "viz": ".visualization",
     "name": ".name", "attribute": ".attribute", "operator": ".operator", "rnn": ".rnn", "log": ".log",
-    "libinfo": ".libinfo", "util": ".util",
+    "libinfo": ".libinfo", "util": ".util", "registry": ".registry", "misc": ".misc", "notebook": ".notebook",
+    "executor_manager": ".executor_manager", "torch": ".torch",
 }
 
 

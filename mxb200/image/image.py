@@ -11,7 +11,7 @@ from .. import recordio
 
 __all__ = ["imdecode", "imread", "imresize", "resize_short", "fixed_crop", "random_crop", "center_crop", "color_normalize",
            "scale_down", "Augmenter", "ResizeAug", "ForceResizeAug", "RandomCropAug", "CenterCropAug", "HorizontalFlipAug",
-           "CastAug", "ColorNormalizeAug", "CreateAugmenter", "ImageIter"]
+           "CastAug", "ColorNormalizeAug", "CreateAugmenter", "ImageIter", "random_size_crop", "SequentialAug", "RandomSizedCropAug", "RandomOrderAug", "BrightnessJitterAug", "ContrastJitterAug", "SaturationJitterAug", "HueJitterAug", "ColorJitterAug", "LightingAug", "RandomGrayAug"]
 
 
 def imdecode(buf, flag=1, to_rgb=1, out=None):
@@ -101,7 +101,14 @@ class Augmenter(object):
 
     def dumps(self):
         import json
-        return json.dumps([self.__class__.__name__.lower(), self._kwargs])
+
+        def conv(v):
+            if isinstance(v, np.ndarray):
+                return v.tolist()
+            if isinstance(v, NDArray):
+                return v.asnumpy().tolist()
+            return v
+        return json.dumps([self.__class__.__name__.lower(), {k: conv(v) for k, v in self._kwargs.items()}])
 
     def __call__(self, src):
         raise NotImplementedError("Must override implementation.")
@@ -173,19 +180,184 @@ class ColorNormalizeAug(Augmenter):
         return color_normalize(src, self.mean, self.std)
 
 
+def random_size_crop(src, size, area, ratio, interp=2, **kwargs):
+    """Random crop with area in ``area`` (fraction or (min, max)) and aspect ratio in ``ratio``, resized to ``size``
+    (Inception-style; image.py:441-495).  Falls back to a centre crop after 10 failed draws."""
+    h, w = src.shape[0], src.shape[1]
+    src_area = h * w
+    if "min_area" in kwargs:
+        area = kwargs.pop("min_area")
+    if not isinstance(area, (tuple, list)):
+        area = (area, 1.0)
+    for _ in range(10):
+        target_area = random.uniform(area[0], area[1]) * src_area
+        log_ratio = (np.log(ratio[0]), np.log(ratio[1]))
+        new_ratio = np.exp(random.uniform(*log_ratio))
+        new_w = int(round(np.sqrt(target_area * new_ratio)))
+        new_h = int(round(np.sqrt(target_area / new_ratio)))
+        if new_w <= w and new_h <= h:
+            x0 = random.randint(0, w - new_w)
+            y0 = random.randint(0, h - new_h)
+            return fixed_crop(src, x0, y0, new_w, new_h, size, interp), (x0, y0, new_w, new_h)
+    return center_crop(src, size, interp)
+
+
+class SequentialAug(Augmenter):
+    def __init__(self, ts):
+        super(SequentialAug, self).__init__()
+        self.ts = ts
+
+    def dumps(self):
+        return [self.__class__.__name__.lower(), [x.dumps() for x in self.ts]]
+
+    def __call__(self, src):
+        for aug in self.ts:
+            src = aug(src)
+        return src
+
+
+class RandomSizedCropAug(Augmenter):
+    def __init__(self, size, area, ratio, interp=2, **kwargs):
+        super(RandomSizedCropAug, self).__init__(size=size, area=area, ratio=ratio, interp=interp)
+        self.size, self.area, self.ratio, self.interp = size, kwargs.pop("min_area", area), ratio, interp
+
+    def __call__(self, src):
+        return random_size_crop(src, self.size, self.area, self.ratio, self.interp)[0]
+
+
+class RandomOrderAug(Augmenter):
+    def __init__(self, ts):
+        super(RandomOrderAug, self).__init__()
+        self.ts = ts
+
+    def dumps(self):
+        return [self.__class__.__name__.lower(), [x.dumps() for x in self.ts]]
+
+    def __call__(self, src):
+        random.shuffle(self.ts)
+        for t in self.ts:
+            src = t(src)
+        return src
+
+
+_GRAY = np.array([[[0.299, 0.587, 0.114]]], dtype=np.float32)
+
+
+class BrightnessJitterAug(Augmenter):
+    def __init__(self, brightness):
+        super(BrightnessJitterAug, self).__init__(brightness=brightness)
+        self.brightness = brightness
+
+    def __call__(self, src):
+        alpha = 1.0 + random.uniform(-self.brightness, self.brightness)
+        return src * alpha
+
+
+class ContrastJitterAug(Augmenter):
+    def __init__(self, contrast):
+        super(ContrastJitterAug, self).__init__(contrast=contrast)
+        self.contrast = contrast
+
+    def __call__(self, src):
+        alpha = 1.0 + random.uniform(-self.contrast, self.contrast)
+        gray = (src.astype("float32") * array(_GRAY)).sum()
+        gray = (3.0 * (1.0 - alpha) / float(src.size)) * float(gray.asnumpy().reshape(-1)[0])
+        return src * alpha + gray
+
+
+class SaturationJitterAug(Augmenter):
+    def __init__(self, saturation):
+        super(SaturationJitterAug, self).__init__(saturation=saturation)
+        self.saturation = saturation
+
+    def __call__(self, src):
+        alpha = 1.0 + random.uniform(-self.saturation, self.saturation)
+        gray = (src.astype("float32") * array(_GRAY)).sum(axis=2, keepdims=True) * (1.0 - alpha)
+        return src * alpha + gray
+
+
+class HueJitterAug(Augmenter):
+    """Rotate the hue in YIQ space (image.py:752-783)."""
+
+    def __init__(self, hue):
+        super(HueJitterAug, self).__init__(hue=hue)
+        self.hue = hue
+        self.tyiq = np.array([[0.299, 0.587, 0.114], [0.596, -0.274, -0.321], [0.211, -0.523, 0.311]])
+        self.ityiq = np.array([[1.0, 0.956, 0.621], [1.0, -0.272, -0.647], [1.0, -1.107, 1.705]])
+
+    def __call__(self, src):
+        alpha = random.uniform(-self.hue, self.hue)
+        u, w = np.cos(alpha * np.pi), np.sin(alpha * np.pi)
+        bt = np.array([[1.0, 0.0, 0.0], [0.0, u, -w], [0.0, w, u]])
+        t = np.dot(np.dot(self.ityiq, bt), self.tyiq).T
+        return NDArray((src._t.float() @ torch.from_numpy(t).float().to(src._t.device)), src.context)
+
+
+class ColorJitterAug(RandomOrderAug):
+    def __init__(self, brightness, contrast, saturation):
+        ts = []
+        if brightness > 0:
+            ts.append(BrightnessJitterAug(brightness))
+        if contrast > 0:
+            ts.append(ContrastJitterAug(contrast))
+        if saturation > 0:
+            ts.append(SaturationJitterAug(saturation))
+        super(ColorJitterAug, self).__init__(ts)
+
+
+class LightingAug(Augmenter):
+    """AlexNet-style PCA noise (image.py:809-832)."""
+
+    def __init__(self, alphastd, eigval, eigvec):
+        super(LightingAug, self).__init__(alphastd=alphastd, eigval=eigval, eigvec=eigvec)
+        self.alphastd, self.eigval, self.eigvec = alphastd, np.asarray(eigval), np.asarray(eigvec)
+
+    def __call__(self, src):
+        alpha = np.random.normal(0, self.alphastd, size=(3,))
+        rgb = np.dot(self.eigvec * alpha, self.eigval)
+        return src + array(rgb.astype(np.float32))
+
+
+class RandomGrayAug(Augmenter):
+    def __init__(self, p):
+        super(RandomGrayAug, self).__init__(p=p)
+        self.p = p
+        self.mat = torch.tensor([[0.21, 0.21, 0.21], [0.72, 0.72, 0.72], [0.07, 0.07, 0.07]])
+
+    def __call__(self, src):
+        if random.random() < self.p:
+            return NDArray(src._t.float() @ self.mat.to(src._t.device), src.context)
+        return src
+
+
 def CreateAugmenter(data_shape, resize=0, rand_crop=False, rand_resize=False, rand_mirror=False, mean=None, std=None,
                     brightness=0, contrast=0, saturation=0, hue=0, pca_noise=0, rand_gray=0, inter_method=2):
+    """Standard augmenter list (image.py:908-1019): resize, (random sized | random | centre) crop, mirror, cast, colour
+    jitter, hue, PCA lighting, random gray, normalisation."""
     auglist = []
     if resize > 0:
         auglist.append(ResizeAug(resize, inter_method))
     crop_size = (data_shape[2], data_shape[1])
-    if rand_crop:
+    if rand_resize:
+        assert rand_crop
+        auglist.append(RandomSizedCropAug(crop_size, 0.08, (3.0 / 4.0, 4.0 / 3.0), inter_method))
+    elif rand_crop:
         auglist.append(RandomCropAug(crop_size, inter_method))
     else:
         auglist.append(CenterCropAug(crop_size, inter_method))
     if rand_mirror:
         auglist.append(HorizontalFlipAug(0.5))
     auglist.append(CastAug())
+    if brightness or contrast or saturation:
+        auglist.append(ColorJitterAug(brightness, contrast, saturation))
+    if hue:
+        auglist.append(HueJitterAug(hue))
+    if pca_noise > 0:
+        eigval = np.array([55.46, 4.794, 1.148])
+        eigvec = np.array([[-0.5675, 0.7192, 0.4009], [-0.5808, -0.0045, -0.8140], [-0.5836, -0.6948, 0.4203]])
+        auglist.append(LightingAug(pca_noise, eigval, eigvec))
+    if rand_gray > 0:
+        auglist.append(RandomGrayAug(rand_gray))
     if mean is True:
         mean = np.array([123.68, 116.28, 103.53])
     if std is True:

@@ -1,0 +1,32 @@
+"""Checkpoint helpers for networks built from RNN cells (reference: python/mxnet/rnn/rnn.py): parameters are saved in
+the unpacked (per-gate) form so checkpoints are interchangeable between fused and unfused cells."""
+from ..model import load_checkpoint, save_checkpoint
+from .rnn_cell import BaseRNNCell
+
+__all__ = ["save_rnn_checkpoint", "load_rnn_checkpoint", "do_rnn_checkpoint"]
+
+
+def save_rnn_checkpoint(cells, prefix, epoch, symbol, arg_params, aux_params):
+    if isinstance(cells, BaseRNNCell):
+        cells = [cells]
+    for cell in cells:
+        arg_params = cell.unpack_weights(arg_params)
+    save_checkpoint(prefix, epoch, symbol, arg_params, aux_params)
+
+
+def load_rnn_checkpoint(cells, prefix, epoch):
+    sym, arg, aux = load_checkpoint(prefix, epoch)
+    if isinstance(cells, BaseRNNCell):
+        cells = [cells]
+    for cell in cells:
+        arg = cell.pack_weights(arg)
+    return sym, arg, aux
+
+
+def do_rnn_checkpoint(cells, prefix, period=1):
+    period = int(max(1, period))
+
+    def _callback(iter_no, sym=None, arg=None, aux=None):
+        if (iter_no + 1) % period == 0:
+            save_rnn_checkpoint(cells, prefix, iter_no + 1, sym, arg, aux)
+    return _callback

@@ -38,6 +38,35 @@ _PARAM_ARGS = {
 _LABEL_OPS = {"SoftmaxOutput": "label", "Softmax": "label", "LinearRegressionOutput": "label",
               "LogisticRegressionOutput": "label", "MAERegressionOutput": "label", "SVMOutput": "label"}
 _MULTI_OUT = {"split": "num_outputs", "SliceChannel": "num_outputs"}
+_FIXED_MULTI_OUT = {"_contrib_MultiBoxTarget": 3, "linalg_gelqf": 2, "_linalg_gelqf": 2, "linalg_syevd": 2, "_linalg_syevd": 2,
+                    "_contrib_quantize": 3, "_contrib_requantize": 3, "_contrib_bipartite_matching": 2, "histogram": 2,
+                    "_histogram": 2, "_contrib_quantized_fully_connected": 3, "_contrib_quantized_conv": 3,
+                    "_contrib_quantized_pooling": 3, "_contrib_quantized_flatten": 3}
+
+
+def _truthy(v):
+    return v in (True, 1, "1", "True", "true")
+
+
+def _num_outputs(op, attrs):
+    """Number of outputs of an operator node (nnvm FNumOutputs of the reference registrations)."""
+    if op in _MULTI_OUT:
+        return int(attrs.get(_MULTI_OUT[op], 1))
+    if op in _FIXED_MULTI_OUT:
+        return _FIXED_MULTI_OUT[op]
+    if op == "RNN":
+        if not _truthy(attrs.get("state_outputs", False)):
+            return 1
+        return 3 if str(attrs.get("mode", "lstm")) == "lstm" else 2
+    if op == "topk":
+        return 2 if str(attrs.get("ret_typ", "indices")) == "both" else 1
+    if op in ("BatchNorm", "BatchNorm_v1", "CuDNNBatchNorm", "LayerNorm"):
+        return 3 if _truthy(attrs.get("output_mean_var", False)) else 1
+    if op == "_sample_multinomial":
+        return 2 if _truthy(attrs.get("get_prob", False)) else 1
+    if op in ("_contrib_Proposal", "_contrib_MultiProposal"):
+        return 2 if _truthy(attrs.get("output_score", False)) else 1
+    return 1
 
 
 class _NameManager(object):
@@ -430,8 +459,8 @@ def load_json(json_str):
         nodes.append(n)
     for n, d in zip(nodes, g["nodes"]):
         n.inputs = [(nodes[i[0]], i[1]) for i in d["inputs"]]
-        if n.op in _MULTI_OUT:
-            n.num_outputs = int(n.attrs.get(_MULTI_OUT[n.op], 1))
+        if n.op is not None:
+            n.num_outputs = _num_outputs(n.op, n.attrs)
         # legacy graphs: aux inputs of BatchNorm are variables named *moving_*
         if n.op == "BatchNorm":
             for inp, _ in n.inputs[3:5]:
@@ -490,7 +519,7 @@ def ones(shape, dtype=None, **kwargs):
 def _make_op(op, inputs, attrs, name=None, hint=None):
     hint = hint or op.lower().lstrip("_")
     name = _NameManager.prefix() + (name if name else _NameManager.get(hint))
-    nout = int(attrs.get(_MULTI_OUT[op], 1)) if op in _MULTI_OUT else 1
+    nout = _num_outputs(op, attrs)
     node = _Node(op, name, attrs, [s._outputs[0] for s in inputs], nout)
     from ..attribute import current_attrs
     for k, v in current_attrs().items():
@@ -548,7 +577,7 @@ def _create(op, args, kwargs):
         order = inputs + [sym_kwargs[k] for k in sym_kwargs]
         if sym_kwargs:
             attrs["__kwarg_inputs__"] = tuple(sym_kwargs.keys())
-    nout = int(attrs.get(_MULTI_OUT[op], 1)) if op in _MULTI_OUT else 1
+    nout = _num_outputs(op, attrs)
     node = _Node(op, node_name, attrs, [s._outputs[0] for s in order], nout)
     from ..attribute import current_attrs
     for k, v in current_attrs().items():
@@ -573,10 +602,13 @@ def _run_node(node, ins, meta):
         ins = [NDArray(t, cpu()) for t in ins]
     if op in _SCALAR_OPS:
         out = _SCALAR_OPS[op](ins[0], attrs["scalar"], attrs.get("reverse", False))
-    elif op == "_zeros":
-        out = nd.zeros(attrs["shape"], dtype=attrs.get("dtype"))
-    elif op == "_ones":
-        out = nd.ones(attrs["shape"], dtype=attrs.get("dtype"))
+    elif op in ("_zeros", "_ones"):
+        if meta:   # shape inference: stay on the meta device
+            import torch as _torch
+            from ..base import torch_dtype as _td
+            out = NDArray(_torch.empty(tuple(attrs["shape"]), dtype=_td(attrs.get("dtype") or "float32"), device="meta"), cpu())
+        else:
+            out = (nd.zeros if op == "_zeros" else nd.ones)(attrs["shape"], dtype=attrs.get("dtype"))
     else:
         fn = _ndop.get(op)
         if fn is None:
@@ -613,6 +645,27 @@ def _run_node(node, ins, meta):
 def _infer_param_shapes(node, vals, vshape, vdtype):
     """Fill shapes of parameter/label variables feeding ``node`` from its data input (infer_shape rules)."""
     op = node.op
+    if op == "RNN":
+        # flat cuDNN-layout parameter vector of the fused RNN op: size from (input size, state size, layers, directions, mode)
+        a = node.attrs
+        names = list(a.get("__kwarg_inputs__", ())) or ["data", "parameters", "state", "state_cell"][:len(node.inputs)]
+        byname = dict(zip(names, node.inputs))
+        if "data" in byname and "parameters" in byname:
+            d = vals.get((id(byname["data"][0]), byname["data"][1]))
+            pn, pidx = byname["parameters"]
+            if d is not None and pn.op is None and (id(pn), pidx) not in vals:
+                g = {"rnn_relu": 1, "rnn_tanh": 1, "lstm": 4, "gru": 3}[str(a.get("mode", "lstm"))]
+                H, L = int(a["state_size"]), int(a.get("num_layers", 1))
+                nd_ = 2 if _truthy(a.get("bidirectional", False)) else 1
+                size, inp = 0, int(d.shape[2])
+                for _l in range(L):
+                    size += nd_ * (g * H * (inp + H) + 2 * g * H)
+                    inp = H * nd_
+                dt = dtype_name(d.dtype)
+                vals[(id(pn), pidx)] = torch.empty((size,), dtype=d.dtype, device="meta")
+                vshape[pn.name] = (size,)
+                vdtype[pn.name] = dt
+        return
     if op not in _PARAM_ARGS and op not in _LABEL_OPS:
         return
     a = node.attrs
