@@ -137,7 +137,13 @@ class Trainer(object):
                 return False
         return True
 
-    def _maybe_fuse(self):
+    def init_kvstore(self):
+        """Create the kvstore (and the fused arena path) now instead of lazily at the first ``step``.  Elastic jobs
+        call this before the first forward pass so that a newcomer starts from the live weights."""
+        if not self._kv_initialized:
+            self._init_kvstore()
+
+    def _maybe_fuse(self, state=None):
         if self._fused is not None or not self._fusable():
             return
         from ..parallel.trainer import DeviceTrainer
@@ -145,14 +151,17 @@ class Trainer(object):
         kv = self._kvstore
         world = kv.num_workers if kv is not None else 1
         rank = kv.rank if kv is not None else 0
+        elastic = kv is not None and hasattr(kv, "elastic_group")
         train = [p for p in self._params if p.grad_req != "null"]
         if not train:
             return
         named = [(p.name, p.data(ctx)._t.detach()) for p in train]
         lr_mult = {p.name: p.lr_mult for p in train}
         wd_mult = {p.name: p.wd_mult for p in train}
-        dt = DeviceTrainer(named, ctx.torch_device, rank=rank, world=world, lr_mult=lr_mult, wd_mult=wd_mult)
+        dt = DeviceTrainer(named, ctx.torch_device, rank=rank, world=world, lr_mult=lr_mult, wd_mult=wd_mult,
+                           group=kv.peer_group(ctx.torch_device) if elastic else None)
         views = dt.params()
+        stale = elastic and (state is not None or kv.is_new_worker)   # gradients computed before the weights were synced
         for p in train:
             v = views[p.name]
             d = p._data[0]
@@ -161,12 +170,19 @@ class Trainer(object):
                 d._grad_hook = None
             sink = dt.grad_sinks[p.name]
             with torch.no_grad():
-                if p._grad is not None and p._grad[0]._t is not None:
+                if not stale and p._grad is not None and p._grad[0]._t is not None:
                     sink.copy_(p._grad[0]._t)           # gradients of the step that triggered the lazy fusion
             d._t = v
             p._grad[0]._t = sink                        # fp32 arena view (what ``param.grad()`` shows)
             p._grad_sink = dt.grad_sinks[p.name]
-        if world > 1:
+        if elastic:
+            if state is not None:
+                dt.import_state(state)
+            dt.sync_from_rank0(kv._barrier)              # weights + optimizer state of rank 0 (a newcomer's live state)
+            dt.broadcast_from_rank0([p._data[0]._t for p in self._params if p.grad_req == "null" and p._data is not None],
+                                    kv._barrier)
+            kv._register_trainer(self)
+        elif world > 1:
             # non-trainable state (BN running stats): start from rank 0's values (kv.init semantics)
             import torch.distributed as dist
             for p in self._params:
@@ -177,6 +193,22 @@ class Trainer(object):
                 dist.broadcast(ar.weights, src=0)
         self._fused = dt
         self._params_to_init = []
+
+    # elastic membership change (kvstore('elastic_device')): called by the store around the scheduler barrier
+    def _elastic_detach(self):
+        self._elastic_state = None
+        if self._fused is None:
+            return
+        kv = self._kvstore
+        self._fused.gather_state(kv._barrier)            # un-shard the ZeRO-1 optimizer state while everyone is still here
+        self._elastic_state = self._fused.export_state()
+        torch.cuda.synchronize(self._fused.device)
+        kv._barrier()
+        self._unfuse()
+
+    def _elastic_attach(self):
+        state, self._elastic_state = getattr(self, "_elastic_state", None), None
+        self._maybe_fuse(state=state if state is not None else {"num_update": 0, "params": {}})
 
     def _unfuse(self):
         dt, self._fused = self._fused, None

@@ -382,10 +382,80 @@ class KVStoreDevice(KVStoreLocal):
         return membership.process_group_membership_barrier(self, env)
 
 
+class KVStoreElasticDevice(KVStoreLocal):
+    """kvstore('elastic_device'): one process per GPU on ONE box whose worker set changes at epoch boundaries.
+
+    Membership is decided by the same scheduler protocol as the parameter-server stores (host file, removal before
+    addition, dense re-ranking, newcomers launched with NEW_WORKER=1 / EPOCH_BEGIN; csrc/host/pslite.cc) but there are no
+    servers in the data path: ``gluon.Trainer`` runs its step as the fused P2P allreduce+update kernel over the GPUs that
+    are currently in the job.  ``_membership_change_barrier`` un-shards the optimizer state, tears the peer mapping down,
+    meets the other workers in the scheduler barrier (leavers exit there), rebuilds the mapping over the new rank set and
+    lets every rank adopt rank 0's weights / optimizer state / aux state (parallel/membership.py)."""
+
+    def __init__(self, kv_type="elastic_device"):
+        super(KVStoreElasticDevice, self).__init__("device")
+        self._type = kv_type
+        from ..parallel.membership import ElasticGroup
+        self.elastic_group = ElasticGroup()
+        self._trainers = []
+        self._closed = False
+
+    @property
+    def type(self):
+        return self._type
+
+    @property
+    def rank(self):
+        return self.elastic_group.rank
+
+    @property
+    def num_workers(self):
+        return self.elastic_group.world
+
+    @property
+    def is_new_worker(self):
+        return self.elastic_group.is_new_worker
+
+    def peer_group(self, device):
+        return self.elastic_group.peer_group(device)
+
+    def _register_trainer(self, trainer):
+        import weakref
+        if not any(r() is trainer for r in self._trainers):
+            self._trainers.append(weakref.ref(trainer))
+
+    def _live_trainers(self):
+        return [t for t in (r() for r in self._trainers) if t is not None]
+
+    def _barrier(self):
+        self.elastic_group.barrier()
+
+    def _membership_change_barrier(self, env):
+        trainers = self._live_trainers()
+        for t in trainers:
+            t._elastic_detach()
+        epoch = int(env.get("EPOCH_BEGIN", 0)) if isinstance(env, dict) else 0
+        old, new = self.elastic_group.membership_barrier(epoch)      # a removed worker exits in here
+        for t in trainers:
+            t._elastic_attach()
+        return new
+
+    def close(self):
+        if not self._closed:
+            self._closed = True
+            for t in self._live_trainers():
+                if t._fused is not None:
+                    t._unfuse()
+            self.elastic_group.close()
+
+
 def create(name="local"):
     """mx.kv.create (python/mxnet/kvstore.py:645-688; type parsing as in src/kvstore/kvstore.cc:40-77)."""
     if not isinstance(name, str):
         raise TypeError("name must be a string")
+    if name.startswith("elastic_device") or ("dist" in name and "device" in name and getenv("MXB200_SINGLE_BOX_ELASTIC", False)):
+        # single-box elastic job: GPUs exchange gradients over NVLink, the scheduler only manages membership
+        return KVStoreElasticDevice("elastic_device")
     if "dist" in name:
         from .dist import KVStoreDist
         return KVStoreDist(name)
