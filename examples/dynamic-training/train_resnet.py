@@ -15,6 +15,8 @@ Launch (reference example/dynamic-training/run.sh):
       --lr 1.6 --lr-mode poly --warmup-epochs 5 --warmup-lr 0.001 --last-gamma --mode symbolic --model resnet50_v1b \\
       --kvstore dist_sync_device --rec-train train.rec --rec-train-idx train.idx --rec-val val.rec --rec-val-idx val.idx
 ``--benchmark 1`` replaces the record files by synthetic data (no dataset on this box).
+``--mode hybrid --kvstore elastic_device`` is the B200-native variant: one process per GPU on one box, the fused P2P
+allreduce+update kernel instead of parameter servers, same host-file driven membership changes.
 """
 import argparse
 import logging
@@ -181,6 +183,10 @@ def train_imperative():
     if opt.mode == 'hybrid':
         net.hybridize()
     trainer = gluon.Trainer(net.collect_params(), 'nag', optimizer_params, kvstore=kv)
+    if kv.type == 'elastic_device':
+        # single-box NVLink path: gradients never leave the GPUs, the scheduler only manages membership; a newcomer
+        # adopts the live weights / momentum before its first forward pass
+        trainer.init_kvstore()
     L = gluon.loss.SoftmaxCrossEntropyLoss()
     metric = mx.metric.Accuracy()
     begin = int(os.environ.get('EPOCH_BEGIN', '0')) if os.environ.get('NEW_WORKER', '0') == '1' else 0
