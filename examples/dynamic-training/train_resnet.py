@@ -157,7 +157,13 @@ def train_symbolic():
     data = mx.sym.var('data')
     if opt.dtype != 'float32':
         data = mx.sym.Cast(data=data, dtype=opt.dtype)
-    out = net(data)
+    fused = opt.model.endswith('_v1b') and opt.model.startswith('resnet') and use_gpu and opt.dtype == 'bfloat16'
+    if fused:
+        # the flagship as ONE graph node running on the B200 kernels (tcgen05 GEMMs, fused BN+ReLU, NHWC inside)
+        out = mx.sym.contrib.FusedResNet(data, num_layers=int(opt.model[len('resnet'):-len('_v1b')]), version='v1b',
+                                         classes=classes, layout='NCHW', name='resnetv1b')
+    else:
+        out = net(data)
     if opt.dtype != 'float32':
         out = mx.sym.Cast(data=out, dtype='float32')
     softmax = mx.sym.SoftmaxOutput(out, name='softmax')

@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from ..ops import functional as K
 from ..base import getenv
 
-__all__ = ["ResNetSpec", "resnet_spec", "init_resnet_params", "resnet_forward", "RESNET_SPECS"]
+__all__ = ["ResNetSpec", "resnet_spec", "resnet_param_spec", "init_resnet_params", "resnet_forward", "RESNET_SPECS"]
 
 RESNET_SPECS = {
     18: ("basic", [2, 2, 2, 2], [64, 64, 128, 256, 512]),
@@ -44,6 +44,42 @@ class ResNetSpec(object):
 
 def resnet_spec(num_layers=50, **kw):
     return ResNetSpec(num_layers, **kw)
+
+
+def resnet_param_spec(spec):
+    """Ordered list of (name, shape, dtype_kind, is_aux) for every parameter / auxiliary state of the fused ResNet
+    (dtype_kind: 'w' = network dtype, 'f' = always fp32).  1x1 convolution weights are 2-D [O, I] (they are GEMM operands),
+    k x k weights are (O, I, kh, kw)."""
+    out = []
+
+    def conv(name, o, i, k):
+        out.append((name, (o, i) if k == 1 else (o, i, k, k), "w", False))
+
+    def bn(name, c):
+        out.extend([(name + "_gamma", (c,), "f", False), (name + "_beta", (c,), "f", False),
+                    (name + "_running_mean", (c,), "f", True), (name + "_running_var", (c,), "f", True)])
+    c0 = spec.channels[0]
+    conv("conv0_weight", c0, spec.in_channels, 3 if spec.thumbnail else 7)
+    bn("bn0", c0)
+    cin = c0
+    for s, (n, cout) in enumerate(zip(spec.layers, spec.channels[1:])):
+        for b in range(n):
+            pre = "stage%d_unit%d_" % (s + 1, b + 1)
+            stride = 2 if (b == 0 and s > 0) else 1
+            if spec.block == "bottleneck":
+                mid = cout // 4
+                conv(pre + "conv1_weight", mid, cin, 1); bn(pre + "bn1", mid)
+                conv(pre + "conv2_weight", mid, mid, 3); bn(pre + "bn2", mid)
+                conv(pre + "conv3_weight", cout, mid, 1); bn(pre + "bn3", cout)
+            else:
+                conv(pre + "conv1_weight", cout, cin, 3); bn(pre + "bn1", cout)
+                conv(pre + "conv2_weight", cout, cout, 3); bn(pre + "bn2", cout)
+            if stride != 1 or cin != cout:
+                conv(pre + "down_weight", cout, cin, 1); bn(pre + "down_bn", cout)
+            cin = cout
+    out.append(("fc_weight", (spec.classes, cin), "w", False))
+    out.append(("fc_bias", (spec.classes,), "f", False))
+    return out
 
 
 def _conv_w(shape_oihw, dtype, device, gen):

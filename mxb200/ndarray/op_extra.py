@@ -970,3 +970,33 @@ def MultiBoxDetection(cls_prob, loc_pred, anchor, clip=True, threshold=0.01, bac
             res[b, :out_rows.shape[0]] = out_rows
         return res.to(cp.dtype)
     return _out(_op(g, cls_prob, loc_pred, anchor), out)
+
+
+# ----------------------------------------------------------------------------- the fused flagship as ONE graph node
+@register(name="_contrib_FusedResNet")
+def FusedResNet(data, num_layers=50, version="v1b", classes=1000, thumbnail=False, in_channels=3, layout="NCHW", eps=1e-5,
+                momentum=0.9, out=None, **params):
+    """ResNet (v1 / v1b) executed by the B200 kernels as a single operator, so that symbolic ``Module.fit`` scripts (the
+    reference's example/dynamic-training/train_resnet.py --mode symbolic) run the same fused path as the Gluon model:
+    tcgen05 GEMMs for the 1x1 convolutions / stem / FC, fused BN(+add)+ReLU, NHWC activations.  Inputs: ``data`` (NCHW like
+    the reference's iterators, or NHWC with layout='NHWC') and every weight / BatchNorm parameter / running statistic by name
+    (models/resnet.py::resnet_param_spec); the symbol layer creates them as ``<node>_<name>`` variables.  Returns logits."""
+    from .. import autograd as _ag
+    from ..models import resnet as R
+    spec = R.ResNetSpec(int(num_layers), classes=int(classes), version=str(version), in_channels=int(in_channels),
+                        thumbnail=thumbnail in (True, 1, "1", "True", "true"))
+    names = [(n, aux) for n, _s, _k, aux in R.resnet_param_spec(spec)]
+    missing = [n for n, _ in names if n not in params]
+    if missing:
+        raise MXNetError("FusedResNet: missing inputs %s" % missing[:4])
+    training = _ag.is_training()
+    arrs = [params[n] for n, _ in names]
+
+    def g(x, *ts):
+        P = {n: t for (n, aux), t in zip(names, ts) if not aux}
+        A = {n: t for (n, aux), t in zip(names, ts) if aux}
+        if str(layout).upper() == "NCHW":
+            x = x.permute(0, 2, 3, 1)
+        x = x.contiguous()
+        return R.resnet_forward(spec, P, A, x, training=training, eps=float(eps), momentum=float(momentum))
+    return _out(_op(g, data, *arrs), out)

@@ -35,6 +35,31 @@ _PARAM_ARGS = {
     "Embedding": [("weight", False)],
     "LeakyReLU": [("gamma", False)],
 }
+
+
+def _fused_resnet_args(attrs):
+    from ..models.resnet import ResNetSpec, resnet_param_spec
+    spec = ResNetSpec(int(attrs.get("num_layers", 50)), classes=int(attrs.get("classes", 1000)), version=str(attrs.get("version", "v1b")),
+                      in_channels=int(attrs.get("in_channels", 3)), thumbnail=_truthy(attrs.get("thumbnail", False)))
+    return spec, resnet_param_spec(spec)
+
+
+# ops whose parameter list depends on their attributes: op -> fn(attrs) -> [(arg_name, is_aux)]
+_DYNAMIC_PARAM_ARGS = {
+    "_contrib_FusedResNet": lambda attrs: [(n, aux) for n, _s, _k, aux in _fused_resnet_args(attrs)[1]],
+}
+
+
+def _param_args(op, attrs):
+    if op in _DYNAMIC_PARAM_ARGS:
+        return _DYNAMIC_PARAM_ARGS[op](attrs)
+    return _PARAM_ARGS.get(op, [])
+
+
+def _has_param_args(op):
+    return op in _PARAM_ARGS or op in _DYNAMIC_PARAM_ARGS
+
+
 _LABEL_OPS = {"SoftmaxOutput": "label", "Softmax": "label", "LinearRegressionOutput": "label",
               "LogisticRegressionOutput": "label", "MAERegressionOutput": "label", "SVMOutput": "label"}
 _MULTI_OUT = {"split": "num_outputs", "SliceChannel": "num_outputs"}
@@ -550,8 +575,8 @@ def _create(op, args, kwargs):
                 if not isinstance(a, Symbol) and a is not None:
                     attrs[pname] = a
     order = []
-    if op in _PARAM_ARGS or op in _LABEL_OPS:
-        spec = [("data", False)] + _PARAM_ARGS.get(op, [])
+    if _has_param_args(op) or op in _LABEL_OPS:
+        spec = [("data", False)] + _param_args(op, attrs)
         if op in _LABEL_OPS:
             spec = spec + [(_LABEL_OPS[op], False)]
         provided = list(inputs)
@@ -613,8 +638,8 @@ def _run_node(node, ins, meta):
         fn = _ndop.get(op)
         if fn is None:
             raise MXNetError("operator %s is not registered" % op)
-        if op in _PARAM_ARGS or op in _LABEL_OPS:
-            spec = ["data"] + [a for a, _ in _PARAM_ARGS.get(op, [])]
+        if _has_param_args(op) or op in _LABEL_OPS:
+            spec = ["data"] + [a for a, _ in _param_args(op, attrs)]
             if op in _LABEL_OPS:
                 spec.append(_LABEL_OPS[op])
             present = []
@@ -666,16 +691,17 @@ def _infer_param_shapes(node, vals, vshape, vdtype):
                 vshape[pn.name] = (size,)
                 vdtype[pn.name] = dt
         return
-    if op not in _PARAM_ARGS and op not in _LABEL_OPS:
+    if not _has_param_args(op) and op not in _LABEL_OPS:
         return
     a = node.attrs
     data = vals.get((id(node.inputs[0][0]), node.inputs[0][1])) if node.inputs else None
     if data is None:
         return
     ds = tuple(data.shape)
-    spec = ["data"] + [x for x, _ in _PARAM_ARGS.get(op, [])]
+    spec = ["data"] + [x for x, _ in _param_args(op, a)]
     if op in _LABEL_OPS:
         spec.append(_LABEL_OPS[op])
+    fused_shapes = {n: (shp, kind) for n, shp, kind, _aux in _fused_resnet_args(a)[1]} if op == "_contrib_FusedResNet" else None
     present = []
     for aname in spec:
         if aname == "bias" and a.get("no_bias", False):
@@ -685,6 +711,8 @@ def _infer_param_shapes(node, vals, vshape, vdtype):
         present.append(aname)
 
     def rule(aname):
+        if fused_shapes is not None:
+            return fused_shapes[aname][0] if aname in fused_shapes else None
         if op == "FullyConnected":
             nh = int(a["num_hidden"])
             inn = int(np.prod(ds[1:])) if a.get("flatten", True) else ds[-1]
@@ -717,7 +745,9 @@ def _infer_param_shapes(node, vals, vshape, vdtype):
             shp = rule(aname)
             if shp is not None:
                 dt = vdtype.get(inp.name, inp.var_attrs.get("__dtype__", "float32"))
-                if aname not in ("label",) and op not in ("BatchNorm",):
+                if fused_shapes is not None:
+                    dt = "float32" if fused_shapes[aname][1] == "f" else dtype_name(data.dtype)
+                elif aname not in ("label",) and op not in ("BatchNorm",):
                     dt = dtype_name(data.dtype) if inp.var_attrs.get("__dtype__") is None else dt
                 vals[(id(inp), idx)] = torch.empty(shp, dtype=torch_dtype(dt), device="meta")
                 vshape[inp.name] = tuple(shp)

@@ -779,3 +779,38 @@ def test_dist_device_sync_with_gpu_workers(tmp_path):
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("OK") == 2
+
+
+def test_module_fit_fused_resnet_symbol_on_gpu():
+    """The fused ResNet as a single graph node: symbolic Module.fit (the reference example's --mode symbolic path) running
+    the tcgen05 / fused-BN kernels in bf16, NCHW input like the reference's iterators."""
+    import numpy as np
+    import mxb200 as mx
+    data = mx.sym.Cast(mx.sym.var("data"), dtype="bfloat16")
+    net = mx.sym.contrib.FusedResNet(data, num_layers=18, classes=10, thumbnail=True, name="rn")
+    net = mx.sym.SoftmaxOutput(mx.sym.Cast(net, dtype="float32"), name="softmax")
+    rs = np.random.RandomState(0)
+    x = rs.rand(64, 3, 32, 32).astype("f")
+    y = rs.randint(0, 10, (64,)).astype("f")
+    it = mx.io.NDArrayIter(x, y, batch_size=32)
+    mod = mx.mod.Module(net, context=[mx.gpu(0)])
+    mod.bind(data_shapes=it.provide_data, label_shapes=it.provide_label)
+    mod.init_params(mx.init.Xavier(rnd_type="gaussian", factor_type="in", magnitude=2))
+    arg, aux = mod.get_params()
+    assert str(arg["rn_stage1_unit1_conv1_weight"].dtype) in ("bfloat16", "torch.bfloat16") or "bfloat16" in str(arg["rn_stage1_unit1_conv1_weight"].dtype)
+    assert "float32" in str(arg["rn_bn0_gamma"].dtype)
+    mod.init_optimizer(kvstore="device", optimizer="nag", optimizer_params={"learning_rate": 0.02, "momentum": 0.9, "multi_precision": True})
+    metric = mx.metric.create("ce")
+    first = last = None
+    for epoch in range(12):
+        it.reset()
+        metric.reset()
+        for batch in it:
+            mod.forward_backward(batch)
+            mod.update()
+            mod.update_metric(metric, batch.label)
+        v = metric.get()[1]
+        first = v if first is None else first
+        last = v
+    assert np.isfinite(last) and last < first
+    assert float(np.abs(mod.get_params()[1]["rn_bn0_running_mean"].asnumpy()).sum()) > 0     # running stats were updated
