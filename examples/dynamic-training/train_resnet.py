@@ -65,7 +65,8 @@ parser.add_argument('--image-size', type=int, default=224)
 parser.add_argument('--num-classes', type=int, default=1000)
 parser.add_argument('--num-training-samples', type=int, default=1281167)
 parser.add_argument('--dynamic-minibatch', type=str, default='constant_global',
-                    help='constant_global (reference behaviour) | linear | sqrt: lr rule applied when the worker count changes')
+                    help='constant_global (reference behaviour: global batch fixed, no lr change) | linear | sqrt: lr rule of the '
+                         'dynamic mini-batch scheduler when the PER-WORKER batch is kept and the global batch follows the worker count')
 opt = parser.parse_args()
 logging.basicConfig(level=logging.INFO)
 logging.info(opt)
@@ -93,7 +94,8 @@ elif opt.lr_mode == 'cosine':
 else:
     raise ValueError('Invalid lr mode')
 if opt.dynamic_minibatch != 'constant_global':
-    lr_scheduler = mx.lr_scheduler.DynamicMiniBatchScheduler(lr_scheduler, base_workers=kv.num_workers, mode=opt.dynamic_minibatch)
+    lr_scheduler = mx.lr_scheduler.DynamicMiniBatchScheduler(lr_scheduler, base_batch=global_batch_size, mode=opt.dynamic_minibatch,
+                                                             smooth_steps=epoch_size // 10, momentum=opt.momentum)
 
 kwargs = {'classes': classes}
 if opt.last_gamma and 'resnet' in opt.model:

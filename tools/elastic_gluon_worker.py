@@ -37,9 +37,6 @@ torch.cuda.set_device(gpu)
 kv = mx.kv.create("elastic_device")
 net = vision.get_resnet("v1b", 18, classes=10, thumbnail=True, ctx=ctx, dtype="bfloat16", layout="NHWC", seed=7 if not is_new else 99)
 net.hybridize()
-sched = mx.lr_scheduler.DynamicMiniBatchScheduler(mx.lr_scheduler.FactorScheduler(step=10 ** 9, base_lr=0.02),
-                                                  base_workers=plan[0], mode="constant_global") \
-    if hasattr(mx.lr_scheduler, "DynamicMiniBatchScheduler") else None
 trainer = gluon.Trainer(net.collect_params(), "nag", {"learning_rate": 0.02, "momentum": 0.9, "wd": 1e-4, "multi_precision": True},
                         kvstore=kv)
 trainer.init_kvstore()            # a newcomer adopts the live weights / momentum before its first forward pass
