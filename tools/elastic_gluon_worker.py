@@ -69,7 +69,9 @@ for epoch in range(begin, len(plan)):
         trainer.step(global_batch)
         losses.append(float(loss.as_torch().detach().float().mean()))
     trainer.check_health()
-    csum = float(sum(p.data().as_torch().detach().float().abs().sum() for p in net.collect_params().values()))
+    # trainable parameters only: BatchNorm running statistics are per-worker state between membership changes
+    csum = float(sum(p.data().as_torch().detach().float().abs().sum() for p in net.collect_params().values()
+                     if p.grad_req != "null"))
     sums = [struct.unpack("<d", b)[0] for b in kv.elastic_group.allgather(struct.pack("<d", csum))]
     log["epochs"].append({"epoch": epoch, "rank": rank, "world": world, "loss_first": losses[0], "loss_last": losses[-1],
                           "weights_identical": max(sums) - min(sums) <= 1e-6 * abs(sums[0]), "checksum": csum})
