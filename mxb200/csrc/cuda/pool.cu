@@ -51,10 +51,13 @@ struct Geo {
   int N, H, W, C, HO, WO, k, s, p;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
+// KS > 0: compile-time window (KS x KS, stride KS-1 ... the ResNet stem uses 3x3 / stride 2): every load of a window is
+// issued before the first comparison (memory-level parallelism), out-of-image taps read as -inf.
+template <typename T, int K, int S>
+__global__ void __launch_bounds__(kThreads, 2)
 maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ idx, Geo g) {
   constexpr int VN = V<T>::N;
+  const int k = K > 0 ? K : g.k, s = S > 0 ? S : g.s;
   const int CV = g.C / VN;
   const int64_t total = (int64_t)g.N * g.HO * g.WO * CV;
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
@@ -67,18 +70,39 @@ maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restri
     int arg[VN];
 #pragma unroll
     for (int j = 0; j < VN; ++j) { best[j] = -INFINITY; arg[j] = 0; }
-    for (int kh = 0; kh < g.k; ++kh) {
-      const int h = ho * g.s - g.p + kh;
-      if (h < 0 || h >= g.H) continue;
-      for (int kw = 0; kw < g.k; ++kw) {
-        const int w = wo * g.s - g.p + kw;
-        if (w < 0 || w >= g.W) continue;
-        const uint4 u = ldg16(x + (((int64_t)n * g.H + h) * g.W + w) * g.C + (int64_t)cv * VN);
-        float v[VN];
-        unpack<T>(u, v);
+    const T* base = x + ((int64_t)n * g.H * g.W) * g.C + (int64_t)cv * VN;
+    if constexpr (K > 0) {
+      uint4 u[K * K];
+      bool ok[K * K];
 #pragma unroll
-        for (int j = 0; j < VN; ++j) {
-          if (v[j] > best[j]) { best[j] = v[j]; arg[j] = kh * g.k + kw; }
+      for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) {
+          const int h = ho * s - g.p + kh, w = wo * s - g.p + kw;
+          ok[kh * K + kw] = (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W;
+          u[kh * K + kw] = ok[kh * K + kw] ? ldg16(base + ((int64_t)h * g.W + w) * g.C) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+      for (int t = 0; t < K * K; ++t) {
+        if (!ok[t]) continue;
+        float v[VN];
+        unpack<T>(u[t], v);
+#pragma unroll
+        for (int j = 0; j < VN; ++j)
+          if (v[j] > best[j]) { best[j] = v[j]; arg[j] = t; }
+      }
+    } else {
+      for (int kh = 0; kh < k; ++kh) {
+        const int h = ho * s - g.p + kh;
+        if (h < 0 || h >= g.H) continue;
+        for (int kw = 0; kw < k; ++kw) {
+          const int w = wo * s - g.p + kw;
+          if (w < 0 || w >= g.W) continue;
+          float v[VN];
+          unpack<T>(ldg16(base + ((int64_t)h * g.W + w) * g.C), v);
+#pragma unroll
+          for (int j = 0; j < VN; ++j)
+            if (v[j] > best[j]) { best[j] = v[j]; arg[j] = kh * k + kw; }
         }
       }
     }
@@ -96,10 +120,12 @@ maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restri
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, int K, int S>
+__global__ void __launch_bounds__(kThreads, 2)
 maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, T* __restrict__ dx, Geo g) {
   constexpr int VN = V<T>::N;
+  constexpr int kMaxWin = K > 0 ? (K + S - 1) / S : 1;     // candidate windows per axis that can cover one input pixel
+  const int k = K > 0 ? K : g.k, s = S > 0 ? S : g.s;
   const int CV = g.C / VN;
   const int64_t total = (int64_t)g.N * g.H * g.W * CV;
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
@@ -112,30 +138,60 @@ maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, T*
 #pragma unroll
     for (int j = 0; j < VN; ++j) acc[j] = 0.f;
     // outputs whose window covers (h, w): ho in [ceil((h+p-k+1)/s), floor((h+p)/s)]
-    const int ho_hi = min(g.HO - 1, (h + g.p) / g.s);
-    const int ho_lo = max(0, (h + g.p - g.k + g.s) / g.s);
-    const int wo_hi = min(g.WO - 1, (w + g.p) / g.s);
-    const int wo_lo = max(0, (w + g.p - g.k + g.s) / g.s);
-    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
-      const int kh = h + g.p - ho * g.s;
-      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-        const int kw = w + g.p - wo * g.s;
-        const int code = kh * g.k + kw;
-        const int64_t o = (((int64_t)n * g.HO + ho) * g.WO + wo) * CV + cv;
-        float v[VN];
-        unpack<T>(ldg16(dy + o * VN), v);
-        if (VN == 8) {
-          const uint2 a = *reinterpret_cast<const uint2*>(idx + o * 8);
+    const int ho_hi = min(g.HO - 1, (h + g.p) / s);
+    const int ho_lo = max(0, (h + g.p - k + s) / s);
+    const int wo_hi = min(g.WO - 1, (w + g.p) / s);
+    const int wo_lo = max(0, (w + g.p - k + s) / s);
+    auto fold = [&](const uint4& uv, const uint2& a, uint32_t a4, int code) {
+      float v[VN];
+      unpack<T>(uv, v);
+      if (VN == 8) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (((a.x >> (8 * j)) & 0xff) == (uint32_t)code) acc[j] += v[j];
-            if (((a.y >> (8 * j)) & 0xff) == (uint32_t)code) acc[4 + j] += v[4 + j];
+        for (int j = 0; j < 4; ++j) {
+          if (((a.x >> (8 * j)) & 0xff) == (uint32_t)code) acc[j] += v[j];
+          if (((a.y >> (8 * j)) & 0xff) == (uint32_t)code) acc[4 + j] += v[4 + j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (((a4 >> (8 * j)) & 0xff) == (uint32_t)code) acc[j] += v[j];
+      }
+    };
+    if constexpr (K > 0) {
+      uint4 uv[kMaxWin * kMaxWin];
+      uint2 ua[kMaxWin * kMaxWin];
+      uint32_t u4[kMaxWin * kMaxWin];
+      int code[kMaxWin * kMaxWin];
+#pragma unroll
+      for (int a = 0; a < kMaxWin; ++a)
+#pragma unroll
+        for (int b = 0; b < kMaxWin; ++b) {
+          const int ho = ho_lo + a, wo = wo_lo + b, t = a * kMaxWin + b;
+          const bool ok = ho <= ho_hi && wo <= wo_hi;
+          code[t] = ok ? (h + g.p - ho * s) * k + (w + g.p - wo * s) : -1;
+          const int64_t o = (((int64_t)n * g.HO + (ok ? ho : 0)) * g.WO + (ok ? wo : 0)) * CV + cv;
+          uv[t] = ok ? ldg16(dy + o * VN) : make_uint4(0, 0, 0, 0);
+          ua[t] = make_uint2(0, 0);
+          u4[t] = 0;
+          if (ok) {
+            if (VN == 8) ua[t] = *reinterpret_cast<const uint2*>(idx + o * 8);
+            else u4[t] = *reinterpret_cast<const uint32_t*>(idx + o * 4);
           }
-        } else {
-          const uint32_t a = *reinterpret_cast<const uint32_t*>(idx + o * 4);
+        }
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (((a >> (8 * j)) & 0xff) == (uint32_t)code) acc[j] += v[j];
+      for (int t = 0; t < kMaxWin * kMaxWin; ++t)
+        if (code[t] >= 0) fold(uv[t], ua[t], u4[t], code[t]);
+    } else {
+      for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+        const int kh = h + g.p - ho * s;
+        for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+          const int kw = w + g.p - wo * s;
+          const int64_t o = (((int64_t)n * g.HO + ho) * g.WO + wo) * CV + cv;
+          uint2 a = make_uint2(0, 0);
+          uint32_t a4 = 0;
+          if (VN == 8) a = *reinterpret_cast<const uint2*>(idx + o * 8);
+          else a4 = *reinterpret_cast<const uint32_t*>(idx + o * 4);
+          fold(ldg16(dy + o * VN), a, a4, kh * k + kw);
         }
       }
     }
@@ -158,13 +214,19 @@ MXB_API int MXBMaxPoolNhwcFwd(const void* x, void* y, void* idx, int dt, int N, 
   if (dt == kBF16) {
     MXB_CHECK(C % 8 == 0, "maxpool: C must be a multiple of 8 for bf16");
     const int64_t total = (int64_t)N * HO * WO * (C / 8);
-    maxpool_fwd_kernel<__nv_bfloat16><<<grid_for(total, kThreads, 1, 16), kThreads, 0, st>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (uint8_t*)idx, g);
+    if (k == 3 && s == 2)
+      maxpool_fwd_kernel<__nv_bfloat16, 3, 2><<<grid_for(total, kThreads, 1, 16), kThreads, 0, st>>>(
+          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (uint8_t*)idx, g);
+    else
+      maxpool_fwd_kernel<__nv_bfloat16, 0, 0><<<grid_for(total, kThreads, 1, 16), kThreads, 0, st>>>(
+          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (uint8_t*)idx, g);
   } else if (dt == kF32) {
     MXB_CHECK(C % 4 == 0, "maxpool: C must be a multiple of 4 for fp32");
     const int64_t total = (int64_t)N * HO * WO * (C / 4);
-    maxpool_fwd_kernel<float><<<grid_for(total, kThreads, 1, 16), kThreads, 0, st>>>((const float*)x, (float*)y,
-                                                                                     (uint8_t*)idx, g);
+    if (k == 3 && s == 2)
+      maxpool_fwd_kernel<float, 3, 2><<<grid_for(total, kThreads, 1, 16), kThreads, 0, st>>>((const float*)x, (float*)y, (uint8_t*)idx, g);
+    else
+      maxpool_fwd_kernel<float, 0, 0><<<grid_for(total, kThreads, 1, 16), kThreads, 0, st>>>((const float*)x, (float*)y, (uint8_t*)idx, g);
   } else {
     throw std::runtime_error("maxpool: dtype must be bf16 or fp32");
   }
@@ -179,12 +241,18 @@ MXB_API int MXBMaxPoolNhwcBwd(const void* dy, const void* idx, void* dx, int dt,
   Geo g{N, H, W, C, HO, WO, k, s, p};
   if (dt == kBF16) {
     const int64_t total = (int64_t)N * H * W * (C / 8);
-    maxpool_bwd_kernel<__nv_bfloat16><<<grid_for(total, kThreads, 1, 16), kThreads, 0, st>>>(
-        (const __nv_bfloat16*)dy, (const uint8_t*)idx, (__nv_bfloat16*)dx, g);
+    if (k == 3 && s == 2)
+      maxpool_bwd_kernel<__nv_bfloat16, 3, 2><<<grid_for(total, kThreads, 1, 16), kThreads, 0, st>>>(
+          (const __nv_bfloat16*)dy, (const uint8_t*)idx, (__nv_bfloat16*)dx, g);
+    else
+      maxpool_bwd_kernel<__nv_bfloat16, 0, 0><<<grid_for(total, kThreads, 1, 16), kThreads, 0, st>>>(
+          (const __nv_bfloat16*)dy, (const uint8_t*)idx, (__nv_bfloat16*)dx, g);
   } else if (dt == kF32) {
     const int64_t total = (int64_t)N * H * W * (C / 4);
-    maxpool_bwd_kernel<float><<<grid_for(total, kThreads, 1, 16), kThreads, 0, st>>>((const float*)dy,
-                                                                                     (const uint8_t*)idx, (float*)dx, g);
+    if (k == 3 && s == 2)
+      maxpool_bwd_kernel<float, 3, 2><<<grid_for(total, kThreads, 1, 16), kThreads, 0, st>>>((const float*)dy, (const uint8_t*)idx, (float*)dx, g);
+    else
+      maxpool_bwd_kernel<float, 0, 0><<<grid_for(total, kThreads, 1, 16), kThreads, 0, st>>>((const float*)dy, (const uint8_t*)idx, (float*)dx, g);
   } else {
     throw std::runtime_error("maxpool: dtype must be bf16 or fp32");
   }

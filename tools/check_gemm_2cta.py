@@ -58,7 +58,11 @@ for (M, N, Kd) in [(8192, 8192, 8192), (50176, 1024, 256), (50176, 256, 1024), (
     t_f = timeit(lambda: K.gemm_nt(x, w))
     t_d = timeit(lambda: K.gemm_nn(dy, w))
     t_c = timeit(lambda: torch.matmul(x, w.t()))
+    t_w = timeit(lambda: K.gemm_tn(dy, x, out_dtype=torch.float32)) if M <= 250000 else float("nan")
+    if M <= 60000:
+        e_w = rel(K.gemm_tn(dy, x, out_dtype=torch.float32), dy.float().t() @ x.float())
+        out["errors"]["wgrad_%dx%dx%d" % (M, N, Kd)] = [e_w]
     fl = 2.0 * M * N * Kd
-    out["ms"]["%dx%dx%d" % (M, N, Kd)] = {"fwd": t_f, "dgrad": t_d, "cublas_fwd": t_c, "fwd_tflops": fl / t_f / 1e9, "cublas_tflops": fl / t_c / 1e9}
+    out["ms"]["%dx%dx%d" % (M, N, Kd)] = {"fwd": t_f, "dgrad": t_d, "cublas_fwd": t_c, "wgrad": t_w, "fwd_tflops": fl / t_f / 1e9, "cublas_tflops": fl / t_c / 1e9}
     del x, w, dy
 print(json.dumps(out))
