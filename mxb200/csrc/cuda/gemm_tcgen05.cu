@@ -615,7 +615,7 @@ MXB_API int MXBGemmBf16(int mode, const void* A, const void* B, void* D, int M, 
   // CTA pairs (cta_group::2): 256 x 256 tiles shared by two SMs; worth it when the problem is compute bound (deep K) and
   // has enough 256-row tiles to fill the 74 clusters.  MXB200_GEMM_2CTA=0/1 forces it off/on.
   static const int two_cta_env = [] { const char* e = getenv("MXB200_GEMM_2CTA"); return e ? atoi(e) : -1; }();
-  static const int two_cta_wgrad = [] { const char* e = getenv("MXB200_GEMM_2CTA_WGRAD"); return e ? atoi(e) : 0; }();
+  static const int two_cta_wgrad = [] { const char* e = getenv("MXB200_GEMM_2CTA_WGRAD"); return e ? atoi(e) : 1; }();
   bool two_cta = false;
   if (bn == 256 && (mode != 2 || two_cta_wgrad == 1)) {
     const int sp2 = (mode == 2 && splits > 1) ? splits : 1;
