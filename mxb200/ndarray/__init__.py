@@ -9,6 +9,7 @@ from .serialization import save, load, load_frombuffer
 from .sparse import RowSparseNDArray, CSRNDArray, BaseSparseNDArray, cast_storage
 from .op import *  # noqa: F401,F403
 from . import op_extra as _op_extra  # noqa: F401  (registers the long tail into _REG)
+from . import op_legacy as _op_legacy  # noqa: F401  (legacy aliases + deformable ops)
 from .op import _REG as _OPS
 
 import functools as _functools

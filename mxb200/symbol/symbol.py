@@ -34,6 +34,8 @@ _PARAM_ARGS = {
     "InstanceNorm": [("gamma", False), ("beta", False)],
     "Embedding": [("weight", False)],
     "LeakyReLU": [("gamma", False)],
+    "_contrib_DeformableConvolution": [("offset", False), ("weight", False), ("bias", False)],
+    "IdentityAttachKLSparseReg": [("moving_avg", True)],
 }
 
 
@@ -721,6 +723,14 @@ def _infer_param_shapes(node, vals, vshape, vdtype):
             k = tuple(a["kernel"]) if not isinstance(a["kernel"], int) else (a["kernel"],) * (len(ds) - 2)
             nf, g = int(a["num_filter"]), int(a.get("num_group", 1))
             return {"weight": (nf, ds[1] // g) + k, "bias": (nf,)}[aname]
+        if op == "_contrib_DeformableConvolution":
+            if aname == "offset":
+                return None
+            k = tuple(a["kernel"]) if not isinstance(a["kernel"], int) else (a["kernel"],) * (len(ds) - 2)
+            nf, g = int(a["num_filter"]), int(a.get("num_group", 1))
+            return {"weight": (nf, ds[1] // g) + k, "bias": (nf,)}[aname]
+        if op == "IdentityAttachKLSparseReg":
+            return (int(np.prod(ds[1:])),)
         if op == "Deconvolution":
             k = tuple(a["kernel"]) if not isinstance(a["kernel"], int) else (a["kernel"],) * (len(ds) - 2)
             nf, g = int(a["num_filter"]), int(a.get("num_group", 1))
