@@ -656,7 +656,8 @@ def Activation(data, act_type="relu", out=None):
     from ..ops.layernorm import bias_act
 
     def _native(t):   # one fused elementwise kernel forward, one backward (csrc/cuda/layernorm.cu)
-        return bias_act(t, None, act_type)
+        from ..ops.functional import act_any_layout
+        return act_any_layout(t, lambda v: bias_act(v, None, act_type))
     if act_type == "softsign":
         return _out(_op(F.softsign, data), out)
     if act_type not in ("relu", "sigmoid", "tanh", "softrelu", "gelu"):
@@ -697,6 +698,11 @@ def Convolution(data, weight, bias=None, kernel=None, stride=None, dilate=None, 
     fn = {1: F.conv1d, 2: F.conv2d, 3: F.conv3d}[nd_]
 
     def g(x, w, b=None):
+        if nd_ == 2 and x.is_cuda:
+            from ..ops import functional as K
+            y = K.conv2d_nchw(x, w, b, stride_, pad_, dil_, num_group)     # tcgen05 GEMM for 1x1, channels_last cuDNN else
+            if y is not None:
+                return y
         return fn(x, w, b, stride_, pad_, dil_, num_group)
     if bias is None or no_bias:
         return _out(_op(g, data, weight), out)
@@ -754,6 +760,11 @@ def BatchNorm(data, gamma, beta, moving_mean, moving_var, eps=1e-3, momentum=0.9
 
     def g(x, gm, bt):
         mm, mv = moving_mean._t, moving_var._t
+        if x.is_cuda and x.dim() == 4 and axis == 1 and not output_mean_var:
+            from ..ops import functional as K
+            y = K.batch_norm_nchw(x, gm, bt, mm, mv, eps, momentum, training, fix_gamma)   # fused statistics + apply kernels
+            if y is not None:
+                return y
         gm_ = torch.ones_like(gm) if fix_gamma else gm
         if axis != 1 and axis % x.dim() != 1:
             xt = x.movedim(axis, 1)

@@ -605,3 +605,63 @@ def softmax_output_grad(p, label, grad_scale=1.0, ignore_label=-1.0, use_ignore=
 def layer_norm(x, gamma, beta, eps=1e-5):
     from . import layernorm
     return layernorm.layer_norm(x, gamma, beta, eps)
+
+
+# --------------------------------------------------------------------------- NCHW-logical operators on the NHWC kernels
+# The generic operators (mx.nd.Convolution / BatchNorm / Activation, and therefore Gluon nn layers and symbolic graphs
+# written for the reference's NCHW layout) keep their logical layout; on a B200 the tensors are carried in torch's
+# channels_last memory format, whose ``permute(0, 2, 3, 1)`` is a free contiguous NHWC view -- exactly what the kernels
+# above consume.  Every helper returns None when the fast path does not apply (the caller then runs the library op).
+def _fastpath():
+    return N.have_cuda_kernels() and getenv("MXB200_OP_FASTPATH", True)
+
+
+def nhwc_view(x):
+    """Contiguous NHWC view of a 4-D NCHW-logical tensor (a transposing copy only if it was not channels_last)."""
+    v = x.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+def conv2d_nchw(x, w, b, stride, pad, dilate, groups):
+    """2-D convolution of a logical-NCHW bf16 CUDA tensor: 1x1 kernels run as tcgen05 GEMMs over pixels (bias in the
+    epilogue), everything else goes to cuDNN in channels_last so the layout chain is never broken."""
+    if not (x.is_cuda and x.dim() == 4 and x.dtype is torch.bfloat16 and w.dtype is torch.bfloat16 and _fastpath()):
+        return None
+    o, c, kh, kw = w.shape
+    if (kh, kw) == (1, 1) and tuple(pad) == (0, 0) and tuple(dilate) == (1, 1) and groups == 1 \
+            and stride[0] == stride[1] and c % 8 == 0 and o % 8 == 0:
+        xn = nhwc_view(x)
+        if stride[0] != 1:
+            xn = subsample_nhwc(xn, stride[0])
+        n, h, ww, _ = xn.shape
+        y = linear(xn.reshape(n * h * ww, c), w.reshape(o, c), b)
+        return y.reshape(n, h, ww, o).permute(0, 3, 1, 2)
+    xc = x.contiguous(memory_format=torch.channels_last)
+    return F.conv2d(xc, w, b.to(x.dtype) if b is not None else None, stride, pad, dilate, groups)
+
+
+def batch_norm_nchw(x, gamma, beta, running_mean, running_var, eps, momentum, training, fix_gamma, residual=None,
+                    relu=False):
+    """BatchNorm over axis 1 of a logical-NCHW CUDA tensor (+ optional residual add and ReLU) on the fused kernels."""
+    if not (x.is_cuda and x.dim() == 4 and _fastpath() and x.dtype in (torch.bfloat16, torch.float32)
+            and running_mean.dtype is torch.float32 and running_var.dtype is torch.float32):
+        return None
+    xn = nhwc_view(x)
+    if not _bn_shape_ok(xn.reshape(-1, xn.shape[-1])):
+        return None
+    rn = None
+    if residual is not None:
+        if residual.shape != x.shape or residual.dtype != x.dtype:
+            return None
+        rn = nhwc_view(residual)
+    y = bn_act(xn, gamma, beta, running_mean, running_var, residual=rn, relu=relu, eps=eps, momentum=momentum,
+               training=training, fix_gamma=fix_gamma)
+    return y.permute(0, 3, 1, 2)
+
+
+def act_any_layout(x, fn):
+    """Apply an elementwise kernel wrapper ``fn`` (which wants a contiguous last dim) to ``x`` without breaking a
+    channels_last layout chain."""
+    if x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last):
+        return fn(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+    return fn(x)

@@ -21,6 +21,7 @@ from .. import ndarray as nd
 from ..ndarray import NDArray
 from ..ndarray import op as _ndop
 from .. import autograd
+from ..base import getenv
 
 __all__ = ["Symbol", "var", "Variable", "Group", "load", "load_json", "zeros", "ones"]
 
@@ -376,21 +377,81 @@ class Symbol(object):
         the map runs on that context; inputs coming from another device are copied there first (the reference inserts
         _CrossDeviceCopy nodes for this: graph_executor.cc:1349-1353, nnvm place_device.cc)."""
         vals = {}
-        for node in self._topo():
-            if node.op is None:
-                if node.name not in feed:
-                    raise MXNetError("eval: missing input %s" % node.name)
-                vals[(id(node), 0)] = feed[node.name]
-                continue
+        topo = self._topo()
+        deferred, tails = self._fusion_plan(topo) if (not group2ctx and getenv("MXB200_GRAPH_FUSION", True)) else ({}, {})
+
+        def run(node):
             ins = [vals[(id(inp), idx)] for inp, idx in node.inputs]
             if group2ctx:
                 tgt = group2ctx.get(node.var_attrs.get("__ctx_group__"))
                 if tgt is not None:
                     ins = [x.as_in_context(tgt) if hasattr(x, "as_in_context") and x.context != tgt else x for x in ins]
-            outs = _run_node(node, ins, meta=False)
-            for i, o in enumerate(outs):
+            for i, o in enumerate(_run_node(node, ins, meta=False)):
                 vals[(id(node), i)] = o
+        for node in topo:
+            if node.op is None:
+                if node.name not in feed:
+                    raise MXNetError("eval: missing input %s" % node.name)
+                vals[(id(node), 0)] = feed[node.name]
+                continue
+            if id(node) in deferred:
+                continue                      # runs (fused or not) when its group's last node is reached
+            group = tails.get(id(node))
+            if group is not None:
+                bn, add, other = group
+                fused = _run_fused_bn([vals[(id(inp), idx)] for inp, idx in bn.inputs], bn.attrs,
+                                      vals[(id(other[0]), other[1])] if other is not None else None)
+                if fused is not None:
+                    vals[(id(node), 0)] = fused
+                    continue
+                run(bn)                       # conditions not met at run time (CPU, dtype, width): op by op
+                if add is not None:
+                    run(add)
+            run(node)
         return [vals[(id(n), i)] for n, i in self._outputs]
+
+    def _fusion_plan(self, topo):
+        """Pattern pass over the graph (the reference has none; cuDNN has no fused BN+add+ReLU in that era):
+            BatchNorm -> Activation(relu)                       => one statistics kernel + one fused apply kernel
+            BatchNorm -> (broadcast|elemwise)_add -> relu        => same, with the residual read inside the apply kernel
+        A group is formed only when the intermediate values have no other consumer and are not graph outputs.
+        Returns (deferred node ids, {id(last node): (bn_node, add_node | None, (other_node, idx) | None)})."""
+        cached = getattr(self, "_fusion_cache", None)
+        if cached is not None and cached[0] == len(topo):
+            return cached[1], cached[2]
+        users = {}
+        for n in topo:
+            for inp, idx in n.inputs:
+                users.setdefault((id(inp), idx), []).append(n)
+        for n, i in self._outputs:
+            users.setdefault((id(n), i), []).append(None)
+        deferred, tails = {}, {}
+        adds = ("broadcast_add", "elemwise_add", "_Plus", "_plus", "_add", "broadcast_plus")
+
+        def only_user(n):
+            u = users.get((id(n), 0), [])
+            return u[0] if len(u) == 1 and u[0] is not None else None
+
+        def is_relu(n):
+            return n is not None and n.op == "Activation" and str(n.attrs.get("act_type", "relu")) == "relu"
+        for n in topo:
+            if n.op != "BatchNorm" or _truthy(n.attrs.get("output_mean_var", False)) or int(n.attrs.get("axis", 1)) != 1:
+                continue
+            if any(len(users.get((id(n), i), [])) for i in (1, 2)):
+                continue
+            u = only_user(n)
+            if is_relu(u):
+                deferred[id(n)] = True
+                tails[id(u)] = (n, None, None)
+            elif u is not None and u.op in adds and len(u.inputs) == 2 and is_relu(only_user(u)):
+                other = [x for x in u.inputs if not (x[0] is n and x[1] == 0)]
+                if len(other) != 1 or (other[0][0].op == "BatchNorm" and id(other[0][0]) in deferred):
+                    continue
+                deferred[id(n)] = True
+                deferred[id(u)] = True
+                tails[id(only_user(u))] = (n, u, other[0])
+        self._fusion_cache = (len(topo), deferred, tails)
+        return deferred, tails
 
     def eval(self, ctx=None, **kwargs):
         return self.eval_nd(kwargs)
@@ -619,6 +680,32 @@ _SCALAR_OPS = {
     "_greater_scalar": lambda x, s, rev: x > s, "_lesser_scalar": lambda x, s, rev: x < s,
     "_equal_scalar": lambda x, s, rev: x == s,
 }
+
+
+def _run_fused_bn(ins, attrs, other):
+    """BatchNorm(+residual)+ReLU group on the fused kernels, or None when they do not apply to these tensors."""
+    data, gamma, beta, mm, mv = ins
+    x = data._t
+    if not (x.is_cuda and x.dim() == 4):
+        return None
+    from ..ops import functional as K
+    from ..ndarray.ndarray import _op
+    training = autograd.is_training() and not _truthy(attrs.get("use_global_stats", False))
+    eps, mom = float(attrs.get("eps", 1e-3)), float(attrs.get("momentum", 0.9))
+    fix_gamma = _truthy(attrs.get("fix_gamma", True))
+
+    class _NoFuse(Exception):
+        pass
+
+    def g(xt, gm, bt, *r):
+        y = K.batch_norm_nchw(xt, gm, bt, mm._t, mv._t, eps, mom, training, fix_gamma, residual=r[0] if r else None, relu=True)
+        if y is None:
+            raise _NoFuse()
+        return y
+    try:
+        return _op(g, data, gamma, beta, *([other] if other is not None else []))
+    except _NoFuse:
+        return None
 
 
 def _run_node(node, ins, meta):

@@ -814,3 +814,92 @@ def test_module_fit_fused_resnet_symbol_on_gpu():
         last = v
     assert np.isfinite(last) and last < first
     assert float(np.abs(mod.get_params()[1]["rn_bn0_running_mean"].asnumpy()).sum()) > 0     # running stats were updated
+
+
+# ----------------------------------------------------------------------------- NCHW operators on the NHWC kernels
+def test_nd_convolution_1x1_and_batchnorm_fast_paths_nchw():
+    """mx.nd.Convolution (1x1, bias, stride 2) and mx.nd.BatchNorm on a logical-NCHW bf16 tensor run on the tcgen05 GEMM /
+    fused BN kernels; values and gradients are compared with an fp32 torch reference."""
+    import mxb200 as mx
+    from mxb200 import autograd
+    from mxb200 import ops as mxops
+    import torch.nn.functional as F
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(4, 64, 14, 14, device=_dev(), generator=g)
+    w = torch.randn(128, 64, 1, 1, device=_dev(), generator=g) * 0.1
+    b = torch.randn(128, device=_dev(), generator=g)
+    gm = torch.rand(128, device=_dev(), generator=g) + 0.5
+    bt = torch.randn(128, device=_dev(), generator=g)
+    ctx = mx.gpu(0)
+    X, W, B = (mx.nd.from_torch(t.bfloat16(), ctx) for t in (x, w, b))
+    G, Bt = mx.nd.from_torch(gm.clone(), ctx), mx.nd.from_torch(bt.clone(), ctx)
+    mm, mv = mx.nd.zeros((128,), ctx=ctx), mx.nd.ones((128,), ctx=ctx)
+    for a in (X, W, B, G, Bt):
+        a.attach_grad()
+    l0 = mxops.launch_count()
+    with autograd.record():
+        y = mx.nd.Convolution(X, W, B, kernel=(1, 1), stride=(2, 2), num_filter=128)
+        z = mx.nd.BatchNorm(y, G, Bt, mm, mv, fix_gamma=False, eps=1e-5, momentum=0.9)
+        a = mx.nd.Activation(z, act_type="relu")
+        loss = (a * a).sum()
+    loss.backward()
+    assert mxops.launch_count() - l0 >= 6            # GEMM + BN + activation kernels really ran
+    assert a.shape == (4, 128, 7, 7)
+    xr, wr, br = x.bfloat16().float().requires_grad_(), w.bfloat16().float().requires_grad_(), b.bfloat16().float().requires_grad_()
+    gr, btr = gm.clone().requires_grad_(), bt.clone().requires_grad_()
+    yr = F.conv2d(xr, wr, br, 2)
+    zr = F.batch_norm(yr, None, None, gr, btr, True, 0.1, 1e-5)
+    ar = torch.relu(zr)
+    (ar * ar).sum().backward()
+    assert _rel_err(a._t, ar) < 3e-2
+    assert _rel_err(X.grad._t, xr.grad) < 6e-2
+    assert _rel_err(W.grad._t, wr.grad) < 6e-2
+    assert _rel_err(G.grad._t, gr.grad) < 6e-2
+    assert _rel_err(Bt.grad._t, btr.grad) < 6e-2
+    # running statistics follow the reference convention (biased variance)
+    assert _rel_err(mm._t, 0.1 * yr.detach().mean((0, 2, 3))) < 3e-2
+
+
+def test_symbol_graph_fusion_bn_add_relu_matches_op_by_op(monkeypatch):
+    """A symbolic bottleneck (NCHW, bf16): BatchNorm->ReLU and BatchNorm->add->ReLU groups executed by the fused kernels
+    give the same outputs / gradients as the op-by-op execution of the same graph."""
+    import numpy as np
+    import mxb200 as mx
+
+    def block(data, name, nf, down):
+        c1 = mx.sym.Convolution(data, kernel=(1, 1), num_filter=nf // 4, no_bias=True, name=name + "_c1")
+        a1 = mx.sym.Activation(mx.sym.BatchNorm(c1, fix_gamma=False, eps=2e-5, name=name + "_bn1"), act_type="relu")
+        c2 = mx.sym.Convolution(a1, kernel=(3, 3), pad=(1, 1), num_filter=nf // 4, no_bias=True, name=name + "_c2")
+        a2 = mx.sym.Activation(mx.sym.BatchNorm(c2, fix_gamma=False, eps=2e-5, name=name + "_bn2"), act_type="relu")
+        c3 = mx.sym.Convolution(a2, kernel=(1, 1), num_filter=nf, no_bias=True, name=name + "_c3")
+        b3 = mx.sym.BatchNorm(c3, fix_gamma=False, eps=2e-5, name=name + "_bn3")
+        sc = data
+        if down:
+            sc = mx.sym.BatchNorm(mx.sym.Convolution(data, kernel=(1, 1), num_filter=nf, no_bias=True, name=name + "_sc"),
+                                  fix_gamma=False, eps=2e-5, name=name + "_scbn")
+        return mx.sym.Activation(b3 + sc, act_type="relu")
+    net = block(block(mx.sym.var("data"), "u1", 256, True), "u2", 256, False)
+    net = mx.sym.MakeLoss(mx.sym.sum(net * net))
+    deferred, tails = net._fusion_plan(net._topo())
+    assert len(tails) == 6 and len(deferred) == 8
+    rng = np.random.RandomState(0)
+    results = []
+    for fusion in ("1", "0"):
+        monkeypatch.setenv("MXB200_GRAPH_FUSION", fusion)
+        ex = net.simple_bind(mx.gpu(0), data=(8, 64, 14, 14), type_dict={"data": "bfloat16"})
+        rng = np.random.RandomState(0)
+        for k, v in sorted(ex.arg_dict.items()):
+            val = rng.randn(*v.shape).astype("f") * (1.0 if k == "data" else 0.1)
+            if k.endswith("_gamma"):
+                val = np.abs(val) + 1.0
+            v[:] = mx.nd.array(val, ctx=mx.gpu(0)).astype(v.dtype)
+        ex.forward(is_train=True)
+        ex.backward()
+        results.append((ex.outputs[0]._t.float().clone(), {k: g._t.float().clone() for k, g in ex.grad_dict.items() if g is not None},
+                        {k: a._t.float().clone() for k, a in ex.aux_dict.items()}))
+    (o1, g1, a1), (o0, g0, a0) = results
+    assert _rel_err(o1, o0) < 3e-2
+    for k in g0:
+        assert _rel_err(g1[k], g0[k]) < 8e-2, k
+    for k in a0:
+        assert _rel_err(a1[k], a0[k]) < 3e-2, k
