@@ -27,10 +27,12 @@ class BucketingModule(BaseModule):
 
     def _gen(self, key):
         sym, dnames, lnames = self._sym_gen(key)
-        return Module(sym, dnames, lnames, logger=self.logger, context=self._context,
-                      work_load_list=self._work_load_list, fixed_param_names=self._fixed_param_names,
-                      state_names=self._state_names, group2ctxs=self._group2ctxs,
-                      compression_params=self._compression_params)
+        m = Module(sym, dnames, lnames, logger=self.logger, context=self._context,
+                   work_load_list=self._work_load_list, fixed_param_names=self._fixed_param_names,
+                   state_names=self._state_names, group2ctxs=self._group2ctxs,
+                   compression_params=self._compression_params)
+        m._no_fuse = True     # buckets share parameter arrays between executors; keep the per-key update path
+        return m
 
     @property
     def data_names(self):

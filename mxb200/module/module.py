@@ -101,6 +101,7 @@ class Module(BaseModule):
             logging.info('Saved optimizer state to "%s"', state_name)
 
     def _reset_bind(self):
+        self._drop_fused()
         self.binded = False
         self._exec_group = None
         self._data_shapes = None
@@ -175,6 +176,8 @@ class Module(BaseModule):
         self.params_initialized = True
         self._params_dirty = False
         self._exec_group.set_params(self._arg_params, self._aux_params, allow_extra=allow_extra)
+        if getattr(self, "_fused", None) is not None:
+            self._fused.refresh_master()
 
     def set_params(self, arg_params, aux_params, allow_missing=False, force_init=True, allow_extra=False):
         if not allow_missing:
@@ -185,6 +188,8 @@ class Module(BaseModule):
             warnings.warn("Parameters already initialized and force_init=False. set_params call ignored.", stacklevel=2)
             return
         self._exec_group.set_params(arg_params, aux_params, allow_extra=allow_extra)
+        if getattr(self, "_fused", None) is not None:
+            self._fused.refresh_master()
         self._params_dirty = True
         self.params_initialized = True
 
@@ -284,9 +289,93 @@ class Module(BaseModule):
         if not update_on_kvstore:
             self._updater = opt.get_updater(optimizer)
         self.optimizer_initialized = True
+        self._maybe_fuse()
         if self._preload_opt_states is not None:
             self.load_optimizer_states(self._preload_opt_states)
             self._preload_opt_states = None
+
+    # ---------------------------------------------------------------------------------- fused update path
+    def _fusable(self):
+        """One GPU per process, a dense optimizer the fused kernel implements, no parameter server in the loop: the
+        whole ``update()`` (cross-GPU gradient sum over NVLink, rescale / clip / weight decay, optimizer, low-precision
+        weight fan-out, gradient clear) is then ONE kernel instead of the reference's per-key push / pull / update ops
+        (module.py:685-719 -> model.py:_update_params_on_kvstore)."""
+        from ..base import getenv
+        if not getenv("MXB200_FUSED_MODULE", True) or getattr(self, "_no_fuse", False):
+            return False
+        if len(self._context) != 1 or self._context[0].device_type != "gpu" or not torch.cuda.is_available():
+            return False
+        if not self.for_training or self._grad_req != "write" or self._compression_params:
+            return False
+        if type(self._optimizer) not in (opt.SGD, opt.NAG, opt.Adam, opt.LAMB):
+            return False
+        kv = self._kvstore
+        if kv is not None and ("dist" in kv.type or hasattr(kv, "elastic_group")):
+            return False
+        if len(self._exec_group.execs) != 1:
+            return False
+        ex = self._exec_group.execs[0]
+        for n in self._exec_group.param_names:
+            a, g = ex.arg_dict.get(n), ex.grad_dict.get(n)
+            if a is None or g is None or getattr(a, "stype", "default") != "default":
+                return False
+        return bool(self._exec_group.param_names)
+
+    def _maybe_fuse(self):
+        if getattr(self, "_fused", None) is not None or not self._fusable():
+            return
+        from ..parallel.trainer import DeviceTrainer
+        ex = self._exec_group.execs[0]
+        ctx = self._context[0]
+        kv = self._kvstore
+        world = kv.num_workers if kv is not None else 1
+        rank = kv.rank if kv is not None else 0
+        names = list(self._exec_group.param_names)
+        o = self._optimizer
+        named = [(n, ex.arg_dict[n]._t.detach()) for n in names]
+        # per-parameter multipliers exactly as Optimizer._get_lr / _get_wd resolve them (optimizer.py:set_lr_mult / set_wd_mult)
+        lr_mult = {n: float(o.lr_mult.get(n, 1.0)) for n in names}
+        wd_mult = {n: float(o.wd_mult.get(n, 1.0)) for n in names}
+        dt = DeviceTrainer(named, ctx.torch_device, rank=rank, world=world, lr_mult=lr_mult, wd_mult=wd_mult)
+        views = dt.params()
+        for n in names:
+            a = ex.arg_dict[n]
+            if a._grad_hook is not None:          # arena gradients are cleared by the fused kernel itself
+                a._grad_hook.remove()
+                a._grad_hook = None
+            a._t = views[n]
+            ex.grad_dict[n]._t = dt.grad_sinks[n]
+        if world > 1:
+            import torch.distributed as dist
+            for ar in dt.arenas:                    # rank 0's initial weights win (kv.init semantics)
+                dist.broadcast(ar.weights, src=0)
+            for n in self._aux_names:
+                if n in ex.aux_dict:
+                    dist.broadcast(ex.aux_dict[n]._t, src=0)
+        self._fused = dt
+
+    def _drop_fused(self):
+        dt, self._fused = getattr(self, "_fused", None), None
+        if dt is not None:
+            try:
+                dt.close()
+            except Exception:  # noqa: BLE001
+                pass
+
+    def _fused_update(self):
+        o = self._optimizer
+        o.num_update += 1
+        lr = o.lr_scheduler(o.num_update) if o.lr_scheduler is not None else o.lr
+        kind = {opt.SGD: "sgd", opt.NAG: "nag", opt.Adam: "adam", opt.LAMB: "lamb"}[type(o)]
+        kw = {}
+        if kind in ("adam", "lamb"):
+            kw.update(beta1=o.beta1, beta2=o.beta2, eps=o.epsilon)
+        if kind == "lamb":
+            kw.update(bias_correction=o.bias_correction,
+                      lamb_bounds=(-1.0 if o.lower_bound is None else o.lower_bound,
+                                   -1.0 if o.upper_bound is None else o.upper_bound))
+        self._fused.step(kind, lr=lr, wd=o.wd, momentum=getattr(o, "momentum", 0.0), rescale=o.rescale_grad,
+                         clip=o.clip_gradient, multi_precision=o.multi_precision, **kw)
 
     def _pull_from_kvstore(self, kvstore):
         """NEW_WORKER bootstrap (module.py:561-571): register keys without initialising them and pull values."""
@@ -335,6 +424,11 @@ class Module(BaseModule):
         """Apply the optimizer to the gradients of the last forward-backward (module.py:685-719)."""
         assert self.binded and self.params_initialized and self.optimizer_initialized
         self._params_dirty = True
+        if getattr(self, "_fused", None) is not None:
+            self._fused_update()
+            if update_aux_params:
+                self.store_aux_params()
+            return
         if self._update_on_kvstore:
             _update_params_on_kvstore(self._exec_group.param_arrays, self._exec_group.grad_arrays, self._kvstore,
                                       self._exec_group.param_names)
@@ -381,6 +475,18 @@ class Module(BaseModule):
 
     def save_optimizer_states(self, fname):
         assert self.optimizer_initialized
+        if getattr(self, "_fused", None) is not None:
+            import pickle
+            dt = self._fused
+            if dt.world > 1:
+                import torch.distributed as dist
+                dt.gather_state(dist.barrier)            # un-shard the ZeRO-1 slices first
+            st = dt.export_state()
+            blob = {"num_update": self._optimizer.num_update,
+                    "params": {n: {k: v.cpu() for k, v in d.items() if k != "weight"} for n, d in st["params"].items()}}
+            with open(fname, "wb") as fout:
+                pickle.dump({"mxb200_fused_states": blob}, fout)
+            return
         if self._update_on_kvstore:
             self._kvstore.save_optimizer_states(fname)
         else:
@@ -389,6 +495,22 @@ class Module(BaseModule):
 
     def load_optimizer_states(self, fname):
         assert self.optimizer_initialized
+        if getattr(self, "_fused", None) is not None:
+            import pickle
+            with open(fname, "rb") as f:
+                blob = pickle.load(f)
+            if not (isinstance(blob, dict) and "mxb200_fused_states" in blob):
+                raise ValueError("%s was not written by the fused update path; set MXB200_FUSED_MODULE=0 to load it" % fname)
+            blob = blob["mxb200_fused_states"]
+            dt = self._fused
+            dev = dt.device
+            cur = dt.export_state()["params"]
+            state = {"num_update": blob["num_update"],
+                     "params": {n: dict({"weight": cur[n]["weight"]}, **{k: v.to(dev) for k, v in d.items()})
+                                for n, d in blob["params"].items() if n in cur}}
+            dt.import_state(state)
+            self._optimizer.num_update = int(blob["num_update"])
+            return
         if self._update_on_kvstore:
             self._kvstore.load_optimizer_states(fname)
         else:

@@ -65,6 +65,12 @@ class DeviceTrainer(object):
         """name -> leaf tensor view into the arena (use these in the model)."""
         return self.param_views
 
+    def refresh_master(self):
+        """The low-precision weights were overwritten from outside (set_params / load): drop the fp32 master copies so
+        the next step re-derives them from the weights instead of resurrecting the old values."""
+        for ar in self.arenas:
+            ar.state.pop("w32", None)
+
     def zero_grad(self):
         for ar in self.arenas:
             ar.grads.zero_()
