@@ -56,6 +56,11 @@ class SymmetricArena(object):
         (wl, self.w_ptrs), (gl, self.g_ptrs) = bufs["weights"], bufs["grads"]
         self.weights = wl.tensor(wdtype, n)
         self.grads = gl.tensor(gdtype, n)
+        with torch.no_grad():
+            # raw cudaMalloc memory (possibly recycled from a closed trainer): the kernel reads whole chunks, including the
+            # alignment gaps, and a trainer built before the first backward pass must start from zero gradients
+            self.weights.zero_()
+            self.grads.zero_()
         self.chunk_tid = torch.from_numpy(self.layout.chunk_tid).to(self.device)
         self.lr_mult = torch.ones(len(names), dtype=torch.float32, device=self.device)
         self.wd_mult = torch.ones(len(names), dtype=torch.float32, device=self.device)
