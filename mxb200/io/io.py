@@ -370,6 +370,14 @@ class SyntheticDataIter(DataIter):
         data = np.random.uniform(-1, 1, data_shape)
         self.data = array(data.astype("float32"), ctx=ctx, dtype=dtype)
         self.label = array(label.astype("float32"), ctx=ctx, dtype=label_dtype)
+        try:
+            import torch
+            if torch.cuda.is_available():   # the reference allocates the batch in cpu_pinned memory (common/data.py:113-118)
+                for a in (self.data, self.label):
+                    if not a._t.is_cuda:
+                        a._t = a._t.pin_memory()
+        except Exception:  # noqa: BLE001
+            pass
         self.provide_data = [DataDesc(data_name, tuple(data_shape), dtype)]
         self.provide_label = [DataDesc(label_name, (self.batch_size,), label_dtype)]
 

@@ -741,6 +741,13 @@ def Pooling(data, kernel=None, pool_type="max", global_pool=False, stride=None, 
         s = _tup(stride, nd_) or (1,) * nd_
         p = _tup(pad, nd_) or (0,) * nd_
         ceil_mode = pooling_convention == "full"
+        if (pool_type == "max" and nd_ == 2 and x.is_cuda and not ceil_mode and k[0] == k[1] and k[0] in (2, 3)
+                and s[0] == s[1] and p[0] == p[1] and p[0] < k[0] and x.dim() == 4 and not x.is_contiguous()
+                and x.is_contiguous(memory_format=torch.channels_last)):
+            from ..ops import functional as K
+            if K._fastpath() and x.shape[1] % (16 // x.element_size()) == 0 and x.dtype in (torch.bfloat16, torch.float32):
+                # layout chain already NHWC: window-index max pooling kernel (csrc/cuda/pool.cu), 1-byte argmax per output
+                return K.max_pool_nhwc(x.permute(0, 2, 3, 1), k[0], s[0], p[0]).permute(0, 3, 1, 2)
         if pool_type == "max":
             return {1: F.max_pool1d, 2: F.max_pool2d, 3: F.max_pool3d}[nd_](x, k, s, p, ceil_mode=ceil_mode)
         fn = {1: F.avg_pool1d, 2: F.avg_pool2d, 3: F.avg_pool3d}[nd_]

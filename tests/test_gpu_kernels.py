@@ -946,3 +946,26 @@ def test_module_fused_update_matches_per_key_update(monkeypatch, tmp_path, optim
     for k in init:
         assert np.allclose(out["1"][k], out["0"][k], rtol=2e-3, atol=2e-4), k
         assert not np.allclose(out["1"][k], init[k])
+
+
+@pytest.mark.parametrize("k,s,p", [(3, 2, 1), (2, 2, 0), (3, 1, 1), (3, 2, 0)])
+def test_nd_pooling_max_fast_path_channels_last(k, s, p):
+    """mx.nd.Pooling(max) on a channels_last tensor uses the NHWC window-index kernel; forward and backward equal torch's."""
+    import mxb200 as mx
+    from mxb200 import autograd
+    from mxb200 import ops as mxops
+    x = torch.randn(3, 32, 15, 17, device=_dev()).bfloat16().contiguous(memory_format=torch.channels_last)
+    X = mx.nd.from_torch(x.clone(), mx.gpu(0))
+    X.attach_grad()
+    l0 = mxops.launch_count()
+    with autograd.record():
+        y = mx.nd.Pooling(X, kernel=(k, k), stride=(s, s), pad=(p, p), pool_type="max")
+        loss = (y * y).sum()
+    loss.backward()
+    assert mxops.launch_count() - l0 >= 2
+    xr = x.float().requires_grad_()
+    yr = torch.nn.functional.max_pool2d(xr, k, s, p)
+    (yr * yr).sum().backward()
+    assert y.shape == tuple(yr.shape)
+    assert torch.equal(y._t.float(), yr.detach())
+    assert _rel_err(X.grad._t, xr.grad) < 1e-2
