@@ -120,7 +120,11 @@ class NDArray(object):
         t = self._t.detach()
         if t.dtype is torch.bfloat16:
             t = t.float()
-        return t.cpu().numpy()
+        c = t.cpu()
+        a = c.numpy()
+        # always a private copy, like the reference (ndarray.py asnumpy -> MXNDArraySyncCopyToCPU): a CPU tensor's
+        # numpy() aliases its storage and would change under the caller at the next in-place update
+        return a.copy() if c.data_ptr() == self._t.data_ptr() else a
 
     def asscalar(self):
         if self.size != 1:

@@ -143,3 +143,11 @@ def test_op_namespace():
     assert mx.nd.Convolution(img, k, kernel=(3, 3), pad=(1, 1), num_filter=4, no_bias=True).shape == (2, 4, 8, 8)
     assert mx.nd.Pooling(img, kernel=(2, 2), stride=(2, 2), pool_type="max").shape == (2, 3, 4, 4)
     assert mx.nd.contrib.div_sqrt_dim(x).shape == x.shape
+
+
+def test_asnumpy_returns_a_private_copy():
+    """asnumpy() copies (MXNDArraySyncCopyToCPU); later in-place updates of the NDArray must not show through."""
+    a = mx.nd.ones((3,))
+    n = a.asnumpy()
+    a[:] = 5
+    assert n.tolist() == [1, 1, 1] and a.asnumpy().tolist() == [5, 5, 5]
