@@ -659,6 +659,35 @@ def batch_norm_nchw(x, gamma, beta, running_mean, running_var, eps, momentum, tr
     return y.permute(0, 3, 1, 2)
 
 
+def conv1x1_bn_nchw(x, w, stride, gamma, beta, running_mean, running_var, eps, momentum, training, fix_gamma,
+                    residual=None, relu=False):
+    """1x1 convolution (no bias) + BatchNorm (+ residual) (+ ReLU) of a logical-NCHW bf16 tensor: the GEMM epilogue emits
+    the per-channel sum / sum of squares, so BatchNorm needs no statistics pass of its own."""
+    if not (x.is_cuda and x.dim() == 4 and x.dtype is torch.bfloat16 and w.dtype is torch.bfloat16 and _fastpath()
+            and running_mean.dtype is torch.float32 and running_var.dtype is torch.float32):
+        return None
+    o, c = w.shape[0], w.shape[1]
+    if c % 8 or o % 8:
+        return None
+    xn = nhwc_view(x)
+    if stride != 1:
+        xn = subsample_nhwc(xn, stride)
+    n, h, ww, _ = xn.shape
+    x2, w2 = xn.reshape(n * h * ww, c), w.reshape(o, c)
+    if not (_gemm_ok(x2, w2) and _bn_shape_ok(torch.empty((1, o), dtype=x.dtype, device="meta"))):
+        return None
+    rn = None
+    if residual is not None:
+        if tuple(residual.shape) != (n, o, h, ww) or residual.dtype != x.dtype:
+            return None
+        rn = nhwc_view(residual)
+    ws = fused_stats_workspace(x2, w2) if training else None
+    y = linear(x2, w2, None, False, ws).reshape(n, h, ww, o)
+    y = bn_act(y, gamma, beta, running_mean, running_var, residual=rn, relu=relu, eps=eps, momentum=momentum,
+               training=training, fix_gamma=fix_gamma, pre_stats=ws)
+    return y.permute(0, 3, 1, 2)
+
+
 def act_any_layout(x, fn):
     """Apply an elementwise kernel wrapper ``fn`` (which wants a contiguous last dim) to ``x`` without breaking a
     channels_last layout chain."""

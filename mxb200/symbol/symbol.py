@@ -398,24 +398,27 @@ class Symbol(object):
                 continue                      # runs (fused or not) when its group's last node is reached
             group = tails.get(id(node))
             if group is not None:
-                bn, add, other = group
-                fused = _run_fused_bn([vals[(id(inp), idx)] for inp, idx in bn.inputs], bn.attrs,
-                                      vals[(id(other[0]), other[1])] if other is not None else None)
+                conv, bn, add, other, relu = group
+                get = lambda ins: [vals[(id(inp), idx)] for inp, idx in ins]   # noqa: E731
+                fused = _run_fused_group(conv, get(conv.inputs) if conv is not None else None, bn, get(bn.inputs[1:]),
+                                         None if conv is not None else get(bn.inputs[:1])[0],
+                                         vals[(id(other[0]), other[1])] if other is not None else None, relu)
                 if fused is not None:
                     vals[(id(node), 0)] = fused
                     continue
-                run(bn)                       # conditions not met at run time (CPU, dtype, width): op by op
-                if add is not None:
-                    run(add)
+                for member in (conv, bn, add):      # conditions not met at run time (CPU, dtype, width): op by op
+                    if member is not None and member is not node:
+                        run(member)
             run(node)
         return [vals[(id(n), i)] for n, i in self._outputs]
 
     def _fusion_plan(self, topo):
-        """Pattern pass over the graph (the reference has none; cuDNN has no fused BN+add+ReLU in that era):
-            BatchNorm -> Activation(relu)                       => one statistics kernel + one fused apply kernel
-            BatchNorm -> (broadcast|elemwise)_add -> relu        => same, with the residual read inside the apply kernel
-        A group is formed only when the intermediate values have no other consumer and are not graph outputs.
-        Returns (deferred node ids, {id(last node): (bn_node, add_node | None, (other_node, idx) | None)})."""
+        """Pattern pass over the graph (the reference has none; cuDNN had no fused BN+add+ReLU in that era):
+            [Convolution 1x1 ->] BatchNorm [-> (broadcast|elemwise)_add] [-> Activation(relu)]
+        executes as: tcgen05 GEMM whose epilogue also emits the BatchNorm statistics, then ONE fused apply kernel that reads
+        the residual and writes the ReLU output + a 1-bit mask.  A node joins a group only when its value has no other
+        consumer and is not a graph output.
+        Returns (deferred node ids, {id(last node): (conv | None, bn, add | None, (other, idx) | None, relu?)})."""
         cached = getattr(self, "_fusion_cache", None)
         if cached is not None and cached[0] == len(topo):
             return cached[1], cached[2]
@@ -434,24 +437,50 @@ class Symbol(object):
 
         def is_relu(n):
             return n is not None and n.op == "Activation" and str(n.attrs.get("act_type", "relu")) == "relu"
+
+        def ones(v, n=2):
+            v = _tuple_attr(v)
+            return v is None or all(int(x) == 1 for x in v)
+
+        def conv_of(bn):
+            c, idx = bn.inputs[0]
+            a = c.attrs
+            if c.op != "Convolution" or idx != 0 or only_user(c) is not bn or id(c) in deferred:
+                return None
+            k, p = _tuple_attr(a.get("kernel")), _tuple_attr(a.get("pad"))
+            if k is None or tuple(int(x) for x in k) != (1, 1) or not (p is None or all(int(x) == 0 for x in p)):
+                return None
+            if not ones(a.get("dilate")) or int(a.get("num_group", 1)) != 1 or not _truthy(a.get("no_bias", False)):
+                return None
+            st = _tuple_attr(a.get("stride"))
+            if st is not None and len(set(int(x) for x in st)) != 1:
+                return None
+            return c
         for n in topo:
             if n.op != "BatchNorm" or _truthy(n.attrs.get("output_mean_var", False)) or int(n.attrs.get("axis", 1)) != 1:
                 continue
             if any(len(users.get((id(n), i), [])) for i in (1, 2)):
                 continue
+            conv = conv_of(n)
             u = only_user(n)
+            tail, add, other, relu = None, None, None, False
             if is_relu(u):
-                deferred[id(n)] = True
-                tails[id(u)] = (n, None, None)
+                tail, relu = u, True
             elif u is not None and u.op in adds and len(u.inputs) == 2 and is_relu(only_user(u)):
-                other = [x for x in u.inputs if not (x[0] is n and x[1] == 0)]
-                if len(other) != 1 or (other[0][0].op == "BatchNorm" and id(other[0][0]) in deferred):
+                rest = [x for x in u.inputs if not (x[0] is n and x[1] == 0)]
+                if len(rest) == 1 and not (rest[0][0].op == "BatchNorm" and id(rest[0][0]) in deferred):
+                    tail, add, other, relu = only_user(u), u, rest[0], True
+            if tail is None:
+                if conv is None:
                     continue
-                deferred[id(n)] = True
-                deferred[id(u)] = True
-                tails[id(only_user(u))] = (n, u, other[0])
+                tail = n                                   # Convolution + BatchNorm only (e.g. the projection shortcut)
+            for member in (conv, n, add):
+                if member is not None and member is not tail:
+                    deferred[id(member)] = True
+            tails[id(tail)] = (conv, n, add, other, relu)
         self._fusion_cache = (len(topo), deferred, tails)
         return deferred, tails
+
 
     def eval(self, ctx=None, **kwargs):
         return self.eval_nd(kwargs)
@@ -499,6 +528,16 @@ class Symbol(object):
 
     def __setstate__(self, state):
         self._outputs = load_json(state["json"])._outputs
+
+
+def _tuple_attr(v):
+    if v is None:
+        return None
+    if isinstance(v, str):
+        v = [x for x in v.strip("()[] ").split(",") if x.strip()]
+    if isinstance(v, (int, float)):
+        return (int(v), int(v))
+    return tuple(int(float(x)) for x in v)
 
 
 def _attr_str(v):
@@ -682,28 +721,43 @@ _SCALAR_OPS = {
 }
 
 
-def _run_fused_bn(ins, attrs, other):
-    """BatchNorm(+residual)+ReLU group on the fused kernels, or None when they do not apply to these tensors."""
-    data, gamma, beta, mm, mv = ins
+def _run_fused_group(conv, conv_ins, bn, bn_params, x_in, other, relu):
+    """[1x1 Convolution +] BatchNorm [+ residual] [+ ReLU] on the fused kernels, or None when they do not apply to these
+    tensors (the caller then runs the member nodes one by one)."""
+    gamma, beta, mm, mv = bn_params
+    data = conv_ins[0] if conv is not None else x_in
     x = data._t
     if not (x.is_cuda and x.dim() == 4):
         return None
     from ..ops import functional as K
     from ..ndarray.ndarray import _op
+    attrs = bn.attrs
     training = autograd.is_training() and not _truthy(attrs.get("use_global_stats", False))
     eps, mom = float(attrs.get("eps", 1e-3)), float(attrs.get("momentum", 0.9))
     fix_gamma = _truthy(attrs.get("fix_gamma", True))
+    stride = 1
+    if conv is not None:
+        st = _tuple_attr(conv.attrs.get("stride"))
+        stride = int(st[0]) if st else 1
 
     class _NoFuse(Exception):
         pass
 
-    def g(xt, gm, bt, *r):
-        y = K.batch_norm_nchw(xt, gm, bt, mm._t, mv._t, eps, mom, training, fix_gamma, residual=r[0] if r else None, relu=True)
+    def g(xt, *ts):
+        ts = list(ts)
+        w = ts.pop(0) if conv is not None else None
+        gm, bt = ts[0], ts[1]
+        res = ts[2] if len(ts) > 2 else None
+        if w is None:
+            y = K.batch_norm_nchw(xt, gm, bt, mm._t, mv._t, eps, mom, training, fix_gamma, residual=res, relu=relu)
+        else:
+            y = K.conv1x1_bn_nchw(xt, w, stride, gm, bt, mm._t, mv._t, eps, mom, training, fix_gamma, residual=res, relu=relu)
         if y is None:
             raise _NoFuse()
         return y
+    args = [data] + ([conv_ins[1]] if conv is not None else []) + [gamma, beta] + ([other] if other is not None else [])
     try:
-        return _op(g, data, gamma, beta, *([other] if other is not None else []))
+        return _op(g, *args)
     except _NoFuse:
         return None
 

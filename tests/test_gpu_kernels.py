@@ -881,7 +881,7 @@ def test_symbol_graph_fusion_bn_add_relu_matches_op_by_op(monkeypatch):
     net = block(block(mx.sym.var("data"), "u1", 256, True), "u2", 256, False)
     net = mx.sym.MakeLoss(mx.sym.sum(net * net))
     deferred, tails = net._fusion_plan(net._topo())
-    assert len(tails) == 6 and len(deferred) == 8
+    assert len(tails) == 7 and len(deferred) == 13          # 5 conv+BN(+add)(+relu) groups, 2 BN+relu groups
     results = []
     for fusion, dtype in (("1", "bfloat16"), ("0", "bfloat16"), ("0", "float32")):
         monkeypatch.setenv("MXB200_GRAPH_FUSION", fusion)

@@ -177,3 +177,43 @@ def test_model_parallel_group2ctx_placement():
     assert out.asnumpy().tolist() == [3.0, 3.0] and out.context == mx.cpu(1)
     c2 = mx.sym.load_json(c.tojson())                     # placement attributes survive serialisation
     assert c2.bind(mx.cpu(), {"a": mx.nd.ones((2,))}, group2ctx={"dev2": mx.cpu(3)}).forward()[0].context == mx.cpu(3)
+
+
+def test_symbol_fusion_plan_groups_and_cpu_fallback(monkeypatch):
+    """The executor's graph pass groups [1x1 Convolution ->] BatchNorm [-> add] [-> relu]; when the fused kernels do not
+    apply (here: CPU) a group runs op by op and gives bit-identical results to MXB200_GRAPH_FUSION=0."""
+    def block(data, name, nf, down):
+        c1 = mx.sym.Convolution(data, kernel=(1, 1), num_filter=nf // 4, no_bias=True, name=name + "_c1")
+        a1 = mx.sym.Activation(mx.sym.BatchNorm(c1, fix_gamma=False, name=name + "_bn1"), act_type="relu")
+        c2 = mx.sym.Convolution(a1, kernel=(3, 3), pad=(1, 1), num_filter=nf // 4, no_bias=True, name=name + "_c2")
+        a2 = mx.sym.Activation(mx.sym.BatchNorm(c2, fix_gamma=False, name=name + "_bn2"), act_type="relu")
+        c3 = mx.sym.Convolution(a2, kernel=(1, 1), num_filter=nf, no_bias=True, name=name + "_c3")
+        b3 = mx.sym.BatchNorm(c3, fix_gamma=False, name=name + "_bn3")
+        sc = data
+        if down:
+            sc = mx.sym.BatchNorm(mx.sym.Convolution(data, kernel=(1, 1), num_filter=nf, no_bias=True, name=name + "_sc"),
+                                  fix_gamma=False, name=name + "_scbn")
+        return mx.sym.Activation(b3 + sc, act_type="relu")
+    net = block(block(mx.sym.var("data"), "u1", 64, True), "u2", 64, False)
+    for sym in (net, mx.sym.load_json(net.tojson())):           # attributes are strings after a JSON round trip
+        deferred, tails = sym._fusion_plan(sym._topo())
+        groups = sorted((g[0].name if g[0] is not None else "-", g[1].name, g[2] is not None, g[4]) for g in tails.values())
+        assert groups == [("-", "u1_bn2", False, True), ("-", "u2_bn2", False, True), ("u1_c1", "u1_bn1", False, True),
+                          ("u1_c3", "u1_bn3", True, True), ("u1_sc", "u1_scbn", False, False),
+                          ("u2_c1", "u2_bn1", False, True), ("u2_c3", "u2_bn3", True, True)]
+        assert len(deferred) == 13
+    # a BatchNorm whose output is also a graph output is never grouped
+    bn = mx.sym.BatchNorm(mx.sym.var("x"), name="b")
+    both = mx.sym.Group([mx.sym.Activation(bn, act_type="relu"), bn])
+    assert both._fusion_plan(both._topo())[1] == {}
+    ex = net.simple_bind(mx.cpu(), data=(2, 16, 8, 8))
+    rs = np.random.RandomState(0)
+    for k, v in ex.arg_dict.items():
+        v[:] = mx.nd.array(rs.randn(*v.shape).astype("f") * 0.1)
+    ex.forward(is_train=True)
+    ex.backward(mx.nd.ones(ex.outputs[0].shape))
+    o1, g1 = ex.outputs[0].asnumpy(), ex.grad_dict["u1_c1_weight"].asnumpy()
+    monkeypatch.setenv("MXB200_GRAPH_FUSION", "0")
+    ex.forward(is_train=True)
+    ex.backward(mx.nd.ones(ex.outputs[0].shape))
+    assert np.array_equal(o1, ex.outputs[0].asnumpy()) and np.array_equal(g1, ex.grad_dict["u1_c1_weight"].asnumpy())
