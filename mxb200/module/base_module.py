@@ -141,7 +141,7 @@ class BaseModule(object):
 
     def fit(self, train_data, eval_data=None, eval_metric="acc", epoch_end_callback=None, batch_end_callback=None,
             kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.01),), eval_end_callback=None,
-            eval_batch_end_callback=None, initializer=Uniform(0.01), arg_params=None, aux_params=None,
+            epoch_begin_callback=None, eval_batch_end_callback=None, initializer=Uniform(0.01), arg_params=None, aux_params=None,
             allow_missing=False, force_rebind=False, force_init=False, begin_epoch=0, num_epoch=None,
             validation_metric=None, monitor=None, sparse_row_id_fn=None):
         """Train.  With ELASTIC_TRAINING_ENABLED=1 the loop runs the fork's protocol (base_module.py:503-623):
@@ -179,6 +179,9 @@ class BaseModule(object):
 
         kv = getattr(self, "_kvstore", None)
         for epoch in range(begin_epoch, num_epoch):
+            if epoch_begin_callback is not None:           # fork addition (base_module.py:415,537-539): before the barrier
+                for callback in _as_list(epoch_begin_callback):
+                    callback(epoch, self.symbol, arg_params, aux_params)
             if elastic and kv is not None:
                 prev_workers = kv.num_workers
                 if not (is_new_worker and epoch == begin_epoch):

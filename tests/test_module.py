@@ -217,3 +217,16 @@ def test_symbol_fusion_plan_groups_and_cpu_fallback(monkeypatch):
     ex.forward(is_train=True)
     ex.backward(mx.nd.ones(ex.outputs[0].shape))
     assert np.array_equal(o1, ex.outputs[0].asnumpy()) and np.array_equal(g1, ex.grad_dict["u1_c1_weight"].asnumpy())
+
+
+def test_fit_epoch_begin_callback_runs_before_each_epoch():
+    """fork addition to Module.fit (python/mxnet/module/base_module.py:415,537-539)."""
+    x = np.random.rand(32, 6).astype("f")
+    y = (x.sum(1) > 3).astype("f")
+    it = mx.io.NDArrayIter(x, y, batch_size=8)
+    net = mx.sym.SoftmaxOutput(mx.sym.FullyConnected(mx.sym.var("data"), num_hidden=2, name="fc"), name="softmax")
+    seen, ends = [], []
+    mod = mx.mod.Module(net)
+    mod.fit(it, num_epoch=3, epoch_begin_callback=lambda epoch, sym, arg, aux: seen.append((epoch, len(ends))),
+            epoch_end_callback=lambda epoch, sym, arg, aux: ends.append(epoch))
+    assert seen == [(0, 0), (1, 1), (2, 2)]
