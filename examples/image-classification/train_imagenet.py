@@ -45,7 +45,10 @@ if __name__ == "__main__":
     kv = mx.kv.create(args.kv_store)
     if args.gc_type != "none":
         kv.set_gradient_compression({"type": args.gc_type, "threshold": args.gc_threshold})
-    devs = [mx.gpu(int(i)) for i in args.gpus.split(",")] if args.gpus else [mx.cpu()]
+    if args.gpus and "LOCAL_RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        devs = [mx.gpu(int(os.environ["LOCAL_RANK"]))]      # torchrun: one process per GPU, --gpus only says "use GPUs"
+    else:
+        devs = [mx.gpu(int(i)) for i in args.gpus.split(",")] if args.gpus else [mx.cpu()]
     shape = tuple(int(v) for v in args.image_shape.split(","))
     name = ("resnet%d_v1" % args.num_layers) if args.network == "resnet" else args.network
     net = vision.get_model(name, classes=args.num_classes)

@@ -449,6 +449,29 @@ class KVStoreElasticDevice(KVStoreLocal):
             self.elastic_group.close()
 
 
+def _maybe_join_torchrun_job(dist):
+    """One process per GPU is this framework's multi-GPU model (the reference drives all GPUs of a box from one process).
+    A script started by ``torchrun`` / ``python -m torch.distributed.run`` (RANK, WORLD_SIZE, LOCAL_RANK, MASTER_* in
+    the environment) joins the NCCL process group on its own GPU the first time it asks for a device store, so reference
+    scripts need no torch-specific set-up code."""
+    import os
+    try:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+    except ValueError:
+        return
+    if world <= 1 or "RANK" not in os.environ or not dist.is_available() or dist.is_initialized():
+        return
+    if not getenv("MXB200_AUTO_PROCESS_GROUP", True):
+        return
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if torch.cuda.is_available():
+        local = int(os.environ.get("LOCAL_RANK", os.environ["RANK"])) % max(1, torch.cuda.device_count())
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=int(os.environ["RANK"]), world_size=world, device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=world)
+
+
 def create(name="local"):
     """mx.kv.create (python/mxnet/kvstore.py:645-688; type parsing as in src/kvstore/kvstore.cc:40-77)."""
     if not isinstance(name, str):
@@ -461,6 +484,7 @@ def create(name="local"):
         return KVStoreDist(name)
     if "device" in name or "nccl" in name:
         import torch.distributed as dist
+        _maybe_join_torchrun_job(dist)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             return KVStoreDevice(name)
         return KVStoreLocal(name)
