@@ -61,10 +61,19 @@ def have_cuda_kernels():
     return torch.cuda.is_available() and cuda() is not None
 
 
+_POST_CHECK = [None]
+
+
 def check(lib, rc):
     if rc != 0:
         msg = lib.MXBGetLastError()
         raise MXNetError(msg.decode("utf-8", "replace") if msg else "native call failed (rc=%d)" % rc)
+    if _POST_CHECK[0] is None:
+        # MXB200_POST_KERNEL_CHECK=1: synchronise after every native launch so an asynchronous fault is reported at the
+        # operator that caused it (the reference's MSHADOW_CUDA_POST_KERNEL_CHECK)
+        _POST_CHECK[0] = bool(getenv("MXB200_POST_KERNEL_CHECK", False)) and torch.cuda.is_available()
+    if _POST_CHECK[0] and lib is _libs.get("cuda"):
+        torch.cuda.synchronize()
 
 
 def ptr(t):

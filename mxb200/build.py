@@ -39,6 +39,15 @@ HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-p
               "-fvisibility-inlines-hidden", "-I", CSRC]
 
 
+# MXB200_SANITIZE=address|undefined|thread: instrument the host runtime (the reference's USE_ASAN cmake switch,
+# CMakeLists.txt:304-309).  The flags are part of the source hash, so switching rebuilds.  Load the result with
+# LD_PRELOAD=$(gcc -print-file-name=libasan.so) python ...
+_SAN = os.environ.get("MXB200_SANITIZE", "")
+if _SAN:
+    HOST_FLAGS = HOST_FLAGS + ["-fsanitize=" + _SAN, "-fno-omit-frame-pointer", "-g"]
+HOST_LINK_FLAGS = (["-fsanitize=" + _SAN] if _SAN else [])
+
+
 def _sources(kind):
     out = []
     for root, _d, files in os.walk(CSRC):
@@ -92,7 +101,8 @@ def _run(cmd, log):
 
 def _obj_for(src, kind):
     rel = os.path.relpath(src, CSRC).replace(os.sep, "_")
-    return os.path.join(OBJ, kind, rel + ".o")
+    sub = kind + ("_" + _SAN.replace(",", "_") if (_SAN and kind == "host") else "")   # instrumented objects never mix in
+    return os.path.join(OBJ, sub, rel + ".o")
 
 
 def _obj_fresh(src, obj, hdr_mtime):
@@ -106,7 +116,7 @@ def build(kind, force=False, verbose=False):
     srcs = _sources(kind)
     if not srcs:
         raise RuntimeError("no %s sources under %s" % (kind, CSRC))
-    os.makedirs(os.path.join(OBJ, kind), exist_ok=True)
+    os.makedirs(os.path.dirname(_obj_for(srcs[0], kind)), exist_ok=True)
     hdr_mtime = max([os.path.getmtime(h) for h in _headers()] + [os.path.getmtime(__file__)])
     log = []
     jobs = []
@@ -128,7 +138,7 @@ def build(kind, force=False, verbose=False):
         _run([NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared",
                                                     "-Xcompiler", "-fPIC", "-lpthread", "-ldl"], log)
     else:
-        _run([CXX, "-shared", "-o", lib] + objs + ["-pthread", "-ldl", "-lrt"], log)
+        _run([CXX, "-shared", "-o", lib] + objs + ["-pthread", "-ldl", "-lrt"] + HOST_LINK_FLAGS, log)
     with open(lib + ".stamp", "w") as f:
         f.write(source_hash(kind))
     with open(os.path.join(OBJ, "build_%s.log" % kind), "w") as f:

@@ -21,6 +21,11 @@ __all__ = ["get", "Engine", "bulk", "set_bulk_size"]
 _CB = ctypes.CFUNCTYPE(None, ctypes.c_void_p)
 
 
+def _log_info(fmt, *args):
+    import logging
+    logging.getLogger("mxb200.engine").info(fmt, *args)
+
+
 class Engine(object):
     def __init__(self, kind=None, num_workers=None):
         self.kind = kind or getenv("MXNET_ENGINE_TYPE", "ThreadedEngine")
@@ -30,6 +35,8 @@ class Engine(object):
         self._keep_lock = threading.Lock()
         self._next = [0]
         self._exc = []
+        # MXNET_ENGINE_INFO=1: log every push / dispatch / wait (threaded_engine.h:302,350 of the reference)
+        self._info = bool(getenv("MXNET_ENGINE_INFO", False))
         if self.kind != "NaiveEngine":
             lib = N.host(required=False)
             if lib is not None and hasattr(lib, "MXBEngineCreate"):
@@ -51,14 +58,21 @@ class Engine(object):
     def push(self, fn, const_vars=(), mutable_vars=(), priority=0, name=None):
         """Schedule ``fn()`` after all earlier writers of const_vars and all earlier users of mutable_vars."""
         if self._lib is None:
+            if self._info:
+                _log_info("run (NaiveEngine) %s", name or getattr(fn, "__name__", "fn"))
             fn()
             return
         with self._keep_lock:
             self._next[0] += 1
             key = self._next[0]
+        if self._info:
+            _log_info("push #%d %s const=%d mutable=%d prio=%d", key, name or getattr(fn, "__name__", "fn"),
+                      len(const_vars), len(mutable_vars), priority)
 
         def tramp(_arg, key=key, fn=fn):
             try:
+                if self._info:
+                    _log_info("dispatch #%d on %s", key, threading.current_thread().name)
                 fn()
             except BaseException as e:  # noqa: BLE001 -- propagated at the next wait (test_exc_handling.py semantics)
                 self._exc.append(e)
@@ -81,11 +95,15 @@ class Engine(object):
             raise e
 
     def wait_for_var(self, var):
+        if self._info:
+            _log_info("wait_for_var")
         if self._lib is not None:
             N.check(self._lib, self._lib.MXBEngineWaitForVar(self._h, var))
         self._raise_pending()
 
     def wait_all(self):
+        if self._info:
+            _log_info("wait_all")
         if self._lib is not None:
             N.check(self._lib, self._lib.MXBEngineWaitAll(self._h))
         self._raise_pending()

@@ -94,3 +94,19 @@ def test_stop_start_drain():
     eng.wait_all()
     assert hits[-1] == 99
     mx.nd.waitall()
+
+
+def test_engine_info_logging(monkeypatch, caplog):
+    """MXNET_ENGINE_INFO=1 reports pushes / dispatches / waits (threaded_engine.h:302,350 of the reference)."""
+    import logging
+    from mxb200 import engine as E
+    monkeypatch.setenv("MXNET_ENGINE_INFO", "1")
+    eng = E.Engine()
+    v = eng.new_variable()
+    out = []
+    with caplog.at_level(logging.INFO, logger="mxb200.engine"):
+        eng.push(lambda: out.append(1), mutable_vars=[v] if not isinstance(v, object().__class__) else [], name="probe")
+        eng.wait_all()
+    assert out == [1]
+    text = caplog.text
+    assert "probe" in text and "wait_all" in text
