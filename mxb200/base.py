@@ -96,3 +96,92 @@ def getenv(name, default=None, typ=None):
         return typ(val)
     except ValueError:
         return default
+
+
+# ----------------------------------------------------------------------------- reference-compatible helpers (python/mxnet/base.py)
+class NotImplementedForSymbol(MXNetError):
+    """Raised by NDArray-only methods called on a Symbol (base.py:93-109)."""
+
+    def __init__(self, function, alias, *args):
+        super(NotImplementedForSymbol, self).__init__()
+        self.function = function.__name__ if hasattr(function, "__name__") else str(function)
+        self.alias = alias
+        self.args = [str(type(a)) for a in args]
+
+    def __str__(self):
+        msg = "Function {}".format(self.function)
+        if self.alias:
+            msg += " (namely operator \"{}\")".format(self.alias)
+        if self.args:
+            msg += " with arguments ({})".format(", ".join(self.args))
+        return msg + " is not implemented for Symbol and only available in NDArray."
+
+
+class NotSupportedForSparseNDArray(MXNetError):
+    """Raised by dense-only methods called on a sparse NDArray (base.py:111-127)."""
+
+    def __init__(self, function, alias, *args):
+        super(NotSupportedForSparseNDArray, self).__init__()
+        self.function = function.__name__ if hasattr(function, "__name__") else str(function)
+        self.alias = alias
+        self.args = [str(type(a)) for a in args]
+
+    def __str__(self):
+        msg = "Function {}".format(self.function)
+        if self.alias:
+            msg += " (namely operator \"{}\")".format(self.alias)
+        if self.args:
+            msg += " with arguments ({})".format(", ".join(self.args))
+        return msg + " is not supported for SparseNDArray and only available in NDArray."
+
+
+class _NullType(object):
+    """Placeholder for "argument not given" in generated operator signatures."""
+
+    def __repr__(self):
+        return "_Null"
+
+
+_Null = _NullType()
+mx_real_t = np.float32
+mx_uint = int
+mx_float = float
+
+
+def py_str(x):
+    return x.decode("utf-8") if isinstance(x, (bytes, bytearray)) else str(x)
+
+
+def c_str(s):
+    return s.encode("utf-8") if isinstance(s, str) else s
+
+
+def data_dir_default():
+    system = __import__("platform").system()
+    if system == "Windows":
+        return os.path.join(os.environ.get("APPDATA", os.path.expanduser("~")), "mxnet")
+    return os.path.join(os.path.expanduser("~"), ".mxnet")
+
+
+def data_dir():
+    """Directory for datasets / pretrained models: $MXNET_HOME or ~/.mxnet (base.py:59-77)."""
+    return os.getenv("MXNET_HOME", data_dir_default())
+
+
+def _as_list(obj):
+    return list(obj) if isinstance(obj, (list, tuple)) else [obj]
+
+
+def check_call(ret):
+    if ret != 0:
+        raise MXNetError("native call failed (rc=%s)" % ret)
+
+
+class classproperty(object):
+    """Read-only property on the class itself (used by AttrScope / NameManager / Context ``_current``)."""
+
+    def __init__(self, fget):
+        self.fget = fget
+
+    def __get__(self, obj, owner):
+        return self.fget(owner)

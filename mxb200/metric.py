@@ -36,7 +36,20 @@ def create(metric, *args, **kwargs):
         for child in metric:
             composite.add(create(child, *args, **kwargs))
         return composite
+    if isinstance(metric, dict):
+        cfg = dict(metric)
+        return create(cfg.pop("metric"), *args, **dict(cfg, **kwargs))
     if isinstance(metric, str):
+        # serialized forms produced by EvalMetric.get_config() + json (registry.py:get_create_func of the reference)
+        if metric.startswith("{"):
+            import json
+            return create(json.loads(metric), *args, **kwargs)
+        if metric.startswith("["):
+            import json
+            name, cfg = json.loads(metric)
+            return create(name, *args, **dict(cfg, **kwargs))
+        if metric.lower() not in _REG:
+            raise ValueError("Metric must be either callable or in %s; got %r" % (sorted(_REG), metric))
         return _REG[metric.lower()](*args, **kwargs)
     raise TypeError("metric should be a str, callable, EvalMetric or list")
 

@@ -45,3 +45,35 @@ for _k, _v in _OPS.items():
     if _k.startswith("linalg_"):
         setattr(linalg, _k[len("linalg_"):], _v)
 _sys.modules[linalg.__name__] = linalg
+
+
+# ----------------------------------------------------------------------------- fluent methods (x.op(...) == mx.nd.op(x, ...))
+# The reference generates one NDArray method per "fluent" operator (python/mxnet/ndarray/ndarray.py:1019-1500).  The
+# hand-written methods of NDArray stay; reductions are re-pointed at the operators so they take the full argument set
+# (exclude=, out=), and every other reference method that is still missing is added from the operator registry.
+_FLUENT_FORCE = ("sum", "mean", "prod", "max", "min", "nansum", "nanprod", "argmax", "argmin", "norm", "topk", "sort", "argsort",
+                 "clip", "broadcast_like", "flip", "tile", "repeat", "pad", "one_hot", "pick", "take", "slice", "slice_like")
+_FLUENT_ADD = ("arccos", "arccosh", "arcsin", "arcsinh", "arctan", "arctanh", "argmax_channel", "broadcast_axes", "cbrt",
+               "ceil", "cos", "cosh", "degrees", "depth_to_space", "diag", "expm1", "fix", "floor", "log10", "log1p", "log2",
+               "radians", "rcbrt", "reciprocal", "rint", "round", "rsqrt", "shape_array", "sin", "sinh", "size_array", "softmin",
+               "space_to_depth", "tan", "trunc", "sign", "softmax", "log_softmax", "zeros_like", "ones_like", "reshape_like",
+               "expand_dims", "squeeze", "relu", "sigmoid", "tanh", "exp", "log", "sqrt", "square", "abs", "flatten", "swapaxes",
+               "split", "slice_axis", "broadcast_to", "transpose")
+
+
+def _install_fluent():
+    def make(fn, name):
+        def method(self, *args, **kwargs):
+            return fn(self, *args, **kwargs)
+        method.__name__ = name
+        method.__doc__ = "Convenience fluent method for :py:func:`%s`." % name
+        return method
+    for _n in _FLUENT_FORCE:
+        if _n in _OPS:
+            setattr(NDArray, _n, make(_OPS[_n], _n))
+    for _n in _FLUENT_ADD:
+        if _n in _OPS and not hasattr(NDArray, _n):
+            setattr(NDArray, _n, make(_OPS[_n], _n))
+
+
+_install_fluent()

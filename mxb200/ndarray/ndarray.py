@@ -46,6 +46,16 @@ def _pin_if(t, ctx):
     return t
 
 
+# storage-type / dtype / grad_req code tables of the reference's C ABI (ndarray.py:52-98); kept because user code and
+# serialised files refer to the integer codes
+_STORAGE_TYPE_UNDEFINED, _STORAGE_TYPE_DEFAULT, _STORAGE_TYPE_ROW_SPARSE, _STORAGE_TYPE_CSR = -1, 0, 1, 2
+_STORAGE_TYPE_STR_TO_ID = {"undefined": -1, "default": 0, "row_sparse": 1, "csr": 2}
+_STORAGE_TYPE_ID_TO_STR = {v: k for k, v in _STORAGE_TYPE_STR_TO_ID.items()}
+_DTYPE_NP_TO_MX = {None: -1, np.float32: 0, np.float64: 1, np.float16: 2, np.uint8: 3, np.int32: 4, np.int8: 5, np.int64: 6}
+_DTYPE_MX_TO_NP = {-1: None, 0: np.float32, 1: np.float64, 2: np.float16, 3: np.uint8, 4: np.int32, 5: np.int8, 6: np.int64}
+_GRAD_REQ_MAP = {"null": 0, "write": 1, "add": 3}
+
+
 class NDArray(object):
     """n-dimensional array on a Context.  ``arr.data_`` / ``arr._t`` is the torch tensor."""
     __slots__ = ("_t", "_ctx", "_grad_req", "_grad_hook", "_bw_epoch", "__weakref__")

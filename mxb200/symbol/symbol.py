@@ -97,6 +97,22 @@ def _num_outputs(op, attrs):
     return 1
 
 
+# attribute keys the reference stores with double underscores whatever the user wrote (c_api_symbolic.cc kHiddenKeys)
+_HIDDEN_ATTR_KEYS = ("ctx_group", "lr_mult", "wd_mult", "force_mirroring", "mirror_stage")
+
+
+def _attr_key(k):
+    return "__%s__" % k if k in _HIDDEN_ATTR_KEYS else k
+
+
+def _put_attr(d, k, v, override=True):
+    """Store a user attribute; hidden keys are visible under both spellings (key and __key__)."""
+    keys = (k, "__%s__" % k) if k in _HIDDEN_ATTR_KEYS else (k,)
+    for kk in keys:
+        if override or kk not in d:
+            d[kk] = v
+
+
 class _NameManager(object):
     _tl = threading.local()
 
@@ -214,7 +230,9 @@ class Symbol(object):
     def attr(self, key):
         n = self._outputs[0][0]
         v = n.var_attrs.get(key, n.attrs.get(key))
-        return str(v) if v is not None else None
+        if v is None and key in _HIDDEN_ATTR_KEYS:
+            v = n.var_attrs.get("__%s__" % key)
+        return _attr_str(v) if v is not None else None
 
     def list_attr(self):
         n = self._outputs[0][0]
@@ -232,7 +250,11 @@ class Symbol(object):
         return ret
 
     def _set_attr(self, **kwargs):
-        self._outputs[0][0].var_attrs.update(kwargs)
+        for k, v in kwargs.items():
+            if not isinstance(v, str):
+                raise ValueError("Set Attr only accepts string values")
+        for k, v in kwargs.items():
+            _put_attr(self._outputs[0][0].var_attrs, k, v)
 
     # ---- arithmetic ------------------------------------------------------------------------------
     def _bin(self, other, op, scalar_op, rev=False):
@@ -618,10 +640,16 @@ def var(name, attr=None, shape=None, lr_mult=None, wd_mult=None, dtype=None, ini
     for k, v in kwargs.items():
         if k.startswith("__") and k.endswith("__"):
             a[k] = str(v)
+        else:
+            raise ValueError("Attribute name=%s is not supported. Additional attributes must start and end with double "
+                             "underscores, e.g, __yourattr__" % k)
+    final = {}
+    for k, v in a.items():
+        _put_attr(final, k, v)
     from ..attribute import current_attrs
-    for k, v in current_attrs().items():        # e.g. AttrScope(ctx_group='dev1') -> __ctx_group__
-        a.setdefault("__%s__" % k, v)
-    n.var_attrs = a
+    for k, v in current_attrs().items():        # e.g. AttrScope(ctx_group='dev1') -> ctx_group + __ctx_group__
+        _put_attr(final, k, v, override=False)
+    n.var_attrs = final
     return Symbol([(n, 0)])
 
 
@@ -650,7 +678,7 @@ def _make_op(op, inputs, attrs, name=None, hint=None):
     node = _Node(op, name, attrs, [s._outputs[0] for s in inputs], nout)
     from ..attribute import current_attrs
     for k, v in current_attrs().items():
-        node.var_attrs["__%s__" % k] = v
+        _put_attr(node.var_attrs, k, v)
     return Symbol([(node, i) for i in range(nout)]) if nout > 1 else Symbol([(node, 0)])
 
 
@@ -658,7 +686,20 @@ def _create(op, args, kwargs):
     """mx.sym.<op>(*args, **kwargs): Symbol inputs become graph edges, the rest become attributes; parameter
     variables (weight/bias/gamma/...) and label variables are auto-created with the reference naming."""
     name = kwargs.pop("name", None)
-    kwargs.pop("attr", None)
+    user_attr = dict(kwargs.pop("attr", None) or {})
+    for v in user_attr.values():
+        if not isinstance(v, str):
+            raise ValueError("Attributes need to be string")
+    for k in _HIDDEN_ATTR_KEYS:                      # e.g. Convolution(..., lr_mult=1): node attribute, not an operator argument
+        if k in kwargs and not isinstance(kwargs[k], Symbol):
+            user_attr[k] = str(kwargs.pop(k))
+    from ..attribute import current_attrs
+    node_attrs = {}
+    for k, v in user_attr.items():
+        _put_attr(node_attrs, k, v)
+    for k, v in current_attrs().items():
+        _put_attr(node_attrs, k, v, override=False)
+    inherit = {k: v for k, v in node_attrs.items() if k.startswith("__") and k.endswith("__")}   # reach the auto-created variables
     sym_kwargs = {k: v for k, v in kwargs.items() if isinstance(v, Symbol)}
     attrs = {k: v for k, v in kwargs.items() if not isinstance(v, Symbol) and v is not None}
     hint = op.lower().lstrip("_")
@@ -695,6 +736,8 @@ def _create(op, args, kwargs):
                 if aname == "data":
                     raise MXNetError("%s: missing data input" % op)
                 s = var("%s_%s" % (node_name, aname))
+                for k, v in inherit.items():
+                    s._outputs[0][0].var_attrs.setdefault(k, v)
                 if is_aux:
                     s._outputs[0][0].is_aux = True
             if is_aux:
@@ -706,9 +749,7 @@ def _create(op, args, kwargs):
             attrs["__kwarg_inputs__"] = tuple(sym_kwargs.keys())
     nout = _num_outputs(op, attrs)
     node = _Node(op, node_name, attrs, [s._outputs[0] for s in order], nout)
-    from ..attribute import current_attrs
-    for k, v in current_attrs().items():
-        node.var_attrs["__%s__" % k] = v
+    node.var_attrs.update(node_attrs)
     return Symbol([(node, i) for i in range(nout)]) if nout > 1 else Symbol([(node, 0)])
 
 

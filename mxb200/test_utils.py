@@ -22,6 +22,11 @@ from .ndarray import NDArray
 
 _DEFAULT_CTX = [None]
 _RNG = np.random
+# names that scripts get through ``from mxnet.test_utils import *`` in the reference (its module-level imports)
+import numpy.random as rnd  # noqa: E402,F401
+from .ndarray import array, zeros, ones  # noqa: E402,F401
+from .symbol import Symbol  # noqa: E402,F401
+import mxb200 as mx  # noqa: E402,F401  (the package itself; safe: it is already in sys.modules when this module loads)
 
 
 # ----------------------------------------------------------------------------- defaults
