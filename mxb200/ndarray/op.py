@@ -1290,3 +1290,61 @@ def group_adagrad_update(weight, grad, history, lr, rescale_grad=1.0, clip_gradi
 
 def get(name):
     return _REG.get(name)
+
+
+# ----------------------------------------------------------------------------- row_sparse gradients / weights in update ops
+def _sparse_aware_update(name, n_states, lazy_capable):
+    """Wrap a dense update operator so it accepts row_sparse gradients / weights / states like the reference kernels
+    (optimizer_op-inl.h: SGDDnsRspKernel, SGDMomStdDnsRspDnsKernel, AdamStdDnsRspDnsKernel, FtrlDnsRspDnsKernel ...):
+
+    * ``lazy_update`` (default True) with a row_sparse gradient touches ONLY the rows present in the gradient -- weight
+      decay and momentum decay of absent rows are skipped;
+    * otherwise ("standard" update) absent rows see a zero gradient;
+    * row_sparse weights / states are updated through a dense round trip and written back in place."""
+    from . import sparse as _spm
+    dense_fn = _REG[name]
+
+    def update(weight, grad, *args, **kwargs):
+        is_sp = lambda a: isinstance(a, _spm.BaseSparseNDArray)   # noqa: E731
+        states = list(args[:n_states])
+        rest = args[n_states:]
+        if not (is_sp(weight) or is_sp(grad) or any(is_sp(s) for s in states)):
+            return dense_fn(weight, grad, *args, **kwargs)
+        out = kwargs.pop("out", None)
+        lazy = kwargs.get("lazy_update", True) if lazy_capable == "flag" else (lazy_capable == "always")
+        dw = weight.todense() if is_sp(weight) else weight
+        ds = [s.todense() if is_sp(s) else s for s in states]
+        if isinstance(grad, _spm.RowSparseNDArray) and lazy:
+            rows = grad._indices
+            if rows.numel():
+                w_rows = NDArray(dw._t.index_select(0, rows), dw.context)
+                s_rows = [NDArray(s._t.index_select(0, rows), s.context) for s in ds]
+                dense_fn(w_rows, NDArray(grad._data, grad.context), *s_rows, *rest, **kwargs)
+                with torch.no_grad():
+                    dw._t.index_copy_(0, rows, w_rows._t)
+                    for s, sr in zip(ds, s_rows):
+                        s._t.index_copy_(0, rows, sr._t)
+        else:
+            dg = grad.todense() if is_sp(grad) else grad
+            dense_fn(dw, dg, *ds, *rest, **kwargs)
+        for orig, dense in zip([weight] + states, [dw] + ds):
+            if is_sp(orig):
+                orig[:] = dense
+        if out is not None and out is not weight:
+            out[:] = dw
+            return out
+        return weight
+    update.__name__ = name
+    update.__doc__ = dense_fn.__doc__
+    return update
+
+
+for _name, _ns, _lazy in (("sgd_update", 0, "flag"), ("sgd_mom_update", 1, "flag"), ("mp_sgd_update", 1, "flag"),
+                          ("mp_sgd_mom_update", 2, "flag"), ("adam_update", 2, "flag"), ("ftrl_update", 2, "always"),
+                          ("signsgd_update", 0, "never"), ("signum_update", 1, "never"), ("rmsprop_update", 1, "never"),
+                          ("rmspropalex_update", 3, "never"), ("ftml_update", 3, "never"),
+                          ("_contrib_group_adagrad_update", 1, "always")):
+    if _name in _REG:
+        _REG[_name] = _sparse_aware_update(_name, _ns, _lazy)
+        if _name in globals():
+            globals()[_name] = _REG[_name]

@@ -266,4 +266,6 @@ def sparse_adagrad_update(weight, grad, history, lr, epsilon=1e-7, wd=0.0, resca
     return out
 
 
+from . import op as _op_mod  # noqa: E402
+_REG["_sparse_adagrad_update"] = _op_mod._sparse_aware_update("_sparse_adagrad_update", 1, "always")
 _unresolved = install_aliases()

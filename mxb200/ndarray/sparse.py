@@ -16,8 +16,13 @@ __all__ = ["BaseSparseNDArray", "RowSparseNDArray", "CSRNDArray", "row_sparse_ar
            "zeros", "cast_storage", "dot", "retain", "add_n_rsp"]
 
 
-class BaseSparseNDArray(object):
+class BaseSparseNDArray(NDArray):
+    """Sparse arrays are NDArrays (python/mxnet/ndarray/sparse.py:BaseSparseNDArray): any operator or method without a
+    sparse implementation sees the dense view ``_t`` (the reference's storage fallback) and returns a dense result."""
     stype = None
+    _grad_req = None
+    _grad_hook = None
+    _bw_epoch = -1
 
     @property
     def context(self):
@@ -43,6 +48,95 @@ class BaseSparseNDArray(object):
 
     def asnumpy(self):
         return self.todense().asnumpy()
+
+    def asscalar(self):
+        return self.todense().asscalar()
+
+    @property
+    def _t(self):
+        """Dense torch view for operators without a sparse kernel (the reference's storage fallback).  READ ONLY: writes
+        go through ``x[:] = value`` / ``copyto``."""
+        return self.todense()._t
+
+    @_t.setter
+    def _t(self, value):
+        self[:] = NDArray(value, self._ctx)
+
+    @property
+    def T(self):
+        return self.todense().T
+
+    def wait_to_write(self):
+        self.wait_to_read()
+
+    def zeros_like(self):
+        return zeros(self.stype, self.shape, ctx=self._ctx, dtype=self.dtype)
+
+    def reshape(self, *a, **k):
+        from ..base import NotSupportedForSparseNDArray
+        raise NotSupportedForSparseNDArray(self.reshape, None, *a)
+
+    # ---- autograd: gradients of sparse leaves are kept dense-backed and exposed with the requested storage type
+    def attach_grad(self, grad_req="write", stype=None):
+        self._grad_stype = stype or self.stype
+        self._dense_leaf = self.todense()
+        self._dense_leaf.attach_grad(grad_req)
+
+    @property
+    def grad(self):
+        leaf = getattr(self, "_dense_leaf", None)
+        if leaf is None or leaf.grad is None:
+            return None
+        st = getattr(self, "_grad_stype", "default")
+        return cast_storage(leaf.grad, st) if st != "default" else leaf.grad
+
+    def detach(self):
+        return self.copy()
+
+    def __neg__(self):
+        return self * -1.0
+
+    def __radd__(self, o):
+        return self.__add__(o)
+
+    def __rmul__(self, o):
+        return self.__mul__(o)
+
+    def __iadd__(self, o):
+        r = self + o
+        self[:] = r
+        return self
+
+    def __isub__(self, o):
+        r = self - o
+        self[:] = r
+        return self
+
+    def __imul__(self, o):
+        r = self * o
+        self[:] = r
+        return self
+
+    def __itruediv__(self, o):
+        r = self / o
+        self[:] = r
+        return self
+
+    def sum(self, *a, **k):
+        return self.todense().sum(*a, **k)
+
+    def mean(self, *a, **k):
+        return self.todense().mean(*a, **k)
+
+    def square(self):
+        return self * self
+
+    def check_format(self, full_check=True):
+        """Raise if the index arrays are malformed (ndarray/sparse.py check_format of the reference)."""
+        from ..base import MXNetError
+        idx = self._indices
+        if idx.numel() and (bool((idx < 0).any()) or bool((idx[1:] < idx[:-1]).any()) and self.stype == "row_sparse"):
+            raise MXNetError("indices must be non-negative and sorted")
 
     def wait_to_read(self):
         if self._data.is_cuda:
@@ -174,6 +268,40 @@ class CSRNDArray(BaseSparseNDArray):
 
     def as_in_context(self, ctx):
         return self if ctx == self._ctx else self.copyto(ctx)
+
+    def astype(self, dtype):
+        return CSRNDArray(self._data.to(torch_dtype(dtype)), self._indices, self._indptr, self._shape, self._ctx)
+
+    def __setitem__(self, key, value):
+        assert isinstance(key, slice) and key == slice(None), "CSRNDArray only supports [:] assignment"
+        if isinstance(value, CSRNDArray):
+            value.copyto(self)
+        else:
+            src = cast_storage(value if isinstance(value, NDArray) else _dense_array(value, ctx=self._ctx), "csr")
+            src.astype(self._data.dtype).copyto(self)
+
+    def _binary(self, other, fn):
+        if isinstance(other, BaseSparseNDArray):
+            return cast_storage(NDArray(fn(self.todense()._t, other.todense()._t), self._ctx), "csr")
+        if isinstance(other, NDArray):
+            return NDArray(fn(self.todense()._t, other._t), self._ctx)
+        return CSRNDArray(fn(self._data, other), self._indices, self._indptr, self._shape, self._ctx)
+
+    def __add__(self, o):
+        return self._binary(o, torch.add)
+
+    def __sub__(self, o):
+        return self._binary(o, torch.sub)
+
+    def __mul__(self, o):
+        return self._binary(o, torch.mul)
+
+    def __truediv__(self, o):
+        return self._binary(o, torch.div)
+
+    def asscipy(self):
+        import scipy.sparse as spsp
+        return spsp.csr_matrix((self._data.cpu().numpy(), self._indices.cpu().numpy(), self._indptr.cpu().numpy()), shape=self._shape)
 
     def __getitem__(self, key):
         if isinstance(key, int):

@@ -25,6 +25,34 @@ __all__ = ["Optimizer", "register", "create", "get_updater", "Updater", "SGD", "
 _LOW_PRECISION = (torch.float16, torch.bfloat16)
 
 
+def _dense_storage_roundtrip(method):
+    """Optimizers are written against dense weights / states; a row_sparse (or csr) weight or state is updated through a
+    dense copy and written back in place (the reference keeps such arrays sparse with every row present).  Sparse
+    GRADIENTS are passed through untouched: lazy-update semantics depend on them."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapped(self, index, weight, grad, state):
+        leaves = []
+
+        def densify(x):
+            if isinstance(x, _sp.BaseSparseNDArray):
+                d = x.todense()
+                leaves.append((x, d))
+                return d
+            if isinstance(x, (tuple, list)):
+                return type(x)(densify(v) for v in x)
+            return x
+        w, st = densify(weight), densify(state)
+        if not leaves:
+            return method(self, index, weight, grad, state)
+        r = method(self, index, w, grad, st)
+        for orig, dense in leaves:
+            orig[:] = dense
+        return r
+    return wrapped
+
+
 class Optimizer(object):
     opt_registry = {}
 
@@ -57,6 +85,9 @@ class Optimizer(object):
     def register(klass):
         assert isinstance(klass, type)
         Optimizer.opt_registry[klass.__name__.lower()] = klass
+        for meth in ("update", "update_multi_precision"):
+            if meth in klass.__dict__:
+                setattr(klass, meth, _dense_storage_roundtrip(klass.__dict__[meth]))
         return klass
 
     @staticmethod
@@ -205,33 +236,12 @@ class SGD(Optimizer):
             return (self.create_state(index, master), master)
         return super(SGD, self).create_state_multi_precision(index, weight)
 
-    def _sparse_update(self, weight, grad, state, lr, wd):
-        # only rows present in the gradient are touched (SGDDnsRspKernel / lazy update semantics)
-        idx = grad._indices
-        with torch.no_grad():
-            g = grad._data.float() * self.rescale_grad
-            if self.clip_gradient is not None:
-                g = g.clamp(-self.clip_gradient, self.clip_gradient)
-            w = weight._t[idx].float()
-            if state is not None:
-                m = state._t[idx].float()
-                m = self.momentum * m - lr * wd * w - lr * g
-                state._t[idx] = m.to(state._t.dtype)
-                weight._t[idx] = (w + m).to(weight._t.dtype)
-            else:
-                weight._t[idx] = ((1 - lr * wd) * w - lr * g).to(weight._t.dtype)
-
     def _update_impl(self, index, weight, grad, state, multi_precision=False):
         self._update_count(index)
         lr, wd = self._get_lr(index), self._get_wd(index)
-        kw = dict(rescale_grad=self.rescale_grad, clip_gradient=_clip_kw(self))
-        if isinstance(grad, _sp.RowSparseNDArray):
-            mom = state[0] if multi_precision else state
-            tgt = state[1] if multi_precision else weight
-            self._sparse_update(tgt, grad, mom, lr, wd)
-            if multi_precision:
-                _assign(weight, tgt._t)
-            return
+        # row_sparse gradients / weights: the update operators themselves implement the lazy (rows present in the gradient
+        # only) and standard semantics (ndarray/op.py::_sparse_aware_update)
+        kw = dict(rescale_grad=self.rescale_grad, clip_gradient=_clip_kw(self), lazy_update=self.lazy_update)
         if not multi_precision:
             if state is not None:
                 ndop.sgd_mom_update(weight, grad, state, lr=lr, wd=wd, momentum=self.momentum, out=weight, **kw)
@@ -486,20 +496,8 @@ class Adam(Optimizer):
         t = self._index_update_count[index]
         lr *= math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
         mean, var = state
-        if isinstance(grad, _sp.RowSparseNDArray):
-            idx = grad._indices
-            with torch.no_grad():
-                w = weight._t[idx].float()
-                g = grad._data.float() * self.rescale_grad + wd * w
-                if self.clip_gradient is not None:
-                    g = g.clamp(-self.clip_gradient, self.clip_gradient)
-                m = self.beta1 * mean._t[idx] + (1 - self.beta1) * g
-                v = self.beta2 * var._t[idx] + (1 - self.beta2) * g * g
-                mean._t[idx], var._t[idx] = m, v
-                weight._t[idx] = (w - lr * m / (v.sqrt() + self.epsilon)).to(weight._t.dtype)
-            return
         ndop.adam_update(weight, grad, mean, var, lr=lr, beta1=self.beta1, beta2=self.beta2, epsilon=self.epsilon, wd=wd,
-                         rescale_grad=self.rescale_grad, clip_gradient=_clip_kw(self), out=weight)
+                         rescale_grad=self.rescale_grad, clip_gradient=_clip_kw(self), lazy_update=self.lazy_update, out=weight)
 
 
 @register
@@ -555,15 +553,8 @@ class AdaGrad(Optimizer):
         self._update_count(index)
         lr, wd = self._get_lr(index), self._get_wd(index)
         if isinstance(grad, _sp.RowSparseNDArray):
-            idx = grad._indices
-            with torch.no_grad():
-                g = grad._data.float() * self.rescale_grad
-                if self.clip_gradient is not None:
-                    g = g.clamp(-self.clip_gradient, self.clip_gradient)
-                h = state._t[idx] + g * g
-                state._t[idx] = h
-                w = weight._t[idx].float()
-                weight._t[idx] = (w - lr * (g / (h + self.float_stable_eps).sqrt() + wd * w)).to(weight._t.dtype)
+            ndop.get("_sparse_adagrad_update")(weight, grad, state, lr=lr, epsilon=self.float_stable_eps, wd=wd,
+                                               rescale_grad=self.rescale_grad, clip_gradient=_clip_kw(self))
             return
         with torch.no_grad():
             g = _prep(self, grad)
