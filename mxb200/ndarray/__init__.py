@@ -47,6 +47,33 @@ for _k, _v in _OPS.items():
 _sys.modules[linalg.__name__] = linalg
 
 
+# mx.nd._internal / mx.nd.op / mx.nd.image: the same registry under the reference's other module names
+class _Prefixed(_types.ModuleType):
+    def __init__(self, name, prefixes, fallback=True):
+        super(_Prefixed, self).__init__(name)
+        self._prefixes, self._fallback = prefixes, fallback
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        for pre in self._prefixes:
+            if pre + name in _OPS:
+                return _OPS[pre + name]
+        if self._fallback and name in _OPS:
+            return _OPS[name]
+        raise AttributeError("module %r has no attribute %r" % (self.__name__, name))
+
+
+_internal = _Prefixed(__name__ + "._internal", ("",))
+image = _Prefixed(__name__ + ".image", ("_image_",), fallback=False)
+_sys.modules[_internal.__name__] = _internal
+_sys.modules[image.__name__] = image
+for _k in ("negative_binomial", "generalized_negative_binomial"):
+    pass
+# legacy top-level sampler names (mx.nd.uniform / mx.nd.normal, python/mxnet/ndarray/random.py re-exports)
+uniform, normal = random.uniform, random.normal
+
+
 # ----------------------------------------------------------------------------- fluent methods (x.op(...) == mx.nd.op(x, ...))
 # The reference generates one NDArray method per "fluent" operator (python/mxnet/ndarray/ndarray.py:1019-1500).  The
 # hand-written methods of NDArray stay; reductions are re-pointed at the operators so they take the full argument set

@@ -4,7 +4,8 @@ import torch
 from ..base import torch_dtype
 from .ndarray import NDArray, _ctx_of, _shape
 
-__all__ = ["uniform", "normal", "randn", "randint", "exponential", "gamma", "poisson", "multinomial", "shuffle", "seed"]
+__all__ = ["uniform", "normal", "randn", "randint", "exponential", "gamma", "poisson", "negative_binomial",
+           "generalized_negative_binomial", "multinomial", "shuffle", "seed"]
 
 
 def _mk(shape, ctx, dtype):
@@ -20,22 +21,37 @@ def _ret(t, ctx, out):
     return NDArray(t, ctx)
 
 
-def uniform(low=0.0, high=1.0, shape=None, dtype=None, ctx=None, out=None, **kw):
+def _random_helper(name, params, shape, dtype, ctx, out, kwargs):
+    """Scalar parameters -> ``_random_<name>`` (one distribution, ``shape`` samples); NDArray parameters -> ``_sample_<name>``
+    (one distribution per element, output shape = params.shape + shape) -- python/mxnet/ndarray/random.py:31-51."""
+    from .op import _REG
+    if all(isinstance(p, NDArray) for p in params):
+        if ctx is not None:
+            raise ValueError("ctx is not supported when the distribution parameters are NDArrays")
+        return _REG["_sample_" + name](*params, shape=shape, dtype=dtype, out=out, **kwargs)
+    if any(isinstance(p, NDArray) for p in params):
+        raise ValueError("Distribution parameters must all have the same type, but got both %s" % str([type(p) for p in params]))
     if out is not None and shape is None:
         shape, ctx = out.shape, out.context
-    ctx, t = _mk(shape, ctx, dtype)
-    return _ret(t.float().uniform_(low, high).to(t.dtype), ctx, out)
+    if shape is None:
+        shape = (1,)
+    return _REG["_random_" + name](*params, shape=shape, dtype=dtype, ctx=ctx, out=out, **kwargs)
 
 
-def normal(loc=0.0, scale=1.0, shape=None, dtype=None, ctx=None, out=None, **kw):
-    if out is not None and shape is None:
-        shape, ctx = out.shape, out.context
-    ctx, t = _mk(shape, ctx, dtype)
-    return _ret(t.float().normal_(loc, scale).to(t.dtype), ctx, out)
+def uniform(low=0, high=1, shape=None, dtype=None, ctx=None, out=None, **kwargs):
+    return _random_helper("uniform", [low, high], shape, dtype, ctx, out, kwargs)
 
 
-def randn(*shape, **kw):
-    return normal(kw.pop("loc", 0.0), kw.pop("scale", 1.0), shape=shape, **kw)
+def normal(loc=0, scale=1, shape=None, dtype=None, ctx=None, out=None, **kwargs):
+    if not isinstance(scale, NDArray) and scale < 0:
+        from ..base import MXNetError
+        raise MXNetError("normal: scale (standard deviation) must be non-negative, got %s" % scale)
+    return _random_helper("normal", [loc, scale], shape, dtype, ctx, out, kwargs)
+
+
+def randn(*shape, **kwargs):
+    loc, scale = kwargs.pop("loc", 0), kwargs.pop("scale", 1)
+    return normal(loc, scale, shape=shape or None, **kwargs)
 
 
 def randint(low, high, shape=None, dtype="int32", ctx=None, out=None, **kw):
@@ -44,32 +60,37 @@ def randint(low, high, shape=None, dtype="int32", ctx=None, out=None, **kw):
     return _ret(t, ctx, out)
 
 
-def exponential(scale=1.0, shape=None, dtype=None, ctx=None, out=None, **kw):
-    ctx, t = _mk(shape, ctx, dtype)
-    return _ret(t.float().exponential_(1.0 / scale).to(t.dtype), ctx, out)
+def poisson(lam=1, shape=None, dtype=None, ctx=None, out=None, **kwargs):
+    return _random_helper("poisson", [lam], shape, dtype, ctx, out, kwargs)
 
 
-def gamma(alpha=1.0, beta=1.0, shape=None, dtype=None, ctx=None, out=None, **kw):
-    ctx, t = _mk(shape, ctx, dtype)
-    d = torch.distributions.Gamma(torch.full_like(t.float(), alpha), torch.full_like(t.float(), 1.0 / beta))
-    return _ret(d.sample().to(t.dtype), ctx, out)
+def exponential(scale=1, shape=None, dtype=None, ctx=None, out=None, **kwargs):
+    # the operators are parameterised by the rate lam = 1/scale (sample_op.h ExponentialParam)
+    return _random_helper("exponential", [1.0 / scale], shape, dtype, ctx, out, kwargs)
 
 
-def poisson(lam=1.0, shape=None, dtype=None, ctx=None, out=None, **kw):
-    ctx, t = _mk(shape, ctx, dtype)
-    return _ret(torch.poisson(torch.full_like(t.float(), lam)).to(t.dtype), ctx, out)
+def gamma(alpha=1, beta=1, shape=None, dtype=None, ctx=None, out=None, **kwargs):
+    return _random_helper("gamma", [alpha, beta], shape, dtype, ctx, out, kwargs)
 
 
-def multinomial(data, shape=1, get_prob=False, dtype="int32", **kw):
-    n = shape if isinstance(shape, int) else int(torch.tensor(shape).prod())
-    p = data._t.float()
-    s = torch.multinomial(p.reshape(-1, p.shape[-1]), n, replacement=True)
-    s = s.reshape(p.shape[:-1] + ((n,) if not (isinstance(shape, int) and shape == 1) else ()))
-    return NDArray(s.to(torch_dtype(dtype)), data._ctx)
+def negative_binomial(k=1, p=1, shape=None, dtype=None, ctx=None, out=None, **kwargs):
+    return _random_helper("negative_binomial", [k, p], shape, dtype, ctx, out, kwargs)
 
 
-def shuffle(data, **kw):
-    return NDArray(data._t[torch.randperm(data.shape[0], device=data._t.device)], data._ctx)
+def generalized_negative_binomial(mu=1, alpha=1, shape=None, dtype=None, ctx=None, out=None, **kwargs):
+    return _random_helper("generalized_negative_binomial", [mu, alpha], shape, dtype, ctx, out, kwargs)
+
+
+def multinomial(data, shape=None, get_prob=False, out=None, dtype="int32", **kwargs):
+    """Samples category indices from the distributions along the last axis of ``data``; with ``get_prob`` also returns the
+    log-likelihood of the samples (for REINFORCE-style gradients)."""
+    from .op import _REG
+    return _REG["_sample_multinomial"](data, shape=shape, get_prob=get_prob, dtype=dtype, out=out)
+
+
+def shuffle(data, **kwargs):
+    from .op import _REG
+    return _REG["_shuffle"](data, **kwargs)
 
 
 def seed(seed_state, ctx="all"):

@@ -114,16 +114,17 @@ def _put_attr(d, k, v, override=True):
 
 
 class _NameManager(object):
-    _tl = threading.local()
+    """Bridge to mx.name.NameManager (per-thread, scoped by ``with``) plus the Gluon block prefix."""
 
     @classmethod
     def get(cls, hint):
-        if not hasattr(cls._tl, "counter"):
-            cls._tl.counter = {}
-        c = cls._tl.counter
-        n = c.get(hint, 0)
-        c[hint] = n + 1
-        return "%s%d" % (hint, n)
+        from ..name import NameManager
+        return NameManager._get_current().get(None, hint)
+
+    @classmethod
+    def resolve(cls, name, hint):
+        from ..name import NameManager
+        return cls.prefix() + NameManager._get_current().get(name, hint)
 
     @classmethod
     def prefix(cls):
@@ -306,6 +307,105 @@ class Symbol(object):
 
     __hash__ = object.__hash__
 
+    def __mod__(self, o):
+        return self._bin(o, "broadcast_mod", "_mod_scalar")
+
+    def __rmod__(self, o):
+        return self._bin(o, "broadcast_mod", "_mod_scalar", rev=True) if isinstance(o, Symbol) else \
+            _make_op("_rmod_scalar", [self], {"scalar": float(o)})
+
+    def __rpow__(self, o):
+        return _make_op("_rpower_scalar", [self], {"scalar": float(o)})
+
+    # ---- things only an NDArray can do (python/mxnet/symbol/symbol.py raises NotImplementedForSymbol for these)
+    def __bool__(self):
+        from ..base import NotImplementedForSymbol
+        raise NotImplementedForSymbol(self.__bool__, "bool")
+
+    __nonzero__ = __bool__
+
+    def _ndarray_only(fname, alias=None):   # noqa: N805
+        def f(self, *args, **kwargs):
+            from ..base import NotImplementedForSymbol
+            raise NotImplementedForSymbol(getattr(Symbol, fname), alias, *args)
+        f.__name__ = fname
+        return f
+
+    __iadd__ = _ndarray_only("__iadd__", "+=")
+    __isub__ = _ndarray_only("__isub__", "-=")
+    __imul__ = _ndarray_only("__imul__", "*=")
+    __idiv__ = _ndarray_only("__idiv__", "/=")
+    __itruediv__ = _ndarray_only("__itruediv__", "/=")
+    __imod__ = _ndarray_only("__imod__", "%=")
+    wait_to_read = _ndarray_only("wait_to_read")
+    asnumpy = _ndarray_only("asnumpy")
+    asscalar = _ndarray_only("asscalar")
+    copy = _ndarray_only("copy")
+    as_in_context = _ndarray_only("as_in_context")
+    detach = _ndarray_only("detach")
+    backward = _ndarray_only("backward")
+    del _ndarray_only
+
+    def astype(self, dtype):
+        return _make_op("Cast", [self], {"dtype": dtype_name(dtype)})
+
+    # ---- composition (symbol.py:375-470 of the reference) ------------------------------------------
+    def __copy__(self):
+        return load_json(self.tojson())
+
+    def __call__(self, *args, **kwargs):
+        """``net2(fc3_data=net1)``: returns a copy of this symbol whose free variables are replaced by other symbols."""
+        s = self.__copy__()
+        s._compose(*args, **kwargs)
+        return s
+
+    def _compose(self, *args, **kwargs):
+        name = kwargs.pop("name", None)
+        if args and kwargs:
+            raise TypeError("compose only accept input Symbols either as positional or keyword arguments, not both")
+        for a in list(args) + list(kwargs.values()):
+            if not isinstance(a, Symbol):
+                raise TypeError("Compose expect `Symbol` as arguments")
+        free = [n for n in self._topo() if n.op is None and not n.is_aux]
+        if args:
+            if len(args) > len(free):
+                raise MXNetError("compose: %d positional arguments for %d free variables" % (len(args), len(free)))
+            repl = {id(n): a._outputs[0] for n, a in zip(free, args)}
+        else:
+            byname = {n.name: n for n in free}
+            unknown = [k for k in kwargs if k not in byname]
+            if unknown:
+                raise MXNetError("compose: no free variable named %s (free variables: %s)" % (unknown, sorted(byname)))
+            repl = {id(byname[k]): v._outputs[0] for k, v in kwargs.items()}
+        for n in self._topo():
+            n.inputs = [repl.get(id(inp), (inp, idx)) if idx == 0 else (inp, idx) for inp, idx in n.inputs]
+        self._outputs = [repl.get(id(n), (n, i)) if i == 0 else (n, i) for n, i in self._outputs]
+        if name and len(self._outputs) == 1:
+            self._outputs[0][0].name = name
+        self._fusion_cache = None
+
+    def debug_str(self):
+        lines = []
+        for n in self._topo():
+            if n.op is None:
+                lines.append("Variable:%s" % n.name)
+            else:
+                lines.append("--------------------\nOp:%s, Name=%s\nInputs:" % (n.op, n.name))
+                lines += ["\targ[%d]=%s(%d)" % (i, inp.name, idx) for i, (inp, idx) in enumerate(n.inputs)]
+                if n.attrs:
+                    lines.append("Attrs:")
+                    lines += ["\t%s=%s" % (k, _attr_str(v)) for k, v in n.attrs.items() if not k.startswith("__kwarg")]
+        return "Symbol Outputs:\n" + "\n".join("\toutput[%d]=%s(%d)" % (i, n.name, idx) for i, (n, idx) in enumerate(self._outputs)) \
+            + "\n" + "\n".join(lines) + "\n"
+
+    def gradient(self, wrt):
+        raise MXNetError("Symbol.gradient is not supported (deprecated in the reference as well: use bind + backward, or autograd)")
+
+    def get_backend_symbol(self, backend):
+        """Graph partitioning for an accelerator backend (MKLDNN / TensorRT in the reference).  The fusion passes of this
+        framework run inside the executor, so the symbol is returned unchanged."""
+        return self
+
     def __getattr__(self, name):
         # method forms: sym.reshape(...), sym.sum(...), ...
         if name.startswith("_"):
@@ -371,16 +471,29 @@ class Symbol(object):
     def infer_shape(self, *args, **kwargs):
         if args:
             kwargs = dict(zip(self.list_arguments(), args))
-        vshape, out_shapes, _, _ = self._infer(kwargs)
+        try:
+            vshape, out_shapes, _, _ = self._infer(kwargs)
+        except MXNetError as e:
+            if "cannot infer shape" not in str(e):
+                raise
+            # not enough information: the reference warns and returns (None, None, None) (symbol.py:1001-1015)
+            import warnings
+            warnings.warn("Cannot decide shape for some arguments: %s" % e, stacklevel=2)
+            return None, None, None
         arg_shapes = [vshape.get(n) for n in self.list_arguments()]
         aux_shapes = [vshape.get(n) for n in self.list_auxiliary_states()]
+        if any(v is None for v in arg_shapes + aux_shapes + list(out_shapes)):
+            return None, None, None
         return arg_shapes, out_shapes, aux_shapes
 
     def infer_shape_partial(self, *args, **kwargs):
+        """Like infer_shape but returns what could be determined; unknown shapes are ``()``."""
         if args:
             kwargs = dict(zip(self.list_arguments(), args))
-        vshape, _out, _, _ = self._infer(kwargs, partial=True)
-        return vshape
+        vshape, out_shapes, _, _ = self._infer(kwargs, partial=True)
+        arg_shapes = [vshape.get(n, ()) for n in self.list_arguments()]
+        aux_shapes = [vshape.get(n, ()) for n in self.list_auxiliary_states()]
+        return arg_shapes, [s if s is not None else () for s in out_shapes], aux_shapes
 
     def infer_type(self, *args, **kwargs):
         if args:
@@ -673,7 +786,7 @@ def ones(shape, dtype=None, **kwargs):
 
 def _make_op(op, inputs, attrs, name=None, hint=None):
     hint = hint or op.lower().lstrip("_")
-    name = _NameManager.prefix() + (name if name else _NameManager.get(hint))
+    name = _NameManager.resolve(name, hint)
     nout = _num_outputs(op, attrs)
     node = _Node(op, name, attrs, [s._outputs[0] for s in inputs], nout)
     from ..attribute import current_attrs
@@ -693,6 +806,8 @@ def _create(op, args, kwargs):
     for k in _HIDDEN_ATTR_KEYS:                      # e.g. Convolution(..., lr_mult=1): node attribute, not an operator argument
         if k in kwargs and not isinstance(kwargs[k], Symbol):
             user_attr[k] = str(kwargs.pop(k))
+    for k in [k for k in kwargs if k.startswith("__") and k.endswith("__") and not isinstance(kwargs[k], Symbol)]:
+        user_attr[k] = str(kwargs.pop(k))            # e.g. Activation(..., __layout__='NCHW')
     from ..attribute import current_attrs
     node_attrs = {}
     for k, v in user_attr.items():
@@ -703,7 +818,7 @@ def _create(op, args, kwargs):
     sym_kwargs = {k: v for k, v in kwargs.items() if isinstance(v, Symbol)}
     attrs = {k: v for k, v in kwargs.items() if not isinstance(v, Symbol) and v is not None}
     hint = op.lower().lstrip("_")
-    node_name = _NameManager.prefix() + (name if name else _NameManager.get(hint))
+    node_name = _NameManager.resolve(name, hint)
     inputs = [a for a in args if isinstance(a, Symbol)]
     pos_attrs = [a for a in args if not isinstance(a, Symbol) and a is not None]
     if pos_attrs:
@@ -733,8 +848,7 @@ def _create(op, args, kwargs):
                     continue
                 if aname == "gamma" and op == "LeakyReLU" and attrs.get("act_type", "leaky") != "prelu":
                     continue
-                if aname == "data":
-                    raise MXNetError("%s: missing data input" % op)
+                # inputs that are not given become free variables "<node>_<argument>" (to be composed later)
                 s = var("%s_%s" % (node_name, aname))
                 for k, v in inherit.items():
                     s._outputs[0][0].var_attrs.setdefault(k, v)
@@ -747,6 +861,15 @@ def _create(op, args, kwargs):
         order = inputs + [sym_kwargs[k] for k in sym_kwargs]
         if sym_kwargs:
             attrs["__kwarg_inputs__"] = tuple(sym_kwargs.keys())
+        if not order and not op.startswith(("_random_", "_zeros", "_ones", "_full", "_arange", "_eye")):
+            import inspect
+            fn = _ndop.get(op)
+            try:
+                first = list(inspect.signature(fn).parameters.values())[0] if fn is not None else None
+            except (TypeError, ValueError, IndexError):
+                first = None
+            if first is not None and first.name in ("data", "lhs", "a") and first.default is inspect.Parameter.empty:
+                order = [var("%s_%s" % (node_name, first.name))]
     nout = _num_outputs(op, attrs)
     node = _Node(op, node_name, attrs, [s._outputs[0] for s in order], nout)
     node.var_attrs.update(node_attrs)
