@@ -24,7 +24,7 @@ _LAZY = {
     "kvstore": ".kvstore", "kv": ".kvstore", "metric": ".metric", "callback": ".callback", "io": ".io",
     "model": ".model", "module": ".module", "mod": ".module", "gluon": ".gluon", "symbol": ".symbol", "sym": ".symbol",
     "profiler": ".profiler", "monitor": ".monitor", "mon": ".monitor", "random": ".random", "rnd": ".random",
-    "recordio": ".recordio", "image": ".image", "test_utils": ".test_utils", "storage": ".storage",
+    "recordio": ".recordio", "image": ".image", "img": ".image", "test_utils": ".test_utils", "storage": ".storage",
     "parallel": ".parallel", "models": ".models", "ops": ".ops", "executor": ".executor", "rtc": ".rtc",
     "kvstore_server": ".kvstore_server", "contrib": ".contrib", "visualization": ".visualization", "viz": ".visualization",
     "name": ".name", "attribute": ".attribute", "operator": ".operator", "rnn": ".rnn", "log": ".log",

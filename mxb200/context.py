@@ -56,6 +56,16 @@ class Context(object):
         Context._default.ctx = self._old_ctx
 
 
+class _DefaultCtx(object):
+    """``Context.default_ctx``: the reference's (deprecated) class property for the current default context."""
+
+    def __get__(self, obj, owner):
+        return current_context()
+
+
+Context.default_ctx = _DefaultCtx()
+
+
 def cpu(device_id=0):
     return Context("cpu", device_id)
 

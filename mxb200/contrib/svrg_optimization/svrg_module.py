@@ -7,6 +7,7 @@ import time
 from ... import metric as _metric
 from ...module.module import Module
 from ...ndarray import zeros_like
+from .svrg_optimizer import _AssignmentOptimizer, _SVRGOptimizer  # noqa: F401  (reference module layout)
 
 
 class SVRGModule(Module):

@@ -270,6 +270,14 @@ class Parameter(object):
             raise RuntimeError("Parameter '%s' has not been initialized" % self.name)
         return self._ctx_list
 
+    def _set_trainer(self, trainer):
+        """A row_sparse parameter can only be managed by one Trainer (parameter.py:188-199 of the reference)."""
+        if getattr(self, "_stype", "default") != "default" and getattr(self, "_trainer", None) and trainer \
+                and self._trainer is not trainer:
+            raise RuntimeError("Failed to set the trainer for Parameter '%s' because it was already set. More than one "
+                               "trainers for a %s Parameter is not supported." % (self.name, self._stype))
+        self._trainer = trainer
+
     def zero_grad(self):
         if self._grad is None:
             return

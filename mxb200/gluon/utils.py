@@ -50,11 +50,19 @@ def split_and_load(data, ctx_list, batch_axis=0, even_split=True):
     return [i.as_in_context(ctx) for i, ctx in zip(slices, ctx_list)]
 
 
-def clip_global_norm(arrays, max_norm):
-    """Rescale arrays so that the sum of their 2-norms is at most max_norm (utils.py:120-150)."""
+def clip_global_norm(arrays, max_norm, check_isfinite=True):
+    """Rescale arrays so that the sum of their 2-norms is at most max_norm (utils.py:120-150).  With
+    ``check_isfinite=False`` no host synchronisation happens and the norm is returned as an NDArray."""
     assert len(arrays) > 0
     dev = arrays[0]._t.device
     total = torch.sqrt(sum((a._t.float() ** 2).sum().to(dev) for a in arrays))
+    if not check_isfinite:
+        scale = torch.clamp(max_norm / (total + 1e-8), max=1.0)
+        with torch.no_grad():
+            for a in arrays:
+                a._t.mul_(scale.to(a._t.device, a._t.dtype))
+        from ..ndarray import NDArray
+        return NDArray(total.reshape(1), arrays[0].context)
     total_f = float(total)
     if not np.isfinite(total_f):
         import warnings
