@@ -91,16 +91,18 @@ def _register_leaf(arr):
     if arr._grad_hook is not None:
         arr._grad_hook.remove()
         arr._grad_hook = None
-    if arr._grad_req != "write":
+    if arr._grad_req not in ("write", "add"):
         return
     ref = weakref.ref(arr)
     t = arr._t
+    write = arr._grad_req == "write"
 
     def hook(g):
         a = ref()
         if a is not None and a._bw_epoch != _bw_epoch[0]:
             a._bw_epoch = _bw_epoch[0]
-            if t.grad is not None:
+            t._mx_fresh_grad = True          # a gradient arrived in this backward pass (NDArray._fresh_grad)
+            if write and t.grad is not None:
                 t.grad.zero_()
         return g
 
@@ -127,8 +129,17 @@ def backward(heads, head_grads=None, retain_graph=False, train_mode=True):
         if not isinstance(head_grads, (list, tuple)):
             head_grads = [head_grads]
         gs = [torch.ones_like(t) if g is None else g._t for t, g in zip(ts, head_grads)]
+    for t in ts:
+        if getattr(t, "_mx_graph_freed", False):
+            from .base import MXNetError
+            raise MXNetError("the computation graph of this array has already been freed by a previous backward(); pass "
+                             "retain_graph=True to the first call to differentiate it again")
     _bw_epoch[0] += 1
     torch.autograd.backward(ts, gs, retain_graph=retain_graph)
+    if not retain_graph:
+        for t in ts:
+            if t.grad_fn is not None:
+                t._mx_graph_freed = True
 
 
 def grad(heads, variables, head_grads=None, retain_graph=None, create_graph=False, train_mode=True):

@@ -2,6 +2,7 @@
 import sys as _sys
 import types as _types
 
+from .ndarray import from_dlpack, to_dlpack_for_read, to_dlpack_for_write  # noqa: F401
 from .ndarray import (NDArray, array, zeros, ones, empty, full, arange, zeros_like, ones_like, from_torch, waitall,
                       concatenate, moveaxis)
 from . import op, sparse, random, serialization
@@ -11,6 +12,7 @@ from .op import *  # noqa: F401,F403
 from . import op_extra as _op_extra  # noqa: F401  (registers the long tail into _REG)
 from . import op_legacy as _op_legacy  # noqa: F401  (legacy aliases + deformable ops)
 from .op import _REG as _OPS
+from .op import CachedOp  # noqa: F401
 
 import functools as _functools
 

@@ -76,6 +76,22 @@ class NDArray(object):
         return self._t
 
     @property
+    def _fresh_grad(self):
+        """True when a backward pass has written this array's gradient since the flag was last cleared (the Trainer's
+        stale-gradient check, ndarray.py:_fresh_grad of the reference)."""
+        return bool(getattr(self._t, "_mx_fresh_grad", False))
+
+    @_fresh_grad.setter
+    def _fresh_grad(self, state):
+        self._t._mx_fresh_grad = bool(state)
+
+    def to_dlpack_for_read(self):
+        from torch.utils import dlpack
+        return dlpack.to_dlpack(self._t.detach())
+
+    to_dlpack_for_write = to_dlpack_for_read
+
+    @property
     def shape(self):
         return tuple(self._t.shape)
 
@@ -222,8 +238,12 @@ class NDArray(object):
         key = _unwrap_key(key)
         with torch.no_grad():
             v = _unwrap(value)
+            if isinstance(v, (list, tuple)):
+                v = np.asarray(v)
+            if isinstance(v, np.generic):
+                v = v.item()
             if isinstance(v, np.ndarray):
-                v = torch.from_numpy(v)
+                v = torch.from_numpy(np.ascontiguousarray(v))
             if isinstance(v, torch.Tensor):
                 v = v.to(device=self._t.device, dtype=self._t.dtype)
             if isinstance(key, slice) and key == slice(None):
@@ -240,6 +260,9 @@ class NDArray(object):
             shape = tuple(shape[0])
         if not shape:
             shape = tuple(kwargs["shape"])
+        if kwargs.get("reverse", False):
+            from . import op as _o
+            return _o.reshape(self, shape=shape, reverse=True)
         shape = _mx_reshape(self.shape, shape)
         return _op(lambda t: t.reshape(shape), self)
 
@@ -399,10 +422,10 @@ class NDArray(object):
     __rmul__ = __mul__
 
     def __truediv__(self, o):
-        return _binop(torch.div, self, o)
+        return _binop(_mx_div, self, o)
 
     def __rtruediv__(self, o):
-        return _binop(lambda a, b: torch.div(b, a), self, o)
+        return _binop(lambda a, b: _mx_div(b, a), self, o)
 
     __div__ = __truediv__
     __rdiv__ = __rtruediv__
@@ -440,7 +463,7 @@ class NDArray(object):
         return self._inplace(lambda t, v: t.mul_(v), o)
 
     def __itruediv__(self, o):
-        return self._inplace(lambda t, v: t.div_(v), o)
+        return self._inplace(lambda t, v: t.div_(v) if t.is_floating_point() else t.copy_(_mx_div(t, v)), o)
 
     __idiv__ = __itruediv__
 
@@ -497,8 +520,33 @@ def _unwrap_key(key):
     return key
 
 
-def _mx_reshape(src, shape):
-    """MXNet reshape special codes: 0 copy dim, -1 infer, -2 copy rest, -3 merge two, -4 split."""
+def _mx_div(a, b):
+    """Division keeps the array's dtype: integer arrays divide like C (truncation), as the reference kernels do."""
+    if isinstance(a, torch.Tensor) and not a.is_floating_point() and not (isinstance(b, torch.Tensor) and b.is_floating_point()) \
+            and not isinstance(b, float):
+        return torch.div(a, b, rounding_mode="trunc")
+    if isinstance(a, torch.Tensor) and not a.is_floating_point() and isinstance(b, float):
+        return torch.div(a, b, rounding_mode="trunc").to(a.dtype)
+    return torch.div(a, b)
+
+
+def _mx_reshape(src, shape, reverse=False):
+    """MXNet reshape special codes: 0 copy dim, -1 infer, -2 copy rest, -3 merge two, -4 split.  ``reverse``: the codes
+    are matched against the source dimensions from the right (matrix_op-inl.h ReshapeParam.reverse)."""
+    if reverse:
+        shape = list(shape)
+        # -4 takes its two arguments to the right: keep the triple together while reversing
+        groups, j = [], 0
+        while j < len(shape):
+            if shape[j] == -4:
+                groups.append([shape[j], shape[j + 2], shape[j + 1]])
+                j += 3
+            else:
+                groups.append([shape[j]])
+                j += 1
+        rshape = [v for g in reversed(groups) for v in g]
+        out = _mx_reshape(tuple(reversed(src)), rshape, reverse=False)
+        return tuple(reversed(out))
     if all(isinstance(s, (int, np.integer)) and s > 0 or s == -1 for s in shape):
         return tuple(int(s) for s in shape)
     out, i, j = [], 0, 0
@@ -583,8 +631,8 @@ def array(source, ctx=None, dtype=None):
             dtype = np.float32
     td = torch_dtype(dtype)
     t = torch.from_numpy(np.array(a, copy=True, order="C")).to(td)   # always own the memory (never alias numpy)
-    if t.dim() == 0:
-        t = t.reshape(1)
+    if t.dim() == 0 and not isinstance(source, np.ndarray):
+        t = t.reshape(1)        # python scalars become 1-element arrays; a 0-d numpy array keeps shape ()
     return NDArray(_pin_if(t.to(ctx.torch_device), ctx), ctx)
 
 
@@ -599,18 +647,48 @@ def _new(fn, shape, ctx, dtype, **kw):
     return NDArray(t, ctx)
 
 
-def zeros(shape, ctx=None, dtype=None, stype=None, **kw):
+def _into(out, res):
+    if out is None:
+        return res
+    out[:] = res
+    return out
+
+
+def zeros(shape, ctx=None, dtype=None, stype=None, out=None, **kw):
     if stype in ("row_sparse", "csr"):
         from . import sparse
         return sparse.zeros(stype, shape, ctx=ctx, dtype=dtype)
+    if out is not None:
+        out[:] = 0
+        return out
     return _new(torch.zeros, shape, ctx, dtype)
 
 
-def ones(shape, ctx=None, dtype=None, **kw):
+def ones(shape, ctx=None, dtype=None, out=None, **kw):
+    if out is not None:
+        out[:] = 1
+        return out
     return _new(torch.ones, shape, ctx, dtype)
 
 
-def empty(shape, ctx=None, dtype=None):
+def from_dlpack(capsule):
+    """NDArray sharing memory with a DLPack capsule (or any object with ``__dlpack__``)."""
+    from torch.utils import dlpack
+    return NDArray(dlpack.from_dlpack(capsule))
+
+
+def to_dlpack_for_read(data):
+    return data.to_dlpack_for_read()
+
+
+def to_dlpack_for_write(data):
+    return data.to_dlpack_for_write()
+
+
+def empty(shape, ctx=None, dtype=None, stype=None):
+    if stype not in (None, "default"):
+        from . import sparse as _sp
+        return _sp.zeros(stype, shape, ctx=ctx, dtype=dtype)
     return _new(torch.empty, shape, ctx, dtype)
 
 
@@ -646,7 +724,18 @@ def concatenate(arrays, axis=0, always_copy=True):
 
 
 def moveaxis(a, source, destination):
-    return _op(lambda t: torch.movedim(t, source, destination), a)
+    """Move one axis to a new position (ndarray.py:moveaxis of the reference: list pop / insert, so a destination past the
+    end means "last")."""
+    axes = list(range(a.ndim))
+    try:
+        axes.pop(source)
+    except IndexError:
+        raise ValueError("Source should verify 0 <= source < tensor.ndim. Got %d." % source)
+    try:
+        axes.insert(destination, source)
+    except IndexError:
+        raise ValueError("Destination should verify 0 <= destination < tensor.ndim. Got %d." % destination)
+    return _op(lambda t: t.permute(*axes), a)
 
 
 def waitall():

@@ -204,7 +204,7 @@ def _reduce(name, fn):
             if ax is None:
                 r = fn(t)
                 return r.reshape((1,) * t.dim()) if keepdims else r.reshape(1)
-            return fn(t, dim=ax, keepdim=keepdims)
+            return fn(t, dim=ax, keepdim=bool(keepdims))
         return _out(_op(g, data), out)
     f.__name__ = name
     _REG[name] = f
@@ -247,7 +247,9 @@ def argmax_channel(data, out=None):
 @register
 def topk(data, axis=-1, k=1, ret_typ="indices", is_ascend=False, dtype="float32", out=None):
     def g(t):
-        v, i = torch.topk(t, k, dim=axis, largest=not is_ascend)
+        if axis is None:
+            t = t.reshape(-1)
+        v, i = torch.topk(t, k, dim=-1 if axis is None else axis, largest=not is_ascend)
         i = i.to(torch_dtype(dtype))
         if ret_typ == "indices":
             return i
@@ -277,6 +279,10 @@ def argsort(data, axis=-1, is_ascend=True, dtype="float32", out=None):
 
 @register
 def reshape(data, shape, reverse=False, out=None):
+    if reverse in (True, 1, "1", "True", "true"):
+        from .ndarray import _mx_reshape
+        tgt = _mx_reshape(data.shape, tuple(shape), reverse=True)
+        return _out(_op(lambda t: t.reshape(tgt), data), out)
     return _out(data.reshape(shape), out)
 
 
@@ -408,8 +414,19 @@ def broadcast_to(data, shape, out=None):
 
 
 @register
-def broadcast_like(lhs, rhs):
-    return broadcast_to(lhs, rhs.shape)
+def broadcast_like(lhs, rhs, lhs_axes=None, rhs_axes=None, out=None):
+    """Broadcast lhs to the shape of rhs; with ``lhs_axes`` / ``rhs_axes`` only those axes of lhs take the sizes of the
+    given axes of rhs (broadcast_reduce_op_value.cc BroadcastLikeParam)."""
+    if lhs_axes is None and rhs_axes is None:
+        return _out(broadcast_to(lhs, rhs.shape), out)
+    la = [lhs_axes] if isinstance(lhs_axes, int) else list(lhs_axes)
+    ra = [rhs_axes] if isinstance(rhs_axes, int) else list(rhs_axes)
+    if len(la) != len(ra) or not la:
+        raise MXNetError("broadcast_like: lhs_axes and rhs_axes must be non-empty and of equal length")
+    shp = list(lhs.shape)
+    for a, b in zip(la, ra):
+        shp[a % lhs.ndim] = rhs.shape[b % rhs.ndim]
+    return _out(broadcast_to(lhs, tuple(shp)), out)
 
 
 @register
@@ -1348,3 +1365,55 @@ for _name, _ns, _lazy in (("sgd_update", 0, "flag"), ("sgd_mom_update", 1, "flag
         _REG[_name] = _sparse_aware_update(_name, _ns, _lazy)
         if _name in globals():
             globals()[_name] = _REG[_name]
+
+
+# ----------------------------------------------------------------------------- pre-NNVM helpers still exported by mx.nd
+@register
+def onehot_encode(indices, out):
+    """out[i, indices[i]] = 1, everything else 0 (legacy ndarray function, ndarray.py:onehot_encode)."""
+    with torch.no_grad():
+        o = out._t
+        o.zero_()
+        o.scatter_(1, indices._t.long().reshape(-1, 1), 1.0)
+    return out
+
+
+@register
+def choose_element_0index(lhs, rhs, out=None):
+    """out[i] = lhs[i, rhs[i]]."""
+    return _out(_op(lambda a, idx: a.gather(1, idx.long().reshape(-1, 1)).reshape(-1), lhs, rhs), out)
+
+
+@register
+def fill_element_0index(lhs, mhs, rhs, out=None):
+    """Copy of lhs with out[i, rhs[i]] = mhs[i]."""
+    def g(a, v, idx):
+        r = a.clone()
+        r.scatter_(1, idx.long().reshape(-1, 1), v.reshape(-1, 1).to(a.dtype))
+        return r
+    return _out(_op(g, lhs, mhs, rhs), out)
+
+
+class CachedOp(object):
+    """Callable compiled from a Symbol (ndarray CachedOp of the reference, src/imperative/cached_op.cc): inputs are bound
+    positionally in ``sym.list_inputs()`` order.  Here a thin wrapper over the graph executor's evaluation loop, so the
+    BatchNorm(+add)+ReLU grouping of the executor applies to hybridized Gluon blocks that go through it."""
+
+    def __init__(self, sym, flags=()):
+        self._sym = sym
+        self._names = sym.list_inputs()
+        self._flags = dict(flags)
+
+    def __call__(self, *args, **kwargs):
+        out = kwargs.pop("out", None)
+        if kwargs:
+            raise TypeError("CachedOp.__call__ got unexpected keyword argument(s): %s" % ", ".join(kwargs))
+        if len(args) != len(self._names):
+            raise MXNetError("CachedOp expects %d inputs (%s), got %d" % (len(self._names), self._names, len(args)))
+        res = self._sym.eval_nd(dict(zip(self._names, args)))
+        if out is not None:
+            outs = out if isinstance(out, (list, tuple)) else [out]
+            for o, r in zip(outs, res):
+                o[:] = r
+            return out
+        return res[0] if len(res) == 1 else res

@@ -283,7 +283,14 @@ for _n in ("potri", "trmm", "gelqf", "syevd"):
 
 
 # ----------------------------------------------------------------------------- random samplers (random/sample_op.cc, multisample_op.cc)
+_RAND_DEFAULTS = {"uniform": (("low", 0.0), ("high", 1.0)), "normal": (("loc", 0.0), ("scale", 1.0)), "exponential": (("lam", 1.0),),
+                  "gamma": (("alpha", 1.0), ("beta", 1.0)), "poisson": (("lam", 1.0),), "negative_binomial": (("k", 1.0), ("p", 1.0)),
+                  "generalized_negative_binomial": (("mu", 1.0), ("alpha", 1.0))}
+
+
 def _rand(name, draw):
+    spec = _RAND_DEFAULTS[name.split("_", 2)[2]]
+
     def f(*params, **kw):
         shape = kw.pop("shape", None)
         dtype = kw.pop("dtype", None) or "float32"
@@ -296,7 +303,10 @@ def _rand(name, draw):
             full = tuple(ps[0].shape) + shp
             ex = [p.reshape(tuple(p.shape) + (1,) * len(shp)).expand(full) for p in ps]
             return _out(NDArray(draw(full, ex, ps[0].device).to(torch_dtype(dtype)), params[0].context), out)
-        vals = list(params) + [kw[k] for k in list(kw.keys())]
+        # scalar parameters: positional first, then by name, then the distribution's defaults (sample_op.h *Param structs)
+        vals = list(params)
+        for pname, default in spec[len(vals):]:
+            vals.append(kw.pop(pname, default))
         ex = [torch.full(shp or (1,), float(v), device=dev) for v in vals]
         return _out(NDArray(draw(shp or (1,), ex, dev).to(torch_dtype(dtype)), c), out)
     f.__name__ = name
