@@ -237,14 +237,16 @@ class Block(object):
         self._children[name] = block
 
     def register_forward_pre_hook(self, hook):
-        key = len(self._forward_pre_hooks)
-        self._forward_pre_hooks[key] = hook
-        return key
+        """hook(block, inputs) runs before forward; returns a handle whose ``detach()`` removes it (block.py:356-386)."""
+        handle = HookHandle()
+        handle.attach(self._forward_pre_hooks, hook)
+        return handle
 
     def register_forward_hook(self, hook):
-        key = len(self._forward_hooks)
-        self._forward_hooks[key] = hook
-        return key
+        """hook(block, inputs, outputs) runs after forward; returns a detachable handle."""
+        handle = HookHandle()
+        handle.attach(self._forward_hooks, hook)
+        return handle
 
     def apply(self, fn):
         for cld in self._children.values():
@@ -280,6 +282,7 @@ class Block(object):
     def summary(self, *inputs):
         summary = OrderedDict()
         hooks = []
+        assert not getattr(self, "_active", False), "\"{}\" must not be hybridized to print summary.".format(self.name)
 
         def _register(block):
             def hook(blk, _inp, outputs):
@@ -301,8 +304,36 @@ class Block(object):
             lines.append("Total params (incl. shared/nested): %d" % total)
             print("\n".join(lines))
         finally:
-            for blk, key in hooks:
-                blk._forward_hooks.pop(key, None)
+            for _blk, handle in hooks:
+                handle.detach()
+
+
+class HookHandle(object):
+    """Removable registration of a forward (pre-)hook (reference: python/mxnet/gluon/utils.py HookHandle)."""
+    _next_id = [0]
+
+    def __init__(self):
+        self._hooks_dict_ref = None
+        self._id = None
+
+    def attach(self, hooks_dict, hook):
+        import weakref
+        assert not self._hooks_dict_ref, "The same handle cannot be attached twice."
+        HookHandle._next_id[0] += 1
+        self._id = HookHandle._next_id[0]
+        hooks_dict[self._id] = hook
+        self._hooks_dict_ref = weakref.ref(hooks_dict)
+
+    def detach(self):
+        hooks_dict = self._hooks_dict_ref() if self._hooks_dict_ref else None
+        if hooks_dict is not None and self._id in hooks_dict:
+            del hooks_dict[self._id]
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, ptype, value, trace):
+        self.detach()
 
 
 class HybridBlock(Block):

@@ -49,6 +49,11 @@ class Parameter(object):
         self.wd_mult = wd_mult
         self.grad_req = grad_req
         self.init = init
+        valid = ("default", "row_sparse", "csr")
+        assert grad_stype in valid, "grad_stype for Parameter '%s' must be one of 'default', 'row_sparse', or 'csr', " \
+                                    "but got '%s'" % (name, grad_stype)
+        assert stype in valid, "stype for Parameter '%s' must be one of 'default', 'row_sparse', or 'csr', but got '%s'" \
+                               % (name, stype)
         self._stype = stype
         self._grad_stype = grad_stype
         self._fresh_grad = False
@@ -313,9 +318,14 @@ class Constant(Parameter):
         class Init(initializer.Initializer):
             def _init_weight(self2, _, arr):
                 arr[:] = value
+
+            def dumps(self2):
+                import json
+                return json.dumps([init_name.lower(), {}])
         init_name = "Constant_{}_{}".format(name, id(self))
+        Init.__name__ = init_name
         initializer._REG[init_name.lower()] = Init
-        super(Constant, self).__init__(name, grad_req="null", shape=value.shape, dtype=value.dtype, init=Init())
+        super(Constant, self).__init__(name, grad_req="null", shape=value.shape, dtype=value.dtype, init=init_name)
 
 
 class ParameterDict(object):

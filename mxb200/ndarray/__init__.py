@@ -72,6 +72,11 @@ _sys.modules[_internal.__name__] = _internal
 _sys.modules[image.__name__] = image
 for _k in ("negative_binomial", "generalized_negative_binomial"):
     pass
+def eye(N, M=0, k=0, ctx=None, dtype=None, **kwargs):
+    """2-D array with ones on the k-th diagonal (ndarray.py:eye of the reference)."""
+    return _OPS["_eye"](N=N, M=M, k=k, ctx=ctx, dtype=dtype or "float32", **kwargs)
+
+
 # legacy top-level sampler names (mx.nd.uniform / mx.nd.normal, python/mxnet/ndarray/random.py re-exports)
 uniform, normal = random.uniform, random.normal
 

@@ -248,6 +248,8 @@ class NDArray(object):
                 v = v.to(device=self._t.device, dtype=self._t.dtype)
             if isinstance(key, slice) and key == slice(None):
                 if isinstance(v, torch.Tensor):
+                    if v.numel() == self._t.numel() and v.shape != self._t.shape:
+                        v = v.reshape(self._t.shape)          # e.g. shape () <- (1,)
                     self._t.copy_(v.expand_as(self._t) if v.shape != self._t.shape else v)
                 else:
                     self._t.fill_(v)
@@ -278,7 +280,9 @@ class NDArray(object):
     def squeeze(self, axis=None):
         return _op(lambda t: t.squeeze() if axis is None else t.squeeze(axis), self)
 
-    def transpose(self, *axes):
+    def transpose(self, *axes, **kwargs):
+        if "axes" in kwargs:
+            axes = (kwargs["axes"],) if kwargs["axes"] is not None else ()
         if len(axes) == 1 and isinstance(axes[0], (list, tuple)):
             axes = tuple(axes[0])
         if not axes:

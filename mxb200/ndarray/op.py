@@ -231,12 +231,12 @@ def norm(data, ord=2, axis=None, keepdims=False, out=None):
 
 @register
 def argmax(data, axis=None, keepdims=False, out=None):
-    return _out(_op(lambda t: torch.argmax(t, dim=axis, keepdim=keepdims).to(torch.float32), data), out)
+    return _out(_op(lambda t: torch.argmax(t, dim=axis, keepdim=bool(keepdims)).to(torch.float32), data), out)
 
 
 @register
 def argmin(data, axis=None, keepdims=False, out=None):
-    return _out(_op(lambda t: torch.argmin(t, dim=axis, keepdim=keepdims).to(torch.float32), data), out)
+    return _out(_op(lambda t: torch.argmin(t, dim=axis, keepdim=bool(keepdims)).to(torch.float32), data), out)
 
 
 @register
@@ -258,8 +258,8 @@ def topk(data, axis=-1, k=1, ret_typ="indices", is_ascend=False, dtype="float32"
         if ret_typ == "both":
             return [v, i]
         m = torch.zeros_like(t)
-        m.scatter_(axis, i.long(), 1)
-        return m
+        m.scatter_(-1 if axis is None else axis, i.long(), 1)
+        return m.reshape(data.shape) if axis is None else m
     return _out(_op(g, data), out)
 
 
@@ -835,9 +835,21 @@ def LRN(data, alpha=1e-4, beta=0.75, knorm=2.0, nsize=5, out=None):
 
 
 @register
-def Dropout(data, p=0.5, mode="training", axes=(), out=None):
+def Dropout(data, p=0.5, mode="training", axes=(), out=None, **kw):
+    """Inverted dropout; ``axes``: the mask is shared (broadcast) along these axes -- variational dropout
+    (src/operator/nn/dropout-inl.h:64-80)."""
     train = _ag.is_training() or mode == "always"
-    return _out(_op(lambda x: F.dropout(x, p, training=train), data), out)
+    axes_ = tuple(axes) if isinstance(axes, (list, tuple)) else ((axes,) if axes not in (None, ()) else ())
+
+    def g(x):
+        if not train or p == 0:
+            return x
+        if not axes_:
+            return F.dropout(x, p, training=True)
+        shp = [1 if (i in axes_ or i - x.dim() in axes_) else s for i, s in enumerate(x.shape)]
+        mask = (torch.rand(shp, device=x.device) >= p).to(x.dtype) / (1.0 - p)
+        return x * mask
+    return _out(_op(g, data), out)
 
 
 @register
