@@ -104,8 +104,10 @@ class Executor(object):
                     name, str(self.arg_dict[name].shape), str(array.shape)))
         feed = dict(self.arg_dict)
         feed.update(self.aux_dict)
-        if is_train:
-            with autograd.record(train_mode=True):
+        if is_train or self.grad_dict:
+            # an executor bound with gradient arrays can always run backward(), also after forward(is_train=False): the
+            # mode only selects training / inference behaviour of the operators (graph_executor.cc RunOps)
+            with autograd.record(train_mode=bool(is_train)):
                 self.outputs = self._symbol.eval_nd(feed, self._group2ctx)
         else:
             with autograd.pause(train_mode=False):
@@ -161,8 +163,20 @@ class Executor(object):
         vshape, _o, vdtype, _ = self._symbol._infer(kwargs)
         new_args, new_aux = {}, {}
         for n, a in self.arg_dict.items():
-            shp = vshape.get(n, a.shape)
-            new_args[n] = a if tuple(shp) == a.shape else nd.zeros(shp, ctx=self._ctx, dtype=a.dtype)
+            shp = tuple(vshape.get(n, a.shape))
+            if shp == a.shape:
+                new_args[n] = a
+                continue
+            size = int(np.prod(shp)) if shp else 1
+            if size <= a.size and a._t.is_contiguous():
+                # smaller view of the SAME memory, like the reference (graph_executor.cc Reshape shares the arrays)
+                new_args[n] = NDArray(a._t.detach().reshape(-1)[:size].view(shp), a.context)
+            elif size > a.size and not allow_up_sizing:
+                raise AssertionError("New shape of arg: %s is larger than original. First making a big executor and then down "
+                                     "sizing it is more efficient than the reverse. If you really want to up size, set "
+                                     "allow_up_sizing=True to enable allocation of new arrays." % n)
+            else:
+                new_args[n] = nd.zeros(shp, ctx=self._ctx, dtype=a.dtype)
         for n, a in self.aux_dict.items():
             new_aux[n] = a
         return Executor(self._symbol, self._ctx, new_args, None, self._grad_req, new_aux, self._group2ctx)

@@ -12,7 +12,8 @@ from .. import ndarray as nd
 from ..context import cpu
 from ..model import BatchEndParam
 from ..initializer import Uniform
-from ..io import DataDesc
+from ..io import DataDesc, DataBatch, DataIter
+from ..ndarray import NDArray
 from ..base import getenv
 
 __all__ = ["BaseModule"]
@@ -115,6 +116,15 @@ class BaseModule(object):
     def predict(self, eval_data, num_batch=None, merge_batches=True, reset=True, always_output_list=False,
                 sparse_row_id_fn=None):
         assert self.binded and self.params_initialized
+        if isinstance(eval_data, (NDArray, np.ndarray)):
+            # a bare array is one data batch stream (base_module.py:330-340 of the reference)
+            from ..io import NDArrayIter
+            if isinstance(eval_data, np.ndarray):
+                eval_data = nd.array(eval_data)
+            self.forward(DataBatch([eval_data]), is_train=False)
+            return self.get_outputs()[0]
+        if not isinstance(eval_data, DataIter):
+            raise ValueError("eval_data must be of type NDArray or DataIter")
         if reset:
             eval_data.reset()
         output_list = []

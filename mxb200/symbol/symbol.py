@@ -677,7 +677,7 @@ def _tuple_attr(v):
 
 def _attr_str(v):
     if isinstance(v, (tuple, list)):
-        return "(" + ", ".join(str(x) for x in v) + ")"
+        return "(" + ", ".join(str(x) for x in v) + ("," if len(v) == 1 else "") + ")"
     return str(v)
 
 
@@ -741,7 +741,7 @@ def var(name, attr=None, shape=None, lr_mult=None, wd_mult=None, dtype=None, ini
     n = _Node(None, name)
     a = dict(attr or {})
     if shape is not None:
-        a["__shape__"] = tuple(shape)
+        a["__shape__"] = (int(shape),) if isinstance(shape, (int, np.integer)) else tuple(shape)
     if lr_mult is not None:
         a["__lr_mult__"] = lr_mult
     if wd_mult is not None:
