@@ -315,12 +315,14 @@ class NDArrayIter(DataIter):
 
     def hard_reset(self):
         self.cursor = -self.batch_size
+        self._carry = 0
 
     def reset(self):
-        if self.last_batch_handle == "roll_over" and self.cursor > self.num_data:
-            self.cursor = -self.batch_size + (self.cursor % self.num_data) % self.batch_size
-        else:
-            self.cursor = -self.batch_size
+        """'roll_over': the incomplete tail of the finished epoch is not emitted; it becomes the head of the first batch of
+        the next epoch (io.py NDArrayIter of the reference)."""
+        carry = getattr(self, "_carry", 0)
+        self._carry = 0
+        self.cursor = -self.batch_size - carry if self.last_batch_handle == "roll_over" else -self.batch_size
 
     def iter_next(self):
         self.cursor += self.batch_size
@@ -328,11 +330,17 @@ class NDArrayIter(DataIter):
 
     def next(self):
         if self.iter_next():
+            if self.last_batch_handle == "roll_over" and self.cursor + self.batch_size > self.num_data:
+                self._carry = self.num_data - self.cursor       # keep the tail for the next epoch
+                raise StopIteration
             return DataBatch(data=self.getdata(), label=self.getlabel(), pad=self.getpad(), index=None)
         raise StopIteration
 
     def _getdata(self, data_source):
         assert self.cursor < self.num_data, "DataIter needs reset."
+        if self.cursor < 0:          # first batch after a roll-over: tail of the previous epoch + head of this one
+            return [NDArray(torch.cat([x._t[self.cursor:], x._t[:self.cursor + self.batch_size]]), x.context)
+                    for _, x in data_source]
         if self.cursor + self.batch_size <= self.num_data:
             out = []
             for _, x in data_source:

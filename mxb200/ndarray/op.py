@@ -204,6 +204,11 @@ def _reduce(name, fn):
             if ax is None:
                 r = fn(t)
                 return r.reshape((1,) * t.dim()) if keepdims else r.reshape(1)
+            if isinstance(ax, tuple) and fn in (torch.prod,):      # torch.prod takes one axis at a time
+                r = t
+                for a in sorted((a % t.dim() for a in ax), reverse=True):
+                    r = fn(r, dim=a, keepdim=bool(keepdims))
+                return r
             return fn(t, dim=ax, keepdim=bool(keepdims))
         return _out(_op(g, data), out)
     f.__name__ = name

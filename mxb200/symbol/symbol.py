@@ -223,9 +223,12 @@ class Symbol(object):
         return Symbol(outs)
 
     def get_children(self):
-        if len(self._outputs) != 1:
-            return None
-        inputs = self._outputs[0][0].inputs
+        """Inputs of the output node(s) as a grouped symbol; None for variables (symbol.py:get_children)."""
+        inputs, seen = [], set()
+        for n, _ in self._outputs:
+            if id(n) not in seen:                  # several outputs of one node (SliceChannel) share their inputs
+                seen.add(id(n))
+                inputs.extend(n.inputs)
         return Symbol(inputs) if inputs else None
 
     def attr(self, key):
@@ -496,14 +499,44 @@ class Symbol(object):
         return arg_shapes, [s if s is not None else () for s in out_shapes], aux_shapes
 
     def infer_type(self, *args, **kwargs):
+        """Propagate dtypes through the graph: an operator's outputs take the dtype of its first typed input (Cast and
+        friends their ``dtype`` attribute); untyped parameter variables take the dtype of the data they are combined with."""
         if args:
             kwargs = dict(zip(self.list_arguments(), args))
-        names = self.list_arguments()
-        dt = {k: v for k, v in kwargs.items() if v is not None}
-        default = list(dt.values())[0] if dt else np.float32
-        arg_types = [np_dtype(torch_dtype(dt.get(n, default))) for n in names]
-        aux_types = [np.float32 for _ in self.list_auxiliary_states()]
-        return arg_types, [arg_types[0] if arg_types else np.float32 for _ in self._outputs], aux_types
+        known = {k: np_dtype(torch_dtype(v)) for k, v in kwargs.items() if v is not None}
+        ty = {}
+        fixed = {"Cast": "dtype", "cast": "dtype", "one_hot": "dtype", "_zeros": "dtype", "_ones": "dtype", "_arange": "dtype",
+                 "_eye": "dtype", "_full": "dtype", "topk": "dtype", "argsort": "dtype"}
+        order = self._topo()
+        for _pass in range(2):          # second pass lets variables typed by a later consumer reach earlier nodes
+            for n in order:
+                if n.op is None:
+                    if n.name in known:
+                        ty[(id(n), 0)] = known[n.name]
+                    elif "__dtype__" in n.var_attrs and (id(n), 0) not in ty:
+                        ty[(id(n), 0)] = np_dtype(torch_dtype(n.var_attrs["__dtype__"]))
+                    continue
+                in_t = [ty.get((id(i), k)) for i, k in n.inputs]
+                first = next((t for t in in_t if t is not None), None)
+                if n.op in fixed and n.attrs.get(fixed[n.op]) is not None:
+                    out_t = np_dtype(torch_dtype(n.attrs[fixed[n.op]]))
+                else:
+                    out_t = first
+                if first is not None:
+                    for (i, k), t in zip(n.inputs, in_t):
+                        if t is None and i.op is None:
+                            ty[(id(i), k)] = first
+                if out_t is not None:
+                    for k in range(n.num_outputs):
+                        ty[(id(n), k)] = out_t
+        args_l = [n for n in order if n.op is None and not n.is_aux]
+        auxs_l = [n for n in order if n.op is None and n.is_aux]
+        if not known and not any("__dtype__" in n.var_attrs for n in args_l):
+            return None, None, None
+        arg_types = [ty.get((id(n), 0), np.float32) for n in args_l]
+        aux_types = [ty.get((id(n), 0), np.float32) for n in auxs_l]
+        out_types = [ty.get((id(n), i), np.float32) for n, i in self._outputs]
+        return arg_types, out_types, aux_types
 
     # ---- execution ---------------------------------------------------------------------------------
     def eval_nd(self, feed, group2ctx=None):
