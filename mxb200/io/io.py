@@ -251,7 +251,8 @@ def _init_data(data, allow_empty, default_name):
     assert (data is not None) or allow_empty
     if data is None:
         data = []
-    if isinstance(data, (np.ndarray, NDArray, torch.Tensor)) or hasattr(data, "stype"):
+    if isinstance(data, (np.ndarray, NDArray, torch.Tensor)) or hasattr(data, "stype") \
+            or type(data).__module__.startswith("scipy.sparse"):
         data = [data]
     if isinstance(data, list):
         if not allow_empty:
@@ -264,6 +265,8 @@ def _init_data(data, allow_empty, default_name):
         raise TypeError("Input must be NDArray, numpy.ndarray, a list of them or dict with them as values")
     out = []
     for k, v in data.items():
+        if type(v).__module__.startswith("scipy.sparse"):
+            v = _sp.csr_matrix(v.tocsr(), dtype=v.dtype if v.dtype != np.float64 else np.float32)    # scipy -> CSRNDArray
         if not isinstance(v, (NDArray, _sp.BaseSparseNDArray)):
             try:
                 v = array(v, dtype=v.dtype if hasattr(v, "dtype") and not isinstance(v, torch.Tensor) and v.dtype != np.float64 else None)
@@ -364,6 +367,23 @@ class NDArrayIter(DataIter):
         return 0
 
 
+class _ArrayBackedCIter(NDArrayIter):
+    """NDArrayIter behind the iterators that are C++ classes in the reference (CSVIter, LibSVMIter): with those,
+    ``getdata()`` / ``getlabel()`` return THE array of the current batch instead of a list."""
+
+    def next(self):
+        if self.iter_next():
+            return DataBatch(data=self._getdata(self.data), label=self._getdata(self.label), pad=self.getpad(), index=None)
+        raise StopIteration
+
+    def getdata(self):
+        return self._getdata(self.data)[0]
+
+    def getlabel(self):
+        lab = self._getdata(self.label)
+        return lab[0] if lab else None
+
+
 class SyntheticDataIter(DataIter):
     """One fixed random batch served ``epoch_size`` times per epoch (the reference's --benchmark 1 iterator,
     example/image-classification/common/data.py:98-130)."""
@@ -411,9 +431,32 @@ class MXDataIter(DataIter):
 
     def reset(self):
         self._gen = self._factory()
+        self._cur = None
 
     def next(self):
-        return next(self._gen)
+        self._cur = next(self._gen)
+        return self._cur
+
+    # iter_next / getdata / getlabel / getpad protocol of the C++ iterators (io.py MXDataIter of the reference: getdata()
+    # is THE data array of the current batch, not a list)
+    def iter_next(self):
+        try:
+            self._cur = next(self._gen)
+            return True
+        except StopIteration:
+            return False
+
+    def getdata(self):
+        return self._cur.data[0]
+
+    def getlabel(self):
+        return self._cur.label[0] if self._cur.label else None
+
+    def getindex(self):
+        return self._cur.index
+
+    def getpad(self):
+        return self._cur.pad or 0
 
 
 def _shard(n, num_parts, part_index):
@@ -424,13 +467,13 @@ def _shard(n, num_parts, part_index):
 def CSVIter(data_csv, data_shape, label_csv=None, label_shape=(1,), batch_size=1, round_batch=True, dtype="float32",
             num_parts=1, part_index=0, **kwargs):
     """CSV iterator (src/io/iter_csv.cc) with num_parts/part_index sharding."""
-    data = np.loadtxt(data_csv, delimiter=",", dtype=np.float32, ndmin=2).reshape((-1,) + tuple(data_shape))
+    data = np.loadtxt(data_csv, delimiter=",", dtype=np.dtype(dtype), ndmin=2).reshape((-1,) + tuple(data_shape))
     label = np.loadtxt(label_csv, delimiter=",", dtype=np.float32, ndmin=2).reshape((-1,) + tuple(label_shape)) \
         if label_csv else np.zeros((data.shape[0],) + tuple(label_shape), np.float32)
     b, e = _shard(len(data), num_parts, part_index)
     if tuple(label_shape) == (1,):
         label = label.reshape(-1)
-    return NDArrayIter(data[b:e], label[b:e], batch_size, last_batch_handle="pad" if round_batch else "discard")
+    return _ArrayBackedCIter(data[b:e], label[b:e], batch_size, last_batch_handle="pad" if round_batch else "discard")
 
 
 def MNISTIter(image, label, batch_size=128, shuffle=True, flat=False, seed=0, silent=False, num_parts=1, part_index=0,
@@ -475,7 +518,7 @@ def LibSVMIter(data_libsvm, data_shape, label_libsvm=None, label_shape=(1,), bat
     b, e = _shard(n, num_parts, part_index)
     csr = _sp.csr_matrix((np.array(vals[indptr[b]:indptr[e]], np.float32), np.array(cols[indptr[b]:indptr[e]], np.int64),
                           np.array(indptr[b:e + 1], np.int64) - indptr[b]), shape=(e - b, data_shape[0]))
-    return NDArrayIter(csr, np.array(labels[b:e], np.float32), batch_size, last_batch_handle="discard")
+    return _ArrayBackedCIter(csr, np.array(labels[b:e], np.float32), batch_size, last_batch_handle="discard")
 
 
 def ImageRecordIter(path_imgrec, data_shape, batch_size, path_imgidx=None, label_width=1, shuffle=False, num_parts=1,

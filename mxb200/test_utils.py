@@ -633,6 +633,45 @@ def get_mnist(path="data"):
     return {"train_data": ti, "train_label": tl, "test_data": vi, "test_label": vl}
 
 
+def _needs_network(what):
+    raise MXNetError("%s downloads its data set; this host has no network access. Place the files manually." % what)
+
+
+def get_mnist_pkl():
+    if not os.path.isfile("data/mnist.pkl.gz"):
+        _needs_network("get_mnist_pkl")
+
+
+def get_mnist_ubyte():
+    """MNIST idx files under ./data (train-images-idx3-ubyte ...), as the reference's C++ MNISTIter expects them."""
+    need = ["data/train-images-idx3-ubyte", "data/train-labels-idx1-ubyte", "data/t10k-images-idx3-ubyte", "data/t10k-labels-idx1-ubyte"]
+    if not all(os.path.isfile(f) for f in need):
+        _needs_network("get_mnist_ubyte")
+
+
+def get_cifar10():
+    """CIFAR-10 RecordIO files under ./data/cifar."""
+    need = ["data/cifar/train.rec", "data/cifar/test.rec", "data/cifar/train.lst", "data/cifar/test.lst"]
+    if not all(os.path.isfile(f) for f in need):
+        _needs_network("get_cifar10")
+
+
+def get_zip_data(data_dir, url, data_origin_name):
+    if not os.path.isfile(os.path.join(data_dir, data_origin_name)):
+        _needs_network("get_zip_data")
+
+
+def get_bz2_data(data_dir, data_name, url, data_origin_name):
+    if not os.path.isfile(os.path.join(data_dir, data_name)):
+        _needs_network("get_bz2_data")
+
+
+def get_im2rec_path(home_env="MXNET_HOME"):
+    """Path of the im2rec tool (python version shipped in tools/)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return os.path.join(here, "tools", "im2rec.py")
+
+
 def get_mnist_iterator(batch_size, input_shape, num_parts=1, part_index=0, path="data"):
     from . import io
     m = get_mnist(path)
