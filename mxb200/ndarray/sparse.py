@@ -336,6 +336,21 @@ def csr_matrix(arg1, shape=None, ctx=None, dtype=None):
         if shape is None:
             shape = (indptr.numel() - 1, int(indices.max()) + 1 if indices.numel() else 0)
         return CSRNDArray(data, indices, indptr, shape, ctx)
+    if type(arg1).__module__.startswith("scipy.sparse"):
+        m = arg1.tocsr()
+        m.sort_indices()
+        return csr_matrix((m.data, m.indices, m.indptr), shape=shape or m.shape, ctx=ctx,
+                          dtype=dtype or (m.dtype if m.dtype != np.float64 else np.float32))
+    if isinstance(arg1, CSRNDArray):
+        return arg1.copyto(ctx) if dtype is None else arg1.copyto(ctx).astype(dtype)
+    if isinstance(arg1, tuple) and len(arg1) == 2 and isinstance(arg1[0], int):
+        return zeros("csr", arg1, ctx=ctx, dtype=dtype)       # csr_matrix((M, N)): empty matrix
+    if isinstance(arg1, tuple) and len(arg1) == 2:
+        # (data, (row, col)) coordinate form
+        import scipy.sparse as spsp
+        data, (row, col) = arg1
+        as_np = lambda v: v.asnumpy() if hasattr(v, "asnumpy") else np.asarray(v)   # noqa: E731
+        return csr_matrix(spsp.coo_matrix((as_np(data), (as_np(row), as_np(col))), shape=shape), ctx=ctx, dtype=dtype)
     return cast_storage(_dense_array(arg1, ctx=ctx, dtype=dtype), "csr")
 
 
