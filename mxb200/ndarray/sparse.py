@@ -6,7 +6,12 @@ A RowSparseNDArray is (data[nnz_rows, ...], indices[nnz_rows]) with sorted
 unique int64 row ids; a CSRNDArray is (data, indices, indptr).
 """
 import numpy as np
+import warnings
+
 import torch
+
+warnings.filterwarnings("ignore", message="Sparse CSR tensor support is in beta state")
+warnings.filterwarnings("ignore", message="Sparse invariant checks are implicitly disabled")
 
 from ..base import torch_dtype, np_dtype
 from ..context import current_context

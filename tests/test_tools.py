@@ -69,3 +69,21 @@ def test_im2rec_and_rec2idx_roundtrip(tmp_path):
     it = mx.image.ImageIter(2, (3, 16, 16), path_imgrec=prefix + ".rec", path_imgidx=prefix + ".idx")
     b = next(iter(it))
     assert b.data[0].shape == (2, 3, 16, 16)
+
+
+def test_reference_unittest_runner(tmp_path):
+    """tools/run_reference_tests.py executes the reference's own unit tests against this package (API-parity probe)."""
+    import os
+    import subprocess
+    import sys
+    ref = os.environ.get("MXB200_REFERENCE_TESTS", "/root/reference/tests/python/unittest")
+    if not os.path.exists(os.path.join(ref, "test_metric.py")):
+        import pytest
+        pytest.skip("reference test tree not mounted")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "t.md")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "run_reference_tests.py"), "--out", out, "test_metric", "test_attr"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout
+    assert "test_metric" in r.stdout and "failed   0" in r.stdout
+    assert "| test_attr | 4 | 0 |" in open(out).read()
