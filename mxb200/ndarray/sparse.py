@@ -10,6 +10,8 @@ import warnings
 
 import torch
 
+from ..base import MXNetError
+
 warnings.filterwarnings("ignore", message="Sparse CSR tensor support is in beta state")
 warnings.filterwarnings("ignore", message="Sparse invariant checks are implicitly disabled")
 
@@ -198,8 +200,10 @@ class RowSparseNDArray(BaseSparseNDArray):
     def as_in_context(self, ctx):
         return self if ctx == self._ctx else self.copyto(ctx)
 
-    def astype(self, dtype):
-        return RowSparseNDArray(self._data.to(torch_dtype(dtype)), self._indices, self._shape, self._ctx)
+    def astype(self, dtype, copy=True):
+        if not copy and torch_dtype(dtype) == self._data.dtype:
+            return self
+        return RowSparseNDArray(self._data.to(torch_dtype(dtype), copy=True), self._indices.clone(), self._shape, self._ctx)
 
     def retain(self, row_ids):
         return retain(self, row_ids)
@@ -274,8 +278,11 @@ class CSRNDArray(BaseSparseNDArray):
     def as_in_context(self, ctx):
         return self if ctx == self._ctx else self.copyto(ctx)
 
-    def astype(self, dtype):
-        return CSRNDArray(self._data.to(torch_dtype(dtype)), self._indices, self._indptr, self._shape, self._ctx)
+    def astype(self, dtype, copy=True):
+        if not copy and torch_dtype(dtype) == self._data.dtype:
+            return self
+        return CSRNDArray(self._data.to(torch_dtype(dtype), copy=True), self._indices.clone(), self._indptr.clone(), self._shape,
+                          self._ctx)
 
     def __setitem__(self, key, value):
         assert isinstance(key, slice) and key == slice(None), "CSRNDArray only supports [:] assignment"
@@ -390,8 +397,14 @@ def cast_storage(arr, stype):
     raise ValueError("unknown stype " + str(stype))
 
 
-def retain(rsp, row_ids):
-    """sparse_retain: keep only the requested rows (src/operator/tensor/sparse_retain.cu)."""
+def retain(data=None, indices=None, out=None, **kwargs):
+    """sparse_retain: keep only the requested rows (src/operator/tensor/sparse_retain.cu).  ``retain(rsp, row_ids)`` or the
+    operator's keyword form ``retain(data=rsp, indices=row_ids)``."""
+    if kwargs:
+        raise TypeError("retain() got unexpected keyword argument(s) %s" % sorted(kwargs))
+    rsp, row_ids = data, indices
+    if not isinstance(rsp, RowSparseNDArray):
+        raise MXNetError("sparse retain expects a row_sparse input, got %s" % type(rsp).__name__)
     ids = row_ids._t.long() if isinstance(row_ids, NDArray) else torch.as_tensor(row_ids, dtype=torch.int64, device=rsp._data.device)
     ids = torch.unique(ids)
     mask = torch.isin(rsp._indices, ids)
@@ -428,3 +441,17 @@ def dot(lhs, rhs, transpose_a=False, transpose_b=False):
     if transpose_b:
         b = b.t()
     return NDArray(torch.matmul(a, b), lhs._ctx if isinstance(lhs, NDArray) else rhs._ctx)
+
+
+def __getattr__(name):
+    """mx.nd.sparse.<op>: operators without a dedicated sparse kernel fall back to the dense implementation on the dense
+    view of their inputs (the reference generates this namespace from the same registry: ndarray/sparse.py + gen_sparse)."""
+    if name.startswith("__"):
+        raise AttributeError(name)
+    from . import op as _opmod
+    for cand in ("_sparse_" + name, name, {"add": "elemwise_add", "subtract": "elemwise_sub", "multiply": "elemwise_mul",
+                                            "divide": "elemwise_div"}.get(name, "")):
+        f = _opmod._REG.get(cand)
+        if f is not None:
+            return f
+    raise AttributeError("module 'mxb200.ndarray.sparse' has no attribute %r" % name)
