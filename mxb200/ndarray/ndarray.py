@@ -143,6 +143,7 @@ class NDArray(object):
 
     # ---- conversion ------------------------------------------------------
     def asnumpy(self):
+        _raise_deferred(self._t)
         t = self._t.detach()
         if t.dtype is torch.bfloat16:
             t = t.float()
@@ -176,10 +177,14 @@ class NDArray(object):
                 return other
             with torch.no_grad():
                 other._t.copy_(self._t, non_blocking=True)
+            if getattr(self._t, "_mx_exc", None) is not None:
+                other._t._mx_exc = self._t._mx_exc
             return other
         ctx = _ctx_of(other)
         with torch.no_grad():
             t = self._t.detach().to(ctx.torch_device, copy=True)
+        if getattr(self._t, "_mx_exc", None) is not None:
+            t._mx_exc = self._t._mx_exc
         return NDArray(_pin_if(t, ctx), ctx)
 
     def as_in_context(self, ctx):
@@ -200,6 +205,7 @@ class NDArray(object):
         return sparse.cast_storage(self, stype)
 
     def wait_to_read(self):
+        _raise_deferred(self._t)
         if self._t.is_cuda:
             torch.cuda.current_stream(self._t.device).synchronize()
 
@@ -587,7 +593,34 @@ def _op(fn, *arrs, **kw):
     else:
         with torch.no_grad():
             r = fn(*ts, **kw)
+    for t in ts:
+        e = getattr(t, "_mx_exc", None) if isinstance(t, torch.Tensor) else None
+        if e is not None:                      # inputs carried a deferred failure: so do the outputs
+            for o in (r if isinstance(r, (tuple, list)) else [r]):
+                if isinstance(o, torch.Tensor):
+                    o._mx_exc = e
+            break
     return _wrap(r, ctx)
+
+
+def _poison(t, exc):
+    """Mark a tensor as the result of an operation that failed asynchronously: like the reference's engine, the error is
+    raised when the value is needed on the host (asnumpy / wait_to_read / waitall), and it propagates to every array
+    computed from this one (test_exc_handling.py semantics, threaded_engine.cc exception_ptr propagation)."""
+    t._mx_exc = exc
+    _PENDING.append(exc)
+    return t
+
+
+_PENDING = []
+
+
+def _raise_deferred(t):
+    e = getattr(t, "_mx_exc", None)
+    if e is not None:
+        if e in _PENDING:
+            _PENDING.remove(e)
+        raise e
 
 
 def _wrap(r, ctx):
@@ -749,3 +782,7 @@ def waitall():
     if torch.cuda.is_available():
         for d in range(torch.cuda.device_count()):
             torch.cuda.synchronize(d)
+    if _PENDING:
+        e = _PENDING.pop(0)
+        del _PENDING[:]
+        raise e

@@ -305,10 +305,22 @@ def _rand(name, draw):
             return _out(NDArray(draw(full, ex, ps[0].device).to(torch_dtype(dtype)), params[0].context), out)
         # scalar parameters: positional first, then by name, then the distribution's defaults (sample_op.h *Param structs)
         vals = list(params)
+        if len(vals) > len(spec) and shape is None:        # legacy positional form: random_normal(loc, scale, shape)
+            shape = vals[len(spec)]
+            vals = vals[:len(spec)]
+            shp = (shape,) if isinstance(shape, int) else tuple(shape)
         for pname, default in spec[len(vals):]:
             vals.append(kw.pop(pname, default))
+        poison = None
+        if name.endswith("normal") and float(vals[1]) < 0:
+            from .ndarray import _poison
+            poison = MXNetError("normal: scale (standard deviation) must be non-negative, got %s" % float(vals[1]))
+            vals[1] = 0.0
         ex = [torch.full(shp or (1,), float(v), device=dev) for v in vals]
-        return _out(NDArray(draw(shp or (1,), ex, dev).to(torch_dtype(dtype)), c), out)
+        res = NDArray(draw(shp or (1,), ex, dev).to(torch_dtype(dtype)), c)
+        if poison is not None:
+            _poison(res._t, poison)
+        return _out(res, out)
     f.__name__ = name
     _REG[name] = f
 

@@ -44,8 +44,12 @@ def uniform(low=0, high=1, shape=None, dtype=None, ctx=None, out=None, **kwargs)
 
 def normal(loc=0, scale=1, shape=None, dtype=None, ctx=None, out=None, **kwargs):
     if not isinstance(scale, NDArray) and scale < 0:
+        # invalid parameters fail like any asynchronous operator error: at the next synchronisation point
         from ..base import MXNetError
-        raise MXNetError("normal: scale (standard deviation) must be non-negative, got %s" % scale)
+        from .ndarray import _poison
+        res = _random_helper("normal", [loc, 0.0], shape, dtype, ctx, out, kwargs)
+        _poison(res._t, MXNetError("normal: scale (standard deviation) must be non-negative, got %s" % scale))
+        return res
     return _random_helper("normal", [loc, scale], shape, dtype, ctx, out, kwargs)
 
 

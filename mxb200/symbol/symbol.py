@@ -885,6 +885,9 @@ def _create(op, args, kwargs):
                 s = var("%s_%s" % (node_name, aname))
                 for k, v in inherit.items():
                     s._outputs[0][0].var_attrs.setdefault(k, v)
+                if op == "LeakyReLU" and aname == "gamma":
+                    # the PReLU slope starts at 0.25 whatever the global initializer is (leaky_relu.cc FSetInputVarAttrOnCompose)
+                    s._outputs[0][0].var_attrs.setdefault("__init__", '["constant", {"value": 0.25}]')
                 if is_aux:
                     s._outputs[0][0].is_aux = True
             if is_aux:
