@@ -31,6 +31,16 @@ def get_pretrained_file_names(embedding_name=None):
 
 
 class _TokenEmbedding(vocab.Vocabulary):
+    pretrained_file_name_sha1 = {}
+
+    @classmethod
+    def _check_pretrained_file_names(cls, pretrained_file_name):
+        """Raise KeyError if the file name is not one this embedding class knows how to fetch."""
+        embedding_name = cls.__name__.lower()
+        if pretrained_file_name not in cls.pretrained_file_name_sha1:
+            raise KeyError("Cannot find pretrained file %s for token embedding %s. Valid pretrained files for embedding %s: %s"
+                           % (pretrained_file_name, embedding_name, embedding_name, ", ".join(cls.pretrained_file_name_sha1.keys())))
+
     def __init__(self, **kwargs):
         super(_TokenEmbedding, self).__init__(**kwargs)
         self._vec_len = 0
@@ -38,15 +48,23 @@ class _TokenEmbedding(vocab.Vocabulary):
 
     def _load_embedding(self, path, elem_delim, init_unknown_vec, encoding="utf8"):
         vecs, toks = [], []
+        seen = set()
+        loaded_unknown_vec = None
         with io.open(path, "r", encoding=encoding) as f:
             for n, line in enumerate(f):
                 parts = line.rstrip().split(elem_delim)
                 if len(parts) < 2 or (n == 0 and len(parts) == 2):     # fastText header "count dim"
                     continue
                 tok, vals = parts[0], parts[1:]
-                if tok == self.unknown_token or tok in self._token_to_idx and tok in toks:
-                    logging.warning("duplicate / unknown token %r in %s skipped", tok, path)
+                if tok == self.unknown_token:
+                    # the file's own vector for the unknown token wins over init_unknown_vec (embedding.py:232-260)
+                    if loaded_unknown_vec is None:
+                        loaded_unknown_vec = np.asarray(vals, dtype=np.float32)
                     continue
+                if tok in seen:
+                    logging.warning("duplicate token %r in %s skipped (first occurrence kept)", tok, path)
+                    continue
+                seen.add(tok)
                 if self._vec_len and len(vals) != self._vec_len:
                     continue
                 self._vec_len = self._vec_len or len(vals)
@@ -57,7 +75,10 @@ class _TokenEmbedding(vocab.Vocabulary):
                 self._idx_to_token.append(t)
                 self._token_to_idx[t] = len(self._idx_to_token) - 1
         mat = np.zeros((len(self._idx_to_token), self._vec_len), dtype=np.float32)
-        mat[0] = init_unknown_vec(shape=self._vec_len).asnumpy() if init_unknown_vec is not None else 0
+        if loaded_unknown_vec is not None and len(loaded_unknown_vec) == self._vec_len:
+            mat[0] = loaded_unknown_vec
+        else:
+            mat[0] = init_unknown_vec(shape=self._vec_len).asnumpy() if init_unknown_vec is not None else 0
         for t, v in zip(toks, vecs):
             mat[self._token_to_idx[t]] = v
         self._idx_to_vec = nd.array(mat)
@@ -94,7 +115,13 @@ class _TokenEmbedding(vocab.Vocabulary):
     def update_token_vectors(self, tokens, new_vectors):
         assert self._idx_to_vec is not None, "The property `idx_to_vec` has not been properly set."
         toks = [tokens] if not isinstance(tokens, list) else tokens
-        nv = new_vectors.asnumpy().reshape(len(toks), -1)
+        assert isinstance(new_vectors, nd.NDArray) and len(new_vectors.shape) in (1, 2), \
+            "`new_vectors` must be a 1-D or 2-D NDArray."
+        nv = new_vectors.asnumpy()
+        nv = nv.reshape(1, -1) if nv.ndim == 1 else nv
+        assert nv.shape == (len(toks), self._vec_len), \
+            "The length of new_vectors must be equal to the number of tokens and the width of new_vectors must be equal " \
+            "to the dimension of embeddings of the glossary."
         mat = self._idx_to_vec.asnumpy()
         for t, v in zip(toks, nv):
             if t not in self._token_to_idx:

@@ -31,6 +31,10 @@ def imdecode(buf, flag=1, to_rgb=1, out=None):
 def imread(filename, flag=1, to_rgb=1):
     if filename.endswith(".npy"):
         return array(np.load(filename), dtype=np.uint8)
+    import os
+    if not os.path.isfile(filename):
+        from ..base import MXNetError
+        raise MXNetError("imread: cannot open %s" % filename)      # same error class as the C++ reader
     with open(filename, "rb") as f:
         return imdecode(f.read(), flag, to_rgb)
 
