@@ -79,12 +79,21 @@ class Executor(object):
         type_dict = type_dict or {}
         vshape, _out, vdtype, _ = symbol._infer(shapes, type_dict)
         args, aux = {}, {}
+        # model parallelism by placement: a variable created under AttrScope(ctx_group=...) lives on group2ctx[group]
+        # (graph_executor.cc AssignContext); everything else on the default context
+        place = {}
+        if group2ctx:
+            for node in symbol._topo():
+                if node.op is None:
+                    g = node.var_attrs.get("__ctx_group__")
+                    if g in group2ctx:
+                        place[node.name] = group2ctx[g] if not isinstance(group2ctx[g], (list, tuple)) else group2ctx[g][0]
         for n in symbol.list_arguments():
             if n not in vshape:
                 raise MXNetError("simple_bind: cannot infer shape of argument %s" % n)
-            args[n] = nd.zeros(vshape[n], ctx=ctx, dtype=type_dict.get(n, vdtype.get(n, "float32")))
+            args[n] = nd.zeros(vshape[n], ctx=place.get(n, ctx), dtype=type_dict.get(n, vdtype.get(n, "float32")))
         for n in symbol.list_auxiliary_states():
-            aux[n] = nd.zeros(vshape[n], ctx=ctx, dtype="float32")
+            aux[n] = nd.zeros(vshape[n], ctx=place.get(n, ctx), dtype="float32")
         if isinstance(grad_req, str):
             req = {n: ("null" if n in shapes and grad_req != "null" and False else grad_req) for n in args}
         else:

@@ -213,8 +213,22 @@ class DataParallelExecutorGroup(object):
             end = self.num_outputs
         outputs = [[exec_.outputs[i] for exec_ in self.execs] for i in range(begin, end)]
         if merge_multi_context:
-            return [_merge(x) for x in outputs]
+            axes = self._output_batch_axes()[begin:end]
+            return [_merge(x, axis=ax) for x, ax in zip(outputs, axes)]
         return outputs
+
+    def _output_batch_axes(self):
+        """Batch axis of every output from its ``__layout__`` attribute (executor_group.py:241-244 of the reference); 0 when
+        the symbol does not say."""
+        axes = getattr(self, "_out_axes", None)
+        if axes is None:
+            axes = []
+            for i in range(self.num_outputs):
+                lay = self.symbol[i].attr("__layout__")
+                ax = DataDesc.get_batch_axis(lay) if lay else 0
+                axes.append(0 if ax is None or ax < 0 else ax)
+            self._out_axes = axes
+        return axes
 
     def get_states(self, merge_multi_context=True):
         return [_merge(x) for x in self.state_arrays] if merge_multi_context else self.state_arrays
@@ -241,10 +255,10 @@ class DataParallelExecutorGroup(object):
             out_grads = []
         for i, (exec_, islice) in enumerate(zip(self.execs, self.slices)):
             out_grads_slice = []
-            for grad in out_grads:
+            for grad, ax in zip(out_grads, self._output_batch_axes()):
                 g = grad._t
                 if len(self.execs) > 1:
-                    g = g.narrow(0, islice.start, islice.stop - islice.start)
+                    g = g.narrow(ax, islice.start, islice.stop - islice.start)
                 out_grads_slice.append(NDArray(g.to(exec_._ctx.torch_device), exec_._ctx))
             exec_.backward(out_grads=out_grads_slice)
         if self.for_training:
@@ -270,8 +284,8 @@ class DataParallelExecutorGroup(object):
             mon.install(exe)
 
 
-def _merge(tensors):
+def _merge(tensors, axis=0):
     if len(tensors) == 1:
         return tensors[0]
     dev = tensors[0]._t.device
-    return NDArray(torch.cat([t._t.to(dev) for t in tensors], dim=0), tensors[0].context)
+    return NDArray(torch.cat([t._t.to(dev) for t in tensors], dim=axis), tensors[0].context)
