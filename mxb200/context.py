@@ -11,7 +11,20 @@ import torch
 __all__ = ["Context", "cpu", "gpu", "cpu_pinned", "current_context", "num_gpus"]
 
 
-class Context(object):
+class _ContextMeta(type):
+    """``Context.default_ctx`` (deprecated in the reference but still used): per-thread default context, readable and
+    assignable on the class."""
+
+    @property
+    def default_ctx(cls):
+        return current_context()
+
+    @default_ctx.setter
+    def default_ctx(cls, ctx):
+        Context._default.ctx = ctx
+
+
+class Context(object, metaclass=_ContextMeta):
     devtype2str = {1: "cpu", 2: "gpu", 3: "cpu_pinned", 5: "cpu_shared"}
     devstr2type = {"cpu": 1, "gpu": 2, "cpu_pinned": 3, "cpu_shared": 5}
     _default = threading.local()
@@ -54,16 +67,6 @@ class Context(object):
 
     def __exit__(self, *a):
         Context._default.ctx = self._old_ctx
-
-
-class _DefaultCtx(object):
-    """``Context.default_ctx``: the reference's (deprecated) class property for the current default context."""
-
-    def __get__(self, obj, owner):
-        return current_context()
-
-
-Context.default_ctx = _DefaultCtx()
 
 
 def cpu(device_id=0):

@@ -665,8 +665,8 @@ def FullyConnected(data, weight, bias=None, num_hidden=None, no_bias=False, flat
     from ..ops import functional as K
 
     def g(x, w, b=None):
-        if flatten and x.dim() > 2:
-            x = x.reshape(x.shape[0], -1)
+        if flatten and x.dim() != 2:
+            x = x.reshape(x.shape[0], -1)       # (N,) is N samples of one feature, (N, a, b) of a*b features
         return K.linear(x, w, b)
     if bias is None or no_bias:
         return _out(_op(g, data, weight), out)

@@ -31,12 +31,12 @@ import mxb200 as mx  # noqa: E402,F401  (the package itself; safe: it is already
 
 # ----------------------------------------------------------------------------- defaults
 def default_context():
-    """Context used by the check_* helpers when none is given (test_utils.py:53-62)."""
-    return _DEFAULT_CTX[0] if _DEFAULT_CTX[0] is not None else current_context()
+    """Context used by the check_* helpers when none is given (test_utils.py:53-62): the thread's default context."""
+    return current_context()
 
 
 def set_default_context(ctx):
-    _DEFAULT_CTX[0] = ctx
+    Context.default_ctx = ctx
 
 
 def default_dtype():
