@@ -293,5 +293,23 @@ class FusedRNN(Initializer):
                                        forget_bias=forget_bias)
         self._init = init
 
+        self._num_hidden, self._num_layers, self._mode = num_hidden, num_layers, mode
+        self._bidirectional, self._forget_bias = bidirectional, forget_bias
+
     def _init_weight(self, desc, arr):
-        (self._init or Uniform(0.07))._init_weight(desc, arr)
+        """Initialise the packed parameter vector gate by gate: weights with ``init`` (or the global initializer), biases
+        with their own rule and the LSTM forget-gate bias with ``forget_bias`` (initializer.py:FusedRNN of the reference)."""
+        from .rnn import rnn_cell
+        cell = rnn_cell.FusedRNNCell(self._num_hidden, self._num_layers, self._mode, self._bidirectional,
+                                     forget_bias=self._forget_bias, prefix="")
+        args = cell.unpack_weights({"parameters": arr})
+        for name in args:
+            arg_desc = InitDesc(name, global_init=getattr(desc, "global_init", None))
+            if self._mode == "lstm" and name.endswith("_f_bias"):
+                args[name][:] = self._forget_bias
+            elif self._init is None:
+                g = getattr(desc, "global_init", None)
+                (g if g is not None else Uniform(0.07))(arg_desc, args[name])
+            else:
+                self._init(arg_desc, args[name])
+        arr[:] = cell.pack_weights(args)["parameters"]

@@ -453,7 +453,9 @@ class FusedRNNCell(BaseRNNCell):
         self._num_hidden, self._num_layers, self._mode = num_hidden, num_layers, mode
         self._bidirectional, self._dropout, self._get_next_state = bidirectional, dropout, get_next_state
         self._directions = ["l", "r"] if bidirectional else ["l"]
-        self._parameter = self.params.get("parameters")
+        from .. import initializer as _init
+        self._parameter = self.params.get("parameters", init=_init.FusedRNN(None, num_hidden, num_layers, mode, bidirectional,
+                                                                            forget_bias))
 
     @property
     def state_info(self):
@@ -468,6 +470,59 @@ class FusedRNNCell(BaseRNNCell):
     @property
     def _num_gates(self):
         return len(self._gate_names)
+
+    def _slice_weights(self, arr, li, lh):
+        """name -> view of the flat cuDNN-layout vector ``arr`` (1-D NDArray): all weights layer-major (i2h then h2h, gates
+        stacked), then all biases in the same order (rnn_cell.py:600-640 of the reference)."""
+        args = {}
+        g = self._gate_names
+        ng, H = len(g), self._num_hidden
+        b = len(self._directions)
+        p = 0
+        flat = arr
+        for layer in range(self._num_layers):
+            for d in self._directions:
+                inp = li if layer == 0 else b * lh
+                for grp, width in (("i2h", inp), ("h2h", lh)):
+                    for gate in g:
+                        name = "%s%s%d_%s%s_weight" % (self._prefix, d, layer, grp, gate)
+                        args[name] = flat[p:p + H * width].reshape((H, width))
+                        p += H * width
+        for layer in range(self._num_layers):
+            for d in self._directions:
+                for grp in ("i2h", "h2h"):
+                    for gate in g:
+                        name = "%s%s%d_%s%s_bias" % (self._prefix, d, layer, grp, gate)
+                        args[name] = flat[p:p + H]
+                        p += H
+        assert p == arr.size, "Invalid parameters size for FusedRNNCell"
+        return args
+
+    def unpack_weights(self, args):
+        args = args.copy()
+        arr = args.pop(self._parameter.name)
+        b = len(self._directions)
+        m = self._num_gates
+        h = self._num_hidden
+        num_input = arr.size // b // h // m - (self._num_layers - 1) * (h + b * h + 2) - h - 2
+        for name, w in self._slice_weights(arr, num_input, h).items():
+            args[name] = w.copy()
+        return args
+
+    def pack_weights(self, args):
+        from .. import ndarray as nd
+        args = args.copy()
+        b = len(self._directions)
+        m = self._num_gates
+        h = self._num_hidden
+        w0 = args["%sl0_i2h%s_weight" % (self._prefix, self._gate_names[0])]
+        num_input = w0.shape[1]
+        total = (num_input + h + 2) * h * m * b + (self._num_layers - 1) * m * h * (h + b * h + 2) * b
+        arr = nd.zeros((total,), ctx=w0.context, dtype=w0.dtype)
+        for name, view in self._slice_weights(arr, num_input, h).items():
+            view[:] = args.pop(name)
+        args[self._parameter.name] = arr
+        return args
 
     def __call__(self, inputs, states):
         raise NotImplementedError("FusedRNNCell cannot be stepped. Please use unroll")
