@@ -3,6 +3,7 @@ import sys as _sys
 import types as _types
 
 from .symbol import Symbol, var, Variable, Group, load, load_json, zeros, ones, _create  # noqa: F401
+from .symbol import full, arange, eye, pow, power, maximum, minimum, hypot  # noqa: F401,A004
 from ..ndarray import op as _ndop
 
 

@@ -303,6 +303,17 @@ class Symbol(object):
     def __lt__(self, o):
         return self._bin(o, "broadcast_lesser", "_lesser_scalar")
 
+    def __ge__(self, o):
+        return self._bin(o, "broadcast_greater_equal", "_greater_equal_scalar")
+
+    def __le__(self, o):
+        return self._bin(o, "broadcast_lesser_equal", "_lesser_equal_scalar")
+
+    def __ne__(self, o):
+        if isinstance(o, (Symbol, int, float)):
+            return self._bin(o, "broadcast_not_equal", "_not_equal_scalar")
+        return NotImplemented
+
     def __eq__(self, o):
         if isinstance(o, (Symbol, int, float)):
             return self._bin(o, "broadcast_equal", "_equal_scalar")
@@ -809,12 +820,54 @@ def Group(symbols):
     return Symbol(outs)
 
 
+def _shp(shape):
+    return (int(shape),) if isinstance(shape, (int, np.integer)) else tuple(int(x) for x in shape)
+
+
 def zeros(shape, dtype=None, **kwargs):
-    return _make_op("_zeros", [], {"shape": tuple(shape), "dtype": dtype_name(dtype or "float32")})
+    return _make_op("_zeros", [], {"shape": _shp(shape), "dtype": dtype_name(dtype or "float32")}, name=kwargs.get("name"))
 
 
 def ones(shape, dtype=None, **kwargs):
-    return _make_op("_ones", [], {"shape": tuple(shape), "dtype": dtype_name(dtype or "float32")})
+    return _make_op("_ones", [], {"shape": _shp(shape), "dtype": dtype_name(dtype or "float32")}, name=kwargs.get("name"))
+
+
+def full(shape, val, dtype=None, **kwargs):
+    return ones(shape, dtype=dtype, **kwargs) * val
+
+
+def arange(start, stop=None, step=1.0, repeat=1, name=None, dtype=None):
+    return _create("_arange", [], dict(start=start, stop=stop, step=step, repeat=repeat, dtype=dtype_name(dtype or "float32"),
+                                       name=name))
+
+
+def eye(N, M=0, k=0, dtype=None, **kwargs):
+    return _create("_eye", [], dict(N=N, M=M, k=k, dtype=dtype_name(dtype or "float32"), **kwargs))
+
+
+def _sym_or_scalar(name, sym_op, scalar_op, rscalar_op, py_fn):
+    """Module-level binary helpers with MXNet's dispatch: Symbol x Symbol -> broadcast op, Symbol x number -> scalar op,
+    number x number -> plain python (symbol.py:pow / maximum / minimum / hypot of the reference)."""
+    def f(left, right):
+        ls, rs = isinstance(left, Symbol), isinstance(right, Symbol)
+        if ls and rs:
+            return _make_op(sym_op, [left, right], {})
+        if ls:
+            return _make_op(scalar_op, [left], {"scalar": float(right)})
+        if rs:
+            return _make_op(rscalar_op, [right], {"scalar": float(left)})
+        if isinstance(left, (int, float)) and isinstance(right, (int, float)):
+            return py_fn(left, right)
+        raise TypeError("types (%s, %s) not supported" % (str(type(left)), str(type(right))))
+    f.__name__ = name
+    return f
+
+
+pow = _sym_or_scalar("pow", "broadcast_power", "_power_scalar", "_rpower_scalar", lambda a, b: a ** b)   # noqa: A001
+power = pow
+maximum = _sym_or_scalar("maximum", "broadcast_maximum", "_maximum_scalar", "_maximum_scalar", lambda a, b: a if a > b else b)
+minimum = _sym_or_scalar("minimum", "broadcast_minimum", "_minimum_scalar", "_minimum_scalar", lambda a, b: a if a < b else b)
+hypot = _sym_or_scalar("hypot", "broadcast_hypot", "_hypot_scalar", "_hypot_scalar", lambda a, b: (a * a + b * b) ** 0.5)
 
 
 def _make_op(op, inputs, attrs, name=None, hint=None):

@@ -388,10 +388,11 @@ def check_numeric_gradient(sym, location, aux_states=None, numeric_eps=1e-3, rto
     req = {k: grad_nodes.get(k, "null") for k in sym.list_arguments()}
     req["__random_proj"] = "null"
     grads0 = {k: nd.array(_RNG.normal(size=loc[k].shape), ctx=ctx, dtype=dtype) for k in grad_nodes}
-    exe = loss.bind(ctx, args=args, args_grad={k: v.copy() for k, v in grads0.items()}, grad_req=req, aux_states=aux)
+    bound_grads = {k: v.copy() for k, v in grads0.items()}
+    exe = loss.bind(ctx, args=args, args_grad=bound_grads, grad_req=req, aux_states=aux)
     exe.forward(is_train=True)
     exe.backward()
-    sym_grads = {k: exe.grad_dict[k].asnumpy() for k in grad_nodes}
+    sym_grads = {k: (exe.grad_dict[k] if k in exe.grad_dict else bound_grads[k]).asnumpy() for k in grad_nodes}
     num_loc = dict(loc_np)
     num_loc["__random_proj"] = args["__random_proj"].asnumpy()
     fd = numeric_grad(exe, num_loc, aux_np, eps=numeric_eps, use_forward_train=use_forward_train, dtype=dtype)
@@ -441,7 +442,7 @@ def check_symbolic_backward(sym, location, out_grads, expected, rtol=1e-5, atol=
     if out_grads is not None:
         out_grads = [g if isinstance(g, NDArray) else nd.array(g, ctx=ctx, dtype=dtype) for g in out_grads]
     exe.backward(out_grads)
-    got = {k: exe.grad_dict[k].asnumpy() for k in expected}
+    got = {k: (exe.grad_dict[k] if k in exe.grad_dict else args_grad[k]).asnumpy() for k in expected}
     for name in expected:
         req = grad_req.get(name, "null")
         if req == "write":
