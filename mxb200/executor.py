@@ -65,9 +65,29 @@ class Executor(object):
         self.arg_arrays = [self.arg_dict[n] for n in arg_names]
         self.grad_arrays = [self.grad_dict.get(n) for n in arg_names]
         self.aux_arrays = [self.aux_dict[n] for n in aux_names]
-        self.outputs = []
+        self._outputs = []
         self._output_names = symbol.list_outputs()
         self._monitor_callback = None
+
+    @property
+    def outputs(self):
+        """Output arrays.  Before the first forward() they are zero arrays of the inferred shapes / dtypes (the reference
+        allocates them at bind time, so scripts read ``exe.outputs[0].shape`` right after ``bind``)."""
+        if not self._outputs:
+            try:
+                shapes = {n: a.shape for n, a in list(self.arg_dict.items()) + list(self.aux_dict.items())}
+                from .base import dtype_name
+                dtypes = {n: dtype_name(a._t.dtype) for n, a in list(self.arg_dict.items()) + list(self.aux_dict.items())}
+                _v, out_shapes, _d, out_types = self._symbol._infer(shapes, dtypes)
+                if all(s is not None for s in out_shapes):
+                    self._outputs = [nd.zeros(s, ctx=self._ctx, dtype=t) for s, t in zip(out_shapes, out_types)]
+            except Exception:  # noqa: BLE001 -- best effort; forward() fills the real values
+                pass
+        return self._outputs
+
+    @outputs.setter
+    def outputs(self, value):
+        self._outputs = value
 
     @property
     def output_dict(self):

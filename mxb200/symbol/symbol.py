@@ -440,7 +440,7 @@ class Symbol(object):
     # ---- inference -------------------------------------------------------------------------------
     def _infer(self, shapes, dtypes=None, partial=False):
         """Returns ({var_name: shape}, [out shapes], {var_name: dtype}, [out dtypes])."""
-        shapes = {k: tuple(v) for k, v in shapes.items() if v is not None}
+        shapes = {k: ((int(v),) if isinstance(v, (int, np.integer)) else tuple(v)) for k, v in shapes.items() if v is not None}
         dtypes = dict(dtypes or {})
         vals = {}
         vshape, vdtype = {}, {}

@@ -20,7 +20,7 @@ DEFAULT = ["test_attr", "test_autograd", "test_base", "test_contrib_autograd", "
            "test_executor", "test_gluon", "test_gluon_contrib", "test_gluon_data", "test_gluon_data_vision", "test_gluon_model_zoo",
            "test_gluon_rnn", "test_gluon_trainer", "test_image", "test_infer_shape", "test_infer_type", "test_init", "test_io",
            "test_kvstore", "test_loss", "test_metric", "test_model_parallel", "test_module", "test_multi_device_exec",
-           "test_ndarray", "test_optimizer", "test_profiler", "test_random", "test_recordio", "test_rnn", "test_sparse_ndarray",
+           "test_ndarray", "test_operator", "test_optimizer", "test_profiler", "test_random", "test_recordio", "test_rnn", "test_sparse_ndarray",
            "test_sparse_operator", "test_symbol", "test_thread_local", "test_viz"]
 
 
