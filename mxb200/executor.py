@@ -141,6 +141,7 @@ class Executor(object):
         else:
             with autograd.pause(train_mode=False):
                 self.outputs = self._symbol.eval_nd(feed, self._group2ctx)
+        self._ran_forward = True
         if self._monitor_callback is not None:
             for name, out in zip(self._output_names, self.outputs):
                 self._monitor_callback(name, out)
@@ -153,6 +154,8 @@ class Executor(object):
             out_grads = [out_grads]
         elif isinstance(out_grads, dict):
             out_grads = [out_grads[k] for k in self._output_names]
+        if not getattr(self, "_ran_forward", False) and self.grad_dict:
+            self.forward(is_train=is_train)      # backward() straight after bind: the graph has to be evaluated once
         heads, hgrads = [], []
         for i, o in enumerate(self.outputs):
             if not o._t.requires_grad:

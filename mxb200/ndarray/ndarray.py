@@ -663,9 +663,9 @@ def array(source, ctx=None, dtype=None):
         return NDArray(_pin_if(source.detach().to(device=ctx.torch_device, dtype=td, copy=True), ctx), ctx)
     a = np.asarray(source)
     if dtype is None:
-        dtype = a.dtype if isinstance(source, np.ndarray) and a.dtype != np.float64 else np.float32
-        if not isinstance(source, np.ndarray):
-            dtype = np.float32
+        # anything that is not already an NDArray becomes float32 unless a dtype is given (ndarray/utils.py:array of the
+        # reference: ``dtype = mx_real_t if dtype is None``) -- integer numpy arrays included
+        dtype = np.float32
     td = torch_dtype(dtype)
     t = torch.from_numpy(np.array(a, copy=True, order="C")).to(td)   # always own the memory (never alias numpy)
     if t.dim() == 0 and not isinstance(source, np.ndarray):
