@@ -449,6 +449,10 @@ class HybridBlock(Block):
 class SymbolBlock(HybridBlock):
     """Construct a block from a Symbol graph (block.py:903-1040), e.g. a model loaded with ``imports``."""
 
+    def _clear_cached_op(self):
+        # the "cached graph" of a SymbolBlock IS its definition: hybridize() / re-parenting must not drop it
+        self._cached_graph = getattr(self, "_defining_graph", ())
+
     @staticmethod
     def imports(symbol_file, input_names, param_file=None, ctx=None):
         from .. import symbol
@@ -481,6 +485,7 @@ class SymbolBlock(HybridBlock):
             if i not in input_names:
                 self.params.get(i, grad_req="null", allow_deferred_init=True)
         self._cached_graph = syms, out
+        self._defining_graph = (syms, out)
         self._input_names = [i.name for i in syms]
         self._reg_params = {}
 
@@ -494,9 +499,12 @@ class SymbolBlock(HybridBlock):
                 try:
                     feed[name] = p.data(ctx)
                 except DeferredInitializationError:
-                    shapes = self._cached_graph[1].infer_shape_partial(**{n: a.shape for n, a in zip(self._input_names, inputs)})
+                    sym_ = self._cached_graph[1]
+                    arg_s, _o, aux_s = sym_.infer_shape_partial(**{n: a.shape for n, a in zip(self._input_names, inputs)})
+                    shapes = dict(zip(sym_.list_arguments(), arg_s))
+                    shapes.update(zip(sym_.list_auxiliary_states(), aux_s))
                     for pname, shp in shapes.items():
-                        if pname in self.params._params and shp is not None:
+                        if pname in self.params._params and shp:
                             self.params[pname].shape = shp
                             self.params[pname]._finish_deferred_init()
                     feed[name] = p.data(ctx)

@@ -58,9 +58,13 @@ def clip_global_norm(arrays, max_norm, check_isfinite=True):
     total = torch.sqrt(sum((a._t.float() ** 2).sum().to(dev) for a in arrays))
     if not check_isfinite:
         scale = torch.clamp(max_norm / (total + 1e-8), max=1.0)
+        from ..ndarray.sparse import BaseSparseNDArray
         with torch.no_grad():
             for a in arrays:
-                a._t.mul_(scale.to(a._t.device, a._t.dtype))
+                if isinstance(a, BaseSparseNDArray):
+                    a *= float(scale)
+                else:
+                    a._t.mul_(scale.to(a._t.device, a._t.dtype))
         from ..ndarray import NDArray
         return NDArray(total.reshape(1), arrays[0].context)
     total_f = float(total)
@@ -69,9 +73,13 @@ def clip_global_norm(arrays, max_norm, check_isfinite=True):
         warnings.warn(UserWarning("nan or inf is detected. Clipping results will be undefined."), stacklevel=2)
     scale = max_norm / (total_f + 1e-8)
     if scale < 1.0:
+        from ..ndarray.sparse import BaseSparseNDArray
         with torch.no_grad():
             for a in arrays:
-                a._t.mul_(scale)
+                if isinstance(a, BaseSparseNDArray):
+                    a *= scale                 # sparse storage: rescale the stored values
+                else:
+                    a._t.mul_(scale)
     return total_f
 
 
