@@ -170,7 +170,12 @@ _REG["ElementWiseSum"] = add_n
 
 @register
 def where(condition, x, y, out=None):
-    return _out(_op(lambda c, a, b: torch.where(c != 0, a, b), condition, x, y), out)
+    """x where condition != 0 else y; a 1-D condition selects whole rows (control_flow_op.h WhereOpForward)."""
+    def g(c, a, b):
+        if c.dim() == 1 and a.dim() > 1:
+            c = c.reshape((-1,) + (1,) * (a.dim() - 1))
+        return torch.where(c != 0, a, b)
+    return _out(_op(g, condition, x, y), out)
 
 
 @register
@@ -296,8 +301,16 @@ _REG["Reshape"] = reshape
 
 
 @register
-def reshape_like(lhs, rhs):
-    return lhs.reshape(rhs.shape)
+def reshape_like(lhs, rhs, lhs_begin=None, lhs_end=None, rhs_begin=None, rhs_end=None, out=None):
+    """Reshape lhs like rhs; with the begin/end arguments only lhs.shape[lhs_begin:lhs_end] is replaced by
+    rhs.shape[rhs_begin:rhs_end] (matrix_op.cc ReshapeLikeParam)."""
+    if all(v is None for v in (lhs_begin, lhs_end, rhs_begin, rhs_end)):
+        return _out(lhs.reshape(rhs.shape), out)
+    ls, rs = list(lhs.shape), list(rhs.shape)
+    lb, le, _ = np.s_[lhs_begin:lhs_end].indices(len(ls))
+    rb, re_, _ = np.s_[rhs_begin:rhs_end].indices(len(rs))
+    new = tuple(ls[:lb] + rs[rb:re_] + ls[le:])
+    return _out(_op(lambda t: t.reshape(new), lhs), out)
 
 
 @register
@@ -366,11 +379,20 @@ _REG["SliceChannel"] = split
 @register
 def slice(data, begin, end, step=None, out=None):
     def g(t):
-        idx = []
+        # numpy slice semantics incl. negative steps (matrix_op-inl.h SliceParam); torch cannot index with a negative
+        # step, so those axes are gathered through an index vector
+        r = t
         for i in range(len(begin)):
             st = step[i] if step is not None and i < len(step) and step[i] is not None else 1
-            idx.append(np.s_[begin[i]:end[i]:st])
-        return t[tuple(idx)]
+            if st == 0:
+                raise MXNetError("slice: step cannot be 0")
+            b, e, st = np.s_[begin[i]:end[i]:st].indices(t.shape[i])
+            if st > 0:
+                r = r[(np.s_[:],) * i + (np.s_[b:e:st],)]
+            else:
+                idx = torch.arange(b, e, st, device=t.device)
+                r = r.index_select(i, idx)
+        return r
     return _out(_op(g, data), out)
 
 
@@ -818,7 +840,14 @@ def LayerNorm(data, gamma, beta, axis=-1, eps=1e-5, output_mean_var=False, out=N
 
 @register
 def InstanceNorm(data, gamma, beta, eps=1e-3, out=None):
-    return _out(_op(lambda x, g, b: F.instance_norm(x, weight=g, bias=b, eps=eps), data, gamma, beta), out)
+    def f(x, g, b):
+        red = tuple(range(2, x.dim()))
+        xf = x.float()
+        mean = xf.mean(dim=red, keepdim=True)
+        var = xf.var(dim=red, unbiased=False, keepdim=True)
+        shp = (1, -1) + (1,) * (x.dim() - 2)
+        return ((xf - mean) * torch.rsqrt(var + eps) * g.float().reshape(shp) + b.float().reshape(shp)).to(x.dtype)
+    return _out(_op(f, data, gamma, beta), out)
 
 
 @register

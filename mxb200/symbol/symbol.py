@@ -35,6 +35,10 @@ _PARAM_ARGS = {
     "InstanceNorm": [("gamma", False), ("beta", False)],
     "Embedding": [("weight", False)],
     "LeakyReLU": [("gamma", False)],
+    "BatchNorm_v1": [("gamma", False), ("beta", False), ("moving_mean", True), ("moving_var", True)],
+    "CuDNNBatchNorm": [("gamma", False), ("beta", False), ("moving_mean", True), ("moving_var", True)],
+    "_contrib_SyncBatchNorm": [("gamma", False), ("beta", False), ("moving_mean", True), ("moving_var", True)],
+    "Convolution_v1": [("weight", False), ("bias", False)],
     "_contrib_DeformableConvolution": [("offset", False), ("weight", False), ("bias", False)],
     "IdentityAttachKLSparseReg": [("moving_avg", True)],
 }
@@ -1113,7 +1117,7 @@ def _infer_param_shapes(node, vals, vshape, vdtype):
             nh = int(a["num_hidden"])
             inn = int(np.prod(ds[1:])) if a.get("flatten", True) else ds[-1]
             return {"weight": (nh, inn), "bias": (nh,)}[aname]
-        if op == "Convolution":
+        if op in ("Convolution", "Convolution_v1"):
             k = tuple(a["kernel"]) if not isinstance(a["kernel"], int) else (a["kernel"],) * (len(ds) - 2)
             nf, g = int(a["num_filter"]), int(a.get("num_group", 1))
             return {"weight": (nf, ds[1] // g) + k, "bias": (nf,)}[aname]
@@ -1129,7 +1133,7 @@ def _infer_param_shapes(node, vals, vshape, vdtype):
             k = tuple(a["kernel"]) if not isinstance(a["kernel"], int) else (a["kernel"],) * (len(ds) - 2)
             nf, g = int(a["num_filter"]), int(a.get("num_group", 1))
             return {"weight": (ds[1], nf // g) + k, "bias": (nf,)}[aname]
-        if op in ("BatchNorm", "InstanceNorm"):
+        if op in ("BatchNorm", "InstanceNorm", "BatchNorm_v1", "CuDNNBatchNorm", "_contrib_SyncBatchNorm"):
             return (ds[int(a.get("axis", 1))],)
         if op == "LayerNorm":
             return (ds[int(a.get("axis", -1))],)
