@@ -324,8 +324,31 @@ class CSRNDArray(BaseSparseNDArray):
         return CSRNDArray(self._data[lo:hi], self._indices[lo:hi], self._indptr[b:e + 1] - lo, (e - b, self._shape[1]), self._ctx)
 
 
+def _src_dtype(src, dtype):
+    """Default dtype of the sparse constructors: the source's own dtype for numpy / NDArray / scipy inputs, float32 for python
+    lists (ndarray/sparse.py:_prepare_default_dtype of the reference)."""
+    if dtype is not None:
+        return dtype
+    if isinstance(src, tuple) and src:
+        src = src[0]
+    if isinstance(src, (np.ndarray, NDArray)) or type(src).__module__.startswith("scipy.sparse"):
+        return src.dtype
+    return np.float32
+
+
+def array(source_array, ctx=None, dtype=None):
+    """Sparse array from a scipy.sparse matrix or another sparse NDArray (ndarray/sparse.py:array of the reference)."""
+    if isinstance(source_array, BaseSparseNDArray):
+        out = source_array.copyto(_ctx_of(ctx))
+        return out if dtype is None else out.astype(dtype)
+    if type(source_array).__module__.startswith("scipy.sparse"):
+        return csr_matrix(source_array, ctx=ctx, dtype=dtype)
+    raise ValueError("Unexpected source_array type: %s" % type(source_array))
+
+
 def row_sparse_array(arg1, shape=None, ctx=None, dtype=None):
     ctx = _ctx_of(ctx)
+    dtype = _src_dtype(arg1, dtype)
     if isinstance(arg1, tuple) and len(arg1) == 2:
         data, idx = arg1
         data = _dense_array(data, ctx=ctx, dtype=dtype)._t
@@ -340,6 +363,8 @@ def row_sparse_array(arg1, shape=None, ctx=None, dtype=None):
 
 def csr_matrix(arg1, shape=None, ctx=None, dtype=None):
     ctx = _ctx_of(ctx)
+    if not (isinstance(arg1, tuple) and len(arg1) == 2 and isinstance(arg1[0], int)):
+        dtype = _src_dtype(arg1, dtype)
     if isinstance(arg1, tuple) and len(arg1) == 3:
         data, indices, indptr = arg1
         data = _dense_array(data, ctx=ctx, dtype=dtype)._t
@@ -351,8 +376,7 @@ def csr_matrix(arg1, shape=None, ctx=None, dtype=None):
     if type(arg1).__module__.startswith("scipy.sparse"):
         m = arg1.tocsr()
         m.sort_indices()
-        return csr_matrix((m.data, m.indices, m.indptr), shape=shape or m.shape, ctx=ctx,
-                          dtype=dtype or (m.dtype if m.dtype != np.float64 else np.float32))
+        return csr_matrix((m.data, m.indices, m.indptr), shape=shape or m.shape, ctx=ctx, dtype=dtype or m.dtype)
     if isinstance(arg1, CSRNDArray):
         return arg1.copyto(ctx) if dtype is None else arg1.copyto(ctx).astype(dtype)
     if isinstance(arg1, tuple) and len(arg1) == 2 and isinstance(arg1[0], int):
