@@ -42,6 +42,24 @@ for _k, _v in _OPS.items():
         setattr(contrib, _k[len("_contrib_"):], _v)
 _sys.modules[contrib.__name__] = contrib
 
+def _rand_zipfian(true_classes, num_sampled, range_max, ctx=None):
+    """Log-uniform (Zipfian) candidate sampler for sampled-softmax style losses (ndarray/contrib.py:rand_zipfian of the
+    reference): P(class) = log((class + 2) / (class + 1)) / log(range_max + 1).  Returns (sampled classes int64,
+    expected count of the true classes, expected count of the sampled classes), both counts float64."""
+    import math as _math
+    ctx = ctx if ctx is not None else true_classes.context
+    log_range = _math.log(range_max + 1)
+    r = random.uniform(0, log_range, shape=(num_sampled,), dtype="float64", ctx=ctx)
+    sampled = NDArray(((r._t.exp() - 1).to(_torch.int64)) % range_max, ctx)
+    def _expected(cls):
+        c = cls._t.to(_torch.float64)
+        return NDArray(((c + 2.0) / (c + 1.0)).log() / log_range * num_sampled, ctx)
+    return sampled, _expected(true_classes.as_in_context(ctx)), _expected(sampled)
+
+
+import torch as _torch  # noqa: E402
+contrib.rand_zipfian = _rand_zipfian
+
 linalg = _types.ModuleType(__name__ + ".linalg")
 for _k, _v in _OPS.items():
     if _k.startswith("linalg_"):

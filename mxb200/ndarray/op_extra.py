@@ -352,7 +352,12 @@ def _sample_multinomial(data, shape=None, get_prob=False, dtype="int32", out=Non
     def g(p):
         n = 1 if shape in (None, ()) else int(np.prod(shape))
         flat = p.reshape(-1, p.shape[-1]).float()
-        idx = torch.multinomial(flat, n, replacement=True)
+        if flat.shape[-1] < (1 << 24):
+            idx = torch.multinomial(flat, n, replacement=True)
+        else:                                   # torch.multinomial is limited to 2^24 categories: inverse-CDF sampling
+            cdf = torch.cumsum(flat.double(), dim=1)
+            u = torch.rand(flat.shape[0], n, device=flat.device, dtype=torch.float64) * cdf[:, -1:]
+            idx = torch.searchsorted(cdf, u).clamp_(max=flat.shape[-1] - 1)
         tail = () if shape in (None, ()) else ((shape,) if isinstance(shape, int) else tuple(shape))
         res = idx.reshape(tuple(p.shape[:-1]) + tail).to(torch_dtype(dtype))
         if get_prob:

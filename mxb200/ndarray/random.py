@@ -26,8 +26,6 @@ def _random_helper(name, params, shape, dtype, ctx, out, kwargs):
     (one distribution per element, output shape = params.shape + shape) -- python/mxnet/ndarray/random.py:31-51."""
     from .op import _REG
     if all(isinstance(p, NDArray) for p in params):
-        if ctx is not None:
-            raise ValueError("ctx is not supported when the distribution parameters are NDArrays")
         return _REG["_sample_" + name](*params, shape=shape, dtype=dtype, out=out, **kwargs)
     if any(isinstance(p, NDArray) for p in params):
         raise ValueError("Distribution parameters must all have the same type, but got both %s" % str([type(p) for p in params]))

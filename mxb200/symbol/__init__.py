@@ -115,3 +115,19 @@ class _SymRandom(_types.ModuleType):
 
 random = _SymRandom(__name__ + ".random")
 _sys.modules[random.__name__] = random
+
+
+def _sym_rand_zipfian(true_classes, num_sampled, range_max):
+    """Symbolic log-uniform candidate sampler (symbol/contrib.py:rand_zipfian of the reference); see nd.contrib.rand_zipfian."""
+    import math as _math
+    log_range = _math.log(range_max + 1)
+    r = random.uniform(0, log_range, shape=(num_sampled,), dtype="float64")
+    sampled = _create("_mod_scalar", [_create("Cast", [_create("exp", [r], {}) - 1], {"dtype": "int64"})], {"scalar": range_max})
+
+    def expected(cls):
+        c = _create("Cast", [cls], {"dtype": "float64"})
+        return _create("log", [(c + 2.0) / (c + 1.0)], {}) / log_range * num_sampled
+    return sampled, expected(true_classes), expected(sampled)
+
+
+contrib.rand_zipfian = _sym_rand_zipfian
