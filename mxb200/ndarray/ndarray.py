@@ -588,11 +588,17 @@ def _op(fn, *arrs, **kw):
     """Run ``fn`` on unwrapped tensors honouring the autograd recording flag."""
     ctx = _result_ctx(*arrs)
     ts = [_unwrap(a) for a in arrs]
-    if _ag.is_recording():
-        r = fn(*ts, **kw)
-    else:
-        with torch.no_grad():
+    try:
+        if _ag.is_recording():
             r = fn(*ts, **kw)
+        else:
+            with torch.no_grad():
+                r = fn(*ts, **kw)
+    except MXNetError:
+        raise
+    except (RuntimeError, ValueError, IndexError) as e:
+        # every operator failure is an MXNetError for the caller, whatever the backend raised (c_api_error.h)
+        raise MXNetError("%s: %s" % (type(e).__name__, e)) from e
     for t in ts:
         e = getattr(t, "_mx_exc", None) if isinstance(t, torch.Tensor) else None
         if e is not None:                      # inputs carried a deferred failure: so do the outputs

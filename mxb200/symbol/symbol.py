@@ -955,14 +955,18 @@ def _create(op, args, kwargs):
         if sym_kwargs:
             attrs["__kwarg_inputs__"] = tuple(sym_kwargs.keys())
         if not order and not op.startswith(("_random_", "_zeros", "_ones", "_full", "_arange", "_eye")):
+            # no inputs given: every required tensor argument becomes a free variable "<node>_<argument>"
             import inspect
             fn = _ndop.get(op)
             try:
-                first = list(inspect.signature(fn).parameters.values())[0] if fn is not None else None
-            except (TypeError, ValueError, IndexError):
-                first = None
-            if first is not None and first.name in ("data", "lhs", "a") and first.default is inspect.Parameter.empty:
-                order = [var("%s_%s" % (node_name, first.name))]
+                params = list(inspect.signature(fn).parameters.values()) if fn is not None else []
+            except (TypeError, ValueError):
+                params = []
+            for prm in params:
+                if prm.kind not in (prm.POSITIONAL_ONLY, prm.POSITIONAL_OR_KEYWORD) or prm.default is not inspect.Parameter.empty \
+                        or prm.name in attrs:
+                    break
+                order.append(var("%s_%s" % (node_name, prm.name)))
     nout = _num_outputs(op, attrs)
     node = _Node(op, node_name, attrs, [s._outputs[0] for s in order], nout)
     node.var_attrs.update(node_attrs)
