@@ -129,6 +129,12 @@ def backward(heads, head_grads=None, retain_graph=False, train_mode=True):
         if not isinstance(head_grads, (list, tuple)):
             head_grads = [head_grads]
         gs = [torch.ones_like(t) if g is None else g._t for t, g in zip(ts, head_grads)]
+    # integer-valued heads (shape_array, argmax ...) are not differentiable: they contribute zero gradient
+    keep = [i for i, t in enumerate(ts) if t.is_floating_point() or t.requires_grad]
+    if len(keep) != len(ts):
+        ts, gs = [ts[i] for i in keep], [gs[i] for i in keep]
+        if not ts:
+            return
     for t in ts:
         if getattr(t, "_mx_graph_freed", False):
             from .base import MXNetError

@@ -490,17 +490,22 @@ _REG["Pad"] = pad
 
 @register
 def diag(data, k=0, out=None):
+    """k-th diagonal of a matrix, or the matrix with a vector on its k-th diagonal (tensor/diag_op-inl.h)."""
+    if data.ndim == 2 and not (-data.shape[0] < k < data.shape[1]):
+        raise MXNetError("diag: k=%d is outside of the %s matrix" % (k, str(data.shape)))
+    if data.ndim == 0:
+        raise MXNetError("diag: input must have at least 1 dimension")
     return _out(_op(lambda t: torch.diag(t, k) if t.dim() <= 2 else torch.diagonal(t, k), data), out)
 
 
 @register
 def shape_array(data):
-    return NDArray(torch.tensor(data.shape, dtype=torch.int64), data._ctx)
+    return NDArray(torch.tensor(data.shape, dtype=torch.int64, device=data._t.device), data._ctx)
 
 
 @register
 def size_array(data):
-    return NDArray(torch.tensor([data.size], dtype=torch.int64), data._ctx)
+    return NDArray(torch.tensor([data.size], dtype=torch.int64, device=data._t.device), data._ctx)
 
 
 # ---------------------------------------------------------------------------
@@ -530,6 +535,8 @@ def pick(data, index, axis=-1, keepdims=False, mode="clip", out=None):
 @register
 def one_hot(indices, depth, on_value=1.0, off_value=0.0, dtype="float32", out=None):
     def g(i):
+        if depth == 0:
+            return torch.zeros(tuple(i.shape) + (0,), dtype=torch_dtype(dtype), device=i.device)
         r = F.one_hot(i.long().clamp(0, depth - 1), depth).to(torch_dtype(dtype))
         valid = ((i >= 0) & (i < depth)).unsqueeze(-1).to(r.dtype)
         r = r * valid

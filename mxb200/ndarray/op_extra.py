@@ -649,7 +649,8 @@ class _AllReduceSum(torch.autograd.Function):
 
 # ----------------------------------------------------------------------------- misc tensor ops
 @register
-def histogram(data, bins=10, range=None, out=None, **kw):
+def histogram(data=None, bins=10, range=None, out=None, a=None, **kw):
+    data = a if data is None else data           # numpy-style keyword of the python front end: histogram(a=..., bins=...)
     """tensor/histogram.cc: returns (counts, bin_edges); ``bins`` is a count (with ``range``) or an edge array."""
     def g(t, *edges):
         x = t.float().reshape(-1)
