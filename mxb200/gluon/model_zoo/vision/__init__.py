@@ -12,6 +12,33 @@ def get_model(name, **kwargs):
             if callable(f) and n[0].islower():
                 models[n] = f
     name = name.lower()
+    # the registry names of the reference (model_zoo/vision/__init__.py): 'inceptionv3', 'squeezenet1.0', 'mobilenet0.75',
+    # 'mobilenetv2_1.0' ... next to the function names
+    alias = {"inceptionv3": "inception_v3", "squeezenet1.0": "squeezenet1_0", "squeezenet1.1": "squeezenet1_1"}
+    for w in ("1.0", "0.75", "0.5", "0.25"):
+        alias["mobilenet" + w] = "mobilenet" + w.replace(".", "_")
+        alias["mobilenetv2_" + w] = "mobilenet_v2_" + w.replace(".", "_")
+    name = alias.get(name, name)
     if name not in models:
         raise ValueError("Model %s is not supported. Available options are\n\t%s" % (name, "\n\t".join(sorted(models.keys()))))
-    return models[name](**kwargs)
+    # pretrained / root / ctx are loader options of the reference's model zoo, not constructor arguments: weights cannot be
+    # downloaded here, so pretrained=True is an error and the other two are accepted and ignored
+    if kwargs.pop("pretrained", False):
+        raise RuntimeError("pretrained weights need network access, which is not available here")
+    kwargs.pop("root", None)
+    import inspect
+    fn = models[name]
+    try:
+        accepts_ctx = "ctx" in inspect.signature(fn).parameters or any(
+            p.kind is p.VAR_KEYWORD for p in inspect.signature(fn).parameters.values())
+    except (TypeError, ValueError):
+        accepts_ctx = True
+    if not accepts_ctx:
+        kwargs.pop("ctx", None)
+    try:
+        return fn(**kwargs)
+    except TypeError as e:
+        if "ctx" in str(e) and "ctx" in kwargs:
+            kwargs.pop("ctx")
+            return fn(**kwargs)
+        raise
