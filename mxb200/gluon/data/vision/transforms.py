@@ -8,7 +8,8 @@ from ....ndarray import NDArray
 from ....ndarray.ndarray import _op
 
 __all__ = ["Compose", "Cast", "ToTensor", "Normalize", "RandomResizedCrop", "CenterCrop", "Resize", "RandomFlipLeftRight",
-           "RandomFlipTopBottom"]
+           "RandomFlipTopBottom", "RandomBrightness", "RandomContrast", "RandomSaturation", "RandomHue", "RandomColorJitter",
+           "RandomLighting"]
 
 
 class Compose(Sequential):
@@ -107,3 +108,61 @@ class RandomFlipLeftRight(HybridBlock):
 class RandomFlipTopBottom(HybridBlock):
     def hybrid_forward(self, F, x):
         return _op(lambda t: torch.flip(t, [0]) if np.random.rand() < 0.5 else t, x)
+
+
+class _ImageOp(HybridBlock):
+    _op_name, _arg_names = None, ()
+
+    def __init__(self, *args):
+        super(_ImageOp, self).__init__()
+        self._args = dict(zip(self._arg_names, args))
+
+    def hybrid_forward(self, F, x):
+        return getattr(F.image, self._op_name)(x, **self._args)
+
+
+def _jitter_range(v):
+    return max(0, 1 - v), 1 + v
+
+
+class RandomBrightness(_ImageOp):
+    """Scale brightness by a factor drawn from [max(0, 1 - b), 1 + b] (transforms.py:RandomBrightness of the reference)."""
+    _op_name, _arg_names = "random_brightness", ("min_factor", "max_factor")
+
+    def __init__(self, brightness):
+        super(RandomBrightness, self).__init__(*_jitter_range(brightness))
+
+
+class RandomContrast(_ImageOp):
+    _op_name, _arg_names = "random_contrast", ("min_factor", "max_factor")
+
+    def __init__(self, contrast):
+        super(RandomContrast, self).__init__(*_jitter_range(contrast))
+
+
+class RandomSaturation(_ImageOp):
+    _op_name, _arg_names = "random_saturation", ("min_factor", "max_factor")
+
+    def __init__(self, saturation):
+        super(RandomSaturation, self).__init__(*_jitter_range(saturation))
+
+
+class RandomHue(_ImageOp):
+    _op_name, _arg_names = "random_hue", ("min_factor", "max_factor")
+
+    def __init__(self, hue):
+        super(RandomHue, self).__init__(*_jitter_range(hue))
+
+
+class RandomColorJitter(_ImageOp):
+    _op_name, _arg_names = "random_color_jitter", ("brightness", "contrast", "saturation", "hue")
+
+    def __init__(self, brightness=0, contrast=0, saturation=0, hue=0):
+        super(RandomColorJitter, self).__init__(brightness, contrast, saturation, hue)
+
+
+class RandomLighting(_ImageOp):
+    _op_name, _arg_names = "random_lighting", ("alpha_std",)
+
+    def __init__(self, alpha):
+        super(RandomLighting, self).__init__(alpha)

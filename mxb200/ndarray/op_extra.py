@@ -1028,3 +1028,116 @@ def FusedResNet(data, num_layers=50, version="v1b", classes=1000, thumbnail=Fals
         x = x.contiguous()
         return R.resnet_forward(spec, P, A, x, training=training, eps=float(eps), momentum=float(momentum))
     return _out(_op(g, data, *arrs), out)
+
+
+# ----------------------------------------------------------------------------- image augmentation operators (image/image_random-inl.h)
+# HWC (or NHWC) uint8 / float images, as produced by the decoders.
+def _img_op(name):
+    def deco(f):
+        _REG["_image_" + name] = f
+        return f
+    return deco
+
+
+@_img_op("flip_left_right")
+def image_flip_left_right(data, out=None):
+    return _out(_op(lambda t: torch.flip(t, [t.dim() - 2]), data), out)
+
+
+@_img_op("flip_top_bottom")
+def image_flip_top_bottom(data, out=None):
+    return _out(_op(lambda t: torch.flip(t, [t.dim() - 3]), data), out)
+
+
+@_img_op("random_flip_left_right")
+def image_random_flip_left_right(data, out=None):
+    return image_flip_left_right(data, out=out) if np.random.rand() < 0.5 else _out(data, out)
+
+
+@_img_op("random_flip_top_bottom")
+def image_random_flip_top_bottom(data, out=None):
+    return image_flip_top_bottom(data, out=out) if np.random.rand() < 0.5 else _out(data, out)
+
+
+def _gray(t):
+    w = torch.tensor([0.299, 0.587, 0.114], device=t.device, dtype=torch.float32)
+    return (t.float() * w).sum(-1, keepdim=True)
+
+
+def _blend(t, other, alpha):
+    r = t.float() * alpha + other * (1.0 - alpha)
+    return (r.clamp(0, 255) if t.dtype is torch.uint8 else r).to(t.dtype)
+
+
+@_img_op("adjust_lighting")
+def image_adjust_lighting(data, alpha, out=None):
+    """AlexNet-style PCA lighting noise with the ImageNet eigen decomposition."""
+    eigval = torch.tensor([55.46, 4.794, 1.148])
+    eigvec = torch.tensor([[-0.5675, 0.7192, 0.4009], [-0.5808, -0.0045, -0.8140], [-0.5836, -0.6948, 0.4203]])
+
+    def g(t):
+        a = torch.tensor(list(alpha), dtype=torch.float32)
+        rgb = (eigvec * a * eigval).sum(1).to(t.device)
+        r = t.float() + rgb
+        return (r.clamp(0, 255) if t.dtype is torch.uint8 else r).to(t.dtype)
+    return _out(_op(g, data), out)
+
+
+@_img_op("random_lighting")
+def image_random_lighting(data, alpha_std=0.05, out=None):
+    return image_adjust_lighting(data, alpha=tuple(np.random.normal(0, alpha_std, 3)), out=out)
+
+
+def _rand_factor(lo, hi):
+    return float(np.random.uniform(lo, hi))
+
+
+@_img_op("random_brightness")
+def image_random_brightness(data, min_factor, max_factor, out=None):
+    a = _rand_factor(min_factor, max_factor)
+    return _out(_op(lambda t: _blend(t, torch.zeros((), device=t.device), a), data), out)
+
+
+@_img_op("random_contrast")
+def image_random_contrast(data, min_factor, max_factor, out=None):
+    a = _rand_factor(min_factor, max_factor)
+    return _out(_op(lambda t: _blend(t, _gray(t).mean(), a), data), out)
+
+
+@_img_op("random_saturation")
+def image_random_saturation(data, min_factor, max_factor, out=None):
+    a = _rand_factor(min_factor, max_factor)
+    return _out(_op(lambda t: _blend(t, _gray(t), a), data), out)
+
+
+@_img_op("random_hue")
+def image_random_hue(data, min_factor, max_factor, out=None):
+    """Rotate the chroma plane in YIQ space by a random angle (image_random-inl.h RandomHue)."""
+    a = _rand_factor(min_factor, max_factor) - 1.0
+
+    def g(t):
+        h = a * np.pi
+        u, w = np.cos(h), np.sin(h)
+        tyiq = torch.tensor([[0.299, 0.587, 0.114], [0.596, -0.274, -0.321], [0.211, -0.523, 0.311]])
+        ityiq = torch.tensor([[1.0, 0.956, 0.621], [1.0, -0.272, -0.647], [1.0, -1.107, 1.705]])
+        rot = torch.tensor([[1.0, 0.0, 0.0], [0.0, u, -w], [0.0, w, u]], dtype=torch.float32)
+        m = (ityiq @ rot @ tyiq).t().to(t.device)
+        r = t.float() @ m
+        return (r.clamp(0, 255) if t.dtype is torch.uint8 else r).to(t.dtype)
+    return _out(_op(g, data), out)
+
+
+@_img_op("random_color_jitter")
+def image_random_color_jitter(data, brightness=0.0, contrast=0.0, saturation=0.0, hue=0.0, out=None):
+    fns = []
+    if brightness > 0:
+        fns.append(lambda d: image_random_brightness(d, max(0, 1 - brightness), 1 + brightness))
+    if contrast > 0:
+        fns.append(lambda d: image_random_contrast(d, max(0, 1 - contrast), 1 + contrast))
+    if saturation > 0:
+        fns.append(lambda d: image_random_saturation(d, max(0, 1 - saturation), 1 + saturation))
+    if hue > 0:
+        fns.append(lambda d: image_random_hue(d, max(0, 1 - hue), 1 + hue))
+    for i in np.random.permutation(len(fns)):
+        data = fns[i](data)
+    return _out(data, out)
