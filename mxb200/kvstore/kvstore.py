@@ -286,14 +286,13 @@ class KVStoreLocal(KVStore):
             if ik not in self._store:
                 raise MXNetError("key %s has not been initialized" % str(k))
             stored = self._store[ik]
-            if isinstance(stored, _sp.RowSparseNDArray):
-                if ignore_sparse:
-                    continue
-                raise MXNetError("pull with row_sparse stored value: use row_sparse_pull")
+            if isinstance(stored, _sp.RowSparseNDArray) and ignore_sparse:
+                continue                      # kvstore.py:pull -- sparse values are skipped unless ignore_sparse=False
             for o in olist:
                 if isinstance(o, _sp.BaseSparseNDArray):
-                    if not ignore_sparse:
-                        raise MXNetError("pull into a sparse output is not supported; use row_sparse_pull")
+                    if ignore_sparse:
+                        continue
+                    o[:] = stored             # full row_sparse value into a row_sparse output
                     continue
                 with torch.no_grad():
                     o._t.copy_(stored._t, non_blocking=True)
@@ -306,6 +305,9 @@ class KVStoreLocal(KVStore):
         for k, olist, rlist in zip(keys, outs, rids):
             ik = self._int_key(k)
             stored = self._store[ik]
+            for o in olist:
+                if not isinstance(o, _sp.RowSparseNDArray):
+                    raise MXNetError("row_sparse_pull: the output for key %s must be a row_sparse NDArray" % str(k))
             dense = stored.todense()._t if isinstance(stored, _sp.RowSparseNDArray) else stored._t
             if len(rlist) == 1 and len(olist) > 1:
                 rlist = rlist * len(olist)
