@@ -114,8 +114,25 @@ def mark_variables(variables, gradients, grad_reqs="write"):
         variables, gradients = [variables], [gradients]
     if isinstance(grad_reqs, str):
         grad_reqs = [grad_reqs] * len(variables)
+    from .ndarray.sparse import BaseSparseNDArray
+    from .ndarray.ndarray import NDArray
     for v, g, r in zip(variables, gradients, grad_reqs):
         v.attach_grad(r)
+        if isinstance(v, BaseSparseNDArray) or isinstance(g, BaseSparseNDArray):
+            # sparse storage cannot alias the dense buffer autograd accumulates into: mirror it after every backward
+            leaf = v.__dict__["_dense_leaf"]._t if isinstance(v, BaseSparseNDArray) else v._t
+
+            def _mirror(p, g=g):
+                if p.grad is not None:
+                    g[:] = NDArray(p.grad.detach().clone(), g.context)
+            if not hasattr(v, "_mirror_hooks"):
+                try:
+                    v._mirror_hooks = []
+                except AttributeError:
+                    pass
+            h = leaf.register_post_accumulate_grad_hook(_mirror)
+            getattr(v, "_mirror_hooks", []).append(h)
+            continue
         v._t.grad = g._t
 
 

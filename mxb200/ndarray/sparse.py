@@ -62,8 +62,10 @@ class BaseSparseNDArray(NDArray):
     @property
     def _t(self):
         """Dense torch view for operators without a sparse kernel (the reference's storage fallback).  READ ONLY: writes
-        go through ``x[:] = value`` / ``copyto``."""
-        return self.todense()._t
+        go through ``x[:] = value`` / ``copyto``.  After ``attach_grad()`` the dense leaf that owns the gradient is returned, so
+        operators recorded by autograd are connected to it."""
+        leaf = self.__dict__.get("_dense_leaf")
+        return leaf._t if leaf is not None else self.todense()._t
 
     @_t.setter
     def _t(self, value):
