@@ -178,8 +178,10 @@ class LSTMCell(BaseRNNCell):
     def __init__(self, num_hidden, prefix="lstm_", params=None, forget_bias=1.0):
         super(LSTMCell, self).__init__(prefix=prefix, params=params)
         self._num_hidden = num_hidden
+        from .. import initializer as _init
         self._iW, self._hW = self.params.get("i2h_weight"), self.params.get("h2h_weight")
-        self._iB = self.params.get("i2h_bias")
+        # the forget-gate slice of the input bias starts at forget_bias (rnn_cell.py:408-412 of the reference)
+        self._iB = self.params.get("i2h_bias", init=_init.LSTMBias(forget_bias=forget_bias))
         self._hB = self.params.get("h2h_bias")
         self._forget_bias = forget_bias
 
@@ -201,8 +203,8 @@ class LSTMCell(BaseRNNCell):
         forget_gate = symbol.Activation(gates[1], act_type="sigmoid", name="%sf" % name)
         in_transform = symbol.Activation(gates[2], act_type="tanh", name="%sc" % name)
         out_gate = symbol.Activation(gates[3], act_type="sigmoid", name="%so" % name)
-        next_c = forget_gate * states[1] + in_gate * in_transform
-        next_h = out_gate * symbol.Activation(next_c, act_type="tanh", name="%sstate_act" % name)
+        next_c = symbol._internal._plus(forget_gate * states[1], in_gate * in_transform, name="%sstate" % name)
+        next_h = symbol._internal._mul(out_gate, symbol.Activation(next_c, act_type="tanh"), name="%sout" % name)
         return next_h, [next_h, next_c]
 
 
@@ -232,7 +234,7 @@ class GRUCell(BaseRNNCell):
         reset_gate = symbol.Activation(i2h_r + h2h_r, act_type="sigmoid", name="%sr_act" % name)
         update_gate = symbol.Activation(i2h_z + h2h_z, act_type="sigmoid", name="%sz_act" % name)
         next_h_tmp = symbol.Activation(i2h + reset_gate * h2h, act_type="tanh", name="%sh_act" % name)
-        next_h = (1.0 - update_gate) * next_h_tmp + update_gate * prev
+        next_h = symbol._internal._plus((1.0 - update_gate) * next_h_tmp, update_gate * prev, name="%sout" % name)
         return next_h, [next_h]
 
 
