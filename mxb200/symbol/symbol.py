@@ -1153,6 +1153,13 @@ def _infer_param_shapes(node, vals, vshape, vdtype):
             return ds
         return None
     for (inp, idx), aname in zip(node.inputs, present):
+        if inp.op is None and (id(inp), idx) in vals and aname not in ("data", "label") and fused_shapes is None:
+            # a shape given by the caller must agree with what the operator implies (InferShape consistency check)
+            want = rule(aname)
+            have = tuple(vals[(id(inp), idx)].shape)
+            if want is not None and tuple(want) != have:
+                raise MXNetError("infer_shape: shape inconsistent for %s of node %s: provided %s, inferred %s"
+                                 % (inp.name, node.name, str(have), str(tuple(want))))
         if inp.op is None and (id(inp), idx) not in vals and aname != "data":
             shp = rule(aname)
             if shp is not None:
