@@ -240,6 +240,10 @@ class NDArray(object):
         key = _unwrap_key(key)
         return _op(lambda t: t[key], self)
 
+    def __iter__(self):
+        for i in range(self.shape[0] if self.ndim else 0):
+            yield self[i]
+
     def __setitem__(self, key, value):
         key = _unwrap_key(key)
         with torch.no_grad():
@@ -596,7 +600,7 @@ def _op(fn, *arrs, **kw):
                 r = fn(*ts, **kw)
     except MXNetError:
         raise
-    except (RuntimeError, ValueError, IndexError) as e:
+    except (RuntimeError, ValueError) as e:      # (IndexError stays: python's iteration protocol depends on it)
         # every operator failure is an MXNetError for the caller, whatever the backend raised (c_api_error.h)
         raise MXNetError("%s: %s" % (type(e).__name__, e)) from e
     for t in ts:

@@ -151,3 +151,11 @@ def test_asnumpy_returns_a_private_copy():
     n = a.asnumpy()
     a[:] = 5
     assert n.tolist() == [1, 1, 1] and a.asnumpy().tolist() == [5, 5, 5]
+
+
+def test_iteration_over_first_axis_terminates():
+    """``for row in arr`` uses the __getitem__/IndexError protocol (or __iter__): it must stop after shape[0] rows."""
+    a = mx.nd.arange(0, 6).reshape((3, 2))
+    assert [r.asnumpy().tolist() for r in a] == [[0.0, 1.0], [2.0, 3.0], [4.0, 5.0]]
+    with pytest.raises(IndexError):
+        a[5]
