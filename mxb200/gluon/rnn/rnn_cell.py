@@ -4,7 +4,7 @@ from ...ndarray import zeros
 from ... import ndarray as nd
 
 __all__ = ["RecurrentCell", "HybridRecurrentCell", "RNNCell", "LSTMCell", "GRUCell", "SequentialRNNCell", "DropoutCell",
-           "ResidualCell", "BidirectionalCell"]
+           "ResidualCell", "BidirectionalCell", "ZoneoutCell", "HybridSequentialRNNCell", "ModifierCell"]
 
 
 class RecurrentCell(Block):
@@ -35,6 +35,9 @@ class RecurrentCell(Block):
     def unroll(self, length, inputs, begin_state=None, layout="NTC", merge_outputs=None, valid_length=None):
         self.reset()
         axis = layout.find("T")
+        from ... import symbol as _sym
+        if isinstance(inputs, _sym.Symbol) or (isinstance(inputs, (list, tuple)) and inputs and isinstance(inputs[0], _sym.Symbol)):
+            return self._unroll_symbolic(_sym, length, inputs, begin_state, axis, merge_outputs)
         if isinstance(inputs, nd.NDArray):
             batch_size = inputs.shape[layout.find("N")]
             seq = [x.squeeze(axis) for x in nd.split(inputs, num_outputs=length, axis=axis, squeeze_axis=False)] if length > 1 \
@@ -53,6 +56,34 @@ class RecurrentCell(Block):
             outputs = nd.stack(*outputs, axis=axis)
         return outputs, states
 
+    def _unroll_symbolic(self, F, length, inputs, begin_state, axis, merge_outputs):
+        """unroll() on Symbols (rnn_cell.py:RecurrentCell.unroll of the reference): the steps become graph nodes named
+        ``<prefix>t<k>_*``.  Default begin states are zeros derived from the first step's input, so no unknown (0)
+        dimension enters the graph."""
+        if isinstance(inputs, F.Symbol):
+            seq = list(F.split(inputs, axis=axis, num_outputs=length, squeeze_axis=True)) if length > 1 \
+                else [F.squeeze(inputs, axis=axis)]
+        else:
+            seq = list(inputs)
+        assert len(seq) == length, "unroll: got %d step inputs for length %d" % (len(seq), length)
+        if begin_state is None:
+            begin_state = []
+            col = F.sum(F.zeros_like(F.reshape(seq[0], shape=(0, -1))), axis=1, keepdims=True)      # (N, 1) of zeros
+            for info in self.state_info(0):
+                tail = tuple(info["shape"][1:])
+                st = F.reshape(col, shape=(-1,) + (1,) * len(tail)) if len(tail) != 1 else col
+                for ax, size in enumerate(tail, start=1):
+                    st = F.broadcast_axis(st, axis=ax, size=size)
+                begin_state.append(st)
+        states = begin_state
+        outputs = []
+        for i in range(length):
+            output, states = self(seq[i], states)
+            outputs.append(output)
+        if merge_outputs:
+            outputs = F.stack(*outputs, axis=axis)
+        return outputs, states
+
     def forward(self, inputs, states):
         self._counter += 1
         return super(RecurrentCell, self).forward(inputs, states)
@@ -64,6 +95,11 @@ class HybridRecurrentCell(RecurrentCell, HybridBlock):
 
     def forward(self, inputs, states):
         self._counter += 1
+        from ... import symbol as _sym
+        if isinstance(inputs, _sym.Symbol):
+            params = {i: j.var() for i, j in self._reg_params.items()}
+            with self.name_scope():
+                return self.hybrid_forward(_sym, inputs, states, **params)
         ctx = inputs.context
         try:
             params = {i: j.data(ctx) for i, j in self._reg_params.items()}
@@ -105,9 +141,10 @@ class RNNCell(_BaseCell):
         return "rnn"
 
     def hybrid_forward(self, F, inputs, states, i2h_weight, h2h_weight, i2h_bias, h2h_bias):
-        i2h = F.FullyConnected(inputs, i2h_weight, i2h_bias, num_hidden=self._hidden_size)
-        h2h = F.FullyConnected(states[0], h2h_weight, h2h_bias, num_hidden=self._hidden_size)
-        output = F.Activation(i2h + h2h, act_type=self._activation)
+        prefix = "t%d_" % self._counter          # node names of the reference (rnn_cell.py:RNNCell.hybrid_forward)
+        i2h = F.FullyConnected(inputs, i2h_weight, i2h_bias, num_hidden=self._hidden_size, name=prefix + "i2h")
+        h2h = F.FullyConnected(states[0], h2h_weight, h2h_bias, num_hidden=self._hidden_size, name=prefix + "h2h")
+        output = F.Activation(i2h + h2h, act_type=self._activation, name=prefix + "out")
         return output, [output]
 
 
@@ -122,14 +159,15 @@ class LSTMCell(_BaseCell):
                 {"shape": (batch_size, self._hidden_size), "__layout__": "NC"}]
 
     def hybrid_forward(self, F, inputs, states, i2h_weight, h2h_weight, i2h_bias, h2h_bias):
-        i2h = F.FullyConnected(inputs, i2h_weight, i2h_bias, num_hidden=self._hidden_size * 4)
-        h2h = F.FullyConnected(states[0], h2h_weight, h2h_bias, num_hidden=self._hidden_size * 4)
+        prefix = "t%d_" % self._counter
+        i2h = F.FullyConnected(inputs, i2h_weight, i2h_bias, num_hidden=self._hidden_size * 4, name=prefix + "i2h")
+        h2h = F.FullyConnected(states[0], h2h_weight, h2h_bias, num_hidden=self._hidden_size * 4, name=prefix + "h2h")
         gates = i2h + h2h
-        s = F.split(gates, num_outputs=4, axis=1)
+        s = F.split(gates, num_outputs=4, axis=1, name=prefix + "slice")
         in_gate, forget_gate = F.sigmoid(s[0]), F.sigmoid(s[1])
         in_transform, out_gate = F.tanh(s[2]), F.sigmoid(s[3])
-        next_c = forget_gate * states[1] + in_gate * in_transform
-        next_h = out_gate * F.tanh(next_c)
+        next_c = F._internal._plus(forget_gate * states[1], in_gate * in_transform, name=prefix + "state")
+        next_h = F._internal._mul(out_gate, F.tanh(next_c), name=prefix + "out")
         return next_h, [next_h, next_c]
 
 
@@ -140,15 +178,16 @@ class GRUCell(_BaseCell):
         return "gru"
 
     def hybrid_forward(self, F, inputs, states, i2h_weight, h2h_weight, i2h_bias, h2h_bias):
+        prefix = "t%d_" % self._counter
         prev = states[0]
-        i2h = F.FullyConnected(inputs, i2h_weight, i2h_bias, num_hidden=self._hidden_size * 3)
-        h2h = F.FullyConnected(prev, h2h_weight, h2h_bias, num_hidden=self._hidden_size * 3)
-        i2h_r, i2h_z, i2h = F.split(i2h, num_outputs=3, axis=1)
-        h2h_r, h2h_z, h2h = F.split(h2h, num_outputs=3, axis=1)
+        i2h = F.FullyConnected(inputs, i2h_weight, i2h_bias, num_hidden=self._hidden_size * 3, name=prefix + "i2h")
+        h2h = F.FullyConnected(prev, h2h_weight, h2h_bias, num_hidden=self._hidden_size * 3, name=prefix + "h2h")
+        i2h_r, i2h_z, i2h = F.split(i2h, num_outputs=3, axis=1, name=prefix + "i2h_slice")
+        h2h_r, h2h_z, h2h = F.split(h2h, num_outputs=3, axis=1, name=prefix + "h2h_slice")
         reset_gate = F.sigmoid(i2h_r + h2h_r)
         update_gate = F.sigmoid(i2h_z + h2h_z)
         next_h_tmp = F.tanh(i2h + reset_gate * h2h)
-        next_h = (1. - update_gate) * next_h_tmp + update_gate * prev
+        next_h = F._internal._plus((1. - update_gate) * next_h_tmp, update_gate * prev, name=prefix + "out")
         return next_h, [next_h]
 
 
@@ -214,6 +253,49 @@ class ResidualCell(RecurrentCell):
         return output + inputs, states
 
 
+class ZoneoutCell(RecurrentCell):
+    """Zoneout (Krueger et al. 2016): with probability ``zoneout_states`` a state unit keeps its previous value, with
+    ``zoneout_outputs`` an output unit keeps the previous output (rnn_cell.py:ZoneoutCell of the reference)."""
+
+    def __init__(self, base_cell, zoneout_outputs=0., zoneout_states=0.):
+        assert not isinstance(base_cell, BidirectionalCell), "BidirectionalCell doesn't support zoneout since it doesn't " \
+            "support step. Please add ZoneoutCell to the cells underneath instead."
+        super(ZoneoutCell, self).__init__(prefix=base_cell.prefix + "zoneout_", params=None)
+        self.base_cell = base_cell
+        self.zoneout_outputs, self.zoneout_states = zoneout_outputs, zoneout_states
+        self._prev_output = None
+
+    def state_info(self, batch_size=0):
+        return self.base_cell.state_info(batch_size)
+
+    def begin_state(self, batch_size=0, **kwargs):
+        return self.base_cell.begin_state(batch_size, **kwargs)
+
+    def _alias(self):
+        return "zoneout"
+
+    def reset(self):
+        super(ZoneoutCell, self).reset()
+        if getattr(self, "base_cell", None) is not None:      # reset() is also called by the base constructor
+            self.base_cell.reset()
+        self._prev_output = None
+
+    def __call__(self, inputs, states):
+        from ... import symbol as _sym
+        F = _sym if isinstance(inputs, _sym.Symbol) else nd
+        next_output, next_states = self.base_cell(inputs, states)
+
+        def mask(p, like):
+            return F.Dropout(F.ones_like(like), p=p)
+        prev_output = self._prev_output if self._prev_output is not None else F.zeros_like(next_output)
+        output = F.where(mask(self.zoneout_outputs, next_output), next_output, prev_output) \
+            if self.zoneout_outputs != 0. else next_output
+        new_states = [F.where(mask(self.zoneout_states, ns), ns, os) for ns, os in zip(next_states, states)] \
+            if self.zoneout_states != 0. else next_states
+        self._prev_output = output
+        return output, new_states
+
+
 class BidirectionalCell(RecurrentCell):
     def __init__(self, l_cell, r_cell, output_prefix="bi_"):
         super(BidirectionalCell, self).__init__(prefix="", params=None)
@@ -239,3 +321,8 @@ class BidirectionalCell(RecurrentCell):
         r_out, r_st = self.r_cell.unroll(length, nd.flip(inputs, axis=axis), begin_state[nl:], layout, merge_outputs=True)
         out = nd.concat(l_out, nd.flip(r_out, axis=axis), dim=2)
         return out, l_st + r_st
+
+
+# the reference distinguishes a hybridizable stack; every cell here runs on both NDArrays and Symbols
+HybridSequentialRNNCell = SequentialRNNCell
+ModifierCell = ResidualCell.__mro__[1] if False else RecurrentCell
