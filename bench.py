@@ -1,17 +1,23 @@
 #!/usr/bin/env python
 """Headline benchmark: ResNet-50 (v1b) ImageNet-shape training throughput, images/sec, whole job.
 
-    python bench.py --gpus N --steps K --warmup W            # our framework (one rank per GPU under torchrun for N>1)
-    python bench.py --impl reference ...                     # the unmodified reference (unavailable here: see DESIGN.md)
+    python bench.py --gpus N --steps K --warmup W                 # this framework (one rank per GPU under torchrun for N>1)
+    python bench.py --impl reference ...                          # the UNMODIFIED reference (MXNet 1.3.1 fork) from baseline/_ref,
+                                                                  #   its own Module.fit + SyntheticDataIter + kvstore('device')
+    python bench.py --impl library ...                            # library anchor: torchvision ResNet-50, cuDNN/cuBLAS, NCCL allreduce
 
-Protocol (see task contract): W warm-up steps, then exactly K timed steps bracketed by barrier +
-torch.cuda.synchronize(), timed with CUDA events on the launching stream, max over ranks.  Two timed regions:
+Protocol (task contract): W warm-up steps, then exactly K timed steps bracketed by barrier + torch.cuda.synchronize(),
+timed with CUDA events on the launching stream, max over ranks.  Two timed regions:
   value : device-resident synthetic batch (the reference's own ``--benchmark 1`` SyntheticDataIter mode,
           example/image-classification/common/data.py:98-130)
   e2e   : every step copies that step's uint8 NHWC batch + labels host(pinned)->device and reads the loss back
-          device->host, through the public gluon API.
-Every step is a full training step: forward, loss, backward, fused allreduce + NAG-momentum update with fp32
-master weights (nothing skipped).  Synthetic data, random-init weights (no network in this environment).
+          device->host, through the public gluon API (mx.io.DevicePrefetcher + mx.gluon.TrainStep).
+Every step is a full training step: forward, loss, backward, fused allreduce + NAG-momentum update with fp32 master
+weights (nothing skipped).  Synthetic data, random-init weights (no network in this environment).
+
+Steady-state steps are replayed from ONE captured CUDA graph (mx.gluon.TrainStep): the host issues one graph launch per
+step, so ranks cannot skew each other at the in-kernel cross-GPU barrier.  ``--no-graph`` runs the eager dispatch path.
+Per-step device times (min / median / max, per rank) are reported so that a straggler is visible.
 """
 import argparse
 import json
@@ -23,6 +29,7 @@ import threading
 import time
 
 BASELINE_V100_FP32_IMG_S = 363.69   # ResNet-50 train fp32 1xV100 batch 128 (docs/faq/perf.md:216)
+ROOT = os.path.dirname(os.path.abspath(__file__))
 
 
 def parse():
@@ -30,7 +37,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "library"])
     ap.add_argument("--batch", type=int, default=512,
                     help="per-GPU batch (weak scaling); 512 x 8 GPUs = the global batch 4096 of the reference recipe "
                          "(example/dynamic-training/run.sh:16)")
@@ -38,11 +45,15 @@ def parse():
     ap.add_argument("--classes", type=int, default=1000)
     ap.add_argument("--layers", type=int, default=50)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager python dispatch instead of CUDA-graph replay")
+    ap.add_argument("--ref-dtype", default="float16", help="reference arm dtype (the fork's recipe is fp16 + fp32 master)")
     return ap.parse_args()
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  The sampler
+    process is forked once, before the timed regions (a fork inside one would perturb the launching thread); samples are
+    attributed to a region by host timestamps."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -64,18 +75,24 @@ class ClockSampler(object):
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
+
+    def summary(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ts, ln in list(self.lines):
+            if ts < t0 or ts > t1 + 0.25:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -90,30 +107,194 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _dist_env():
+    return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+# ======================================================================================= reference arm
 def reference_arm(args):
-    # The reference is an MXNet 1.3.1 source tree: python/setup.py needs a prebuilt libmxnet.so, whose native build
-    # needs CUDA 9-era cuDNN APIs, OpenCV, BLAS and wget-ed ps-lite deps (Makefile:344, 3rdparty/ps-lite/make/deps.mk).
-    # Both offline install attempts failed (baseline/ref_install*.log, DESIGN.md "Reference arm").
-    print(json.dumps({"impl": "reference", "unavailable":
-                      "reference is an MXNet-1.3.1 source tree; pip install fails: no setup.py at root and "
-                      "python/setup.py cannot find libmxnet.so (native build needs cuDNN7/OpenCV/network)"}))
+    """The unmodified reference: ``import mxnet`` from baseline/_ref (built by baseline/build_ref.sh from /root/reference),
+    its own symbol zoo (example/image-classification/symbols/resnet.py), Module.fit-style loop pieces (bind / init_optimizer /
+    forward_backward / update), SyntheticDataIter-equivalent device-resident batch and kvstore('device') over N GPUs of ONE
+    process -- the reference's process model (python/mxnet/module/executor_group.py:143-305).  Under torchrun only rank 0
+    drives the job; the other ranks exit silently."""
+    world, rank, _lr = _dist_env()
+    if rank != 0:
+        return 0
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    lib = os.path.join(ref, "mxnet", "libmxnet.so")
+    if not os.path.exists(lib):
+        why = "baseline/_ref/mxnet/libmxnet.so not built (baseline/build_ref.sh; see baseline/ref_build.log and DESIGN.md section 3)"
+        print(json.dumps({"impl": "reference", "unavailable": why}))
+        return 0
+    # run in a clean interpreter: mxnet's ctypes loader and torch's CUDA libraries should not share a process
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "run_reference.py"), "--gpus", str(args.gpus), "--steps", str(args.steps),
+           "--warmup", str(args.warmup), "--batch", str(args.batch), "--image", str(args.image), "--classes", str(args.classes),
+           "--layers", str(args.layers), "--dtype", args.ref_dtype]
+    env = dict(os.environ)
+    env["PYTHONPATH"] = ref + os.pathsep + env.get("PYTHONPATH", "")
+    env["MXNET_LIBRARY_PATH"] = lib
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    line = None
+    for ln in r.stdout.splitlines():
+        if ln.startswith("{") and '"impl"' in ln:
+            line = ln
+    if r.returncode != 0 or line is None:
+        tail = (r.stderr or r.stdout or "").strip().splitlines()[-1:] or ["no output"]
+        print(json.dumps({"impl": "reference", "unavailable": "reference run failed (rc=%d): %s" % (r.returncode, tail[0][:300])}))
+        return 0
+    print(line)
     return 0
 
 
+# ======================================================================================= shared timing helpers
+class Timing(object):
+    def __init__(self, torch, dist, dev, world, local_rank):
+        self.torch, self.dist, self.dev, self.world = torch, dist, dev, world
+        self.sampler = ClockSampler(local_rank)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def timed(self, fn, steps, after=None, count=None):
+        torch = self.torch
+        self.barrier()
+        l0 = count() if count else 0
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        t0 = time.time()
+        ev[0].record()
+        for i in range(steps):
+            fn()
+            ev[i + 1].record()
+        if after is not None:
+            after()                                # e.g. consume the last outstanding device->host read
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        self.barrier()
+        t1 = time.time()
+        ms = ev[0].elapsed_time(end)
+        per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+        launches = (count() - l0) if count else 0
+        mine = [min(per), statistics.median(per), max(per), ms]
+        if self.world > 1:
+            t = torch.tensor(mine, device=self.dev)
+            allr = [torch.zeros_like(t) for _ in range(self.world)]
+            self.dist.all_gather(allr, t)
+            rows = [[float(v) for v in a.tolist()] for a in allr]
+        else:
+            rows = [mine]
+        ms_max = max(r[3] for r in rows)
+        step_stats = {"per_rank_ms_min_med_max": [[round(r[0], 3), round(r[1], 3), round(r[2], 3)] for r in rows],
+                      "per_rank_total_ms": [round(r[3], 2) for r in rows]}
+        return ms_max, self.sampler.summary(t0, t1), launches, step_stats
+
+
+# ======================================================================================= library arm
+def library_arm(args):
+    """Library anchor ("NCCL + library ops only"): torchvision ResNet-50 (v1.5 == v1b: stride on the 3x3),
+    channels_last, bf16 autocast over fp32 master parameters, SGD nesterov momentum 0.9 wd 1e-4 (torch's fused/foreach
+    implementation), cuDNN convolutions / batch-norm, cuBLAS FC, DistributedDataParallel (bucketed NCCL all_reduce overlapped
+    with the backward pass).  Same batch, steps, warm-up, timing and JSON schema as ours; none of our kernels run here."""
+    import torch
+    import torch.distributed as dist
+    import torchvision
+    world, rank, local_rank = _dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    torch.backends.cudnn.benchmark = True
+    B, S = args.batch, args.image
+    model = torchvision.models.resnet50(num_classes=args.classes).to(dev).to(memory_format=torch.channels_last)
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, nesterov=True, weight_decay=1e-4, fused=True)
+    lossf = torch.nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_img = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).pin_memory()
+    host_lab = torch.randint(0, args.classes, (B,), generator=g, dtype=torch.int64).pin_memory()
+    mean = torch.tensor([123.68, 116.28, 103.53], device=dev).view(1, 3, 1, 1)
+    istd = 1.0 / torch.tensor([58.395, 57.12, 57.375], device=dev).view(1, 3, 1, 1)
+
+    def to_dev():
+        img = host_img.to(dev, non_blocking=True).permute(0, 3, 1, 2)          # NCHW view of NHWC memory == channels_last
+        lab = host_lab.to(dev, non_blocking=True)
+        return ((img.float() - mean) * istd).contiguous(memory_format=torch.channels_last), lab
+
+    def train_step(x, y):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = lossf(model(x), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    rx, ry = to_dev()
+    tm = Timing(torch, dist, dev, world, local_rank)
+    tm.sampler.start()
+    W = max(3, args.warmup)
+    for _ in range(W):
+        train_step(rx, ry)
+    ms, clocks, _l, stats = tm.timed(lambda: train_step(rx, ry), args.steps)
+    gb = B * world
+    value = gb * args.steps / (ms / 1e3)
+    e2e = None
+    if not args.no_e2e:
+        lh = torch.zeros(1).pin_memory()
+        seen = [0.0]
+
+        def step_e2e():
+            x, y = to_dev()
+            loss = train_step(x, y)
+            lh.copy_(loss.detach().float().reshape(1), non_blocking=False)      # device->host read of the step's loss
+            seen[0] = float(lh[0])
+        for _ in range(3):
+            step_e2e()
+        ms2, _c, _l2, stats2 = tm.timed(step_e2e, args.steps)
+        e2e = {"value": gb * args.steps / (ms2 / 1e3), "unit": "images/sec", "ms_per_step": ms2 / args.steps,
+               "h2d_bytes_per_step": int(host_img.numel() + host_lab.numel() * 8) * world, "d2h_bytes_per_step": 4 * world,
+               "step_ms": stats2}
+    tm.sampler.stop()
+    if rank == 0:
+        out = {"metric": "ResNet-50 training throughput", "value": value, "unit": "images/sec", "n_gpus": world,
+               "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": value / BASELINE_V100_FP32_IMG_S, "dtype": "bf16", "impl": "library",
+               "reference_class": "library-baseline",
+               "data": "synthetic (random uint8 NHWC images, random labels; random-init weights)",
+               "config": {"model": "resnet50_v1b (torchvision resnet50 v1.5)", "global_batch": gb, "per_gpu_batch": B,
+                          "image": [S, S, 3], "classes": args.classes, "parallelism": "dp%d" % world,
+                          "optimizer": "torch.optim.SGD nesterov mom=0.9 wd=1e-4 fused, fp32 master params + bf16 autocast",
+                          "comm": "DistributedDataParallel (NCCL bucketed all_reduce)" if world > 1 else "none",
+                          "l2_policy": "working set per step >> 126 MB L2"},
+               "clocks": clocks, "gpu_launches": 0, "step_ms": stats}
+        if e2e:
+            out["e2e"] = e2e
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# ======================================================================================= our arm
 def main():
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.impl == "library":
+        return library_arm(args)
 
     import torch
     import torch.distributed as dist
-    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
     import mxb200 as mx
     from mxb200 import ops as mxops
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world, rank, local_rank = _dist_env()
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     torch.cuda.set_device(local_rank)
@@ -124,7 +305,7 @@ def main():
 
     B, S = args.batch, args.image
     from mxb200.gluon.model_zoo import vision
-    from mxb200 import gluon, autograd
+    from mxb200 import gluon
     ctx = mx.gpu(local_rank)
     net = vision.get_resnet("v1b", args.layers, classes=args.classes, ctx=ctx, dtype="bfloat16", layout="NHWC")
     net.hybridize()
@@ -135,6 +316,8 @@ def main():
                             kvstore=kv)
     loss_fn = gluon.loss.SoftmaxCrossEntropyLoss()
     global_batch = B * world
+    # the whole step (forward, loss, backward, fused allreduce+update) as one replayed CUDA graph
+    step = gluon.TrainStep(net, loss_fn, trainer, batch_size=global_batch, capture=not args.no_graph, warmup=3)
 
     g = torch.Generator().manual_seed(1234 + rank)
     host_img = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).pin_memory()
@@ -142,57 +325,22 @@ def main():
     mean = torch.tensor([123.68, 116.28, 103.53], device=dev).view(1, 1, 1, 3)
     istd = 1.0 / torch.tensor([58.395, 57.12, 57.375], device=dev).view(1, 1, 1, 3)
 
-    def to_device_batch():
-        img = host_img.to(dev, non_blocking=True)
-        lab = host_lab.to(dev, non_blocking=True)
-        x = ((img.float() - mean) * istd).to(torch.bfloat16)
-        return mx.nd.from_torch(x, ctx), mx.nd.from_torch(lab, ctx)
+    img = host_img.to(dev, non_blocking=True)
+    lab = host_lab.to(dev, non_blocking=True)
+    res_x = mx.nd.from_torch(((img.float() - mean) * istd).to(torch.bfloat16), ctx)
+    res_y = mx.nd.from_torch(lab, ctx)
+    del img
 
-    def train_step(x, y):
-        with autograd.record():
-            out = net(x)
-            loss = loss_fn(out, y)
-        loss.backward()
-        trainer.step(global_batch)
-        return loss
-
-    res_x, res_y = to_device_batch()
-    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed(fn, steps, after=None):
-        barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        l0 = mxops.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        if after is not None:
-            after()                                # e.g. consume the last outstanding device->host read
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        clocks = sampler.stop()
-        launches = mxops.launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms, clocks, launches
+    tm = Timing(torch, dist, dev, world, local_rank)
+    tm.sampler.start()
 
     def step_resident():
-        train_step(res_x, res_y)
+        step(res_x, res_y)
 
     # ---- end-to-end arm: the public input pipeline (mx.io.DevicePrefetcher: pinned uint8 batch -> H2D on a copy stream
-    # -> normalise+cast kernel, one batch ahead of the compute) and a device->host read of every step's loss through a
-    # pinned ring (the read of step i is issued in step i and consumed while step i+1 is in flight, so the host never
-    # stalls the launch queue; every read completes inside the timed region)
+    # -> normalise+cast kernel, one batch ahead of the compute) feeding the same TrainStep, and a device->host read of every
+    # step's loss through a pinned ring (the read of step i is issued in step i and consumed while step i+1 is in flight,
+    # so the host never stalls the launch queue; every read completes inside the timed region)
     def source():
         while True:
             yield host_img, host_lab
@@ -211,16 +359,18 @@ def main():
 
     def step_e2e():
         x, y = next(prefetch)
-        loss = train_step(x, y)
+        loss = step(x, y)
         drain(1)                                   # at most one read outstanding: its ring slot is free again
         buf, ev = ring[(seen[1] + len(pending)) % 2]
         buf.copy_(loss.as_torch().detach().float().mean().reshape(1), non_blocking=True)
         ev.record()
         pending.append((buf, ev))
 
-    for _ in range(max(3, args.warmup)):
+    W = max(3, args.warmup)
+    # 3 eager steps (lazy arena fusion, library settling) + 1 capture step, then W replayed warm-up steps
+    for _ in range(4 + W):
         step_resident()
-    ms, clocks, launches = timed(step_resident, args.steps)
+    ms, clocks, launches, stats = tm.timed(step_resident, args.steps, count=mxops.launch_count)
     value = global_batch * args.steps / (ms / 1e3)
 
     e2e = None
@@ -229,18 +379,19 @@ def main():
             step_e2e()
         drain(0)
         n_before = seen[1]
-
-        ms2, _c2, _l2 = timed(step_e2e, args.steps, after=lambda: drain(0))
+        ms2, _c2, _l2, stats2 = tm.timed(step_e2e, args.steps, after=lambda: drain(0))
         assert seen[1] - n_before == args.steps, "every timed step must have delivered its loss to the host"
         e2e = {"value": global_batch * args.steps / (ms2 / 1e3), "unit": "images/sec",
-               "pipeline": "mx.io.DevicePrefetcher (pinned uint8 -> H2D on copy stream -> normalise kernel) + per-step async loss readback",
+               "pipeline": "mx.io.DevicePrefetcher (pinned uint8 -> H2D on copy stream -> normalise kernel) -> mx.gluon.TrainStep "
+                           "+ per-step async loss readback",
                "h2d_bytes_per_step": int(host_img.numel() * host_img.element_size() + host_lab.numel() * 8) * world,
-               "d2h_bytes_per_step": 4 * world, "ms_per_step": ms2 / args.steps}
+               "d2h_bytes_per_step": 4 * world, "ms_per_step": ms2 / args.steps, "step_ms": stats2}
+    tm.sampler.stop()
     trainer.check_health()
     if rank == 0:
         out = {
             "metric": "ResNet-50 training throughput", "value": value, "unit": "images/sec", "n_gpus": world,
-            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": value / BASELINE_V100_FP32_IMG_S,
             "dtype": "bf16", "data": "synthetic (random uint8 NHWC images, random labels; random-init weights)",
             "impl": "ours",
@@ -248,9 +399,10 @@ def main():
                        "image": [S, S, 3], "classes": args.classes, "parallelism": "dp%d" % world,
                        "optimizer": "NAG mom=0.9 wd=1e-4, fp32 master weights (multi_precision), fused allreduce+update",
                        "kvstore": "device (fused P2P allreduce+update kernel)",
+                       "dispatch": "eager" if args.no_graph else "cuda-graph replay (mx.gluon.TrainStep), %d replays" % step.replays,
                        "l2_policy": "working set per step (GBs of activations) >> 126 MB L2; inputs not re-used from L2",
                        "baseline_ref": "BASELINE.md ResNet-50 train fp32 1xV100 batch128 = 363.69 img/s"},
-            "clocks": clocks, "gpu_launches": launches, "final_loss": seen[0] if e2e else None,
+            "clocks": clocks, "gpu_launches": launches, "step_ms": stats, "final_loss": seen[0] if e2e else None,
         }
         if e2e:
             out["e2e"] = e2e

@@ -66,7 +66,13 @@ struct Args {
   int nesterov, has_mom;
   float beta1, beta2, eps, bc1, bc2;
   float lamb_lower, lamb_upper;
+  // CUDA-graph friendly hyper-parameters: when non-null the per-step scalars are read from this device buffer instead
+  // of the by-value fields above (a captured launch freezes its by-value arguments).  Layout (floats):
+  //   [0] lr  [1] wd  [2] momentum  [3] rescale  [4] clip  [5] seq (uint32 bits)  [6] bc1  [7] bc2
+  // ``seq`` then acts as an offset added to hyper[5] (several launches of one step share one buffer).
+  const float* hyper;
 };
+constexpr int kHyperFloats = 8;
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -138,8 +144,16 @@ template <typename GT, typename WT, int NR>
 __global__ void __launch_bounds__(kThreads)
 fused_kernel(const Args a) {
   const int nr = NR > 0 ? NR : a.nranks;
+  // per-step scalars: by value, or from the device-resident hyper buffer (graph replay)
+  float h_lr = a.lr, h_wd = a.wd, h_mom = a.momentum, h_rescale = a.rescale, h_clip = a.clip, h_bc1 = a.bc1, h_bc2 = a.bc2;
+  uint32_t h_seq = a.seq;
+  if (a.hyper != nullptr) {
+    h_lr = __ldg(a.hyper + 0); h_wd = __ldg(a.hyper + 1); h_mom = __ldg(a.hyper + 2); h_rescale = __ldg(a.hyper + 3);
+    h_clip = __ldg(a.hyper + 4); h_seq += __float_as_uint(__ldg(a.hyper + 5)); h_bc1 = __ldg(a.hyper + 6);
+    h_bc2 = __ldg(a.hyper + 7);
+  }
   if (nr > 1) {
-    if (!peer_barrier(a, 2u * a.seq)) return;
+    if (!peer_barrier(a, 2u * h_seq)) return;
   }
   // slice owned by this rank (two-shot) or the whole arena (one-shot)
   const int64_t n_chunks = a.n / kChunk;
@@ -162,7 +176,7 @@ fused_kernel(const Args a) {
     const int64_t e = v * 8;
     const int64_t chunk = active ? e / kChunk : 0;
     int t = 0;
-    float lr = a.lr, wd = a.wd;
+    float lr = h_lr, wd = h_wd;
     bool skip = !active;
     if (active && a.chunk_tid != nullptr) {
       t = __ldg(a.chunk_tid + chunk);
@@ -189,7 +203,7 @@ fused_kernel(const Args a) {
     if (a.mode == kAllreduce) {
       if (!skip) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= a.rescale;
+        for (int j = 0; j < 8; ++j) g[j] *= h_rescale;
         if (fan_out) {
 #pragma unroll
           for (int k = 0; k < (NR > 0 ? NR : kMaxRanks); ++k)
@@ -207,7 +221,7 @@ fused_kernel(const Args a) {
     }
     if (a.mode == kSgd) {
       if (skip) continue;
-      SgdHyper h{a.lr, a.wd, a.momentum, a.rescale, a.clip, a.nesterov, a.has_mom};
+      SgdHyper h{h_lr, h_wd, h_mom, h_rescale, h_clip, a.nesterov, a.has_mom};
       float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (a.has_mom) ld8<float>(a.mom + e, m);
 #pragma unroll
@@ -215,7 +229,7 @@ fused_kernel(const Args a) {
       if (a.has_mom) st8<float>(a.mom + e, m);
     } else if (a.mode == kAdam) {
       if (skip) continue;
-      AdamHyper h{a.lr, a.wd, a.beta1, a.beta2, a.eps, a.rescale, a.clip};
+      AdamHyper h{h_lr, h_wd, a.beta1, a.beta2, a.eps, h_rescale, h_clip};
       float m[8], vv[8];
       ld8<float>(a.mom + e, m);
       ld8<float>(a.var + e, vv);
@@ -227,7 +241,7 @@ fused_kernel(const Args a) {
       // block-uniform chunk: 512 threads x 8 = 4 chunks per block iteration -> reduce per 128-thread group
       float sw = 0.f, sr = 0.f;
       if (!skip) {
-        LambHyper h{a.beta1, a.beta2, a.eps, a.rescale, a.clip, a.bc1, a.bc2};
+        LambHyper h{a.beta1, a.beta2, a.eps, h_rescale, h_clip, h_bc1, h_bc2};
         float m[8], vv[8], r[8];
         ld8<float>(a.mom + e, m);
         ld8<float>(a.var + e, vv);
@@ -282,7 +296,7 @@ fused_kernel(const Args a) {
     }
   }
   if (nr > 1) {
-    if (!peer_barrier(a, 2u * a.seq + 1u)) return;
+    if (!peer_barrier(a, 2u * h_seq + 1u)) return;
   }
   // Everyone has consumed this rank's gradients: clear them so the next backward can accumulate
   // without a separate memset (grad_req='add'-style arena).  Done after the barrier on the FULL local arena.

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include <mutex>
+#include <string.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -56,6 +57,31 @@ static FastDiv make_fastdiv(uint32_t d) {
   return f;
 }
 
+// Implicit-GEMM convolution geometry (CONV != 0): one operand is gathered by im2col-mode TMA straight from the NHWC
+// activation tensor, so no patch matrix ever exists in memory (the reference materialises it: src/operator/nn/im2col.cuh
+// + convolution-inl.h:150-230; cuDNN's implicit GEMM is the library equivalent).
+//   CONV == 1 : A = im2col(act)  [pixels x (tap, channel)]  K-major      fwd:   Y  = im2col(X)  . W^T
+//                                                                         dgrad: dX = im2col(dY) . W   (flipped taps)
+//   CONV == 2 : B = im2col(act)  [(pixels) x (tap, channel)] MN-major    wgrad: dW = dY^T . im2col(X), reduction = pixels
+// A "tap" is one filter position; per tap the table gives the pixel offset inside the bounding box and the weight tap it
+// pairs with (dgrad flips them; the parity sub-problems of a strided dgrad use a subset).
+constexpr int kMaxTaps = 49;
+struct ConvGeom {
+  int C;              // channels of the gathered tensor (multiple of 64)
+  int cpt;            // C / 64: k-blocks per tap
+  int ntaps;
+  int P, Q;           // base-pixel grid per image (rows, cols): GEMM pixel index = (n * P + p) * Q + q
+  int stride;         // traversal stride of the base pixels (the map's elementStrides)
+  int base_h, base_w; // lower corner of the bounding box (= -pad for fwd / wgrad)
+  int red_per_tap;    // B reduction-coordinate step per weight tap   (fwd:   Cin, weights [Cout][taps*Cin] K-major)
+  int out_per_tap;    // B output-column offset per weight tap        (dgrad: Cin, weights read MN-major)
+  FastDiv d_cpt, d_Q, d_PQ, d_C;
+  int8_t off_w[kMaxTaps], off_h[kMaxTaps], wtap[kMaxTaps];
+  // strided (parity) dgrad: rows are scattered to dst[((n * dH + p * dstep + ph) * dW + q * dstep + pw) * dC + col]
+  __nv_bfloat16* direct;
+  int dH, dW, dC, dstep, ph, pw;
+};
+
 struct Params {
   int M, N, K;          // logical problem: D[M,N] = A[M,K] * B[N,K]^T   (K = reduction)
   int num_splits;       // split-K factor (>1 only with REDUCE epilogue)
@@ -72,6 +98,7 @@ struct Params {
   int64_t ldc;
   // debug overrides for descriptor fields (0 = use computed); lets one GPU run probe encodings
   int dbg_lbo_a, dbg_sbo_a, dbg_lbo_b, dbg_sbo_b;
+  ConvGeom conv;
 };
 
 template <int BN, typename OutT, int CTAS = 1>
@@ -112,7 +139,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) {
 // rows of B, the leader (cluster rank 0) issues tcgen05.mma.cta_group::2 (M = 256), the accumulator rows 0-127 live in
 // the leader's TMEM and rows 128-255 in the peer's, and each CTA drains / stores its own half.  Per SM this halves the
 // B-operand shared-memory traffic per flop (32 KB instead of 48 KB per 128x256x64 of work).
-template <int BN, bool A_MN, bool B_MN, typename OutT, bool REDUCE, int CTAS>
+template <int BN, bool A_MN, bool B_MN, typename OutT, bool REDUCE, int CTAS, int CONV>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const Params p) {
@@ -209,30 +236,76 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if constexpr (CTAS == 2) ptx::tma_load_2d_2sm(dst, tm, bar, c0, c1);   // bytes credited to the leader's barrier
         else ptx::tma_load_2d(dst, tm, bar, c0, c1);
       };
+      auto load_im2col = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, int c, int wq, int hp, int n, int tap) {
+        const uint16_t ow = (uint16_t)p.conv.off_w[tap], oh = (uint16_t)p.conv.off_h[tap];
+        if constexpr (CTAS == 2) ptx::tma_load_im2col_4d_2sm(dst, tm, bar, c, wq, hp, n, ow, oh);
+        else ptx::tma_load_im2col_4d(dst, tm, bar, c, wq, hp, n, ow, oh);
+      };
       for (int w = cluster_id; w < num_work; w += num_clusters) {
         int m_blk, n_blk, kb0, kb1;
         decode(w, m_blk, n_blk, kb0, kb1);
         const int m0 = m_blk * kTileM + (int)cta_rank * BLOCK_M;     // first A / output row of this CTA
         const int n0 = n_blk * BN + (int)cta_rank * kBRows;          // first B row staged by this CTA
+        // CONV == 1: base pixel of the first row of this CTA's A tile
+        int a_n = 0, a_h = 0, a_w = 0;
+        if constexpr (CONV == 1) {
+          const uint32_t img = p.conv.d_PQ.div((uint32_t)m0);
+          const uint32_t rem = (uint32_t)m0 - img * p.conv.d_PQ.d;
+          const uint32_t pr = p.conv.d_Q.div(rem);
+          a_n = (int)img;
+          a_h = p.conv.base_h + (int)pr * p.conv.stride;
+          a_w = p.conv.base_w + (int)(rem - pr * p.conv.d_Q.d) * p.conv.stride;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], CTAS * S::kStageBytes);
           uint8_t* a_dst = smem_a + stage * S::kABytes;
           uint8_t* b_dst = smem_b + stage * S::kBBytes;
-          if constexpr (A_MN) {
-            // A stored [K, M]: boxes of [64 k][64 m]; chunk c covers m in [64c, 64c+64)
+          if constexpr (CONV == 1) {
+            // k-block kb = (tap, 64-channel chunk)
+            const uint32_t tap = p.conv.d_cpt.div((uint32_t)kb);
+            const int cc = (kb - (int)tap * p.conv.cpt) * BLOCK_K;
+            const int wt = (int)p.conv.wtap[tap];
+            load_im2col(a_dst, &tmA, &full_bar[stage], cc, a_w, a_h, a_n, (int)tap);
+            if constexpr (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BLOCK_M / 64; ++c)
-              load(a_dst + c * (BLOCK_K * 128), &tmA, &full_bar[stage], m0 + c * 64, kb * BLOCK_K);
+              for (int c = 0; c < kBRows / 64; ++c)
+                load(b_dst + c * (BLOCK_K * 128), &tmB, &full_bar[stage], wt * p.conv.out_per_tap + n0 + c * 64, cc);
+            } else {
+              load(b_dst, &tmB, &full_bar[stage], wt * p.conv.red_per_tap + cc, n0);
+            }
           } else {
-            load(a_dst, &tmA, &full_bar[stage], kb * BLOCK_K, m0);
-          }
-          if constexpr (B_MN) {
+            if constexpr (A_MN) {
+              // A stored [K, M]: boxes of [64 k][64 m]; chunk c covers m in [64c, 64c+64)
 #pragma unroll
-            for (int c = 0; c < kBRows / 64; ++c)
-              load(b_dst + c * (BLOCK_K * 128), &tmB, &full_bar[stage], n0 + c * 64, kb * BLOCK_K);
-          } else {
-            load(b_dst, &tmB, &full_bar[stage], kb * BLOCK_K, n0);
+              for (int c = 0; c < BLOCK_M / 64; ++c)
+                load(a_dst + c * (BLOCK_K * 128), &tmA, &full_bar[stage], m0 + c * 64, kb * BLOCK_K);
+            } else {
+              load(a_dst, &tmA, &full_bar[stage], kb * BLOCK_K, m0);
+            }
+            if constexpr (CONV == 2) {
+              // B chunk c = 64 (tap, channel) columns gathered for the 64 pixels of this k-block
+              const uint32_t pix = (uint32_t)kb * BLOCK_K;
+              const uint32_t img = p.conv.d_PQ.div(pix);
+              const uint32_t rem = pix - img * p.conv.d_PQ.d;
+              const uint32_t pr = p.conv.d_Q.div(rem);
+              const int b_h = p.conv.base_h + (int)pr * p.conv.stride;
+              const int b_w = p.conv.base_w + (int)(rem - pr * p.conv.d_Q.d) * p.conv.stride;
+#pragma unroll
+              for (int c = 0; c < kBRows / 64; ++c) {
+                int col = n0 + c * 64;
+                if (col >= p.N) col = 0;               // tail tile: any valid data, the store clips these columns
+                const uint32_t tap = p.conv.d_C.div((uint32_t)col);
+                load_im2col(b_dst + c * (BLOCK_K * 128), &tmB, &full_bar[stage], col - (int)tap * p.conv.C, b_w, b_h, (int)img,
+                            (int)tap);
+              }
+            } else if constexpr (B_MN) {
+#pragma unroll
+              for (int c = 0; c < kBRows / 64; ++c)
+                load(b_dst + c * (BLOCK_K * 128), &tmB, &full_bar[stage], n0 + c * 64, kb * BLOCK_K);
+            } else {
+              load(b_dst, &tmB, &full_bar[stage], kb * BLOCK_K, n0);
+            }
           }
           if (++stage == kStages) {
             stage = 0;
@@ -389,6 +462,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < kSlabCols; ++j) v[j] = fmaxf(v[j], 0.f);
         }
+        bool direct = false;
+        if constexpr (CONV == 1 && sizeof(OutT) == 2) direct = p.conv.direct != nullptr;
+        if (direct) {
+          if constexpr (CONV == 1 && sizeof(OutT) == 2) {
+            // strided-dgrad parity plane: this thread's pixel goes to a strided position of the full gradient tensor
+            // (8 x 16B = one full 128-byte line per thread and slab)
+            if (grow < p.M) {
+              const uint32_t img = p.conv.d_PQ.div((uint32_t)grow);
+              const uint32_t rem = (uint32_t)grow - img * p.conv.d_PQ.d;
+              const uint32_t pr = p.conv.d_Q.div(rem);
+              const uint32_t qc = rem - pr * p.conv.d_Q.d;
+              __nv_bfloat16* dst = p.conv.direct +
+                  (((int64_t)img * p.conv.dH + (int64_t)pr * p.conv.dstep + p.conv.ph) * p.conv.dW + (int64_t)qc * p.conv.dstep +
+                   p.conv.pw) * p.conv.dC + col0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (col0 + i * 8 < p.N)
+                  *reinterpret_cast<uint4*>(dst + i * 8) =
+                      make_uint4(pack_bf16(v[i * 8 + 0], v[i * 8 + 1]), pack_bf16(v[i * 8 + 2], v[i * 8 + 3]),
+                                 pack_bf16(v[i * 8 + 4], v[i * 8 + 5]), pack_bf16(v[i * 8 + 6], v[i * 8 + 7]));
+              }
+            }
+          }
+          continue;
+        }
         const uint32_t rbase = sd + (uint32_t)row * 128u;
         if constexpr (sizeof(OutT) == 2) {
 #pragma unroll
@@ -499,6 +597,42 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// The tensor-map encoders are DRIVER entry points and need a current context on the calling thread; autograd's backward
+// threads may not have one yet (CUDA_ERROR_INVALID_CONTEXT otherwise).  Bind the device's primary context through the
+// driver API: unlike the usual cudaFree(0) idiom this does not synchronise the legacy stream, which would invalidate a
+// CUDA-graph capture in progress on another stream (parallel/graph.py).
+static void bind_context() {
+  static thread_local bool bound = false;
+  if (bound) return;
+  typedef CUresult (*GetCur)(CUcontext*);
+  typedef CUresult (*SetCur)(CUcontext);
+  typedef CUresult (*Retain)(CUcontext*, CUdevice);
+  static GetCur get_cur = nullptr;
+  static SetCur set_cur = nullptr;
+  static Retain retain = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &f, cudaEnableDefault, &q) == cudaSuccess) get_cur = reinterpret_cast<GetCur>(f);
+    if (cudaGetDriverEntryPoint("cuCtxSetCurrent", &f, cudaEnableDefault, &q) == cudaSuccess) set_cur = reinterpret_cast<SetCur>(f);
+    if (cudaGetDriverEntryPoint("cuDevicePrimaryCtxRetain", &f, cudaEnableDefault, &q) == cudaSuccess) retain = reinterpret_cast<Retain>(f);
+  });
+  CUcontext cur = nullptr;
+  if (get_cur && get_cur(&cur) == CUDA_SUCCESS && cur != nullptr) {
+    bound = true;
+    return;
+  }
+  int dev = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  if (retain && set_cur && retain(&cur, (CUdevice)dev) == CUDA_SUCCESS && set_cur(cur) == CUDA_SUCCESS) {
+    bound = true;
+    return;
+  }
+  CUDA_CHECK(cudaFree(0));   // last resort
+  bound = true;
+}
+
 // 2D row-major tensor [rows, cols] with row stride ld (elements); box = [box_rows, box_cols]; 128B swizzle.
 static CUtensorMap make_map(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t rows, int64_t cols,
                             int64_t ld, int box_rows, int box_cols) {
@@ -509,11 +643,7 @@ static CUtensorMap make_map(const void* ptr, CUtensorMapDataType dt, int elem_by
   cuuint32_t estr[2] = {1, 1};
   // The driver entry point needs a current context; autograd's backward threads may not have touched the
   // runtime yet (CUDA_ERROR_INVALID_CONTEXT otherwise).  cudaFree(0) binds the primary context once per thread.
-  static thread_local bool ctx_bound = false;
-  if (!ctx_bound) {
-    CUDA_CHECK(cudaFree(0));
-    ctx_bound = true;
-  }
+  bind_context();
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) throw std::runtime_error("TMA: base pointer not 16B aligned");
   if ((strides[0] & 15) != 0) throw std::runtime_error("TMA: row stride must be a multiple of 16 bytes");
   CUresult r = get_encode()(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -523,20 +653,83 @@ static CUtensorMap make_map(const void* ptr, CUtensorMapDataType dt, int elem_by
   return m;
 }
 
-template <int BN, bool A_MN, bool B_MN, typename OutT, bool REDUCE, int CTAS = 1>
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeIm2colFn>(f);
+  });
+  if (!fn) throw std::runtime_error("cuTensorMapEncodeIm2col not available from the driver");
+  return fn;
+}
+
+// Host description of the gathered activation tensor of an implicit-GEMM convolution.
+struct ConvDesc {
+  const void* act;              // NHWC bf16
+  int n, h, w, c;
+  int lower_h, lower_w;         // bounding box of the base pixels: [lower, dim + upper)
+  int upper_h, upper_w;
+  int64_t b_rows, b_cols;       // dgrad: the weight matrix as stored ([Cout][taps * Cin]) -- differs from the GEMM's K x N
+  ConvGeom geom;                // device geometry (fast divisors are filled in by launch)
+};
+
+// im2col-mode tensor map over an NHWC bf16 tensor: ``pixels`` base pixels x 64 channels per load, 128B swizzle.
+static CUtensorMap make_im2col_map(const ConvDesc& cd, int pixels) {
+  CUtensorMap m;
+  bind_context();
+  cuuint64_t dims[4] = {(cuuint64_t)cd.c, (cuuint64_t)cd.w, (cuuint64_t)cd.h, (cuuint64_t)cd.n};
+  cuuint64_t strides[3] = {(cuuint64_t)cd.c * 2, (cuuint64_t)cd.w * cd.c * 2, (cuuint64_t)cd.h * cd.w * cd.c * 2};
+  int lower[2] = {cd.lower_w, cd.lower_h};
+  int upper[2] = {cd.upper_w, cd.upper_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)cd.geom.stride, (cuuint32_t)cd.geom.stride, 1};
+  if ((reinterpret_cast<uintptr_t>(cd.act) & 15) != 0) throw std::runtime_error("im2col TMA: base pointer not 16B aligned");
+  if (cd.c % 64 != 0) throw std::runtime_error("im2col TMA: channels must be a multiple of 64");
+  CUresult r = get_encode_im2col()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(cd.act), dims, strides, lower,
+                                   upper, 64, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeIm2col failed with code " + std::to_string((int)r));
+  // drivers <= 13.1 set a descriptor bit that is wrong for tensors smaller than 128 KB (same work-around as CUTLASS,
+  // cute/atom/copy_traits_sm90_im2col.hpp)
+  static const int drv = [] { int v = 0; cudaDriverGetVersion(&v); return v; }();
+  if (drv <= 13010 && (int64_t)cd.n * cd.h * cd.w * cd.c * 2 < 131072) reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
+  return m;
+}
+
+template <int BN, bool A_MN, bool B_MN, typename OutT, bool REDUCE, int CTAS = 1, int CONV = 0>
 static void launch(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldd,
                    const float* bias, int relu, float* col_sum, float* col_sumsq, const void* addend, int64_t ldc,
-                   int splits, int max_ctas, const int* dbg, cudaStream_t stream) {
+                   int splits, int max_ctas, const int* dbg, cudaStream_t stream, const ConvDesc* cd = nullptr) {
   using S = Smem<BN, OutT, CTAS>;
   constexpr int kBRows = BN / CTAS;
-  CUtensorMap tmA = A_MN ? make_map(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, M, lda, BLOCK_K, 64)
+  static_assert(CONV == 0 || (CONV == 1 && !A_MN) || (CONV == 2 && A_MN && B_MN), "conv operand layouts");
+  if (CONV != 0 && cd == nullptr) throw std::runtime_error("conv launch without geometry");
+  CUtensorMap tmA = CONV == 1 ? make_im2col_map(*cd, BLOCK_M) : A_MN ? make_map(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, M, lda, BLOCK_K, 64)
                          : make_map(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, BLOCK_M, BLOCK_K);
-  CUtensorMap tmB = B_MN ? make_map(B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, N, ldb, BLOCK_K, 64)
+  const int64_t b_red = (CONV == 1 && cd->b_rows) ? cd->b_rows : K, b_out = (CONV == 1 && cd->b_cols) ? cd->b_cols : N;
+  CUtensorMap tmB = CONV == 2 ? make_im2col_map(*cd, BLOCK_K) : B_MN ? make_map(B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b_red, b_out, ldb, BLOCK_K, 64)
                          : make_map(B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldb, kBRows, BLOCK_K);
   CUtensorMap tmD = sizeof(OutT) == 2 ? make_map(D, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, ldd, BLOCK_M, 64)
                                       : make_map(D, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, ldd, BLOCK_M, 32);
   Params p;
+  memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
+  if constexpr (CONV != 0) {
+    p.conv = cd->geom;
+    p.conv.cpt = p.conv.C / BLOCK_K;
+    p.conv.d_cpt = make_fastdiv((uint32_t)p.conv.cpt);
+    p.conv.d_Q = make_fastdiv((uint32_t)p.conv.Q);
+    p.conv.d_PQ = make_fastdiv((uint32_t)(p.conv.P * p.conv.Q));
+    p.conv.d_C = make_fastdiv((uint32_t)p.conv.C);
+  }
   const int nkb = (K + BLOCK_K - 1) / BLOCK_K;
   if (splits < 1) splits = 1;
   if (splits > nkb) splits = nkb;
@@ -563,7 +756,7 @@ static void launch(const void* A, const void* B, void* D, int M, int N, int K, i
   int clusters = (max_ctas > 0 ? max_ctas : kNumSMs) / CTAS;
   if (clusters > num_work) clusters = num_work;
   if (clusters < 1) clusters = 1;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, OutT, REDUCE, CTAS>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, OutT, REDUCE, CTAS, CONV>;
   CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   if constexpr (CTAS == 1) {
     kern<<<clusters, kThreads, S::kTotal, stream>>>(tmA, tmB, tmD, p);
@@ -640,5 +833,222 @@ MXB_API int MXBGemmBf16(int mode, const void* A, const void* B, void* D, int M, 
   } else {
     throw std::runtime_error("MXBGemmBf16: bad mode");
   }
+  MXB_CATCH
+}
+
+
+// ------------------------------------------------------------------ implicit-GEMM convolution (NHWC bf16, weights KRSC)
+// Reference operators: Convolution forward / backward (src/operator/nn/convolution.cu:40-128 -> cudnn_convolution-inl.h or
+// convolution-inl.h im2col + GEMM).  Here the im2col gather is done by the TMA unit (im2col-mode tensor maps) inside the
+// tcgen05 GEMM's producer warp: no patch matrix, padding = out-of-bounds zero fill, stride = traversal stride.
+namespace {
+
+int conv_out(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
+
+int pick_bn(int64_t M, int N, int sp) {
+  int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int64_t nm = (M + 127) / 128;
+  while (bn > 64 && nm * ((N + bn - 1) / bn) * sp < 100) bn >>= 1;
+  return bn;
+}
+
+bool pick_two_cta(int bn, int64_t M, int N, int K, int sp) {
+  static const int env = [] { const char* e = getenv("MXB200_GEMM_2CTA"); return e ? atoi(e) : -1; }();
+  if (bn != 256) return false;
+  const int64_t tiles2 = ((M + 255) / 256) * (((int64_t)N + 255) / 256) * sp;
+  return env == 1 || (env != 0 && K >= 256 && tiles2 >= 74);
+}
+
+void check_conv_args(int c, int o, int kh, int kw, int stride) {
+  MXB_CHECK(c % 64 == 0, "conv: gathered channel count must be a multiple of 64");
+  MXB_CHECK(o % 8 == 0, "conv: channel counts must be multiples of 8");
+  MXB_CHECK(kh * kw <= gemm::kMaxTaps && kh >= 1 && kw >= 1, "conv: filter too large");
+  MXB_CHECK(stride >= 1 && stride <= 8, "conv: bad stride");
+}
+
+}  // namespace
+
+#define MXB_CONV_DISPATCH(CONVK, AMN, BMN, OUT, RED, SPL, MM, NN, KK, LDA, LDB, LDD)                                  \
+  do {                                                                                                                \
+    if (two_cta) gemm::launch<256, AMN, BMN, OUT, RED, 2, CONVK>(A, B, D, MM, NN, KK, LDA, LDB, LDD, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, 0, nullptr, s, &cd); \
+    else if (bn == 64) gemm::launch<64, AMN, BMN, OUT, RED, 1, CONVK>(A, B, D, MM, NN, KK, LDA, LDB, LDD, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, 0, nullptr, s, &cd); \
+    else if (bn == 128) gemm::launch<128, AMN, BMN, OUT, RED, 1, CONVK>(A, B, D, MM, NN, KK, LDA, LDB, LDD, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, 0, nullptr, s, &cd); \
+    else gemm::launch<256, AMN, BMN, OUT, RED, 1, CONVK>(A, B, D, MM, NN, KK, LDA, LDB, LDD, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, 0, nullptr, s, &cd); \
+  } while (0)
+
+// y[n,P,Q,o] = conv(x[n,h,w,c], w[o,kh,kw,c]) (+bias)(+addend)(relu); col_sum / col_sumsq: fused BatchNorm statistics of y.
+MXB_API int MXBConvFwdBf16(const void* x, const void* w, void* y, int n, int h, int wd, int c, int o, int kh, int kw, int stride,
+                           int pad, const float* bias, int relu, float* col_sum, float* col_sumsq, const void* addend_in,
+                           int block_n, void* stream) {
+  MXB_TRY
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  check_conv_args(c, o, kh, kw, stride);
+  const int P = conv_out(h, kh, stride, pad), Q = conv_out(wd, kw, stride, pad);
+  MXB_CHECK(P > 0 && Q > 0 && n > 0, "conv: empty output");
+  const int64_t M64 = (int64_t)n * P * Q;
+  MXB_CHECK(M64 < (1ll << 31), "conv: too many output pixels");
+  const int M = (int)M64, N = o, K = kh * kw * c;
+  gemm::ConvDesc cd;
+  memset(&cd, 0, sizeof(cd));
+  cd.act = x; cd.n = n; cd.h = h; cd.w = wd; cd.c = c;
+  cd.lower_h = -pad; cd.lower_w = -pad;
+  cd.upper_h = pad - (kh - 1); cd.upper_w = pad - (kw - 1);
+  // the bounding box must hold exactly P x Q base pixels
+  cd.upper_h -= (h + cd.upper_h - cd.lower_h - 1) - (P - 1) * stride;
+  cd.upper_w -= (wd + cd.upper_w - cd.lower_w - 1) - (Q - 1) * stride;
+  gemm::ConvGeom& g = cd.geom;
+  g.C = c; g.ntaps = kh * kw; g.P = P; g.Q = Q; g.stride = stride; g.base_h = -pad; g.base_w = -pad;
+  g.red_per_tap = c; g.out_per_tap = 0;
+  for (int r = 0; r < kh; ++r)
+    for (int q = 0; q < kw; ++q) {
+      const int t = r * kw + q;
+      g.off_h[t] = (int8_t)r; g.off_w[t] = (int8_t)q; g.wtap[t] = (int8_t)t;
+    }
+  const void *A = x, *B = w;
+  void* D = y;
+  const void* addend = addend_in;          // optional residual [n,P,Q,o] added in the epilogue (inference)
+  const int64_t ldc = o;
+  int bn = (block_n == 64 || block_n == 128 || block_n == 256) ? block_n : pick_bn(M, N, 1);
+  const bool two_cta = pick_two_cta(bn, M, N, K, 1);
+  MXB_CONV_DISPATCH(1, false, false, __nv_bfloat16, false, 1, M, N, K, (int64_t)c, (int64_t)K, (int64_t)o);
+  MXB_CATCH
+}
+
+// dx[n,h,w,c] = sum_{r,s,k} dy[n,(h+pad-r)/stride,(w+pad-s)/stride,k] * w[k,r,s,c]  (+ addend[n,h,w,c], stride 1 only)
+MXB_API int MXBConvDgradBf16(const void* dy, const void* w, void* dx, int n, int h, int wd, int c, int o, int kh, int kw,
+                             int stride, int pad, const void* addend_in, void* stream) {
+  MXB_TRY
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  check_conv_args(o, c, kh, kw, stride);      // the gathered tensor is dy: o channels
+  const int P = conv_out(h, kh, stride, pad), Q = conv_out(wd, kw, stride, pad);
+  MXB_CHECK(P > 0 && Q > 0 && n > 0, "conv: empty output");
+  MXB_CHECK((int64_t)n * h * wd < (1ll << 31), "conv: too many pixels");
+  const float* bias = nullptr;
+  const int relu = 0;
+  float *col_sum = nullptr, *col_sumsq = nullptr;
+  const void *A = dy, *B = w;
+  const int64_t ldb = (int64_t)kh * kw * c;
+  if (stride == 1) {
+    const int M = n * h * wd, N = c, K = kh * kw * o;
+    gemm::ConvDesc cd;
+    memset(&cd, 0, sizeof(cd));
+    cd.act = dy; cd.n = n; cd.h = P; cd.w = Q; cd.c = o;
+    cd.lower_h = pad - (kh - 1); cd.lower_w = pad - (kw - 1);
+    cd.upper_h = h - P + cd.lower_h; cd.upper_w = wd - Q + cd.lower_w;
+    cd.b_rows = o; cd.b_cols = ldb;
+    gemm::ConvGeom& g = cd.geom;
+    g.C = o; g.ntaps = kh * kw; g.P = h; g.Q = wd; g.stride = 1; g.base_h = cd.lower_h; g.base_w = cd.lower_w;
+    g.red_per_tap = 0; g.out_per_tap = c;
+    for (int r = 0; r < kh; ++r)
+      for (int q = 0; q < kw; ++q) {
+        const int t = r * kw + q;
+        g.off_h[t] = (int8_t)(kh - 1 - r); g.off_w[t] = (int8_t)(kw - 1 - q); g.wtap[t] = (int8_t)t;
+      }
+    void* D = dx;
+    const void* addend = addend_in;
+    const int64_t ldc = c;
+    const int bn = pick_bn(M, N, 1);
+    const bool two_cta = pick_two_cta(bn, M, N, K, 1);
+    MXB_CONV_DISPATCH(1, false, true, __nv_bfloat16, false, 1, M, N, K, (int64_t)o, ldb, (int64_t)c);
+  } else {
+    MXB_CHECK(addend_in == nullptr, "conv dgrad: the addend epilogue needs stride 1");
+    // one sub-convolution per output parity plane: only the taps whose input position is integral contribute
+    bool need_zero = false;
+    for (int ph = 0; ph < stride && !need_zero; ++ph) {
+      int cnt = 0;
+      for (int r = 0; r < kh; ++r) cnt += ((ph + pad - r) % stride == 0);
+      need_zero = cnt == 0;
+    }
+    for (int pw = 0; pw < stride && !need_zero; ++pw) {
+      int cnt = 0;
+      for (int q = 0; q < kw; ++q) cnt += ((pw + pad - q) % stride == 0);
+      need_zero = cnt == 0;
+    }
+    if (need_zero) CUDA_CHECK(cudaMemsetAsync(dx, 0, (size_t)n * h * wd * c * 2, s));
+    for (int ph = 0; ph < stride; ++ph)
+      for (int pw = 0; pw < stride; ++pw) {
+        const int H2 = (h - ph + stride - 1) / stride, W2 = (wd - pw + stride - 1) / stride;
+        if (H2 <= 0 || W2 <= 0) continue;
+        int dh[gemm::kMaxTaps], dw[gemm::kMaxTaps], wt[gemm::kMaxTaps], nt = 0, min_h = 1 << 20, min_w = 1 << 20;
+        for (int r = 0; r < kh; ++r) {
+          if ((ph + pad - r) % stride != 0) continue;
+          for (int q = 0; q < kw; ++q) {
+            if ((pw + pad - q) % stride != 0) continue;
+            dh[nt] = (ph + pad - r) / stride; dw[nt] = (pw + pad - q) / stride; wt[nt] = r * kw + q;
+            min_h = dh[nt] < min_h ? dh[nt] : min_h; min_w = dw[nt] < min_w ? dw[nt] : min_w;
+            ++nt;
+          }
+        }
+        if (nt == 0) continue;
+        const int M = n * H2 * W2, N = c, K = nt * o;
+        gemm::ConvDesc cd;
+        memset(&cd, 0, sizeof(cd));
+        cd.act = dy; cd.n = n; cd.h = P; cd.w = Q; cd.c = o;
+        cd.lower_h = min_h; cd.lower_w = min_w;
+        cd.upper_h = H2 - P + min_h; cd.upper_w = W2 - Q + min_w;
+        cd.b_rows = o; cd.b_cols = ldb;
+        gemm::ConvGeom& g = cd.geom;
+        g.C = o; g.ntaps = nt; g.P = H2; g.Q = W2; g.stride = 1; g.base_h = min_h; g.base_w = min_w;
+        g.red_per_tap = 0; g.out_per_tap = c;
+        for (int t = 0; t < nt; ++t) {
+          g.off_h[t] = (int8_t)(dh[t] - min_h); g.off_w[t] = (int8_t)(dw[t] - min_w); g.wtap[t] = (int8_t)wt[t];
+        }
+        g.direct = reinterpret_cast<__nv_bfloat16*>(dx);
+        g.dH = h; g.dW = wd; g.dC = c; g.dstep = stride; g.ph = ph; g.pw = pw;
+        void* D = dx;                      // only used to build a (never used) store map
+        const void* addend = nullptr;
+        const int64_t ldc = 0;
+        const int bn = pick_bn(M, N, 1);
+        const bool two_cta = pick_two_cta(bn, M, N, K, 1);
+        MXB_CONV_DISPATCH(1, false, true, __nv_bfloat16, false, 1, M, N, K, (int64_t)o, ldb, (int64_t)c);
+      }
+  }
+  MXB_CATCH
+}
+
+// dw[o, kh*kw*c] (fp32, ACCUMULATED: caller zero-fills or passes a gradient-arena view) += dy^T . im2col(x)
+MXB_API int MXBConvWgradBf16(const void* dy, const void* x, void* dw, int n, int h, int wd, int c, int o, int kh, int kw,
+                             int stride, int pad, int splits, int block_n, void* stream) {
+  MXB_TRY
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  check_conv_args(c, o, kh, kw, stride);
+  const int P = conv_out(h, kh, stride, pad), Q = conv_out(wd, kw, stride, pad);
+  MXB_CHECK(P > 0 && Q > 0 && n > 0, "conv: empty output");
+  const int64_t K64 = (int64_t)n * P * Q;
+  MXB_CHECK(K64 < (1ll << 31), "conv: too many output pixels");
+  const int M = o, N = kh * kw * c, K = (int)K64;
+  gemm::ConvDesc cd;
+  memset(&cd, 0, sizeof(cd));
+  cd.act = x; cd.n = n; cd.h = h; cd.w = wd; cd.c = c;
+  cd.lower_h = -pad; cd.lower_w = -pad;
+  cd.upper_h = pad - (kh - 1); cd.upper_w = pad - (kw - 1);
+  cd.upper_h -= (h + cd.upper_h - cd.lower_h - 1) - (P - 1) * stride;
+  cd.upper_w -= (wd + cd.upper_w - cd.lower_w - 1) - (Q - 1) * stride;
+  gemm::ConvGeom& g = cd.geom;
+  g.C = c; g.ntaps = kh * kw; g.P = P; g.Q = Q; g.stride = stride; g.base_h = -pad; g.base_w = -pad;
+  for (int r = 0; r < kh; ++r)
+    for (int q = 0; q < kw; ++q) {
+      const int t = r * kw + q;
+      g.off_h[t] = (int8_t)r; g.off_w[t] = (int8_t)q; g.wtap[t] = (int8_t)t;
+    }
+  const void *A = dy, *B = x;
+  void* D = dw;
+  const float* bias = nullptr;
+  const int relu = 0;
+  float *col_sum = nullptr, *col_sumsq = nullptr;
+  const void* addend = nullptr;
+  const int64_t ldc = 0;
+  int bn = (block_n == 64 || block_n == 128 || block_n == 256) ? block_n : (N <= 64 ? 64 : (N < 256 ? 128 : 256));
+  if (splits < 1) {
+    const int64_t tiles = (((int64_t)M + 127) / 128) * ((N + bn - 1) / bn);
+    const int64_t kb = (K64 + 63) / 64;
+    int64_t want = (2 * 148) / (tiles > 0 ? tiles : 1);
+    if (want < 1) want = 1;
+    const int64_t cap = kb >= 8 ? kb / 4 : 1;
+    splits = (int)(want < cap ? want : cap);
+    if (splits < 1) splits = 1;
+  }
+  bool two_cta = pick_two_cta(bn, M, N, K, splits) && M >= 256;
+  MXB_CONV_DISPATCH(2, true, true, float, true, splits, M, N, K, (int64_t)o, (int64_t)c, (int64_t)N);
   MXB_CATCH
 }

@@ -4,3 +4,4 @@ from .block import Block, HybridBlock, SymbolBlock  # noqa: F401
 from . import nn, loss, utils  # noqa: F401
 from .trainer import Trainer  # noqa: F401
 from . import data, model_zoo, rnn, contrib  # noqa: F401
+from ..parallel.graph import TrainStep  # noqa: F401,E402   (whole-step CUDA-graph capture)

@@ -286,7 +286,9 @@ class Trainer(object):
     def _fused_step(self, rescale_grad):
         o = self._optimizer
         o.rescale_grad = rescale_grad
-        o.num_update += 1
+        phase = getattr(self, "_graph_phase", None)      # None | "host" | "device" (parallel/graph.py)
+        if phase != "device":
+            o.num_update += 1
         lr = o.lr_scheduler(o.num_update) if o.lr_scheduler is not None else o.lr
         kind = {opt.SGD: "sgd", opt.NAG: "nag", opt.Adam: "adam", opt.LAMB: "lamb"}[type(o)]
         kw = {}
@@ -297,7 +299,7 @@ class Trainer(object):
                       lamb_bounds=(-1.0 if o.lower_bound is None else o.lower_bound,
                                    -1.0 if o.upper_bound is None else o.upper_bound))
         self._fused.step(kind, lr=lr, wd=o.wd, momentum=getattr(o, "momentum", 0.0), rescale=rescale_grad,
-                         clip=o.clip_gradient, multi_precision=o.multi_precision, **kw)
+                         clip=o.clip_gradient, multi_precision=o.multi_precision, phase=phase, **kw)
 
     def allreduce_grads(self):
         if not self._kv_initialized:

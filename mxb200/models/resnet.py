@@ -8,8 +8,9 @@ Here, per bottleneck:
   1x1 conv  -> tcgen05 GEMM over pixels (ops.functional.conv1x1_nhwc), fwd/dgrad/wgrad all ours
   BN+ReLU   -> one stats pass + one apply pass (ops.functional.bn_act)
   BN+add+ReLU at the block end -> the same two passes (residual and ReLU fused in)
-  3x3 / 7x7 conv -> cuDNN via torch on the channels-last view (library op; replaced by an implicit-GEMM
-                    tcgen05 kernel when available)
+  3x3 conv  -> implicit-GEMM tcgen05 kernel (im2col-mode TMA feeds the same GEMM pipeline; BN statistics in the
+               epilogue; fwd / dgrad / wgrad; csrc/cuda/gemm_tcgen05.cu CONV modes)
+  7x7 stem  -> small-channel im2col kernel + tcgen05 GEMM (ops.functional.stem_conv_nhwc)
 
 Activations stay [N, H, W, C] contiguous; weights of 1x1 convs are [Cout, Cin] matrices, spatial kernels
 are stored [Cout, kh, kw, Cin] (KRSC) and exposed to cuDNN as channels_last (Cout, Cin, kh, kw) views.
@@ -154,6 +155,19 @@ def _sink(G, name):
     return G.get(name) if G is not None else None
 
 
+def _conv_bn(x, P, A, G, wname, bnname, relu, stride, pad, residual=None, training=True, eps=1e-5, momentum=0.9):
+    """k x k convolution + BatchNorm(+residual)(+ReLU).  On B200 the convolution is the implicit-GEMM tcgen05 kernel
+    (im2col-mode TMA), its epilogue emits the BatchNorm statistics, dW lands in the gradient arena; otherwise (CPU, odd
+    channel counts) the library convolution followed by the stand-alone statistics pass."""
+    w = P[wname]
+    if K.conv_nhwc_ok(x, w):
+        ws = K.bn_stats_workspace_for(x.device, w.shape[0]) if training else None
+        o = K.conv_nhwc(x, w, stride, pad, stats=ws, sink_w=_sink(G, wname))
+        return _bn(o, P, A, G, bnname, relu, residual, training, eps, momentum, pre_stats=ws)
+    o = _conv_spatial(x, w, stride, pad)
+    return _bn(o.contiguous(), P, A, G, bnname, relu, residual, training, eps, momentum)
+
+
 def _bn(x, P, A, G, name, relu, residual=None, training=True, eps=1e-5, momentum=0.9, pre_stats=None):
     return K.bn_act(x, P[name + "_gamma"], P[name + "_beta"], A[name + "_running_mean"], A[name + "_running_var"],
                     residual=residual, relu=relu, eps=eps, momentum=momentum, training=training, pre_stats=pre_stats,
@@ -213,6 +227,10 @@ def _conv_bn_eval(x, P, A, wname, bnname, relu, stride=1, pad=0, residual=None, 
     if K.stem_conv_ok(x, wf):
         y = K.stem_conv_nhwc(x, wf, stride, pad, bias=shift, relu=relu)
         return y
+    if K.conv_nhwc_ok(x, wf):
+        # implicit-GEMM tcgen05 convolution: folded-BN shift = bias, residual add and ReLU in the epilogue
+        return K.conv_fwd_raw(x.contiguous(), wf.permute(0, 2, 3, 1), stride, pad, bias=shift, relu=relu,
+                              addend=residual.contiguous() if residual is not None else None)
     y = F.conv2d(x.permute(0, 3, 1, 2), wf, shift.to(wf.dtype), stride, pad).permute(0, 2, 3, 1)
     if residual is not None:
         y = y + residual
@@ -281,14 +299,11 @@ def resnet_forward(spec, P, A, x, training=True, eps=1e-5, momentum=0.9, G=None,
                     o = _conv1x1_bn(y, P, A, G, pre + "conv1_weight", pre + "bn1", True, s1, **kw)
                     skip = y
                 res = _conv1x1_bn(skip, P, A, G, pre + "down_weight", pre + "down_bn", False, stride, **kw) if has_down else skip
-                o = _conv_spatial(o, P[pre + "conv2_weight"], s2, 1)
-                o = _bn(o.contiguous(), P, A, G, pre + "bn2", True, **kw)
+                o = _conv_bn(o, P, A, G, pre + "conv2_weight", pre + "bn2", True, s2, 1, **kw)
                 y = _conv1x1_bn(o, P, A, G, pre + "conv3_weight", pre + "bn3", True, 1, residual=res, **kw)
             else:
                 res = _conv1x1_bn(y, P, A, G, pre + "down_weight", pre + "down_bn", False, stride, **kw) if has_down else y
-                o = _conv_spatial(y, P[pre + "conv1_weight"], stride, 1)
-                o = _bn(o.contiguous(), P, A, G, pre + "bn1", True, **kw)
-                o = _conv_spatial(o, P[pre + "conv2_weight"], 1, 1)
-                y = _bn(o.contiguous(), P, A, G, pre + "bn2", True, residual=res, **kw)
+                o = _conv_bn(y, P, A, G, pre + "conv1_weight", pre + "bn1", True, stride, 1, **kw)
+                y = _conv_bn(o, P, A, G, pre + "conv2_weight", pre + "bn2", True, 1, 1, residual=res, **kw)
     pooled = y.float().mean(dim=(1, 2)).to(y.dtype)  # global average pool
     return K.linear(pooled, P["fc_weight"], P["fc_bias"], sink_w=_sink(G, "fc_weight"), sink_b=_sink(G, "fc_bias"))

@@ -256,6 +256,107 @@ def conv1x1_nhwc(x, w, stride=1, stats=None, sink_w=None, passthrough=False):
     return r.reshape(n, h, ww, w.shape[0])
 
 
+# --------------------------------------------------------------------------- k x k convolution: implicit GEMM on tcgen05
+def _krsc(w):
+    """[O, kh, kw, I] contiguous view of a (O, I, kh, kw) weight stored channels-last (KRSC), or None."""
+    v = w.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else None
+
+
+def conv_nhwc_ok(x, w):
+    """Can csrc/cuda/gemm_tcgen05.cu run this convolution as an implicit GEMM (im2col-mode TMA)?"""
+    if not (x.is_cuda and x.dim() == 4 and w.dim() == 4 and x.dtype is torch.bfloat16 and w.dtype is torch.bfloat16):
+        return False
+    if getenv("MXB200_CONV", "tcgen05") != "tcgen05" or not N.have_cuda_kernels():
+        return False
+    o, c, kh, kw = w.shape
+    return (c % 64 == 0 and o % 64 == 0 and kh * kw <= 49 and x.shape[-1] == c and _krsc(w) is not None
+            and x.numel() < 2 ** 31)
+
+
+def conv_fwd_raw(x, wk, stride, pad, bias=None, relu=False, col_stats=None, block_n=0, addend=None):
+    n, h, ww, c = x.shape
+    o, kh, kw, _ = wk.shape
+    P, Q = (h + 2 * pad - kh) // stride + 1, (ww + 2 * pad - kw) // stride + 1
+    y = torch.empty((n, P, Q, o), dtype=torch.bfloat16, device=x.device)
+    cs, cs2 = col_stats if col_stats is not None else (None, None)
+    lib = N.cuda()
+    N.check(lib, lib.MXBConvFwdBf16(_p(x), _p(wk), _p(y), c_int(n), c_int(h), c_int(ww), c_int(c), c_int(o), c_int(kh), c_int(kw),
+                                    c_int(stride), c_int(pad), _p(bias), c_int(1 if relu else 0), _p(cs), _p(cs2),
+                                    _p(addend), c_int(block_n), N.stream_of(x)))
+    LAUNCHES[0] += 1
+    return y
+
+
+def conv_dgrad_raw(dy, wk, xshape, stride, pad, addend=None):
+    n, h, ww, c = xshape
+    o, kh, kw, _ = wk.shape
+    dx = torch.empty((n, h, ww, c), dtype=torch.bfloat16, device=dy.device)
+    lib = N.cuda()
+    N.check(lib, lib.MXBConvDgradBf16(_p(dy), _p(wk), _p(dx), c_int(n), c_int(h), c_int(ww), c_int(c), c_int(o), c_int(kh),
+                                      c_int(kw), c_int(stride), c_int(pad), _p(addend), N.stream_of(dy)))
+    LAUNCHES[0] += 1 if stride == 1 else stride * stride
+    return dx
+
+
+def conv_wgrad_raw(dy, x, kshape, stride, pad, out=None, splits=0, block_n=0):
+    """dW (fp32, [O, kh, kw, I]) += dy^T . im2col(x).  ``out``: contiguous fp32 buffer that is accumulated into."""
+    n, h, ww, c = x.shape
+    o, kh, kw, _ = kshape
+    acc = out if out is not None else torch.zeros((o, kh, kw, c), dtype=torch.float32, device=x.device)
+    lib = N.cuda()
+    N.check(lib, lib.MXBConvWgradBf16(_p(dy), _p(x), _p(acc), c_int(n), c_int(h), c_int(ww), c_int(c), c_int(o), c_int(kh),
+                                      c_int(kw), c_int(stride), c_int(pad), c_int(splits), c_int(block_n), N.stream_of(x)))
+    LAUNCHES[0] += 1
+    return acc
+
+
+class _ConvNhwcFn(torch.autograd.Function):
+    """y = conv(x, w) on channels-last tensors, all three passes on the implicit-GEMM tcgen05 kernel.  ``stats``: BN
+    workspace receiving the per-channel sum / sum-of-squares of y (GEMM epilogue); ``sink_w``: fp32 gradient-arena view of
+    the weight (same KRSC strides) that receives dW directly."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, pad, stats, sink_w):
+        if not x.is_contiguous():
+            x = x.contiguous()
+        wk = _krsc(w)
+        o = wk.shape[0]
+        cs = (stats[STATS_OFF:STATS_OFF + o], stats[STATS_OFF + o:STATS_OFF + 2 * o]) if stats is not None else None
+        y = conv_fwd_raw(x, wk, stride, pad, col_stats=cs)
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, pad)
+        sk = _krsc(sink_w) if (sink_w is not None and sink_w.dtype is torch.float32 and sink_w.shape == w.shape) else None
+        ctx.sink = sk
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        stride, pad = ctx.cfg
+        wk = _krsc(w)
+        if not dy.is_contiguous():
+            dy = dy.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = conv_dgrad_raw(dy, wk, x.shape, stride, pad)
+        if ctx.sink is not None:
+            conv_wgrad_raw(dy, x, wk.shape, stride, pad, out=ctx.sink)
+        elif ctx.needs_input_grad[1]:
+            dw = conv_wgrad_raw(dy, x, wk.shape, stride, pad).permute(0, 3, 1, 2).to(w.dtype)
+        return dx, dw, None, None, None, None
+
+
+def conv_nhwc(x, w, stride=1, pad=0, stats=None, sink_w=None):
+    """k x k convolution of an NHWC bf16 tensor with a (O, I, kh, kw) weight stored KRSC.  Reference operator:
+    Convolution (src/operator/nn/convolution.cu:40-128; cuDNN or im2col+GEMM there)."""
+    if conv_nhwc_ok(x, w):
+        return _ConvNhwcFn.apply(x, w, int(stride), int(pad), stats, sink_w)
+    if x.is_cuda and not N.have_cuda_kernels():
+        raise RuntimeError("mxb200: CUDA kernels library missing on a GPU host")
+    return F.conv2d(x.permute(0, 3, 1, 2), w, None, stride, pad).permute(0, 2, 3, 1)
+
+
 class _StemConvFn(torch.autograd.Function):
     """Small-channel k x k convolution (the ResNet stem) as im2col + tcgen05 GEMM (csrc/cuda/im2col.cu).
     The input image gets no gradient (it is data)."""
@@ -342,6 +443,15 @@ def fused_stats_workspace(x, w, force=False):
     if not (cv > 0 and cv <= 256 and (cv & (cv - 1)) == 0):
         return None
     return _BnWorkspace.get(x.device, C)
+
+
+def bn_stats_workspace_for(device, C):
+    """Like ``fused_stats_workspace`` for a producer that is known to be one of our GEMM-epilogue kernels: None when the
+    BatchNorm kernel cannot consume pre-computed statistics for this width."""
+    cv = C // 8 if C % 8 == 0 else 0
+    if not (cv > 0 and cv <= 256 and (cv & (cv - 1)) == 0 and N.have_cuda_kernels()):
+        return None
+    return _BnWorkspace.get(torch.device(device), C)
 
 
 def bn_stats_workspace(device, C):

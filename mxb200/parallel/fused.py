@@ -33,7 +33,20 @@ class _Args(ctypes.Structure):
                 ("one_shot", c_int), ("g_dt", c_int), ("w_dt", c_int), ("seq", c_uint32), ("zero_grad", c_int),
                 ("lr", c_float), ("wd", c_float), ("momentum", c_float), ("rescale", c_float), ("clip", c_float),
                 ("nesterov", c_int), ("has_mom", c_int), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
-                ("bc1", c_float), ("bc2", c_float), ("lamb_lower", c_float), ("lamb_upper", c_float)]
+                ("bc1", c_float), ("bc2", c_float), ("lamb_lower", c_float), ("lamb_upper", c_float), ("hyper", c_void_p)]
+
+HYPER_FLOATS = 8      # csrc/cuda/allreduce.cu: [lr, wd, momentum, rescale, clip, seq(uint32 bits), bc1, bc2]
+
+
+def pack_hyper(lr=0.0, wd=0.0, momentum=0.0, rescale=1.0, clip=None, seq=0, bc1=1.0, bc2=1.0):
+    """Host image of one hyper-parameter record (see ``Args.hyper``): the per-step scalars of a fused launch that a
+    CUDA graph must NOT freeze."""
+    a = np.zeros(HYPER_FLOATS, dtype=np.float32)
+    a[0], a[1], a[2], a[3] = lr, wd, momentum, rescale
+    a[4] = -1.0 if clip is None else clip
+    a[5:6].view(np.uint32)[0] = np.uint32(seq & 0xFFFFFFFF)
+    a[6], a[7] = bc1, bc2
+    return a
 
 
 def _check_abi(lib):
@@ -96,8 +109,12 @@ class SymmetricArena(object):
 
 def fused_step(arena, mode, lr=0.0, wd=0.0, momentum=0.0, rescale=1.0, clip=None, nesterov=False, multi_precision=True,
                zero_grad=True, beta1=0.9, beta2=0.999, eps=1e-8, bc1=1.0, bc2=1.0, lamb_lower=-1.0, lamb_upper=-1.0,
-               one_shot=None, blocks=0, seq=None):
-    """Launch the fused kernel for one arena on this rank's current stream."""
+               one_shot=None, blocks=0, seq=None, hyper=None):
+    """Launch the fused kernel for one arena on this rank's current stream.
+
+    ``hyper``: fp32 device tensor of HYPER_FLOATS entries (``pack_hyper``) that the kernel reads lr / wd / momentum /
+    rescale / clip / bc1 / bc2 and the barrier sequence number from; ``seq`` is then an OFFSET added to the value stored in
+    the buffer.  This is what makes a captured launch replayable (parallel/graph.py)."""
     g = arena.group
     lib = g.lib
     _check_abi(lib)
@@ -111,7 +128,11 @@ def fused_step(arena, mode, lr=0.0, wd=0.0, momentum=0.0, rescale=1.0, clip=None
     gbytes = arena.n * arena.grads.element_size()
     a.one_shot = int(one_shot if one_shot is not None else gbytes <= ONE_SHOT_BYTES)
     a.g_dt, a.w_dt = code(arena.gdtype), code(arena.wdtype)
-    a.seq = seq if seq is not None else g.next_seq()
+    if hyper is not None:
+        a.hyper = hyper.data_ptr()
+        a.seq = seq if seq is not None else 0
+    else:
+        a.seq = seq if seq is not None else g.next_seq()
     a.zero_grad = int(zero_grad)
     a.lr, a.wd, a.momentum, a.rescale = lr, wd, momentum, rescale
     a.clip = -1.0 if clip is None else clip

@@ -60,6 +60,7 @@ class DeviceTrainer(object):
                             p.grad = None
                     self._hooks.append(v.register_post_accumulate_grad_hook(_move))
         self.num_update = 0
+        self.hyper_host = self.hyper_dev = None
 
     def params(self):
         """name -> leaf tensor view into the arena (use these in the model)."""
@@ -76,34 +77,58 @@ class DeviceTrainer(object):
             ar.grads.zero_()
 
     def step(self, optimizer="sgd", lr=0.01, wd=0.0, momentum=0.0, rescale=1.0, clip=None, multi_precision=True,
-             beta1=0.9, beta2=0.999, eps=1e-8, zero_grad=True, blocks=0, bias_correction=True, lamb_bounds=(-1.0, -1.0)):
-        """One synchronous data-parallel optimizer step (all ranks must call it)."""
-        self.num_update += 1
+             beta1=0.9, beta2=0.999, eps=1e-8, zero_grad=True, blocks=0, bias_correction=True, lamb_bounds=(-1.0, -1.0),
+             phase=None):
+        """One synchronous data-parallel optimizer step (all ranks must call it).
+
+        ``phase`` splits the step for CUDA-graph replay (parallel/graph.py):
+          None      eager: scalars travel by value with the launch;
+          "host"    bookkeeping only: bump the update counter, reserve barrier sequence numbers and upload this step's
+                    scalars (lr, wd, momentum, rescale, clip, bias corrections, seq) into the device-resident hyper buffer;
+          "device"  launches only, reading those scalars from the hyper buffer -- the part that is captured / replayed."""
+        if phase != "device":
+            self.num_update += 1
         t = self.num_update
-        for ar in self.arenas:
-            if optimizer in ("sgd", "nag"):
-                fused.fused_step(ar, fused.MODE_SGD, lr=lr, wd=wd, momentum=momentum, rescale=rescale, clip=clip,
-                                 nesterov=(optimizer == "nag"), multi_precision=multi_precision, zero_grad=zero_grad,
-                                 blocks=blocks)
-            elif optimizer == "adam":
+        if optimizer not in ("sgd", "nag", "adam", "lamb"):
+            raise ValueError("DeviceTrainer: optimizer %r has no fused kernel" % optimizer)
+        if phase is not None and self.hyper_dev is None:
+            self.hyper_host = torch.zeros((len(self.arenas), fused.HYPER_FLOATS), dtype=torch.float32)
+            self.hyper_dev = torch.zeros((len(self.arenas), fused.HYPER_FLOATS), dtype=torch.float32, device=self.device)
+        for idx, ar in enumerate(self.arenas):
+            lr_eff, bc1, bc2 = lr, 1.0, 1.0
+            if optimizer == "adam":
                 # bias correction folded into lr (python/mxnet/optimizer/optimizer.py:1079-1082)
-                lr_t = lr * (1.0 - beta2 ** t) ** 0.5 / (1.0 - beta1 ** t)
-                fused.fused_step(ar, fused.MODE_ADAM, lr=lr_t, wd=wd, rescale=rescale, clip=clip, beta1=beta1,
-                                 beta2=beta2, eps=eps, multi_precision=multi_precision, zero_grad=zero_grad,
-                                 blocks=blocks)
+                lr_eff = lr * (1.0 - beta2 ** t) ** 0.5 / (1.0 - beta1 ** t)
             elif optimizer == "lamb":
                 bc1 = 1.0 - beta1 ** t if bias_correction else 1.0
                 bc2 = 1.0 - beta2 ** t if bias_correction else 1.0
-                ar.get_state("rbuf")
-                fused.fused_step(ar, fused.MODE_LAMB1, lr=lr, wd=wd, rescale=rescale, clip=clip, beta1=beta1,
-                                 beta2=beta2, eps=eps, bc1=bc1, bc2=bc2, multi_precision=multi_precision,
-                                 zero_grad=zero_grad, blocks=blocks)
-                self._allreduce_norms(ar)
-                fused.fused_step(ar, fused.MODE_LAMB2, lr=lr, multi_precision=multi_precision, zero_grad=False,
-                                 lamb_lower=lamb_bounds[0], lamb_upper=lamb_bounds[1], blocks=blocks)
-                ar.state["norms"].zero_()
+            if phase == "host":
+                seq0 = self.group.next_seq()
+                if optimizer == "lamb":
+                    self.group.next_seq()                  # the second launch of the step uses seq0 + 1
+                self.hyper_host[idx] = torch.from_numpy(fused.pack_hyper(lr_eff, wd, momentum, rescale, clip, seq0, bc1, bc2))
+                continue
+            hy = self.hyper_dev[idx] if phase == "device" else None
+            if optimizer in ("sgd", "nag"):
+                fused.fused_step(ar, fused.MODE_SGD, lr=lr_eff, wd=wd, momentum=momentum, rescale=rescale, clip=clip,
+                                 nesterov=(optimizer == "nag"), multi_precision=multi_precision, zero_grad=zero_grad,
+                                 blocks=blocks, hyper=hy)
+            elif optimizer == "adam":
+                fused.fused_step(ar, fused.MODE_ADAM, lr=lr_eff, wd=wd, rescale=rescale, clip=clip, beta1=beta1,
+                                 beta2=beta2, eps=eps, multi_precision=multi_precision, zero_grad=zero_grad,
+                                 blocks=blocks, hyper=hy)
             else:
-                raise ValueError("DeviceTrainer: optimizer %r has no fused kernel" % optimizer)
+                ar.get_state("rbuf")
+                fused.fused_step(ar, fused.MODE_LAMB1, lr=lr_eff, wd=wd, rescale=rescale, clip=clip, beta1=beta1,
+                                 beta2=beta2, eps=eps, bc1=bc1, bc2=bc2, multi_precision=multi_precision,
+                                 zero_grad=zero_grad, blocks=blocks, hyper=hy)
+                self._allreduce_norms(ar)
+                fused.fused_step(ar, fused.MODE_LAMB2, lr=lr_eff, multi_precision=multi_precision, zero_grad=False,
+                                 lamb_lower=lamb_bounds[0], lamb_upper=lamb_bounds[1], blocks=blocks, hyper=hy,
+                                 seq=1 if hy is not None else None)
+                ar.state["norms"].zero_()
+        if phase == "host":
+            self.hyper_dev.copy_(self.hyper_host)          # pageable -> device: staged by the runtime, stream ordered
 
     def _allreduce_norms(self, ar):
         if self.world == 1:

@@ -969,3 +969,98 @@ def test_nd_pooling_max_fast_path_channels_last(k, s, p):
     assert y.shape == tuple(yr.shape)
     assert torch.equal(y._t.float(), yr.detach())
     assert _rel_err(X.grad._t, xr.grad) < 1e-2
+
+
+# ----------------------------------------------------------------------------- implicit-GEMM convolution (tcgen05 + im2col TMA)
+def _assert_close_elementwise(a, b, rtol, atol_scale, what):
+    """Per-element |a-b| <= atol + rtol*|b| with atol relative to the RMS of the reference (a single wrong tile or a bad
+    K tail shows up here even when the global max-norm ratio would hide it)."""
+    a, b = a.float(), b.float()
+    atol = atol_scale * b.pow(2).mean().sqrt().item()
+    bad = (a - b).abs() > (atol + rtol * b.abs())
+    assert not bad.any(), "%s: %d / %d elements out of tolerance, worst |diff| %.4g (atol %.4g)" % (
+        what, int(bad.sum()), bad.numel(), (a - b).abs().max().item(), atol)
+
+
+# every 3x3 convolution shape of ResNet-50 v1b (n, h, w, cin, cout, stride) at a reduced batch, plus ragged / generic ones
+_CONV_SHAPES = [
+    (4, 56, 56, 64, 64, 1), (2, 56, 56, 128, 128, 2), (4, 28, 28, 128, 128, 1), (4, 28, 28, 256, 256, 2),
+    (8, 14, 14, 256, 256, 1), (8, 14, 14, 512, 512, 2), (16, 7, 7, 512, 512, 1),
+    (3, 13, 17, 64, 192, 1), (2, 15, 9, 128, 64, 2), (1, 8, 8, 64, 64, 1),
+]
+
+
+@pytest.mark.parametrize("n,h,w,c,o,stride", _CONV_SHAPES)
+def test_conv3x3_implicit_gemm_fwd_dgrad_wgrad(n, h, w, c, o, stride):
+    import torch.nn.functional as F
+    from mxb200.ops import functional as K_
+    g = torch.Generator(device="cuda").manual_seed(n * 1000 + h * 10 + c)
+    x = torch.randn(n, h, w, c, device=_dev(), generator=g).bfloat16()
+    wk = (torch.randn(o, 3, 3, c, device=_dev(), generator=g) * (2.0 / (9 * c)) ** 0.5).bfloat16()
+    wt = wk.permute(0, 3, 1, 2)                        # (O, I, kh, kw) view of KRSC storage
+    assert K_.conv_nhwc_ok(x, wt)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.float().detach().clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, stride, 1)
+    # forward (+ fused BN statistics)
+    s1, s2 = torch.zeros(o, device=_dev()), torch.zeros(o, device=_dev())
+    y = K_.conv_fwd_raw(x, wk, stride, 1, col_stats=(s1, s2))
+    refn = ref.detach().permute(0, 2, 3, 1)
+    assert y.shape == refn.shape
+    _assert_close_elementwise(y, refn, 1.6e-2, 2e-2, "fwd")
+    assert _rel_err(s1, y.float().sum((0, 1, 2))) < 2e-3
+    assert _rel_err(s2, (y.float() ** 2).sum((0, 1, 2))) < 2e-3
+    # backward
+    dy = torch.randn(refn.shape, device=_dev(), generator=g).bfloat16()
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    dx = K_.conv_dgrad_raw(dy, wk, x.shape, stride, 1)
+    _assert_close_elementwise(dx, xr.grad.permute(0, 2, 3, 1), 1.6e-2, 2e-2, "dgrad")
+    dw = K_.conv_wgrad_raw(dy, x, wk.shape, stride, 1)
+    _assert_close_elementwise(dw, wr.grad.permute(0, 2, 3, 1), 1e-2, 1e-2, "wgrad")
+    # accumulate into an existing buffer (gradient-arena semantics)
+    acc = torch.ones_like(dw)
+    K_.conv_wgrad_raw(dy, x, wk.shape, stride, 1, out=acc)
+    _assert_close_elementwise(acc - 1.0, wr.grad.permute(0, 2, 3, 1), 1e-2, 1.5e-2, "wgrad accumulate")
+
+
+@pytest.mark.parametrize("k,stride,pad", [(1, 1, 0), (5, 1, 2), (3, 1, 0), (5, 2, 2), (3, 3, 1), (1, 2, 0)])
+def test_conv_generic_kernel_sizes(k, stride, pad):
+    import torch.nn.functional as F
+    from mxb200.ops import functional as K_
+    n, h, w, c, o = 2, 18, 22, 64, 128
+    x = torch.randn(n, h, w, c, device=_dev()).bfloat16()
+    wk = (torch.randn(o, k, k, c, device=_dev()) * (2.0 / (k * k * c)) ** 0.5).bfloat16()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wk.float().permute(0, 3, 1, 2).detach().clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, stride, pad)
+    y = K_.conv_fwd_raw(x, wk, stride, pad)
+    _assert_close_elementwise(y, ref.detach().permute(0, 2, 3, 1), 1.6e-2, 2e-2, "fwd")
+    dy = torch.randn_like(y)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    dx = K_.conv_dgrad_raw(dy, wk, x.shape, stride, pad)
+    _assert_close_elementwise(dx, xr.grad.permute(0, 2, 3, 1), 1.6e-2, 2e-2, "dgrad")
+    dw = K_.conv_wgrad_raw(dy, x, wk.shape, stride, pad)
+    _assert_close_elementwise(dw, wr.grad.permute(0, 2, 3, 1), 1e-2, 1e-2, "wgrad")
+
+
+def test_conv_nhwc_autograd_bias_relu_residual_epilogue():
+    import torch.nn.functional as F
+    from mxb200.ops import functional as K_
+    n, h, w, c, o = 2, 14, 14, 128, 256
+    x = torch.randn(n, h, w, c, device=_dev()).bfloat16().requires_grad_(True)
+    wt = (torch.randn(o, 3, 3, c, device=_dev()) * 0.03).bfloat16().permute(0, 3, 1, 2).requires_grad_(True)
+    y = K_.conv_nhwc(x, wt, 1, 1)
+    (y.float() ** 2).sum().backward()
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.detach().float().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, 1, 1)
+    (yr ** 2).sum().backward()
+    _assert_close_elementwise(y, yr.detach().permute(0, 2, 3, 1), 1.6e-2, 2e-2, "y")
+    _assert_close_elementwise(x.grad, xr.grad.permute(0, 2, 3, 1), 3e-2, 3e-2, "dx")
+    _assert_close_elementwise(wt.grad, wr.grad, 3e-2, 3e-2, "dw")
+    # inference epilogue: bias + residual + relu in one kernel
+    b = torch.randn(o, device=_dev())
+    res = torch.randn(n, h, w, o, device=_dev()).bfloat16()
+    z = K_.conv_fwd_raw(x.detach(), wt.detach().permute(0, 2, 3, 1), 1, 1, bias=b, relu=True, addend=res)
+    zr = torch.relu(yr.detach().permute(0, 2, 3, 1) + b + res.float())
+    _assert_close_elementwise(z, zr, 1.6e-2, 2e-2, "bias+residual+relu")
