@@ -4,6 +4,7 @@ import math
 import time
 
 from .model import save_checkpoint
+from .base import getenv
 
 __all__ = ["module_checkpoint", "do_checkpoint", "log_train_metric", "Speedometer", "ProgressBar", "LogValidationMetricsCallback"]
 
@@ -23,7 +24,8 @@ def do_checkpoint(prefix, period=1):
 
     def _callback(iter_no, sym, arg, aux):
         if (iter_no + 1) % period == 0:
-            save_checkpoint(prefix, iter_no + 1, sym, arg, aux)
+            # written by the dependency engine while the next epoch trains (fit() / nd.load / waitall wait for it)
+            save_checkpoint(prefix, iter_no + 1, sym, arg, aux, async_write=bool(getenv("MXB200_ASYNC_CHECKPOINT", True)))
     return _callback
 
 

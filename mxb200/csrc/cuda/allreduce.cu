@@ -40,6 +40,7 @@ enum Mode : int {
   kLambPhase1 = 3,  // reduce + moments + direction r (local slice) + per-tensor partial norms
   kLambPhase2 = 4,  // w -= lr*trust*r on the slice, weights fanned out (no gradient traffic)
   kBroadcast = 5,   // weights_p[i] = src[i] for the owned slice (init / re-shard)
+  kLamb = 6,        // phases 1 + 2 in one launch with an in-kernel cross-rank reduction of the per-tensor norms
 };
 
 struct Args {
@@ -71,6 +72,20 @@ struct Args {
   //   [0] lr  [1] wd  [2] momentum  [3] rescale  [4] clip  [5] seq (uint32 bits)  [6] bc1  [7] bc2
   // ``seq`` then acts as an offset added to hyper[5] (several launches of one step share one buffer).
   const float* hyper;
+  // NVLS: multicast mappings of the gradient / weight arenas (null: P2P loads / stores over the unicast peer mappings)
+  void* grads_mc;
+  void* weights_mc;
+  // fused LAMB (mode kLamb): per-rank partial norm buffers [2][nt_pad] in peer-mapped memory, local totals, grid barrier
+  float* norms[kMaxRanks];
+  float* norm_tot;
+  uint32_t* gsync;            // local {count, generation} words of the intra-rank grid barrier
+  int nt_pad;
+  int pad0;
+  int64_t state_off;
+  // Device-resident barrier sequence number {seq, finished-CTA count}: when non-null the kernel reads seq from here and the
+  // last CTA to finish increments it, so replaying a captured launch needs no host-side bookkeeping at all (every rank
+  // advances its own copy identically: one increment per launch on the group).
+  uint32_t* seq_dev;          // arena element index of element 0 of w32 / mom / var / rbuf (ZeRO-1: state only for my slice)
 };
 constexpr int kHyperFloats = 8;
 
@@ -140,6 +155,69 @@ __device__ __forceinline__ void st8<float>(float* p, const float (&o)[8]) {
   *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
 }
 
+// ---- NVLS: in-switch reduction / broadcast through a multicast mapping of the symmetric arenas (csrc/cuda/vmm.cu).
+// One multimem.ld_reduce returns the sum over ALL ranks' copies of 16 bytes (the NVSwitch reduces; SASS: LDGMC.ADD),
+// one multimem.st writes 16 bytes into every rank's copy.  Per GPU the two-shot exchange then moves S(N-1)/N out + S/N in
+// for the gradients instead of S(N-1)/N in only, i.e. both link directions carry payload.
+template <typename T>
+__device__ __forceinline__ void mc_ld_reduce8(const T* p, float (&o)[8]);
+template <>
+__device__ __forceinline__ void mc_ld_reduce8<float>(const float* p, float (&o)[8]) {
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "l"(p) : "memory");
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7]) : "l"(p + 4) : "memory");
+}
+template <>
+__device__ __forceinline__ void mc_ld_reduce8<__nv_bfloat16>(const __nv_bfloat16* p, float (&o)[8]) {
+  uint4 u;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p) : "memory");
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o[2 * i] = __low2float(h[i]);
+    o[2 * i + 1] = __high2float(h[i]);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void mc_st8(T* p, const float (&o)[8]);
+template <>
+__device__ __forceinline__ void mc_st8<float>(float* p, const float (&o)[8]) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p + 4), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+}
+template <>
+__device__ __forceinline__ void mc_st8<__nv_bfloat16>(__nv_bfloat16* p, const float (&o)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+  asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+
+// All CTAs of this rank (co-resident by construction: <= 1 per SM).  count returns to zero, gen is monotonic.
+__device__ __forceinline__ void grid_barrier(uint32_t* gsync) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile uint32_t* gen = gsync + 1;
+    const uint32_t g = *gen;
+    __threadfence();
+    if (atomicAdd(gsync, 1u) == gridDim.x - 1) {
+      gsync[0] = 0;
+      __threadfence();
+      atomicAdd(gsync + 1, 1u);
+    } else {
+      uint32_t spins = 0;
+      while (*gen == g) {
+        if (++spins > kSpinLimit) break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 template <typename GT, typename WT, int NR>
 __global__ void __launch_bounds__(kThreads)
 fused_kernel(const Args a) {
@@ -152,8 +230,9 @@ fused_kernel(const Args a) {
     h_clip = __ldg(a.hyper + 4); h_seq += __float_as_uint(__ldg(a.hyper + 5)); h_bc1 = __ldg(a.hyper + 6);
     h_bc2 = __ldg(a.hyper + 7);
   }
+  if (a.seq_dev != nullptr) h_seq = a.seq + *reinterpret_cast<const volatile uint32_t*>(a.seq_dev);
   if (nr > 1) {
-    if (!peer_barrier(a, 2u * h_seq)) return;
+    if (!peer_barrier(a, 4u * h_seq)) return;
   }
   // slice owned by this rank (two-shot) or the whole arena (one-shot)
   const int64_t n_chunks = a.n / kChunk;
@@ -164,139 +243,181 @@ fused_kernel(const Args a) {
     c_end = min(n_chunks, c_begin + per);
   }
   const bool fan_out = !a.one_shot && nr > 1;
+  const bool mc_grads = a.grads_mc != nullptr && nr > 1;
+  const bool mc_weights = a.weights_mc != nullptr && fan_out;
   constexpr int kVecPerChunk = kChunk / 8;  // 128 vectors of 8 elements
   const int64_t v_begin = c_begin * kVecPerChunk, v_end = c_end * kVecPerChunk;
+  const int64_t so = a.state_off;           // optimizer state arrays start at this arena element (slice-only state)
   __shared__ float red[2][kThreads / 32];
 
-  // block-uniform trip count (LAMB phase 1 has __syncthreads inside); base is a multiple of 128 vectors, so
-  // every group of 128 consecutive threads works on exactly one 1024-element chunk (= one tensor).
-  for (int64_t base = v_begin + (int64_t)blockIdx.x * kThreads; base < v_end; base += (int64_t)gridDim.x * kThreads) {
-    const int64_t v = base + threadIdx.x;
-    const bool active = v < v_end;
-    const int64_t e = v * 8;
-    const int64_t chunk = active ? e / kChunk : 0;
-    int t = 0;
-    float lr = h_lr, wd = h_wd;
-    bool skip = !active;
-    if (active && a.chunk_tid != nullptr) {
-      t = __ldg(a.chunk_tid + chunk);
-      if (t < 0) skip = true;
-      else {
-        lr *= a.lr_mult ? __ldg(a.lr_mult + t) : 1.f;
-        wd *= a.wd_mult ? __ldg(a.wd_mult + t) : 1.f;
-      }
-    }
-    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (!skip && a.mode != kLambPhase2 && a.mode != kBroadcast) {
-      // gradient reduction: own copy first, then peers in a rank-rotated order to spread link load
-#pragma unroll
-      for (int k = 0; k < (NR > 0 ? NR : kMaxRanks); ++k) {
-        if (k < nr) {
-          const int p = (a.rank + k) % nr;
-          float x[8];
-          ld8<GT>(reinterpret_cast<const GT*>(a.grads[p]) + e, x);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] += x[j];
-        }
-      }
-    }
-    if (a.mode == kAllreduce) {
-      if (!skip) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= h_rescale;
-        if (fan_out) {
-#pragma unroll
-          for (int k = 0; k < (NR > 0 ? NR : kMaxRanks); ++k)
-            if (k < nr) st8<WT>(reinterpret_cast<WT*>(a.weights[(a.rank + k) % nr]) + e, g);
-        } else {
-          st8<WT>(reinterpret_cast<WT*>(a.weights[a.rank]) + e, g);
-        }
-      }
-      continue;
-    }
-    float w[8];
-    if (!skip) {
-      if (a.w32 != nullptr) ld8<float>(a.w32 + e, w);
-      else ld8<WT>(reinterpret_cast<const WT*>(a.weights[a.rank]) + e, w);
-    }
-    if (a.mode == kSgd) {
-      if (skip) continue;
-      SgdHyper h{h_lr, h_wd, h_mom, h_rescale, h_clip, a.nesterov, a.has_mom};
-      float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (a.has_mom) ld8<float>(a.mom + e, m);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sgd_step(w[j], g[j], m[j], h, lr, wd);
-      if (a.has_mom) st8<float>(a.mom + e, m);
-    } else if (a.mode == kAdam) {
-      if (skip) continue;
-      AdamHyper h{h_lr, h_wd, a.beta1, a.beta2, a.eps, h_rescale, h_clip};
-      float m[8], vv[8];
-      ld8<float>(a.mom + e, m);
-      ld8<float>(a.var + e, vv);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) adam_step(w[j], g[j], m[j], vv[j], h, lr, wd);
-      st8<float>(a.mom + e, m);
-      st8<float>(a.var + e, vv);
-    } else if (a.mode == kLambPhase1) {
-      // block-uniform chunk: 512 threads x 8 = 4 chunks per block iteration -> reduce per 128-thread group
-      float sw = 0.f, sr = 0.f;
-      if (!skip) {
-        LambHyper h{a.beta1, a.beta2, a.eps, h_rescale, h_clip, h_bc1, h_bc2};
-        float m[8], vv[8], r[8];
-        ld8<float>(a.mom + e, m);
-        ld8<float>(a.var + e, vv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          r[j] = lamb_dir(w[j], g[j], m[j], vv[j], h, wd);
-          sw += w[j] * w[j];
-          sr += r[j] * r[j];
-        }
-        st8<float>(a.mom + e, m);
-        st8<float>(a.var + e, vv);
-        st8<float>(a.rbuf + e, r);
-      }
-      // 128 consecutive threads (4 warps) share one chunk => one tensor id
-      sw = warp_sum(sw);
-      sr = warp_sum(sr);
-      if ((threadIdx.x & 31) == 0) {
-        red[0][threadIdx.x >> 5] = sw;
-        red[1][threadIdx.x >> 5] = sr;
-      }
-      __syncthreads();
-      if ((threadIdx.x & 127) == 0 && !skip) {
-        const int wq = threadIdx.x >> 5;
-        const float aw = red[0][wq] + red[0][wq + 1] + red[0][wq + 2] + red[0][wq + 3];
-        const float arr = red[1][wq] + red[1][wq + 1] + red[1][wq + 2] + red[1][wq + 3];
-        atomicAdd(a.w_norm2 + t, aw);
-        atomicAdd(a.r_norm2 + t, arr);
-      }
-      __syncthreads();
-      continue;
-    } else if (a.mode == kLambPhase2) {
-      if (skip) continue;
-      float wn = sqrtf(__ldg(a.w_norm2 + t)), rn = sqrtf(__ldg(a.r_norm2 + t));
-      if (a.lamb_lower >= 0.f) wn = fmaxf(wn, a.lamb_lower);
-      if (a.lamb_upper >= 0.f) wn = fminf(wn, a.lamb_upper);
-      const float ratio = (wn > 0.f && rn > 0.f) ? wn / rn : 1.f;
-      float r[8];
-      ld8<float>(a.rbuf + e, r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) w[j] -= lr * ratio * r[j];
-    } else if (a.mode == kBroadcast) {
-      if (skip) continue;
-    }
-    // write back master + fan the low-precision weights out to every replica
-    if (a.w32 != nullptr) st8<float>(a.w32 + e, w);
-    if (fan_out) {
+  auto fan = [&](int64_t e, const float (&w)[8]) {
+    if (mc_weights) {
+      mc_st8<WT>(reinterpret_cast<WT*>(a.weights_mc) + e, w);
+    } else if (fan_out) {
 #pragma unroll
       for (int k = 0; k < (NR > 0 ? NR : kMaxRanks); ++k)
         if (k < nr) st8<WT>(reinterpret_cast<WT*>(a.weights[(a.rank + k) % nr]) + e, w);
     } else {
       st8<WT>(reinterpret_cast<WT*>(a.weights[a.rank]) + e, w);
     }
+  };
+
+  // One sweep over the owned slice.  block-uniform trip count (LAMB phase 1 has __syncthreads inside); base is a multiple of
+  // 128 vectors, so every group of 128 consecutive threads works on exactly one 1024-element chunk (= one tensor).
+  auto sweep = [&](const int mode, float* wn2, float* rn2) {
+    for (int64_t base = v_begin + (int64_t)blockIdx.x * kThreads; base < v_end; base += (int64_t)gridDim.x * kThreads) {
+      const int64_t v = base + threadIdx.x;
+      const bool active = v < v_end;
+      const int64_t e = v * 8;
+      const int64_t chunk = active ? e / kChunk : 0;
+      int t = 0;
+      float lr = h_lr, wd = h_wd;
+      bool skip = !active;
+      if (active && a.chunk_tid != nullptr) {
+        t = __ldg(a.chunk_tid + chunk);
+        if (t < 0) skip = true;
+        else {
+          lr *= a.lr_mult ? __ldg(a.lr_mult + t) : 1.f;
+          wd *= a.wd_mult ? __ldg(a.wd_mult + t) : 1.f;
+        }
+      }
+      float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (!skip && mode != kLambPhase2 && mode != kBroadcast) {
+        if (mc_grads) {
+          // the switch sums the N copies: one load per 16 bytes instead of N
+          mc_ld_reduce8<GT>(reinterpret_cast<const GT*>(a.grads_mc) + e, g);
+        } else {
+          // gradient reduction: own copy first, then peers in a rank-rotated order to spread link load
+#pragma unroll
+          for (int k = 0; k < (NR > 0 ? NR : kMaxRanks); ++k) {
+            if (k < nr) {
+              const int p = (a.rank + k) % nr;
+              float x[8];
+              ld8<GT>(reinterpret_cast<const GT*>(a.grads[p]) + e, x);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) g[j] += x[j];
+            }
+          }
+        }
+      }
+      if (mode == kAllreduce) {
+        if (!skip) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] *= h_rescale;
+          fan(e, g);
+        }
+        continue;
+      }
+      float w[8];
+      if (!skip) {
+        if (a.w32 != nullptr) ld8<float>(a.w32 + (e - so), w);
+        else ld8<WT>(reinterpret_cast<const WT*>(a.weights[a.rank]) + e, w);
+      }
+      if (mode == kSgd) {
+        if (skip) continue;
+        SgdHyper h{h_lr, h_wd, h_mom, h_rescale, h_clip, a.nesterov, a.has_mom};
+        float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (a.has_mom) ld8<float>(a.mom + (e - so), m);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sgd_step(w[j], g[j], m[j], h, lr, wd);
+        if (a.has_mom) st8<float>(a.mom + (e - so), m);
+      } else if (mode == kAdam) {
+        if (skip) continue;
+        AdamHyper h{h_lr, h_wd, a.beta1, a.beta2, a.eps, h_rescale, h_clip};
+        float m[8], vv[8];
+        ld8<float>(a.mom + (e - so), m);
+        ld8<float>(a.var + (e - so), vv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) adam_step(w[j], g[j], m[j], vv[j], h, lr, wd);
+        st8<float>(a.mom + (e - so), m);
+        st8<float>(a.var + (e - so), vv);
+      } else if (mode == kLambPhase1) {
+        // block-uniform chunk: 512 threads x 8 = 4 chunks per block iteration -> reduce per 128-thread group
+        float sw = 0.f, sr = 0.f;
+        if (!skip) {
+          LambHyper h{a.beta1, a.beta2, a.eps, h_rescale, h_clip, h_bc1, h_bc2};
+          float m[8], vv[8], r[8];
+          ld8<float>(a.mom + (e - so), m);
+          ld8<float>(a.var + (e - so), vv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            r[j] = lamb_dir(w[j], g[j], m[j], vv[j], h, wd);
+            sw += w[j] * w[j];
+            sr += r[j] * r[j];
+          }
+          st8<float>(a.mom + (e - so), m);
+          st8<float>(a.var + (e - so), vv);
+          st8<float>(a.rbuf + (e - so), r);
+        }
+        // 128 consecutive threads (4 warps) share one chunk => one tensor id
+        sw = warp_sum(sw);
+        sr = warp_sum(sr);
+        if ((threadIdx.x & 31) == 0) {
+          red[0][threadIdx.x >> 5] = sw;
+          red[1][threadIdx.x >> 5] = sr;
+        }
+        __syncthreads();
+        if ((threadIdx.x & 127) == 0 && !skip) {
+          const int wq = threadIdx.x >> 5;
+          const float aw = red[0][wq] + red[0][wq + 1] + red[0][wq + 2] + red[0][wq + 3];
+          const float arr = red[1][wq] + red[1][wq + 1] + red[1][wq + 2] + red[1][wq + 3];
+          atomicAdd(wn2 + t, aw);
+          atomicAdd(rn2 + t, arr);
+        }
+        __syncthreads();
+        continue;
+      } else if (mode == kLambPhase2) {
+        if (skip) continue;
+        float wn = sqrtf(__ldcg(wn2 + t)), rn = sqrtf(__ldcg(rn2 + t));
+        if (a.lamb_lower >= 0.f) wn = fmaxf(wn, a.lamb_lower);
+        if (a.lamb_upper >= 0.f) wn = fminf(wn, a.lamb_upper);
+        const float ratio = (wn > 0.f && rn > 0.f) ? wn / rn : 1.f;
+        float r[8];
+        ld8<float>(a.rbuf + (e - so), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] -= lr * ratio * r[j];
+      } else if (mode == kBroadcast) {
+        if (skip) continue;
+      }
+      // write back master + fan the low-precision weights out to every replica
+      if (a.w32 != nullptr) st8<float>(a.w32 + (e - so), w);
+      fan(e, w);
+    }
+  };
+
+  if (a.mode == kLamb) {
+    // LAMB in ONE launch: phase 1 (reduce, moments, direction, partial norms of my slice) -> all my CTAs done ->
+    // cross-rank sum of the per-tensor partial norms over peer memory -> phase 2 (trust ratio, update, fan-out).
+    // No NCCL call, no second launch.
+    float* my_w = a.norms[a.rank];
+    float* my_r = my_w + a.nt_pad;
+    sweep(kLambPhase1, my_w, my_r);
+    grid_barrier(a.gsync);
+    float *tot_w = my_w, *tot_r = my_r;
+    if (fan_out) {
+      if (!peer_barrier(a, 4u * h_seq + 1u)) return;           // every rank's partial norms are complete and visible
+      tot_w = a.norm_tot;
+      tot_r = a.norm_tot + a.nt_pad;
+      for (int i = blockIdx.x * kThreads + threadIdx.x; i < 2 * a.nt_pad; i += gridDim.x * kThreads) {
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < (NR > 0 ? NR : kMaxRanks); ++k)
+          if (k < nr) sum += *(reinterpret_cast<const volatile float*>(a.norms[(a.rank + k) % nr]) + i);
+        a.norm_tot[i] = sum;
+      }
+      grid_barrier(a.gsync);
+    }
+    sweep(kLambPhase2, tot_w, tot_r);
+  } else {
+    sweep(a.mode, a.w_norm2, a.r_norm2);
   }
   if (nr > 1) {
-    if (!peer_barrier(a, 2u * h_seq + 1u)) return;
+    if (!peer_barrier(a, 4u * h_seq + 2u)) return;
+  }
+  if (a.mode == kLamb) {
+    // peers have finished reading my partial norms: clear them for the next step
+    float* my_w = a.norms[a.rank];
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < 2 * a.nt_pad; i += gridDim.x * kThreads) my_w[i] = 0.f;
   }
   // Everyone has consumed this rank's gradients: clear them so the next backward can accumulate
   // without a separate memset (grad_req='add'-style arena).  Done after the barrier on the FULL local arena.
@@ -305,6 +426,17 @@ fused_kernel(const Args a) {
     const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < nv; v += (int64_t)gridDim.x * kThreads)
       st8<GT>(reinterpret_cast<GT*>(a.grads[a.rank]) + v * 8, z);
+  }
+  if (a.seq_dev != nullptr) {
+    // every CTA has read the sequence number long ago (before its first barrier); the last one to finish advances it
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (atomicAdd(a.seq_dev + 1, 1u) == gridDim.x - 1) {
+        a.seq_dev[1] = 0;
+        a.seq_dev[0] = a.seq_dev[0] + 1u;
+        __threadfence();
+      }
+    }
   }
 }
 
@@ -342,6 +474,11 @@ MXB_API int MXBFusedAllreduce(const void* args_blob, int blob_bytes, int blocks,
     blocks = (int)(want < 8 ? 8 : (want > kNumSMs ? kNumSMs : want));
   }
   if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+  if (a.mode == kLamb) {
+    MXB_CHECK(a.gsync != nullptr && a.norm_tot != nullptr && a.norms[a.rank] != nullptr && a.nt_pad > 0,
+              "fused LAMB needs the norm buffers and the grid-barrier words");
+    if (blocks > kNumSMs) blocks = kNumSMs;     // the intra-rank grid barrier needs every CTA resident
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (a.g_dt == kBF16 && a.w_dt == kBF16) launch_nr<__nv_bfloat16, __nv_bfloat16>(a, blocks, s);
   else if (a.g_dt == kBF16 && a.w_dt == kF32) launch_nr<__nv_bfloat16, float>(a, blocks, s);

@@ -134,7 +134,18 @@ def get():
     with _lock:
         if _engine[0] is None:
             _engine[0] = Engine()
+            import atexit
+            atexit.register(_drain_at_exit)
         return _engine[0]
+
+
+def _drain_at_exit():
+    e = _engine[0]
+    if e is not None:
+        try:
+            e.wait_all()                       # asynchronous checkpoint writes must reach the disk
+        except BaseException:  # noqa: BLE001
+            pass
 
 
 _bulk = threading.local()

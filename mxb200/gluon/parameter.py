@@ -187,6 +187,8 @@ class Parameter(object):
             warnings.warn("Parameter '%s' is already initialized, ignoring. Set force_reinit=True to re-initialize."
                           % self.name, stacklevel=2)
             return
+        if self._data is not None and self._trainer is not None and getattr(self._trainer, "_fused", None) is not None:
+            self._trainer._reset_kvstore()        # the arena views are about to be replaced: un-fuse, re-fuse lazily
         self._data = self._grad = None
         if ctx is None:
             ctx = [current_context()]
@@ -231,6 +233,14 @@ class Parameter(object):
         for arr in self._data:
             with torch.no_grad():
                 arr._t.copy_(data._t.to(arr._t.device))
+        self._refresh_fused_master()
+
+    def _refresh_fused_master(self):
+        """The low-precision weights were overwritten from outside (set_data / load_parameters): the fused Trainer must
+        re-derive its fp32 master copy from them, otherwise its next step would resurrect the old values."""
+        tr = self._trainer
+        if tr is not None and getattr(tr, "_fused", None) is not None:
+            tr._fused.refresh_master()
 
     def row_sparse_data(self, row_id):
         d = self.data(row_id.context)
@@ -301,6 +311,8 @@ class Parameter(object):
         self.dtype = dtype
         if self._data is None:
             return
+        if self._trainer is not None and getattr(self._trainer, "_fused", None) is not None:
+            self._trainer._reset_kvstore()        # parameters leave the arena: the Trainer re-fuses over the new tensors
         with autograd.pause():
             self._data = [NDArray(d._t.detach().to(torch_dtype(dtype)), d.context) for d in self._data]
             self._init_grad()

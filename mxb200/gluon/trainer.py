@@ -135,6 +135,9 @@ class Trainer(object):
         for p in self._params:
             if p._data is None:
                 return False
+            # the fused kernel is instantiated for fp32 and bf16 arenas; float16 / float64 nets take the generic updaters
+            if p.grad_req != "null" and p._data[0]._t.dtype not in (torch.float32, torch.bfloat16):
+                return False
         return True
 
     def init_kvstore(self):
@@ -177,7 +180,7 @@ class Trainer(object):
             p._grad_sink = dt.grad_sinks[p.name]
         if elastic:
             if state is not None:
-                dt.import_state(state)
+                dt.import_state(state, keep_full=True)
             dt.sync_from_rank0(kv._barrier)              # weights + optimizer state of rank 0 (a newcomer's live state)
             dt.broadcast_from_rank0([p._data[0]._t for p in self._params if p.grad_req == "null" and p._data is not None],
                                     kv._barrier)
@@ -200,8 +203,13 @@ class Trainer(object):
         if self._fused is None:
             return
         kv = self._kvstore
-        self._fused.gather_state(kv._barrier)            # un-shard the ZeRO-1 optimizer state while everyone is still here
-        self._elastic_state = self._fused.export_state()
+        # BatchNorm running statistics: average over the current members (one launch of the fused kernel), so that
+        # newcomers -- and everybody after the change -- continue from the job-wide statistics
+        aux = [p._data[0]._t for p in self._params if p.grad_req == "null" and p._data is not None
+               and p._data[0]._t.is_floating_point()]
+        self._fused.average_across_ranks(aux)
+        # un-shard the ZeRO-1 optimizer state while everyone is still here (collective over peer memory)
+        self._elastic_state = self._fused.export_state(kv._barrier)
         torch.cuda.synchronize(self._fused.device)
         kv._barrier()
         self._unfuse()
@@ -209,6 +217,33 @@ class Trainer(object):
     def _elastic_attach(self):
         state, self._elastic_state = getattr(self, "_elastic_state", None), None
         self._maybe_fuse(state=state if state is not None else {"num_update": 0, "params": {}})
+
+    def _on_membership_change(self, old_world, new_world):
+        """Re-apply the dynamic-mini-batch learning-rate rule after the worker set changed (hook location in the
+        reference: python/mxnet/module/base_module.py:540-549; rule: lr_scheduler.DynamicMiniBatchScheduler).  With a
+        constant per-worker batch the global batch follows the membership; an abrupt k-fold lr change also rescales the
+        accumulated momentum (momentum correction)."""
+        o = self._optimizer
+        sched = getattr(o, "lr_scheduler", None)
+        if sched is None or not hasattr(sched, "on_membership_change") or old_world == new_world:
+            return None
+        per_worker = getattr(sched, "per_worker_batch", None)
+        new_batch = per_worker * new_world if per_worker else sched.base_batch
+        lr_before = sched(o.num_update) if o.num_update else sched.base_lr * sched.cur_factor
+        sched.on_membership_change(new_batch, num_update=o.num_update)
+        corr = sched.momentum_correction() if sched.smooth_steps == 0 else 1.0
+        if self._fused is not None and corr != 1.0 and getattr(o, "momentum", 0.0):
+            self._fused.scale_state("mom", corr)
+        elif corr != 1.0:
+            for upd in self._updaters:
+                for st in upd.states.values():
+                    for x in (st if isinstance(st, (list, tuple)) else [st]):
+                        if isinstance(x, NDArray) and x._t.dtype.is_floating_point and getattr(o, "momentum", 0.0):
+                            x._t.mul_(corr)
+        self.last_lr_change = {"old_world": old_world, "new_world": new_world, "global_batch": new_batch,
+                               "lr_before": lr_before, "lr_after": sched(max(1, o.num_update)),
+                               "momentum_correction": corr}
+        return self.last_lr_change
 
     def _unfuse(self):
         dt, self._fused = self._fused, None
@@ -226,6 +261,15 @@ class Trainer(object):
             dt.close()
         except Exception:  # noqa: BLE001
             pass
+
+    def _fused_barrier(self):
+        kv = self._kvstore
+        if kv is not None and hasattr(kv, "_barrier") and hasattr(kv, "elastic_group"):
+            return kv._barrier
+        if self._fused is not None and self._fused.world > 1:
+            import torch.distributed as dist
+            return dist.barrier
+        return None
 
     def check_health(self):
         """Raise if a fused collective timed out (a peer never arrived)."""
@@ -350,9 +394,15 @@ class Trainer(object):
         if not self._kv_initialized:
             self._init_kvstore()
         if self._fused is not None:
-            state = {"num_update": self._optimizer.num_update, "trainer_num_update": self._fused.num_update,
-                     "arenas": [{k: v.detach().cpu() for k, v in ar.state.items()} for ar in self._fused.arenas]}
-            torch.save(state, fname)
+            # collective on the fused multi-GPU path: every rank's ZeRO-1 slice is fetched over peer memory, then each
+            # rank could write the same complete file (callers usually let rank 0 write).  Layout: per-parameter tensors,
+            # independent of arena packing and world size; a pickle like the reference's updater states.
+            import pickle
+            st = self._fused.export_state(self._fused_barrier())
+            blob = {"num_update": self._optimizer.num_update, "trainer_num_update": self._fused.num_update,
+                    "params": {n: {k: v.cpu() for k, v in d.items() if k != "weight"} for n, d in st["params"].items()}}
+            with open(fname, "wb") as fout:
+                pickle.dump({"mxb200_fused_states": blob}, fout)
             return
         if self._params_to_init:
             self._init_params()
@@ -366,13 +416,27 @@ class Trainer(object):
         if not self._kv_initialized:
             self._init_kvstore()
         if self._fused is not None:
-            state = torch.load(fname, map_location="cpu")
-            self._optimizer.num_update = state["num_update"]
-            self._fused.num_update = state["trainer_num_update"]
-            for ar, st in zip(self._fused.arenas, state["arenas"]):
-                for k, v in st.items():
-                    ar.get_state(k).copy_(v) if k != "norms" else None
-            return
+            import pickle
+            with open(fname, "rb") as f:
+                raw = f.read()
+            try:
+                blob = pickle.loads(raw)
+            except Exception:  # noqa: BLE001
+                blob = None
+            if isinstance(blob, dict) and "mxb200_fused_states" in blob:
+                blob = blob["mxb200_fused_states"]
+                dt = self._fused
+                dev = dt.device
+                cur = {n: {"weight": v.detach()} for n, v in dt.params().items()}
+                state = {"num_update": int(blob.get("trainer_num_update", blob["num_update"])),
+                         "params": {n: dict(cur[n], **{k: v.to(dev) for k, v in d.items()})
+                                    for n, d in blob["params"].items() if n in cur}}
+                dt.import_state(state)
+                self._optimizer.num_update = int(blob["num_update"])
+                return
+            # a file written by the generic (per-parameter updater) path, e.g. by the reference: adopt it there
+            self._unfuse()
+            self._fusable = lambda: False
         if self._params_to_init:
             self._init_params()
         if self._update_on_kvstore:

@@ -159,6 +159,7 @@ class KVStoreLocal(KVStore):
         self._store = {}
         self._device_mode = ("device" in kv_type) or ("nccl" in kv_type)
         self._residuals = {}
+        self._fused = {}            # device set -> FusedLocalComm (bucketed push / pull on the fused kernel)
 
     # reduce / broadcast (Comm) ----------------------------------------------------------------------
     def _reduce(self, ikey, vals):
@@ -236,11 +237,67 @@ class KVStoreLocal(KVStore):
             grouped[ik].extend(vlist)
         return [(ik, grouped[ik]) for ik in order]
 
+    # -- fused multi-GPU path (one process, one array per GPU): kvstore/fused_local.py ---------------------
+    def _fused_comm(self, vlist):
+        """The bucketed fused-kernel communicator for this device set, or None when the request does not qualify."""
+        if not self._device_mode or self._compression is not None:
+            return None
+        from .fused_local import FusedLocalComm
+        devs = FusedLocalComm.usable(vlist)
+        if devs is None:
+            return None
+        key = tuple(sorted(d.index for d in devs))
+        fc = self._fused.get(key)
+        if fc is None:
+            try:
+                fc = FusedLocalComm([torch.device("cuda", i) for i in key])
+            except Exception:  # noqa: BLE001 -- no peer access between these GPUs: per-key path
+                fc = False
+            self._fused[key] = fc
+        return fc or None
+
+    def _flush_fused(self):
+        for fc in self._fused.values():
+            if fc and fc.pending:
+                iks = list(fc.pending)
+                fc.flush(self._store)
+                for ik in iks:
+                    stored = self._store[ik]
+                    res = fc.results[ik]
+                    try:
+                        r = fc.device_index(stored._t.device)
+                    except ValueError:
+                        r = 0
+                    if self._updater is not None:
+                        # update on the store: the optimizer runs on the merged gradient where the weight lives; pulls
+                        # then broadcast the WEIGHT (the arena holds gradient sums)
+                        merged = NDArray(res[r] if stored._t.device == res[r].device else res[r].to(stored._t.device),
+                                         stored.context)
+                        self._updater(self._orig_key(ik), merged, stored)
+                        del fc.results[ik]
+                        continue
+                    with torch.no_grad():
+                        # device kvstore without updater: the stored value becomes the merged value (kvstore_local.h)
+                        if stored._t.device == res[r].device:
+                            stored._t.copy_(res[r])
+                        else:
+                            self._store[ik] = NDArray(res[r].clone())
+
     def push(self, key, value, priority=0):
         keys, vals = _key_value_lists(key, value)
         for ik, vlist in self._group(keys, vals):
             if ik not in self._store:
                 raise MXNetError("key %s has not been initialized" % str(ik))
+            fc = self._fused_comm(vlist) if ik <= MAX_ALLOWED_KEY_FOR_UPDATE and type(self._store[ik]) is NDArray and \
+                tuple(self._store[ik].shape) == tuple(vlist[0].shape) and self._store[ik]._t.dtype == vlist[0]._t.dtype else None
+            if fc is not None:
+                order = sorted(vlist, key=lambda v: fc.device_index(v._t.device))
+                if not fc.push(ik, [v._t for v in order]):
+                    self._flush_fused()
+                    fc.push(ik, [v._t for v in order])
+                continue
+            if self._fused:
+                self._flush_fused()
             merged = self._reduce(ik, vlist)
             stored = self._store[ik]
             if ik > MAX_ALLOWED_KEY_FOR_UPDATE:
@@ -281,6 +338,29 @@ class KVStoreLocal(KVStore):
     def pull(self, key, out=None, priority=0, ignore_sparse=True):
         assert out is not None
         keys, outs = _key_value_lists(key, out)
+        if self._fused:
+            self._flush_fused()
+            # keys reduced by the last flush: every GPU already holds the result in its arena -> one multi-tensor copy
+            # per GPU instead of a broadcast from the owner
+            per_dev = {}
+            rest_k, rest_o = [], []
+            for k, olist in zip(keys, outs):
+                ik = self._int_key(k)
+                fc = next((f for f in self._fused.values() if f and ik in f.results), None)
+                ok = fc is not None and all(type(o) is NDArray and o._t.is_cuda and o._t.device in fc.devices
+                                            and o._t.dtype == fc.results[ik][0].dtype for o in olist)
+                if not ok:
+                    rest_k.append(k); rest_o.append(olist)
+                    continue
+                for o in olist:
+                    r = fc.device_index(o._t.device)
+                    dst, src = per_dev.setdefault(o._t.device, ([], []))
+                    dst.append(o._t); src.append(fc.results[ik][r])
+            with torch.no_grad():
+                for dev, (dst, src) in per_dev.items():
+                    with torch.cuda.device(dev):
+                        torch._foreach_copy_(dst, src)
+            keys, outs = rest_k, rest_o
         for k, olist in zip(keys, outs):
             ik = self._int_key(k)
             if ik not in self._store:
@@ -401,6 +481,7 @@ class KVStoreElasticDevice(KVStoreLocal):
         self.elastic_group = ElasticGroup()
         self._trainers = []
         self._closed = False
+        self.reinit_log = []
 
     @property
     def type(self):
@@ -433,13 +514,31 @@ class KVStoreElasticDevice(KVStoreLocal):
         self.elastic_group.barrier()
 
     def _membership_change_barrier(self, env):
+        """The elastic re-init (north star: drain the engine -> rebuild the peer map -> re-apply the dynamic-mini-batch
+        learning-rate rule, without killing the process).  Timed: ``self.reinit_log`` gets one record per boundary."""
+        import time
+        from .. import engine as _engine
+        t0 = time.time()
         trainers = self._live_trainers()
+        eng = _engine.get()
+        eng.stop()                                   # drain host-side work in flight (async checkpoints, IO prefetch)
         for t in trainers:
-            t._elastic_detach()
+            t._elastic_detach()                      # average aux state, un-shard optimizer state, unmap the arenas
+        t1 = time.time()
         epoch = int(env.get("EPOCH_BEGIN", 0)) if isinstance(env, dict) else 0
         old, new = self.elastic_group.membership_barrier(epoch)      # a removed worker exits in here
+        t2 = time.time()
+        eng.start()
         for t in trainers:
-            t._elastic_attach()
+            t._elastic_attach()                      # new peer map, new arenas, state re-sharded, newcomers synced
+            t._on_membership_change(old, new)        # dynamic-mini-batch learning-rate rule + momentum correction
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        t3 = time.time()
+        rec = {"epoch": epoch, "old_world": old, "new_world": new, "drain_detach_ms": (t1 - t0) * 1e3,
+               "scheduler_barrier_ms": (t2 - t1) * 1e3, "attach_ms": (t3 - t2) * 1e3,
+               "reinit_ms_excl_scheduler": ((t1 - t0) + (t3 - t2)) * 1e3, "total_ms": (t3 - t0) * 1e3}
+        self.reinit_log.append(rec)
         return new
 
     def close(self):

@@ -162,10 +162,13 @@ class DynamicMiniBatchScheduler(LRScheduler):
     lr/(1-mu), so an abrupt k-fold lr change is a k-fold jump of an already accumulated velocity).
     """
 
-    def __init__(self, scheduler, base_batch, mode="linear", smooth_steps=0, momentum=0.0):
+    def __init__(self, scheduler, base_batch, mode="linear", smooth_steps=0, momentum=0.0, per_worker_batch=None):
         super(DynamicMiniBatchScheduler, self).__init__(getattr(scheduler, "base_lr", 0.01), 0, 0)
         assert mode in ("linear", "sqrt", "constant_global_batch")
         self.scheduler, self.base_batch, self.mode = scheduler, float(base_batch), mode
+        # constant PER-WORKER batch: the frameworks' membership hooks (gluon.Trainer._on_membership_change,
+        # BaseModule._on_membership_change) compute the new global batch as per_worker_batch * num_workers
+        self.per_worker_batch = per_worker_batch
         self.smooth_steps, self.momentum = int(smooth_steps), momentum
         self.cur_factor = 1.0
         self._from, self._to, self._t0 = 1.0, 1.0, 0

@@ -9,6 +9,7 @@ import numpy as np
 from . import kvstore as kvs
 from . import ndarray as nd
 from .ndarray import NDArray
+from .base import getenv
 
 BatchEndParam = namedtuple("BatchEndParams", ["epoch", "nbatch", "eval_metric", "locals"])
 
@@ -23,6 +24,10 @@ def _create_kvstore(kvstore, num_device, arg_params):
         kv = kvstore
     elif isinstance(kvstore, str):
         import torch.distributed as dist
+        if ("device" in kvstore or "nccl" in kvstore) and "dist" not in kvstore:
+            # a script started by torchrun joins the process group lazily: do it BEFORE deciding whether this is a
+            # multi-process job, otherwise every rank would train an unsynchronised replica with no store at all
+            kvs.kvstore._maybe_join_torchrun_job(dist)
         multi_proc = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         if num_device == 1 and "dist" not in kvstore and not multi_proc:
             kv = None
@@ -102,14 +107,17 @@ def _update_params(param_arrays, grad_arrays, updater, num_device, kvstore=None,
             updater(index * num_device + k, g, w)
 
 
-def save_checkpoint(prefix, epoch, symbol, arg_params, aux_params):
+def save_checkpoint(prefix, epoch, symbol, arg_params, aux_params, async_write=False):
     """prefix-symbol.json + prefix-%04d.params with arg:/aux: keys (model.py:434-460)."""
     if symbol is not None:
         symbol.save("%s-symbol.json" % prefix)
     save_dict = {("arg:%s" % k): v for k, v in arg_params.items()}
     save_dict.update({("aux:%s" % k): v for k, v in aux_params.items()})
     param_name = "%s-%04d.params" % (prefix, epoch)
-    nd.save(param_name, save_dict)
+    # async_write (used by the epoch-end checkpoint callbacks): the arrays are snapshotted now, the file is written by the
+    # dependency engine while the next epoch trains; readers of the file (nd.load / load_checkpoint), mx.nd.waitall(), the
+    # end of fit() and the elastic re-init drain wait for it
+    nd.save(param_name, save_dict, async_write=bool(async_write))
     logging.info('Saved checkpoint to "%s"', param_name)
 
 

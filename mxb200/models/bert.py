@@ -76,6 +76,17 @@ def init_bert_params(spec, dtype=torch.bfloat16, device="cpu", seed=0):
     return P
 
 
+def _sub(g, lo, hi):
+    """Row slice of a gradient-arena sink that keeps the arena tag (ops.functional.sink_touch)."""
+    if g is None:
+        return None
+    v = g[lo:hi]
+    ar = getattr(g, "_mxb_arena", None)
+    if ar is not None:
+        v._mxb_arena = ar
+    return v
+
+
 def _s(G, name):
     return G.get(name) if G is not None else None
 
@@ -119,8 +130,7 @@ def bert_encoder(spec, P, input_ids, token_types=None, attention_mask=None, trai
         qkv = []
         for i in range(3):
             t = K.linear(x, Wqkv[i * H:(i + 1) * H], bqkv[i * H:(i + 1) * H],
-                         sink_w=gw[i * H:(i + 1) * H] if gw is not None else None,
-                         sink_b=gb[i * H:(i + 1) * H] if gb is not None else None)
+                         sink_w=_sub(gw, i * H, (i + 1) * H), sink_b=_sub(gb, i * H, (i + 1) * H))
             qkv.append(t.view(B, S, nh, H // nh).transpose(1, 2))          # [B, nh, S, dh] view, no copy
         q, k, v = qkv
         a = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=spec.dropout if training else 0.0)

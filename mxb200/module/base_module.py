@@ -251,9 +251,37 @@ class BaseModule(object):
                 for name, val in res:
                     self.logger.info("Epoch[%d] Validation-%s=%f", epoch, name, val)
             train_data.reset()
+        # asynchronous epoch-end work pushed to the dependency engine (checkpoint writes) lands before fit() returns
+        from .. import engine as _engine
+        _engine.get().wait_all()
 
     def _on_membership_change(self, kv, prev_workers):
-        """Hook: re-apply the dynamic-mini-batch learning-rate rule (no-op for constant global batch)."""
+        """Re-apply the dynamic-mini-batch learning-rate rule (hook location in the reference:
+        python/mxnet/module/base_module.py:540-549).  A no-op for the reference's constant-global-batch recipe; with a
+        ``DynamicMiniBatchScheduler(per_worker_batch=...)`` the learning rate follows the new global batch and, for an abrupt
+        change, the momentum buffers are rescaled (momentum correction)."""
+        o = getattr(self, "_optimizer", None)
+        sched = getattr(o, "lr_scheduler", None) if o is not None else None
+        new_workers = kv.num_workers
+        if sched is None or not hasattr(sched, "on_membership_change") or new_workers == prev_workers:
+            return None
+        per_worker = getattr(sched, "per_worker_batch", None)
+        new_batch = per_worker * new_workers if per_worker else sched.base_batch
+        sched.on_membership_change(new_batch, num_update=o.num_update)
+        corr = sched.momentum_correction() if sched.smooth_steps == 0 else 1.0
+        dt = getattr(self, "_fused", None)
+        if corr != 1.0 and getattr(o, "momentum", 0.0):
+            if dt is not None:
+                dt.scale_state("mom", corr)
+            else:
+                upd = getattr(self, "_updater", None)
+                for st in (upd.states.values() if upd is not None else []):
+                    for x in (st if isinstance(st, (list, tuple)) else [st]):
+                        if hasattr(x, "_t") and x._t.dtype.is_floating_point:
+                            x._t.mul_(corr)
+        self.logger.info("membership %d -> %d workers: global batch %s, lr factor %.4f, momentum correction %.4f",
+                         prev_workers, new_workers, new_batch, sched.cur_factor if sched.smooth_steps == 0 else sched._to, corr)
+        return {"global_batch": new_batch, "momentum_correction": corr}
 
     # ---------------------------------------------------------------------------------- symbol / params
     @property

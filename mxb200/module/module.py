@@ -319,6 +319,8 @@ class Module(BaseModule):
             a, g = ex.arg_dict.get(n), ex.grad_dict.get(n)
             if a is None or g is None or getattr(a, "stype", "default") != "default":
                 return False
+            if a._t.dtype not in (torch.float32, torch.bfloat16):      # fp16 / fp64: generic per-key updaters
+                return False
         return bool(self._exec_group.param_names)
 
     def _maybe_fuse(self):
@@ -478,10 +480,7 @@ class Module(BaseModule):
         if getattr(self, "_fused", None) is not None:
             import pickle
             dt = self._fused
-            if dt.world > 1:
-                import torch.distributed as dist
-                dt.gather_state(dist.barrier)            # un-shard the ZeRO-1 slices first
-            st = dt.export_state()
+            st = dt.export_state()                       # collective: un-shards the ZeRO-1 slices over peer memory
             blob = {"num_update": self._optimizer.num_update,
                     "params": {n: {k: v.cpu() for k, v in d.items() if k != "weight"} for n, d in st["params"].items()}}
             with open(fname, "wb") as fout:

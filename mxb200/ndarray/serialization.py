@@ -208,8 +208,27 @@ def loads(buf, ctx=None):
     return arrs
 
 
-def save(fname, data, dtype=None):
-    """mx.nd.save (python/mxnet/ndarray/utils.py:214).  Uses the native writer when built."""
+_FILE_VARS = {}
+
+
+def _file_var(fname, create=True):
+    """Engine variable that orders asynchronous writes to (and reads of) one checkpoint file."""
+    import os
+    from .. import engine
+    key = os.path.abspath(fname)
+    v = _FILE_VARS.get(key)
+    if v is None and create:
+        v = _FILE_VARS[key] = engine.get().new_variable()
+    return v
+
+
+def save(fname, data, dtype=None, async_write=False):
+    """mx.nd.save (python/mxnet/ndarray/utils.py:214).  Uses the native writer when built.
+
+    ``async_write``: the arrays are snapshotted to host memory now (so training may overwrite them immediately) and the
+    file is written by a dependency-engine worker (csrc/host/engine.cc) -- the reference pushes the same kind of host work
+    through its ThreadedEngine.  ``mx.nd.load`` of that file, ``mx.nd.waitall()``, the elastic re-init drain
+    (engine.stop()) and interpreter exit wait for the write."""
     from .. import _native
     nat = _native.params_io()
     if nat is not None and dtype is None and _native_ok(data):
@@ -217,11 +236,27 @@ def save(fname, data, dtype=None):
         if isinstance(data, dict) and not all(isinstance(k, str) for k in names):
             raise TypeError("save only accept dict str->NDArray or list of NDArray")
         ts = [a._t.detach().contiguous().cpu() for a in arrs]
+        if async_write:
+            ts = [t.clone() if (not a._t.is_cuda and t.data_ptr() == a._t.data_ptr()) else t for t, a in zip(ts, arrs)]
         ctxs = [(a.context.device_typeid, a.context.device_id) for a in arrs]
-        nat.save(fname, names, ts, ctxs)
+
+        def write():
+            nat.save(fname, names, ts, ctxs)
+    else:
+        blob = dumps(data, dtype)
+
+        def write():
+            with open(fname, "wb") as f:
+                f.write(blob)
+    if async_write:
+        from .. import engine
+        engine.get().push(write, mutable_vars=[_file_var(fname)], name="nd.save")
         return
-    with open(fname, "wb") as f:
-        f.write(dumps(data, dtype))
+    v = _file_var(fname, create=False)
+    if v is not None:
+        from .. import engine
+        engine.get().wait_for_var(v)          # an earlier asynchronous write of the same file must land first
+    write()
 
 
 def _native_ok(data):
@@ -231,6 +266,10 @@ def _native_ok(data):
 
 def load(fname, ctx=None):
     """mx.nd.load."""
+    v = _file_var(fname, create=False)
+    if v is not None:
+        from .. import engine
+        engine.get().wait_for_var(v)          # asynchronous checkpoint write still in flight
     with open(fname, "rb") as f:
         return loads(f.read(), ctx)
 

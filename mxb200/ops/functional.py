@@ -117,6 +117,23 @@ def _gemm_ok(x, w):
     return K % 8 == 0 and Nn % 8 == 0 and x.stride(-1) == 1 and w.stride(-1) == 1 and N.have_cuda_kernels()
 
 
+def sink_touch(*sinks):
+    """'write' gradient semantics for gradient-arena sinks (reference: grad_req='write', every backward pass overwrites).
+    The arena is accumulated into by the backward kernels and cleared by the fused optimizer step; if a backward pass is
+    NOT followed by that trainer's step (GAN-style loops, skipped steps, repeated backward calls) the next backward that
+    touches the arena clears the stale gradients first -- one memset per arena and backward pass, only when needed."""
+    from .. import autograd as _ag
+    ep = _ag._bw_epoch[0]
+    for sk in sinks:
+        ar = getattr(sk, "_mxb_arena", None) if sk is not None else None
+        if ar is None or ar.bw_epoch == ep:
+            continue
+        if ar.dirty and ar.write_semantics:
+            ar.grads.zero_()
+        ar.bw_epoch = ep
+        ar.dirty = True
+
+
 def _sink_ok(sink, shape):
     return sink is not None and sink.dtype is torch.float32 and tuple(sink.shape) == tuple(shape) and sink.is_contiguous()
 
@@ -171,6 +188,7 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, gskip=None):
         x2, w, y = ctx.saved_tensors
+        sink_touch(ctx.sink_w, ctx.sink_b)
         g2 = gy.reshape(-1, gy.shape[-1])
         if ctx.relu:
             g2 = g2 * (y > 0)
@@ -328,12 +346,14 @@ class _ConvNhwcFn(torch.autograd.Function):
         ctx.cfg = (stride, pad)
         sk = _krsc(sink_w) if (sink_w is not None and sink_w.dtype is torch.float32 and sink_w.shape == w.shape) else None
         ctx.sink = sk
+        ctx.sink_owner = sink_w if sk is not None else None
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         stride, pad = ctx.cfg
+        sink_touch(ctx.sink_owner)
         wk = _krsc(w)
         if not dy.is_contiguous():
             dy = dy.contiguous()
@@ -388,6 +408,7 @@ class _StemConvFn(torch.autograd.Function):
     def backward(ctx, dy):
         (a,) = ctx.saved_tensors
         wshape, wdtype, kwp, kp, sink_w = ctx.meta
+        sink_touch(sink_w)
         o, c, kh, kw = wshape
         dy2 = dy.reshape(-1, o)
         if not dy2.is_contiguous():
@@ -510,6 +531,7 @@ class _BnActFn(torch.autograd.Function):
         lib = N.cuda()
         x, mask, stats, g32 = ctx.saved_tensors
         relu, has_res, fix_gamma, gdt, bdt = ctx.cfg
+        sink_touch(ctx.sink_g, ctx.sink_b)
         M, C = x.shape
         if not dy.is_contiguous():
             dy = dy.contiguous()

@@ -61,6 +61,8 @@ class _LayerNormFn(torch.autograd.Function):
         dy2 = dy.contiguous().view(-1, C)
         dx = torch.empty_like(x2)
         sink_g, sink_b = ctx.sinks
+        from .functional import sink_touch
+        sink_touch(sink_g, sink_b)
         use_sink = sink_g is not None and sink_b is not None
         if use_sink:
             dg, db = sink_g, sink_b
@@ -111,6 +113,8 @@ class _BiasActFn(torch.autograd.Function):
     def backward(ctx, dy):
         x2, b32 = ctx.saved_tensors
         shape, act, slope, bdt, sink_b = ctx.meta
+        from .functional import sink_touch
+        sink_touch(sink_b)
         C = x2.shape[-1]
         dy2 = dy.contiguous().view(-1, C)
         dx = torch.empty_like(x2)

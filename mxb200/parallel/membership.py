@@ -103,7 +103,7 @@ class ElasticDeviceTrainer(object):
         pg = self.eg.peer_group(self.device)
         self.tr = DeviceTrainer(named, self.device, self.eg.rank, self.eg.world, group=pg, **self.kw)
         if state is not None:
-            self.tr.import_state(state)
+            self.tr.import_state(state, keep_full=True)
         self.tr.sync_from_rank0(self.eg.barrier)
         self.tr.broadcast_from_rank0(self.aux, self.eg.barrier)
 
@@ -128,8 +128,7 @@ class ElasticDeviceTrainer(object):
     def epoch_boundary(self, epoch):
         """Call at the start of every epoch except a newcomer's first.  Returns (old_world, new_world)."""
         import torch
-        self.tr.gather_state(self.eg.barrier)
-        state = self.tr.export_state()
+        state = self.tr.export_state(self.eg.barrier)     # full (un-sharded) state on every current member
         named = [(n, d["weight"]) for n, d in state["params"].items()]
         torch.cuda.synchronize(self.device)
         self.eg.barrier()

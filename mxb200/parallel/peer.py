@@ -18,7 +18,7 @@ import ctypes
 import torch
 
 from .. import _native as N
-from ..base import MXNetError
+from ..base import MXNetError, getenv
 
 c_void_p, c_int64, c_int = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
 
@@ -61,11 +61,17 @@ class PeerGroup(object):
         self.exchange = exchange          # callable(list_of_bytes_local) -> list over ranks (process mode)
         self.lib = N.cuda()
         self._allocs = []                 # (local _RawBuffer, [peer ptrs], [opened handles])
+        self._segments = []               # VMM segments (multicast-capable allocations)
+        self._mc_ok = None
+        self._job = None
+        self._mc_tag = 0
         self.seq = 0
         self.err_host = c_void_p()
         self.err_dev = c_void_p()
         N.check(self.lib, self.lib.MXBHostAllocMapped(c_int64(64), ctypes.byref(self.err_host), ctypes.byref(self.err_dev)))
         self.flags_local, self.flag_ptrs = self.alloc(FLAG_BYTES)
+        # device-resident barrier sequence {seq, finished CTAs}: starts at 1 on every rank, advanced by the kernels
+        self.seq_dev = torch.tensor([1, 0], dtype=torch.int32, device=self.device)
 
     # -- allocation -------------------------------------------------------------------------------
     def _malloc(self, nbytes, device):
@@ -100,6 +106,45 @@ class PeerGroup(object):
         self._allocs.append((local, ptrs, opened))
         return local, ptrs
 
+    # -- multicast-capable allocation (cuMem VMM, csrc/cuda/vmm.cu) --------------------------------------
+    def multicast_ok(self):
+        """True when every GPU of the group can bind memory to a multicast object (NVLS: in-switch reduction)."""
+        if self.world == 1 or not getenv("MXB200_NVLS", True) or not hasattr(self.lib, "MXBVmmCreate"):
+            return False
+        if self._mc_ok is None:
+            v = c_int(0)
+            ok = self.lib.MXBVmmMulticastSupported(c_int(self.device.index or 0), ctypes.byref(v)) == 0 and v.value == 1
+            if self.exchange is not None:
+                ok = all(self.exchange(b"1" if ok else b"0")[r] == b"1" for r in range(self.world))
+            self._mc_ok = bool(ok)
+        return self._mc_ok
+
+    def alloc_multicast(self, nbytes):
+        """Symmetric allocation that is ALSO bound to a multicast object: returns (local buffer, [unicast ptr per rank],
+        multicast ptr).  Physical memory comes from cuMemCreate; handles travel as file descriptors over unix sockets."""
+        if self.mode != "process":
+            raise MXNetError("alloc_multicast: process-mode groups only (local groups use alloc_multicast_local)")
+        lib = self.lib
+        dev = self.device.index or 0
+        if self._job is None:
+            import os as _os
+            self._job = self.exchange(_os.urandom(6).hex().encode())[0].decode()
+        self._mc_tag += 1
+        seg, padded, lptr = c_void_p(), c_int64(0), c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(lib, lib.MXBVmmCreate(c_int(dev), c_int(self.rank), c_int(self.world), c_int64(int(nbytes)), c_int(1),
+                                          ctypes.byref(seg), ctypes.byref(padded), ctypes.byref(lptr)))
+            N.check(lib, lib.MXBVmmExchange(seg, self._job.encode(), c_int(self._mc_tag), c_int(1)))
+            self.exchange(b"added")                      # every device has been added to the multicast object
+            N.check(lib, lib.MXBVmmBindMulticast(seg))
+            self.exchange(b"bound")
+            ptrs = (c_void_p * self.world)()
+            mc = c_void_p()
+            N.check(lib, lib.MXBVmmPointers(seg, ptrs, ctypes.byref(mc)))
+        local = _RawBuffer(lptr.value, padded.value, self.device, owner=False)
+        self._segments.append(seg)
+        return local, [int(ptrs[r]) for r in range(self.world)], mc.value
+
     def check_error(self):
         v = ctypes.cast(self.err_host, ctypes.POINTER(ctypes.c_int))[0]
         if v != 0:
@@ -116,6 +161,9 @@ class PeerGroup(object):
             if local.owner:
                 self.lib.MXBDeviceFree(c_void_p(local.ptr))
         self._allocs = []
+        for seg in self._segments:
+            self.lib.MXBVmmFree(seg)
+        self._segments = []
 
 
 def make_local_groups(devices, loopback=False):

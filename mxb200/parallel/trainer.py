@@ -39,13 +39,21 @@ class DeviceTrainer(object):
             # gradients are always accumulated in fp32 (better numerics than bf16 accumulation, and it lets the
             # wgrad GEMM / BN backward kernels reduce straight into the arena); weights keep their own dtype
             gdtype = grad_dtype or (torch.float32 if dtype in (torch.bfloat16, torch.float16) else dtype)
-            bufs = {"weights": group.alloc(fused.SymmetricArena.bytes_needed(tensors, dtype)),
-                    "grads": group.alloc(fused.SymmetricArena.bytes_needed(tensors, gdtype))}
+            wbytes = fused.SymmetricArena.bytes_needed(tensors, dtype)
+            gbytes = fused.SymmetricArena.bytes_needed(tensors, gdtype)
+            if getattr(group, "multicast_ok", None) is not None and group.multicast_ok():
+                # NVLS: arenas bound to a multicast object -> multimem.ld_reduce / multimem.st in the fused kernel
+                wl, wp, wmc = group.alloc_multicast(wbytes)
+                gl, gp, gmc = group.alloc_multicast(gbytes)
+                bufs = {"weights": (wl, wp), "grads": (gl, gp), "weights_mc": wmc, "grads_mc": gmc}
+            else:
+                bufs = {"weights": group.alloc(wbytes), "grads": group.alloc(gbytes)}
             ar = fused.SymmetricArena(group, names, tensors, bufs, dtype, gdtype)
             ar.lr_mult.copy_(torch.tensor([lr_mult.get(n, 1.0) for n in names], dtype=torch.float32))
             ar.wd_mult.copy_(torch.tensor([wd_mult.get(n, 1.0) for n in names], dtype=torch.float32))
             self.arenas.append(ar)
             for n, v, g in zip(names, ar.views, ar.grad_views):
+                g._mxb_arena = ar                   # ops.functional.sink_touch: 'write' gradient semantics per backward pass
                 v.requires_grad_(True)
                 self.param_views[n] = v
                 self.grad_sinks[n] = g
@@ -56,11 +64,16 @@ class DeviceTrainer(object):
                     # everything else (library convolutions) the freshly produced gradient is folded in here
                     def _move(p, sink=g):
                         if p.grad is not None:
+                            from ..ops.functional import sink_touch
+                            sink_touch(sink)
                             sink.add_(p.grad)
                             p.grad = None
                     self._hooks.append(v.register_post_accumulate_grad_hook(_move))
         self.num_update = 0
         self.hyper_host = self.hyper_dev = None
+        self._aux = {}
+        from ..base import getenv as _ge
+        self.fused_lamb = bool(_ge("MXB200_FUSED_LAMB", True))
 
     def params(self):
         """name -> leaf tensor view into the arena (use these in the model)."""
@@ -103,9 +116,11 @@ class DeviceTrainer(object):
                 bc1 = 1.0 - beta1 ** t if bias_correction else 1.0
                 bc2 = 1.0 - beta2 ** t if bias_correction else 1.0
             if phase == "host":
-                seq0 = self.group.next_seq()
-                if optimizer == "lamb":
-                    self.group.next_seq()                  # the second launch of the step uses seq0 + 1
+                seq0 = 0
+                if getattr(self.group, "seq_dev", None) is None:
+                    seq0 = self.group.next_seq()
+                    if optimizer == "lamb" and not (hasattr(self.group, "alloc") and self.fused_lamb):
+                        self.group.next_seq()              # the second launch of the step uses seq0 + 1
                 self.hyper_host[idx] = torch.from_numpy(fused.pack_hyper(lr_eff, wd, momentum, rescale, clip, seq0, bc1, bc2))
                 continue
             hy = self.hyper_dev[idx] if phase == "device" else None
@@ -117,6 +132,13 @@ class DeviceTrainer(object):
                 fused.fused_step(ar, fused.MODE_ADAM, lr=lr_eff, wd=wd, rescale=rescale, clip=clip, beta1=beta1,
                                  beta2=beta2, eps=eps, multi_precision=multi_precision, zero_grad=zero_grad,
                                  blocks=blocks, hyper=hy)
+            elif hasattr(self.group, "alloc") and self.fused_lamb:
+                # ONE launch: reduce + moments + direction + per-tensor norms, in-kernel cross-rank norm reduction over
+                # peer memory, trust ratio + update + weight fan-out (no NCCL call, no second kernel)
+                fused.fused_step(ar, fused.MODE_LAMB, lr=lr_eff, wd=wd, rescale=rescale, clip=clip, beta1=beta1,
+                                 beta2=beta2, eps=eps, bc1=bc1, bc2=bc2, multi_precision=multi_precision,
+                                 zero_grad=zero_grad, blocks=blocks, hyper=hy, lamb_lower=lamb_bounds[0],
+                                 lamb_upper=lamb_bounds[1])
             else:
                 ar.get_state("rbuf")
                 fused.fused_step(ar, fused.MODE_LAMB1, lr=lr_eff, wd=wd, rescale=rescale, clip=clip, beta1=beta1,
@@ -125,7 +147,7 @@ class DeviceTrainer(object):
                 self._allreduce_norms(ar)
                 fused.fused_step(ar, fused.MODE_LAMB2, lr=lr_eff, multi_precision=multi_precision, zero_grad=False,
                                  lamb_lower=lamb_bounds[0], lamb_upper=lamb_bounds[1], blocks=blocks, hyper=hy,
-                                 seq=1 if hy is not None else None)
+                                 seq=1 if (hy is not None and getattr(self.group, "seq_dev", None) is None) else None)
                 ar.state["norms"].zero_()
         if phase == "host":
             self.hyper_dev.copy_(self.hyper_host)          # pageable -> device: staged by the runtime, stream ordered
@@ -137,87 +159,65 @@ class DeviceTrainer(object):
         # tiny message (2 floats per tensor); per-tensor trust ratios need the global norms
         dist.all_reduce(ar.state["norms"])
 
-    # ------------------------------------------------------------------ state re-sharding (elastic membership)
+    # ------------------------------------------------------------------ state re-sharding (elastic membership, checkpoints)
     _STATE_NAMES = ("w32", "mom", "var")
 
-    def _slice(self, ar, rank, world):
-        """Element range of the arena owned by ``rank`` in the two-shot kernel (csrc/cuda/allreduce.cu: per =
-        ceil(n_chunks / world) chunks of 1024 elements); one-shot arenas are replicated."""
-        from . import fused as F_
-        gbytes = ar.n * ar.grads.element_size()
-        if world == 1 or gbytes <= F_.ONE_SHOT_BYTES:
-            return 0, ar.n
-        n_chunks = ar.n // 1024
-        per = (n_chunks + world - 1) // world
-        lo = min(n_chunks, per * rank)
-        return lo * 1024, min(n_chunks, lo + per) * 1024
-
     def gather_state(self, barrier):
-        """Make every rank hold the FULL optimizer state (fp32 master weights, momentum, second moment), which the
-        fused kernel keeps sharded ZeRO-1 style.  Staging area = the peer-mapped fp32 gradient arena (must be idle:
-        call between steps); ``barrier`` is a host-level barrier over the current ranks.  Needed before a
-        membership change: ranks that leave take their shard with them."""
-        from . import peer as P_
-        if self.world == 1:
-            return
-        for ar in self.arenas:
-            if ar.gdtype is not torch.float32:
-                continue
-            lo, hi = self._slice(ar, self.rank, self.world)
-            if (lo, hi) == (0, ar.n):
-                continue                       # replicated (one-shot) arena: nothing is sharded
-            for name in self._STATE_NAMES:
-                st = ar.state.get(name)
-                if st is None:
-                    continue
-                ar.grads[lo:hi].copy_(st[lo:hi])
-                torch.cuda.synchronize(self.device)
-                barrier()
-                for r in range(self.world):
-                    if r == self.rank:
-                        continue
-                    rlo, rhi = self._slice(ar, r, self.world)
-                    if rhi <= rlo:
-                        continue
-                    src = P_._RawBuffer(ar.g_ptrs[r], ar.n * 4, self.device, owner=False).tensor(torch.float32, ar.n)
-                    st[rlo:rhi].copy_(src[rlo:rhi])
-                torch.cuda.synchronize(self.device)
-                barrier()
-            ar.grads.zero_()
-        torch.cuda.synchronize(self.device)
+        """Kept for API compatibility: the optimizer state is sharded ZeRO-1 style (each rank allocates and updates only
+        its slice); ``export_state`` assembles the full tensors itself, so there is nothing to do ahead of it."""
+        return None
 
-    def export_state(self):
-        """name -> dict(weight=tensor, <state>=fp32 tensor ...) as private copies (call after gather_state)."""
+    def export_state(self, barrier=None):
+        """{num_update, params: name -> dict(weight=tensor, <state>=fp32 tensor ...)} as private, arena-layout-independent
+        copies.  Collective when world > 1 (every rank's slice is fetched over peer memory); ``barrier`` is a host-level
+        barrier over the current ranks (default: torch.distributed.barrier)."""
+        if barrier is None and self.world > 1:
+            import torch.distributed as dist
+            barrier = dist.barrier
         out = {"num_update": self.num_update, "params": {}}
         for ar in self.arenas:
+            fulls = {}
+            for sname in self._STATE_NAMES:
+                if sname in ar.state:
+                    fulls[sname] = ar.full_state(sname, barrier)
             for i, n in enumerate(ar.layout.names):
                 d = {"weight": ar.views[i].detach().clone()}
-                for sname in self._STATE_NAMES:
-                    st = ar.state.get(sname)
-                    if st is not None:
-                        d[sname] = ar.layout.view(st, i, False).detach().clone()
+                for sname, full in fulls.items():
+                    d[sname] = ar.layout.view(full, i, False).detach().clone()
                 out["params"][n] = d
+        torch.cuda.synchronize(self.device)
         return out
 
-    def import_state(self, state):
-        """Inverse of export_state on a (new) trainer over the same parameter set."""
+    def import_state(self, state, keep_full=False):
+        """Inverse of export_state on a (new) trainer over the same parameter set (any world size / sharding).
+        ``keep_full``: keep the assembled full-size state tensors until ``sync_from_rank0`` has served the other ranks."""
         self.num_update = int(state.get("num_update", 0))
         with torch.no_grad():
             for ar in self.arenas:
+                present = set()
+                for n in ar.layout.names:
+                    present.update(k for k in state["params"].get(n, {}) if k in self._STATE_NAMES)
+                fulls = {k: torch.zeros(ar.n, dtype=torch.float32, device=self.device) for k in present}
+                if "w32" in fulls:
+                    fulls["w32"].copy_(ar.weights)
                 for i, n in enumerate(ar.layout.names):
                     d = state["params"].get(n)
                     if d is None:
                         continue
-                    ar.views[i].copy_(d["weight"].reshape(ar.views[i].shape))
-                    for sname in self._STATE_NAMES:
+                    ar.views[i].copy_(d["weight"].reshape(ar.views[i].shape).to(self.device))
+                    for sname in present:
                         if sname in d:
-                            full = ar.get_state(sname, init_from_weights=(sname == "w32"))
-                            ar.layout.view(full, i, False).copy_(d[sname].reshape(-1).view_as(ar.layout.view(full, i, False)))
+                            tgt = ar.layout.view(fulls[sname], i, False)
+                            tgt.copy_(d[sname].reshape(-1).to(self.device).view_as(tgt))
+                for sname, full in fulls.items():
+                    ar.load_full_state(sname, full, init_from_weights=(sname == "w32"))
+                ar._fulls = fulls if keep_full else None
 
     def sync_from_rank0(self, barrier):
-        """Every rank adopts rank 0's weights and optimizer state (how a newcomer obtains live state; the reference's
-        newcomers pull from the parameter servers, python/mxnet/module/module.py + kvstore_dist.h).  Uses peer reads of
-        rank 0's arenas: weights directly, state staged through its fp32 gradient arena."""
+        """Every rank adopts rank 0's weights and its own SLICE of rank 0's full optimizer state (how a newcomer obtains
+        live state; the reference's newcomers pull from the parameter servers, python/mxnet/module/module.py +
+        kvstore_dist.h).  Rank 0 must hold the full state (``import_state(..., keep_full=True)``, or world was 1 / the arena
+        is one-shot); it stages one state tensor at a time in its peer-mapped fp32 gradient arena."""
         from . import peer as P_
         if self.world == 1:
             return
@@ -228,58 +228,87 @@ class DeviceTrainer(object):
             if self.rank != 0:
                 src = P_._RawBuffer(ar.w_ptrs[0], ar.n * esz, self.device, owner=False).tensor(ar.wdtype, ar.n)
                 ar.weights.copy_(src)
-            # which state tensors exist is decided by rank 0 (the optimizer in use); all ranks walk the same list
-            for name in self._STATE_NAMES:
-                has = torch.tensor([1 if name in ar.state else 0], device=self.device, dtype=torch.float32)
-                if ar.gdtype is not torch.float32:
+            if ar.gdtype is not torch.float32:
+                continue
+            fulls = getattr(ar, "_fulls", None) or {}
+            g0 = P_._RawBuffer(ar.g_ptrs[0], ar.n * 4, self.device, owner=False).tensor(torch.float32, ar.n)
+            lo, hi = ar.slice_range()
+            # which state tensors exist is decided by rank 0 (the optimizer in use): a 3-float mask in its gradient arena
+            if self.rank == 0:
+                mask = [1.0 if (n in fulls or (n in ar.state and ar.slice_range() == (0, ar.n))) else 0.0
+                        for n in self._STATE_NAMES]
+                ar.grads[:3].copy_(torch.tensor(mask, device=self.device))
+            torch.cuda.synchronize(self.device)
+            barrier()
+            present = [bool(v > 0.5) for v in g0[:3].tolist()]
+            torch.cuda.synchronize(self.device)
+            barrier()
+            for name, has in zip(self._STATE_NAMES, present):
+                if not has:
                     continue
                 if self.rank == 0:
-                    ar.grads[:1].copy_(has)
+                    ar.grads.copy_(fulls[name] if name in fulls else ar.state[name][:ar.n])
                 torch.cuda.synchronize(self.device)
                 barrier()
-                g0 = P_._RawBuffer(ar.g_ptrs[0], ar.n * 4, self.device, owner=False).tensor(torch.float32, ar.n)
-                present = bool(g0[:1].item() > 0.5)
-                torch.cuda.synchronize(self.device)
-                barrier()
-                if not present:
-                    continue
-                if self.rank == 0:
-                    ar.grads.copy_(ar.state[name])
-                torch.cuda.synchronize(self.device)
-                barrier()
-                if self.rank != 0:
-                    ar.get_state(name).copy_(g0)
+                if self.rank != 0 and hi > lo:
+                    ar.get_state(name)[:hi - lo].copy_(g0[lo:hi])
                 torch.cuda.synchronize(self.device)
                 barrier()
             ar.grads.zero_()
+            ar._fulls = None
         torch.cuda.synchronize(self.device)
         barrier()
 
-    def broadcast_from_rank0(self, tensors, barrier):
-        """Small fp32/any-dtype tensors (BatchNorm running statistics, counters): every rank adopts rank 0's values.
-        Staged through the first fp32 gradient arena in chunks."""
-        from . import peer as P_
+    # ------------------------------------------------------------------ small-tensor collectives on the fused kernel
+    def _aux_arena(self, numel):
+        """fp32 symmetric arena (gradient side = contributions, weight side = result) for small replicated state such as
+        BatchNorm running statistics.  Collective allocation: every rank must ask for the same size."""
+        n = (int(numel) + 8191) // 8192 * 8192
+        ar = self._aux.get(n)
+        if ar is None:
+            t0 = torch.zeros(n, dtype=torch.float32, device=self.device)
+            bufs = {"weights": self.group.alloc(n * 4), "grads": self.group.alloc(n * 4)}
+            ar = self._aux[n] = fused.SymmetricArena(self.group, ["aux"], [t0], bufs, torch.float32, torch.float32)
+        return ar
+
+    def _allreduce_small(self, tensors, scale, only_rank0=False):
         if self.world == 1 or not tensors:
             return
-        ar = next(a for a in self.arenas if a.gdtype is torch.float32)
-        g0 = P_._RawBuffer(ar.g_ptrs[0], ar.n * 4, self.device, owner=False).tensor(torch.float32, ar.n)
         flat = torch.cat([t.detach().reshape(-1).float() for t in tensors])
-        for off in range(0, flat.numel(), ar.n):
-            m = min(ar.n, flat.numel() - off)
-            if self.rank == 0:
-                ar.grads[:m].copy_(flat[off:off + m])
-            torch.cuda.synchronize(self.device)
-            barrier()
-            if self.rank != 0:
-                flat[off:off + m].copy_(g0[:m])
-            torch.cuda.synchronize(self.device)
-            barrier()
-        ar.grads.zero_()
+        ar = self._aux_arena(flat.numel())
+        m = flat.numel()
+        if only_rank0 and self.rank != 0:
+            ar.grads[:m].zero_()
+        else:
+            ar.grads[:m].copy_(flat)
+        # ONE launch: cross-GPU sum over peer memory (its own flag barriers order the ranks, no host barrier needed)
+        fused.fused_step(ar, fused.MODE_ALLREDUCE, rescale=scale, zero_grad=True)
+        res = ar.weights[:m]
         o = 0
         with torch.no_grad():
             for t in tensors:
-                t.copy_(flat[o:o + t.numel()].reshape(t.shape).to(t.dtype))
+                t.copy_(res[o:o + t.numel()].reshape(t.shape).to(t.dtype))
                 o += t.numel()
+
+    def average_across_ranks(self, tensors):
+        """In-place mean over the ranks (BatchNorm running statistics at an epoch end; the reference averages aux states
+        over devices in executor_group.py:415-434 and over workers on the servers)."""
+        self._allreduce_small(tensors, 1.0 / self.world)
+
+    def broadcast_from_rank0(self, tensors, barrier=None):
+        """Small tensors (BatchNorm running statistics, counters): every rank adopts rank 0's values -- a plain-sum launch of
+        the fused kernel in which only rank 0 contributes."""
+        self._allreduce_small(tensors, 1.0, only_rank0=True)
+
+    def scale_state(self, name, factor):
+        """Multiply an optimizer state tensor (e.g. the momentum buffer) by ``factor``: the momentum correction of an abrupt
+        learning-rate change at a membership change (Goyal et al. 2017, remark 2)."""
+        if factor == 1.0:
+            return
+        for ar in self.arenas:
+            st = ar.state.get(name)
+            if st is not None:
+                st.mul_(float(factor))
 
     def check(self):
         self.group.check_error()

@@ -79,8 +79,7 @@ for epoch in range(begin, len(plan)):
     torch.cuda.synchronize(dev)
     csum = float(sum(v.detach().float().abs().sum() for v in W.values()))
     mom = sess.tr.arenas[0].state.get("mom")
-    lo_, hi_ = sess.tr._slice(sess.tr.arenas[0], rank, world)
-    mom_norm = float(mom[lo_:hi_].abs().sum()) if mom is not None else 0.0
+    mom_norm = float(mom.abs().sum()) if mom is not None else 0.0      # the state tensor IS the owned slice
     sums = [struct.unpack("<d", b)[0] for b in eg.allgather(struct.pack("<d", csum))]
     log["epochs"].append({"epoch": epoch, "rank": rank, "world": world, "loss_first": losses[0], "loss_last": losses[-1],
                           "weights_identical": max(sums) - min(sums) <= 1e-6 * abs(sums[0]), "checksum": csum,
