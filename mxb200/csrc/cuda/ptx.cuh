@@ -232,8 +232,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //  [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base_offset | [61,64) layout
 constexpr uint64_t kLayoutSW128 = 2;
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// ``base_offset``: (start address >> 7) & 7 when the operand does not start on a 1024-byte boundary of the 128B-swizzle
+// pattern (e.g. a K-major tile entered a few 128-byte rows below its first row: the row-shifted convolution taps).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= (uint64_t)(base_offset & 7u) << 49;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;

@@ -184,6 +184,11 @@ class Trainer(object):
             dt.sync_from_rank0(kv._barrier)              # weights + optimizer state of rank 0 (a newcomer's live state)
             dt.broadcast_from_rank0([p._data[0]._t for p in self._params if p.grad_req == "null" and p._data is not None],
                                     kv._barrier)
+            # the update counter drives lr schedules and Adam / LAMB bias corrections: newcomers continue at the job's count
+            cnt = torch.tensor([float(self._optimizer.num_update), float(dt.num_update)], device=dt.device)
+            dt.broadcast_from_rank0([cnt])
+            self._optimizer.num_update = int(round(cnt[0].item()))
+            dt.num_update = int(round(cnt[1].item()))
             kv._register_trainer(self)
         elif world > 1:
             # non-trainable state (BN running stats): start from rank 0's values (kv.init semantics)
@@ -232,7 +237,14 @@ class Trainer(object):
         lr_before = sched(o.num_update) if o.num_update else sched.base_lr * sched.cur_factor
         sched.on_membership_change(new_batch, num_update=o.num_update)
         corr = sched.momentum_correction() if sched.smooth_steps == 0 else 1.0
-        if self._fused is not None and corr != 1.0 and getattr(o, "momentum", 0.0):
+        est = getattr(self, "_elastic_state", None)
+        if est is not None and corr != 1.0 and getattr(o, "momentum", 0.0):
+            # between detach and attach of an elastic re-init: correct the exported (full) state, so that every rank --
+            # newcomers included, replicated one-shot arenas included -- continues from the SAME corrected momentum
+            for d in est["params"].values():
+                if "mom" in d:
+                    d["mom"].mul_(corr)
+        elif self._fused is not None and corr != 1.0 and getattr(o, "momentum", 0.0):
             self._fused.scale_state("mom", corr)
         elif corr != 1.0:
             for upd in self._updaters:
@@ -428,9 +440,13 @@ class Trainer(object):
                 dt = self._fused
                 dev = dt.device
                 cur = {n: {"weight": v.detach()} for n, v in dt.params().items()}
+                saved = blob["params"]
+                if not any(n in cur for n in saved) and len(saved) == len(cur):
+                    # other name prefixes (a re-created net): match by position, like the reference's index-keyed states
+                    saved = {n: d for n, d in zip(cur.keys(), saved.values())}
                 state = {"num_update": int(blob.get("trainer_num_update", blob["num_update"])),
                          "params": {n: dict(cur[n], **{k: v.to(dev) for k, v in d.items()})
-                                    for n, d in blob["params"].items() if n in cur}}
+                                    for n, d in saved.items() if n in cur}}
                 dt.import_state(state)
                 self._optimizer.num_update = int(blob["num_update"])
                 return

@@ -160,6 +160,8 @@ class KVStoreLocal(KVStore):
         self._device_mode = ("device" in kv_type) or ("nccl" in kv_type)
         self._residuals = {}
         self._fused = {}            # device set -> FusedLocalComm (bucketed push / pull on the fused kernel)
+        self._plans = {}            # (key, devices) -> cached routing decision of the hot per-key calls
+        self._pull_q = None         # deferred pulls of fused keys: per device ([dst], [src]) drained by one foreach copy
 
     # reduce / broadcast (Comm) ----------------------------------------------------------------------
     def _reduce(self, ikey, vals):
@@ -283,7 +285,38 @@ class KVStoreLocal(KVStore):
                         else:
                             self._store[ik] = NDArray(res[r].clone())
 
+    def _fast_plan(self, key, vlist):
+        """Cached routing decision for the hot per-key call ``push(key, [array per GPU])`` / ``pull``: (communicator,
+        permutation into its device order), or None.  Keyed by (key, device tuple); the per-call cost of the fused path is
+        then a dict lookup and two list comprehensions (the python loop over ~200 keys IS the cost of a ResNet step's
+        push / pull, tools/bandwidth/measure.py)."""
+        devs = tuple(v._t.device.index if (type(v) is NDArray and v._t.is_cuda) else -1 for v in vlist)
+        pk = (key, devs)
+        plan = self._plans.get(pk, False)
+        if plan is not False:
+            return plan
+        plan = None
+        ik = self._int_key(key)
+        if ik in self._store and ik <= MAX_ALLOWED_KEY_FOR_UPDATE and type(self._store[ik]) is NDArray and -1 not in devs and \
+                tuple(self._store[ik].shape) == tuple(vlist[0].shape) and self._store[ik]._t.dtype == vlist[0]._t.dtype:
+            fc = self._fused_comm(vlist)
+            if fc is not None:
+                order = sorted(range(len(vlist)), key=lambda i: fc.device_index(vlist[i]._t.device))
+                plan = (fc, order, ik, tuple(vlist[0].shape), vlist[0]._t.dtype)
+        self._plans[pk] = plan
+        return plan
+
     def push(self, key, value, priority=0):
+        if self._device_mode and type(value) is list and len(value) > 1 and isinstance(key, (int, str)):
+            plan = self._fast_plan(key, value)
+            if plan is not None:
+                fc, order, ik, shape, dt = plan
+                ts = [value[i]._t for i in order]
+                if all(t.dtype is dt and tuple(t.shape) == shape and t.is_contiguous() for t in ts):
+                    if not fc.push(ik, ts):
+                        self._flush_fused()
+                        fc.push(ik, ts)
+                    return
         keys, vals = _key_value_lists(key, value)
         for ik, vlist in self._group(keys, vals):
             if ik not in self._store:
@@ -337,6 +370,24 @@ class KVStoreLocal(KVStore):
 
     def pull(self, key, out=None, priority=0, ignore_sparse=True):
         assert out is not None
+        if self._fused and type(out) is list and isinstance(key, (int, str)):
+            # hot per-key call: every GPU already holds the reduced value in its arena
+            if any(f and f.pending for f in self._fused.values()):
+                self._flush_fused()
+            ik = key if isinstance(key, int) else self._str2int.get(key)
+            for fc in self._fused.values():
+                res = fc.results.get(ik) if fc else None
+                if res is not None:
+                    try:
+                        pairs = [(o._t, res[fc.device_index(o._t.device)]) for o in out]
+                    except (ValueError, AttributeError):
+                        break
+                    if all(d.dtype is s_.dtype and d.shape == s_.shape for d, s_ in pairs):
+                        with torch.no_grad():
+                            for d, s_ in pairs:
+                                d.copy_(s_, non_blocking=True)
+                        return
+                    break
         keys, outs = _key_value_lists(key, out)
         if self._fused:
             self._flush_fused()
@@ -530,8 +581,9 @@ class KVStoreElasticDevice(KVStoreLocal):
         t2 = time.time()
         eng.start()
         for t in trainers:
+            t._on_membership_change(old, new)        # dynamic-mini-batch learning-rate rule + momentum correction (on the
+            #                                          exported state: newcomers then copy the corrected values)
             t._elastic_attach()                      # new peer map, new arenas, state re-sharded, newcomers synced
-            t._on_membership_change(old, new)        # dynamic-mini-batch learning-rate rule + momentum correction
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         t3 = time.time()

@@ -21,6 +21,7 @@ import torch
 import torch.nn.functional as F
 
 from ..ops import functional as K
+from ..ops.attention import self_attention, advance_rng_step
 from ..ops.layernorm import bias_act, layer_norm
 
 
@@ -117,9 +118,9 @@ def bert_encoder(spec, P, input_ids, token_types=None, attention_mask=None, trai
         x = x + P["type_embed"][0]
     x = _ln(x, P, G, "embed_ln", spec.eps)
     x = _dropout(x, spec.dropout, training)
-    mask = None
-    if attention_mask is not None:
-        mask = attention_mask[:, None, None, :].to(torch.bool)
+    kmask = attention_mask.to(torch.bool) if attention_mask is not None else None
+    if training and spec.dropout > 0 and x.is_cuda:
+        advance_rng_step(x.device)        # device-side Philox stream offset: fresh masks on every (replayed) step
     for l in range(spec.layers):
         p = "layer%d_" % l
         # Q, K, V as three GEMMs over row-slices of the single [3H, H] parameter: each lands directly in the
@@ -129,12 +130,13 @@ def bert_encoder(spec, P, input_ids, token_types=None, attention_mask=None, trai
         gw, gb = _s(G, p + "qkv_weight"), _s(G, p + "qkv_bias")
         qkv = []
         for i in range(3):
-            t = K.linear(x, Wqkv[i * H:(i + 1) * H], bqkv[i * H:(i + 1) * H],
-                         sink_w=_sub(gw, i * H, (i + 1) * H), sink_b=_sub(gb, i * H, (i + 1) * H))
-            qkv.append(t.view(B, S, nh, H // nh).transpose(1, 2))          # [B, nh, S, dh] view, no copy
+            qkv.append(K.linear(x, Wqkv[i * H:(i + 1) * H], bqkv[i * H:(i + 1) * H],
+                                sink_w=_sub(gw, i * H, (i + 1) * H), sink_b=_sub(gb, i * H, (i + 1) * H)))   # [B, S, H]
         q, k, v = qkv
-        a = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=spec.dropout if training else 0.0)
-        a = a.transpose(1, 2).reshape(B, S, H)
+        # scores, key-padding mask, softmax, attention dropout and the value product in ONE tcgen05 kernel per pass
+        # (ops/attention.py -> csrc/cuda/attention.cu); head h lives in columns [64h, 64h+64) of the projections, so no
+        # head transposes exist.  Sequences > 128 tokens / other head sizes take the eager composition in there.
+        a = self_attention(q, k, v, nh, key_mask=kmask, p_drop=spec.dropout, training=training, call_id=l + 1)
         a = _dropout(_linear(a, P, G, p + "proj"), spec.dropout, training)
         x = _ln(a, P, G, p + "ln1", spec.eps, residual=x)
         h = K.linear(x, P[p + "ffn1_weight"], None, sink_w=_s(G, p + "ffn1_weight"))

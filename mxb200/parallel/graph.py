@@ -50,6 +50,7 @@ class TrainStep(object):
         self.capture = capture if capture is not None else bool(getenv("MXB200_CUDA_GRAPH", True))
         self.warmup = max(1, int(warmup))
         self._cache = {}
+        self._fused_id = None
         self._stream = None            # side stream: warm-up AND capture run on it (never the legacy default stream)
         self.replays = 0
         self.eager_calls = 0
@@ -130,10 +131,18 @@ class TrainStep(object):
         return c.loss
 
     # ------------------------------------------------------------------ call
+    def reset(self):
+        """Drop every captured graph (the parameter / gradient arenas moved: membership change, re-fused trainer)."""
+        self._cache = {}
+        self._fused_id = None
+
     def __call__(self, x, y, batch_size=None):
         bs = batch_size or self.batch_size or x.shape[0]
         if not self._can_capture(x):
             return self._eager(x, y, bs)
+        if self._fused_id is not None and self._fused_id != id(self.trainer._fused):
+            self.reset()                     # graphs captured over the old arenas must never be replayed
+        self._fused_id = id(self.trainer._fused)
         tx, ty = x.as_torch(), y.as_torch()
         key = (tuple(tx.shape), tx.dtype, tuple(ty.shape), ty.dtype, bs)
         c = self._cache.get(key)

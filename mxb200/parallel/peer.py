@@ -71,7 +71,7 @@ class PeerGroup(object):
         N.check(self.lib, self.lib.MXBHostAllocMapped(c_int64(64), ctypes.byref(self.err_host), ctypes.byref(self.err_dev)))
         self.flags_local, self.flag_ptrs = self.alloc(FLAG_BYTES)
         # device-resident barrier sequence {seq, finished CTAs}: starts at 1 on every rank, advanced by the kernels
-        self.seq_dev = torch.tensor([1, 0], dtype=torch.int32, device=self.device)
+        self.seq_dev = torch.tensor([1, 0], dtype=torch.int32, device=self.device) if getenv("MXB200_SEQ_DEV", True) else None
 
     # -- allocation -------------------------------------------------------------------------------
     def _malloc(self, nbytes, device):

@@ -103,12 +103,11 @@ def scenario_checkpoint(rank, world, dev):
         torch.manual_seed(seed)
         mx.random.seed(seed)
         ctx = mx.gpu(dev.index)
-        net = gluon.nn.HybridSequential()
+        net = gluon.nn.HybridSequential(prefix="ckpt_")
         with net.name_scope():
             net.add(gluon.nn.Dense(256, activation="relu", in_units=512), gluon.nn.Dense(512, in_units=256),
                     gluon.nn.Dense(16, in_units=512))
         net.initialize(mx.init.Xavier(), ctx=ctx)
-        net.cast("bfloat16") if False else None
         tr = gluon.Trainer(net.collect_params(), "nag", {"learning_rate": 0.05, "momentum": 0.9, "wd": 1e-4},
                            kvstore=mx.kv.create("device"))
         return ctx, net, tr
@@ -186,7 +185,8 @@ def scenario_graph(rank, world, dev):
             l = step(mx.nd.from_torch(x, ctx), mx.nd.from_torch(y, ctx))
             losses.append(float(l.as_torch().float().mean().item()))
         tr.check_health()
-        csum = sum(p.data().as_torch().float().abs().sum().item() for p in net.collect_params().values())
+        # trainable parameters only: BatchNorm running statistics are per-rank state
+        csum = sum(p.data().as_torch().float().abs().sum().item() for p in net.collect_params().values() if p.grad_req != "null")
         t = torch.tensor([csum], device=dev, dtype=torch.float64)
         lo, hi = t.clone(), t.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)

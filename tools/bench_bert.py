@@ -83,7 +83,7 @@ def main():
                           "tokens_per_sec": seqs * S, "n_gpus": world, "ms_per_step": ms, "steps": args.steps,
                           "warmup": args.warmup, "dtype": "bf16", "optimizer": "LAMB (fused arena kernels)",
                           "config": {"batch_per_gpu": B, "seq_len": S, "masked_per_seq": Mp, "params": nparams,
-                                     "attention": "torch SDPA (library flash attention)"},
+                                     "attention": "fused tcgen05 kernel (csrc/cuda/attention.cu)", "lamb": "one fused launch per arena (in-kernel cross-rank norm reduction)"},
                           "model_tflops_per_gpu": flops / ms / 1e9, "gpu_launches": ops.launch_count() - l0,
                           "final_loss": float(loss.detach()), "data": "synthetic token ids, random-init weights"}))
     if world > 1:
