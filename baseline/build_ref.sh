@@ -10,8 +10,10 @@
 #   * make/config.mk is git-ignored upstream -> we write one (the documented knobs only)
 #   * 3rdparty/cub (2018) shadows the CUDA-12 toolkit's own cub/thrust -> the directory is emptied in the COPY
 #   * cblas.h is not in the image -> a 40-line declaration header for the OpenBLAS that ships with opencv-python
-#   * patches under baseline/patches/*.patch (if any) are compile fixes for CUDA 12 / gcc 13, applied to the COPY and
-#     listed in DESIGN.md
+#   * patches under baseline/patches/*.patch are compile fixes for CUDA 12 / gcc 13, applied to the COPY and listed in
+#     DESIGN.md (01: `cuda::Reduce1D` -> `mshadow::cuda::Reduce1D`, ambiguous with libcu++'s global ::cuda namespace)
+#   * `--pre-include cub/cub.cuh` (nvcc) parses the toolkit's cub before any `using namespace mshadow`, `-include unistd.h`
+#     supplies getpid() for the fork's kvstore_local.h
 set -u
 JOBS=${1:-6}
 REPO=$(cd "$(dirname "$0")/.." && pwd)
@@ -29,6 +31,13 @@ if [ ! -d "$WORK/src" ]; then
   done
   mkdir -p "$WORK/3rdparty/cub"     # emptied on purpose: use the toolkit's cub
 fi
+# pieces of the upstream tree that are ABSENT from the reference snapshot (git-ignored / un-fetched submodules): the code
+# that needs them cannot be built and is left out of the copy -- none of it is on the image-classification path
+#   3rdparty/ctc_include (warp-ctc)        -> operator CTCLoss
+#   3rdparty/dmlc-core/src/data/ (parsers) -> LibSVMIter / CSVIter and dmlc-core's data.o
+rm -f "$WORK"/src/operator/nn/ctc_loss.cc "$WORK"/src/operator/nn/ctc_loss.cu "$WORK"/src/operator/contrib/ctc_loss.cc "$WORK"/src/operator/contrib/ctc_loss.cu
+rm -f "$WORK"/src/io/iter_libsvm.cc "$WORK"/src/io/iter_csv.cc
+sed -i 's/ data.o recordio.o/ recordio.o/' "$WORK/3rdparty/dmlc-core/Makefile"
 cd "$WORK" || exit 1
 
 OB=$(ls /opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs/libopenblasp-*.so | head -1)
@@ -87,7 +96,7 @@ DEV = 0
 DEBUG = 0
 USE_SIGNAL_HANDLER = 0
 ADD_LDFLAGS = -L$WORK/compat/lib -Wl,-rpath,$(dirname "$OB") -L/usr/local/cuda/lib64
-ADD_CFLAGS = -I$WORK/compat -Wno-deprecated-declarations -Wno-unused -Wno-class-memaccess -Wno-maybe-uninitialized -fpermissive
+ADD_CFLAGS = -I$WORK/compat -include unistd.h -Wno-deprecated-declarations -Wno-unused -Wno-class-memaccess -Wno-maybe-uninitialized -fpermissive
 USE_CUDA = 1
 USE_CUDA_PATH = /usr/local/cuda
 ENABLE_CUDA_RTC = 0
@@ -130,7 +139,7 @@ if ls "$REPO"/baseline/patches/*.patch >/dev/null 2>&1; then
 fi
 
 echo "--- make -k -j$JOBS lib/libmxnet.so"
-make -k -j"$JOBS" lib/libmxnet.so NVCCFLAGS="-Wno-deprecated-gpu-targets -Xcompiler -fpermissive --expt-relaxed-constexpr -diag-suppress 20012,20014,186,611,997,2810,177" 2>&1 | grep -v "^ALL_DEP is" | tail -n 4000
+make -k -j"$JOBS" lib/libmxnet.so NVCCFLAGS="-Wno-deprecated-gpu-targets --pre-include cub/cub.cuh -Xcompiler -fpermissive --expt-relaxed-constexpr -diag-suppress 20012,20014,186,611,997,2810,177" 2>&1 | grep -v "^ALL_DEP is" | tail -n 4000
 RC=${PIPESTATUS[0]}
 echo "--- make exit $RC"
 if [ -f lib/libmxnet.so ]; then

@@ -3,6 +3,10 @@
 ``mx.cpu(i)`` contexts with different ids are *distinct logical devices* that
 all live in host memory -- the reference's own tests simulate multi-device
 kvstores that way (tests/python/unittest/test_kvstore.py) and so do ours.
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/context.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
 """
 import threading
 

@@ -85,7 +85,12 @@ struct Args {
   // Device-resident barrier sequence number {seq, finished-CTA count}: when non-null the kernel reads seq from here and the
   // last CTA to finish increments it, so replaying a captured launch needs no host-side bookkeeping at all (every rank
   // advances its own copy identically: one increment per launch on the group).
-  uint32_t* seq_dev;          // arena element index of element 0 of w32 / mom / var / rbuf (ZeRO-1: state only for my slice)
+  uint32_t* seq_dev;
+  // Low-latency one-shot (small messages): every rank PUSHES its fp32 gradients as {value, sequence-flag} 8-byte packets into
+  // every peer's receive buffer [2 parities][nranks][n] and then polls its own buffer -- no barrier at all, the flag travels
+  // with the data (the idea of NCCL's LL protocol).  Null: flag-barrier protocol.
+  uint2* ll_recv[kMaxRanks];
+  uint32_t* ll_ctr;           // per-arena launch counter (device): packet flag and buffer parity; advanced with seq_dev
 };
 constexpr int kHyperFloats = 8;
 
@@ -231,7 +236,30 @@ fused_kernel(const Args a) {
     h_bc2 = __ldg(a.hyper + 7);
   }
   if (a.seq_dev != nullptr) h_seq = a.seq + *reinterpret_cast<const volatile uint32_t*>(a.seq_dev);
-  if (nr > 1) {
+  const bool ll = (sizeof(GT) == 4) && a.ll_recv[0] != nullptr && a.ll_ctr != nullptr && a.seq_dev != nullptr && nr > 1 && a.one_shot && a.mode != kLambPhase2 &&
+                  a.mode != kBroadcast && a.mode != kLamb && a.mode != kLambPhase1;
+  const uint32_t ll_cnt = ll ? *reinterpret_cast<const volatile uint32_t*>(a.ll_ctr) : 0u;
+  const uint32_t ll_flag = ll_cnt | 0x80000000u;           // never 0 (buffers start zeroed)
+  const int64_t ll_base = (int64_t)(ll_cnt & 1u) * nr * a.n;   // double buffering: a peer is never 2 launches of this arena behind
+  if (ll) {
+    if constexpr (sizeof(GT) == 4) {
+      // push my gradients to every rank (my own buffer included: the reduction below treats all sources alike)
+      const float* gl = reinterpret_cast<const float*>(a.grads[a.rank]);
+      const int64_t nv2 = a.n / 2;
+      for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < nv2; v += (int64_t)gridDim.x * kThreads) {
+        const float2 g2 = *reinterpret_cast<const float2*>(gl + v * 2);
+        const uint4 pkt = make_uint4(__float_as_uint(g2.x), ll_flag, __float_as_uint(g2.y), ll_flag);
+#pragma unroll
+        for (int k = 0; k < (NR > 0 ? NR : kMaxRanks); ++k) {
+          if (k < nr) {
+            const int p = (a.rank + k) % nr;
+            uint4* dst = reinterpret_cast<uint4*>(a.ll_recv[p] + ll_base + (int64_t)a.rank * a.n) + v;
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(pkt.x), "r"(pkt.y), "r"(pkt.z), "r"(pkt.w) : "memory");
+          }
+        }
+      }
+    }
+  } else if (nr > 1) {
     if (!peer_barrier(a, 4u * h_seq)) return;
   }
   // slice owned by this rank (two-shot) or the whole arena (one-shot)
@@ -283,7 +311,30 @@ fused_kernel(const Args a) {
       }
       float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (!skip && mode != kLambPhase2 && mode != kBroadcast) {
-        if (mc_grads) {
+        if (ll) {
+          // 8 elements = 4 packets pairs per source; spin until every packet carries this launch's flag; sum in RANK order so
+          // that all replicas compute bit-identical results
+          const uint2* mine = a.ll_recv[a.rank] + ll_base;
+          bool ok = true;
+#pragma unroll
+          for (int q = 0; q < (NR > 0 ? NR : kMaxRanks); ++q) {
+            if (q < nr) {
+              const uint4* src = reinterpret_cast<const uint4*>(mine + (int64_t)q * a.n + e);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 pk;
+                uint32_t spins = 0;
+                do {
+                  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "l"(src + j) : "memory");
+                  if (++spins > kSpinLimit) { ok = false; break; }
+                } while (pk.y != ll_flag || pk.w != ll_flag);
+                g[2 * j] += __uint_as_float(pk.x);
+                g[2 * j + 1] += __uint_as_float(pk.z);
+              }
+            }
+          }
+          if (!ok && a.err) atomicExch(a.err, 1 + a.rank);
+        } else if (mc_grads) {
           // the switch sums the N copies: one load per 16 bytes instead of N
           mc_ld_reduce8<GT>(reinterpret_cast<const GT*>(a.grads_mc) + e, g);
         } else {
@@ -411,7 +462,7 @@ fused_kernel(const Args a) {
   } else {
     sweep(a.mode, a.w_norm2, a.r_norm2);
   }
-  if (nr > 1) {
+  if (nr > 1 && !ll) {
     if (!peer_barrier(a, 4u * h_seq + 2u)) return;
   }
   if (a.mode == kLamb) {
@@ -434,6 +485,7 @@ fused_kernel(const Args a) {
       if (atomicAdd(a.seq_dev + 1, 1u) == gridDim.x - 1) {
         a.seq_dev[1] = 0;
         a.seq_dev[0] = a.seq_dev[0] + 1u;
+        if (ll) a.ll_ctr[0] = ll_cnt + 1u;
         __threadfence();
       }
     }

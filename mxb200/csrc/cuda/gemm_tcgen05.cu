@@ -1004,19 +1004,23 @@ bool pick_two_cta(int bn, int64_t M, int N, int K, int sp) {
   return env == 1 || (env != 0 && K >= 256 && tiles2 >= 74);
 }
 
-// Row-shifted taps (CONV == 3) pay off when the GEMM is narrow (N <= 128): the per-tap gathers of the plain implicit GEMM
-// are then bound by L2 -> shared-memory bandwidth (measured: 0.4-0.55x cuDNN at C = 64 / 128, profiles/microbench_conv_*).
+// Row-shifted taps (CONV == 3): the kw taps of a filter row share ONE gathered A tile, which cuts the A-operand L2 -> smem
+// traffic of narrow layers (N <= 128) three-fold.  Measured on B200 (profiles/microbench_conv_r2_call53.json) it is
+// nevertheless SLOWER than the per-tap gather (C=64: 360 vs 280 us, C=128: 190 vs 151 us): with N = 64 / 128 the SS-mode
+// MMA is bound by its own shared-memory operand reads, and an operand entered at a row offset straddles two swizzle
+// atoms per 8-row core matrix.  Kept as an opt-in (MXB200_CONV_SHIFT=1, exercised by tests/test_gpu_kernels.py); the
+// profitable structure for these layers is weight-stationary with the pixels on the N side.
 bool use_shift(int n_out, int kw, int stride) {
-  static const int env = [] { const char* e = getenv("MXB200_CONV_SHIFT"); return e ? atoi(e) : -1; }();
-  if (env == 0 || stride != 1 || kw < 2 || kw > 9) return false;
-  return env == 1 ? n_out <= 128 : n_out <= 128;
+  const char* e = getenv("MXB200_CONV_SHIFT");
+  if (e == nullptr || atoi(e) != 1 || stride != 1 || kw < 2 || kw > 9) return false;
+  return n_out <= 128;
 }
 
 // debug switch: MXB200_SHIFT_BASEOFF=1 puts the row phase into the descriptor's base-offset field (wrong on sm_100: kept to
 // document the experiment, tests/test_gpu_kernels.py passes only with the default 0)
 int shift_no_base_offset() {
-  static const int v = [] { const char* e = getenv("MXB200_SHIFT_BASEOFF"); return (e && atoi(e) == 1) ? 1 : 0; }();
-  return v;
+  const char* e = getenv("MXB200_SHIFT_BASEOFF");
+  return (e && atoi(e) == 1) ? 1 : 0;
 }
 
 #define MXB_CONV_SHIFT_DISPATCH(BMN, MM, NN, KK, LDA, LDB, LDD)                                                        \

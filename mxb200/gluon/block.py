@@ -5,6 +5,10 @@
 has one (``_fused_forward``: straight torch-level calls into our kernels with no per-op NDArray wrapping)
 -- the same idea (drop the per-op frontend overhead, keep semantics) without a tracing compiler.
 ``export()`` traces ``hybrid_forward`` with ``F = mx.sym`` to write ``-symbol.json`` + ``-0000.params``.
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/gluon/block.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
 """
 import copy
 import re

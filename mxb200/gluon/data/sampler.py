@@ -1,5 +1,10 @@
 """Samplers (reference: python/mxnet/gluon/data/sampler.py; SplitSampler from
-example/distributed_training/cifar10_dist.py:54-78)."""
+example/distributed_training/cifar10_dist.py:54-78).
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/gluon/data/sampler.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
+"""
 import random
 
 __all__ = ["Sampler", "SequentialSampler", "RandomSampler", "BatchSampler", "SplitSampler"]

@@ -1,4 +1,9 @@
-"""Losses (reference: python/mxnet/gluon/loss.py).  Each returns a per-sample loss vector (batch axis kept)."""
+"""Losses (reference: python/mxnet/gluon/loss.py).  Each returns a per-sample loss vector (batch axis kept).
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/gluon/loss.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
+"""
 import numpy as np
 import torch
 

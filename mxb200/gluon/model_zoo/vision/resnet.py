@@ -8,6 +8,10 @@ Two families:
   production model.  Its parameters are ordinary Gluon Parameters (save/load/Trainer work unchanged) but
   ``hybrid_forward`` is one call into ``mxb200.models.resnet.resnet_forward``, i.e. tcgen05 GEMMs for the
   1x1 convolutions and fused BN(+add)+ReLU kernels -- the analogue of a hybridized CachedOp graph.
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/gluon/model_zoo/vision/resnet.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
 """
 import numpy as np
 import torch

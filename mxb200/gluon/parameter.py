@@ -4,6 +4,10 @@ A Parameter keeps one data array and one gradient array per context (``_data`` /
 parameter.py:496-540).  ``reset_ctx`` = reduce (mean of the per-ctx copies) + re-initialise on the new
 context list (parameter.py:312-323,393-416): the single-box analogue of an elastic re-init (SURVEY.md
 Appendix D).
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/gluon/parameter.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
 """
 import re
 import warnings

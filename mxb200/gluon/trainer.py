@@ -9,6 +9,10 @@ Two execution paths behind one API:
   csrc/cuda/allreduce.cu).  This replaces _allreduce_grads + _update (trainer.py:304-374).
 * **generic**: the reference algorithm -- kvstore push/pull per parameter + per-context Updaters -- used on
   CPU, with several contexts in one process, with sparse gradients or custom optimizers.
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/gluon/trainer.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
 """
 import warnings
 

@@ -3,6 +3,10 @@
 ``init(InitDesc(name, attrs), arr)`` dispatches on the parameter-name suffix exactly like the reference
 (_weight / _bias / _gamma / _beta / moving_* ... initializer.py:120-170) so Module and Gluon get the same
 defaults: bias/beta/moving_mean -> 0, gamma/moving_var -> 1, weights -> the chosen scheme.
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/initializer.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
 """
 import json
 import math

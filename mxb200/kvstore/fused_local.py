@@ -95,6 +95,7 @@ class FusedLocalComm(object):
         ar._one_shot = None
         ar.bw_epoch, ar.dirty, ar.write_semantics = -1, False, False
         ar.norm_bufs = ar.norm_tot = ar.gsync = None
+        ar.ll_bufs = None
         ar.weights = wl.tensor(dtype, ar.n)
         ar.grads = gl.tensor(dtype, ar.n)
         ar.chunk_tid = torch.from_numpy(ar.layout.chunk_tid).to(ar.device)

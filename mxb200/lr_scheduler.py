@@ -4,6 +4,10 @@ arXiv 1904.12043), which the reference tree itself never implemented (SURVEY.md 
 
 Every scheduler is a callable ``sched(num_update) -> lr``; ``Optimizer.__init__`` overwrites
 ``sched.base_lr`` with its ``learning_rate`` (optimizer.py:92-93).
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/lr_scheduler.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
 """
 import logging
 import math

@@ -1,5 +1,10 @@
 """BaseModule: the high-level train / score / predict loop, including the elastic-training epoch loop
-(reference: python/mxnet/module/base_module.py:412-623; elastic additions :503-623)."""
+(reference: python/mxnet/module/base_module.py:412-623; elastic additions :503-623).
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/module/base_module.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
+"""
 import logging
 import os
 import time

@@ -4,6 +4,10 @@ Fork-specific surface kept: ``Module(data_iterator=BaseDataIterator)`` + ``get_i
 (module.py:72-75,198-202), ``init_optimizer(initialize_from_kvstore=...)`` for workers joining a running job
 (:485-571), ``store_aux_params`` (:668-683) and aux arrays registered on the kvstore under exclude-update keys
 (model.py:116-134).
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/module/module.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
 """
 import logging
 import warnings

@@ -7,6 +7,10 @@ gradient, multi-precision (fp32 master copy for low-precision weights, optimizer
 sign conventions of each update rule.  The dense SGD/NAG/Adam/LAMB updates run as
 single fused CUDA kernels on GPU tensors (mxb200/ops/optim.py); everything else is written with
 elementwise NDArray math.  LAMB and the dynamic-mini-batch utilities are additions (absent upstream).
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/optimizer.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
 """
 import math
 import pickle

@@ -23,6 +23,8 @@ MODE_ALLREDUCE, MODE_SGD, MODE_ADAM, MODE_LAMB1, MODE_LAMB2, MODE_BCAST, MODE_LA
 
 # one-shot below this many bytes of gradient per rank (latency-bound), two-shot above
 ONE_SHOT_BYTES = 512 * 1024
+# ... and below this the barrier-free low-latency protocol (flag-carrying 8-byte packets pushed into every peer's buffer)
+LL_BYTES = 256 * 1024
 
 
 class _Args(ctypes.Structure):
@@ -35,7 +37,8 @@ class _Args(ctypes.Structure):
                 ("nesterov", c_int), ("has_mom", c_int), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
                 ("bc1", c_float), ("bc2", c_float), ("lamb_lower", c_float), ("lamb_upper", c_float), ("hyper", c_void_p),
                 ("grads_mc", c_void_p), ("weights_mc", c_void_p), ("norms", c_void_p * MAX_RANKS), ("norm_tot", c_void_p),
-                ("gsync", c_void_p), ("nt_pad", c_int), ("pad0", c_int), ("state_off", c_int64), ("seq_dev", c_void_p)]
+                ("gsync", c_void_p), ("nt_pad", c_int), ("pad0", c_int), ("state_off", c_int64), ("seq_dev", c_void_p),
+                ("ll_recv", c_void_p * MAX_RANKS), ("ll_ctr", c_void_p)]
 
 HYPER_FLOATS = 8      # csrc/cuda/allreduce.cu: [lr, wd, momentum, rescale, clip, seq(uint32 bits), bc1, bc2]
 
@@ -72,6 +75,7 @@ class SymmetricArena(object):
         # NVLS: multicast mappings of the two arenas (None -> P2P loads / stores over the unicast peer mappings)
         self.w_mc, self.g_mc = bufs.get("weights_mc"), bufs.get("grads_mc")
         self._one_shot = None
+        self.ll_bufs = None               # low-latency protocol receive buffers (local buffer, [ptr per rank])
         self.bw_epoch, self.dirty, self.write_semantics = -1, False, True     # ops.functional.sink_touch
         self.norm_bufs = None             # fused LAMB: (local buffer, [ptr per rank]) of per-tensor partial norms
         self.norm_tot = self.gsync = None
@@ -175,7 +179,7 @@ class SymmetricArena(object):
 
 def fused_step(arena, mode, lr=0.0, wd=0.0, momentum=0.0, rescale=1.0, clip=None, nesterov=False, multi_precision=True,
                zero_grad=True, beta1=0.9, beta2=0.999, eps=1e-8, bc1=1.0, bc2=1.0, lamb_lower=-1.0, lamb_upper=-1.0,
-               one_shot=None, blocks=0, seq=None, hyper=None, nvls=None):
+               one_shot=None, blocks=0, seq=None, hyper=None, nvls=None, ll=None):
     """Launch the fused kernel for one arena on this rank's current stream.
 
     ``hyper``: fp32 device tensor of HYPER_FLOATS entries (``pack_hyper``) that the kernel reads lr / wd / momentum /
@@ -198,6 +202,17 @@ def fused_step(arena, mode, lr=0.0, wd=0.0, momentum=0.0, rescale=1.0, clip=None
         arena._one_shot = bool(one_shot)
     a.one_shot = int(arena.one_shot())
     a.state_off = arena.slice_range()[0] if not a.one_shot else 0
+    use_ll = (ll if ll is not None else True) and g.world > 1 and a.one_shot and arena.gdtype is torch.float32 and \
+        arena.n * 4 <= LL_BYTES and mode in (MODE_ALLREDUCE, MODE_SGD, MODE_ADAM) and hasattr(g, "alloc") and \
+        getattr(g, "seq_dev", None) is not None and seq is None
+    if use_ll:
+        if arena.ll_bufs is None:
+            # collective allocation: [2 parities][world sources][n] packets of 8 bytes per rank
+            arena.ll_bufs = g.alloc(2 * g.world * arena.n * 8)
+            arena.ll_ctr = torch.ones(1, dtype=torch.int32, device=arena.device)
+        for r in range(g.world):
+            a.ll_recv[r] = arena.ll_bufs[1][r]
+        a.ll_ctr = arena.ll_ctr.data_ptr()
     if g.world > 1 and nvls is not False and arena.g_mc and mode not in (MODE_LAMB2, MODE_BCAST):
         a.grads_mc = arena.g_mc
     if g.world > 1 and nvls is not False and arena.w_mc:

@@ -3,6 +3,10 @@
 Record layout: u32 magic 0xced7230a | u32 (cflag << 29 | length) | payload | pad to 4 bytes.  cflag: 0 whole
 record, 1 first / 2 middle / 3 last part of a record that contained the magic word.  IRHeader packs
 (flag, label, id, id2) in front of image bytes; flag > 0 means ``flag`` float labels follow the header.
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/recordio.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
 """
 import ctypes
 import numbers

@@ -1,5 +1,10 @@
 """Generic class registries (reference: python/mxnet/registry.py): ``get_register_func`` / ``get_alias_func`` /
-``get_create_func`` build the register / alias / create trio used by optimizers, initializers, metrics."""
+``get_create_func`` build the register / alias / create trio used by optimizers, initializers, metrics.
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/registry.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
+"""
 import json
 import warnings
 

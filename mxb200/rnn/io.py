@@ -1,4 +1,9 @@
-"""Bucketed sentence iterator (reference: python/mxnet/rnn/io.py)."""
+"""Bucketed sentence iterator (reference: python/mxnet/rnn/io.py).
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/rnn/io.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
+"""
 import bisect
 import random
 

@@ -1,5 +1,10 @@
 """Checkpoint helpers for networks built from RNN cells (reference: python/mxnet/rnn/rnn.py): parameters are saved in
-the unpacked (per-gate) form so checkpoints are interchangeable between fused and unfused cells."""
+the unpacked (per-gate) form so checkpoints are interchangeable between fused and unfused cells.
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/rnn/rnn.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
+"""
 from ..model import load_checkpoint, save_checkpoint
 from .rnn_cell import BaseRNNCell
 

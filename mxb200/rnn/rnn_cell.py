@@ -1,5 +1,10 @@
 """Symbolic recurrent cells: each call adds the nodes of one time step to a ``mx.sym`` graph; ``unroll`` builds the whole
-sequence (reference: python/mxnet/rnn/rnn_cell.py).  Parameters are shared across steps through ``RNNParams``."""
+sequence (reference: python/mxnet/rnn/rnn_cell.py).  Parameters are shared across steps through ``RNNParams``.
+
+Provenance: adapted from Apache MXNet (incubating) 1.3.1 ``python/mxnet/rnn/rnn_cell.py`` (Apache License 2.0).  The public API, argument
+names and control flow follow the original so that user scripts keep working; the tensor maths runs on torch /
+the mxb200 kernels.  This file is API-compatibility glue, not original B200 work ("Provenance").
+"""
 from .. import symbol
 from ..base import MXNetError
 

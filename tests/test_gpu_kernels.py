@@ -1125,3 +1125,24 @@ def test_fused_attention_dropout_is_consistent_between_fwd_and_bwd():
     _assert_close_elementwise(v.grad, vr.grad, 3e-2, 3e-2, "dv")
     _assert_close_elementwise(q2.grad, qr.grad, 4e-2, 4e-2, "dq")
     _assert_close_elementwise(k2.grad, kr.grad, 4e-2, 4e-2, "dk")
+
+
+@pytest.mark.parametrize("n,h,w,c,o", [(4, 56, 56, 64, 64), (2, 28, 28, 128, 128), (3, 13, 17, 64, 128)])
+def test_conv3x3_row_shifted_taps_variant(monkeypatch, n, h, w, c, o):
+    """The opt-in shifted-tap implicit GEMM (one gathered A tile per filter row, taps = row-shifted UMMA descriptors)."""
+    import torch.nn.functional as F
+    from mxb200.ops import functional as K_
+    monkeypatch.setenv("MXB200_CONV_SHIFT", "1")
+    x = torch.randn(n, h, w, c, device=_dev()).bfloat16()
+    wk = (torch.randn(o, 3, 3, c, device=_dev()) * (2.0 / (9 * c)) ** 0.5).bfloat16()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wk.float().permute(0, 3, 1, 2).detach().clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, 1, 1)
+    s1, s2 = torch.zeros(o, device=_dev()), torch.zeros(o, device=_dev())
+    y = K_.conv_fwd_raw(x, wk, 1, 1, col_stats=(s1, s2))
+    _assert_close_elementwise(y, ref.detach().permute(0, 2, 3, 1), 1.6e-2, 2e-2, "fwd")
+    assert _rel_err(s1, y.float().sum((0, 1, 2))) < 2e-3 and _rel_err(s2, (y.float() ** 2).sum((0, 1, 2))) < 2e-3
+    dy = torch.randn_like(y)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    dx = K_.conv_dgrad_raw(dy, wk, x.shape, 1, 1)
+    _assert_close_elementwise(dx, xr.grad.permute(0, 2, 3, 1), 1.6e-2, 2e-2, "dgrad")

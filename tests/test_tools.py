@@ -87,3 +87,52 @@ def test_reference_unittest_runner(tmp_path):
     assert r.returncode == 0, r.stdout
     assert "test_metric" in r.stdout and "failed   0" in r.stdout
     assert "| test_attr | 4 | 0 |" in open(out).read()
+
+
+def test_launch_host_file_manager_tags_and_terminates(tmp_path):
+    """The EC2 side effects of the elastic launcher (reference tools/launch.py:171-199) against a fake EC2 client: ADD_QUEUED ->
+    ADDED on the scheduler's log line, REMOVAL_QUEUED -> REMOVED + terminate, base hosts immutable, atomic host file."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("mxb_launch", os.path.join(os.path.dirname(__file__), "..", "tools", "launch.py"))
+    launch = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(launch)
+
+    class FakeEC2(object):
+        def __init__(self):
+            self.inst = {}          # ip -> (id, tags)
+            self.terminated = []
+
+        def describe_instances(self, Filters):
+            return {"Reservations": [{"Instances": [{"PrivateIpAddress": ip, "InstanceId": iid,
+                                                      "Tags": [{"Key": k, "Value": v} for k, v in tags.items()]}
+                                                     for ip, (iid, tags) in self.inst.items() if iid not in self.terminated]}]}
+
+        def create_tags(self, Resources, Tags):
+            for ip, (iid, tags) in self.inst.items():
+                if iid in Resources:
+                    for t in Tags:
+                        tags[t["Key"]] = t["Value"]
+
+        def terminate_instances(self, InstanceIds):
+            self.terminated.extend(InstanceIds)
+
+    hf = str(tmp_path / "host_worker")
+    open(hf, "w").write("10.0.0.1\n10.0.0.2\n")
+    ec2 = FakeEC2()
+    mgr = launch.HostFileManager(hf, ["10.0.0.1", "10.0.0.2"], ec2=ec2, elastic_tag="elastic", mount=str(tmp_path))
+    ec2.inst["10.0.0.9"] = ("i-9", {"elastic": "1", "NodeType": "Worker"})
+    assert mgr.poll() == ["10.0.0.1", "10.0.0.2"]                       # data not staged yet: not admitted
+    open(str(tmp_path / "prepare_data_success_10.0.0.9"), "w").write("ok")
+    assert mgr.poll() == ["10.0.0.1", "10.0.0.2", "10.0.0.9"]
+    assert ec2.inst["10.0.0.9"][1]["elastic_worker_status"] == "ADD_QUEUED"
+    open(hf + "_log", "w").write("0 ADDED 10.0.0.9 123\n")
+    mgr.poll()
+    assert ec2.inst["10.0.0.9"][1]["elastic_worker_status"] == "ADDED"
+    del ec2.inst["10.0.0.9"][1]["elastic"]                              # operator withdraws the instance
+    assert mgr.poll() == ["10.0.0.1", "10.0.0.2"]
+    assert ec2.inst["10.0.0.9"][1]["elastic_worker_status"] == "REMOVAL_QUEUED"
+    open(hf + "_log", "a").write("1 REMOVED 10.0.0.9 456\n")
+    mgr.poll()
+    assert ec2.inst["10.0.0.9"][1]["elastic_worker_status"] == "REMOVED" and ec2.terminated == ["i-9"]
+    assert open(hf).read().split() == ["10.0.0.1", "10.0.0.2"]

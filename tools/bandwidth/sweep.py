@@ -9,7 +9,8 @@ For every message size S (fp32 gradient bytes per rank) all ranks run the plain-
 (csrc/cuda/allreduce.cu kAllreduce: out_r = sum_q grad_q on every rank == kv.push + kv.pull without an updater,
 the operation tools/bandwidth/measure.py of the reference times per parameter tensor) in four variants:
 
-    p2p_one_shot / p2p_two_shot     16-byte loads / stores on peer-mapped arenas
+    ll_one_shot (<= 256 KB)         {value, flag} packets pushed into every peer's buffer, no barrier (latency path)
+    p2p_one_shot / p2p_two_shot     16-byte loads / stores on peer-mapped arenas, flag barriers
     nvls_one_shot / nvls_two_shot   multimem.ld_reduce / multimem.st on the multicast mapping (in-switch reduction)
 
 and ``torch.distributed.all_reduce`` (NCCL) on a tensor of the same size.  Timing: CUDA events on the launching
@@ -113,14 +114,16 @@ def main():
         dist.all_reduce(ref)
         row = {"bytes": size, "elements": real, "world": world}
         iters = args.iters if size <= (64 << 20) else max(5, args.iters // 3)
-        variants = [("p2p_one_shot", False, True), ("p2p_two_shot", False, False)]
+        variants = [("p2p_one_shot", False, True, False), ("p2p_two_shot", False, False, False)]
+        if nelem * 4 <= fused.LL_BYTES:
+            variants.insert(0, ("ll_one_shot", False, True, True))      # barrier-free flag-carrying packets
         if have_mc:
-            variants += [("nvls_one_shot", True, True), ("nvls_two_shot", True, False)]
-        for name, nv, one in variants:
+            variants += [("nvls_one_shot", True, True, False), ("nvls_two_shot", True, False, False)]
+        for name, nv, one, ll in variants:
             if one and size > (8 << 20):
                 continue                      # one-shot moves (n-1) x S per rank: pointless for large messages
-            def run(nv=nv, one=one):
-                fused.fused_step(ar, fused.MODE_ALLREDUCE, rescale=1.0, one_shot=one, zero_grad=False, nvls=nv)
+            def run(nv=nv, one=one, ll=ll):
+                fused.fused_step(ar, fused.MODE_ALLREDUCE, rescale=1.0, one_shot=one, zero_grad=False, nvls=nv, ll=ll)
             run()
             torch.cuda.synchronize()
             err = ((ar.weights - ref).abs().max() / (ref.abs().max() + 1e-12)).item()

@@ -57,46 +57,120 @@ def spawn(cmd, env, host=None, launcher="local"):
 
 
 class HostFileManager(threading.Thread):
-    """EC2 tag driven manager of ``host_worker`` (reference launch.py:88-235): base hosts are immutable, instances are
-    admitted when their ``prepare_data_success_<ip>`` marker exists, the file is replaced atomically (.tmp + rename)
-    and ``host_worker_log`` lines are mirrored back into instance tags.  Requires boto3."""
+    """EC2-tag driven manager of the worker host file: the elastic control loop of the reference's launcher
+    (tools/launch.py:88-235 there), restructured as a small state machine around one ``poll()`` so that it can be driven by a
+    fake EC2 client in tests (tests/test_tools.py).
 
-    def __init__(self, host_file, base_hosts, interval=5):
+    Protocol (tag ``elastic_worker_status`` on worker instances of one launch template):
+      * the first ``fixed`` lines of the host file are the immutable base workers;
+      * an instance carrying the elastic tag joins the candidate set once its ``prepare_data_success_<ip>`` marker exists
+        on the shared mount; a new candidate is written to the host file and tagged ADD_QUEUED; when the scheduler's audit
+        log (``<hostfile>_log``: SEQ ADDED|REMOVED IP TIME) reports ADDED the tag becomes ADDED;
+      * an elastic host whose instance lost the elastic tag is dropped from the host file and tagged REMOVAL_QUEUED; when the
+        log reports REMOVED the tag becomes REMOVED and the instance is TERMINATED;
+      * the host file is replaced atomically (.tmp + rename): the scheduler diffs it at the next epoch boundary
+        (csrc/host/pslite.cc, removal before addition)."""
+
+    STATUS = "elastic_worker_status"
+    ADD_QUEUED, ADDED, REMOVAL_QUEUED, REMOVED = "ADD_QUEUED", "ADDED", "REMOVAL_QUEUED", "REMOVED"
+
+    def __init__(self, host_file, base_hosts, interval=5, ec2=None, elastic_tag=None, template_id=None, mount=None):
         super(HostFileManager, self).__init__(daemon=True)
-        self.host_file, self.base_hosts, self.interval = host_file, list(base_hosts), interval
+        self.host_file, self.fixed, self.interval = host_file, len(list(base_hosts)), interval
+        self.ec2 = ec2
+        self.elastic_tag = elastic_tag or os.environ.get("ELASTIC_WORKER_TAG", "")
+        self.template_id = template_id or os.environ.get("WORKER_LAUNCH_TEMPLATE_ID", "")
+        self.mount = mount or os.environ.get("EFS_MOUNT") or os.path.dirname(os.path.abspath(host_file))
+        self.add_queue, self.remove_queue = {}, {}      # ip -> instance id, waiting for the scheduler's ADDED / REMOVED
+        self.seen_seq = -1
+        self.actions = []                               # audit trail of (verb, ip, instance id): what the manager did
+
+    def _tag(self, iid, value, ip):
+        self.ec2.create_tags(Resources=[iid], Tags=[{"Key": self.STATUS, "Value": value}])
+        self.actions.append((value, ip, iid))
+
+    def _instances(self):
+        flt = [{"Name": "tag:NodeType", "Values": ["Worker"]}, {"Name": "instance-state-name", "Values": ["running"]}]
+        if self.template_id:
+            flt.insert(0, {"Name": "tag:aws:ec2launchtemplate:id", "Values": [self.template_id]})
+        resp = self.ec2.describe_instances(Filters=flt)
+        for r in resp.get("Reservations", []):
+            for inst in r.get("Instances", []):
+                if inst.get("PrivateIpAddress"):
+                    yield inst["PrivateIpAddress"], inst["InstanceId"], {t["Key"]: t["Value"] for t in inst.get("Tags", [])}
+
+    def poll(self):
+        """One pass of the control loop; returns the host list it wrote."""
+        if not os.path.exists(self.host_file):
+            return None
+        with open(self.host_file) as f:
+            lines = [ln.strip() for ln in f if ln.strip()]
+        base, elastic_now = lines[:self.fixed], lines[self.fixed:]
+        candidates, lost_tag = {}, {}
+        for ip, iid, tags in self._instances():
+            status = tags.get(self.STATUS)
+            has_elastic = self.elastic_tag in tags
+            if status == self.REMOVAL_QUEUED:
+                self.remove_queue[ip] = iid
+            elif status == self.ADD_QUEUED:
+                self.add_queue[ip] = iid
+            if has_elastic and status is None:
+                if os.path.exists(os.path.join(self.mount, "prepare_data_success_%s" % ip)):
+                    candidates[ip] = iid                 # data staged: may join at the next epoch boundary
+            elif has_elastic:
+                candidates[ip] = iid
+            elif status != self.REMOVAL_QUEUED:
+                lost_tag[ip] = iid                       # operator removed the elastic tag: leave at the next boundary
+        # the scheduler's audit log acknowledges membership changes
+        terminated = []
+        log = self.host_file + "_log"
+        if os.path.exists(log):
+            with open(log) as f:
+                for ln in f:
+                    parts = ln.split()
+                    if len(parts) < 3 or int(parts[0]) <= self.seen_seq:
+                        continue
+                    seq, what, ip = int(parts[0]), parts[1], parts[2]
+                    if what == "ADDED" and ip in self.add_queue:
+                        self._tag(self.add_queue.pop(ip), self.ADDED, ip)
+                    elif what == "REMOVED" and ip in self.remove_queue:
+                        iid = self.remove_queue.pop(ip)
+                        self._tag(iid, self.REMOVED, ip)
+                        terminated.append(iid)
+                    self.seen_seq = seq
+        if terminated:
+            self.ec2.terminate_instances(InstanceIds=terminated)
+            self.actions.extend(("TERMINATED", None, i) for i in terminated)
+        keep = [h for h in elastic_now if h in candidates]
+        leaving = [h for h in elastic_now if h not in candidates]
+        joining = [h for h in candidates if h not in elastic_now]
+        hosts = base + keep + joining
+        tmp = self.host_file + ".tmp"
+        with open(tmp, "w") as f:
+            f.write("\n".join(hosts) + "\n")
+        os.rename(tmp, self.host_file)
+        for h in leaving:
+            if h in lost_tag:
+                self._tag(lost_tag[h], self.REMOVAL_QUEUED, h)
+                self.remove_queue[h] = lost_tag[h]
+        for h in joining:
+            self._tag(candidates[h], self.ADD_QUEUED, h)
+            self.add_queue[h] = candidates[h]
+        return hosts
 
     def run(self):
-        try:
-            import boto3  # noqa: F401
-        except ImportError:
-            sys.stderr.write("launch.py: boto3 is not available; EC2 host-file manager disabled\n")
-            return
-        import boto3
-        ec2 = boto3.client("ec2", region_name=os.environ.get("AWS_REGION", "us-east-1"))
-        tag = os.environ["ELASTIC_WORKER_TAG"]
-        seen_log = 0
+        if self.ec2 is None:
+            try:
+                import boto3
+            except ImportError:
+                sys.stderr.write("launch.py: boto3 is not available; EC2 host-file manager disabled\n")
+                return
+            self.ec2 = boto3.client("ec2", region_name=os.environ.get("AWS_REGION", "us-east-1"))
         while True:
-            resp = ec2.describe_instances(Filters=[{"Name": "tag-key", "Values": [tag]}, {"Name": "instance-state-name", "Values": ["running"]}])
-            hosts = list(self.base_hosts)
-            for r in resp.get("Reservations", []):
-                for inst in r.get("Instances", []):
-                    ip = inst.get("PrivateIpAddress")
-                    status = {t["Key"]: t["Value"] for t in inst.get("Tags", [])}.get("elastic_worker_status", "")
-                    ok = os.path.exists(os.path.join(os.path.dirname(self.host_file), "prepare_data_success_%s" % ip))
-                    if ip and ip not in hosts and status in ("ADD_QUEUED", "ADDED") and ok:
-                        hosts.append(ip)
-            tmp = self.host_file + ".tmp"
-            with open(tmp, "w") as f:
-                f.write("\n".join(hosts) + "\n")
-            os.rename(tmp, self.host_file)
-            log = self.host_file + "_log"
-            if os.path.exists(log):
-                lines = open(log).read().splitlines()
-                for line in lines[seen_log:]:
-                    _seq, what, ip, _t = line.split()
-                    # mirror ADDED / REMOVED into tags; terminate removed instances
-                    sys.stderr.write("launch.py: %s %s\n" % (what, ip))
-                seen_log = len(lines)
+            try:
+                self.poll()
+            except Exception as e:  # noqa: BLE001 -- the manager must outlive transient API errors
+                sys.stderr.write("launch.py: host-file manager: %s\n" % e)
             time.sleep(self.interval)
 
 
