@@ -146,7 +146,7 @@ __device__ __forceinline__ float key_bias(const Params& p, int b, int key) {
 }
 
 // ================================================================================================ forward
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 3)
 fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
            const __grid_constant__ CUtensorMap tmV, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -154,8 +154,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   uint8_t* sq = sm;
   uint8_t* sk = sm + kTile;
   uint8_t* sv = sm + 2 * kTile;
-  uint8_t* sp = sm + 3 * kTile;                 // 2 panels
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 5 * kTile);   // 0: q,k,v landed  1: S ready  2: P staged  3: O ready
+  uint8_t* sp = sm;                             // P (2 panels) overwrites Q | K once S = Q K^T has completed
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 3 * kTile);   // 0: q,k,v landed  1: S ready  2: P staged  3: O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.nh, h = blockIdx.x % p.nh;
@@ -176,14 +176,14 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
-    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_alloc(tmem_slot, 128);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t t_s = tmem, t_o = tmem + 128;
+  const uint32_t t_s = tmem, t_o = tmem;        // O reuses the first 64 score columns (every row was drained before bars[2])
 
   if (warp == 4) {
     if (lane == 0) {
@@ -271,23 +271,23 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   __syncthreads();
   if (warp == 0) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem, 256);
+    ptx::tmem_dealloc(tmem, 128);
   }
 }
 
 // ================================================================================================ backward
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sq = sm;
   uint8_t* sk = sm + kTile;
-  uint8_t* sv = sm + 2 * kTile;
-  uint8_t* sdo = sm + 3 * kTile;
-  uint8_t* sp = sm + 4 * kTile;                 // P~  (2 panels)
-  uint8_t* sds = sm + 6 * kTile;                // dS  (2 panels)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 8 * kTile);
+  uint8_t* sdo = sm + 2 * kTile;
+  uint8_t* sv = sm + 3 * kTile;
+  uint8_t* sp = sm + 3 * kTile;                 // P~  (2 panels): panel 0 overwrites V once dP = dO V^T has completed
+  uint8_t* sds = sm + 5 * kTile;                // dS  (2 panels)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 7 * kTile);
   // 0: tiles landed  1: S + dP ready  2: P~ and dS staged  3: dV, dQ, dK ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -302,14 +302,15 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
-    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_alloc(tmem_slot, 256);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t t_s = tmem, t_dp = tmem + 128, t_dv = tmem + 256, t_dq = tmem + 320, t_dk = tmem + 384;
+  // dV / dQ / dK reuse the S and dP columns: all 128 rows have been drained into P~ / dS before bars[2] is signalled
+  const uint32_t t_s = tmem, t_dp = tmem + 128, t_dv = tmem, t_dq = tmem + 64, t_dk = tmem + 128;
 
   if (warp == 4) {
     if (lane == 0) {
@@ -425,7 +426,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   __syncthreads();
   if (warp == 0) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem, 512);
+    ptx::tmem_dealloc(tmem, 256);
   }
 }
 
@@ -485,7 +486,7 @@ MXB_API int MXBAttnFwd(const void* q, const void* k, const void* v, void* out, f
   p.lse = lse;
   const int64_t rows = (int64_t)B * S, cols = (int64_t)nh * attn::kD;
   CUtensorMap tq = attn::map_rows(q, rows, cols, ld), tk = attn::map_rows(k, rows, cols, ld), tv = attn::map_rows(v, rows, cols, ld);
-  const int smem = 5 * attn::kTile + 256 + 1024;
+  const int smem = 3 * attn::kTile + 256 + 1024;
   CUDA_CHECK(cudaFuncSetAttribute(attn::fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   attn::fwd_kernel<<<B * nh, attn::kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   CUDA_CHECK(cudaGetLastError());
@@ -511,7 +512,7 @@ MXB_API int MXBAttnBwd(const void* q, const void* k, const void* v, const void* 
   const int64_t rows = (int64_t)B * S, cols = (int64_t)nh * attn::kD;
   CUtensorMap tq = attn::map_rows(q, rows, cols, ld), tk = attn::map_rows(k, rows, cols, ld), tv = attn::map_rows(v, rows, cols, ld),
               tdo = attn::map_rows(dout, rows, cols, ld);
-  const int smem = 8 * attn::kTile + 256 + 1024;
+  const int smem = 7 * attn::kTile + 256 + 1024;
   CUDA_CHECK(cudaFuncSetAttribute(attn::bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   attn::bwd_kernel<<<B * nh, attn::kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, tdo, p);
   CUDA_CHECK(cudaGetLastError());

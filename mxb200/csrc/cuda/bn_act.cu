@@ -566,6 +566,167 @@ bwd_reduce_bulk_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Elementwise BatchNorm passes on the same bulk-copy ring as bwd_reduce_bulk_kernel: inputs stream global -> shared memory
+// through a producer warp (UBLKCP), the 256 consumer threads read their vectors from shared memory, compute and write
+// 16-byte results straight to global memory (a warp writes 512 contiguous bytes).
+//   MODE 0: forward apply   y = act(x * scale + shift (+ res)), 1-bit ReLU mask            in: x (, res)      out: y, mask
+//   MODE 1: backward apply  dx = a1 * dy' + k1 * x + k0, dres = dy' (dy' = dy . mask)       in: dy, x, mask    out: dx (, dres)
+struct ElemArgs {
+  const __nv_bfloat16* in0;     // x  | dy
+  const __nv_bfloat16* in1;     // res | x
+  const uint8_t* mask_in;       // backward: ReLU mask
+  __nv_bfloat16* out0;          // y  | dx
+  __nv_bfloat16* out1;          // -  | dres
+  uint8_t* mask_out;            // forward: ReLU mask
+  const float* p0;              // scale | c1
+  const float* p1;              // shift | c2
+  const float* p2;              // -     | c3
+  const float* mean;            // backward
+  const float* invstd;          // backward
+  int64_t M;
+  int C;
+};
+
+template <int MODE, bool RELU, bool SECOND>     // SECOND: forward residual input / backward dres output
+__global__ void __launch_bounds__(kRedThreads, 2)
+elem_bulk_kernel(const ElemArgs a) {
+  extern __shared__ uint8_t red_smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(red_smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + kRedStages * kRedStageBytes);
+  uint64_t* empty = full + kRedStages;
+  const int C = a.C, CV = C / 8;
+  const int R = kRedVecs / CV;
+  const int64_t nchunks = (a.M + R - 1) / R;
+  constexpr bool kTwoIn = (MODE == 1) || SECOND;           // second 16 KB input stream
+  constexpr bool kMaskIn = (MODE == 1) && RELU;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRedStages; ++i) {
+      mbar_init_(&full[i], 1);
+      mbar_init_(&empty[i], kRedConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if ((threadIdx.x >> 5) == kRedConsumers / 32) {
+    if ((threadIdx.x & 31) == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const int64_t r0 = c * R;
+        const int rows = (int)min((int64_t)R, a.M - r0);
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)C * 2u;
+        const uint32_t mbytes = kMaskIn ? (uint32_t)rows * (uint32_t)CV : 0u;
+        mbar_wait_(&empty[stage], phase ^ 1);
+        uint8_t* dst = sm + stage * kRedStageBytes;
+        mbar_expect_(&full[stage], (kTwoIn ? 2u : 1u) * bytes + mbytes);
+        bulk_g2s(dst, a.in0 + r0 * C, bytes, &full[stage]);
+        if (kTwoIn) bulk_g2s(dst + kRedVecs * 16, a.in1 + r0 * C, bytes, &full[stage]);
+        if (kMaskIn) bulk_g2s(dst + 2 * kRedVecs * 16, a.mask_in + r0 * CV, mbytes, &full[stage]);
+        if (++stage == kRedStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    return;
+  }
+  const int col = threadIdx.x % CV;
+  float k1[8], k0[8], a1[8];      // forward: k1 = scale, k0 = shift;  backward: dx = a1 * dy' + k1 * x + k0
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (MODE == 0) {
+      k1[j] = __ldg(a.p0 + col * 8 + j);
+      k0[j] = __ldg(a.p1 + col * 8 + j);
+      a1[j] = 0.f;
+    } else {
+      const float c1 = __ldg(a.p0 + col * 8 + j), c2 = __ldg(a.p1 + col * 8 + j), c3 = __ldg(a.p2 + col * 8 + j);
+      const float mu = __ldg(a.mean + col * 8 + j), is = __ldg(a.invstd + col * 8 + j);
+      a1[j] = c1;
+      k1[j] = -c1 * is * c3;
+      k0[j] = -k1[j] * mu - c1 * c2;
+    }
+  }
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int64_t r0 = c * R;
+    const int nvec = (int)min((int64_t)R, a.M - r0) * CV;
+    const int64_t v0 = r0 * CV;
+    mbar_wait_(&full[stage], phase);
+    const uint4* s0 = reinterpret_cast<const uint4*>(sm + stage * kRedStageBytes);
+    const uint4* s1 = s0 + kRedVecs;
+    const uint8_t* smk = reinterpret_cast<const uint8_t*>(s1 + kRedVecs);
+    uint4 u0[4], u1[4];
+    uint32_t bits[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int v = threadIdx.x + k * kRedConsumers;
+      if (v < nvec) {
+        u0[k] = s0[v];
+        if (kTwoIn) u1[k] = s1[v];
+        bits[k] = kMaskIn ? (uint32_t)smk[v] : 0xFFu;
+      }
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive_(&empty[stage]);       // the ring slot is free as soon as it sits in registers
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int v = threadIdx.x + k * kRedConsumers;
+      if (v >= nvec) continue;
+      float x0[8], x1[8], o[8];
+      unpack<__nv_bfloat16>(u0[k], x0);
+      if (kTwoIn) unpack<__nv_bfloat16>(u1[k], x1);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(x0[j], k1[j], k0[j]) + (SECOND ? x1[j] : 0.f);
+        if (RELU) {
+          uint32_t m = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            m |= (o[j] > 0.f ? 1u : 0u) << j;
+            o[j] = fmaxf(o[j], 0.f);
+          }
+          if (a.mask_out != nullptr) a.mask_out[v0 + v] = (uint8_t)m;
+        }
+        stg16(a.out0 + (v0 + v) * 8, pack<__nv_bfloat16>(o));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = ((bits[k] >> j) & 1u) ? x0[j] : 0.f;
+          x0[j] = d;
+          o[j] = fmaf(a1[j], d, fmaf(k1[j], x1[j], k0[j]));
+        }
+        stg16(a.out0 + (v0 + v) * 8, pack<__nv_bfloat16>(o));
+        if (SECOND) stg16(a.out1 + (v0 + v) * 8, pack<__nv_bfloat16>(x0));
+      }
+    }
+    if (++stage == kRedStages) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+}
+
+template <int MODE, bool RELU, bool SECOND>
+static void launch_elem_bulk(const ElemArgs& a, cudaStream_t s) {
+  const int CV = a.C / 8, R = kRedVecs / CV;
+  const int64_t nchunks = (a.M + R - 1) / R;
+  const int grid = (int)std::min<int64_t>(nchunks, (int64_t)kNumSMs * 2);
+  auto kern = elem_bulk_kernel<MODE, RELU, SECOND>;
+  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRedSmem));
+  kern<<<grid, kRedThreads, kRedSmem, s>>>(a);
+}
+
+static bool elem_bulk_ok(int64_t M, int C, const void* p0, const void* p1, const void* p2, const void* p3, const void* mask) {
+  static const bool off = [] { const char* e = getenv("MXB200_BN_BULK"); return e && e[0] == '0'; }();
+  const int CV = C / 8;
+  if (off || C % 8 != 0 || CV > 256 || (kRedVecs % CV) != 0) return false;
+  const int R = kRedVecs / CV;
+  auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % 16) == 0; };
+  return M >= 4 * R && ((M * CV) % 16) == 0 && al(p0) && al(p1) && al(p2) && al(p3) && al(mask);
+}
+
 template <typename T, bool RELU, bool RES>
 __global__ void __launch_bounds__(kThreads, 2)
 bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const uint8_t* __restrict__ mask, T* __restrict__ dx,
@@ -713,6 +874,17 @@ MXB_API int MXBBnApply(const void* x, const void* res, void* y, void* mask, int 
     const int CV = C / V<T>::N;
     const int g = grid_elems(M * CV, CV);
     const T* xx = (const T*)x; const T* rr = (const T*)res; T* yy = (T*)y; uint8_t* mm = (uint8_t*)mask;
+    if constexpr (sizeof(T) == 2) {
+      if (elem_bulk_ok(M, C, x, res, y, nullptr, nullptr)) {
+        ElemArgs ea{(const __nv_bfloat16*)x, (const __nv_bfloat16*)res, nullptr, (__nv_bfloat16*)y, nullptr, mm, scale, shift,
+                    nullptr, nullptr, nullptr, M, C};
+        if (relu && res) launch_elem_bulk<0, true, true>(ea, s);
+        else if (relu) launch_elem_bulk<0, true, false>(ea, s);
+        else if (res) launch_elem_bulk<0, false, true>(ea, s);
+        else launch_elem_bulk<0, false, false>(ea, s);
+        return;
+      }
+    }
     if (relu && res) apply_kernel<T, true, true><<<g, kThreads, 0, s>>>(xx, rr, yy, mm, M, C, scale, shift);
     else if (relu) apply_kernel<T, true, false><<<g, kThreads, 0, s>>>(xx, rr, yy, mm, M, C, scale, shift);
     else if (res) apply_kernel<T, false, true><<<g, kThreads, 0, s>>>(xx, rr, yy, mm, M, C, scale, shift);
@@ -768,6 +940,17 @@ MXB_API int MXBBnBackward(const void* dy, const void* x, const void* mask, void*
     else bwd_reduce_kernel<T, false><<<grid_rows<T>(M, C), kThreads, 0, s>>>(dd, xx, mm, M, C, mean, f);
     const int g = grid_elems(M * CV, CV);
     T* ox = (T*)dx; T* orr = (T*)dres;
+    if constexpr (sizeof(T) == 2) {
+      if (elem_bulk_ok(M, C, dy, x, dx, dres, relu ? mask : nullptr)) {
+        ElemArgs ea{(const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mm, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, nullptr,
+                    f.c1, f.c2, f.c3, mean, invstd, M, C};
+        if (relu && dres) launch_elem_bulk<1, true, true>(ea, s);
+        else if (relu) launch_elem_bulk<1, true, false>(ea, s);
+        else if (dres) launch_elem_bulk<1, false, true>(ea, s);
+        else launch_elem_bulk<1, false, false>(ea, s);
+        return;
+      }
+    }
     if (relu && dres) bwd_apply_kernel<T, true, true><<<g, kThreads, 0, s>>>(dd, xx, mm, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
     else if (relu) bwd_apply_kernel<T, true, false><<<g, kThreads, 0, s>>>(dd, xx, mm, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);
     else if (dres) bwd_apply_kernel<T, false, true><<<g, kThreads, 0, s>>>(dd, xx, mm, ox, orr, M, C, mean, invstd, f.c1, f.c2, f.c3);

@@ -244,3 +244,51 @@ def test_gluon_bert_model_trains_on_cpu():
     assert losses[-1] < losses[0]
     enc = net(ids)
     assert enc.shape == (B, S, 256)
+
+
+def test_train_step_eager_path_matches_manual_loop():
+    """mx.gluon.TrainStep without capture (CPU) is exactly record / backward / step."""
+    import torch
+    import mxb200 as mx
+    from mxb200 import gluon, autograd
+
+    def build():
+        torch.manual_seed(0)
+        mx.random.seed(0)
+        net = gluon.nn.HybridSequential(prefix="ts_")
+        with net.name_scope():
+            net.add(gluon.nn.Dense(16, activation="relu", in_units=8), gluon.nn.Dense(4, in_units=16))
+        net.initialize(mx.init.Xavier())
+        tr = gluon.Trainer(net.collect_params(), "sgd", {"learning_rate": 0.1, "momentum": 0.9})
+        return net, tr
+
+    lossf = gluon.loss.SoftmaxCrossEntropyLoss()
+    xs = [mx.nd.array(torch.randn(6, 8).numpy()) for _ in range(4)]
+    ys = [mx.nd.array(torch.randint(0, 4, (6,)).numpy()) for _ in range(4)]
+    net, tr = build()
+    step = gluon.TrainStep(net, lossf, tr, batch_size=6)
+    a = [float(step(x, y).asnumpy().mean()) for x, y in zip(xs, ys)]
+    assert step.replays == 0 and step.eager_calls == 4
+    net2, tr2 = build()
+    b = []
+    for x, y in zip(xs, ys):
+        with autograd.record():
+            l = lossf(net2(x), y)
+        l.backward()
+        tr2.step(6)
+        b.append(float(l.asnumpy().mean()))
+    assert a == b
+
+
+def test_async_checkpoint_is_written_by_the_engine_and_load_waits(tmp_path):
+    import os
+    import mxb200 as mx
+    from mxb200 import engine
+    prefix = str(tmp_path / "ck")
+    arg = {"w": mx.nd.ones((64, 64)) * 3, "b": mx.nd.zeros((64,))}
+    mx.model.save_checkpoint(prefix, 7, None, arg, {}, async_write=True)
+    arg["w"][:] = 0                                        # the snapshot was taken at call time
+    _sym, a2, _aux = mx.model.load_checkpoint(prefix, 7)   # waits for the engine's write of exactly this file
+    assert float(a2["w"].asnumpy().mean()) == 3.0
+    engine.get().wait_all()
+    assert os.path.exists(prefix + "-0007.params")

@@ -1146,3 +1146,41 @@ def test_conv3x3_row_shifted_taps_variant(monkeypatch, n, h, w, c, o):
     ref.backward(dy.float().permute(0, 3, 1, 2))
     dx = K_.conv_dgrad_raw(dy, wk, x.shape, 1, 1)
     _assert_close_elementwise(dx, xr.grad.permute(0, 2, 3, 1), 1.6e-2, 2e-2, "dgrad")
+
+
+def test_fused_trainer_keeps_write_gradient_semantics_when_a_step_is_skipped():
+    """a backward pass that is NOT followed by trainer.step() must not leak its gradients into the next step
+    (grad_req='write'): the gradient arena is cleared by the first sink write of the next backward pass."""
+    import mxb200 as mx
+    from mxb200 import gluon, autograd
+    from mxb200.gluon.model_zoo import vision
+
+    def run(skip_first):
+        torch.manual_seed(0)
+        mx.random.seed(0)
+        ctx = mx.gpu(0)
+        net = vision.get_resnet("v1b", 18, classes=10, thumbnail=True, ctx=ctx, dtype="bfloat16", layout="NHWC")
+        net.hybridize()
+        tr = gluon.Trainer(net.collect_params(), "sgd", {"learning_rate": 0.05, "multi_precision": True}, kvstore="device")
+        lf = gluon.loss.SoftmaxCrossEntropyLoss()
+        g = torch.Generator(device="cuda").manual_seed(3)
+        x0 = mx.nd.from_torch(torch.randn(8, 32, 32, 3, device="cuda", generator=g).bfloat16(), ctx)
+        x1 = mx.nd.from_torch(torch.randn(8, 32, 32, 3, device="cuda", generator=g).bfloat16(), ctx)
+        y = mx.nd.from_torch(torch.randint(0, 10, (8,), device="cuda", generator=g), ctx)
+        with autograd.record():
+            l = lf(net(x0), y)
+        l.backward()
+        tr.step(8)                                  # fuses the trainer (lazy) -- identical in both runs
+        if skip_first:
+            with autograd.record():
+                l = lf(net(x0 * 3.0), y)
+            l.backward()                            # gradients computed, step skipped
+        with autograd.record():
+            l = lf(net(x1), y)
+        l.backward()
+        tr.step(8)
+        return [p.data().as_torch().detach().float().clone() for p in net.collect_params().values() if p.grad_req != "null"]
+
+    a, b = run(False), run(True)
+    worst = max((u - v).abs().max().item() / (u.abs().max().item() + 1e-6) for u, v in zip(a, b))
+    assert worst < 2e-2, worst      # (BatchNorm running statistics differ by the extra forward; trainable weights must agree)

@@ -213,3 +213,25 @@ def test_gpu_topology_trees_and_tree_comm():
         tc.broadcast(torch.full((5,), 2.5), outs, root)
         assert all(torch.equal(o, torch.full((5,), 2.5)) for o in outs)
     assert all(float(x[0]) == i + 1 for i, x in enumerate(xs))   # inputs untouched
+
+
+def test_create_kvstore_joins_torchrun_job_before_deciding(tmp_path):
+    """under torchrun with one device per process, ``_create_kvstore('device', 1, ...)`` must join the
+    process group first -- otherwise every rank trains an unsynchronised replica with kv=None."""
+    import os
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent('''
+        import os, sys
+        sys.path.insert(0, %r)
+        os.environ.update(WORLD_SIZE="2", RANK=sys.argv[1], LOCAL_RANK=sys.argv[1], MASTER_ADDR="127.0.0.1", MASTER_PORT="29671")
+        from mxb200.model import _create_kvstore
+        kv, upd = _create_kvstore("device", 1, {})
+        print("KV", type(kv).__name__, kv.num_workers if kv is not None else None)
+    ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    ps = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+          for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in ps]
+    for o in outs:
+        assert "KV KVStoreDevice 2" in o, o

@@ -5,8 +5,9 @@
     torchrun --nproc-per-node N tools/bench_bert.py ...          (one rank per GPU, fused P2P allreduce + LAMB)
 
 Synthetic token ids, random-init weights.  Device-timed (CUDA events, max over ranks); prints one JSON line.
-Per step: forward + backward of MLM+NSP loss, gradient allreduce and the LAMB update (2 fused kernels + the norm
-exchange), dropout 0.1 active."""
+Per step: forward + backward of the MLM + NSP loss (fused tcgen05 attention with in-kernel dropout, csrc/cuda/attention.cu),
+gradient allreduce and the LAMB update in ONE fused launch per arena (the per-tensor norms are reduced across ranks inside
+the kernel, csrc/cuda/allreduce.cu mode kLamb), dropout 0.1 active."""
 import argparse
 import json
 import os
