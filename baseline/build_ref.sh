@@ -12,8 +12,8 @@
 #   * cblas.h is not in the image -> a 40-line declaration header for the OpenBLAS that ships with opencv-python
 #   * patches under baseline/patches/*.patch are compile fixes for CUDA 12 / gcc 13, applied to the COPY and listed in
 #     DESIGN.md (01: `cuda::Reduce1D` -> `mshadow::cuda::Reduce1D`, ambiguous with libcu++'s global ::cuda namespace)
-#   * `--pre-include cub/cub.cuh` (nvcc) parses the toolkit's cub before any `using namespace mshadow`, `-include unistd.h`
-#     supplies getpid() for the fork's kvstore_local.h
+#     (02: `#include <unistd.h>` for the getpid() call the fork added to kvstore_local.h)
+#   * `--pre-include cub/cub.cuh` (nvcc) parses the toolkit's cub before any `using namespace mshadow`
 set -u
 JOBS=${1:-6}
 REPO=$(cd "$(dirname "$0")/.." && pwd)
@@ -96,7 +96,7 @@ DEV = 0
 DEBUG = 0
 USE_SIGNAL_HANDLER = 0
 ADD_LDFLAGS = -L$WORK/compat/lib -Wl,-rpath,$(dirname "$OB") -L/usr/local/cuda/lib64
-ADD_CFLAGS = -I$WORK/compat -include unistd.h -Wno-deprecated-declarations -Wno-unused -Wno-class-memaccess -Wno-maybe-uninitialized -fpermissive
+ADD_CFLAGS = -I$WORK/compat -Wno-deprecated-declarations -Wno-unused -Wno-class-memaccess -Wno-maybe-uninitialized -fpermissive
 USE_CUDA = 1
 USE_CUDA_PATH = /usr/local/cuda
 ENABLE_CUDA_RTC = 0

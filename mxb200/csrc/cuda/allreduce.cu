@@ -80,7 +80,7 @@ struct Args {
   float* norm_tot;
   uint32_t* gsync;            // local {count, generation} words of the intra-rank grid barrier
   int nt_pad;
-  int pad0;
+  int pad0;                   // != 0: kU-fold unrolled gather in the bandwidth-bound modes
   int64_t state_off;
   // Device-resident barrier sequence number {seq, finished-CTA count}: when non-null the kernel reads seq from here and the
   // last CTA to finish increments it, so replaying a captured launch needs no host-side bookkeeping at all (every rank
@@ -290,74 +290,38 @@ fused_kernel(const Args a) {
     }
   };
 
-  // One sweep over the owned slice.  block-uniform trip count (LAMB phase 1 has __syncthreads inside); base is a multiple of
-  // 128 vectors, so every group of 128 consecutive threads works on exactly one 1024-element chunk (= one tensor).
-  auto sweep = [&](const int mode, float* wn2, float* rn2) {
-    for (int64_t base = v_begin + (int64_t)blockIdx.x * kThreads; base < v_end; base += (int64_t)gridDim.x * kThreads) {
-      const int64_t v = base + threadIdx.x;
-      const bool active = v < v_end;
-      const int64_t e = v * 8;
-      const int64_t chunk = active ? e / kChunk : 0;
-      int t = 0;
-      float lr = h_lr, wd = h_wd;
-      bool skip = !active;
-      if (active && a.chunk_tid != nullptr) {
-        t = __ldg(a.chunk_tid + chunk);
-        if (t < 0) skip = true;
-        else {
-          lr *= a.lr_mult ? __ldg(a.lr_mult + t) : 1.f;
-          wd *= a.wd_mult ? __ldg(a.wd_mult + t) : 1.f;
-        }
+  // Per-vector metadata from the chunk table (tensor id -> lr / wd multipliers; padding chunks are skipped).
+  struct Meta { int64_t e; int t; float lr, wd; bool skip; };
+  auto meta_of = [&](int64_t v) {
+    Meta m;
+    const bool active = v < v_end;
+    m.e = v * 8;
+    m.t = 0; m.lr = h_lr; m.wd = h_wd; m.skip = !active;
+    if (active && a.chunk_tid != nullptr) {
+      m.t = __ldg(a.chunk_tid + m.e / kChunk);
+      if (m.t < 0) m.skip = true;
+      else {
+        m.lr *= a.lr_mult ? __ldg(a.lr_mult + m.t) : 1.f;
+        m.wd *= a.wd_mult ? __ldg(a.wd_mult + m.t) : 1.f;
       }
-      float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (!skip && mode != kLambPhase2 && mode != kBroadcast) {
-        if (ll) {
-          // 8 elements = 4 packets pairs per source; spin until every packet carries this launch's flag; sum in RANK order so
-          // that all replicas compute bit-identical results
-          const uint2* mine = a.ll_recv[a.rank] + ll_base;
-          bool ok = true;
-#pragma unroll
-          for (int q = 0; q < (NR > 0 ? NR : kMaxRanks); ++q) {
-            if (q < nr) {
-              const uint4* src = reinterpret_cast<const uint4*>(mine + (int64_t)q * a.n + e);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 pk;
-                uint32_t spins = 0;
-                do {
-                  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "l"(src + j) : "memory");
-                  if (++spins > kSpinLimit) { ok = false; break; }
-                } while (pk.y != ll_flag || pk.w != ll_flag);
-                g[2 * j] += __uint_as_float(pk.x);
-                g[2 * j + 1] += __uint_as_float(pk.z);
-              }
-            }
-          }
-          if (!ok && a.err) atomicExch(a.err, 1 + a.rank);
-        } else if (mc_grads) {
-          // the switch sums the N copies: one load per 16 bytes instead of N
-          mc_ld_reduce8<GT>(reinterpret_cast<const GT*>(a.grads_mc) + e, g);
-        } else {
-          // gradient reduction: own copy first, then peers in a rank-rotated order to spread link load
-#pragma unroll
-          for (int k = 0; k < (NR > 0 ? NR : kMaxRanks); ++k) {
-            if (k < nr) {
-              const int p = (a.rank + k) % nr;
-              float x[8];
-              ld8<GT>(reinterpret_cast<const GT*>(a.grads[p]) + e, x);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) g[j] += x[j];
-            }
-          }
-        }
-      }
+    }
+    return m;
+  };
+
+  // Everything after the gradient of one 8-element vector is known: optimizer math, master / state update, weight fan-out.
+  auto process = [&](const int mode, const Meta& mm, float (&g)[8], float* wn2, float* rn2) {
+    const int64_t e = mm.e;
+    const int t = mm.t;
+    const float lr = mm.lr, wd = mm.wd;
+    const bool skip = mm.skip;
+    do {
       if (mode == kAllreduce) {
         if (!skip) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) g[j] *= h_rescale;
           fan(e, g);
         }
-        continue;
+        break;
       }
       float w[8];
       if (!skip) {
@@ -365,7 +329,7 @@ fused_kernel(const Args a) {
         else ld8<WT>(reinterpret_cast<const WT*>(a.weights[a.rank]) + e, w);
       }
       if (mode == kSgd) {
-        if (skip) continue;
+        if (skip) break;
         SgdHyper h{h_lr, h_wd, h_mom, h_rescale, h_clip, a.nesterov, a.has_mom};
         float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (a.has_mom) ld8<float>(a.mom + (e - so), m);
@@ -373,7 +337,7 @@ fused_kernel(const Args a) {
         for (int j = 0; j < 8; ++j) sgd_step(w[j], g[j], m[j], h, lr, wd);
         if (a.has_mom) st8<float>(a.mom + (e - so), m);
       } else if (mode == kAdam) {
-        if (skip) continue;
+        if (skip) break;
         AdamHyper h{h_lr, h_wd, a.beta1, a.beta2, a.eps, h_rescale, h_clip};
         float m[8], vv[8];
         ld8<float>(a.mom + (e - so), m);
@@ -416,9 +380,9 @@ fused_kernel(const Args a) {
           atomicAdd(rn2 + t, arr);
         }
         __syncthreads();
-        continue;
+        break;
       } else if (mode == kLambPhase2) {
-        if (skip) continue;
+        if (skip) break;
         float wn = sqrtf(__ldcg(wn2 + t)), rn = sqrtf(__ldcg(rn2 + t));
         if (a.lamb_lower >= 0.f) wn = fmaxf(wn, a.lamb_lower);
         if (a.lamb_upper >= 0.f) wn = fminf(wn, a.lamb_upper);
@@ -428,11 +392,113 @@ fused_kernel(const Args a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) w[j] -= lr * ratio * r[j];
       } else if (mode == kBroadcast) {
-        if (skip) continue;
+        if (skip) break;
       }
       // write back master + fan the low-precision weights out to every replica
       if (a.w32 != nullptr) st8<float>(a.w32 + (e - so), w);
       fan(e, w);
+        } while (0);
+  };
+
+  // Gradient of one vector through the selected data path.
+  auto gather = [&](const Meta& mm, float (&g)[8]) {
+    const int64_t e = mm.e;
+    if (ll) {
+      // 8 elements = 4 packet pairs per source; spin until every packet carries this launch's flag; sum in RANK order so
+      // that all replicas compute bit-identical results
+      const uint2* mine = a.ll_recv[a.rank] + ll_base;
+      bool ok = true;
+#pragma unroll
+      for (int q = 0; q < (NR > 0 ? NR : kMaxRanks); ++q) {
+        if (q < nr) {
+          const uint4* src = reinterpret_cast<const uint4*>(mine + (int64_t)q * a.n + e);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            uint32_t spins = 0;
+            do {
+              asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "l"(src + j) : "memory");
+              if (++spins > kSpinLimit) { ok = false; break; }
+            } while (pk.y != ll_flag || pk.w != ll_flag);
+            g[2 * j] += __uint_as_float(pk.x);
+            g[2 * j + 1] += __uint_as_float(pk.z);
+          }
+        }
+      }
+      if (!ok && a.err) atomicExch(a.err, 1 + a.rank);
+    } else if (mc_grads) {
+      // the switch sums the N copies: one load per 16 bytes instead of N
+      mc_ld_reduce8<GT>(reinterpret_cast<const GT*>(a.grads_mc) + e, g);
+    } else {
+      // own copy first, then peers in a rank-rotated order to spread link load
+#pragma unroll
+      for (int k = 0; k < (NR > 0 ? NR : kMaxRanks); ++k) {
+        if (k < nr) {
+          const int p = (a.rank + k) % nr;
+          float x[8];
+          ld8<GT>(reinterpret_cast<const GT*>(a.grads[p]) + e, x);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += x[j];
+        }
+      }
+    }
+  };
+
+  // One sweep over the owned slice.  Block-uniform trip count (LAMB phase 1 has __syncthreads inside); base is a multiple of
+  // 128 vectors, so every group of 128 consecutive threads works on exactly one 1024-element chunk (= one tensor).
+  // Bandwidth-bound modes process kU vectors per thread and iteration with all their remote loads issued before the first
+  // use: a peer load takes ~2-3 us over NVLink, one vector per iteration left the links latency-bound (0.29 of the link
+  // roofline at 1 GB, profiles/bandwidth_sweep_n8_r2_call57.json).
+  constexpr int kU = 4;
+  auto sweep = [&](const int mode, float* wn2, float* rn2) {
+    const bool needs_grad = mode != kLambPhase2 && mode != kBroadcast;
+    const int64_t G = (int64_t)gridDim.x * kThreads;
+    int64_t base = v_begin + (int64_t)blockIdx.x * kThreads;
+    if (!ll && a.pad0 != 0 && (mode == kAllreduce || mode == kSgd || mode == kAdam)) {
+      for (; base < v_end; base += kU * G) {
+        Meta mm[kU];
+        float g[kU][8];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          mm[u] = meta_of(base + u * G + threadIdx.x);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[u][j] = 0.f;
+        }
+        if (mc_grads) {
+#pragma unroll
+          for (int u = 0; u < kU; ++u)
+            if (!mm[u].skip) mc_ld_reduce8<GT>(reinterpret_cast<const GT*>(a.grads_mc) + mm[u].e, g[u]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < (NR > 0 ? NR : kMaxRanks); ++k) {
+            if (k < nr) {
+              const GT* src = reinterpret_cast<const GT*>(a.grads[(a.rank + k) % nr]);
+              float x[kU][8];
+#pragma unroll
+              for (int u = 0; u < kU; ++u) {
+                if (!mm[u].skip) ld8<GT>(src + mm[u].e, x[u]);
+                else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) x[u][j] = 0.f;
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < kU; ++u)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[u][j] += x[u][j];
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) process(mode, mm[u], g[u], wn2, rn2);
+      }
+      return;
+    }
+    for (; base < v_end; base += G) {
+      const Meta mm = meta_of(base + threadIdx.x);
+      float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (!mm.skip && needs_grad) gather(mm, g);
+      process(mode, mm, g, wn2, rn2);
     }
   };
 

@@ -376,11 +376,13 @@ class Trainer(object):
 
     def _allreduce_grads(self):
         if self._kvstore:
-            for i, param in enumerate(self._params):
-                if param.grad_req != "null":
-                    self._kvstore.push(i, param.list_grad(), priority=-i)
-                    if not self._update_on_kvstore:
-                        self._kvstore.pull(i, param.list_grad(), priority=-i, ignore_sparse=False)
+            live = [(i, param) for i, param in enumerate(self._params) if param.grad_req != "null"]
+            for i, param in live:
+                self._kvstore.push(i, param.list_grad(), priority=-i)
+            if not self._update_on_kvstore:
+                # all pushes first: a multi-GPU device store then reduces every key in ONE bucketed fused launch per GPU
+                for i, param in live:
+                    self._kvstore.pull(i, param.list_grad(), priority=-i, ignore_sparse=False)
 
     def update(self, batch_size, ignore_stale_grad=False):
         if not self._kv_initialized:

@@ -384,8 +384,8 @@ class KVStoreLocal(KVStore):
                         break
                     if all(d.dtype is s_.dtype and d.shape == s_.shape for d, s_ in pairs):
                         with torch.no_grad():
-                            for d, s_ in pairs:
-                                d.copy_(s_, non_blocking=True)
+                            # one call for all GPUs: the multi-tensor copy groups its operands by device itself
+                            torch._foreach_copy_([d for d, _ in pairs], [s_ for _, s_ in pairs], non_blocking=True)
                         return
                     break
         keys, outs = _key_value_lists(key, out)

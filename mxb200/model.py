@@ -69,13 +69,14 @@ def _store_aux_params_on_kvstore(aux_arrays, kvstore, aux_names):
 
 
 def _update_params_on_kvstore(param_arrays, grad_arrays, kvstore, param_names, aux_arrays=None, aux_names=None):
-    for index, pair in enumerate(zip(param_arrays, grad_arrays)):
-        arg_list, grad_list = pair
-        if grad_list[0] is None:
-            continue
-        name = param_names[index]
-        kvstore.push(name, grad_list, priority=-index)
-        kvstore.pull(name, arg_list, priority=-index)
+    """push every gradient, then pull every weight (model.py:136-152).  The reference interleaves push / pull per key and
+    relies on its engine to run them asynchronously; issuing all pushes first is the same dataflow and lets the device
+    store reduce ALL keys in one bucketed launch of the fused kernel (kvstore/fused_local.py)."""
+    live = [(index, pair) for index, pair in enumerate(zip(param_arrays, grad_arrays)) if pair[1][0] is not None]
+    for index, (arg_list, grad_list) in live:
+        kvstore.push(param_names[index], grad_list, priority=-index)
+    for index, (arg_list, grad_list) in live:
+        kvstore.pull(param_names[index], arg_list, priority=-index)
 
 
 def _update_params_on_kvstore_nccl(param_arrays, grad_arrays, kvstore, param_names):
@@ -93,15 +94,14 @@ def _update_params_on_kvstore_nccl(param_arrays, grad_arrays, kvstore, param_nam
 
 
 def _update_params(param_arrays, grad_arrays, updater, num_device, kvstore=None, param_names=None):
-    for i, pair in enumerate(zip(param_arrays, grad_arrays)):
-        arg_list, grad_list = pair
-        if grad_list[0] is None:
-            continue
-        index = i
-        if kvstore:
-            name = param_names[index]
-            kvstore.push(name, grad_list, priority=-index)
-            kvstore.pull(name, grad_list, priority=-index)
+    live = [(i, pair) for i, pair in enumerate(zip(param_arrays, grad_arrays)) if pair[1][0] is not None]
+    if kvstore:
+        # all pushes, then all pulls: one bucketed reduction for the whole parameter set (see _update_params_on_kvstore)
+        for index, (arg_list, grad_list) in live:
+            kvstore.push(param_names[index], grad_list, priority=-index)
+        for index, (arg_list, grad_list) in live:
+            kvstore.pull(param_names[index], grad_list, priority=-index)
+    for index, (arg_list, grad_list) in live:
         for k, p in enumerate(zip(arg_list, grad_list)):
             w, g = p
             updater(index * num_device + k, g, w)

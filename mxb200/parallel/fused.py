@@ -18,6 +18,7 @@ from .peer import MAX_RANKS
 c_void_p, c_int, c_int64, c_float, c_uint32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_uint32
 
 LAUNCHES = [0]
+_UNROLL = [None]
 
 MODE_ALLREDUCE, MODE_SGD, MODE_ADAM, MODE_LAMB1, MODE_LAMB2, MODE_BCAST, MODE_LAMB = 0, 1, 2, 3, 4, 5, 6
 
@@ -179,7 +180,7 @@ class SymmetricArena(object):
 
 def fused_step(arena, mode, lr=0.0, wd=0.0, momentum=0.0, rescale=1.0, clip=None, nesterov=False, multi_precision=True,
                zero_grad=True, beta1=0.9, beta2=0.999, eps=1e-8, bc1=1.0, bc2=1.0, lamb_lower=-1.0, lamb_upper=-1.0,
-               one_shot=None, blocks=0, seq=None, hyper=None, nvls=None, ll=None):
+               one_shot=None, blocks=0, seq=None, hyper=None, nvls=None, ll=None, unroll=None):
     """Launch the fused kernel for one arena on this rank's current stream.
 
     ``hyper``: fp32 device tensor of HYPER_FLOATS entries (``pack_hyper``) that the kernel reads lr / wd / momentum /
@@ -188,6 +189,9 @@ def fused_step(arena, mode, lr=0.0, wd=0.0, momentum=0.0, rescale=1.0, clip=None
     g = arena.group
     lib = g.lib
     _check_abi(lib)
+    if _UNROLL[0] is None:
+        from ..base import getenv
+        _UNROLL[0] = int(getenv("MXB200_AR_UNROLL", 0))
     a = _Args()
     for r in range(g.world):
         a.grads[r] = arena.g_ptrs[r]
@@ -213,9 +217,13 @@ def fused_step(arena, mode, lr=0.0, wd=0.0, momentum=0.0, rescale=1.0, clip=None
         for r in range(g.world):
             a.ll_recv[r] = arena.ll_bufs[1][r]
         a.ll_ctr = arena.ll_ctr.data_ptr()
-    if g.world > 1 and nvls is not False and arena.g_mc and mode not in (MODE_LAMB2, MODE_BCAST):
+    # data path: in-switch reduction pays off with many ranks and mid-size messages (measured, tools/bandwidth/sweep.py:
+    # N=8: NVLS wins from 256 KB to 256 MB; N=2/4: the unicast peer loads are as fast or faster); nvls=True/False forces it
+    gbytes = arena.n * arena.grads.element_size()
+    use_nvls = nvls if nvls is not None else (g.world >= 8 and (256 << 10) <= gbytes <= (512 << 20))
+    if g.world > 1 and use_nvls and arena.g_mc and mode not in (MODE_LAMB2, MODE_BCAST):
         a.grads_mc = arena.g_mc
-    if g.world > 1 and nvls is not False and arena.w_mc:
+    if g.world > 1 and use_nvls and arena.w_mc:
         a.weights_mc = arena.w_mc
     a.g_dt, a.w_dt = code(arena.gdtype), code(arena.wdtype)
     if hyper is not None:
@@ -237,6 +245,7 @@ def fused_step(arena, mode, lr=0.0, wd=0.0, momentum=0.0, rescale=1.0, clip=None
     a.beta1, a.beta2, a.eps, a.bc1, a.bc2 = beta1, beta2, eps, bc1, bc2
     a.lamb_lower, a.lamb_upper = lamb_lower, lamb_upper
     a.chunk_tid = arena.chunk_tid.data_ptr()
+    a.pad0 = int(_UNROLL[0] if unroll is None else unroll)
     a.lr_mult = arena.lr_mult.data_ptr()
     a.wd_mult = arena.wd_mult.data_ptr()
     a.err = g.err_dev.value

@@ -59,6 +59,12 @@ class DeviceTrainer(object):
                 self.grad_sinks[n] = g
                 if g.dtype == v.dtype:
                     v.grad = g                      # autograd accumulates in place into the arena
+
+                    def _touch(grad, sink=g):       # runs BEFORE the accumulation: 'write' semantics per backward pass
+                        from ..ops.functional import sink_touch
+                        sink_touch(sink)
+                        return grad
+                    self._hooks.append(v.register_hook(_touch))
                 else:
                     # low-precision parameter, fp32 arena: ops that know about sinks write there directly; for
                     # everything else (library convolutions) the freshly produced gradient is folded in here

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--out", default="")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph (device-side latency) measurements")
+    ap.add_argument("--unroll", type=int, default=None, help="1: four vectors per thread and iteration in the fused kernel")
     args = ap.parse_args()
     rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", lrank)
@@ -123,7 +124,7 @@ def main():
             if one and size > (8 << 20):
                 continue                      # one-shot moves (n-1) x S per rank: pointless for large messages
             def run(nv=nv, one=one, ll=ll):
-                fused.fused_step(ar, fused.MODE_ALLREDUCE, rescale=1.0, one_shot=one, zero_grad=False, nvls=nv, ll=ll)
+                fused.fused_step(ar, fused.MODE_ALLREDUCE, rescale=1.0, one_shot=one, zero_grad=False, nvls=nv, ll=ll, unroll=args.unroll)
             run()
             torch.cuda.synchronize()
             err = ((ar.weights - ref).abs().max() / (ref.abs().max() + 1e-12)).item()
