@@ -13,6 +13,8 @@
 #   * patches under baseline/patches/*.patch are compile fixes for CUDA 12 / gcc 13, applied to the COPY and listed in
 #     DESIGN.md (01: `cuda::Reduce1D` -> `mshadow::cuda::Reduce1D`, ambiguous with libcu++'s global ::cuda namespace)
 #     (02: `#include <unistd.h>` for the getpid() call the fork added to kvstore_local.h)
+#     (03: one more `cuda::Reduce1D`; random/sampler.h's file-scope `using namespace mshadow` moved inside
+#          namespace mxnet::op -- at file scope it makes `cuda::` ambiguous in nvcc's generated host stubs)
 #   * `--pre-include cub/cub.cuh` (nvcc) parses the toolkit's cub before any `using namespace mshadow`
 set -u
 JOBS=${1:-6}
@@ -37,6 +39,9 @@ fi
 #   3rdparty/dmlc-core/src/data/ (parsers) -> LibSVMIter / CSVIter and dmlc-core's data.o
 rm -f "$WORK"/src/operator/nn/ctc_loss.cc "$WORK"/src/operator/nn/ctc_loss.cu "$WORK"/src/operator/contrib/ctc_loss.cc "$WORK"/src/operator/contrib/ctc_loss.cu
 rm -f "$WORK"/src/io/iter_libsvm.cc "$WORK"/src/io/iter_csv.cc
+#   quantized_conv.cu is a cuDNN-only operator (its whole body is `#if MXNET_USE_CUDNN`); with USE_CUDNN=0 it only
+#   registers a LOG(FATAL) stub, and its host stub does not compile against the CUDA-12 libcu++ -> left out
+rm -f "$WORK"/src/operator/quantization/quantized_conv.cu
 sed -i 's/ data.o recordio.o/ recordio.o/' "$WORK/3rdparty/dmlc-core/Makefile"
 cd "$WORK" || exit 1
 

@@ -264,16 +264,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   };
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp walks the loop, the elected lane issues: see the MMA warp) =====================
+    {
+      const bool issuer = ptx::elect_one();
       int stage = 0;
       uint32_t phase = 0;
       auto load = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+        if (!issuer) return;
         if constexpr (CTAS == 2) ptx::tma_load_2d_2sm(dst, tm, bar, c0, c1);   // bytes credited to the leader's barrier
         else ptx::tma_load_2d(dst, tm, bar, c0, c1);
       };
       auto load_im2col = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, int c, int wq, int hp, int n, int tap) {
         const uint16_t ow = (uint16_t)p.conv.off_w[tap], oh = (uint16_t)p.conv.off_h[tap];
+        if (!issuer) return;
         if constexpr (CTAS == 2) ptx::tma_load_im2col_4d_2sm(dst, tm, bar, c, wq, hp, n, ow, oh);
         else ptx::tma_load_im2col_4d(dst, tm, bar, c, wq, hp, n, ow, oh);
       };
@@ -295,20 +298,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int cc = (ka - (int)fr * p.conv.cpt) * BLOCK_K;
             const int t0 = (int)fr * p.conv.kw;
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], kABytes);
-            ptx::tma_load_im2col_4d(smem_a + stage * kABytes, &tmA, &full_bar[stage], cc, a_w, a_h, (int)img, (uint16_t)0,
+            if (issuer) ptx::mbar_arrive_expect_tx(&full_bar[stage], kABytes);
+            if (issuer) ptx::tma_load_im2col_4d(smem_a + stage * kABytes, &tmA, &full_bar[stage], cc, a_w, a_h, (int)img, (uint16_t)0,
                                     (uint16_t)p.conv.off_h[t0]);
             for (int sx = 0; sx < p.conv.kw; ++sx) {
               const int wt = (int)p.conv.wtap[t0 + sx];
               ptx::mbar_wait(&bempty_bar[bstage], bphase ^ 1);
-              ptx::mbar_arrive_expect_tx(&bfull_bar[bstage], kBBytes);
+              if (issuer) ptx::mbar_arrive_expect_tx(&bfull_bar[bstage], kBBytes);
               uint8_t* b_dst = smem_b + bstage * kBBytes;
               if constexpr (B_MN) {
 #pragma unroll
                 for (int c = 0; c < BN / 64; ++c)
-                  ptx::tma_load_2d(b_dst + c * (BLOCK_K * 128), &tmB, &bfull_bar[bstage], wt * p.conv.out_per_tap + n0 + c * 64, cc);
+                  if (issuer) ptx::tma_load_2d(b_dst + c * (BLOCK_K * 128), &tmB, &bfull_bar[bstage], wt * p.conv.out_per_tap + n0 + c * 64, cc);
               } else {
-                ptx::tma_load_2d(b_dst, &tmB, &bfull_bar[bstage], wt * p.conv.red_per_tap + cc, n0);
+                if (issuer) ptx::tma_load_2d(b_dst, &tmB, &bfull_bar[bstage], wt * p.conv.red_per_tap + cc, n0);
               }
               if (++bstage == kBStages) {
                 bstage = 0;
@@ -339,7 +342,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], CTAS * S::kStageBytes);
+          if (is_leader && issuer) ptx::mbar_arrive_expect_tx(&full_bar[stage], CTAS * S::kStageBytes);
           uint8_t* a_dst = smem_a + stage * kABytes;
           uint8_t* b_dst = smem_b + stage * kBBytes;
           if constexpr (CONV == 1) {
@@ -396,8 +399,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0 && is_leader) {
+    // ===================== MMA issuer =====================
+    // The whole warp walks the loop (barrier waits, stage / phase bookkeeping) so every operand is provably warp-uniform
+    // and lives in uniform registers; only the elected lane issues tcgen05.mma / tcgen05.commit.  (A loop entered by
+    // lane 0 alone keeps the descriptors in vector registers: ~30 SASS instructions incl. five R2UR per MMA.)
+    if (is_leader) {
+      const bool issuer = ptx::elect_one();
       constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, BN, true, A_MN, B_MN);
       // K-major: rows of 128B, 8-row groups 1024B apart (SBO); LBO unused (encoded as 16B).
       // MN-major: 64-element MN chunks LBO apart, 8-deep k groups 1024B apart (SBO).
@@ -439,21 +446,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                 uint64_t adesc = ptx::make_smem_desc(a_addr + shift * 128u + k * kstep_a, lbo_a, sbo_a, p.conv.ph ? shift : 0u);
                 uint64_t bdesc = ptx::make_smem_desc(b_addr + k * kstep_b, lbo_b, sbo_b);
-                ptx::umma_f16(tmem_d, adesc, bdesc, idesc, (ka > 0 || sx > 0 || k > 0) ? 1u : 0u);
+                if (issuer) ptx::umma_f16(tmem_d, adesc, bdesc, idesc, (ka > 0 || sx > 0 || k > 0) ? 1u : 0u);
               }
-              ptx::umma_commit(&bempty_bar[bstage]);
+              if (issuer) ptx::umma_commit(&bempty_bar[bstage]);
               if (++bstage == kBStages) {
                 bstage = 0;
                 bphase ^= 1;
               }
             }
-            ptx::umma_commit(&empty_bar[stage]);
+            if (issuer) ptx::umma_commit(&empty_bar[stage]);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
             }
           }
-          ptx::umma_commit(&tmem_full[buf]);
+          if (issuer) ptx::umma_commit(&tmem_full[buf]);
           continue;
         }
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -461,24 +468,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(smem_a + stage * kABytes);
           const uint32_t b_addr = ptx::smem_u32(smem_b + stage * kBBytes);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            uint64_t adesc = ptx::make_smem_desc(a_addr + k * kstep_a, lbo_a, sbo_a);
-            uint64_t bdesc = ptx::make_smem_desc(b_addr + k * kstep_b, lbo_b, sbo_b);
-            if constexpr (CTAS == 2) ptx::umma_f16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else ptx::umma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              uint64_t adesc = ptx::make_smem_desc(a_addr + k * kstep_a, lbo_a, sbo_a);
+              uint64_t bdesc = ptx::make_smem_desc(b_addr + k * kstep_b, lbo_b, sbo_b);
+              if constexpr (CTAS == 2) ptx::umma_f16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else ptx::umma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+            if constexpr (CTAS == 2) ptx::umma_commit_2sm(&empty_bar[stage], 3);
+            else ptx::umma_commit(&empty_bar[stage]);
           }
-          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-          if constexpr (CTAS == 2) ptx::umma_commit_2sm(&empty_bar[stage], 3);
-          else ptx::umma_commit(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
         // accumulator ready for the epilogue (of both CTAs)
-        if constexpr (CTAS == 2) ptx::umma_commit_2sm(&tmem_full[buf], 3);
-        else ptx::umma_commit(&tmem_full[buf]);
+        if (issuer) {
+          if constexpr (CTAS == 2) ptx::umma_commit_2sm(&tmem_full[buf], 3);
+          else ptx::umma_commit(&tmem_full[buf]);
+        }
       }
     }
   } else if (warp >= 4) {

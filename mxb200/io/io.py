@@ -524,9 +524,32 @@ def LibSVMIter(data_libsvm, data_shape, label_libsvm=None, label_shape=(1,), bat
 def ImageRecordIter(path_imgrec, data_shape, batch_size, path_imgidx=None, label_width=1, shuffle=False, num_parts=1,
                     part_index=0, rand_crop=False, rand_mirror=False, mean_r=0.0, mean_g=0.0, mean_b=0.0, std_r=1.0,
                     std_g=1.0, std_b=1.0, resize=0, preprocess_threads=4, prefetch_buffer=4, dtype="float32",
-                    data_name="data", label_name="softmax_label", **kwargs):
-    """RecordIO image pipeline (src/io/iter_image_recordio_2.cc): native chunk reader + threaded decode/augment
-    + prefetch; see mxb200/io/native.py for the C++ reader."""
+                    data_name="data", label_name="softmax_label", ctx=None, layout="NCHW", random_resized_crop=False,
+                    min_random_area=1.0, max_random_area=1.0, min_aspect_ratio=None, max_aspect_ratio=0.0, seed=0,
+                    round_batch=True, **kwargs):
+    """RecordIO image pipeline (src/io/iter_image_recordio_2.cc).
+
+    ``ctx=mx.gpu(i)`` (or ``MXB200_GPU_DECODE=1`` with a visible GPU) selects the device pipeline
+    (``io/gpu_pipeline.py``: C++ loader threads, nvJPEG batched decode, fused augmentation kernel; batches are born on
+    the GPU in ``layout`` / ``dtype``).  Otherwise batches are produced in host memory by the threaded OpenCV pipeline of
+    ``io/native.py`` exactly like the reference's iterator."""
+    from ..base import getenv
+    use_gpu = ctx is not None and getattr(ctx, "device_type", "cpu") == "gpu"
+    if ctx is None and getenv("MXB200_GPU_DECODE", False):
+        import torch
+        if torch.cuda.is_available():
+            from ..context import gpu
+            ctx, use_gpu = gpu(0), True
+    if use_gpu:
+        from .gpu_pipeline import GPUImageRecordIter
+        return GPUImageRecordIter(path_imgrec, data_shape, batch_size, path_imgidx=path_imgidx, label_width=label_width,
+                                  shuffle=shuffle, num_parts=num_parts, part_index=part_index, rand_crop=rand_crop,
+                                  rand_mirror=rand_mirror, random_resized_crop=random_resized_crop,
+                                  min_random_area=min_random_area, max_random_area=max_random_area,
+                                  min_aspect_ratio=min_aspect_ratio, max_aspect_ratio=max_aspect_ratio,
+                                  mean=(mean_r, mean_g, mean_b), std=(std_r, std_g, std_b), resize=resize,
+                                  threads=preprocess_threads, prefetch=prefetch_buffer, dtype=dtype, layout=layout, ctx=ctx,
+                                  seed=seed, round_batch=round_batch, data_name=data_name, label_name=label_name)
     from .native import ImageRecordIterImpl
     return ImageRecordIterImpl(path_imgrec, data_shape, batch_size, path_imgidx=path_imgidx, label_width=label_width,
                                shuffle=shuffle, num_parts=num_parts, part_index=part_index, rand_crop=rand_crop,

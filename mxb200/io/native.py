@@ -1,7 +1,8 @@
-"""ImageRecordIter implementation: RecordIO reader -> thread-pool JPEG decode + augment -> batch assembly ->
-prefetch queue (reference pipeline: src/io/iter_image_recordio_2.cc, image_aug_default.cc, iter_batchloader.h,
-iter_prefetcher.h).  Decode runs in OpenCV (GIL released), batches are assembled into pinned host memory so
-the device copy can be asynchronous."""
+"""Host-memory ImageRecordIter: native mmap RecordIO reader (csrc/host/recordio.cc) -> thread-pool JPEG decode + augment
+-> batch assembly -> prefetch queue (reference pipeline: src/io/iter_image_recordio_2.cc, image_aug_default.cc,
+iter_batchloader.h, iter_prefetcher.h).  Decode runs in OpenCV (GIL released), batches are assembled into pinned host
+memory so the device copy can be asynchronous.  The device-side pipeline (nvJPEG + fused augmentation kernel) is
+io/gpu_pipeline.py; ``mx.io.ImageRecordIter(ctx=mx.gpu(i))`` selects it."""
 import concurrent.futures as cf
 import queue
 import random
@@ -26,7 +27,13 @@ class ImageRecordIterImpl(DataIter):
         self.mean = np.asarray(mean, np.float32).reshape(3, 1, 1)
         self.std = np.asarray(std, np.float32).reshape(3, 1, 1)
         self.dtype = dtype
-        self.records = self._index(path_imgrec, path_imgidx)
+        try:
+            from .gpu_pipeline import RecordFile
+            self._rf = RecordFile(path_imgrec, path_imgidx)
+            self.records = list(range(len(self._rf)))
+        except Exception:  # noqa: BLE001  (host library unavailable: python scan)
+            self._rf = None
+            self.records = self._index(path_imgrec, path_imgidx)
         n = len(self.records) // num_parts
         self.records = self.records[part_index * n:(part_index + 1) * n]
         self.path = path_imgrec
@@ -86,7 +93,7 @@ class ImageRecordIterImpl(DataIter):
         return a, header.label
 
     def _producer(self, order):
-        f = recordio.MXRecordIO(self.path, "r")
+        f = recordio.MXRecordIO(self.path, "r") if self._rf is None else None
         bs = self.batch_size
         try:
             for b0 in range(0, len(order), bs):
@@ -95,6 +102,9 @@ class ImageRecordIterImpl(DataIter):
                 idx = order[b0:b0 + bs]
                 raws = []
                 for off in idx:
+                    if f is None:
+                        raws.append(self._rf.read(off))
+                        continue
                     f.handle.seek(off)
                     raws.append(f.read())
                 outs = list(self.pool.map(self._decode, raws))
@@ -110,7 +120,8 @@ class ImageRecordIterImpl(DataIter):
                 self._q.put(DataBatch([NDArray(data)], [NDArray(label)], pad=pad, provide_data=self.provide_data,
                                       provide_label=self.provide_label))
         finally:
-            f.close()
+            if f is not None:
+                f.close()
             self._q.put(None)
 
     def reset(self):
