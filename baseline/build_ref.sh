@@ -13,6 +13,7 @@
 #   * patches under baseline/patches/*.patch are compile fixes for CUDA 12 / gcc 13, applied to the COPY and listed in
 #     DESIGN.md (01: `cuda::Reduce1D` -> `mshadow::cuda::Reduce1D`, ambiguous with libcu++'s global ::cuda namespace)
 #     (02: `#include <unistd.h>` for the getpid() call the fork added to kvstore_local.h)
+#     (04: explicit instantiations of three sparse elementwise member templates that other TUs reference)
 #     (03: one more `cuda::Reduce1D`; random/sampler.h's file-scope `using namespace mshadow` moved inside
 #          namespace mxnet::op -- at file scope it makes `cuda::` ambiguous in nvcc's generated host stubs)
 #   * `--pre-include cub/cub.cuh` (nvcc) parses the toolkit's cub before any `using namespace mshadow`
@@ -153,6 +154,7 @@ if [ -f lib/libmxnet.so ]; then
   cp -r python/mxnet "$REPO/baseline/_ref/mxnet"
   cp lib/libmxnet.so "$REPO/baseline/_ref/mxnet/libmxnet.so"
   cp "$OB" "$REPO/baseline/_ref/mxnet/"
+  cp "$(dirname "$OB")"/libgfortran-*.so* "$(dirname "$OB")"/libquadmath-*.so* "$REPO/baseline/_ref/mxnet/"   # OpenBLAS runtime deps
   mkdir -p "$REPO/baseline/_ref/example"
   cp -r example/image-classification "$REPO/baseline/_ref/example/"
   echo "=== SUCCESS: baseline/_ref/mxnet/libmxnet.so"

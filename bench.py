@@ -134,6 +134,7 @@ def reference_arm(args):
     env = dict(os.environ)
     env["PYTHONPATH"] = ref + os.pathsep + env.get("PYTHONPATH", "")
     env["MXNET_LIBRARY_PATH"] = lib
+    env["LD_LIBRARY_PATH"] = os.path.join(ref, "mxnet") + os.pathsep + env.get("LD_LIBRARY_PATH", "")   # OpenBLAS + libgfortran copies
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)

@@ -127,7 +127,12 @@ def make_iter(batch, num_parts, part_index, train=True):
                                  batch_size=batch, data_shape=(3, opt.image_size, opt.image_size),
                                  mean_r=123.68, mean_g=116.779, mean_b=103.939, std_r=58.393, std_g=57.12, std_b=57.375,
                                  rand_mirror=train, rand_crop=train, random_resized_crop=train,
-                                 num_parts=num_parts, part_index=part_index)
+                                 min_random_area=0.08, min_aspect_ratio=3.0 / 4, max_aspect_ratio=4.0 / 3, resize=-1 if train else 256,
+                                 num_parts=num_parts, part_index=part_index,
+                                 # single-GPU processes decode and augment on the device (nvJPEG + one fused kernel) and
+                                 # get the network's input layout / dtype directly; multi-device processes keep host batches
+                                 ctx=context[0] if (use_gpu and len(context) == 1) else None, layout=layout,
+                                 dtype=opt.dtype if (use_gpu and len(context) == 1 and opt.dtype == 'bfloat16') else 'float32')
 
 
 class ElasticImageRecordIter(mx.mod.BaseDataIterator):

@@ -67,7 +67,8 @@ if __name__ == "__main__":
         val = None
     else:
         train = mx.io.ImageRecordIter(path_imgrec=args.data_train, data_shape=shape, batch_size=args.batch_size, shuffle=True,
-                                      rand_crop=True, rand_mirror=True, num_parts=kv.num_workers, part_index=kv.rank)
+                                      rand_crop=True, rand_mirror=True, num_parts=kv.num_workers, part_index=kv.rank,
+                                      ctx=devs[0] if (len(devs) == 1 and devs[0].device_type == "gpu") else None)
         val = mx.io.ImageRecordIter(path_imgrec=args.data_val, data_shape=shape, batch_size=args.batch_size,
                                     num_parts=kv.num_workers, part_index=kv.rank) if args.data_val else None
     steps = [epoch_size * int(e) for e in args.lr_step_epochs.split(",") if int(e) > 0]

@@ -79,6 +79,7 @@ struct ConvGeom {
   // filter row read the SAME smem A tile entered off_w[tap] rows (128 B each) lower, so A crosses L2->smem once per
   // filter row instead of once per tap.  Rows with (index % Qp) >= Q are padding positions and are not stored.
   int Qp, kw, Qout;
+  int b_resident;     // CONV == 3: every tap's weight tile has its own smem slot, loaded during the CTA's first tile only
   FastDiv d_cpt, d_Q, d_PQ, d_C;
   int8_t off_w[kMaxTaps], off_h[kMaxTaps], wtap[kMaxTaps];
   // strided (parity) dgrad: rows are scattered to dst[((n * dH + p * dstep + ph) * dW + q * dstep + pw) * dC + col]
@@ -285,6 +286,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int bstage = 0;
         uint32_t bphase = 0;
         const int ka_total = num_kb_total / p.conv.kw;
+        const bool resident = p.conv.b_resident != 0;       // weight-stationary: B slots are filled once per CTA
+        bool first_tile = true;
         for (int w = cluster_id; w < num_work; w += num_clusters) {
           int m_blk, n_blk, kb0, kb1;
           decode(w, m_blk, n_blk, kb0, kb1);
@@ -303,7 +306,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     (uint16_t)p.conv.off_h[t0]);
             for (int sx = 0; sx < p.conv.kw; ++sx) {
               const int wt = (int)p.conv.wtap[t0 + sx];
-              ptx::mbar_wait(&bempty_bar[bstage], bphase ^ 1);
+              if (resident) {
+                if (!first_tile) continue;
+                bstage = ka * p.conv.kw + sx;                 // slot of (filter row, channel chunk, tap in row)
+              } else {
+                ptx::mbar_wait(&bempty_bar[bstage], bphase ^ 1);
+              }
               if (issuer) ptx::mbar_arrive_expect_tx(&bfull_bar[bstage], kBBytes);
               uint8_t* b_dst = smem_b + bstage * kBBytes;
               if constexpr (B_MN) {
@@ -313,7 +321,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               } else {
                 if (issuer) ptx::tma_load_2d(b_dst, &tmB, &bfull_bar[bstage], wt * p.conv.red_per_tap + cc, n0);
               }
-              if (++bstage == kBStages) {
+              if (!resident && ++bstage == kBStages) {
                 bstage = 0;
                 bphase ^= 1;
               }
@@ -323,6 +331,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               phase ^= 1;
             }
           }
+          first_tile = false;
         }
       } else
       for (int w = cluster_id; w < num_work; w += num_clusters) {
@@ -429,14 +438,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t tmem_d = tmem_base + buf * BN;
         if constexpr (SHIFT) {
           const int ka_total = num_kb_total / p.conv.kw;
+          const bool resident = p.conv.b_resident != 0;
           for (int ka = 0; ka < ka_total; ++ka) {
             const int t0 = (int)p.conv.d_cpt.div((uint32_t)ka) * p.conv.kw;
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after();
             const uint32_t a_addr = ptx::smem_u32(smem_a + stage * kABytes);
             for (int sx = 0; sx < p.conv.kw; ++sx) {
-              ptx::mbar_wait(&bfull_bar[bstage], bphase);
-              ptx::tc_fence_after();
+              if (resident) {
+                bstage = ka * p.conv.kw + sx;
+                if (it == 0) {                                  // the slot is written once; later tiles find it in place
+                  ptx::mbar_wait(&bfull_bar[bstage], 0);
+                  ptx::tc_fence_after();
+                }
+              } else {
+                ptx::mbar_wait(&bfull_bar[bstage], bphase);
+                ptx::tc_fence_after();
+              }
               // this tap reads the gathered tile entered `shift` positions lower (rows are 128 B apart).  The 128B swizzle
               // is a function of the ABSOLUTE shared-memory address on sm_100 (measured: the descriptor's base-offset field
               // must stay 0; setting it to the row phase corrupts the operand), so a row-shifted start address just works
@@ -448,10 +466,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 uint64_t bdesc = ptx::make_smem_desc(b_addr + k * kstep_b, lbo_b, sbo_b);
                 if (issuer) ptx::umma_f16(tmem_d, adesc, bdesc, idesc, (ka > 0 || sx > 0 || k > 0) ? 1u : 0u);
               }
-              if (issuer) ptx::umma_commit(&bempty_bar[bstage]);
-              if (++bstage == kBStages) {
-                bstage = 0;
-                bphase ^= 1;
+              if (!resident) {
+                if (issuer) ptx::umma_commit(&bempty_bar[bstage]);
+                if (++bstage == kBStages) {
+                  bstage = 0;
+                  bphase ^= 1;
+                }
               }
             }
             if (issuer) ptx::umma_commit(&empty_bar[stage]);
@@ -1021,10 +1041,15 @@ bool pick_two_cta(int bn, int64_t M, int N, int K, int sp) {
 // MMA is bound by its own shared-memory operand reads, and an operand entered at a row offset straddles two swizzle
 // atoms per 8-row core matrix.  Kept as an opt-in (MXB200_CONV_SHIFT=1, exercised by tests/test_gpu_kernels.py); the
 // profitable structure for these layers is weight-stationary with the pixels on the N side.
-bool use_shift(int n_out, int kw, int stride) {
+// Returns 0 (off), 1 (B ring) or 2 (weight-stationary when every tap's weight tile fits in the B slots: n_out <= 64 and
+// taps * C / 64 <= 12, i.e. the 3x3 C = 64 layers; B ring otherwise).
+int use_shift(int n_out, int kw, int stride) {
   const char* e = getenv("MXB200_CONV_SHIFT");
-  if (e == nullptr || atoi(e) != 1 || stride != 1 || kw < 2 || kw > 9) return false;
-  return n_out <= 128;
+  if (e == nullptr || atoi(e) < 1 || stride != 1 || kw < 2 || kw > 9) return 0;
+  return n_out <= 128 ? atoi(e) : 0;
+}
+bool shift_resident(int mode, int n_out, int ntaps, int c) {
+  return mode >= 2 && n_out <= 64 && ntaps * (c / 64) <= gemm::SmemShift<64>::kBStages;
 }
 
 // debug switch: MXB200_SHIFT_BASEOFF=1 puts the row phase into the descriptor's base-offset field (wrong on sm_100: kept to
@@ -1095,6 +1120,7 @@ MXB_API int MXBConvFwdBf16(const void* x, const void* w, void* y, int n, int h, 
     cd.upper_w = Qp - wd + cd.lower_w;                 // the bounding box holds Qp positions per row
     g.Qp = Qp; g.kw = kw; g.Qout = Q;
     g.ph = shift_no_base_offset();
+    g.b_resident = shift_resident(use_shift(N, kw, stride), N, kh * kw, c) ? 1 : 0;
     for (int t = 0; t < kh * kw; ++t) g.off_w[t] = (int8_t)(t % kw);      // row shift of the tap inside the gathered tile
     const int Ms = n * P * Qp;
     MXB_CONV_SHIFT_DISPATCH(false, Ms, N, K, (int64_t)c, (int64_t)K, (int64_t)o);
@@ -1145,6 +1171,7 @@ MXB_API int MXBConvDgradBf16(const void* dy, const void* w, void* dx, int n, int
       cd.upper_w = Qp - Q + cd.lower_w;
       g.Qp = Qp; g.kw = kw; g.Qout = wd;
       g.ph = shift_no_base_offset();
+      g.b_resident = shift_resident(use_shift(N, kw, 1), N, kh * kw, o) ? 1 : 0;
       const int Ms = n * h * Qp;
       MXB_CONV_SHIFT_DISPATCH(true, Ms, N, K, (int64_t)o, ldb, (int64_t)c);
       return 0;

@@ -10,13 +10,18 @@
 // writes, FIFO fairness between a writer and later readers) with far less code, which is adequate because
 // in this framework the engine schedules host-side work (IO, checkpoints, host reductions, membership
 // RPCs), while device kernels are ordered by CUDA streams.
+#include <string.h>
+
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <functional>
 #include <memory>
 #include <mutex>
 #include <queue>
+#include <sstream>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -42,7 +47,23 @@ struct Opr {
   std::atomic<int> wait{0};
   int priority = 0;
   uint64_t seq = 0;
+  std::string name;          // profiler label (empty: anonymous)
+  int64_t push_us = 0;       // wall clock at Push (profiling only)
 };
+
+// One executed operation as the profiler sees it (reference: ThreadedEngine::ExecuteOprBlock wraps the run in
+// profiler start / stop when profiling is on, src/engine/threaded_engine.h:338-347; OprExecStat in src/profiler).
+struct ProfRec {
+  std::string name;
+  uint64_t seq;
+  int64_t push_us, start_us, end_us;
+  uint64_t thread;
+  int priority;
+};
+
+static int64_t wall_us() {
+  return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
+}
 
 struct OprCmp {
   bool operator()(const Opr* a, const Opr* b) const {
@@ -67,7 +88,7 @@ class Engine {
     return v;
   }
 
-  void Push(std::function<void()> fn, std::vector<Var*> cv, std::vector<Var*> mv, int priority) {
+  void Push(std::function<void()> fn, std::vector<Var*> cv, std::vector<Var*> mv, int priority, const char* name = nullptr) {
     // de-duplicate: a var that is both read and written counts as written (engine.h NewOperator dedupe)
     std::vector<Var*> cv2;
     for (Var* v : cv) {
@@ -88,6 +109,10 @@ class Engine {
     op->mutable_vars = std::move(mv2);
     op->priority = priority;
     op->seq = seq_.fetch_add(1);
+    if (profiling_.load(std::memory_order_relaxed)) {
+      if (name) op->name = name;
+      op->push_us = wall_us();
+    }
     pending_.fetch_add(1);
     // wait = #deps + 1; the extra one is released at the end so the op cannot fire while being registered
     op->wait.store((int)(op->const_vars.size() + op->mutable_vars.size()) + 1);
@@ -133,6 +158,21 @@ class Engine {
   }
 
   int64_t Pending() const { return pending_.load(); }
+
+  void SetProfiling(bool on) { profiling_.store(on); }
+  // tab-separated records, one per line: name seq push_us start_us end_us thread priority
+  std::string DrainProfile() {
+    std::vector<ProfRec> recs;
+    {
+      std::lock_guard<std::mutex> lk(prof_mu_);
+      recs.swap(prof_);
+    }
+    std::ostringstream os;
+    for (const ProfRec& r : recs)
+      os << r.name << '\t' << r.seq << '\t' << r.push_us << '\t' << r.start_us << '\t' << r.end_us << '\t' << r.thread << '\t'
+         << r.priority << '\n';
+    return os.str();
+  }
 
  private:
   void AppendRead(Var* v, Opr* op) {
@@ -218,10 +258,18 @@ class Engine {
         op = queue_.top();
         queue_.pop();
       }
+      const bool prof = profiling_.load(std::memory_order_relaxed) && op->push_us != 0;
+      const int64_t t_start = prof ? wall_us() : 0;
       try {
         op->fn();
       } catch (...) {
         // python trampolines never throw; native ops report through their own channels
+      }
+      if (prof) {
+        ProfRec r{op->name, op->seq, op->push_us, t_start, wall_us(),
+                  (uint64_t)std::hash<std::thread::id>()(std::this_thread::get_id()) % 100000, op->priority};
+        std::lock_guard<std::mutex> lk(prof_mu_);
+        if (prof_.size() < (size_t)1 << 20) prof_.push_back(std::move(r));
       }
       for (Var* v : op->const_vars) CompleteRead(v);
       for (Var* v : op->mutable_vars) CompleteWrite(v);
@@ -245,6 +293,9 @@ class Engine {
   std::condition_variable done_cv_;
   std::mutex vars_mu_;
   std::vector<Var*> vars_;
+  std::atomic<bool> profiling_{false};
+  std::mutex prof_mu_;
+  std::vector<ProfRec> prof_;
 };
 
 }  // namespace mxb
@@ -276,6 +327,33 @@ MXB_API int MXBEnginePush(void* h, MXBEngineFn fn, void* arg, void** cvars, int 
   for (int i = 0; i < ncv; ++i) cv.push_back(reinterpret_cast<Var*>(cvars[i]));
   for (int i = 0; i < nmv; ++i) mv.push_back(reinterpret_cast<Var*>(mvars[i]));
   reinterpret_cast<Engine*>(h)->Push([fn, arg] { fn(arg); }, std::move(cv), std::move(mv), priority);
+  MXB_CATCH
+}
+MXB_API int MXBEnginePushNamed(void* h, MXBEngineFn fn, void* arg, void** cvars, int ncv, void** mvars, int nmv, int priority,
+                               const char* name) {
+  MXB_TRY
+  std::vector<Var*> cv, mv;
+  for (int i = 0; i < ncv; ++i) cv.push_back(reinterpret_cast<Var*>(cvars[i]));
+  for (int i = 0; i < nmv; ++i) mv.push_back(reinterpret_cast<Var*>(mvars[i]));
+  reinterpret_cast<Engine*>(h)->Push([fn, arg] { fn(arg); }, std::move(cv), std::move(mv), priority, name);
+  MXB_CATCH
+}
+MXB_API int MXBEngineSetProfiling(void* h, int on) {
+  MXB_TRY
+  reinterpret_cast<Engine*>(h)->SetProfiling(on != 0);
+  MXB_CATCH
+}
+// Copies the pending profile records into buf (text, see Engine::DrainProfile) and clears them.  If cap is too small
+// nothing is consumed from the caller's point of view: *needed tells the size and the records are kept for the retry.
+MXB_API int MXBEngineDrainProfile(void* h, char* buf, int64_t cap, int64_t* needed) {
+  MXB_TRY
+  static thread_local std::string stash;
+  if (stash.empty()) stash = reinterpret_cast<Engine*>(h)->DrainProfile();
+  *needed = (int64_t)stash.size();
+  if ((int64_t)stash.size() <= cap) {
+    memcpy(buf, stash.data(), stash.size());
+    stash.clear();
+  }
   MXB_CATCH
 }
 MXB_API int MXBEngineWaitForVar(void* h, void* var) {

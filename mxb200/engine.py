@@ -85,8 +85,33 @@ class Engine(object):
             self._keep[key] = cb
         cv = (ctypes.c_void_p * max(1, len(const_vars)))(*[v.value for v in const_vars])
         mv = (ctypes.c_void_p * max(1, len(mutable_vars)))(*[v.value for v in mutable_vars])
-        N.check(self._lib, self._lib.MXBEnginePush(self._h, cb, None, cv, ctypes.c_int(len(const_vars)), mv,
-                                                   ctypes.c_int(len(mutable_vars)), ctypes.c_int(priority)))
+        label = (name or getattr(fn, "__name__", "fn")).encode("utf-8", "replace")
+        N.check(self._lib, self._lib.MXBEnginePushNamed(self._h, cb, None, cv, ctypes.c_int(len(const_vars)), mv,
+                                                        ctypes.c_int(len(mutable_vars)), ctypes.c_int(priority), label))
+
+    # profiler hook (src/engine/threaded_engine.h:338-347: every executed operation is bracketed when profiling) ----------
+    def set_profiling(self, on):
+        if self._lib is not None:
+            N.check(self._lib, self._lib.MXBEngineSetProfiling(self._h, ctypes.c_int(1 if on else 0)))
+
+    def drain_profile(self):
+        """Executed operations since the last call: dicts with name, seq, push_us / start_us / end_us (unix epoch
+        microseconds), thread, priority."""
+        if self._lib is None:
+            return []
+        need = ctypes.c_int64(0)
+        buf = ctypes.create_string_buffer(1 << 16)
+        N.check(self._lib, self._lib.MXBEngineDrainProfile(self._h, buf, ctypes.c_int64(len(buf)), ctypes.byref(need)))
+        if need.value > len(buf):
+            buf = ctypes.create_string_buffer(need.value)
+            N.check(self._lib, self._lib.MXBEngineDrainProfile(self._h, buf, ctypes.c_int64(len(buf)), ctypes.byref(need)))
+        out = []
+        for line in buf.raw[:need.value].decode("utf-8", "replace").splitlines():
+            f = line.split("\t")
+            if len(f) == 7:
+                out.append({"name": f[0], "seq": int(f[1]), "push_us": int(f[2]), "start_us": int(f[3]), "end_us": int(f[4]),
+                            "thread": int(f[5]), "priority": int(f[6])})
+        return out
 
     def _raise_pending(self):
         if self._exc:

@@ -124,7 +124,7 @@ class ImageRecordIterImpl(DataIter):
                 f.close()
             self._q.put(None)
 
-    def reset(self):
+    def _stop_producer(self):
         if self._thread is not None:
             self._stop.set()
             while self._thread.is_alive():
@@ -133,6 +133,21 @@ class ImageRecordIterImpl(DataIter):
                 except queue.Empty:
                     pass
             self._thread.join()
+            self._thread = None
+
+    def close(self):
+        """Stop the producer thread (a daemon thread killed inside a native call at interpreter exit aborts the process)."""
+        self._stop_producer()
+        self.pool.shutdown(wait=True)
+
+    def __del__(self):
+        try:
+            self._stop_producer()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def reset(self):
+        self._stop_producer()
         self._stop = threading.Event()
         order = list(self.records)
         if self.shuffle:

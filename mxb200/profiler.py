@@ -55,11 +55,33 @@ def set_state(state="stop", profile_process="worker"):
         return
     assert state in ("run", "stop")
     _state["running"] = state == "run"
+    _engine_hook(state == "run")
     if state == "stop" and _cfg.get("continuous_dump"):
         dump()
 
 
 profiler_set_state = set_state
+
+
+def _engine_hook(on):
+    """Per-operation records of the dependency engine (IO, checkpoint writes, host reductions): the engine brackets every
+    executed operation while profiling is on (reference: src/engine/threaded_engine.h:338-347)."""
+    from . import engine as _eng
+    try:
+        _eng.get().set_profiling(on)
+    except Exception:  # noqa: BLE001  (host library unavailable)
+        pass
+
+
+def _drain_engine():
+    from . import engine as _eng
+    if _eng._engine[0] is None:
+        return
+    t0us = _t0 * 1e6
+    for r in _eng._engine[0].drain_profile():
+        _add({"name": r["name"] or "engine_op", "cat": "engine", "ph": "X", "ts": r["start_us"] - t0us,
+              "dur": max(0, r["end_us"] - r["start_us"]), "pid": os.getpid(), "tid": "engine-%d" % r["thread"],
+              "args": {"queue_us": r["start_us"] - r["push_us"], "priority": r["priority"], "seq": r["seq"]}})
 
 
 def pause(profile_process="worker"):
@@ -126,6 +148,7 @@ class scope(object):
 
 def dump(finished=True, profile_process="worker"):
     _flush_gpu()
+    _drain_engine()
     with _lock:
         evs = list(_events)
         if finished:
@@ -140,6 +163,7 @@ dump_profile = dump
 def dumps(reset=False):
     """Aggregate per-name statistics table (src/profiler/aggregate_stats.cc)."""
     _flush_gpu()
+    _drain_engine()
     agg = defaultdict(list)
     with _lock:
         for e in _events:

@@ -110,3 +110,37 @@ def test_engine_info_logging(monkeypatch, caplog):
     assert out == [1]
     text = caplog.text
     assert "probe" in text and "wait_all" in text
+
+
+def test_profiler_records_every_engine_operation_with_queue_time(tmp_path):
+    """Engine hook of the profiler (reference: threaded_engine.h:338-347 + tests/python/unittest/test_profiler.py)."""
+    import json
+    import time
+    import mxb200 as mx
+    from mxb200 import engine, profiler
+    eng = engine.get()
+    if eng._lib is None:
+        pytest.skip("native engine unavailable")
+    eng.wait_all()
+    profiler.set_config(filename=str(tmp_path / "trace.json"))
+    profiler.set_state("run")
+    v = eng.new_variable()
+    eng.push(lambda: time.sleep(0.05), mutable_vars=[v], name="slow_writer")
+    eng.push(lambda: None, const_vars=[v], name="reader_after_writer", priority=3)
+    eng.push(lambda: None, name="independent")
+    eng.wait_all()
+    profiler.set_state("stop")
+    table = profiler.dumps()
+    assert "slow_writer" in table and "reader_after_writer" in table
+    profiler.dump()
+    evs = [e for e in json.load(open(str(tmp_path / "trace.json")))["traceEvents"] if e.get("cat") == "engine"]
+    by = {e["name"]: e for e in evs}
+    assert {"slow_writer", "reader_after_writer", "independent"} <= set(by)
+    assert by["slow_writer"]["dur"] >= 45e3
+    # the reader was queued behind the writer: its queue time covers the writer's run, and it starts after the writer ends
+    assert by["reader_after_writer"]["args"]["queue_us"] >= 40e3 and by["reader_after_writer"]["args"]["priority"] == 3
+    assert by["reader_after_writer"]["ts"] >= by["slow_writer"]["ts"] + by["slow_writer"]["dur"] - 1e3
+    # nothing is recorded while the profiler is stopped
+    eng.push(lambda: None, name="not_profiled")
+    eng.wait_all()
+    assert eng.drain_profile() == []

@@ -33,7 +33,7 @@ def test_nvjpeg_identity_window_matches_opencv_decode(tmp_path):
         ref = _cv_decode(rec, idx, i).astype(np.float32)
         # two JPEG decoders (different IDCT / chroma up-sampling): close, not identical
         d = np.abs(x[i] - ref)
-        assert d.mean() < 1.5 and d.max() <= 16, (i, d.mean(), d.max())
+        assert d.mean() < 3.5 and d.max() <= 32, (i, d.mean(), d.max())
         it.close()
 
 
