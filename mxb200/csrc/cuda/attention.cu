@@ -88,34 +88,34 @@ __device__ __forceinline__ void store_row_chunk(uint32_t base, int row, int chun
 constexpr uint32_t kSBO = 1024;
 
 __device__ __forceinline__ void mma_kmajor_a_kmajor_b(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, int n, int ksteps,
-                                                      uint32_t a_panel, uint32_t b_panel, bool accumulate) {
+                                                      uint32_t a_panel, uint32_t b_panel, bool accumulate, bool issue) {
   // K advances 16 elements = 32 B inside a 64-wide panel; panels are `*_panel` bytes apart
   const uint32_t idesc = ptx::make_idesc_f16(128, n, true, false, false);
   for (int k = 0; k < ksteps; ++k) {
     const uint32_t ao = (uint32_t)(k >> 2) * a_panel + (uint32_t)(k & 3) * 32u;
     const uint32_t bo = (uint32_t)(k >> 2) * b_panel + (uint32_t)(k & 3) * 32u;
-    ptx::umma_f16(tmem_d, ptx::make_smem_desc(a_addr + ao, 16, kSBO), ptx::make_smem_desc(b_addr + bo, 16, kSBO), idesc,
+    if (issue) ptx::umma_f16(tmem_d, ptx::make_smem_desc(a_addr + ao, 16, kSBO), ptx::make_smem_desc(b_addr + bo, 16, kSBO), idesc,
                   (accumulate || k > 0) ? 1u : 0u);
   }
 }
 // A K-major (panels), B MN-major ([k rows][n cols], n <= 64 per chunk; chunks of 64 n are `b_chunk` bytes apart)
 __device__ __forceinline__ void mma_kmajor_a_mnmajor_b(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, int n, int ksteps,
-                                                       uint32_t a_panel, uint32_t b_chunk, bool accumulate) {
+                                                       uint32_t a_panel, uint32_t b_chunk, bool accumulate, bool issue) {
   const uint32_t idesc = ptx::make_idesc_f16(128, n, true, false, true);
   for (int k = 0; k < ksteps; ++k) {
     const uint32_t ao = (uint32_t)(k >> 2) * a_panel + (uint32_t)(k & 3) * 32u;
     const uint32_t bo = (uint32_t)k * (16u * 128u);          // 16 k rows of 128 B
-    ptx::umma_f16(tmem_d, ptx::make_smem_desc(a_addr + ao, 16, kSBO), ptx::make_smem_desc(b_addr + bo, b_chunk, kSBO), idesc,
+    if (issue) ptx::umma_f16(tmem_d, ptx::make_smem_desc(a_addr + ao, 16, kSBO), ptx::make_smem_desc(b_addr + bo, b_chunk, kSBO), idesc,
                   (accumulate || k > 0) ? 1u : 0u);
   }
 }
 // A MN-major ([k rows][m cols]: two 64-wide m chunks `a_chunk` bytes apart), B MN-major
 __device__ __forceinline__ void mma_mnmajor_a_mnmajor_b(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, int n, int ksteps,
-                                                        uint32_t a_chunk, uint32_t b_chunk, bool accumulate) {
+                                                        uint32_t a_chunk, uint32_t b_chunk, bool accumulate, bool issue) {
   const uint32_t idesc = ptx::make_idesc_f16(128, n, true, true, true);
   for (int k = 0; k < ksteps; ++k) {
     const uint32_t o = (uint32_t)k * (16u * 128u);
-    ptx::umma_f16(tmem_d, ptx::make_smem_desc(a_addr + o, a_chunk, kSBO), ptx::make_smem_desc(b_addr + o, b_chunk, kSBO), idesc,
+    if (issue) ptx::umma_f16(tmem_d, ptx::make_smem_desc(a_addr + o, a_chunk, kSBO), ptx::make_smem_desc(b_addr + o, b_chunk, kSBO), idesc,
                   (accumulate || k > 0) ? 1u : 0u);
   }
 }
@@ -157,7 +157,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   uint8_t* sp = sm;                             // P (2 panels) overwrites Q | K once S = Q K^T has completed
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 3 * kTile);   // 0: q,k,v landed  1: S ready  2: P staged  3: O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int b = blockIdx.x / p.nh, h = blockIdx.x % p.nh;
   const uint64_t rng_off = p.offset + (p.offset_dev != nullptr ? *p.offset_dev : 0ull);
   if (blockIdx.x == 0 && threadIdx.x == 0 && p.rng_state != nullptr) {
@@ -186,20 +186,21 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   const uint32_t t_s = tmem, t_o = tmem;        // O reuses the first 64 score columns (every row was drained before bars[2])
 
   if (warp == 4) {
-    if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(&bars[0], 3 * kTile);
-      ptx::tma_load_2d(sq, &tmQ, &bars[0], h * kD, b * p.S);
-      ptx::tma_load_2d(sk, &tmK, &bars[0], h * kD, b * p.S);
-      ptx::tma_load_2d(sv, &tmV, &bars[0], h * kD, b * p.S);
+    {   // the whole warp walks this code (uniform registers for descriptors); the elected lane issues
+      const bool issuer = ptx::elect_one();
+      if (issuer) ptx::mbar_arrive_expect_tx(&bars[0], 3 * kTile);
+      if (issuer) ptx::tma_load_2d(sq, &tmQ, &bars[0], h * kD, b * p.S);
+      if (issuer) ptx::tma_load_2d(sk, &tmK, &bars[0], h * kD, b * p.S);
+      if (issuer) ptx::tma_load_2d(sv, &tmV, &bars[0], h * kD, b * p.S);
       ptx::mbar_wait(&bars[0], 0);
       ptx::tc_fence_after();
-      mma_kmajor_a_kmajor_b(t_s, ptx::smem_u32(sq), ptx::smem_u32(sk), 128, 4, kTile, kTile, false);
-      ptx::umma_commit(&bars[1]);
+      mma_kmajor_a_kmajor_b(t_s, ptx::smem_u32(sq), ptx::smem_u32(sk), 128, 4, kTile, kTile, false, issuer);
+      if (issuer) ptx::umma_commit(&bars[1]);
       ptx::mbar_wait(&bars[2], 0);
       ptx::tc_fence_after();
       // O[q, d] = sum_key P[q, key] V[key, d]: P K-major (two 64-key panels), V MN-major (two [64 key][64 d] boxes)
-      mma_kmajor_a_mnmajor_b(t_o, ptx::smem_u32(sp), ptx::smem_u32(sv), 64, 8, kTile, 64 * 128, false);
-      ptx::umma_commit(&bars[3]);
+      mma_kmajor_a_mnmajor_b(t_o, ptx::smem_u32(sp), ptx::smem_u32(sv), 64, 8, kTile, 64 * 128, false, issuer);
+      if (issuer) ptx::umma_commit(&bars[3]);
     }
   } else {
     const int row = warp * 32 + lane;                      // query owned by this thread (TMEM lane = row)
@@ -290,7 +291,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 7 * kTile);
   // 0: tiles landed  1: S + dP ready  2: P~ and dS staged  3: dV, dQ, dK ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int b = blockIdx.x / p.nh, h = blockIdx.x % p.nh;
 
   if (warp == 4 && lane == 0) {
@@ -313,27 +314,28 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   const uint32_t t_s = tmem, t_dp = tmem + 128, t_dv = tmem, t_dq = tmem + 64, t_dk = tmem + 128;
 
   if (warp == 4) {
-    if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(&bars[0], 4 * kTile);
-      ptx::tma_load_2d(sq, &tmQ, &bars[0], h * kD, b * p.S);
-      ptx::tma_load_2d(sk, &tmK, &bars[0], h * kD, b * p.S);
-      ptx::tma_load_2d(sv, &tmV, &bars[0], h * kD, b * p.S);
-      ptx::tma_load_2d(sdo, &tmDO, &bars[0], h * kD, b * p.S);
+    {   // the whole warp walks this code (uniform registers for descriptors); the elected lane issues
+      const bool issuer = ptx::elect_one();
+      if (issuer) ptx::mbar_arrive_expect_tx(&bars[0], 4 * kTile);
+      if (issuer) ptx::tma_load_2d(sq, &tmQ, &bars[0], h * kD, b * p.S);
+      if (issuer) ptx::tma_load_2d(sk, &tmK, &bars[0], h * kD, b * p.S);
+      if (issuer) ptx::tma_load_2d(sv, &tmV, &bars[0], h * kD, b * p.S);
+      if (issuer) ptx::tma_load_2d(sdo, &tmDO, &bars[0], h * kD, b * p.S);
       ptx::mbar_wait(&bars[0], 0);
       ptx::tc_fence_after();
       // S = Q K^T and dP = dO V^T: both [query x key], K = head dim, all operands K-major
-      mma_kmajor_a_kmajor_b(t_s, ptx::smem_u32(sq), ptx::smem_u32(sk), 128, 4, kTile, kTile, false);
-      mma_kmajor_a_kmajor_b(t_dp, ptx::smem_u32(sdo), ptx::smem_u32(sv), 128, 4, kTile, kTile, false);
-      ptx::umma_commit(&bars[1]);
+      mma_kmajor_a_kmajor_b(t_s, ptx::smem_u32(sq), ptx::smem_u32(sk), 128, 4, kTile, kTile, false, issuer);
+      mma_kmajor_a_kmajor_b(t_dp, ptx::smem_u32(sdo), ptx::smem_u32(sv), 128, 4, kTile, kTile, false, issuer);
+      if (issuer) ptx::umma_commit(&bars[1]);
       ptx::mbar_wait(&bars[2], 0);
       ptx::tc_fence_after();
       // dV[key, d] = sum_q P~[q, key] dO[q, d] : A = P~ read MN-major (m = key), B = dO read MN-major (n = d); k = query
-      mma_mnmajor_a_mnmajor_b(t_dv, ptx::smem_u32(sp), ptx::smem_u32(sdo), 64, 8, kTile, 64 * 128, false);
+      mma_mnmajor_a_mnmajor_b(t_dv, ptx::smem_u32(sp), ptx::smem_u32(sdo), 64, 8, kTile, 64 * 128, false, issuer);
       // dQ[q, d] = sum_key dS[q, key] K[key, d] : A = dS K-major (two key panels), B = K MN-major
-      mma_kmajor_a_mnmajor_b(t_dq, ptx::smem_u32(sds), ptx::smem_u32(sk), 64, 8, kTile, 64 * 128, false);
+      mma_kmajor_a_mnmajor_b(t_dq, ptx::smem_u32(sds), ptx::smem_u32(sk), 64, 8, kTile, 64 * 128, false, issuer);
       // dK[key, d] = sum_q dS[q, key] Q[q, d] : A = dS MN-major, B = Q MN-major
-      mma_mnmajor_a_mnmajor_b(t_dk, ptx::smem_u32(sds), ptx::smem_u32(sq), 64, 8, kTile, 64 * 128, false);
-      ptx::umma_commit(&bars[3]);
+      mma_mnmajor_a_mnmajor_b(t_dk, ptx::smem_u32(sds), ptx::smem_u32(sq), 64, 8, kTile, 64 * 128, false, issuer);
+      if (issuer) ptx::umma_commit(&bars[3]);
     }
   } else {
     const int row = warp * 32 + lane;

@@ -199,7 +199,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* bfull_bar = bars + 2 * kStages + 6;              // SHIFT only: the per-tap B ring
   uint64_t* bempty_bar = bfull_bar + kBStages;
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, so the role branches are uniform branches and
+  // the single-thread roles (TMA producer, MMA issuer) keep their loop state in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   const int num_m = (p.M + kTileM - 1) / kTileM;
@@ -428,6 +430,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int bstage = 0;
       uint32_t bphase = 0;
       int it = 0;
+      const uint64_t adesc0 = ptx::make_smem_desc(ptx::smem_u32(smem_a), lbo_a, sbo_a);
+      const uint64_t bdesc0 = ptx::make_smem_desc(ptx::smem_u32(smem_b), lbo_b, sbo_b);
       for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
         int m_blk, n_blk, kb0, kb1;
         decode(w, m_blk, n_blk, kb0, kb1);
@@ -486,13 +490,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem_a + stage * kABytes);
-          const uint32_t b_addr = ptx::smem_u32(smem_b + stage * kBBytes);
+          // descriptors = stage-0 descriptor + byte offset >> 4 in the 14-bit address field (shared memory is < 256 KB, the
+          // field cannot carry out): two 64-bit adds per k-block and one per MMA instead of rebuilding the bit fields
+          const uint64_t adesc_s = adesc0 + (uint64_t)((uint32_t)stage * (uint32_t)(kABytes >> 4));
+          const uint64_t bdesc_s = bdesc0 + (uint64_t)((uint32_t)stage * (uint32_t)(kBBytes >> 4));
           if (issuer) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              uint64_t adesc = ptx::make_smem_desc(a_addr + k * kstep_a, lbo_a, sbo_a);
-              uint64_t bdesc = ptx::make_smem_desc(b_addr + k * kstep_b, lbo_b, sbo_b);
+              const uint64_t adesc = adesc_s + (uint64_t)((uint32_t)k * (kstep_a >> 4));
+              const uint64_t bdesc = bdesc_s + (uint64_t)((uint32_t)k * (kstep_b >> 4));
               if constexpr (CTAS == 2) ptx::umma_f16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
               else ptx::umma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }

@@ -1150,7 +1150,12 @@ def test_conv3x3_row_shifted_taps_variant(monkeypatch, n, h, w, c, o):
 
 def test_fused_trainer_keeps_write_gradient_semantics_when_a_step_is_skipped():
     """a backward pass that is NOT followed by trainer.step() must not leak its gradients into the next step
-    (grad_req='write'): the gradient arena is cleared by the first sink write of the next backward pass."""
+    (grad_req='write'): the gradient arena is cleared by the first sink write of the next backward pass.
+
+    A freshly initialised bf16 ResNet at batch 8 is not reproducible run to run at the bit level (BatchNorm statistics are
+    accumulated with fp32 atomics, one flipped bf16 rounding moves the gradients by ~20 % in norm), so the leak is made
+    unmistakable instead: the skipped backward pass uses a loss scaled by 100, which would put ~40x the gradient norm into
+    the arena if it survived."""
     import mxb200 as mx
     from mxb200 import gluon, autograd
     from mxb200.gluon.model_zoo import vision
@@ -1173,14 +1178,20 @@ def test_fused_trainer_keeps_write_gradient_semantics_when_a_step_is_skipped():
         tr.step(8)                                  # fuses the trainer (lazy) -- identical in both runs
         if skip_first:
             with autograd.record():
-                l = lf(net(x0 * 3.0), y)
+                l = lf(net(x0), y) * 100.0
             l.backward()                            # gradients computed, step skipped
+            assert any(ar.dirty for ar in tr._fused.arenas)
         with autograd.record():
             l = lf(net(x1), y)
         l.backward()
+        grads = [p.grad().as_torch().detach().float().clone() for p in net.collect_params().values() if p.grad_req != "null"]
         tr.step(8)
-        return [p.data().as_torch().detach().float().clone() for p in net.collect_params().values() if p.grad_req != "null"]
+        assert not any(ar.dirty for ar in tr._fused.arenas)
+        return grads
+
+    def norm(ts):
+        return float(sum((t.double() ** 2).sum() for t in ts)) ** 0.5
 
     a, b = run(False), run(True)
-    worst = max((u - v).abs().max().item() / (u.abs().max().item() + 1e-6) for u, v in zip(a, b))
-    assert worst < 2e-2, worst      # (BatchNorm running statistics differ by the extra forward; trainable weights must agree)
+    ref, diff = norm(a), norm([u - v for u, v in zip(a, b)])
+    assert ref > 0 and diff < 0.6 * ref, (diff, ref)      # run-to-run noise is ~0.2 * ref; a leak would be ~40 * ref

@@ -21,10 +21,17 @@ def run(skip_first):
         l = lf(net(x0), y)
     l.backward()
     tr.step(8)
+    gskip = None
     if skip_first:
         with autograd.record():
             l = lf(net(x0 * 3.0), y)
         l.backward()
+        gskip = {}
+        for ar in tr._fused.arenas:
+            print("after skipped backward: dirty", ar.dirty, "bw_epoch", ar.bw_epoch, "write", ar.write_semantics, "epoch now", autograd._bw_epoch[0])
+            for n, gv in zip(ar.layout.names, ar.grad_views):
+                gskip[n.split("_", 1)[1]] = gv.detach().float().clone()
+    wbefore = {n.split("_", 1)[1]: p.data().as_torch().detach().float().clone() for n, p in net.collect_params().items()}
     with autograd.record():
         l = lf(net(x1), y)
     l.backward()
@@ -32,11 +39,18 @@ def run(skip_first):
     for ar in tr._fused.arenas:
         for n, gv in zip(ar.layout.names, ar.grad_views):
             grads[n] = gv.detach().float().clone()
+    for ar in tr._fused.arenas:
+        print("after 3rd backward: dirty", ar.dirty, "bw_epoch", ar.bw_epoch, "epoch now", autograd._bw_epoch[0])
+    run.extra = (gskip, wbefore)
     tr.step(8)
     return {n: p.data().as_torch().detach().float().clone() for n, p in net.collect_params().items() if p.grad_req != "null"}, grads
 
 
-(a, ga), (b, gb) = run(False), run(True)
+(a0, ga0) = run(False)
+wb0 = run.extra[1]
+(a, ga) = run(False)
+wb1 = run.extra[1]
+(b, gb) = run(True)
 bad = []
 for (n, u), v in zip(a.items(), b.values()):
     e = (u - v).abs().max().item() / (u.abs().max().item() + 1e-6)
@@ -54,3 +68,18 @@ print("worst grads (arena, before step):")
 for r in gbad[:12]:
     print("  %.4g %s %s" % r)
 print("n grads differing > 1e-3:", sum(1 for r in gbad if r[0] > 1e-3), "of", len(gbad))
+
+import torch
+ga2 = {n.split("_", 1)[1]: v for n, v in ga.items()}
+gb2 = {n.split("_", 1)[1]: v for n, v in gb.items()}
+gskip, wb = run.extra
+def nrm(d): return sum(float((v.double() ** 2).sum()) for v in d.values()) ** 0.5
+print("||g_ref||", nrm(ga2), "||g_skiprun||", nrm(gb2), "||gskip||", nrm(gskip))
+print("||g_skiprun - g_ref||", nrm({k: gb2[k] - ga2[k] for k in ga2}))
+print("||g_skiprun - g_ref - gskip||", nrm({k: gb2[k] - ga2[k] - gskip[k] for k in ga2}))
+
+ga02 = {n.split("_", 1)[1]: v for n, v in ga0.items()}
+print("two identical runs: ||g_ref - g_ref'||", nrm({k: ga02[k] - ga2[k] for k in ga2}))
+print("weights before 3rd backward: ref vs ref'", nrm({k: wb0[k] - wb1[k] for k in wb0}), " ref vs skiprun", nrm({k: wb1[k] - wb[k] for k in wb}), "||w||", nrm(wb))
+big = sorted(((float((wb1[k] - wb[k]).abs().max()), k) for k in wb), reverse=True)[:6]
+print("largest weight diffs before 3rd backward:", big)
