@@ -7,7 +7,7 @@ baseline/_ref) through its own public API and stock code path, for the headline 
   loop    : mx.mod.Module bind / init_params / init_optimizer(kvstore='device') / forward_backward / update -- what
             Module.fit does per batch (python/mxnet/module/base_module.py:520-560), N GPUs driven by ONE process (the
             reference's process model, executor_group.py:143-305)
-  data    : synthetic, device-resident for ``value`` (common/data.py:98-130 SyntheticDataIter semantics); for ``e2e`` every
+  data    : synthetic, one pinned-host batch re-used for ``value`` (common/data.py:98-130 SyntheticDataIter semantics); for ``e2e`` every
             step feeds a host numpy batch (uint8 -> float on host like ImageRecordIter would deliver floats) and reads the
             softmax output of the step back to the host.
 
@@ -57,9 +57,10 @@ mod.init_optimizer(kvstore=kv if kv is not None else "local", optimizer="nag",
 rng = np.random.RandomState(1234)
 host_img = rng.randint(0, 256, size=(B, 3, S, S)).astype(np.uint8)
 host_lab = rng.randint(0, args.classes, size=(B,)).astype(np.float32)
-# device-resident synthetic batch (SyntheticDataIter keeps one NDArray and returns it every iteration)
-res = mx.io.DataBatch(data=[mx.nd.array(host_img.astype(np.float32), ctx=mx.cpu()).astype(np.float32)],
-                      label=[mx.nd.array(host_lab, ctx=mx.cpu())])
+# the synthetic batch (SyntheticDataIter keeps one pinned-host NDArray and returns it every iteration)
+pinned = mx.Context("cpu_pinned", 0)      # where the reference's SyntheticDataIter keeps its batch (common/data.py:110-111)
+res = mx.io.DataBatch(data=[mx.nd.array(host_img.astype(np.float32), ctx=pinned)],
+                      label=[mx.nd.array(host_lab, ctx=pinned)])
 
 
 def step(batch):

@@ -29,8 +29,12 @@ def _load(kind, required):
         from . import build as B
         path = B.lib_path(kind)
         lib = None
+        # MXB200_CUDA_LIB / MXB200_HOST_LIB: load an explicitly named build of the library (A/B runs of two kernel versions)
+        override = os.environ.get("MXB200_%s_LIB" % kind.upper())
         try:
-            if not B.is_fresh(kind):
+            if override:
+                path = override
+            elif not B.is_fresh(kind):
                 if getenv("MXB200_NO_BUILD", False):
                     if not os.path.exists(path):
                         raise MXNetError("native library %s missing and MXB200_NO_BUILD set" % path)

@@ -154,8 +154,8 @@ class GPUImageRecordIter(DataIter):
             raise MXNetError("empty RecordIO file %s" % path_imgrec)
         self.depth = max(2, int(prefetch))
         self.slot_bytes = max(4096, self.rec.max_batch_bytes(batch_size))
-        pin = self._cuda
-        self._slots = [torch.empty(self.slot_bytes, dtype=torch.uint8, pin_memory=pin) for _ in range(self.depth)]
+        from .. import storage as _st              # pooled pinned blocks (plain host memory without a GPU)
+        self._slots = [_st.alloc_pinned(self.slot_bytes) for _ in range(self.depth)]
         ptrs = (c_void_p * self.depth)(*[c_void_p(t.data_ptr()) for t in self._slots])
         self.loader = c_void_p()
         N.check(self.lib, self.lib.MXBLoaderCreate(self.rec.h, c_int(batch_size), c_int(self.label_width), c_int(max(1, int(threads))),
@@ -395,6 +395,11 @@ class GPUImageRecordIter(DataIter):
             self._dec = None
         if getattr(self, "rec", None):
             self.rec.close()
+        if getattr(self, "_slots", None):
+            from .. import storage as _st
+            for b in self._slots:
+                _st.free_pinned(b)
+            self._slots = None
 
     def __del__(self):
         try:

@@ -18,6 +18,8 @@ This is the *functional core*; ``mxb200.gluon.model_zoo.vision`` wraps it as Hyb
 """
 import math
 
+import weakref
+
 import torch
 import torch.nn.functional as F
 
@@ -198,7 +200,9 @@ def _folded(P, A, wname, bnname, eps):
     key = (w.data_ptr(), g.data_ptr(), b.data_ptr(), m.data_ptr(), v.data_ptr())
     ver = (w._version, g._version, b._version, m._version, v._version, float(eps))
     hit = _FOLD_CACHE.get(key)
-    if hit is not None and hit[0] == ver:
+    # the entry must belong to THESE tensor objects: after a model is freed the caching allocator hands the same addresses
+    # (with the same fresh version counters) to the next model's parameters
+    if hit is not None and hit[0] == ver and all(r() is t for r, t in zip(hit[3], (w, g, b, m, v))):
         return hit[1], hit[2]
     with torch.no_grad():
         scale = g.float() * torch.rsqrt(v.float() + eps)
@@ -210,7 +214,7 @@ def _folded(P, A, wname, bnname, eps):
             wf = wf.contiguous()
     if len(_FOLD_CACHE) > 4096:
         _FOLD_CACHE.clear()
-    _FOLD_CACHE[key] = (ver, wf, shift)
+    _FOLD_CACHE[key] = (ver, wf, shift, tuple(weakref.ref(t) for t in (w, g, b, m, v)))
     return wf, shift
 
 

@@ -235,13 +235,38 @@ def save(fname, data, dtype=None, async_write=False):
         names, arrs = (list(data.keys()), list(data.values())) if isinstance(data, dict) else ([], list(data) if not isinstance(data, NDArray) else [data])
         if isinstance(data, dict) and not all(isinstance(k, str) for k in names):
             raise TypeError("save only accept dict str->NDArray or list of NDArray")
-        ts = [a._t.detach().contiguous().cpu() for a in arrs]
-        if async_write:
-            ts = [t.clone() if (not a._t.is_cuda and t.data_ptr() == a._t.data_ptr()) else t for t, a in zip(ts, arrs)]
+        staged = []
+        if async_write and any(a._t.is_cuda for a in arrs):
+            # device arrays are snapshotted through pinned staging blocks of the pooled storage manager: all copies are
+            # queued asynchronously, ONE synchronisation covers them, and the engine worker returns the blocks to the pool
+            # after the file is written (the next checkpoint finds them there)
+            from .. import storage as _st
+            ts = []
+            for a in arrs:
+                t = a._t.detach().contiguous()
+                if t.is_cuda and t.numel() > 0:
+                    buf = _st.alloc_pinned(t.numel() * t.element_size())
+                    staged.append(buf)
+                    h = buf.view(t.dtype).view(t.shape)
+                    h.copy_(t, non_blocking=True)
+                    ts.append(h)
+                else:
+                    ts.append(t.cpu().clone())
+            torch.cuda.synchronize()
+        else:
+            ts = [a._t.detach().contiguous().cpu() for a in arrs]
+            if async_write:
+                ts = [t.clone() if (not a._t.is_cuda and t.data_ptr() == a._t.data_ptr()) else t for t, a in zip(ts, arrs)]
         ctxs = [(a.context.device_typeid, a.context.device_id) for a in arrs]
 
         def write():
-            nat.save(fname, names, ts, ctxs)
+            try:
+                nat.save(fname, names, ts, ctxs)
+            finally:
+                if staged:
+                    from .. import storage as _st
+                    for b in staged:
+                        _st.free_pinned(b)
     else:
         blob = dumps(data, dtype)
 

@@ -61,6 +61,7 @@ class PeerGroup(object):
         self.exchange = exchange          # callable(list_of_bytes_local) -> list over ranks (process mode)
         self.lib = N.cuda()
         self._allocs = []                 # (local _RawBuffer, [peer ptrs], [opened handles])
+        self._pooled = {}                 # device pointer -> storage.Handle of blocks that came from the pool
         self._segments = []               # VMM segments (multicast-capable allocations)
         self._mc_ok = None
         self._job = None
@@ -75,10 +76,29 @@ class PeerGroup(object):
 
     # -- allocation -------------------------------------------------------------------------------
     def _malloc(self, nbytes, device):
+        """Zero-filled device block.  By default it comes from the pooled storage manager (csrc/host/storage.cc): when the
+        group is rebuilt after a membership change the arenas of the previous peer set are found in the pool instead of
+        paying cudaFree + cudaMalloc (``MXB200_POOLED_ARENAS=0``: plain cudaMalloc)."""
+        if getenv("MXB200_POOLED_ARENAS", True):
+            from .. import storage as _st
+            h = _st.alloc(nbytes, torch.device(device))
+            with torch.cuda.device(device):
+                h.tensor(torch.uint8, numel=nbytes).zero_()
+                torch.cuda.current_stream().synchronize()
+            self._pooled[h.ptr] = h
+            return h.ptr
         p = c_void_p()
         with torch.cuda.device(device):
             N.check(self.lib, self.lib.MXBDeviceMalloc(c_int64(nbytes), ctypes.byref(p)))
         return p.value
+
+    def _free(self, ptr):
+        h = self._pooled.pop(ptr, None)
+        if h is not None:
+            from .. import storage as _st
+            _st.free(h)
+        else:
+            self.lib.MXBDeviceFree(c_void_p(ptr))
 
     def alloc(self, nbytes):
         nbytes = (int(nbytes) + 255) // 256 * 256
@@ -159,7 +179,7 @@ class PeerGroup(object):
             for p in opened:
                 self.lib.MXBIpcCloseHandle(c_void_p(p))
             if local.owner:
-                self.lib.MXBDeviceFree(c_void_p(local.ptr))
+                self._free(local.ptr)
         self._allocs = []
         for seg in self._segments:
             self.lib.MXBVmmFree(seg)
