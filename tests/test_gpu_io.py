@@ -22,11 +22,13 @@ def _cv_decode(rec, idx, i):
     return a
 
 
-def test_nvjpeg_identity_window_matches_opencv_decode(tmp_path):
+@pytest.mark.parametrize("backend", [0, 2])
+def test_nvjpeg_identity_window_matches_opencv_decode(tmp_path, backend):
     sizes = [(64, 64), (48, 80), (80, 48), (33, 47), (96, 96), (64, 64), (50, 70), (72, 40)]
     rec, idx, imgs, labels = _make_rec(tmp_path, n=8, sizes=sizes)
     for i, (h, w) in enumerate(sizes):
-        it = GPUImageRecordIter(rec, (3, h, w), 8, path_imgidx=idx, layout="NHWC", ctx=mx.gpu(0))
+        it = GPUImageRecordIter(rec, (3, h, w), 8, path_imgidx=idx, layout="NHWC", ctx=mx.gpu(0), backend=backend)
+        assert it.backend == backend
         (x, y, pad, ids), = _collect(it)
         assert x.shape == (8, h, w, 3) and pad == 0 and list(ids) == list(range(8))
         assert np.allclose(y, labels)

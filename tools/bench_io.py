@@ -84,7 +84,7 @@ def main():
         res["device_pipeline_img_s"] = round(run(it, args.batches, sync), 1)
         res["device_pipeline_h2d_bytes_per_image"] = int(it.h2d_bytes / args.batch)
         it.close()
-        for be, name in ((3, "hardware"),):
+        for be, name in ((0, "default_hybrid"), (3, "hardware")):
             try:
                 it = mx.io.gpu_pipeline.GPUImageRecordIter(rec, (3, 224, 224), args.batch, path_imgidx=idx, shuffle=True, rand_mirror=True,
                                                            random_resized_crop=True, min_random_area=0.08, min_aspect_ratio=0.75,
