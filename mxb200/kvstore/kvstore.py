@@ -443,7 +443,7 @@ class KVStoreLocal(KVStore):
             if len(rlist) == 1 and len(olist) > 1:
                 rlist = rlist * len(olist)
             for o, rid in zip(olist, rlist):
-                ids = unique_rows(rid._t.to(dense.device))
+                ids = unique_rows(rid._t.to(dense.device), num_rows=dense.shape[0])
                 data = dense.index_select(0, ids)
                 if isinstance(o, _sp.RowSparseNDArray):
                     dev = o._data.device

@@ -432,7 +432,8 @@ def retain(data=None, indices=None, out=None, **kwargs):
     if not isinstance(rsp, RowSparseNDArray):
         raise MXNetError("sparse retain expects a row_sparse input, got %s" % type(rsp).__name__)
     ids = row_ids._t.long() if isinstance(row_ids, NDArray) else torch.as_tensor(row_ids, dtype=torch.int64, device=rsp._data.device)
-    ids = torch.unique(ids)
+    from ..kvstore.utils import unique_rows
+    ids = unique_rows(ids, num_rows=rsp._shape[0])
     mask = torch.isin(rsp._indices, ids)
     return RowSparseNDArray(rsp._data[mask], rsp._indices[mask], rsp._shape, rsp._ctx)
 

@@ -1195,3 +1195,22 @@ def test_fused_trainer_keeps_write_gradient_semantics_when_a_step_is_skipped():
     a, b = run(False), run(True)
     ref, diff = norm(a), norm([u - v for u, v in zip(a, b)])
     assert ref > 0 and diff < 0.6 * ref, (diff, ref)      # run-to-run noise is ~0.2 * ref; a leak would be ~40 * ref
+
+
+@pytest.mark.parametrize("n,num_rows", [(1, 1), (10, 33), (5000, 1000), (100000, 3000000), (70000, 8192), (3, 100000)])
+def test_unique_row_ids_native_matches_torch_unique(n, num_rows):
+    """csrc/cuda/unique.cu (bitmap + scan + compaction) against torch.unique (reference: kvstore_utils.cu UniqueImpl)."""
+    from mxb200.kvstore.utils import unique_rows
+    g = torch.Generator(device="cpu").manual_seed(n)
+    ids = torch.randint(0, num_rows, (n,), generator=g).to(_dev())
+    for _ in range(2):                                   # the scratch bitmap must be left clean for the next call
+        got = unique_rows(ids, num_rows=num_rows)
+        assert torch.equal(got, torch.unique(ids, sorted=True))
+    ids2 = torch.randint(0, num_rows, (max(1, n // 2),), generator=g).to(_dev())
+    assert torch.equal(unique_rows(ids2.view(1, -1), num_rows=num_rows), torch.unique(ids2))
+    bad = ids.clone()
+    bad[0] = num_rows
+    if n >= 1 and num_rows <= 64 * 32 * max(n, 1024):
+        with pytest.raises(Exception):
+            unique_rows(bad, num_rows=num_rows)
+        assert torch.equal(unique_rows(ids, num_rows=num_rows), torch.unique(ids))   # and the state is clean afterwards
