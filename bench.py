@@ -135,7 +135,10 @@ def reference_arm(args):
     env["PYTHONPATH"] = ref + os.pathsep + env.get("PYTHONPATH", "")
     env["MXNET_LIBRARY_PATH"] = lib
     env["LD_LIBRARY_PATH"] = os.path.join(ref, "mxnet") + os.pathsep + env.get("LD_LIBRARY_PATH", "")   # OpenBLAS + libgfortran copies
-    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+    # torchrun's rendezvous variables mean nothing to MXNet, and its OMP_NUM_THREADS=1 would cripple the fork's host-side
+    # operators (its default is all cores)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS", "GROUP_RANK", "LOCAL_WORLD_SIZE",
+              "TORCHELASTIC_RUN_ID"):
         env.pop(k, None)
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     line = None

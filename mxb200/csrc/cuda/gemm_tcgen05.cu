@@ -924,7 +924,14 @@ static void launch(const void* A, const void* B, void* D, int M, int N, int K, i
     throw std::runtime_error("gemm: bias must be 16B aligned and N a multiple of 4");
   p.dbg_lbo_a = dbg ? dbg[0] : 0; p.dbg_sbo_a = dbg ? dbg[1] : 0; p.dbg_lbo_b = dbg ? dbg[2] : 0; p.dbg_sbo_b = dbg ? dbg[3] : 0;
   const int num_m = (M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS), num_n = (N + BN - 1) / BN;
-  p.gm = num_m < 16 ? num_m : 16;
+  // raster group height: the concurrently running tiles (one per CTA / CTA pair) should cover a near-square patch of the
+  // output so that each wave streams the fewest A + B panels (MXB200_GEMM_GM overrides: experiments)
+  int gm_want = 16;
+  {
+    static const int env_gm = [] { const char* e = getenv("MXB200_GEMM_GM"); return e ? atoi(e) : 0; }();
+    if (env_gm > 0) gm_want = env_gm;
+  }
+  p.gm = num_m < gm_want ? num_m : gm_want;
   p.full_groups = num_m / p.gm;
   p.tail_gm = num_m - p.full_groups * p.gm;
   p.d_split = make_fastdiv((uint32_t)p.num_splits);
@@ -986,6 +993,21 @@ MXB_API int MXBGemmBf16(int mode, const void* A, const void* B, void* D, int M, 
     const int64_t nm = (M + 127) / 128;
     const int sp = (mode == 2 && splits > 1) ? splits : 1;
     while (bn > 64 && nm * ((N + bn - 1) / bn) * sp < 100) bn >>= 1;
+    // compute-bound problems (deep K) with few tiles: the persistent grid runs whole waves, so 96 tiles on 74 CTA pairs
+    // cost two waves.  Estimate waves x cycles per tile for the 256-wide configurations and for 128-wide tiles (64 tensor
+    // cycles per 128x128x16 MMA against 128 for 128x256x16) and take the narrower tile when it saves more than 12 %
+    // (BERT FFN-2 8192x768x3072: 3 waves of 128-wide tiles instead of 2 waves of 256x256 pairs).
+    if (bn == 256 && mode != 2 && K >= 512 && block_n == 0) {
+      const int64_t kb16 = (K + 15) / 16;
+      const int64_t m128 = (M + 127) / 128, m256 = (M + 255) / 256;
+      const int64_t n256 = (N + 255) / 256, n128 = (N + 127) / 128;
+      auto waves = [](int64_t tiles, int64_t slots) { return (tiles + slots - 1) / slots; };
+      const int64_t fixed = 600;                                        // pipeline fill / drain per tile
+      const int64_t c_pair = waves(m256 * n256, 74) * (kb16 * 128 + fixed);
+      const int64_t c_256 = waves(m128 * n256, 148) * (kb16 * 128 + fixed);
+      const int64_t c_128 = waves(m128 * n128, 148) * (kb16 * 64 + fixed);
+      if (c_128 * 100 < std::min(c_pair, c_256) * 88) bn = 128;
+    }
   }
   // CTA pairs (cta_group::2): 256 x 256 tiles shared by two SMs; worth it when the problem is compute bound (deep K) and
   // has enough 256-row tiles to fill the 74 clusters.  MXB200_GEMM_2CTA=0/1 forces it off/on.
