@@ -993,21 +993,6 @@ MXB_API int MXBGemmBf16(int mode, const void* A, const void* B, void* D, int M, 
     const int64_t nm = (M + 127) / 128;
     const int sp = (mode == 2 && splits > 1) ? splits : 1;
     while (bn > 64 && nm * ((N + bn - 1) / bn) * sp < 100) bn >>= 1;
-    // compute-bound problems (deep K) with few tiles: the persistent grid runs whole waves, so 96 tiles on 74 CTA pairs
-    // cost two waves.  Estimate waves x cycles per tile for the 256-wide configurations and for 128-wide tiles (64 tensor
-    // cycles per 128x128x16 MMA against 128 for 128x256x16) and take the narrower tile when it saves more than 12 %
-    // (BERT FFN-2 8192x768x3072: 3 waves of 128-wide tiles instead of 2 waves of 256x256 pairs).
-    if (bn == 256 && mode != 2 && K >= 512 && block_n == 0) {
-      const int64_t kb16 = (K + 15) / 16;
-      const int64_t m128 = (M + 127) / 128, m256 = (M + 255) / 256;
-      const int64_t n256 = (N + 255) / 256, n128 = (N + 127) / 128;
-      auto waves = [](int64_t tiles, int64_t slots) { return (tiles + slots - 1) / slots; };
-      const int64_t fixed = 600;                                        // pipeline fill / drain per tile
-      const int64_t c_pair = waves(m256 * n256, 74) * (kb16 * 128 + fixed);
-      const int64_t c_256 = waves(m128 * n256, 148) * (kb16 * 128 + fixed);
-      const int64_t c_128 = waves(m128 * n128, 148) * (kb16 * 64 + fixed);
-      if (c_128 * 100 < std::min(c_pair, c_256) * 88) bn = 128;
-    }
   }
   // CTA pairs (cta_group::2): 256 x 256 tiles shared by two SMs; worth it when the problem is compute bound (deep K) and
   // has enough 256-row tiles to fill the 74 clusters.  MXB200_GEMM_2CTA=0/1 forces it off/on.
@@ -1020,9 +1005,17 @@ MXB_API int MXBGemmBf16(int mode, const void* A, const void* B, void* D, int M, 
     two_cta = two_cta_env == 1 || (two_cta_env != 0 && K >= 256 && tiles2 >= 74);
     if (mode == 2 && M < 256) two_cta = false;
   }
+  // 256 x 128 CTA-pair tiles (experiment switch MXB200_GEMM_2CTA_128=1, read per call): with N = 128 a single CTA's MMA is
+  // bound by its shared-memory operand reads (A 4 KB + B 4 KB per 64 tensor cycles); in a pair each CTA stages half of B
+  bool pair128 = false;
+  if (bn == 128 && mode != 2 && M >= 256 && K >= 128) {
+    const char* e = getenv("MXB200_GEMM_2CTA_128");
+    pair128 = e != nullptr && atoi(e) == 1;
+  }
 #define MXB_GEMM_DISPATCH(AMN, BMN, OUT, RED, SPL)                                                                   \
   do {                                                                                                                \
-    if (two_cta) gemm::launch<256, AMN, BMN, OUT, RED, 2>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
+    if (pair128) gemm::launch<128, AMN, BMN, OUT, RED, 2>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
+    else if (two_cta) gemm::launch<256, AMN, BMN, OUT, RED, 2>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
     else if (bn == 64) gemm::launch<64, AMN, BMN, OUT, RED>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
     else if (bn == 128) gemm::launch<128, AMN, BMN, OUT, RED>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
     else gemm::launch<256, AMN, BMN, OUT, RED>(A, B, D, M, N, K, lda, ldb, ldd, bias, relu, col_sum, col_sumsq, addend, ldc, SPL, max_ctas, dbg, s); \
