@@ -924,22 +924,24 @@ MXB_API int MXBBnBackward(const void* dy, const void* x, const void* mask, void*
         const int64_t nchunks = (M + R - 1) / R;
         int grid = (int)std::min<int64_t>(nchunks, (int64_t)kNumSMs * 2);
         if (grid > kMaxGrid) grid = kMaxGrid;
-        // Small layers: the streaming part takes 10-50 us and the combine step of the block sums (grid x 2C fp32 RED.ADDs,
-        // or grid x 2C partials summed by the last block) costs as much again (profiles/step_roofline_bn_r2_call32.txt:
-        // 25088 x 512 runs at 1.0 TB/s, 100352 x 256 at 2.0 TB/s).  Below 450 MB of input pick the grid that minimises
-        //   t(grid) = max(bytes / HBM, bytes / (grid * per-CTA stream rate)) + grid * 2C * cost per combined value
-        // and always combine with RED.ADD.  Opt-in (MXB200_BN_REDUCE_GRID=1) until measured; default: the plain 2-CTAs-per-SM grid.
-        static const bool grid_model = [] { const char* e = getenv("MXB200_BN_REDUCE_GRID"); return e && e[0] == '1'; }();
+        // Small layers (< 300 MB of input): the streaming part takes 8-30 us and a fixed ~40 us appears on top once the
+        // grid goes beyond one CTA per SM (profiles/step_roofline_bn_r2_call32.txt: 25088 x 512 ran at 1.0 TB/s,
+        // 100352 x 256 at 2.0 TB/s).  Measured A/B (profiles/bn_reduce_grid_ab_r2_call33.txt): 103 MB 53 -> 36 us at
+        // 148 CTAs, 51 MB 50 -> 29 us at 111 CTAs, 205 MB 56 -> 53 us at 185 CTAs; larger inputs need the full grid (a
+        // CTA's 96 KB ring streams ~24 GB/s).  Pick the grid that minimises
+        //   t(grid) = max(bytes / HBM, bytes / (grid * 24 GB/s)) + 30 us * (grid - 148) / 148   [second term only above 148]
+        // and combine the block sums with RED.ADD.  MXB200_BN_REDUCE_GRID=0: always 2 CTAs per SM.
+        static const bool grid_model = [] { const char* e = getenv("MXB200_BN_REDUCE_GRID"); return !(e && e[0] == '0'); }();
         static const bool det = [] { const char* e = getenv("MXB200_BN_DETERMINISTIC"); return e && e[0] == '1'; }();
         const double bytes = (double)M * C * 4.0;
-        if (grid_model && !det && bytes < 450e6) {
+        if (grid_model && !det && bytes < 300e6) {
           f.use_atomics = 1;
           double best = 1e30;
           int best_grid = grid;
-          for (int g = kNumSMs / 4; g <= kNumSMs * 2; g += kNumSMs / 4) {
+          for (int g = kNumSMs / 2; g <= kNumSMs * 2; g += kNumSMs / 4) {
             if (g > nchunks || g > kMaxGrid) break;
-            const double stream = std::max(bytes / 6.4e12, bytes / (g * 40e9));
-            const double t = stream + (double)g * 2.0 * C * 0.08e-9;
+            const double stream = std::max(bytes / 6.4e12, bytes / (g * 24e9));
+            const double t = stream + (g > kNumSMs ? 30e-6 * (g - kNumSMs) / kNumSMs : 0.0);
             if (t < best) {
               best = t;
               best_grid = g;
