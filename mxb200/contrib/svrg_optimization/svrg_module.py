@@ -37,6 +37,37 @@ class SVRGModule(Module):
             arg, aux = self.get_params()
             self._mod_aux.init_params(arg_params=arg, aux_params=aux, allow_missing=False, force_init=True)
 
+    def init_optimizer(self, kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.01),), force_init=False):
+        """Install ``_SVRGOptimizer`` around the user's optimizer (svrg_module.py:114-151 of the reference): ordinary keys
+        are updated by ``optimizer``; keys named ``<param>_full`` are ASSIGNED, which is how several workers accumulate the
+        full gradients in a kvstore."""
+        from ... import model as _model
+        from ...ndarray import zeros
+        batch_size = self._exec_group.batch_size
+        arg_params = self.get_params()[0]
+        kv, update_on_kvstore = _model._create_kvstore(kvstore, len(self._context), arg_params)
+        if kv is not None and "dist" in kv.type and "_sync" in kv.type:
+            batch_size *= kv.num_workers
+        names = list(self._exec_group.param_names)
+        nctx = len(self._context)
+        idx2name = {}
+        if update_on_kvstore:
+            idx2name.update(enumerate(names))
+        else:
+            for k in range(nctx):
+                idx2name.update({i * nctx + k: n for i, n in enumerate(names)})
+        for n in names:
+            idx2name[max(idx2name) + 1] = n + "_full"
+        params = dict(optimizer_params)
+        params.setdefault("rescale_grad", 1.0 / batch_size)
+        params["param_idx2name"] = idx2name
+        svrg_opt = _SVRGOptimizer(default_optimizer=optimizer, **params)
+        super(SVRGModule, self).init_optimizer(kvstore=kv if kv is not None else None, optimizer=svrg_opt,
+                                               optimizer_params=optimizer_params, force_init=force_init)
+        if self._kvstore is not None:
+            for idx, n in enumerate(names):
+                self._kvstore.init(n + "_full", zeros(arg_params[n].shape))
+
     def forward(self, data_batch, is_train=None):
         super(SVRGModule, self).forward(data_batch, is_train)
         if is_train is None or is_train:

@@ -388,10 +388,10 @@ class HybridBlock(Block):
         if isinstance(x, NDArray):
             ctx = x.context
             try:
-                params = {i: j.data(ctx) for i, j in self._reg_params.items()}
+                params = {i: j._raw_data(ctx) for i, j in self._reg_params.items()}
             except DeferredInitializationError:
                 self._deferred_infer(x, *args)
-                params = {i: j.data(ctx) for i, j in self._reg_params.items()}
+                params = {i: j._raw_data(ctx) for i, j in self._reg_params.items()}
             return self.hybrid_forward(nd, x, *args, **params)
         from .. import symbol
         assert isinstance(x, symbol.Symbol), "HybridBlock requires the first argument to forward be either Symbol " \
@@ -501,7 +501,7 @@ class SymbolBlock(HybridBlock):
             ctx = x.context
             for name, p in self.params.items():
                 try:
-                    feed[name] = p.data(ctx)
+                    feed[name] = p._raw_data(ctx)
                 except DeferredInitializationError:
                     sym_ = self._cached_graph[1]
                     arg_s, _o, aux_s = sym_.infer_shape_partial(**{n: a.shape for n, a in zip(self._input_names, inputs)})
@@ -511,7 +511,7 @@ class SymbolBlock(HybridBlock):
                         if pname in self.params._params and shp:
                             self.params[pname].shape = shp
                             self.params[pname]._finish_deferred_init()
-                    feed[name] = p.data(ctx)
+                    feed[name] = p._raw_data(ctx)
             outs = self._cached_graph[1].eval_nd(feed)
             return outs[0] if len(outs) == 1 else outs
         return self._cached_graph[1]

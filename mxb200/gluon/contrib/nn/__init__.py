@@ -44,7 +44,7 @@ class SparseEmbedding(Block):
 
     def forward(self, x):
         from .... import ndarray as nd
-        return nd.Embedding(x, self.weight.data(x.context), **self._kwargs)
+        return nd.Embedding(x, self.weight._raw_data(x.context), **self._kwargs)
 
     def __repr__(self):
         return "{name}({input_dim} -> {output_dim}, {dtype})".format(name=self.__class__.__name__, **self._kwargs)

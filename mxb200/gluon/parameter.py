@@ -180,7 +180,7 @@ class Parameter(object):
 
     def _reduce(self):
         """Average of the per-context copies, on CPU (parameter.py:312-323)."""
-        block = self.list_data()
+        block = self._raw_list_data()
         acc = block[0]._t.detach().to("cpu").float()
         for b in block[1:]:
             acc = acc + b._t.detach().to("cpu").float()
@@ -246,30 +246,77 @@ class Parameter(object):
         if tr is not None and getattr(tr, "_fused", None) is not None:
             tr._fused.refresh_master()
 
+    def _check_row_sparse_access(self):
+        if self._stype != "row_sparse":
+            raise RuntimeError("Cannot return a copy of Parameter %s via row_sparse_data() because its storage type is %s. "
+                               "Please use data() instead." % (self.name, self._stype))
+        if getattr(self, "_trainer", None) is None:
+            raise RuntimeError("Cannot get row_sparse data for Parameter '%s' when no Trainer is created with it." % self.name)
+
     def row_sparse_data(self, row_id):
-        d = self.data(row_id.context)
-        return _sp.retain(_sp.cast_storage(d, "row_sparse"), row_id)
+        """Rows ``row_id`` of a row_sparse Parameter on ``row_id``'s context (reference: the Trainer pulls them from the
+        kvstore, gluon/parameter.py:441-459)."""
+        self._check_row_sparse_access()
+        return self._rows_of(self._raw_data(row_id.context), row_id)
 
     def list_row_sparse_data(self, row_id):
-        return [self.row_sparse_data(row_id)]
+        self._check_row_sparse_access()
+        return [self._rows_of(d, row_id.as_in_context(d.context)) for d in self._raw_list_data()]
+
+    @staticmethod
+    def _rows_of(d, row_id):
+        """Row-sparse view of the requested rows.  Its dense leaf is the parameter's own array, so an operator that consumes
+        it under ``autograd.record()`` (Embedding, sparse dot) back-propagates into the parameter."""
+        rsp = _sp.retain(_sp.cast_storage(d, "row_sparse"), row_id)
+        if d._t.requires_grad:
+            rsp.__dict__["_dense_leaf"] = d
+        return rsp
+
+    def _raw_data(self, ctx=None):
+        """Dense backing array regardless of the declared storage type (framework-internal access)."""
+        return self._check_and_get(self._data, ctx)
+
+    def _raw_list_data(self):
+        return self._check_and_get(self._data, list)
+
+    def _check_dense_access(self, what):
+        if self._stype != "default":
+            raise RuntimeError("Cannot return a copy of Parameter '%s' via %s() because its storage type is %s. Please use "
+                               "row_sparse_data() instead." % (self.name, what, self._stype))
 
     def data(self, ctx=None):
+        self._check_dense_access("data")
         return self._check_and_get(self._data, ctx)
 
     def list_data(self):
+        self._check_dense_access("list_data")
         return self._check_and_get(self._data, list)
 
     def grad(self, ctx=None):
         if self._data is not None and self._grad is None:
             raise RuntimeError("Cannot get gradient array for Parameter '%s' because grad_req='null'" % self.name)
         self._sync_grad()
-        return self._check_and_get(self._grad, ctx)
+        return self._grad_view(self._check_and_get(self._grad, ctx))
 
     def list_grad(self):
         if self._data is not None and self._grad is None:
             raise RuntimeError("Cannot get gradient array for Parameter '%s' because grad_req='null'" % self.name)
         self._sync_grad()
+        return [self._grad_view(g) for g in self._check_and_get(self._grad, list)]
+
+    def _raw_list_grad(self):
+        """The dense gradient buffers themselves (framework-internal: kvstore push / pull targets)."""
+        self._sync_grad()
         return self._check_and_get(self._grad, list)
+
+    def _grad_view(self, g):
+        """``grad_stype='row_sparse'`` (e.g. ``Embedding(sparse_grad=True)``): the gradient buffer is dense-backed (autograd
+        accumulates into it) and is exposed with the declared storage type, like the reference's sparse gradient arrays."""
+        st = getattr(self, "_grad_stype", "default")
+        if st == "default" or g is None:
+            return g
+        from ..ndarray.sparse import BaseSparseNDArray, cast_storage
+        return g if isinstance(g, BaseSparseNDArray) else cast_storage(g, st)
 
     def _sync_grad(self):
         # torch may replace .grad; keep our NDArray handles pointing at the live tensor
@@ -308,7 +355,7 @@ class Parameter(object):
         if self._var is None:
             from .. import symbol
             self._var = symbol.var(self.name, shape=self.shape, dtype=self.dtype, lr_mult=self.lr_mult,
-                                   wd_mult=self.wd_mult, init=self.init)
+                                   wd_mult=self.wd_mult, init=self.init, stype=self._stype)
         return self._var
 
     def cast(self, dtype):

@@ -42,7 +42,7 @@ class Trainer(object):
                 raise ValueError("First argument must be a list or dict of Parameters, got list of %s." % (type(param)))
             self._param2idx[param.name] = i
             self._params.append(param)
-            param._trainer = self
+            param._set_trainer(self)
             if param._stype != "default" or param._grad_stype != "default":
                 self._contains_sparse = True
         self._compression_params = compression_params
@@ -92,17 +92,30 @@ class Trainer(object):
     # ---------------------------------------------------------------------------------- kvstore init
     def _init_kvstore(self):
         config = self._kvstore_params
-        if self._contains_sparse:
-            kvstore, update_on_kvstore = _create_kvstore(config["kvstore"], len(self._contexts), {})
+        sparse_weight = any(p._stype != "default" for p in self._params)
+        sparse_grad = any(p._grad_stype != "default" for p in self._params)
+        if sparse_weight:
+            # row_sparse weights live in the kvstore and are updated there, even with one device
+            # (gluon/trainer.py:168-180 of the reference: _create_sparse_kvstore)
+            from .. import kvstore as _kvs
+            kv = config["kvstore"]
+            kvstore = _kvs.create(kv) if isinstance(kv, str) else kv
+            if kvstore is None:
+                raise ValueError("Cannot create a kvstore for sparse weights from %r" % (kv,))
             if config["update_on_kvstore"] is False:
-                raise RuntimeError("Cannot set update_on_kvstore to False when sparse gradients and/or sparse "
-                                   "weights are present for Parameter.")
-            update_on_kvstore = True if kvstore else update_on_kvstore
+                raise RuntimeError("Cannot set update_on_kvstore to False when sparse weights are present.")
+            update_on_kvstore = True
+        elif sparse_grad:
+            # dense weights with row_sparse gradients: aggregated through the kvstore, updated locally (reference :181-185)
+            kvstore, _ = _create_kvstore(config["kvstore"], len(self._contexts), {})
+            update_on_kvstore = False
+            if config["update_on_kvstore"]:
+                update_on_kvstore = True
         else:
             arg_arrays = {}
             for param in self._params:
                 try:
-                    arg_arrays[param.name] = param.data(self._contexts[0])
+                    arg_arrays[param.name] = param._raw_data(self._contexts[0])
                 except Exception:  # noqa: BLE001
                     pass
             kvstore, update_on_kvstore = _create_kvstore(config["kvstore"], len(self._contexts), arg_arrays)
@@ -112,7 +125,7 @@ class Trainer(object):
             if self._compression_params:
                 kvstore.set_gradient_compression(self._compression_params)
             if "dist" in kvstore.type:
-                update_on_kvstore = True if "async" in kvstore.type else update_on_kvstore
+                update_on_kvstore = True if ("async" in kvstore.type or sparse_weight or sparse_grad) else update_on_kvstore
             if update_on_kvstore:
                 kvstore.set_optimizer(self._optimizer)
             self._kvstore = kvstore
@@ -162,7 +175,7 @@ class Trainer(object):
         train = [p for p in self._params if p.grad_req != "null"]
         if not train:
             return
-        named = [(p.name, p.data(ctx)._t.detach()) for p in train]
+        named = [(p.name, p._raw_data(ctx)._t.detach()) for p in train]
         lr_mult = {p.name: p.lr_mult for p in train}
         wd_mult = {p.name: p.wd_mult for p in train}
         dt = DeviceTrainer(named, ctx.torch_device, rank=rank, world=world, lr_mult=lr_mult, wd_mult=wd_mult,
@@ -378,11 +391,11 @@ class Trainer(object):
         if self._kvstore:
             live = [(i, param) for i, param in enumerate(self._params) if param.grad_req != "null"]
             for i, param in live:
-                self._kvstore.push(i, param.list_grad(), priority=-i)
+                self._kvstore.push(i, param._raw_list_grad(), priority=-i)
             if not self._update_on_kvstore:
                 # all pushes first: a multi-GPU device store then reduces every key in ONE bucketed fused launch per GPU
                 for i, param in live:
-                    self._kvstore.pull(i, param.list_grad(), priority=-i, ignore_sparse=False)
+                    self._kvstore.pull(i, param._raw_list_grad(), priority=-i, ignore_sparse=False)
 
     def update(self, batch_size, ignore_stale_grad=False):
         if not self._kv_initialized:
@@ -400,10 +413,11 @@ class Trainer(object):
             if param.grad_req == "null":
                 continue
             if self._kvstore and self._update_on_kvstore:
-                if param._stype == "default":
-                    self._kvstore.pull(i, param.list_data(), priority=-i)
+                # row_sparse parameters: the reference pulls the rows lazily from row_sparse_data(); the dense backing
+                # arrays kept here are refreshed in full instead (single box: a device copy)
+                self._kvstore.pull(i, param._raw_list_data(), priority=-i, ignore_sparse=False)
                 continue
-            for upd, arr, grad in zip(self._updaters, param.list_data(), param.list_grad()):
+            for upd, arr, grad in zip(self._updaters, param._raw_list_data(), param.list_grad()):
                 upd(i, grad, arr)
 
     # ---------------------------------------------------------------------------------- states

@@ -58,7 +58,7 @@ _GRAD_REQ_MAP = {"null": 0, "write": 1, "add": 3}
 
 class NDArray(object):
     """n-dimensional array on a Context.  ``arr.data_`` / ``arr._t`` is the torch tensor."""
-    __slots__ = ("_t", "_ctx", "_grad_req", "_grad_hook", "_bw_epoch", "__weakref__")
+    __slots__ = ("_t", "_ctx", "_grad_req", "_grad_hook", "_bw_epoch", "_grad_stype", "__weakref__")
     __array_priority__ = 1000.0
 
     def __init__(self, t, ctx=None):
@@ -124,7 +124,13 @@ class NDArray(object):
     @property
     def grad(self):
         g = self._t.grad
-        return None if g is None else NDArray(g, self._ctx)
+        if g is None:
+            return None
+        st = getattr(self, "_grad_stype", None)
+        if st in ("row_sparse", "csr"):        # attach_grad(stype=...): the gradient is exposed with that storage type
+            from .sparse import cast_storage
+            return cast_storage(NDArray(g, self._ctx), st)
+        return NDArray(g, self._ctx)
 
     def __repr__(self):
         return "\n%s\n<NDArray %s @%s>" % (str(self.asnumpy()), "x".join(str(s) for s in self.shape), self._ctx)
@@ -226,6 +232,8 @@ class NDArray(object):
         if self._t.grad is None:
             self._t.grad = torch.zeros_like(self._t)
         self._grad_req = grad_req
+        if stype is not None:
+            self._grad_stype = stype
         _ag._register_leaf(self)
 
     def backward(self, out_grad=None, retain_graph=False, train_mode=True):

@@ -160,6 +160,22 @@ class BaseSparseNDArray(NDArray):
         return "\n<%s %s @%s>" % (type(self).__name__, "x".join(map(str, self.shape)), self._ctx)
 
 
+def _recorded_dense(a, b, fn, ctx):
+    """Arithmetic on sparse arrays under ``autograd.record()``: when an operand carries a gradient (attach_grad /
+    mark_variables) the operation runs on the dense leaves so that it is taped -- the reference's storage fallback for
+    operators without a sparse backward.  Returns None when nothing needs recording."""
+    from .. import autograd as _ag
+    if not _ag.is_recording():
+        return None
+    has_leaf = lambda v: isinstance(v, BaseSparseNDArray) and v.__dict__.get("_dense_leaf") is not None   # noqa: E731
+    needs = has_leaf(a) or has_leaf(b) or (isinstance(b, NDArray) and not isinstance(b, BaseSparseNDArray) and b._t.requires_grad)
+    if not needs:
+        return None
+    tb = b._t if isinstance(b, NDArray) else b
+    return NDArray(fn(a._t, tb), ctx)
+
+
+
 class RowSparseNDArray(BaseSparseNDArray):
     stype = "row_sparse"
 
@@ -219,6 +235,9 @@ class RowSparseNDArray(BaseSparseNDArray):
             src.copyto(self)
 
     def _binary(self, other, fn):
+        rec = _recorded_dense(self, other, fn, self._ctx)
+        if rec is not None:
+            return rec
         if isinstance(other, RowSparseNDArray):
             return cast_storage(NDArray(fn(self.todense()._t, other.todense()._t), self._ctx), "row_sparse")
         if isinstance(other, NDArray):
@@ -295,6 +314,9 @@ class CSRNDArray(BaseSparseNDArray):
             src.astype(self._data.dtype).copyto(self)
 
     def _binary(self, other, fn):
+        rec = _recorded_dense(self, other, fn, self._ctx)
+        if rec is not None:
+            return rec
         if isinstance(other, BaseSparseNDArray):
             return cast_storage(NDArray(fn(self.todense()._t, other.todense()._t), self._ctx), "csr")
         if isinstance(other, NDArray):

@@ -798,6 +798,8 @@ def var(name, attr=None, shape=None, lr_mult=None, wd_mult=None, dtype=None, ini
         a["__dtype__"] = dtype_name(dtype)
     if init is not None:
         a["__init__"] = init if isinstance(init, str) else init.dumps()
+    if stype is not None:
+        a["__storage_type__"] = str({"default": 0, "row_sparse": 1, "csr": 2}[stype])    # _STORAGE_TYPE_STR_TO_ID
     for k, v in kwargs.items():
         if k.startswith("__") and k.endswith("__"):
             a[k] = str(v)
