@@ -24,7 +24,13 @@ _unary("radians", torch.deg2rad)
 _unary("fix", torch.trunc)
 _unary("rint", lambda t: torch.where((t - torch.floor(t)) <= 0.5, torch.floor(t), torch.ceil(t)))   # ties toward -inf like the reference
 _unary("_copy", lambda t: t.clone())
-_unary("_identity_with_attr_like_rhs", lambda t: t)
+
+
+@register(name="_identity_with_attr_like_rhs")
+def _identity_with_attr_like_rhs(lhs, rhs=None, out=None):
+    """Identity on ``lhs`` whose shape / storage attributes are declared equal to ``rhs`` (a shape-inference constraint in
+    the reference: src/operator/tensor/elemwise_unary_op_basic.cc)."""
+    return _out(_op(lambda t, *_r: t, *([lhs] if rhs is None else [lhs, rhs])), out)
 
 
 @register

@@ -268,7 +268,9 @@ class Symbol(object):
     def _bin(self, other, op, scalar_op, rev=False):
         if isinstance(other, Symbol):
             a, b = (other, self) if rev else (self, other)
-            return _make_op(op, [a, b], {})
+            # the reference's symbol operators are the same-shape element-wise ops (_Plus, ...): shape inference may unify
+            # the operands; evaluation here broadcasts, which is a superset
+            return _make_op(op, [a, b], {"__same_shape__": True})
         return _make_op(scalar_op, [self], {"scalar": float(other), "reverse": rev})
 
     def __add__(self, o):
@@ -446,6 +448,21 @@ class Symbol(object):
         """Returns ({var_name: shape}, [out shapes], {var_name: dtype}, [out dtypes])."""
         shapes = {k: ((int(v),) if isinstance(v, (int, np.integer)) else tuple(v)) for k, v in shapes.items() if v is not None}
         dtypes = dict(dtypes or {})
+        # partially known shapes (0 = unknown dimension) and variables without a shape: a bidirectional pre-pass completes what
+        # the graph determines (shape_solver.py: NNVM's forward + backward InferShape sweeps); the forward evaluation below
+        # then sees complete shapes
+        order0 = self._topo()
+        need = any(n.op is None and shapes.get(n.name) is None and
+                   not ("__shape__" in n.var_attrs and all(d > 0 for d in n.var_attrs["__shape__"])) for n in order0) \
+            or any(any(d == 0 for d in v) for v in shapes.values())
+        if need:
+            from .shape_solver import solve
+            solved, solved_heads = solve(self, shapes)
+            shapes = {k: v for k, v in shapes.items() if all(d > 0 for d in v)}
+            for k, v in solved.items():
+                shapes.setdefault(k, v)
+        else:
+            solved_heads = None
         vals = {}
         vshape, vdtype = {}, {}
         order = self._topo()
@@ -484,6 +501,8 @@ class Symbol(object):
             t = vals.get((id(n), i))
             out_shapes.append(tuple(t.shape) if t is not None else None)
             out_types.append(np_dtype(t.dtype) if t is not None else None)
+        if partial and solved_heads is not None:      # what the bidirectional pass knows about outputs the forward pass could not reach
+            out_shapes = [o if o is not None else h for o, h in zip(out_shapes, solved_heads)]
         return vshape, out_shapes, vdtype, out_types
 
     def infer_shape(self, *args, **kwargs):
