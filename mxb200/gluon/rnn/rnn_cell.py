@@ -37,7 +37,7 @@ class RecurrentCell(Block):
         axis = layout.find("T")
         from ... import symbol as _sym
         if isinstance(inputs, _sym.Symbol) or (isinstance(inputs, (list, tuple)) and inputs and isinstance(inputs[0], _sym.Symbol)):
-            return self._unroll_symbolic(_sym, length, inputs, begin_state, axis, merge_outputs)
+            return self._unroll_symbolic(_sym, length, inputs, begin_state, axis, merge_outputs, valid_length)
         if isinstance(inputs, nd.NDArray):
             batch_size = inputs.shape[layout.find("N")]
             seq = [x.squeeze(axis) for x in nd.split(inputs, num_outputs=length, axis=axis, squeeze_axis=False)] if length > 1 \
@@ -48,15 +48,25 @@ class RecurrentCell(Block):
         if begin_state is None:
             begin_state = self.begin_state(batch_size, ctx=seq[0].context, dtype=seq[0].dtype)
         states = begin_state
-        outputs = []
+        outputs, all_states = [], []
         for i in range(length):
             output, states = self(seq[i], states)
             outputs.append(output)
-        if merge_outputs is None or merge_outputs:
+            if valid_length is not None:
+                all_states.append(states)
+        if valid_length is not None:
+            # padded steps: outputs beyond a sequence's length are zero, the returned states are those of its last valid step
+            # (rnn_cell.py:_mask_sequence_variable_length / SequenceLast in the reference)
+            states = [nd.SequenceLast(nd.stack(*[st[k] for st in all_states], axis=0), sequence_length=valid_length,
+                                      use_sequence_length=True, axis=0) for k in range(len(states))]
+            masked = nd.SequenceMask(nd.stack(*outputs, axis=0), sequence_length=valid_length, use_sequence_length=True, axis=0)
+            outputs = [masked[i] for i in range(length)]
+        merged_in = isinstance(inputs, nd.NDArray)
+        if merge_outputs or (merge_outputs is None and merged_in):
             outputs = nd.stack(*outputs, axis=axis)
         return outputs, states
 
-    def _unroll_symbolic(self, F, length, inputs, begin_state, axis, merge_outputs):
+    def _unroll_symbolic(self, F, length, inputs, begin_state, axis, merge_outputs, valid_length=None):
         """unroll() on Symbols (rnn_cell.py:RecurrentCell.unroll of the reference): the steps become graph nodes named
         ``<prefix>t<k>_*``.  Default begin states are zeros derived from the first step's input, so no unknown (0)
         dimension enters the graph."""
@@ -76,11 +86,18 @@ class RecurrentCell(Block):
                     st = F.broadcast_axis(st, axis=ax, size=size)
                 begin_state.append(st)
         states = begin_state
-        outputs = []
+        outputs, all_states = [], []
         for i in range(length):
             output, states = self(seq[i], states)
             outputs.append(output)
-        if merge_outputs:
+            if valid_length is not None:
+                all_states.append(states)
+        if valid_length is not None:
+            states = [F.SequenceLast(F.stack(*[st[k] for st in all_states], axis=0), sequence_length=valid_length,
+                                     use_sequence_length=True, axis=0) for k in range(len(states))]
+            masked = F.SequenceMask(F.stack(*outputs, axis=0), sequence_length=valid_length, use_sequence_length=True, axis=0)
+            outputs = list(F.split(masked, axis=0, num_outputs=length, squeeze_axis=True)) if length > 1 else [F.squeeze(masked, axis=0)]
+        if merge_outputs or (merge_outputs is None and isinstance(inputs, F.Symbol)):
             outputs = F.stack(*outputs, axis=axis)
         return outputs, states
 
@@ -198,8 +215,8 @@ class SequentialRNNCell(RecurrentCell):
     def state_info(self, batch_size=0):
         return sum([c.state_info(batch_size) for c in self._children.values()], [])
 
-    def begin_state(self, **kwargs):
-        return sum([c.begin_state(**kwargs) for c in self._children.values()], [])
+    def begin_state(self, batch_size=0, **kwargs):
+        return sum([c.begin_state(batch_size, **kwargs) for c in self._children.values()], [])
 
     def __call__(self, inputs, states):
         self._counter += 1
@@ -212,6 +229,24 @@ class SequentialRNNCell(RecurrentCell):
             inputs, state = cell(inputs, state)
             next_states.append(state)
         return inputs, sum(next_states, [])
+
+    def unroll(self, length, inputs, begin_state=None, layout="NTC", merge_outputs=None, valid_length=None):
+        """Layer by layer: every child unrolls over the whole sequence and feeds the next one (rnn_cell.py:
+        SequentialRNNCell.unroll of the reference), so children that cannot be stepped (BidirectionalCell) are fine."""
+        self.reset()
+        children = list(self._children.values())
+        if not children:
+            return inputs, []
+        p = 0
+        next_states = []
+        for i, cell in enumerate(children):
+            n = len(cell.state_info())
+            st = None if begin_state is None else list(begin_state[p:p + n])
+            p += n
+            inputs, st = cell.unroll(length, inputs, begin_state=st, layout=layout,
+                                     merge_outputs=None if i < len(children) - 1 else merge_outputs, valid_length=valid_length)
+            next_states.extend(st)
+        return inputs, next_states
 
     def __len__(self):
         return len(self._children)
@@ -237,7 +272,7 @@ class DropoutCell(HybridRecurrentCell):
         return inputs, states
 
 
-class ResidualCell(RecurrentCell):
+class ResidualCell(HybridRecurrentCell):
     def __init__(self, base_cell):
         super(ResidualCell, self).__init__(prefix=base_cell.prefix + "res_", params=None)
         self.base_cell = base_cell
@@ -252,8 +287,44 @@ class ResidualCell(RecurrentCell):
         output, states = self.base_cell(inputs, states)
         return output + inputs, states
 
+    def unroll(self, length, inputs, begin_state=None, layout="NTC", merge_outputs=None, valid_length=None):
+        """Unrolls the base cell as a whole (so cells that cannot be stepped, like BidirectionalCell, work) and adds the
+        inputs step by step (rnn_cell.py:ResidualCell.unroll of the reference)."""
+        self.reset()
+        self.base_cell._modified = False
+        outputs, states = self.base_cell.unroll(length, inputs, begin_state=begin_state, layout=layout, merge_outputs=merge_outputs,
+                                                valid_length=valid_length)
+        self.base_cell._modified = True
+        axis = layout.find("T")
+        F, seq_in = _as_steps(inputs, length, axis)
+        if isinstance(outputs, (list, tuple)):
+            outputs = [o + i for o, i in zip(outputs, seq_in)]
+            if valid_length is not None:      # the residual re-introduces the padded inputs: mask again
+                m = F.SequenceMask(F.stack(*outputs, axis=0), sequence_length=valid_length, use_sequence_length=True, axis=0)
+                outputs = [m[i] for i in range(length)] if F is nd else list(F.split(m, axis=0, num_outputs=length, squeeze_axis=True))
+        else:
+            outputs = outputs + (F.stack(*seq_in, axis=axis) if isinstance(inputs, (list, tuple)) else inputs)
+            if valid_length is not None:
+                outputs = F.SequenceMask(outputs, sequence_length=valid_length, use_sequence_length=True, axis=axis)
+        return outputs, states
 
-class ZoneoutCell(RecurrentCell):
+
+def _as_steps(inputs, length, axis):
+    """(namespace, [step inputs]) for a merged tensor / symbol or a list of per-step tensors / symbols."""
+    from ... import symbol as _sym
+    first = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
+    F = _sym if isinstance(first, _sym.Symbol) else nd
+    if isinstance(inputs, (list, tuple)):
+        seq = list(inputs)
+    elif length > 1:
+        seq = list(F.split(inputs, axis=axis, num_outputs=length, squeeze_axis=True))
+    else:
+        seq = [F.squeeze(inputs, axis=axis)]
+    assert len(seq) == length, "unroll: got %d step inputs for length %d" % (len(seq), length)
+    return F, seq
+
+
+class ZoneoutCell(HybridRecurrentCell):
     """Zoneout (Krueger et al. 2016): with probability ``zoneout_states`` a state unit keeps its previous value, with
     ``zoneout_outputs`` an output unit keeps the previous output (rnn_cell.py:ZoneoutCell of the reference)."""
 
@@ -296,7 +367,7 @@ class ZoneoutCell(RecurrentCell):
         return output, new_states
 
 
-class BidirectionalCell(RecurrentCell):
+class BidirectionalCell(HybridRecurrentCell):
     def __init__(self, l_cell, r_cell, output_prefix="bi_"):
         super(BidirectionalCell, self).__init__(prefix="", params=None)
         self.l_cell, self.r_cell = l_cell, r_cell
@@ -312,17 +383,44 @@ class BidirectionalCell(RecurrentCell):
         raise NotImplementedError("Bidirectional cannot be stepped. Please use unroll")
 
     def unroll(self, length, inputs, begin_state=None, layout="NTC", merge_outputs=None, valid_length=None):
+        """Left cell over the sequence, right cell over the reversed sequence, per-step concatenation named
+        ``<output_prefix>t<k>_output`` (rnn_cell.py:BidirectionalCell.unroll of the reference).  Inputs: a merged NDArray /
+        Symbol or a list of per-step ones."""
+        self.reset()
         axis = layout.find("T")
-        if begin_state is None:
-            bs = inputs.shape[layout.find("N")]
-            begin_state = self.begin_state(batch_size=bs, ctx=inputs.context)
+        F, seq = _as_steps(inputs, length, axis)
         nl = len(self.l_cell.state_info())
-        l_out, l_st = self.l_cell.unroll(length, inputs, begin_state[:nl], layout, merge_outputs=True)
-        r_out, r_st = self.r_cell.unroll(length, nd.flip(inputs, axis=axis), begin_state[nl:], layout, merge_outputs=True)
-        out = nd.concat(l_out, nd.flip(r_out, axis=axis), dim=2)
-        return out, l_st + r_st
+        if begin_state is None:
+            l_begin = r_begin = None
+        else:
+            l_begin, r_begin = list(begin_state[:nl]), list(begin_state[nl:])
+        if valid_length is None:
+            rev_in = list(reversed(seq))
+        else:       # reverse every sequence inside its own length (padding stays at the end)
+            rv = F.SequenceReverse(F.stack(*seq, axis=0), sequence_length=valid_length, use_sequence_length=True, axis=0)
+            rev_in = [rv[i] for i in range(length)] if F is nd else list(F.split(rv, axis=0, num_outputs=length, squeeze_axis=True))
+        l_out, l_st = self.l_cell.unroll(length, seq, begin_state=l_begin, layout=layout, merge_outputs=False, valid_length=valid_length)
+        r_out, r_st = self.r_cell.unroll(length, rev_in, begin_state=r_begin, layout=layout, merge_outputs=False, valid_length=valid_length)
+        if valid_length is None:
+            r_out = list(reversed(list(r_out)))
+        else:
+            rr = F.SequenceReverse(F.stack(*r_out, axis=0), sequence_length=valid_length, use_sequence_length=True, axis=0)
+            r_out = [rr[i] for i in range(length)] if F is nd else list(F.split(rr, axis=0, num_outputs=length, squeeze_axis=True))
+        if F is nd:
+            outs = [nd.concat(lo, ro, dim=1) for lo, ro in zip(l_out, r_out)]
+        else:
+            outs = [F.Concat(lo, ro, dim=1, name="%st%d" % (self._output_prefix, i)) for i, (lo, ro) in enumerate(zip(l_out, r_out))]
+        merged_in = not isinstance(inputs, (list, tuple))
+        if merge_outputs or (merge_outputs is None and merged_in):
+            outs = F.stack(*outs, axis=axis)
+        return outs, list(l_st) + list(r_st)
 
 
 # the reference distinguishes a hybridizable stack; every cell here runs on both NDArrays and Symbols
-HybridSequentialRNNCell = SequentialRNNCell
+class HybridSequentialRNNCell(SequentialRNNCell, HybridBlock):
+    """SequentialRNNCell that may be nested inside a HybridBlock (its children must be hybrid cells themselves)."""
+
+    def __init__(self, prefix=None, params=None):
+        super(HybridSequentialRNNCell, self).__init__(prefix=prefix, params=params)
+
 ModifierCell = ResidualCell.__mro__[1] if False else RecurrentCell

@@ -83,6 +83,35 @@ class _RNNLayer(HybridBlock):
                     self._param_names.append(name)
             ni = nh * self._dir
 
+    def __getattr__(self, name):
+        # layer.l0_i2h_weight etc.: the per-layer parameters are attributes in the reference
+        reg = self.__dict__.get("_reg_params")
+        if reg is not None and name in reg:
+            return reg[name]
+        raise AttributeError("'%s' object has no attribute '%s'" % (type(self).__name__, name))
+
+    def _unfuse(self):
+        """The same network as a stack of cells sharing this layer's parameters (rnn_layer.py:115-149 of the reference):
+        one (Bidirectional) cell per layer, DropoutCell in between."""
+        from . import rnn_cell
+        make = {"rnn_relu": lambda **kw: rnn_cell.RNNCell(self._hidden_size, activation="relu", **kw),
+                "rnn_tanh": lambda **kw: rnn_cell.RNNCell(self._hidden_size, activation="tanh", **kw),
+                "lstm": lambda **kw: rnn_cell.LSTMCell(self._hidden_size, **kw),
+                "gru": lambda **kw: rnn_cell.GRUCell(self._hidden_size, **kw)}[self._mode]
+        stack = rnn_cell.HybridSequentialRNNCell(prefix=self.prefix, params=self.params)
+        with stack.name_scope():
+            ni = self._input_size
+            for i in range(self._num_layers):
+                kw = {"input_size": ni}
+                if self._dir == 2:
+                    stack.add(rnn_cell.BidirectionalCell(make(prefix="l%d_" % i, **kw), make(prefix="r%d_" % i, **kw)))
+                else:
+                    stack.add(make(prefix="l%d_" % i, **kw))
+                if self._dropout > 0 and i != self._num_layers - 1:
+                    stack.add(rnn_cell.DropoutCell(self._dropout))
+                ni = self._hidden_size * self._dir
+        return stack
+
     def _infer_param_shapes(self, x, *args):
         ni = x.shape[2]
         ng, nh = self._gates, self._hidden_size
