@@ -166,7 +166,13 @@ class RNNCell(_BaseCell):
 
 
 class LSTMCell(_BaseCell):
+    """``activation`` (cell transform / output squashing, default tanh) and ``recurrent_activation`` (the three gates,
+    default sigmoid) take any Activation type name (rnn_cell.py:LSTMCell of the reference)."""
     _ngates = 4
+
+    def __init__(self, hidden_size, activation="tanh", recurrent_activation="sigmoid", **kwargs):
+        super(LSTMCell, self).__init__(hidden_size, **kwargs)
+        self._activation, self._recurrent_activation = activation, recurrent_activation
 
     def _alias(self):
         return "lstm"
@@ -181,10 +187,12 @@ class LSTMCell(_BaseCell):
         h2h = F.FullyConnected(states[0], h2h_weight, h2h_bias, num_hidden=self._hidden_size * 4, name=prefix + "h2h")
         gates = i2h + h2h
         s = F.split(gates, num_outputs=4, axis=1, name=prefix + "slice")
-        in_gate, forget_gate = F.sigmoid(s[0]), F.sigmoid(s[1])
-        in_transform, out_gate = F.tanh(s[2]), F.sigmoid(s[3])
+        act = lambda x, kind: F.Activation(x, act_type=kind)   # noqa: E731
+        ra, ca = self._recurrent_activation, self._activation
+        in_gate, forget_gate = act(s[0], ra), act(s[1], ra)
+        in_transform, out_gate = act(s[2], ca), act(s[3], ra)
         next_c = F._internal._plus(forget_gate * states[1], in_gate * in_transform, name=prefix + "state")
-        next_h = F._internal._mul(out_gate, F.tanh(next_c), name=prefix + "out")
+        next_h = F._internal._mul(out_gate, act(next_c, ca), name=prefix + "out")
         return next_h, [next_h, next_c]
 
 

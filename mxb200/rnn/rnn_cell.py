@@ -9,7 +9,8 @@ from .. import symbol
 from ..base import MXNetError
 
 __all__ = ["RNNParams", "BaseRNNCell", "RNNCell", "LSTMCell", "GRUCell", "FusedRNNCell", "SequentialRNNCell", "DropoutCell",
-           "ModifierCell", "ZoneoutCell", "ResidualCell", "BidirectionalCell"]
+           "ModifierCell", "ZoneoutCell", "ResidualCell", "BidirectionalCell", "BaseConvRNNCell", "ConvRNNCell", "ConvLSTMCell",
+           "ConvGRUCell"]
 
 
 class RNNParams(object):
@@ -129,11 +130,11 @@ class BaseRNNCell(object):
         col = symbol.sum(symbol.reshape(x, shape=(0, -1)), axis=1, keepdims=True) * 0.0          # [N, 1] zeros
         states = []
         for info in self.state_info:
-            shape = info["shape"]
-            z = symbol.broadcast_add(symbol.zeros(shape=(1, shape[-1])), col)                      # [N, H]
-            if len(shape) == 3:                                                                     # fused: [L, N, H]
-                z = symbol.broadcast_add(symbol.zeros(shape=(shape[0], 1, shape[-1])), symbol.expand_dims(z, axis=0))
-            states.append(z)
+            shape = tuple(info["shape"])
+            b = shape.index(0) if 0 in shape else 0                  # the batch axis: 0 for cells, 1 for the fused [L, N, H] state
+            unit = tuple(1 if i == b else d for i, d in enumerate(shape))
+            n_shape = tuple(-1 if i == b else 1 for i in range(len(shape)))
+            states.append(symbol.broadcast_add(symbol.zeros(shape=unit), symbol.reshape(col, shape=n_shape)))
         return states
 
     def unroll(self, length, inputs, begin_state=None, layout="NTC", merge_outputs=None):
@@ -573,3 +574,139 @@ class FusedRNNCell(BaseRNNCell):
             if self._dropout > 0 and i != self._num_layers - 1:
                 stack.add(DropoutCell(self._dropout, prefix="%s_dropout%d_" % (self._prefix, i)))
         return stack
+
+
+# ---------------------------------------------------------------------------------------------------- convolutional cells
+class BaseConvRNNCell(BaseRNNCell):
+    """Cells whose input-to-hidden and hidden-to-hidden transforms are convolutions (Shi et al. 2015; reference:
+    python/mxnet/rnn/rnn_cell.py:1094-1190).  ``input_shape`` is the per-step input (N, C, spatial...); the state has the
+    shape of the i2h convolution's output with ``num_hidden`` channels; the h2h convolution is padded to keep that shape."""
+
+    def __init__(self, input_shape, num_hidden, h2h_kernel, h2h_dilate, i2h_kernel, i2h_stride, i2h_pad, i2h_dilate,
+                 i2h_weight_initializer, h2h_weight_initializer, i2h_bias_initializer, h2h_bias_initializer, activation, prefix="",
+                 params=None, conv_layout="NCHW"):
+        super(BaseConvRNNCell, self).__init__(prefix=prefix, params=params)
+        self._h2h_kernel, self._h2h_dilate = tuple(h2h_kernel), tuple(h2h_dilate)
+        assert all(k % 2 == 1 for k in self._h2h_kernel), "Only support odd number, get h2h_kernel= %s" % str(h2h_kernel)
+        self._h2h_pad = tuple(d * (k - 1) // 2 for k, d in zip(self._h2h_kernel, self._h2h_dilate))
+        self._i2h_kernel, self._i2h_stride = tuple(i2h_kernel), tuple(i2h_stride)
+        self._i2h_pad, self._i2h_dilate = tuple(i2h_pad), tuple(i2h_dilate)
+        self._num_hidden, self._input_shape, self._conv_layout = num_hidden, tuple(input_shape), conv_layout
+        self._activation = activation
+        # state shape = output shape of the i2h convolution
+        data = symbol.Variable("data")
+        conv = symbol.Convolution(data=data, num_filter=num_hidden, kernel=self._i2h_kernel, stride=self._i2h_stride,
+                                  pad=self._i2h_pad, dilate=self._i2h_dilate, layout=conv_layout)
+        self._state_shape = (0,) + tuple(conv.infer_shape(data=self._input_shape)[1][0][1:])
+        self._iW = self.params.get("i2h_weight", init=i2h_weight_initializer)
+        self._hW = self.params.get("h2h_weight", init=h2h_weight_initializer)
+        self._iB = self.params.get("i2h_bias", init=i2h_bias_initializer)
+        self._hB = self.params.get("h2h_bias", init=h2h_bias_initializer)
+
+    @property
+    def _num_gates(self):
+        return len(self._gate_names)
+
+    @property
+    def state_info(self):
+        return [{"shape": self._state_shape, "__layout__": self._conv_layout},
+                {"shape": self._state_shape, "__layout__": self._conv_layout}]
+
+    def _conv_forward(self, inputs, states, name):
+        nf = self._num_hidden * self._num_gates
+        i2h = symbol.Convolution(name="%si2h" % name, data=inputs, num_filter=nf, kernel=self._i2h_kernel, stride=self._i2h_stride,
+                                 pad=self._i2h_pad, dilate=self._i2h_dilate, weight=self._iW, bias=self._iB, layout=self._conv_layout)
+        h2h = symbol.Convolution(name="%sh2h" % name, data=states[0], num_filter=nf, kernel=self._h2h_kernel, dilate=self._h2h_dilate,
+                                 pad=self._h2h_pad, stride=(1,) * len(self._h2h_kernel), weight=self._hW, bias=self._hB,
+                                 layout=self._conv_layout)
+        return i2h, h2h
+
+    def __call__(self, inputs, states):
+        raise NotImplementedError("BaseConvRNNCell is abstract class for convolutional RNN")
+
+
+class ConvRNNCell(BaseConvRNNCell):
+    def __init__(self, input_shape, num_hidden, h2h_kernel=(3, 3), h2h_dilate=(1, 1), i2h_kernel=(3, 3), i2h_stride=(1, 1),
+                 i2h_pad=(1, 1), i2h_dilate=(1, 1), i2h_weight_initializer=None, h2h_weight_initializer=None,
+                 i2h_bias_initializer="zeros", h2h_bias_initializer="zeros", activation=None, prefix="ConvRNN_", params=None,
+                 conv_layout="NCHW"):
+        act = activation if activation is not None else (lambda x, **kw: symbol.LeakyReLU(x, act_type="leaky", slope=0.2, **kw))
+        super(ConvRNNCell, self).__init__(input_shape, num_hidden, h2h_kernel, h2h_dilate, i2h_kernel, i2h_stride, i2h_pad, i2h_dilate,
+                                          i2h_weight_initializer, h2h_weight_initializer, i2h_bias_initializer, h2h_bias_initializer,
+                                          act, prefix=prefix, params=params, conv_layout=conv_layout)
+
+    @property
+    def _gate_names(self):
+        return ("",)
+
+    @property
+    def state_info(self):
+        return [{"shape": self._state_shape, "__layout__": self._conv_layout}]
+
+    def __call__(self, inputs, states):
+        self._counter += 1
+        name = "%st%d_" % (self._prefix, self._counter)
+        i2h, h2h = self._conv_forward(inputs, states, name)
+        output = self._get_activation(i2h + h2h, self._activation, name="%sout" % name)
+        return output, [output]
+
+
+class ConvLSTMCell(BaseConvRNNCell):
+    def __init__(self, input_shape, num_hidden, h2h_kernel=(3, 3), h2h_dilate=(1, 1), i2h_kernel=(3, 3), i2h_stride=(1, 1),
+                 i2h_pad=(1, 1), i2h_dilate=(1, 1), i2h_weight_initializer=None, h2h_weight_initializer=None,
+                 i2h_bias_initializer="zeros", h2h_bias_initializer="zeros", activation=None, prefix="ConvLSTM_", params=None,
+                 conv_layout="NCHW"):
+        act = activation if activation is not None else (lambda x, **kw: symbol.LeakyReLU(x, act_type="leaky", slope=0.2, **kw))
+        super(ConvLSTMCell, self).__init__(input_shape, num_hidden, h2h_kernel, h2h_dilate, i2h_kernel, i2h_stride, i2h_pad, i2h_dilate,
+                                           i2h_weight_initializer, h2h_weight_initializer, i2h_bias_initializer, h2h_bias_initializer,
+                                           act, prefix=prefix, params=params, conv_layout=conv_layout)
+
+    @property
+    def _gate_names(self):
+        return ["_i", "_f", "_c", "_o"]
+
+    def __call__(self, inputs, states):
+        self._counter += 1
+        name = "%st%d_" % (self._prefix, self._counter)
+        i2h, h2h = self._conv_forward(inputs, states, name)
+        ch = self._conv_layout.find("C")
+        gates = symbol.SliceChannel(i2h + h2h, num_outputs=4, axis=ch, name="%sslice" % name)
+        in_gate = symbol.Activation(gates[0], act_type="sigmoid", name="%si" % name)
+        forget_gate = symbol.Activation(gates[1], act_type="sigmoid", name="%sf" % name)
+        in_transform = self._get_activation(gates[2], self._activation, name="%sc" % name)
+        out_gate = symbol.Activation(gates[3], act_type="sigmoid", name="%so" % name)
+        next_c = symbol._internal._plus(forget_gate * states[1], in_gate * in_transform, name="%sstate" % name)
+        next_h = symbol._internal._mul(out_gate, self._get_activation(next_c, self._activation), name="%sout" % name)
+        return next_h, [next_h, next_c]
+
+
+class ConvGRUCell(BaseConvRNNCell):
+    def __init__(self, input_shape, num_hidden, h2h_kernel=(3, 3), h2h_dilate=(1, 1), i2h_kernel=(3, 3), i2h_stride=(1, 1),
+                 i2h_pad=(1, 1), i2h_dilate=(1, 1), i2h_weight_initializer=None, h2h_weight_initializer=None,
+                 i2h_bias_initializer="zeros", h2h_bias_initializer="zeros", activation=None, prefix="ConvGRU_", params=None,
+                 conv_layout="NCHW"):
+        act = activation if activation is not None else (lambda x, **kw: symbol.LeakyReLU(x, act_type="leaky", slope=0.2, **kw))
+        super(ConvGRUCell, self).__init__(input_shape, num_hidden, h2h_kernel, h2h_dilate, i2h_kernel, i2h_stride, i2h_pad, i2h_dilate,
+                                          i2h_weight_initializer, h2h_weight_initializer, i2h_bias_initializer, h2h_bias_initializer,
+                                          act, prefix=prefix, params=params, conv_layout=conv_layout)
+
+    @property
+    def _gate_names(self):
+        return ["_r", "_z", "_o"]
+
+    @property
+    def state_info(self):
+        return [{"shape": self._state_shape, "__layout__": self._conv_layout}]
+
+    def __call__(self, inputs, states):
+        self._counter += 1
+        name = "%st%d_" % (self._prefix, self._counter)
+        i2h, h2h = self._conv_forward(inputs, states, name)
+        ch = self._conv_layout.find("C")
+        i2h_r, i2h_z, i2h = symbol.SliceChannel(i2h, num_outputs=3, axis=ch, name="%si2h_slice" % name)
+        h2h_r, h2h_z, h2h = symbol.SliceChannel(h2h, num_outputs=3, axis=ch, name="%sh2h_slice" % name)
+        reset_gate = symbol.Activation(i2h_r + h2h_r, act_type="sigmoid", name="%sr_act" % name)
+        update_gate = symbol.Activation(i2h_z + h2h_z, act_type="sigmoid", name="%sz_act" % name)
+        next_h_tmp = self._get_activation(i2h + reset_gate * h2h, self._activation, name="%sh_act" % name)
+        next_h = symbol._internal._plus((1.0 - update_gate) * next_h_tmp, update_gate * states[0], name="%sout" % name)
+        return next_h, [next_h]
