@@ -76,14 +76,15 @@ class LSTMPCell(HybridRecurrentCell):
         return "lstmp"
 
     def hybrid_forward(self, F, inputs, states, i2h_weight, h2h_weight, h2r_weight, i2h_bias, h2h_bias):
-        i2h = F.FullyConnected(inputs, i2h_weight, i2h_bias, num_hidden=self._hidden_size * 4)
-        h2h = F.FullyConnected(states[0], h2h_weight, h2h_bias, num_hidden=self._hidden_size * 4)
-        s = F.split(i2h + h2h, num_outputs=4, axis=1)
+        prefix = "t%d_" % self._counter            # node names of the reference cell
+        i2h = F.FullyConnected(inputs, i2h_weight, i2h_bias, num_hidden=self._hidden_size * 4, name=prefix + "i2h")
+        h2h = F.FullyConnected(states[0], h2h_weight, h2h_bias, num_hidden=self._hidden_size * 4, name=prefix + "h2h")
+        s = F.split(i2h + h2h, num_outputs=4, axis=1, name=prefix + "slice")
         in_gate, forget_gate = F.sigmoid(s[0]), F.sigmoid(s[1])
         in_transform, out_gate = F.tanh(s[2]), F.sigmoid(s[3])
-        next_c = forget_gate * states[1] + in_gate * in_transform
-        hidden = out_gate * F.tanh(next_c)
-        next_r = F.FullyConnected(hidden, h2r_weight, no_bias=True, num_hidden=self._projection_size)
+        next_c = F._internal._plus(forget_gate * states[1], in_gate * in_transform, name=prefix + "state")
+        hidden = F._internal._mul(out_gate, F.tanh(next_c), name=prefix + "hidden")
+        next_r = F.FullyConnected(hidden, h2r_weight, no_bias=True, num_hidden=self._projection_size, name=prefix + "out")
         return next_r, [next_r, next_c]
 
 
@@ -112,7 +113,8 @@ class _BaseConvRNNCell(HybridRecurrentCell):
         self._state_shape = (hidden_channels,) + tuple(
             (s + 2 * p - d * (k - 1) - 1) + 1 for s, p, d, k in zip(spatial, self._i2h_pad, self._i2h_dilate, self._i2h_kernel))
         g = self._ngates
-        self.i2h_weight = self.params.get("i2h_weight", shape=(g * hidden_channels, in_c) + self._i2h_kernel, init=i2h_weight_initializer)
+        self.i2h_weight = self.params.get("i2h_weight", shape=(g * hidden_channels, in_c) + self._i2h_kernel, init=i2h_weight_initializer,
+                                          allow_deferred_init=True)
         self.h2h_weight = self.params.get("h2h_weight", shape=(g * hidden_channels, hidden_channels) + self._h2h_kernel, init=h2h_weight_initializer)
         self.i2h_bias = self.params.get("i2h_bias", shape=(g * hidden_channels,), init=i2h_bias_initializer)
         self.h2h_bias = self.params.get("h2h_bias", shape=(g * hidden_channels,), init=h2h_bias_initializer)
@@ -122,14 +124,22 @@ class _BaseConvRNNCell(HybridRecurrentCell):
 
     def _conv_forward(self, F, inputs, states, i2h_weight, h2h_weight, i2h_bias, h2h_bias):
         g = self._ngates
+        prefix = "t%d_" % self._counter
         i2h = F.Convolution(inputs, i2h_weight, i2h_bias, kernel=self._i2h_kernel, stride=self._stride, pad=self._i2h_pad,
-                            dilate=self._i2h_dilate, num_filter=g * self._hidden_channels)
+                            dilate=self._i2h_dilate, num_filter=g * self._hidden_channels, name=prefix + "i2h")
         h2h = F.Convolution(states[0], h2h_weight, h2h_bias, kernel=self._h2h_kernel, stride=self._stride, pad=self._h2h_pad,
-                            dilate=self._h2h_dilate, num_filter=g * self._hidden_channels)
+                            dilate=self._h2h_dilate, num_filter=g * self._hidden_channels, name=prefix + "h2h")
         return i2h, h2h
 
-    def _act(self, F, x):
-        return F.Activation(x, act_type=self._activation) if isinstance(self._activation, str) else self._activation(x)
+    def _act(self, F, x, name=None):
+        kw = {"name": name} if (name is not None and F is not nd) else {}
+        return F.Activation(x, act_type=self._activation, **kw) if isinstance(self._activation, str) else self._activation(x, **kw)
+
+    def _infer_param_shapes(self, x, *args):
+        # input_shape was given with 0 channels: the channel count comes from the first input
+        w = self.i2h_weight
+        if w.shape is not None and w.shape[1] == 0:
+            w.shape = (w.shape[0], x.shape[1]) + tuple(w.shape[2:])
 
 
 class _ConvRNNCell(_BaseConvRNNCell):
@@ -140,7 +150,7 @@ class _ConvRNNCell(_BaseConvRNNCell):
 
     def hybrid_forward(self, F, inputs, states, i2h_weight, h2h_weight, i2h_bias, h2h_bias):
         i2h, h2h = self._conv_forward(F, inputs, states, i2h_weight, h2h_weight, i2h_bias, h2h_bias)
-        out = self._act(F, i2h + h2h)
+        out = self._act(F, i2h + h2h, name="t%d_out" % self._counter)
         return out, [out]
 
 
@@ -159,8 +169,9 @@ class _ConvLSTMCell(_BaseConvRNNCell):
         s = F.split(i2h + h2h, num_outputs=4, axis=1)
         in_gate, forget_gate = F.sigmoid(s[0]), F.sigmoid(s[1])
         in_transform, out_gate = self._act(F, s[2]), F.sigmoid(s[3])
-        next_c = forget_gate * states[1] + in_gate * in_transform
-        next_h = out_gate * self._act(F, next_c)
+        prefix = "t%d_" % self._counter
+        next_c = F._internal._plus(forget_gate * states[1], in_gate * in_transform, name=prefix + "state")
+        next_h = F._internal._mul(out_gate, self._act(F, next_c), name=prefix + "out")
         return next_h, [next_h, next_c]
 
 
@@ -176,7 +187,7 @@ class _ConvGRUCell(_BaseConvRNNCell):
         h2h_r, h2h_z, h2h_n = F.split(h2h, num_outputs=3, axis=1)
         reset_gate, update_gate = F.sigmoid(i2h_r + h2h_r), F.sigmoid(i2h_z + h2h_z)
         cand = self._act(F, i2h_n + reset_gate * h2h_n)
-        next_h = (1. - update_gate) * cand + update_gate * states[0]
+        next_h = F._internal._plus((1. - update_gate) * cand, update_gate * states[0], name="t%d_out" % self._counter)
         return next_h, [next_h]
 
 
