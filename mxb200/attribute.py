@@ -2,7 +2,23 @@
 import threading
 
 
-class AttrScope(object):
+class _ScopeMeta(type):
+    """``AttrScope.current``: the calling thread's innermost scope, readable and assignable on the class
+    (python/mxnet/attribute.py of the reference: classproperty over a thread-local)."""
+
+    @property
+    def current(cls):
+        cur = getattr(cls._current, "value", None)
+        if cur is None:
+            cur = cls._current.value = cls()
+        return cur
+
+    @current.setter
+    def current(cls, value):
+        cls._current.value = value
+
+
+class AttrScope(object, metaclass=_ScopeMeta):
     _current = threading.local()
 
     def __init__(self, **kwargs):

@@ -70,11 +70,16 @@ class _BlockScope(object):
             return self
         self._old_scope = getattr(_BlockScope._current, "value", None)
         _BlockScope._current.value = self
+        from .. import name as _name
+        self._name_scope = _name.Prefix(self._block.prefix)     # symbols created inside are named <block prefix><hint><n>
+        self._name_scope.__enter__()
         return self
 
     def __exit__(self, ptype, value, trace):
         if self._block._empty_prefix:
             return
+        self._name_scope.__exit__(ptype, value, trace)
+        self._name_scope = None
         _BlockScope._current.value = self._old_scope
 
 

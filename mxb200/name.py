@@ -8,16 +8,23 @@ import warnings
 __all__ = ["NameManager", "Prefix"]
 
 
-class _Current(object):
-    def __get__(self, obj, owner):
+class _ManagerMeta(type):
+    """``NameManager.current``: the calling thread's manager, readable (deprecated in favour of ``with``) and assignable on
+    the class (python/mxnet/name.py of the reference: classproperty over a thread-local)."""
+
+    @property
+    def current(cls):
         warnings.warn("NameManager.current has been deprecated. It is advised to use the `with` statement with NameManager.",
                       DeprecationWarning)
-        return owner._get_current()
+        return cls._get_current()
+
+    @current.setter
+    def current(cls, value):
+        NameManager._current.value = value
 
 
-class NameManager(object):
+class NameManager(object, metaclass=_ManagerMeta):
     _current = threading.local()
-    current = _Current()
 
     def __init__(self):
         self._counter = {}

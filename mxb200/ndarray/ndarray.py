@@ -286,7 +286,11 @@ class NDArray(object):
         shape = _mx_reshape(self.shape, shape)
         return _op(lambda t: t.reshape(shape), self)
 
-    def reshape_like(self, other):
+    def reshape_like(self, other=None, rhs=None, **kwargs):
+        other = rhs if other is None else other
+        if kwargs:                               # lhs_begin / lhs_end / rhs_begin / rhs_end ranges: the operator handles them
+            from . import op as _op_mod
+            return _op_mod.reshape_like(self, other, **kwargs)
         return self.reshape(other.shape)
 
     def flatten(self):

@@ -275,11 +275,15 @@ def topk(data, axis=-1, k=1, ret_typ="indices", is_ascend=False, dtype="float32"
 
 @register
 def sort(data, axis=-1, is_ascend=True, out=None):
+    if axis is None or axis == "None":           # the flattened array is sorted (ordering_op-inl.h: axis=None)
+        return _out(_op(lambda t: torch.sort(t.reshape(-1), dim=0, descending=not is_ascend)[0], data), out)
     return _out(_op(lambda t: torch.sort(t, dim=axis, descending=not is_ascend)[0], data), out)
 
 
 @register
 def argsort(data, axis=-1, is_ascend=True, dtype="float32", out=None):
+    if axis is None or axis == "None":
+        return _out(_op(lambda t: torch.argsort(t.reshape(-1), dim=0, descending=not is_ascend).to(torch_dtype(dtype)), data), out)
     return _out(_op(lambda t: torch.argsort(t, dim=axis, descending=not is_ascend).to(torch_dtype(dtype)), data), out)
 
 

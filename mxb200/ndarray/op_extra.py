@@ -150,8 +150,10 @@ def _eye(N=1, M=0, k=0, ctx=None, dtype="float32", out=None):
     c, dev = _ctx_dev(ctx)
     m = int(M) if int(M) > 0 else int(N)
     t = torch.zeros(int(N), m, dtype=torch_dtype(dtype), device=dev)
-    idx = torch.arange(max(0, -int(k)), min(int(N), m - int(k)), device=dev)
-    t[idx, idx + int(k)] = 1
+    lo, hi = max(0, -int(k)), min(int(N), m - int(k))
+    if hi > lo:                                  # a diagonal outside the matrix leaves it all zeros (numpy.eye)
+        idx = torch.arange(lo, hi, device=dev)
+        t[idx, idx + int(k)] = 1
     return _out(NDArray(t, c), out)
 
 

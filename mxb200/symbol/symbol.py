@@ -127,8 +127,10 @@ class _NameManager(object):
 
     @classmethod
     def resolve(cls, name, hint):
+        # inside a Gluon name scope the current NameManager is a ``Prefix(block.prefix)`` pushed by _BlockScope.__enter__
+        # (python/mxnet/gluon/block.py:_BlockScope of the reference), so the block prefix is already part of the name
         from ..name import NameManager
-        return cls.prefix() + NameManager._get_current().get(name, hint)
+        return NameManager._get_current().get(name, hint)
 
     @classmethod
     def prefix(cls):
