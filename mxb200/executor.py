@@ -133,19 +133,39 @@ class Executor(object):
                     name, str(self.arg_dict[name].shape), str(array.shape)))
         feed = dict(self.arg_dict)
         feed.update(self.aux_dict)
+        mon = self._make_monitor() if self._monitor_callback is not None else None
         if is_train or self.grad_dict:
             # an executor bound with gradient arrays can always run backward(), also after forward(is_train=False): the
             # mode only selects training / inference behaviour of the operators (graph_executor.cc RunOps)
             with autograd.record(train_mode=bool(is_train)):
-                self.outputs = self._symbol.eval_nd(feed, self._group2ctx)
+                self.outputs = self._symbol.eval_nd(feed, self._group2ctx, monitor=mon)
         else:
             with autograd.pause(train_mode=False):
-                self.outputs = self._symbol.eval_nd(feed, self._group2ctx)
+                self.outputs = self._symbol.eval_nd(feed, self._group2ctx, monitor=mon)
         self._ran_forward = True
-        if self._monitor_callback is not None:
-            for name, out in zip(self._output_names, self.outputs):
-                self._monitor_callback(name, out)
         return self.outputs
+
+    def _make_monitor(self):
+        """Adapter between Symbol.eval_nd's (name, array, when) and the user's monitor callback: operator outputs are
+        reported at once; for the backward pass a hook on every operator input reports the gradient that reaches it
+        (inputs that carry no gradient -- data, labels -- are reported as zeros after backward, like the reference's backward
+        graph which materialises them)."""
+        cb = self._monitor_callback
+        self._mon_nograd = []
+
+        def mon(name, arr, when):
+            if when == "forward":
+                cb(name, arr)
+                return
+            t = arr._t if hasattr(arr, "_t") else None
+            if t is None:
+                return
+            if t.requires_grad and t.is_floating_point():
+                ctx = arr.context
+                t.register_hook(lambda g, name=name, ctx=ctx: (cb(name, NDArray(g.detach(), ctx)), None)[1])
+            else:
+                self._mon_nograd.append((name, arr))
+        return mon
 
     def backward(self, out_grads=None, is_train=True):
         if out_grads is None:
@@ -164,6 +184,10 @@ class Executor(object):
             hgrads.append(out_grads[i] if i < len(out_grads) else None)
         if heads:
             autograd.backward(heads, hgrads)
+        if self._monitor_callback is not None:
+            for name, arr in getattr(self, "_mon_nograd", []):
+                self._monitor_callback(name, nd.zeros(arr.shape, ctx=arr.context, dtype=arr.dtype))
+            self._mon_nograd = []
         # keep grad handles pointing at the live tensors
         for n, g in self.grad_dict.items():
             live = self.arg_dict[n]._t.grad

@@ -109,7 +109,7 @@ class DataParallelExecutorGroup(object):
             for desc in list(data_shapes) + list(label_shapes or []):
                 if isinstance(desc, DataDesc):
                     type_dict[desc.name] = desc.dtype
-            ex = Executor.simple_bind(self.symbol, ctx, self.grad_req, type_dict, None, shapes)
+            ex = Executor.simple_bind(self.symbol, ctx, self.grad_req, type_dict, self._group2ctx_of(i), shapes)
             if reshape and old_execs:
                 ex.copy_params_from({n: old_execs[i].arg_dict[n] for n in self.param_names},
                                     old_execs[i].aux_dict, allow_extra_params=True)
@@ -128,6 +128,24 @@ class DataParallelExecutorGroup(object):
                 ex.aux_arrays = [ex.aux_dict[n] for n in self.aux_names]
             self.execs.append(ex)
         self._collect_arrays()
+
+    def _group2ctx_of(self, i):
+        """ctx_group -> context map of the i-th executor (executor_group.py:_prepare_group2ctxs of the reference): one dict
+        for every device, a list of dicts (one per device), or a dict whose values are per-device lists."""
+        g = self.group2ctxs
+        if not g:
+            return None
+        if isinstance(g, (list, tuple)):
+            assert len(g) == len(self.contexts), "length of group2ctxs should be %d" % len(self.contexts)
+            return g[i]
+        out = {}
+        for k, v in g.items():
+            if isinstance(v, (list, tuple)):
+                assert len(v) in (1, len(self.contexts)), "length of group2ctxs[%s] should be %d or 1" % (k, len(self.contexts))
+                out[k] = v[i] if len(v) > 1 else v[0]
+            else:
+                out[k] = v
+        return out
 
     def _sliced_shape(self, shape, i, axis):
         shape = list(shape)

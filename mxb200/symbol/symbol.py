@@ -575,14 +575,30 @@ class Symbol(object):
         return arg_types, out_types, aux_types
 
     # ---- execution ---------------------------------------------------------------------------------
-    def eval_nd(self, feed, group2ctx=None):
+    def eval_nd(self, feed, group2ctx=None, monitor=None):
         """Run the graph on NDArrays: feed maps variable name -> NDArray.  Returns list of outputs.
         ``group2ctx``: model parallelism by placement -- a node whose ``ctx_group`` attribute (AttrScope) is a key of
         the map runs on that context; inputs coming from another device are copied there first (the reference inserts
         _CrossDeviceCopy nodes for this: graph_executor.cc:1349-1353, nnvm place_device.cc)."""
         vals = {}
         topo = self._topo()
-        deferred, tails = self._fusion_plan(topo) if (not group2ctx and getenv("MXB200_GRAPH_FUSION", True)) else ({}, {})
+        # ``monitor(name, array, when)``: called with every operator output (``<node>_output``) right after it is computed
+        # and, during backward, with the gradient arriving at every operator input (``<node>_backward_<input>``): the
+        # executor's monitor callback of the reference (graph_executor.cc:ExecuteMonCallback).  Fusion is off while monitoring
+        # so that every node of the graph shows up.
+        deferred, tails = self._fusion_plan(topo) if (not group2ctx and monitor is None and getenv("MXB200_GRAPH_FUSION", True)) \
+            else ({}, {})
+
+        def input_names(node):
+            names = ["data"] + [x for x, _ in _param_args(node.op, node.attrs)]
+            if node.op in _LABEL_OPS:
+                names.append(_LABEL_OPS[node.op])
+            if len(node.inputs) == 2 and len(names) == 1:
+                names = ["lhs", "rhs"]
+            kw = node.attrs.get("__kwarg_inputs__")
+            if kw:
+                names = list(kw)
+            return [names[i] if i < len(names) else "arg%d" % i for i in range(len(node.inputs))]
 
         def run(node):
             ins = [vals[(id(inp), idx)] for inp, idx in node.inputs]
@@ -590,8 +606,14 @@ class Symbol(object):
                 tgt = group2ctx.get(node.var_attrs.get("__ctx_group__"))
                 if tgt is not None:
                     ins = [x.as_in_context(tgt) if hasattr(x, "as_in_context") and x.context != tgt else x for x in ins]
-            for i, o in enumerate(_run_node(node, ins, meta=False)):
+            outs = _run_node(node, ins, meta=False)
+            for i, o in enumerate(outs):
                 vals[(id(node), i)] = o
+            if monitor is not None:
+                for i, o in enumerate(outs):
+                    monitor(node.name + ("_output" if len(outs) == 1 else "_output%d" % i), o, "forward")
+                for x, aname in zip(ins, input_names(node)):
+                    monitor("%s_backward_%s" % (node.name, aname), x, "register")
         for node in topo:
             if node.op is None:
                 if node.name not in feed:
