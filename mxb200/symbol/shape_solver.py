@@ -101,11 +101,7 @@ def _apply(node, s):
     elif op == "_identity_with_attr_like_rhs":
         s.unify(ins + [out0], where)
     elif op in _SHAPE_PRESERVING:
-        s.unify([ins[0], out0], where)
-        if op in ("SoftmaxOutput", "Softmax", "LinearRegressionOutput", "LogisticRegressionOutput", "MAERegressionOutput") and len(ins) > 1:
-            d = s.get(ins[0])
-            if d is not None and op not in ("SoftmaxOutput", "Softmax"):
-                s.put(ins[1], d, where)
+        s.unify([ins[0], out0], where)      # (labels are left to the forward rules: a (N,) label is legal for (N, 1) data)
     elif op == "FullyConnected":
         nh = int(a["num_hidden"])
         flat = _truthy(a.get("flatten", True))
