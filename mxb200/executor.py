@@ -44,26 +44,43 @@ class Executor(object):
             self._grad_req = {n: grad_req.get(n, "null") for n in arg_names}
         if args_grad is None:
             args_grad = {}
-        if not isinstance(args_grad, dict):
-            args_grad = dict(zip(arg_names, args_grad))
+        # several DISTINCT variables may carry the same name (positional binding keeps them apart in the reference): such
+        # graphs are fed by node identity, and the by-name dictionaries show the last array of each name
+        self._by_node = None
+        dup = len(set(arg_names)) != len(arg_names) and not isinstance(args, dict)
+        if dup:
+            var_nodes = [nd_ for nd_ in symbol._topo() if nd_.op is None and not nd_.is_aux]
+            self._by_node = {id(nd_): a for nd_, a in zip(var_nodes, args)}
+        pos_args = list(args) if dup else [self.arg_dict[n] for n in arg_names]
+        if isinstance(args_grad, dict):
+            pos_grads = [args_grad.get(n) for n in arg_names]
+        else:
+            pos_grads = list(args_grad) + [None] * (len(arg_names) - len(args_grad))
+        pos_req = list(grad_req) if (dup and isinstance(grad_req, (list, tuple))) else [self._grad_req.get(n, "null") for n in arg_names]
         self.grad_dict = {}
-        for n in arg_names:
-            req = self._grad_req.get(n, "null")
-            if req == "null" or (args_grad.get(n) is None and n not in args_grad and False):
+        self._grad_cast = {}
+        self._grad_pairs = []               # (argument array, bound gradient array, request) per position
+        self.grad_arrays = []
+        for n, a, g, req in zip(arg_names, pos_args, pos_grads, pos_req):
+            if req == "null":
+                self.grad_arrays.append(None)
                 continue
-            a = self.arg_dict[n]
             if not a._t.is_floating_point():
                 self._grad_req[n] = "null"
+                self.grad_arrays.append(None)
                 continue
             a.attach_grad(req)
-            g = args_grad.get(n)
-            if g is not None:
+            if g is not None and (g._t.dtype != a._t.dtype or g._t.device != a._t.device):
+                # a gradient array of another dtype: autograd accumulates in the argument's dtype, backward() casts into it
+                self._grad_cast[id(a)] = g
+            elif g is not None:
                 a._t.grad = g._t
-                self.grad_dict[n] = g
             else:
-                self.grad_dict[n] = NDArray(a._t.grad, a.context)
-        self.arg_arrays = [self.arg_dict[n] for n in arg_names]
-        self.grad_arrays = [self.grad_dict.get(n) for n in arg_names]
+                g = NDArray(a._t.grad, a.context)
+            self.grad_dict[n] = g
+            self.grad_arrays.append(g)
+            self._grad_pairs.append((a, g, req))
+        self.arg_arrays = pos_args
         self.aux_arrays = [self.aux_dict[n] for n in aux_names]
         self._outputs = []
         self._output_names = symbol.list_outputs()
@@ -95,7 +112,8 @@ class Executor(object):
 
     @staticmethod
     def simple_bind(symbol, ctx, grad_req="write", type_dict=None, group2ctx=None, shapes=None):
-        shapes = shapes or {}
+        known = set(symbol.list_inputs())
+        shapes = {k: v for k, v in (shapes or {}).items() if k in known}      # stray keyword arguments are ignored
         type_dict = type_dict or {}
         vshape, _out, vdtype, _ = symbol._infer(shapes, type_dict)
         args, aux = {}, {}
@@ -133,6 +151,8 @@ class Executor(object):
                     name, str(self.arg_dict[name].shape), str(array.shape)))
         feed = dict(self.arg_dict)
         feed.update(self.aux_dict)
+        if self._by_node is not None:
+            feed["__by_node__"] = self._by_node
         mon = self._make_monitor() if self._monitor_callback is not None else None
         if is_train or self.grad_dict:
             # an executor bound with gradient arrays can always run backward(), also after forward(is_train=False): the
@@ -182,17 +202,26 @@ class Executor(object):
                 continue
             heads.append(o)
             hgrads.append(out_grads[i] if i < len(out_grads) else None)
+        epoch = autograd._bw_epoch[0]
         if heads:
             autograd.backward(heads, hgrads)
+        # 'write' means every bound gradient array is written by every backward(): arguments no gradient reached (inputs of
+        # integer-valued operators, disconnected branches) read zero, not the previous contents
+        for a, g, req in self._grad_pairs:
+            if req == "write" and (not heads or a._bw_epoch <= epoch) and a._t.grad is not None:
+                a._t.grad.zero_()
+            live = a._t.grad
+            if live is None:
+                continue
+            if id(a) in self._grad_cast:
+                with torch.no_grad():
+                    g._t.copy_(live)
+            elif live is not g._t:
+                g._t = live                       # keep the handles pointing at the live tensors
         if self._monitor_callback is not None:
             for name, arr in getattr(self, "_mon_nograd", []):
                 self._monitor_callback(name, nd.zeros(arr.shape, ctx=arr.context, dtype=arr.dtype))
             self._mon_nograd = []
-        # keep grad handles pointing at the live tensors
-        for n, g in self.grad_dict.items():
-            live = self.arg_dict[n]._t.grad
-            if live is not None and live is not g._t:
-                g._t = live
 
     def set_monitor_callback(self, callback):
         self._monitor_callback = callback

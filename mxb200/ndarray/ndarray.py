@@ -323,8 +323,13 @@ class NDArray(object):
     def tile(self, reps):
         return _op(lambda t: t.repeat(*reps), self)
 
-    def slice_axis(self, axis, begin, end):
-        return _op(lambda t: t.narrow(axis, begin, (end if end is not None else t.shape[axis]) - begin), self)
+    def slice_axis(self, axis, begin, end=None):
+        def f(t):
+            n = t.shape[axis]
+            b = begin + n if begin < 0 else begin
+            e = n if end is None else (end + n if end < 0 else end)
+            return t.narrow(axis, b, e - b)
+        return _op(f, self)
 
     def split(self, num_outputs, axis=1, squeeze_axis=False):
         from . import op
@@ -560,18 +565,9 @@ def _mx_reshape(src, shape, reverse=False):
     """MXNet reshape special codes: 0 copy dim, -1 infer, -2 copy rest, -3 merge two, -4 split.  ``reverse``: the codes
     are matched against the source dimensions from the right (matrix_op-inl.h ReshapeParam.reverse)."""
     if reverse:
-        shape = list(shape)
-        # -4 takes its two arguments to the right: keep the triple together while reversing
-        groups, j = [], 0
-        while j < len(shape):
-            if shape[j] == -4:
-                groups.append([shape[j], shape[j + 2], shape[j + 1]])
-                j += 3
-            else:
-                groups.append([shape[j]])
-                j += 1
-        rshape = [v for g in reversed(groups) for v in g]
-        out = _mx_reshape(tuple(reversed(src)), rshape, reverse=False)
+        # the reference reverses the source dimensions AND the whole code vector, infers, and reverses the result: in this
+        # mode a -4 is therefore written AFTER its two arguments ((16, -1, -4) splits the last dimension)
+        out = _mx_reshape(tuple(reversed(src)), tuple(reversed(list(shape))), reverse=False)
         return tuple(reversed(out))
     if all(isinstance(s, (int, np.integer)) and s > 0 or s == -1 for s in shape):
         return tuple(int(s) for s in shape)

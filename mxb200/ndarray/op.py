@@ -117,7 +117,19 @@ add = _binary("add", torch.add)
 subtract = _binary("subtract", torch.sub)
 multiply = _binary("multiply", torch.mul)
 divide = _binary("divide", torch.div)
-modulo = _binary("modulo", torch.remainder)
+def _mx_mod(a, b):
+    """mshadow_op::mod: python-style remainder, and x mod 0 = 0 (also for integers, where torch raises)."""
+    ta = a if isinstance(a, torch.Tensor) else b
+    if not ta.is_floating_point():
+        bt = b if isinstance(b, torch.Tensor) else torch.as_tensor(b, device=ta.device)
+        zero = bt == 0
+        r = torch.remainder(a, torch.where(zero, torch.ones_like(bt), bt))
+        return torch.where(zero, torch.zeros_like(r), r)
+    r = torch.remainder(a, b)
+    return torch.where(torch.as_tensor(b, device=r.device) == 0, torch.zeros_like(r), r) if isinstance(b, torch.Tensor) else (r if b != 0 else torch.zeros_like(r))
+
+
+modulo = _binary("modulo", _mx_mod)
 power = _binary("power", torch.pow)
 maximum = _binary("maximum", lambda a, b: torch.maximum(a, b) if isinstance(b, torch.Tensor) and isinstance(a, torch.Tensor)
                   else torch.clamp(a if isinstance(a, torch.Tensor) else b, min=b if isinstance(a, torch.Tensor) else a))
@@ -213,8 +225,9 @@ def _reduce(name, fn):
                 r = t
                 for a in sorted((a % t.dim() for a in ax), reverse=True):
                     r = fn(r, dim=a, keepdim=bool(keepdims))
-                return r
-            return fn(t, dim=ax, keepdim=bool(keepdims))
+                return r.reshape(1) if r.dim() == 0 else r
+            r = fn(t, dim=ax, keepdim=bool(keepdims))
+            return r.reshape(1) if r.dim() == 0 else r           # a full reduction has shape (1,) in MXNet 1.x
         return _out(_op(g, data), out)
     f.__name__ = name
     _REG[name] = f
@@ -234,7 +247,7 @@ sum_axis = sum
 @register
 def norm(data, ord=2, axis=None, keepdims=False, out=None):
     def g(t):
-        r = torch.linalg.vector_norm(t.float(), ord=ord, dim=_axes(axis), keepdim=keepdims).to(t.dtype)
+        r = torch.linalg.vector_norm(t.float(), ord=ord, dim=_axes(axis), keepdim=bool(keepdims)).to(t.dtype)
         return r.reshape(1) if r.dim() == 0 else r
     return _out(_op(g, data), out)
 
@@ -256,6 +269,9 @@ def argmax_channel(data, out=None):
 
 @register
 def topk(data, axis=-1, k=1, ret_typ="indices", is_ascend=False, dtype="float32", out=None):
+    if axis == "None":
+        axis = None
+
     def g(t):
         if axis is None:
             t = t.reshape(-1)
@@ -292,7 +308,13 @@ def argsort(data, axis=-1, is_ascend=True, dtype="float32", out=None):
 # ---------------------------------------------------------------------------
 
 @register
-def reshape(data, shape, reverse=False, out=None):
+def reshape(data, shape=None, reverse=False, target_shape=None, keep_highest=False, out=None):
+    if shape is None or len(shape) == 0:
+        # legacy arguments (matrix_op-inl.h ReshapeParam.target_shape / keep_highest): a 0 is the one inferred dimension
+        tgt = [int(v) for v in target_shape]
+        if keep_highest:
+            tgt[0] = data.shape[0]
+        shape = tuple(-1 if v == 0 else v for v in tgt)
     if reverse in (True, 1, "1", "True", "true"):
         from .ndarray import _mx_reshape
         tgt = _mx_reshape(data.shape, tuple(shape), reverse=True)
@@ -405,7 +427,7 @@ _REG["crop"] = slice
 
 
 @register
-def slice_axis(data, axis, begin, end, out=None):
+def slice_axis(data, axis, begin, end=None, out=None):
     return _out(data.slice_axis(axis, begin, end), out)
 
 
@@ -421,6 +443,9 @@ def slice_like(data, shape_like, axes=None):
 
 @register
 def tile(data, reps, out=None):
+    reps = (reps,) if isinstance(reps, (int, np.integer)) else tuple(reps)
+    if any(int(r) <= 0 for r in reps):
+        raise MXNetError("tile: invalid reps value %s, every element must be positive" % (reps,))
     return _out(_op(lambda t: t.repeat(*reps) if len(reps) >= t.dim() else t.repeat(*([1] * (t.dim() - len(reps)) + list(reps))), data), out)
 
 
@@ -520,9 +545,10 @@ def size_array(data):
 def take(a, indices, axis=0, mode="clip", out=None):
     def g(t, i):
         i = i.long()
-        n = t.shape[axis]
+        ax = axis % t.dim()
+        n = t.shape[ax]
         i = i.clamp(0, n - 1) if mode == "clip" else i % n
-        return torch.index_select(t, axis, i.reshape(-1)).reshape(t.shape[:axis] + tuple(i.shape) + t.shape[axis + 1:])
+        return torch.index_select(t, ax, i.reshape(-1)).reshape(t.shape[:ax] + tuple(i.shape) + t.shape[ax + 1:])
     return _out(_op(g, a, indices), out)
 
 
@@ -727,7 +753,13 @@ def LeakyReLU(data, gamma=None, act_type="leaky", slope=0.25, lower_bound=0.125,
             from ..ops.layernorm import bias_act
             return bias_act(t, None, act_type, slope)
         if act_type == "prelu":
-            return F.prelu(t, gm.reshape(-1))
+            # leaky_relu-inl.h: a 1-D gamma is per channel (axis 1) or a single shared slope; a gamma with more
+            # dimensions lines up with the LEADING dimensions of the data and broadcasts over the rest
+            if gm.dim() <= 1:
+                gb = gm.reshape([1, -1] + [1] * (t.dim() - 2)) if gm.numel() > 1 and t.dim() > 1 else gm.reshape([1] * t.dim() if gm.numel() == 1 else [-1])
+            else:
+                gb = gm.reshape(list(gm.shape) + [1] * (t.dim() - gm.dim()))
+            return torch.where(t > 0, t, t * gb.to(t.dtype))
         if act_type == "rrelu":
             return F.rrelu(t, lower_bound, upper_bound, training=_ag.is_training())
         raise MXNetError("unknown act_type " + act_type)
@@ -828,6 +860,15 @@ def BatchNorm(data, gamma, beta, moving_mean, moving_var, eps=1e-3, momentum=0.9
             if y is not None:
                 return y
         gm_ = torch.ones_like(gm) if fix_gamma else gm
+        if mm.dtype != x.dtype or gm_.dtype != x.dtype:
+            # mixed dtypes (fp32 statistics under fp64 / fp16 data): compute in the data's dtype, write the statistics back
+            mm_c, mv_c = mm.to(x.dtype), mv.to(x.dtype)
+            r = F.batch_norm(x.movedim(axis, 1), mm_c, mv_c, gm_.to(x.dtype), bt.to(x.dtype), training, 1.0 - momentum, eps).movedim(1, axis)
+            if training:
+                with torch.no_grad():
+                    mm.copy_(mm_c)
+                    mv.copy_(mv_c)
+            return r
         if axis != 1 and axis % x.dim() != 1:
             xt = x.movedim(axis, 1)
             r = F.batch_norm(xt, mm, mv, gm_, bt, training, 1.0 - momentum, eps)
@@ -1055,8 +1096,29 @@ def SVMOutput(data, label, margin=1.0, regularization_coefficient=1.0, use_linea
 
 
 @register
-def UpSampling(*data, scale=2, sample_type="nearest", num_args=1, out=None, **kw):
-    return _out(_op(lambda x, *r: F.interpolate(x, scale_factor=scale, mode="nearest" if sample_type == "nearest" else "bilinear"), *data), out)
+def UpSampling(*data, scale=2, sample_type="nearest", num_args=1, num_filter=0, multi_input_mode="concat", workspace=512, out=None, **kw):
+    """nn/upsampling-inl.h: 'nearest' brings every input to scale x the FIRST input's size (input k by its own integer
+    factor) and concatenates them on the channel axis (or sums them, ``multi_input_mode='sum'``); 'bilinear' is a grouped
+    transposed convolution of ``data`` with the ``weight`` input (kernel 2*scale - scale%2, stride scale, pad
+    ceil((scale-1)/2), one group per channel)."""
+    scale = int(scale)
+    if sample_type == "nearest":
+        def g(x, *rest):
+            oh = x.shape[2] * scale
+            ups = [F.interpolate(t, scale_factor=oh // t.shape[2], mode="nearest") if oh != t.shape[2] else t for t in (x,) + rest]
+            if len(ups) == 1:
+                return ups[0]
+            if multi_input_mode == "sum":
+                r = ups[0]
+                for u in ups[1:]:
+                    r = r + u
+                return r
+            return torch.cat(ups, 1)
+        return _out(_op(g, *data), out)
+    if len(data) < 2:
+        return _out(_op(lambda x: F.interpolate(x, scale_factor=scale, mode="bilinear"), data[0]), out)
+    k, pd = 2 * scale - scale % 2, int(math.ceil((scale - 1) / 2.0))
+    return _out(_op(lambda x, w: F.conv_transpose2d(x, w.to(x.dtype), None, stride=scale, padding=pd, groups=x.shape[1]), data[0], data[1]), out)
 
 
 @register(name="_contrib_BilinearResize2D")
@@ -1121,28 +1183,47 @@ def ROIAlign(data, rois, pooled_size, spatial_scale, sample_ratio=-1, out=None):
 @register
 def CTCLoss(data, label, data_lengths=None, label_lengths=None, use_data_lengths=False, use_label_lengths=False,
             blank_label="first", out=None):
-    def g(x, l, dl=None, ll=None):
+    use_dl = bool(use_data_lengths) and data_lengths is not None
+    use_ll = bool(use_label_lengths) and label_lengths is not None
+
+    def g(x, l, *lens):
         T, N, C = x.shape
-        lp = torch.log_softmax(x, dim=2)
+        if x.device.type == "meta":                      # shape inference
+            return x.new_empty((N,))
+        lens = list(lens)
+        dl = lens.pop(0) if use_dl else None
+        ll = lens.pop(0) if use_ll else None
+        if dl is not None:
+            # frames past a sequence's length take no part (they may hold anything, NaN included): zero value, zero gradient
+            live = (torch.arange(T, device=x.device)[:, None] < dl.long()[None, :])[:, :, None]
+            x = torch.where(live, x, torch.zeros_like(x))
+        lp = torch.log_softmax(x.float(), dim=2)
         blank = 0 if blank_label == "first" else C - 1
         li = l.long()
         if ll is None:
-            pad = 0 if blank_label == "last" else -1
-            ll_ = (li != pad).sum(1) if blank_label == "last" else ((li > 0) | (li == li)).sum(1)
-            if blank_label == "first":
-                ll_ = (li != 0).sum(1)
+            # ctc_loss-inl.h LabelTensorToPackedVector: a label sequence ends at the FIRST padding value (0 when the blank
+            # is the first class, -1 when it is the last)
+            pad = 0 if blank_label == "first" else -1
+            is_pad = (li == pad)
+            first = torch.where(is_pad.any(1), is_pad.float().argmax(1), torch.full((N,), li.shape[1], device=li.device))
+            ll_ = first.long()
         else:
             ll_ = ll.long()
-        dl_ = dl.long() if dl is not None else torch.full((N,), T, dtype=torch.long)
-        return F.ctc_loss(lp, li, dl_, ll_, blank=blank, reduction="none", zero_infinity=True)
+        dl_ = dl.long() if dl is not None else torch.full((N,), T, dtype=torch.long, device=x.device)
+        li = li.clamp_min(0)
+        return F.ctc_loss(lp, li, dl_, ll_, blank=blank, reduction="none", zero_infinity=True).to(x.dtype)
     args = [data, label]
-    if use_data_lengths and data_lengths is not None:
+    if use_dl:
         args.append(data_lengths)
+    if use_ll:
+        args.append(label_lengths)
     return _out(_op(lambda *a: g(*a), *args), out)
 
 
 ctc_loss = CTCLoss
 _REG["ctc_loss"] = CTCLoss
+_REG["_contrib_ctc_loss"] = CTCLoss
+_REG["_contrib_CTCLoss"] = CTCLoss
 
 
 @register

@@ -54,8 +54,8 @@ def nanprod(data, axis=None, keepdims=False, exclude=False, out=None):
         if exclude:
             axes = tuple(i for i in range(t.dim()) if i not in [a % t.dim() for a in axes])
         for a in sorted([a % t.dim() for a in axes], reverse=True):
-            t = t.prod(dim=a, keepdim=keepdims)
-        return t
+            t = t.prod(dim=a, keepdim=bool(keepdims))
+        return t.reshape(1) if t.dim() == 0 else t
     return _out(_op(g, data), out)
 
 
@@ -79,7 +79,7 @@ _scalar("_rminus_scalar", lambda t, s: s - t)
 _scalar("_mul_scalar", lambda t, s: t * s)
 _scalar("_div_scalar", lambda t, s: t / s)
 _scalar("_rdiv_scalar", lambda t, s: s / t)
-_scalar("_mod_scalar", lambda t, s: torch.remainder(t, s))
+_scalar("_mod_scalar", lambda t, s: _o._mx_mod(t, s))
 _scalar("_rmod_scalar", lambda t, s: torch.remainder(torch.full_like(t, s), t))
 _scalar("_power_scalar", lambda t, s: torch.pow(t, s))
 _scalar("_rpower_scalar", lambda t, s: torch.pow(torch.full_like(t, s), t))
@@ -106,7 +106,7 @@ _binary("_lesser", _cmpf(torch.lt))
 _binary("_lesser_equal", _cmpf(torch.le))
 _binary("_maximum", torch.maximum)
 _binary("_minimum", torch.minimum)
-_binary("_mod", torch.remainder)
+_binary("_mod", _o._mx_mod)
 _binary("_power", torch.pow)
 _binary("_hypot", torch.hypot)
 _binary("_logical_and", lambda a, b: ((a != 0) & (b != 0)).to(a.dtype))
@@ -599,7 +599,11 @@ def Correlation(data1, data2, kernel_size=1, max_displacement=1, stride1=1, stri
                     for kx in range(-(k // 2), k // 2 + 1):
                         pa = a[:, :, (ys + ky)][:, :, :, (xs + kx)]
                         pb = b[:, :, (ys + ky + dy * stride2)][:, :, :, (xs + kx + dx * stride2)]
-                        acc = acc + ((pa * pb) if is_multiply else (pa - pb).abs()).sum(1)
+                        if is_multiply:
+                            acc = acc + (pa * pb).sum(1)
+                        else:
+                            df = pa - pb                       # |a - b| with the reference's tie rule: d/da = +1 at a == b
+                            acc = acc + torch.where(df >= 0, df, -df).sum(1)
                 outs.append(acc / (k * k * c))
         return torch.stack(outs, 1)
     return _out(_op(g, data1, data2), out)
@@ -828,6 +832,8 @@ def PSROIPooling(data, rois, spatial_scale, output_dim, pooled_size, group_size=
 
     def g(x, r):
         n_roi = r.shape[0]
+        if x.device.type == "meta":                     # shape inference
+            return torch.empty(n_roi, int(output_dim), ps, ps, dtype=x.dtype, device="meta")
         res = torch.zeros(n_roi, int(output_dim), ps, ps, dtype=torch.float32, device=x.device)
         H, W = x.shape[2], x.shape[3]
         for i in range(n_roi):

@@ -201,6 +201,18 @@ def _apply(node, s):
         o = s.get(out0)
         if o is not None and d is not None:
             s.put(ins[0], [o[0]] + [0] * (len(d) - 1), where)
+    elif op in ("_ones", "_zeros", "_full", "ones", "zeros", "full") and not ins:
+        shp = _tuple(a.get("shape"), 1)
+        if shp is not None and all(x > 0 for x in shp):
+            s.put(out0, list(shp), where)
+    elif op in ("Reshape", "reshape"):
+        # backward only: a fully known output fixes the one missing input dimension (element count is preserved)
+        d, o = s.get(ins[0]), s.get(out0)
+        if d is not None and o is not None and all(x != 0 for x in o) and sum(1 for x in d if x == 0) == 1:
+            rest = int(np.prod([x for x in d if x != 0])) if len(d) > 1 else 1
+            tot = int(np.prod(o))
+            if rest > 0 and tot % rest == 0:
+                s.put(ins[0], [x if x != 0 else tot // rest for x in d], where)
     elif op == "Embedding":
         d = s.get(ins[0])
         if d is not None:

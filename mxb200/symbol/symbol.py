@@ -443,7 +443,10 @@ class Symbol(object):
             shape = tuple(shape[0])
         if not shape:
             shape = tuple(kwargs["shape"])
-        return _make_op("reshape", [self], {"shape": tuple(shape)})
+        attrs = {"shape": tuple(shape)}
+        if kwargs.get("reverse", False):
+            attrs["reverse"] = True
+        return _make_op("reshape", [self], attrs)
 
     # ---- inference -------------------------------------------------------------------------------
     def _infer(self, shapes, dtypes=None, partial=False):
@@ -614,8 +617,12 @@ class Symbol(object):
                     monitor(node.name + ("_output" if len(outs) == 1 else "_output%d" % i), o, "forward")
                 for x, aname in zip(ins, input_names(node)):
                     monitor("%s_backward_%s" % (node.name, aname), x, "register")
+        by_node = feed.get("__by_node__") or {}
         for node in topo:
             if node.op is None:
+                if id(node) in by_node:
+                    vals[(id(node), 0)] = by_node[id(node)]
+                    continue
                 if node.name not in feed:
                     raise MXNetError("eval: missing input %s" % node.name)
                 vals[(id(node), 0)] = feed[node.name]
@@ -952,6 +959,8 @@ def _create(op, args, kwargs):
     inherit = {k: v for k, v in node_attrs.items() if k.startswith("__") and k.endswith("__")}   # reach the auto-created variables
     sym_kwargs = {k: v for k, v in kwargs.items() if isinstance(v, Symbol)}
     attrs = {k: v for k, v in kwargs.items() if not isinstance(v, Symbol) and v is not None}
+    if op in ("topk", "sort", "argsort") and "axis" in kwargs and kwargs["axis"] is None:
+        attrs["axis"] = "None"               # an explicit None (= flatten) differs from these operators' default axis -1
     hint = op.lower().lstrip("_")
     node_name = _NameManager.resolve(name, hint)
     inputs = [a for a in args if isinstance(a, Symbol)]
@@ -1202,7 +1211,7 @@ def _infer_param_shapes(node, vals, vshape, vdtype):
             # a shape given by the caller must agree with what the operator implies (InferShape consistency check)
             want = rule(aname)
             have = tuple(vals[(id(inp), idx)].shape)
-            if want is not None and tuple(want) != have:
+            if want is not None and tuple(want) != have and op != "LeakyReLU":     # (prelu's gamma may be any broadcastable shape)
                 raise MXNetError("infer_shape: shape inconsistent for %s of node %s: provided %s, inferred %s"
                                  % (inp.name, node.name, str(have), str(tuple(want))))
         if inp.op is None and (id(inp), idx) not in vals and aname != "data":

@@ -216,7 +216,7 @@ def assert_almost_equal(a, b, rtol=None, atol=None, names=("a", "b"), equal_nan=
 
 
 def almost_equal_ignore_nan(a, b, rtol=None, atol=None):
-    a, b = np.copy(_np(a)), np.copy(_np(b))
+    a, b = np.atleast_1d(np.copy(_np(a))), np.atleast_1d(np.copy(_np(b)))
     nan = np.logical_or(np.isnan(a), np.isnan(b))
     a[nan] = 0
     b[nan] = 0
@@ -309,7 +309,9 @@ def simple_forward(sym, ctx=None, is_train=False, **inputs):
 
 
 def numeric_grad(executor, location, aux_states=None, eps=1e-4, use_forward_train=True, dtype=np.float32):
-    """Central finite differences of sum(outputs[0]) w.r.t. every array in ``location`` (dict name -> numpy)."""
+    """Central finite differences of sum(outputs[0]) w.r.t. every array in ``location`` (dict name -> numpy).  The
+    difference is taken element-wise on the output BEFORE the sum (test_utils.py:numeric_grad of the reference): only the
+    elements that depend on the perturbed input contribute, so a float32 executor is not drowned in cancellation noise."""
     for k, v in location.items():
         executor.arg_dict[k][:] = v
     grads = {k: np.zeros(v.shape, dtype=np.float64) for k, v in location.items()}
@@ -319,7 +321,7 @@ def numeric_grad(executor, location, aux_states=None, eps=1e-4, use_forward_trai
             for k, v in aux_states.items():
                 executor.aux_dict[k][:] = v
         executor.forward(is_train=use_forward_train)
-        return float(executor.outputs[0].asnumpy().astype(np.float64).sum())
+        return executor.outputs[0].asnumpy().astype(np.float64)
     for k, v in location.items():
         if not np.issubdtype(np.asarray(v).dtype, np.floating):
             continue
@@ -335,7 +337,7 @@ def numeric_grad(executor, location, aux_states=None, eps=1e-4, use_forward_trai
             executor.arg_dict[k][:] = base.reshape(v.shape)
             fm = f()
             flat[i] = old
-            g[i] = (fp - fm) / eps
+            g[i] = float((fp - fm).sum()) / eps
         executor.arg_dict[k][:] = base.reshape(v.shape)
     return grads
 
@@ -382,7 +384,7 @@ def check_numeric_gradient(sym, location, aux_states=None, numeric_eps=1e-3, rto
         grad_nodes = {k: "write" for k in grad_nodes}
     out_shape = sym.infer_shape(**{k: v.shape for k, v in loc.items()})[1][0]
     proj = S.var("__random_proj")
-    loss = S.make_loss(S.sum(sym[0] * proj) if len(sym.list_outputs()) > 1 else S.sum(sym * proj))
+    loss = S.make_loss(sym[0] * proj if len(sym.list_outputs()) > 1 else sym * proj)
     args = dict(loc)
     args["__random_proj"] = nd.array(_RNG.uniform(0.5, 1.5, out_shape), ctx=ctx, dtype=dtype)
     req = {k: grad_nodes.get(k, "null") for k in sym.list_arguments()}
