@@ -208,7 +208,9 @@ class Executor(object):
         # 'write' means every bound gradient array is written by every backward(): arguments no gradient reached (inputs of
         # integer-valued operators, disconnected branches) read zero, not the previous contents
         for a, g, req in self._grad_pairs:
-            if req == "write" and (not heads or a._bw_epoch <= epoch) and a._t.grad is not None:
+            leaf = getattr(a, "_dense_leaf", None)                # sparse arguments accumulate in their dense leaf
+            leaf = a if leaf is None else leaf
+            if req == "write" and (not heads or getattr(leaf, "_bw_epoch", -1) <= epoch) and a._t.grad is not None:
                 a._t.grad.zero_()
             live = a._t.grad
             if live is None:

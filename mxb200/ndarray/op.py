@@ -518,8 +518,11 @@ _REG["Pad"] = pad
 
 
 @register
-def diag(data, k=0, out=None):
-    """k-th diagonal of a matrix, or the matrix with a vector on its k-th diagonal (tensor/diag_op-inl.h)."""
+def diag(data, k=0, axis1=0, axis2=1, out=None):
+    """k-th diagonal of a matrix, or the matrix with a vector on its k-th diagonal (tensor/diag_op-inl.h); for more than
+    two dimensions the diagonal of the (axis1, axis2) planes is appended as the last axis."""
+    if data.ndim > 2 or (data.ndim == 2 and (axis1 % 2, axis2 % 2) == (1, 0)):
+        return _out(_op(lambda t: torch.diagonal(t, k, axis1, axis2), data), out)
     if data.ndim == 2 and not (-data.shape[0] < k < data.shape[1]):
         raise MXNetError("diag: k=%d is outside of the %s matrix" % (k, str(data.shape)))
     if data.ndim == 0:
@@ -674,15 +677,30 @@ def batch_dot(lhs, rhs, transpose_a=False, transpose_b=False, out=None):
 
 
 @register
-def linalg_gemm2(A, B, transpose_a=False, transpose_b=False, alpha=1.0, out=None):
-    return _out(_op(lambda a, b: alpha * torch.matmul(a.transpose(-1, -2) if transpose_a else a,
-                                                      b.transpose(-1, -2) if transpose_b else b), A, B), out)
+def linalg_gemm2(A, B, transpose_a=False, transpose_b=False, alpha=1.0, axis=-2, out=None):
+    """``axis``: which axis holds the matrix rows (la_op.cc: default -2; the columns are always the last axis)."""
+    def g(a, b):
+        a, b = _la_rows(a, axis), _la_rows(b, axis)
+        r = alpha * torch.matmul(a.transpose(-1, -2) if transpose_a else a, b.transpose(-1, -2) if transpose_b else b)
+        return _la_rows_back(r, axis)
+    return _out(_op(g, A, B), out)
+
+
+def _la_rows(t, axis):
+    return t if axis in (-2, t.dim() - 2) else t.movedim(axis, -2)
+
+
+def _la_rows_back(t, axis):
+    return t if axis in (-2, t.dim() - 2) else t.movedim(-2, axis)
 
 
 @register
-def linalg_gemm(A, B, C, transpose_a=False, transpose_b=False, alpha=1.0, beta=1.0, out=None):
-    return _out(_op(lambda a, b, c: alpha * torch.matmul(a.transpose(-1, -2) if transpose_a else a,
-                                                         b.transpose(-1, -2) if transpose_b else b) + beta * c, A, B, C), out)
+def linalg_gemm(A, B, C, transpose_a=False, transpose_b=False, alpha=1.0, beta=1.0, axis=-2, out=None):
+    def g(a, b, c):
+        a, b, c = _la_rows(a, axis), _la_rows(b, axis), _la_rows(c, axis)
+        r = alpha * torch.matmul(a.transpose(-1, -2) if transpose_a else a, b.transpose(-1, -2) if transpose_b else b) + beta * c
+        return _la_rows_back(r, axis)
+    return _out(_op(g, A, B, C), out)
 
 
 @register
@@ -826,8 +844,16 @@ def Pooling(data, kernel=None, pool_type="max", global_pool=False, stride=None, 
             return x.mean(dim=ax, keepdim=True)
         k = _tup(kernel, nd_)
         s = _tup(stride, nd_) or (1,) * nd_
-        p = _tup(pad, nd_) or (0,) * nd_
+        p = (_tup(pad, nd_) or (0,) * nd_)[:nd_]
         ceil_mode = pooling_convention == "full"
+        if pooling_convention == "same":
+            # output = ceil(input / stride), padding implied on the right (pooling-inl.h: 1-D max pooling only, pad must be 0)
+            if any(p) or pool_type != "max" or nd_ != 1:
+                raise MXNetError("Pooling: the 'same' convention is for 1-D max pooling with zero pad")
+            need = (-(-x.shape[2] // s[0]) - 1) * s[0] + k[0] - x.shape[2]
+            if need > 0:
+                x = F.pad(x, (0, need), value=float("-inf"))
+            return F.max_pool1d(x, k, s, 0)
         if (pool_type == "max" and nd_ == 2 and x.is_cuda and not ceil_mode and k[0] == k[1] and k[0] in (2, 3)
                 and s[0] == s[1] and p[0] == p[1] and p[0] < k[0] and x.dim() == 4 and not x.is_contiguous()
                 and x.is_contiguous(memory_format=torch.channels_last)):
@@ -930,6 +956,8 @@ def Dropout(data, p=0.5, mode="training", axes=(), out=None, **kw):
     def g(x):
         if not train or p == 0:
             return x
+        if p >= 1:
+            return x * float("nan")          # keep-probability 0: the reference's mask is 0 * (1/0) = NaN
         if not axes_:
             return F.dropout(x, p, training=True)
         shp = [1 if (i in axes_ or i - x.dim() in axes_) else s for i, s in enumerate(x.shape)]
@@ -998,6 +1026,13 @@ def SoftmaxOutput(data, label=None, grad_scale=1.0, ignore_label=-1.0, multi_out
                   preserve_shape=False, normalization="null", out_grad=False, smooth_alpha=0.0, out=None, **kw):
     if label is None:
         return softmax(data, axis=1 if multi_output or not preserve_shape else -1, out=out)
+    if preserve_shape and not multi_output:
+        # softmax over the LAST axis, every leading position is its own row (softmax_output-inl.h preserve_shape)
+        def gp(x, l):
+            x2 = x.reshape(-1, x.shape[-1])
+            l2 = l.reshape(x2.shape) if l.shape == x.shape else l.reshape(-1)
+            return _SoftmaxOutputFn.apply(x2, l2, grad_scale, ignore_label, use_ignore, normalization, smooth_alpha, False).reshape(x.shape)
+        return _out(_op(gp, data, label), out)
     return _out(_op(lambda x, l: _SoftmaxOutputFn.apply(x, l, grad_scale, ignore_label, use_ignore, normalization,
                                                         smooth_alpha, multi_output), data, label), out)
 
@@ -1154,29 +1189,94 @@ def SpatialTransformer(data, loc, target_shape=None, transform_type="affine", sa
     return BilinearSampler(data, g, out=out)
 
 
+def _clip(v, lo, hi):
+    return lo if v < lo else (hi if v > hi else v)        # (the module-level min / max are the reduction operators)
+
+
 @register
 def ROIPooling(data, rois, pooled_size, spatial_scale, out=None):
-    import torchvision.ops as tvo  # noqa: F401  (optional)
-    raise MXNetError("ROIPooling requires torchvision; use contrib.ROIAlign")
+    """Max pooling of every ROI to a fixed (ph, pw) grid (src/operator/roi_pooling.cc): ROI corners are rounded to the
+    feature map, a ROI spans end - start + 1 cells (at least 1), bin (i, j) covers [floor(i*bh), ceil((i+1)*bh)) clipped to
+    the map; an empty bin yields 0."""
+    ph, pw = (int(pooled_size),) * 2 if isinstance(pooled_size, (int, np.integer)) else (int(pooled_size[0]), int(pooled_size[1]))
+
+    def g(x, r):
+        R, (C, H, W) = r.shape[0], x.shape[1:]
+        if x.device.type == "meta":
+            return x.new_empty((R, C, ph, pw))
+        rr = r.detach().double().cpu()
+        outs = []
+        for k in range(R):
+            b = int(rr[k, 0])
+            x1, y1, x2, y2 = [int(math.floor(float(v) * float(spatial_scale) + 0.5)) for v in rr[k, 1:5]]
+            rh, rw = (y2 - y1 + 1 if y2 - y1 + 1 > 1 else 1), (x2 - x1 + 1 if x2 - x1 + 1 > 1 else 1)
+            bh, bw = rh / float(ph), rw / float(pw)
+            rows = []
+            for i in range(ph):
+                hs, he = int(math.floor(i * bh)) + y1, int(math.ceil((i + 1) * bh)) + y1
+                hs, he = _clip(hs, 0, H), _clip(he, 0, H)
+                cols = []
+                for j in range(pw):
+                    ws, we = int(math.floor(j * bw)) + x1, int(math.ceil((j + 1) * bw)) + x1
+                    ws, we = _clip(ws, 0, W), _clip(we, 0, W)
+                    if he <= hs or we <= ws:
+                        cols.append(x.new_zeros((C,)))
+                    else:
+                        cols.append(x[b, :, hs:he, ws:we].amax(dim=(1, 2)))
+                rows.append(torch.stack(cols, -1))
+            outs.append(torch.stack(rows, -2))
+        return torch.stack(outs, 0) if outs else x.new_zeros((0, C, ph, pw))
+    return _out(_op(g, data, rois), out)
 
 
 @register(name="_contrib_ROIAlign")
-def ROIAlign(data, rois, pooled_size, spatial_scale, sample_ratio=-1, out=None):
-    """Bilinear ROI align (src/operator/contrib/roi_align.cu) written with grid_sample."""
+def ROIAlign(data, rois, pooled_size, spatial_scale=1.0, sample_ratio=0, out=None, **kw):
+    """ROI align (src/operator/contrib/roi_align.cc): every output bin averages a grid of bilinear samples
+    (``sample_ratio`` per side, or ceil(roi extent / pooled extent) when <= 0); samples further than one pixel outside the
+    map contribute 0, coordinates are clamped at the border.  No gradient reaches ``rois``.  One gather per corner over the
+    whole sample grid of a ROI -- autograd turns it into the scatter-add of the backward pass."""
+    ph, pw = (int(pooled_size),) * 2 if isinstance(pooled_size, (int, np.integer)) else (int(pooled_size[0]), int(pooled_size[1]))
+
     def g(x, r):
-        ph, pw = pooled_size
+        R, (C, H, W) = r.shape[0], x.shape[1:]
+        if x.device.type == "meta":
+            return x.new_empty((R, C, ph, pw))
+        rr = r.detach().double().cpu()
         outs = []
-        for k in range(r.shape[0]):
-            b = int(r[k, 0].item())
-            x1, y1, x2, y2 = [r[k, i] * spatial_scale for i in range(1, 5)]
-            H, W = x.shape[2], x.shape[3]
-            ys = y1 + (torch.arange(ph, device=x.device) + 0.5) * (torch.clamp(y2 - y1, min=1.0) / ph)
-            xs = x1 + (torch.arange(pw, device=x.device) + 0.5) * (torch.clamp(x2 - x1, min=1.0) / pw)
-            gy = (ys / max(H - 1, 1)) * 2 - 1
-            gx = (xs / max(W - 1, 1)) * 2 - 1
-            grid = torch.stack(torch.meshgrid(gy, gx, indexing="ij")[::-1], -1)[None]
-            outs.append(F.grid_sample(x[b:b + 1], grid.to(x.dtype), align_corners=True))
-        return torch.cat(outs, 0)
+        for k in range(R):
+            b = int(rr[k, 0])
+            sw, sh, ew, eh = [float(v) * float(spatial_scale) for v in rr[k, 1:5]]
+            roi_w, roi_h = ew - sw if ew - sw > 1.0 else 1.0, eh - sh if eh - sh > 1.0 else 1.0
+            bin_h, bin_w = roi_h / ph, roi_w / pw
+            gh = int(sample_ratio) if int(sample_ratio) > 0 else int(math.ceil(roi_h / ph))
+            gw = int(sample_ratio) if int(sample_ratio) > 0 else int(math.ceil(roi_w / pw))
+            ys = sh + (torch.arange(ph, dtype=torch.float64)[:, None] * bin_h + (torch.arange(gh, dtype=torch.float64)[None, :] + 0.5) * bin_h / gh).reshape(-1)
+            xs = sw + (torch.arange(pw, dtype=torch.float64)[:, None] * bin_w + (torch.arange(gw, dtype=torch.float64)[None, :] + 0.5) * bin_w / gw).reshape(-1)
+
+            def corners(c, n):
+                dead = (c < -1.0) | (c > n)
+                c = c.clamp_min(0.0)
+                lo = c.floor().long()
+                top = lo >= n - 1
+                lo = torch.where(top, torch.full_like(lo, n - 1), lo)
+                hi = torch.where(top, lo, lo + 1)
+                frac = torch.where(top, torch.zeros_like(c), c - lo.to(c.dtype))
+                return lo, hi, frac, dead
+            yl, yh, ly, ydead = corners(ys, H)
+            xl, xh, lx, xdead = corners(xs, W)
+            dev = x.device
+            wy = torch.stack([1.0 - ly, ly]).to(dev, x.dtype)                    # (2, ph*gh)
+            wx = torch.stack([1.0 - lx, lx]).to(dev, x.dtype)
+            live = ((~ydead)[:, None] & (~xdead)[None, :]).to(dev, x.dtype)      # (ph*gh, pw*gw)
+            img = x[b]
+            acc = 0
+            for iy, yy in enumerate((yl, yh)):
+                rows = img.index_select(1, yy.to(dev))
+                for ix, xx in enumerate((xl, xh)):
+                    acc = acc + rows.index_select(2, xx.to(dev)) * (wy[iy][:, None] * wx[ix][None, :])
+            acc = acc * live
+            outs.append(acc.reshape(C, ph, gh, pw, gw).mean(dim=(2, 4)))
+        return torch.stack(outs, 0) if outs else x.new_zeros((0, C, ph, pw))
     return _out(_op(g, data, rois), out)
 
 

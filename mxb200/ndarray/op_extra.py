@@ -172,6 +172,9 @@ def _arange(start=0.0, stop=None, step=1.0, repeat=1, infer_range=False, ctx=Non
 @register
 def depth_to_space(data, block_size, out=None):
     b = int(block_size)
+    if b <= 0 or data.ndim != 4 or data.shape[1] % (b * b) != 0 or 0 in data.shape or data.shape[1] == 0:
+        raise MXNetError("depth_to_space: block_size %d does not fit the %s input (depth must be a positive multiple of "
+                         "block_size^2, no empty dimension)" % (b, str(data.shape)))
 
     def g(t):
         n, c, h, w = t.shape
@@ -182,6 +185,9 @@ def depth_to_space(data, block_size, out=None):
 @register
 def space_to_depth(data, block_size, out=None):
     b = int(block_size)
+    if b <= 0 or data.ndim != 4 or 0 in data.shape or data.shape[2] % b != 0 or data.shape[3] % b != 0:
+        raise MXNetError("space_to_depth: block_size %d does not fit the %s input (height and width must be positive "
+                         "multiples of block_size)" % (b, str(data.shape)))
 
     def g(t):
         n, c, h, w = t.shape
@@ -251,10 +257,14 @@ def Crop(*data, **kw):
 
 
 # ----------------------------------------------------------------------------- linalg (tensor/la_op.cc)
+def _la_float(a):
+    return a if a.dtype in (torch.float32, torch.float64) else a.float()
+
+
 @register
 def linalg_potri(A, out=None):
     """inverse from the Cholesky factor: (L L^T)^-1."""
-    return _out(_op(lambda L: torch.cholesky_inverse(L.float()).to(L.dtype), A), out)
+    return _out(_op(lambda L: torch.cholesky_inverse(_la_float(L)).to(L.dtype), A), out)
 
 
 @register
@@ -270,7 +280,7 @@ def linalg_trmm(A, B, transpose=False, rightside=False, alpha=1.0, out=None):
 def linalg_gelqf(A, out=None):
     """A = L Q with Q orthonormal rows (LQ factorisation)."""
     def g(a):
-        q, r = torch.linalg.qr(a.float().transpose(-1, -2))
+        q, r = torch.linalg.qr(_la_float(a).transpose(-1, -2))
         sgn = torch.sign(torch.diagonal(r, dim1=-2, dim2=-1))
         sgn = torch.where(sgn == 0, torch.ones_like(sgn), sgn)
         q, r = q * sgn.unsqueeze(-2), r * sgn.unsqueeze(-1)
@@ -281,8 +291,14 @@ def linalg_gelqf(A, out=None):
 @register
 def linalg_syevd(A, out=None):
     def g(a):
-        w, v = torch.linalg.eigh(a.float())
-        return v.transpose(-1, -2).to(a.dtype), w.to(a.dtype)
+        w, v = torch.linalg.eigh(_la_float(a))
+        # eigenvectors are rows of U; sign convention of the reference (la_op-inl.h syevd: LAPACK output as is) is not
+        # unique -- normalise every row so that its largest-magnitude entry is positive
+        u = v.transpose(-1, -2)
+        idx = u.abs().argmax(-1, keepdim=True)
+        sgn = torch.sign(torch.gather(u, -1, idx))
+        u = u * torch.where(sgn == 0, torch.ones_like(sgn), sgn)
+        return u.to(a.dtype), w.to(a.dtype)
     return _out(_op(g, A), out)
 
 
@@ -665,17 +681,18 @@ def histogram(data=None, bins=10, range=None, out=None, a=None, **kw):
     data = a if data is None else data           # numpy-style keyword of the python front end: histogram(a=..., bins=...)
     """tensor/histogram.cc: returns (counts, bin_edges); ``bins`` is a count (with ``range``) or an edge array."""
     def g(t, *edges):
-        x = t.float().reshape(-1)
+        x = _la_float(t).reshape(-1)
         if edges:
-            e = edges[0].float()
+            e = edges[0].to(x.dtype)
             idx = torch.bucketize(x, e, right=True) - 1
             idx = torch.where(x == e[-1], torch.full_like(idx, e.numel() - 2), idx)
             ok = (idx >= 0) & (idx < e.numel() - 1)
-            cnt = torch.zeros(e.numel() - 1, device=t.device).index_add(0, idx[ok], torch.ones_like(x[ok]))
+            cnt = torch.zeros(e.numel() - 1, dtype=x.dtype, device=t.device).index_add(0, idx[ok], torch.ones_like(x[ok]))
             return cnt, e
         lo, hi = (float(range[0]), float(range[1])) if range is not None else (float(x.min()), float(x.max()))
         cnt = torch.histc(x, bins=int(bins), min=lo, max=hi)
-        return cnt, torch.linspace(lo, hi, int(bins) + 1, device=t.device)
+        edges_np = np.linspace(lo, hi, int(bins) + 1)          # float64 edges rounded once, like numpy.histogram
+        return cnt, torch.as_tensor(edges_np, dtype=x.dtype, device=t.device)
     if isinstance(bins, NDArray):
         return _out(_op(g, data, bins), out)
     return _out(_op(g, data), out)
@@ -891,6 +908,7 @@ def Proposal(cls_prob, bbox_pred, im_info, rpn_pre_nms_top_n=6000, rpn_post_nms_
              scales=(4, 8, 16, 32), ratios=(0.5, 1, 2), feature_stride=16, output_score=False, iou_loss=False, out=None):
     """RPN proposal layer (contrib/proposal.cc): anchors + deltas -> clip -> min-size filter -> top-N -> NMS -> pad."""
     def g(cp, bp, info):
+        cp, bp, info = cp.detach(), bp.detach(), info.detach()      # not differentiable: the reference's backward writes zeros
         res, res_s = [], []
         A = len(scales) * len(ratios)
         for b in range(cp.shape[0]):

@@ -213,6 +213,25 @@ def _apply(node, s):
             tot = int(np.prod(o))
             if rest > 0 and tot % rest == 0:
                 s.put(ins[0], [x if x != 0 else tot // rest for x in d], where)
+    elif op in ("slice", "crop", "slice_axis"):
+        d = s.get(ins[0])
+        if d is not None:
+            if op == "slice_axis":
+                ax = int(a["axis"]) % len(d)
+                begin = [None] * ax + [a.get("begin")]
+                end = [None] * ax + [a.get("end")]
+                step = []
+            else:
+                begin, end, step = list(a.get("begin", ())), list(a.get("end", ())), list(a.get("step", ()) or ())
+            od = []
+            for i, n in enumerate(d):
+                if n == 0 or i >= len(begin):
+                    od.append(n)
+                    continue
+                none = lambda v: None if v in (None, "None") else int(v)     # noqa: E731
+                st = none(step[i]) if i < len(step) else None
+                od.append(len(range(*slice(none(begin[i]), none(end[i]) if i < len(end) else None, st).indices(n))))
+            s.put(out0, od, where)
     elif op == "Embedding":
         d = s.get(ins[0])
         if d is not None:
@@ -221,10 +240,11 @@ def _apply(node, s):
             s.put(ins[1], [int(a["input_dim"]), int(a["output_dim"])], where)
 
 
-def solve(sym, shapes):
+def solve(sym, shapes, partial_heads=False):
     """``shapes``: {variable name: tuple with 0 for unknown dimensions}.  Returns {variable name: fully known shape} for
     every variable whose shape could be completed (including the ones that were complete already), and the list of the
-    symbol's output shapes (None where still unknown)."""
+    symbol's output shapes (None where still unknown; with ``partial_heads`` a partly known shape is returned with its
+    0 dimensions, as ``infer_shape_partial`` reports it)."""
     order = sym._topo()
     s = _Solver()
     for node in order:
@@ -253,5 +273,5 @@ def solve(sym, shapes):
     heads = []
     for n, i in sym._outputs:
         d = s.S.get((id(n), i))
-        heads.append(tuple(d) if d is not None and all(x != 0 for x in d) else None)
+        heads.append(tuple(d) if d is not None and (partial_heads or all(x != 0 for x in d)) else None)
     return out, heads

@@ -80,12 +80,20 @@ def _truthy(v):
     return v in (True, 1, "1", "True", "true")
 
 
+def _custom_prop(attrs):
+    """CustomOpProp of a Custom node (operator.py registry); its constructor takes the node's parameters as strings."""
+    from .. import operator as _custom
+    return _custom.get_prop(attrs.get("op_type"), {k: v for k, v in attrs.items() if k != "op_type" and not k.startswith("__")})
+
+
 def _num_outputs(op, attrs):
     """Number of outputs of an operator node (nnvm FNumOutputs of the reference registrations)."""
     if op in _MULTI_OUT:
         return int(attrs.get(_MULTI_OUT[op], 1))
     if op in _FIXED_MULTI_OUT:
         return _FIXED_MULTI_OUT[op]
+    if op == "Custom":
+        return len(_custom_prop(attrs).list_outputs())
     if op == "RNN":
         if not _truthy(attrs.get("state_outputs", False)):
             return 1
@@ -216,7 +224,7 @@ class Symbol(object):
             if n.op is None:
                 out.append(n.name)
             elif n.num_outputs > 1:
-                out.append("%s_output%d" % (n.name, i))
+                out.append("%s_%s" % (n.name, _custom_prop(n.attrs).list_outputs()[i]) if n.op == "Custom" else "%s_output%d" % (n.name, i))
             else:
                 out.append("%s_output" % n.name)
         return out
@@ -462,7 +470,7 @@ class Symbol(object):
             or any(any(d == 0 for d in v) for v in shapes.values())
         if need:
             from .shape_solver import solve
-            solved, solved_heads = solve(self, shapes)
+            solved, solved_heads = solve(self, shapes, partial_heads=partial)
             shapes = {k: v for k, v in shapes.items() if all(d > 0 for d in v)}
             for k, v in solved.items():
                 shapes.setdefault(k, v)
@@ -500,6 +508,8 @@ class Symbol(object):
                 raise MXNetError("infer_shape: cannot infer shape of inputs %s of node %s" % (unknown, node.name))
             outs = _run_node(node, ins, meta=True)
             for i, o in enumerate(outs):
+                if isinstance(o, torch.Tensor) and o.device.type != "meta":
+                    o = torch.empty(o.shape, dtype=o.dtype, device="meta")    # constants (zeros / eye / arange) carry no data here
                 vals[(id(node), i)] = o
         out_shapes, out_types = [], []
         for n, i in self._outputs:
@@ -533,8 +543,11 @@ class Symbol(object):
         if args:
             kwargs = dict(zip(self.list_arguments(), args))
         vshape, out_shapes, _, _ = self._infer(kwargs, partial=True)
-        arg_shapes = [vshape.get(n, ()) for n in self.list_arguments()]
-        aux_shapes = [vshape.get(n, ()) for n in self.list_auxiliary_states()]
+        declared = {n.name: tuple(n.var_attrs["__shape__"]) for n in self._topo() if n.op is None and "__shape__" in n.var_attrs}
+        given = {k: tuple(v) for k, v in kwargs.items() if v is not None}
+        part = lambda n: vshape.get(n, given.get(n, declared.get(n, ())))      # noqa: E731 -- partly known shapes keep their 0s
+        arg_shapes = [part(n) for n in self.list_arguments()]
+        aux_shapes = [part(n) for n in self.list_auxiliary_states()]
         return arg_shapes, [s if s is not None else () for s in out_shapes], aux_shapes
 
     def infer_type(self, *args, **kwargs):
@@ -1004,6 +1017,22 @@ def _create(op, args, kwargs):
             if is_aux:
                 s._outputs[0][0].is_aux = True
             order.append(s)
+    elif op == "Custom":
+        # inputs = the prop's arguments followed by its auxiliary states (custom.cc ListArguments); whatever is not given
+        # becomes a free variable "<node>_<name>", auxiliary ones flagged as such
+        prop = _custom_prop(attrs)
+        provided = list(inputs)
+        for aname in list(prop.list_arguments()) + list(prop.list_auxiliary_states()):
+            is_aux = aname in prop.list_auxiliary_states()
+            if aname in sym_kwargs:
+                s_ = sym_kwargs[aname]
+            elif provided:
+                s_ = provided.pop(0)
+            else:
+                s_ = var("%s_%s" % (node_name, aname))
+            if is_aux and s_._outputs[0][0].op is None:
+                s_._outputs[0][0].is_aux = True
+            order.append(s_)
     else:
         order = inputs + [sym_kwargs[k] for k in sym_kwargs]
         if sym_kwargs:
@@ -1128,6 +1157,19 @@ def _run_node(node, ins, meta):
 def _infer_param_shapes(node, vals, vshape, vdtype):
     """Fill shapes of parameter/label variables feeding ``node`` from its data input (infer_shape rules)."""
     op = node.op
+    if op == "Custom":
+        prop = _custom_prop(node.attrs)
+        nargs = len(prop.list_arguments())
+        known = [vals.get((id(n), i)) for n, i in node.inputs]
+        if any(k is None for k in known) and all(k is not None for k in known[:nargs]) and nargs:
+            ishapes, _o, aux_shapes = prop.infer_shape([list(k.shape) for k in known[:nargs]])
+            full = list(ishapes) + list(aux_shapes)
+            for (n, i), k, shp in zip(node.inputs, known, full):
+                if k is None and n.op is None:
+                    vals[(id(n), i)] = torch.empty(tuple(shp), dtype=known[0].dtype, device="meta")
+                    vshape[n.name] = tuple(shp)
+                    vdtype[n.name] = dtype_name(known[0].dtype)
+        return
     if op == "RNN":
         # flat cuDNN-layout parameter vector of the fused RNN op: size from (input size, state size, layers, directions, mode)
         a = node.attrs
@@ -1148,6 +1190,18 @@ def _infer_param_shapes(node, vals, vshape, vdtype):
                 vals[(id(pn), pidx)] = torch.empty((size,), dtype=d.dtype, device="meta")
                 vshape[pn.name] = (size,)
                 vdtype[pn.name] = dt
+        if "data" in byname:
+            d = vals.get((id(byname["data"][0]), byname["data"][1]))
+            if d is not None:
+                nd_ = 2 if _truthy(a.get("bidirectional", False)) else 1
+                sshape = (int(a.get("num_layers", 1)) * nd_, int(d.shape[1]), int(a["state_size"]))
+                for sname in ("state", "state_cell"):          # initial states: (layers * directions, batch, state size)
+                    if sname in byname:
+                        sn, sidx = byname[sname]
+                        if sn.op is None and (id(sn), sidx) not in vals:
+                            vals[(id(sn), sidx)] = torch.empty(sshape, dtype=d.dtype, device="meta")
+                            vshape[sn.name] = sshape
+                            vdtype[sn.name] = dtype_name(d.dtype)
         return
     if not _has_param_args(op) and op not in _LABEL_OPS:
         return
