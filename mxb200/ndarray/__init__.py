@@ -17,19 +17,25 @@ from .op import CachedOp  # noqa: F401
 import functools as _functools
 
 
-def _strip_sym_kwargs(f):
-    """Ops accept (and ignore) the symbolic-only ``name=`` / ``attr=`` kwargs so HybridBlocks can pass them."""
+def _strip_sym_kwargs(f, opname=None):
+    """Ops accept (and ignore) the symbolic-only ``name=`` / ``attr=`` kwargs so HybridBlocks can pass them.  Operators run
+    on the dense view of sparse inputs (storage fallback); ``sparse.storage_rule`` then gives the result the storage type
+    the reference's FInferStorageType would have picked (relu(row_sparse) stays row_sparse ...)."""
     @_functools.wraps(f)
     def g(*a, **k):
         k.pop("name", None)
         k.pop("attr", None)
-        return f(*a, **k)
+        r = f(*a, **k)
+        for x in a:
+            if isinstance(x, BaseSparseNDArray):
+                return sparse.storage_rule(opname, a, k, r)
+        return r
     return g
 
 
 _this = _sys.modules[__name__]
 for _k in list(_OPS.keys()):
-    _OPS[_k] = _strip_sym_kwargs(_OPS[_k])
+    _OPS[_k] = _strip_sym_kwargs(_OPS[_k], _k)
     setattr(_this, _k, _OPS[_k])
 # creation functions win over same-named elementwise ops
 zeros_like = ndarray.zeros_like

@@ -181,6 +181,9 @@ class NDArray(object):
         if isinstance(other, NDArray):
             if other is self:
                 return other
+            if getattr(other, "stype", "default") != "default":
+                other[:] = self                     # dense -> sparse destination: storage conversion (cast_storage)
+                return other
             with torch.no_grad():
                 other._t.copy_(self._t, non_blocking=True)
             if getattr(self._t, "_mx_exc", None) is not None:
@@ -671,6 +674,10 @@ def from_torch(t, ctx=None):
 
 
 def array(source, ctx=None, dtype=None):
+    # sparse sources keep their storage type (ndarray/utils.py:array dispatches scipy.sparse / sparse NDArrays to sparse.array)
+    if getattr(source, "stype", "default") != "default" or type(source).__module__.startswith("scipy.sparse"):
+        from . import sparse as _sp
+        return _sp.array(source, ctx=ctx, dtype=dtype)
     ctx = _ctx_of(ctx)
     if isinstance(source, NDArray):
         t = source._t.detach()

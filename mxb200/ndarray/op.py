@@ -327,6 +327,44 @@ _REG["Reshape"] = reshape
 
 
 @register
+def cast_storage(data, stype="default", out=None):
+    """Storage-type conversion (tensor/cast_storage.cc); the gradient passes through unchanged (dense-backed)."""
+    from . import sparse as _sp
+    if data._t.device.type == "meta":
+        return data                                        # shape inference: storage does not change the shape
+    leaf = getattr(data, "_dense_leaf", None)
+    if _ag.is_recording() and (leaf is not None or (getattr(data, "stype", "default") == "default" and data._t.requires_grad)):
+        dense = _op(lambda t: t * 1, data)                 # taped identity on the dense view
+        if stype == "default":
+            return _out(dense, out)
+        res = _sp.cast_storage(NDArray(dense._t.detach(), data.context), stype)
+        res._dense_leaf = dense                            # operators downstream read the taped dense tensor
+        return _out(res, out)
+    return _out(_sp.cast_storage(data, stype), out)
+
+
+@register(name="_sparse_retain")
+def sparse_retain(data, indices, out=None):
+    from . import sparse as _sp
+    if data._t.device.type == "meta":
+        return data
+    leaf = getattr(data, "_dense_leaf", None)
+    if _ag.is_recording() and leaf is not None:
+        # taped form: rows that are not retained are multiplied by 0, the gradient reaches the retained rows only
+        def g(t, i):
+            keep = torch.zeros(t.shape[0], dtype=t.dtype, device=t.device)
+            keep[i.long()] = 1
+            return t * keep.reshape([-1] + [1] * (t.dim() - 1))
+        dense = _op(g, data, indices)
+        res = _sp.cast_storage(NDArray(dense._t.detach(), data.context), "row_sparse")
+        res._dense_leaf = dense
+        return _out(res, out)
+    if not isinstance(data, _sp.RowSparseNDArray):
+        data = _sp.cast_storage(data, "row_sparse")
+    return _out(_sp.retain(data, indices), out)
+
+
+@register
 def reshape_like(lhs, rhs, lhs_begin=None, lhs_end=None, rhs_begin=None, rhs_end=None, out=None):
     """Reshape lhs like rhs; with the begin/end arguments only lhs.shape[lhs_begin:lhs_end] is replaced by
     rhs.shape[rhs_begin:rhs_end] (matrix_op.cc ReshapeLikeParam)."""
@@ -404,6 +442,20 @@ _REG["SliceChannel"] = split
 
 @register
 def slice(data, begin, end, step=None, out=None):
+    if isinstance(begin, (int, np.integer)) or begin is None:
+        begin, end = (begin,), (end,)
+    if isinstance(step, (int, np.integer)):
+        step = (step,)
+    if getattr(data, "stype", "default") == "csr" and (step is None or all(s in (None, 1) for s in step)):
+        # row range of a csr matrix keeps the csr storage (matrix_op.cc SliceEx); column ranges go through the dense view
+        from . import sparse as _sp
+        b0, e0, _ = np.s_[begin[0]:end[0]].indices(data.shape[0])
+        r = data[b0:e0]
+        if len(begin) > 1 and (begin[1] not in (None, 0) or end[1] not in (None, data.shape[1])):
+            b1, e1, _ = np.s_[begin[1]:end[1]].indices(data.shape[1])
+            r = _sp.cast_storage(NDArray(r.todense()._t[:, b1:e1], data.context), "csr")
+        return _out(r, out)
+
     def g(t):
         # numpy slice semantics incl. negative steps (matrix_op-inl.h SliceParam); torch cannot index with a negative
         # step, so those axes are gathered through an index vector
@@ -744,6 +796,8 @@ def FullyConnected(data, weight, bias=None, num_hidden=None, no_bias=False, flat
     def g(x, w, b=None):
         if flatten and x.dim() != 2:
             x = x.reshape(x.shape[0], -1)       # (N,) is N samples of one feature, (N, a, b) of a*b features
+        if b is not None and b.dim() != 1:
+            b = b.reshape(-1)                   # a (num_hidden, 1) bias is accepted like the reference's shape check does
         return K.linear(x, w, b)
     if bias is None or no_bias:
         return _out(_op(g, data, weight), out)

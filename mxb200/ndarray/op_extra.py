@@ -17,7 +17,22 @@ from .op import _REG, _out, register, _unary, _binary, _cmpf
 _unary("arcsinh", torch.asinh)
 _unary("arccosh", torch.acosh)
 _unary("arctanh", torch.atanh)
-_unary("cbrt", lambda t: torch.sign(t) * torch.abs(t).pow(1.0 / 3.0))
+class _Cbrt(torch.autograd.Function):
+    """cube root with the analytic gradient 1 / (3 y^2) (inf at 0, like mshadow_op::cube_root_grad)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        y = torch.sign(t) * torch.abs(t).pow(1.0 / 3.0)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        return g / (3.0 * y * y)
+
+
+_unary("cbrt", _Cbrt.apply)
 _unary("rcbrt", lambda t: torch.sign(t) * torch.abs(t).pow(-1.0 / 3.0))
 _unary("degrees", torch.rad2deg)
 _unary("radians", torch.deg2rad)

@@ -140,12 +140,51 @@ class BaseSparseNDArray(NDArray):
     def square(self):
         return self * self
 
+    def _sync_leaf(self):
+        """After a write into a sparse array that carries a gradient: refresh the dense leaf operators read."""
+        leaf = self.__dict__.get("_dense_leaf")
+        if leaf is not None:
+            with torch.no_grad():
+                leaf._t.copy_(self.todense()._t)
+
     def check_format(self, full_check=True):
-        """Raise if the index arrays are malformed (ndarray/sparse.py check_format of the reference)."""
+        """Raise MXNetError if the index arrays are malformed (ndarray/sparse.py check_format -> common/utils.h
+        CheckFormatWrapper): csr -- indptr starts at 0, is non-decreasing, ends at nnz, column ids within [0, cols) and
+        ascending inside a row; row_sparse -- row ids within [0, rows) and strictly ascending."""
         from ..base import MXNetError
         idx = self._indices
-        if idx.numel() and (bool((idx < 0).any()) or bool((idx[1:] < idx[:-1]).any()) and self.stype == "row_sparse"):
-            raise MXNetError("indices must be non-negative and sorted")
+        if self.stype == "row_sparse":
+            if idx.numel() and (bool((idx < 0).any()) or bool((idx >= self._shape[0]).any()) or bool((idx[1:] <= idx[:-1]).any())):
+                raise MXNetError("row_sparse indices must be within [0, %d) and strictly ascending" % self._shape[0])
+            return
+        ptr = self._indptr
+        if ptr.numel() != self._shape[0] + 1 or int(ptr[0]) != 0 or int(ptr[-1]) != idx.numel() or bool((ptr[1:] < ptr[:-1]).any()):
+            raise MXNetError("csr indptr must start at 0, be non-decreasing and end at the number of stored values")
+        if idx.numel() and (bool((idx < 0).any()) or bool((idx >= self._shape[1]).any())):
+            raise MXNetError("csr indices must be within [0, %d)" % self._shape[1])
+        if full_check and idx.numel() > 1:
+            rows = torch.repeat_interleave(torch.arange(self._shape[0], device=ptr.device), ptr[1:] - ptr[:-1])
+            same_row = rows[1:] == rows[:-1]
+            if bool(((idx[1:] <= idx[:-1]) & same_row).any()):
+                raise MXNetError("csr indices must be ascending inside every row")
+
+    @property
+    def _num_aux(self):
+        return 1 if self.stype == "row_sparse" else 2
+
+    def __getstate__(self):
+        st = {"stype": self.stype, "shape": self._shape, "data": self._data.cpu().numpy(), "indices": self._indices.cpu().numpy()}
+        if self.stype == "csr":
+            st["indptr"] = self._indptr.cpu().numpy()
+        return st
+
+    def __setstate__(self, st):
+        self._ctx = current_context()
+        self._shape = tuple(st["shape"])
+        self._data = torch.from_numpy(st["data"])
+        self._indices = torch.from_numpy(st["indices"]).to(torch.int64)
+        if st["stype"] == "csr":
+            self._indptr = torch.from_numpy(st["indptr"]).to(torch.int64)
 
     def wait_to_read(self):
         if self._data.is_cuda:
@@ -207,6 +246,7 @@ class RowSparseNDArray(BaseSparseNDArray):
             other._data = self._data.to(other._data.device, copy=True)
             other._indices = self._indices.to(other._data.device, copy=True)
             other._shape = self._shape
+            other._sync_leaf()
             return other
         if isinstance(other, NDArray):
             other[:] = self.todense()
@@ -291,6 +331,10 @@ class CSRNDArray(BaseSparseNDArray):
     def copyto(self, other):
         if isinstance(other, CSRNDArray):
             other._data, other._indices, other._indptr, other._shape = self._data.clone(), self._indices.clone(), self._indptr.clone(), self._shape
+            other._sync_leaf()
+            return other
+        if isinstance(other, NDArray):
+            other[:] = self.todense()
             return other
         ctx = _ctx_of(other)
         d = ctx.torch_device
@@ -370,48 +414,68 @@ def array(source_array, ctx=None, dtype=None):
     raise ValueError("Unexpected source_array type: %s" % type(source_array))
 
 
+def _is_shape(v):
+    return isinstance(v, tuple) and len(v) > 0 and all(isinstance(x, (int, np.integer)) for x in v)
+
+
 def row_sparse_array(arg1, shape=None, ctx=None, dtype=None):
     ctx = _ctx_of(ctx)
+    if _is_shape(arg1):                               # row_sparse_array((D0, D1, ..)): an empty array of that shape
+        if shape is not None and tuple(int(x) for x in shape) != tuple(int(x) for x in arg1):
+            raise ValueError("shape %s does not match the shape given as first argument %s" % (tuple(shape), arg1))
+        return zeros("row_sparse", tuple(int(x) for x in arg1), ctx=ctx, dtype=dtype or np.float32)
     dtype = _src_dtype(arg1, dtype)
     if isinstance(arg1, tuple) and len(arg1) == 2:
         data, idx = arg1
         data = _dense_array(data, ctx=ctx, dtype=dtype)._t
         idx = _dense_array(idx, ctx=ctx, dtype="int64")._t
         if shape is None:
-            shape = (int(idx.max()) + 1 if idx.numel() else 0,) + tuple(data.shape[1:])
+            if idx.numel() == 0:
+                raise ValueError("invalid shape: it cannot be inferred from empty indices")
+            shape = (int(idx.max()) + 1,) + tuple(data.shape[1:])
         return RowSparseNDArray(data, idx, shape, ctx)
     if isinstance(arg1, RowSparseNDArray):
-        return arg1.copyto(ctx)
-    return cast_storage(_dense_array(arg1, ctx=ctx, dtype=dtype), "row_sparse")
+        return arg1.copyto(ctx).astype(dtype, copy=False)
+    dense = _dense_array(arg1, ctx=ctx, dtype=dtype)
+    if shape is not None and tuple(shape) != dense.shape:
+        raise ValueError("shape %s does not match the source array's %s" % (tuple(shape), dense.shape))
+    return cast_storage(dense, "row_sparse")
 
 
 def csr_matrix(arg1, shape=None, ctx=None, dtype=None):
     ctx = _ctx_of(ctx)
-    if not (isinstance(arg1, tuple) and len(arg1) == 2 and isinstance(arg1[0], int)):
-        dtype = _src_dtype(arg1, dtype)
+    if _is_shape(arg1) and len(arg1) == 2:            # csr_matrix((M, N)): empty matrix
+        if shape is not None and tuple(int(x) for x in shape) != tuple(int(x) for x in arg1):
+            raise ValueError("shape %s does not match the shape given as first argument %s" % (tuple(shape), arg1))
+        return zeros("csr", tuple(int(x) for x in arg1), ctx=ctx, dtype=dtype or np.float32)
+    dtype = _src_dtype(arg1, dtype)
     if isinstance(arg1, tuple) and len(arg1) == 3:
         data, indices, indptr = arg1
         data = _dense_array(data, ctx=ctx, dtype=dtype)._t
         indices = _dense_array(indices, ctx=ctx, dtype="int64")._t
         indptr = _dense_array(indptr, ctx=ctx, dtype="int64")._t
         if shape is None:
-            shape = (indptr.numel() - 1, int(indices.max()) + 1 if indices.numel() else 0)
+            if indices.numel() == 0:
+                raise ValueError("invalid shape: it cannot be inferred from empty indices")
+            shape = (indptr.numel() - 1, int(indices.max()) + 1)
         return CSRNDArray(data, indices, indptr, shape, ctx)
     if type(arg1).__module__.startswith("scipy.sparse"):
-        m = arg1.tocsr()
+        m = arg1.tocsr().copy()
+        m.sum_duplicates()                           # canonical form: no duplicate entries, sorted column ids
         m.sort_indices()
         return csr_matrix((m.data, m.indices, m.indptr), shape=shape or m.shape, ctx=ctx, dtype=dtype or m.dtype)
     if isinstance(arg1, CSRNDArray):
         return arg1.copyto(ctx) if dtype is None else arg1.copyto(ctx).astype(dtype)
-    if isinstance(arg1, tuple) and len(arg1) == 2 and isinstance(arg1[0], int):
-        return zeros("csr", arg1, ctx=ctx, dtype=dtype)       # csr_matrix((M, N)): empty matrix
     if isinstance(arg1, tuple) and len(arg1) == 2:
         # (data, (row, col)) coordinate form
         import scipy.sparse as spsp
         data, (row, col) = arg1
         as_np = lambda v: v.asnumpy() if hasattr(v, "asnumpy") else np.asarray(v)   # noqa: E731
         return csr_matrix(spsp.coo_matrix((as_np(data), (as_np(row), as_np(col))), shape=shape), ctx=ctx, dtype=dtype)
-    return cast_storage(_dense_array(arg1, ctx=ctx, dtype=dtype), "csr")
+    dense = _dense_array(arg1, ctx=ctx, dtype=dtype)
+    if shape is not None and tuple(shape) != dense.shape:
+        raise ValueError("shape %s does not match the source array's %s" % (tuple(shape), dense.shape))
+    return cast_storage(dense, "csr")
 
 
 def zeros(stype, shape, ctx=None, dtype=None):
@@ -424,6 +488,8 @@ def zeros(stype, shape, ctx=None, dtype=None):
     if stype == "csr":
         return CSRNDArray(torch.zeros(0, dtype=td, device=d), torch.zeros(0, dtype=torch.int64, device=d),
                           torch.zeros(shape[0] + 1, dtype=torch.int64, device=d), shape, ctx)
+    if stype != "default":
+        raise ValueError("unknown storage type " + str(stype))
     from .ndarray import zeros as dz
     return dz(shape, ctx, dtype)
 
@@ -449,7 +515,7 @@ def retain(data=None, indices=None, out=None, **kwargs):
     """sparse_retain: keep only the requested rows (src/operator/tensor/sparse_retain.cu).  ``retain(rsp, row_ids)`` or the
     operator's keyword form ``retain(data=rsp, indices=row_ids)``."""
     if kwargs:
-        raise TypeError("retain() got unexpected keyword argument(s) %s" % sorted(kwargs))
+        raise MXNetError("sparse_retain: unknown argument(s) %s" % sorted(kwargs))
     rsp, row_ids = data, indices
     if not isinstance(rsp, RowSparseNDArray):
         raise MXNetError("sparse retain expects a row_sparse input, got %s" % type(rsp).__name__)
@@ -473,23 +539,84 @@ def add_n_rsp(arrs):
     return RowSparseNDArray(out, uniq, shape, ctx)
 
 
-def dot(lhs, rhs, transpose_a=False, transpose_b=False):
-    """Sparse dot: csr x dense, csr^T x dense -> dense (dot-inl.cuh)."""
-    if isinstance(lhs, CSRNDArray):
+def dot(lhs, rhs, transpose_a=False, transpose_b=False, forward_stype=None, out=None):
+    """Sparse dot: csr x dense, csr^T x dense -> dense (dot-inl.cuh); ``forward_stype`` asks for the result in that storage."""
+    r = _dot(lhs, rhs, transpose_a, transpose_b)
+    if forward_stype not in (None, "default"):
+        r = cast_storage(r, forward_stype)
+    if out is not None:
+        out[:] = r
+        return out
+    return r
+
+
+def _dot(lhs, rhs, transpose_a=False, transpose_b=False):
+    has_leaf = lambda v: isinstance(v, BaseSparseNDArray) and v.__dict__.get("_dense_leaf") is not None   # noqa: E731
+    if isinstance(lhs, CSRNDArray) and not has_leaf(lhs):
         a = lhs._torch_csr()
-        b = rhs._t if isinstance(rhs, NDArray) else rhs.todense()._t
+        b = rhs._t                      # (dense view / gradient leaf of a sparse right-hand side)
         if transpose_b:
             b = b.t()
         if transpose_a:
             return NDArray(torch.matmul(a.to_dense().t(), b), lhs._ctx)
         return NDArray(torch.matmul(a, b), lhs._ctx)
-    a = lhs._t if isinstance(lhs, NDArray) else lhs.todense()._t
-    b = rhs.todense()._t if isinstance(rhs, BaseSparseNDArray) else rhs._t
+    a, b = lhs._t, rhs._t
     if transpose_a:
         a = a.t()
     if transpose_b:
         b = b.t()
-    return NDArray(torch.matmul(a, b), lhs._ctx if isinstance(lhs, NDArray) else rhs._ctx)
+    return NDArray(torch.matmul(a, b), lhs._ctx)
+
+
+# ---- result storage types of operators that ran on the dense view (FInferStorageType of the reference registrations) ----
+_ZERO_PRESERVING = {"relu", "abs", "sign", "sqrt", "square", "sin", "tan", "arcsin", "arctan", "sinh", "tanh", "arcsinh", "arctanh",
+                    "floor", "ceil", "round", "rint", "fix", "trunc", "negative", "expm1", "log1p", "degrees", "radians", "cbrt",
+                    "_mul_scalar", "_div_scalar", "zeros_like", "identity", "_copy", "stop_gradient", "BlockGrad", "make_loss"}
+_SPARSE_ONLY_IF_ALL = {"elemwise_add", "elemwise_sub", "_plus", "_minus", "_grad_add", "add_n", "ElementWiseSum", "_add", "_sub",
+                       "_maximum", "_minimum", "maximum", "minimum", "_hypot", "hypot"}
+_SPARSE_IF_ANY = {"elemwise_mul", "_mul"}
+
+
+def storage_rule(op, args, kwargs, result):
+    """Storage type of ``result`` (computed densely) given the operator and its inputs; the value is unchanged.  Under
+    autograd the sparse result keeps the taped dense tensor as its ``_dense_leaf`` so that consumers stay connected."""
+    if isinstance(result, (list, tuple)) or isinstance(result, BaseSparseNDArray) or not isinstance(result, NDArray) or result.ndim < 1:
+        return result
+    arrs = [a for a in args if isinstance(a, NDArray)]
+    sp = [a for a in arrs if isinstance(a, BaseSparseNDArray)]
+    st = None
+    if op in _ZERO_PRESERVING:
+        st = sp[0].stype
+    elif op in _SPARSE_IF_ANY:
+        st = "row_sparse" if any(a.stype == "row_sparse" for a in sp) and not all(a.stype == "csr" for a in sp) else sp[0].stype
+        if len(sp) == 2 and sp[0].stype != sp[1].stype:
+            st = None
+    elif op in _SPARSE_ONLY_IF_ALL:
+        st = sp[0].stype if len(sp) == len(arrs) and all(a.stype == sp[0].stype for a in sp) else None
+    elif op and op.startswith("_scatter_"):
+        st = arrs[0].stype if isinstance(arrs[0], BaseSparseNDArray) else None
+    elif op in ("square_sum", "_square_sum"):
+        ax = kwargs.get("axis")
+        ax = ax[0] if isinstance(ax, (list, tuple)) and len(ax) == 1 else ax
+        st = "row_sparse" if sp[0].stype == "row_sparse" and ax in (1, -1) and kwargs.get("keepdims", False) else None
+    elif op == "_contrib_quadratic":
+        st = sp[0].stype if float(kwargs.get("c", 0.0)) == 0.0 and sp[0].stype == "csr" else None
+    if st in (None, "default") or result.shape != sp[0].shape and op not in ("square_sum", "_square_sum"):
+        return result
+    if op and op.startswith("_scatter_") and st == "row_sparse":
+        # scatter operators touch exactly the rows the left operand stores (elemwise_scatter_op.cc)
+        idx = arrs[0]._indices
+        return RowSparseNDArray(result._t.detach()[idx], idx.clone(), result.shape, result.context)
+    if op and op.startswith("_scatter_") and st == "csr":
+        src = arrs[0]                                  # ... and exactly the stored elements of a csr left operand
+        rows = torch.repeat_interleave(torch.arange(src._shape[0], device=src._indptr.device), src._indptr[1:] - src._indptr[:-1])
+        return CSRNDArray(result._t.detach()[rows, src._indices], src._indices.clone(), src._indptr.clone(), result.shape, result.context)
+    if result.ndim != 2 and st == "csr":
+        return result
+    out = cast_storage(NDArray(result._t.detach(), result.context), st)
+    if result._t.requires_grad:
+        out._dense_leaf = result
+    return out
 
 
 def __getattr__(name):

@@ -232,7 +232,7 @@ def _apply(node, s):
                 st = none(step[i]) if i < len(step) else None
                 od.append(len(range(*slice(none(begin[i]), none(end[i]) if i < len(end) else None, st).indices(n))))
             s.put(out0, od, where)
-    elif op == "Embedding":
+    elif op in ("Embedding", "_contrib_SparseEmbedding"):
         d = s.get(ins[0])
         if d is not None:
             s.put(out0, list(d) + [int(a["output_dim"])], where)

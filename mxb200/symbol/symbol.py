@@ -34,6 +34,7 @@ _PARAM_ARGS = {
     "LayerNorm": [("gamma", False), ("beta", False)],
     "InstanceNorm": [("gamma", False), ("beta", False)],
     "Embedding": [("weight", False)],
+    "_contrib_SparseEmbedding": [("weight", False)],
     "LeakyReLU": [("gamma", False)],
     "BatchNorm_v1": [("gamma", False), ("beta", False), ("moving_mean", True), ("moving_var", True)],
     "CuDNNBatchNorm": [("gamma", False), ("beta", False), ("moving_mean", True), ("moving_var", True)],
@@ -954,6 +955,7 @@ def _create(op, args, kwargs):
     """mx.sym.<op>(*args, **kwargs): Symbol inputs become graph edges, the rest become attributes; parameter
     variables (weight/bias/gamma/...) and label variables are auto-created with the reference naming."""
     name = kwargs.pop("name", None)
+    kwargs.pop("out", None)                     # generated symbol functions accept and ignore ``out`` (symbol/register.py)
     user_attr = dict(kwargs.pop("attr", None) or {})
     for v in user_attr.values():
         if not isinstance(v, str):
@@ -1249,7 +1251,7 @@ def _infer_param_shapes(node, vals, vshape, vdtype):
             return (ds[int(a.get("axis", 1))],)
         if op == "LayerNorm":
             return (ds[int(a.get("axis", -1))],)
-        if op == "Embedding":
+        if op in ("Embedding", "_contrib_SparseEmbedding"):
             return (int(a["input_dim"]), int(a["output_dim"]))
         if op == "LeakyReLU":
             return (ds[1],)

@@ -116,12 +116,15 @@ def rand_sparse_ndarray(shape, stype, density=None, dtype=None, distribution=Non
         assert len(shape) == 2
         dense = _RNG.rand(*shape).astype(dtype)
         if distribution == "powerlaw":
+            # row r holds 2^r leading non-zeros until the total budget density * size is used up (the last row takes the rest)
             keep = np.zeros(shape, bool)
-            n = 1
+            n, left = 1, int(density * shape[0] * shape[1])
             for r in range(shape[0]):
-                keep[r, :min(shape[1], n)] = True
-                n = min(shape[1], n * 2)
-                if keep.sum() >= density * shape[0] * shape[1]:
+                take = min(shape[1], n, left)
+                keep[r, :take] = True
+                left -= take
+                n *= 2
+                if left <= 0:
                     break
         else:
             keep = _RNG.rand(*shape) < density
@@ -444,7 +447,10 @@ def check_symbolic_backward(sym, location, out_grads, expected, rtol=1e-5, atol=
     if out_grads is not None:
         out_grads = [g if isinstance(g, NDArray) else nd.array(g, ctx=ctx, dtype=dtype) for g in out_grads]
     exe.backward(out_grads)
-    got = {k: (exe.grad_dict[k] if k in exe.grad_dict else args_grad[k]).asnumpy() for k in expected}
+    got_nd = {k: (exe.grad_dict[k] if k in exe.grad_dict else args_grad[k]) for k in expected}
+    if grad_stypes:
+        got_nd = {k: (v.tostype(grad_stypes[k]) if k in grad_stypes else v) for k, v in got_nd.items()}
+    got = {k: v.asnumpy() for k, v in got_nd.items()}
     for name in expected:
         req = grad_req.get(name, "null")
         if req == "write":
@@ -458,7 +464,7 @@ def check_symbolic_backward(sym, location, out_grads, expected, rtol=1e-5, atol=
                                 ("EXPECTED_%s" % name, "BACKWARD_%s" % name), equal_nan=equal_nan)
         else:
             raise ValueError("Invalid grad_req %s for argument %s" % (req, name))
-    return got
+    return got_nd             # NDArrays (with the requested gradient storage types), like the reference
 
 
 def check_speed(sym, location=None, ctx=None, N=20, grad_req=None, typ="whole", **kwargs):
