@@ -487,6 +487,13 @@ class SymbolBlock(HybridBlock):
         out, self._out_format = _flatten(outputs, "output")
         out = symbol.Group(out) if len(out) > 1 else out[0]
         input_names = set(i.name for i in syms)
+        # a SymbolBlock cannot own sparse parameters (block.py of the reference asserts on the inferred storage types)
+        for node in out._topo():
+            if node.op is None and node.name not in input_names:
+                st = node.var_attrs.get("__storage_type__", "default")
+                st = {"0": "default", "1": "row_sparse", "2": "csr"}.get(str(st), st)
+                assert st == "default", \
+                    "SymbolBlock doesn't support Parameter '%s' because its storage type is '%s'." % (node.name, st)
         for i in out.list_arguments():
             if i not in input_names:
                 self.params.get(i, allow_deferred_init=True)

@@ -21,11 +21,13 @@ def get_model(name, **kwargs):
     name = alias.get(name, name)
     if name not in models:
         raise ValueError("Model %s is not supported. Available options are\n\t%s" % (name, "\n\t".join(sorted(models.keys()))))
-    # pretrained / root / ctx are loader options of the reference's model zoo, not constructor arguments: weights cannot be
-    # downloaded here, so pretrained=True is an error and the other two are accepted and ignored
-    if kwargs.pop("pretrained", False):
-        raise RuntimeError("pretrained weights need network access, which is not available here")
-    kwargs.pop("root", None)
+    # pretrained / root / ctx are loader options of the reference's model zoo, not constructor arguments: pretrained weights
+    # come from the local model store (model_store.get_model_file; nothing is downloaded)
+    pretrained = kwargs.pop("pretrained", False)
+    root = kwargs.pop("root", None)
+    if pretrained:
+        from ..model_store import get_model_file
+        pfile = get_model_file(name, root=root)          # raises (with the expected location) when the file is not staged
     import inspect
     fn = models[name]
     try:
@@ -36,7 +38,10 @@ def get_model(name, **kwargs):
     if not accepts_ctx:
         kwargs.pop("ctx", None)
     try:
-        return fn(**kwargs)
+        net = fn(**kwargs)
+        if pretrained:
+            net.load_parameters(pfile, ctx=kwargs.get("ctx"))
+        return net
     except TypeError as e:
         if "ctx" in str(e) and "ctx" in kwargs:
             kwargs.pop("ctx")

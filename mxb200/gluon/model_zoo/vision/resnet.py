@@ -294,19 +294,25 @@ _BLOCKS = [{"basic_block": BasicBlockV1, "bottle_neck": BottleneckV1},
 def get_resnet(version, num_layers, pretrained=False, ctx=None, root=None, layout=None, dtype=None, **kwargs):
     """``version`` 1 / 2 -> reference Gluon definitions; ``'v1b'`` (or layout='NHWC') -> FusedResNet."""
     assert num_layers in _SPEC, "Invalid number of layers: %d. Options are %s" % (num_layers, str(_SPEC.keys()))
+    pfile = None
     if pretrained:
-        raise RuntimeError("pretrained weights need network access, which is not available here")
+        from ..model_store import get_model_file
+        pfile = get_model_file("resnet%d_v%s" % (num_layers, version), root=root)    # local model store, nothing is downloaded
     if version in ("v1b", "1b") or layout == "NHWC":
         ver = "v1b" if version in ("v1b", "1b", 1) else "v1"
         net = FusedResNet(num_layers, version=ver, dtype=dtype or "bfloat16", layout=layout or "NHWC", **kwargs)
         if ctx is not None:
             net.initialize(ctx=ctx)
+        if pfile is not None:
+            net.load_parameters(pfile, ctx=ctx)
         return net
     block_type, layers, channels = _SPEC[num_layers]
     assert 1 <= version <= 2, "Invalid resnet version: %d. Options are 1 and 2." % version
     net = _NETS[version - 1](_BLOCKS[version - 1][block_type], layers, channels, **kwargs)
     if ctx is not None:
         net.initialize(ctx=ctx)
+    if pfile is not None:
+        net.load_parameters(pfile, ctx=ctx)
     if dtype is not None:
         net.cast(dtype)
     return net

@@ -380,7 +380,7 @@ for _pre in ("_random_", "_sample_"):
     _rand(_pre + "uniform", lambda s, ex, dev: ex[0] + (ex[1] - ex[0]) * torch.rand(s, device=dev))
     _rand(_pre + "normal", lambda s, ex, dev: ex[0] + ex[1] * torch.randn(s, device=dev))
     _rand(_pre + "exponential", lambda s, ex, dev: torch.distributions.Exponential(ex[0]).sample())
-    _rand(_pre + "gamma", lambda s, ex, dev: torch.distributions.Gamma(ex[0], 1.0 / ex[1]).sample())
+    _rand(_pre + "gamma", lambda s, ex, dev: torch.where(ex[0] > 0, torch._standard_gamma(ex[0].clamp_min(1e-30)) * ex[1], torch.zeros_like(ex[0])))   # alpha = 0: the point mass at 0
     _rand(_pre + "poisson", lambda s, ex, dev: torch.poisson(ex[0]))
     _rand(_pre + "negative_binomial", _neg_binomial)
     _rand(_pre + "generalized_negative_binomial", _gen_neg_binomial)
@@ -388,6 +388,11 @@ for _pre in ("_random_", "_sample_"):
 
 @register(name="_sample_multinomial")
 def _sample_multinomial(data, shape=None, get_prob=False, dtype="int32", out=None):
+    # the class index must be representable in the output dtype (sample_multinomial_op.h bound check)
+    limit = {"uint8": 1 << 8, "int8": 1 << 7, "float16": 1 << 11, "float32": 1 << 24, "int32": 1 << 31}.get(np.dtype(dtype).name if not isinstance(dtype, str) else dtype)
+    if limit is not None and data.shape[-1] > limit:
+        raise MXNetError("sample_multinomial: %d classes exceed the largest integer dtype %s holds exactly (%d)" % (data.shape[-1], dtype, limit))
+
     def g(p):
         n = 1 if shape in (None, ()) else int(np.prod(shape))
         flat = p.reshape(-1, p.shape[-1]).float()
@@ -404,6 +409,41 @@ def _sample_multinomial(data, shape=None, get_prob=False, dtype="int32", out=Non
             return res, lp
         return res
     return _out(_op(g, data), out)
+
+
+@register(name="_sample_unique_zipfian")
+def _sample_unique_zipfian(range_max, shape=None, ctx=None, out=None):
+    """Per row: ``num_sampled`` DISTINCT classes from the log-uniform (Zipfian) distribution over [0, range_max), drawn with
+    rejection of duplicates; also returns how many draws each row needed (random/unique_sample_op.h) -- the count sampled
+    softmax uses to correct for the without-replacement sampling."""
+    c, dev = _ctx_dev(ctx)
+    batch, n = int(shape[0]), int(shape[1])
+    if n > int(range_max):
+        raise MXNetError("_sample_unique_zipfian: cannot draw %d distinct classes out of %d" % (n, int(range_max)))
+    log_range = math.log(int(range_max) + 1)
+    res = torch.empty((batch, n), dtype=torch.int64, device=dev)
+    tries = torch.empty((batch,), dtype=torch.int64, device=dev)
+    for b in range(batch):
+        got = torch.empty(0, dtype=torch.int64, device=dev)
+        ntry = 0
+        while got.numel() < n:
+            m = max(2 * (n - got.numel()), 64)
+            draw = ((torch.rand(m, device=dev, dtype=torch.float64) * log_range).exp() - 1).to(torch.int64) % int(range_max)
+            # keep first occurrences in draw order, count the draws consumed up to the one that completes the set
+            allv = torch.cat([got, draw])
+            uniq, inv = torch.unique(allv, return_inverse=True)
+            first = torch.full((uniq.numel(),), allv.numel(), dtype=torch.int64, device=dev).scatter_reduce(
+                0, inv, torch.arange(allv.numel(), device=dev), reduce="amin")
+            order = torch.sort(first).values
+            if uniq.numel() >= n:
+                last = int(order[n - 1])
+                ntry += last - got.numel() + 1
+                got = allv[order[:n]]
+            else:
+                ntry += m
+                got = allv[order]
+        res[b], tries[b] = got, ntry
+    return NDArray(res, c), NDArray(tries, c)
 
 
 # ----------------------------------------------------------------------------- contrib: detection helpers
