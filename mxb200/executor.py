@@ -17,6 +17,8 @@ from . import autograd
 
 __all__ = ["Executor"]
 
+_NON_DIFFERENTIABLE = {"batch_take"}
+
 
 class Executor(object):
     def __init__(self, symbol, ctx, args, args_grad=None, grad_req="write", aux_states=None, group2ctx=None):
@@ -81,6 +83,13 @@ class Executor(object):
             self.grad_arrays.append(g)
             self._grad_pairs.append((a, g, req))
         self.arg_arrays = pos_args
+        if self._grad_pairs:
+            # operators without a gradient definition cannot sit on a path a requested gradient takes (nnvm gradient pass:
+            # "Operator X is non-differentiable because it didn't register FGradient attribute")
+            _reach, ops = self._grad_reach()
+            for node in ops:
+                if node.op in _NON_DIFFERENTIABLE:
+                    raise MXNetError("Operator %s is non-differentiable because it didn't register FGradient attribute." % node.op)
         self.aux_arrays = [self.aux_dict[n] for n in aux_names]
         self._outputs = []
         self._output_names = symbol.list_outputs()
@@ -220,6 +229,13 @@ class Executor(object):
                     g._t.copy_(live)
             elif live is not g._t:
                 g._t = live                       # keep the handles pointing at the live tensors
+        # a failed operator's exception travels with everything computed from it: the gradients too
+        for o in self.outputs:
+            exc = getattr(o._t, "_mx_exc", None)
+            if exc is not None:
+                for _a, g, _r in self._grad_pairs:
+                    g._t._mx_exc = exc
+                break
         if self._monitor_callback is not None:
             for name, arr in getattr(self, "_mon_nograd", []):
                 self._monitor_callback(name, nd.zeros(arr.shape, ctx=arr.context, dtype=arr.dtype))
@@ -268,5 +284,61 @@ class Executor(object):
             new_aux[n] = a
         return Executor(self._symbol, self._ctx, new_args, None, self._grad_req, new_aux, self._group2ctx)
 
+    def _rebind_arrays(self):
+        """After arg_dict / grad_dict entries were replaced from outside (parameter sharing between bucket executors):
+        refresh the per-position bookkeeping backward() works from."""
+        if self._by_node is not None:
+            return
+        names = self._symbol.list_arguments()
+        self.arg_arrays = [self.arg_dict[n] for n in names]
+        self.grad_arrays = [self.grad_dict.get(n) for n in names]
+        self._grad_pairs = [(self.arg_dict[n], self.grad_dict[n], self._grad_req.get(n, "null")) for n in names
+                            if n in self.grad_dict and self._grad_req.get(n, "null") != "null"]
+        self._grad_cast = {id(a): g for a, g, _r in self._grad_pairs
+                           if g._t.dtype != a._t.dtype or g._t.device != a._t.device}
+
+    def _grad_reach(self):
+        """Names of the arguments a gradient can reach from the outputs (zero-gradient propagation stops at BlockGrad /
+        stop_gradient like the reference's gradient pass) and the operator nodes on those paths."""
+        reach, ops, seen = set(), [], set()
+        stack = [n for n, _i in self._symbol._outputs]
+        while stack:
+            n = stack.pop()
+            if id(n) in seen:
+                continue
+            seen.add(id(n))
+            if n.op is None:
+                reach.add(n.name)
+                continue
+            if n.op in ("BlockGrad", "stop_gradient"):
+                continue
+            ops.append(n)
+            stack.extend(i for i, _ in n.inputs)
+        return reach, ops
+
     def debug_str(self):
-        return self._symbol.tojson()
+        """Graph listing plus the memory the bound graph needs (graph_executor.cc debug string: "Total N MB allocated").
+        Inference-only graphs (no gradient requested, or none can reach an argument) recycle intermediates; a training
+        graph keeps every intermediate for the backward pass and owns the gradient arrays."""
+        lines = ["Symbol Outputs:"] + ["\toutput[%d]=%s" % (i, n) for i, n in enumerate(self._output_names)]
+        size = lambda a: int(np.prod(a.shape)) * a._t.element_size() if hasattr(a, "_t") else 0   # noqa: E731
+        total = sum(size(a) for a in self.arg_dict.values()) + sum(size(a) for a in self.aux_dict.values())
+        reach, _ops = self._grad_reach()
+        training = any(self._grad_req.get(n, "null") != "null" for n in reach if n in self.arg_dict)
+        try:
+            internals = self._symbol.get_internals()
+            shapes = {n: a.shape for n, a in list(self.arg_dict.items()) + list(self.aux_dict.items())}
+            _a, outs, _x = internals.infer_shape(**shapes)
+            names = internals.list_outputs()
+            inter = [int(np.prod(s)) * 4 for n, s in zip(names, outs) if s is not None and n not in self.arg_dict and n not in self.aux_dict]
+        except Exception:  # noqa: BLE001 -- best effort report
+            inter = []
+        for node in self._symbol._topo():
+            if node.op is not None:
+                lines.append("Op:%s, Name=%s" % (node.op, node.name))
+        if training:
+            total += sum(inter) + sum(size(self.arg_dict[n]) for n in reach if n in self.arg_dict and self._grad_req.get(n, "null") != "null")
+        else:
+            total += sum(sorted(inter)[-2:])               # ping-pong buffers
+        lines.append("Total %d MB allocated" % (total >> 20))
+        return "\n".join(lines)

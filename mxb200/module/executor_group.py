@@ -98,6 +98,12 @@ class DataParallelExecutorGroup(object):
         self.label_names = [i[0] for i in label_shapes] if label_shapes is not None else []
         old_execs = self.execs
         self.execs = []
+        # input arrays are pooled per device and shared between the executor groups of a bucketing module: a bucket whose
+        # inputs fit into an array that exists already gets a view of it (executor_group.py shared_data_arrays)
+        if shared_group is not None and getattr(shared_group, "shared_data_arrays", None) is not None:
+            self.shared_data_arrays = shared_group.shared_data_arrays
+        elif getattr(self, "shared_data_arrays", None) is None or reshape:
+            self.shared_data_arrays = [{} for _ in self.contexts]
         for i, ctx in enumerate(self.contexts):
             shapes = {}
             for desc, axis in zip(data_shapes, self.data_layouts):
@@ -126,6 +132,25 @@ class DataParallelExecutorGroup(object):
                 ex.arg_arrays = [ex.arg_dict[n] for n in self.arg_names]
                 ex.grad_arrays = [ex.grad_dict.get(n) for n in self.arg_names]
                 ex.aux_arrays = [ex.aux_dict[n] for n in self.aux_names]
+            pool = self.shared_data_arrays[i]
+            if shared_group is not None and not (reshape and old_execs):
+                # arrays this group had to create itself (parameters the shared group does not have) join the pool too
+                for n in self.arg_names:
+                    if n not in shared_group.execs[i].arg_dict and n not in self.data_names + self.label_names:
+                        pool.setdefault(n, ex.arg_dict[n])
+            for n in self.data_names + self.label_names:
+                if n not in ex.arg_dict or ex._grad_req.get(n, "null") != "null":
+                    continue
+                arr = ex.arg_dict[n]
+                have = pool.get(n)
+                if have is not None and have.size >= arr.size and have.dtype == arr.dtype and have.context == arr.context \
+                        and have._t.is_contiguous():
+                    view = have if have.shape == arr.shape else NDArray(have._t.reshape(-1)[:arr.size].view(arr.shape), have.context)
+                    ex.arg_dict[n] = view
+                else:
+                    pool[n] = arr
+            ex.arg_arrays = [ex.arg_dict[n] for n in self.arg_names]
+            ex._rebind_arrays()
             self.execs.append(ex)
         self._collect_arrays()
 

@@ -638,9 +638,12 @@ _PENDING = []
 
 def _raise_deferred(t):
     e = getattr(t, "_mx_exc", None)
-    if e is not None:
+    if e is not None and not getattr(e, "_mx_delivered", False):
         if e in _PENDING:
             _PENDING.remove(e)
+        # an operator's failure is delivered ONCE, at the first wait on any array that depends on it (threaded_engine.cc
+        # rethrows and clears the exception of the variable); later reads of dependants return without raising
+        e._mx_delivered = True
         raise e
 
 
