@@ -940,8 +940,11 @@ def BatchNorm(data, gamma, beta, moving_mean, moving_var, eps=1e-3, momentum=0.9
             if y is not None:
                 return y
         gm_ = torch.ones_like(gm) if fix_gamma else gm
-        if mm.dtype != x.dtype or gm_.dtype != x.dtype:
-            # mixed dtypes (fp32 statistics under fp64 / fp16 data): compute in the data's dtype, write the statistics back
+        f64 = torch.float64
+        if (x.dtype == f64) != (mm.dtype == f64) or (x.dtype == f64) != (gm_.dtype == f64):
+            # float64 data with float32 parameters / statistics (or the reverse), which torch does not mix (the low-precision
+            # data + fp32 statistics combination IS native and stays on the fast path): compute in the data's dtype and
+            # write the statistics back
             mm_c, mv_c = mm.to(x.dtype), mv.to(x.dtype)
             r = F.batch_norm(x.movedim(axis, 1), mm_c, mv_c, gm_.to(x.dtype), bt.to(x.dtype), training, 1.0 - momentum, eps).movedim(1, axis)
             if training:
