@@ -215,11 +215,20 @@ class Executor(object):
         if heads:
             autograd.backward(heads, hgrads)
         # 'write' means every bound gradient array is written by every backward(): arguments no gradient reached (inputs of
-        # integer-valued operators, disconnected branches) read zero, not the previous contents
-        for a, g, req in self._grad_pairs:
+        # integer-valued operators, disconnected branches) read zero, not the previous contents.  "Not reached" = no path from
+        # a differentiable head in the graph, or the array's write hook did not fire in this pass; arrays whose hook was
+        # taken over by a fused update path (Module._maybe_fuse clears its gradient arena itself) are left alone.
+        head_ids = tuple(i for i, o in enumerate(self.outputs) if o._t.requires_grad)
+        cache = self.__dict__.setdefault("_reach_cache", {})
+        if head_ids not in cache:
+            cache[head_ids] = self._grad_reach(head_ids)[0]
+        reach = cache[head_ids]
+        for (a, g, req), n in zip(self._grad_pairs, self._grad_pair_names()):
             leaf = getattr(a, "_dense_leaf", None)                # sparse arguments accumulate in their dense leaf
             leaf = a if leaf is None else leaf
-            if req == "write" and (not heads or getattr(leaf, "_bw_epoch", -1) <= epoch) and a._t.grad is not None:
+            unreachable = (not heads) or (n is not None and n not in reach)
+            missed = getattr(leaf, "_grad_hook", None) is not None and getattr(leaf, "_bw_epoch", -1) <= epoch
+            if req == "write" and (unreachable or missed) and a._t.grad is not None:
                 a._t.grad.zero_()
             live = a._t.grad
             if live is None:
@@ -297,11 +306,24 @@ class Executor(object):
         self._grad_cast = {id(a): g for a, g, _r in self._grad_pairs
                            if g._t.dtype != a._t.dtype or g._t.device != a._t.device}
 
-    def _grad_reach(self):
+    def _grad_pair_names(self):
+        """Argument name of every entry of ``_grad_pairs`` (None when names are ambiguous: duplicate-named variables)."""
+        names = self.__dict__.get("_pair_names")
+        if names is None or len(names) != len(self._grad_pairs):
+            if self._by_node is not None:
+                names = [None] * len(self._grad_pairs)
+            else:
+                by_id = {id(a): n for n, a in self.arg_dict.items()}
+                names = [by_id.get(id(a)) for a, _g, _r in self._grad_pairs]
+            self._pair_names = names
+        return names
+
+    def _grad_reach(self, head_ids=None):
         """Names of the arguments a gradient can reach from the outputs (zero-gradient propagation stops at BlockGrad /
         stop_gradient like the reference's gradient pass) and the operator nodes on those paths."""
         reach, ops, seen = set(), [], set()
-        stack = [n for n, _i in self._symbol._outputs]
+        outs = self._symbol._outputs
+        stack = [n for k, (n, _i) in enumerate(outs) if head_ids is None or k in head_ids]
         while stack:
             n = stack.pop()
             if id(n) in seen:

@@ -230,3 +230,63 @@ def test_fit_epoch_begin_callback_runs_before_each_epoch():
     mod.fit(it, num_epoch=3, epoch_begin_callback=lambda epoch, sym, arg, aux: seen.append((epoch, len(ends))),
             epoch_end_callback=lambda epoch, sym, arg, aux: ends.append(epoch))
     assert seen == [(0, 0), (1, 1), (2, 2)]
+
+
+def test_module_trains_when_write_hooks_are_taken_over():
+    """The fused GPU update path (Module._maybe_fuse) removes the parameters' 'write' hooks because its kernel clears the
+    gradient arena itself.  The executor's "no gradient reached this argument -> zero" rule must not mistake that for a
+    missing gradient (it once did: every gradient was zeroed after backward and the GPU Module stopped learning)."""
+    import numpy as np
+    import mxb200 as mx
+    rs = np.random.RandomState(0)
+    x = rs.rand(256, 1, 12, 12).astype("f")
+    y = (x.mean(axis=(1, 2, 3)) > 0.5).astype("f")
+    x[y == 1, :, :6, :] += 0.5
+    it = mx.io.NDArrayIter(x, y, batch_size=32, shuffle=True)
+    d = mx.sym.var("data")
+    n = mx.sym.Convolution(d, kernel=(3, 3), num_filter=8, name="c1")
+    n = mx.sym.BatchNorm(n, name="bn1")
+    n = mx.sym.Activation(n, act_type="relu")
+    n = mx.sym.Pooling(n, kernel=(2, 2), stride=(2, 2), pool_type="max")
+    n = mx.sym.FullyConnected(mx.sym.flatten(n), num_hidden=2, name="fc")
+    net = mx.sym.SoftmaxOutput(n, name="softmax")
+    mod = mx.mod.Module(net, context=[mx.cpu(0)])
+    mod.bind(it.provide_data, it.provide_label)
+    mod.init_params(mx.init.Xavier())
+    mod.init_optimizer(optimizer="sgd", optimizer_params={"learning_rate": 0.1, "momentum": 0.9})
+    ex = mod._exec_group.execs[0]
+    for name in mod._exec_group.param_names:
+        a = ex.arg_dict[name]
+        if a._grad_hook is not None:
+            a._grad_hook.remove()
+            a._grad_hook = None
+    for _ in range(6):
+        it.reset()
+        for b in it:
+            mod.forward_backward(b)
+            assert float(abs(ex.grad_dict["fc_weight"].asnumpy()).sum()) > 0
+            mod.update()
+            for name in mod._exec_group.param_names:
+                ex.grad_dict[name][:] = 0
+    assert dict(mod.score(it, "acc"))["accuracy"] > 0.9
+
+
+def test_executor_write_request_zeroes_unreached_gradients():
+    import numpy as np
+    import mxb200 as mx
+    x = mx.sym.var("x")
+    y = mx.sym.shape_array(x)
+    g = mx.nd.array(np.full((3, 4), 7.0))
+    exe = y.bind(mx.cpu(), args={"x": mx.nd.ones((3, 4))}, args_grad={"x": g})
+    exe.forward(is_train=True)
+    exe.backward()
+    assert float(abs(g.asnumpy()).sum()) == 0.0
+    # two variables of the same name are kept apart by position
+    a, b = mx.sym.var("data"), mx.sym.var("data")
+    s = mx.sym.maximum(a, b) + mx.sym.minimum(a, b)
+    ga, gb = mx.nd.zeros((2, 2)), mx.nd.zeros((2, 2))
+    exe = s.bind(mx.cpu(), args=[mx.nd.full((2, 2), 2.0), mx.nd.full((2, 2), 3.0)], args_grad=[ga, gb])
+    out = exe.forward(is_train=True)[0].asnumpy()
+    assert (out == 5.0).all()
+    exe.backward(mx.nd.ones((2, 2)))
+    assert (ga.asnumpy() == 1.0).all() and (gb.asnumpy() == 1.0).all()
