@@ -53,7 +53,11 @@ class _TokenEmbedding(vocab.Vocabulary):
         with io.open(path, "r", encoding=encoding) as f:
             for n, line in enumerate(f):
                 parts = line.rstrip().split(elem_delim)
-                if len(parts) < 2 or (n == 0 and len(parts) == 2):     # fastText header "count dim"
+                assert len(parts) > 1, "At line %d of the pre-trained text embedding file: the data format of the " \
+                    "pre-trained token embedding file %s is unexpected." % (n + 1, path)
+                if len(parts) == 2:                # a 1-dimensional "vector": the fastText header "count dim", skipped
+                    logging.warning("At line %d of %s: token %s with a 1-dimensional vector is likely a header and is skipped",
+                                    n + 1, path, parts[0])
                     continue
                 tok, vals = parts[0], parts[1:]
                 if tok == self.unknown_token:
@@ -65,8 +69,9 @@ class _TokenEmbedding(vocab.Vocabulary):
                     logging.warning("duplicate token %r in %s skipped (first occurrence kept)", tok, path)
                     continue
                 seen.add(tok)
-                if self._vec_len and len(vals) != self._vec_len:
-                    continue
+                assert not self._vec_len or len(vals) == self._vec_len, \
+                    "At line %d of the pre-trained token embedding file: the dimension of token %s is %d but the dimension " \
+                    "of previous tokens is %d. Dimensions of all the tokens must be the same." % (n + 1, tok, len(vals), self._vec_len)
                 self._vec_len = self._vec_len or len(vals)
                 toks.append(tok)
                 vecs.append(np.asarray(vals, dtype=np.float32))
@@ -84,12 +89,17 @@ class _TokenEmbedding(vocab.Vocabulary):
         self._idx_to_vec = nd.array(mat)
 
     def _build_for_vocabulary(self, vocabulary, embeddings):
+        # look the vocabulary's tokens up in every source embedding FIRST (a source may be this very object, whose own
+        # token table is replaced by the vocabulary's below)
+        # row 0 -- the vocabulary's unknown token, whatever it is called -- takes each source's UNKNOWN vector
+        cols = []
+        for emb in embeddings:
+            m = emb.get_vecs_by_tokens(list(vocabulary.idx_to_token)).asnumpy().copy()
+            m[0] = emb.idx_to_vec[0].asnumpy()
+            cols.append(m)
         self._idx_to_token = list(vocabulary.idx_to_token)
         self._token_to_idx = dict(vocabulary.token_to_idx)
         self._unknown_token, self._reserved_tokens = vocabulary.unknown_token, vocabulary.reserved_tokens
-        cols = []
-        for emb in embeddings:
-            cols.append(emb.get_vecs_by_tokens(self._idx_to_token).asnumpy())
         mat = np.concatenate(cols, axis=1)
         self._vec_len = mat.shape[1]
         self._idx_to_vec = nd.array(mat)
