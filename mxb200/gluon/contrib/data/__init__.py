@@ -1,7 +1,8 @@
-"""gluon.contrib.data (reference: python/mxnet/gluon/contrib/data/sampler.py)."""
+"""gluon.contrib.data (reference: python/mxnet/gluon/contrib/data/{sampler,text}.py)."""
 from ...data import sampler as _sampler
+from . import text  # noqa: F401
 
-__all__ = ["IntervalSampler"]
+__all__ = ["IntervalSampler", "text"]
 
 
 class IntervalSampler(_sampler.Sampler):

@@ -156,8 +156,11 @@ class Module(BaseModule):
                 if name in cache:
                     cache_arr = cache[name]
                     if cache_arr is not arr:
-                        with torch.no_grad():
-                            arr._t.copy_(cache_arr._t.to(arr._t.dtype))
+                        if getattr(arr, "stype", "default") != "default":
+                            arr[:] = cache_arr                      # sparse host copy: storage-aware assignment
+                        else:
+                            with torch.no_grad():
+                                arr._t.copy_(cache_arr._t.to(arr._t.dtype))
                 else:
                     if not allow_missing:
                         raise RuntimeError("%s is not presented" % name)
@@ -177,6 +180,13 @@ class Module(BaseModule):
             _impl(name, arr, arg_params)
         for name, arr in sorted(self._aux_params.items()):
             _impl(name, arr, aux_params)
+        # variables declared with a sparse storage type keep it in the host-side copy (module.py:init_params allocates
+        # ``_arg_params`` with the executor arrays' stype); the executor's working arrays stay dense
+        for name in list(self._arg_params):
+            st = (attrs.get(name) or {}).get("__storage_type__")
+            st = {"1": "row_sparse", "2": "csr"}.get(str(st), st)
+            if st in ("row_sparse", "csr") and getattr(self._arg_params[name], "stype", "default") == "default":
+                self._arg_params[name] = self._arg_params[name].tostype(st)
         self.params_initialized = True
         self._params_dirty = False
         self._exec_group.set_params(self._arg_params, self._aux_params, allow_extra=allow_extra)
