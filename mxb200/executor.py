@@ -63,6 +63,13 @@ class Executor(object):
         self._grad_cast = {}
         self._grad_pairs = []               # (argument array, bound gradient array, request) per position
         self.grad_arrays = []
+        self._sparse_mirrors = {}
+        sparse_grad_names = set()
+        for node in symbol._topo():
+            if (node.op == "Embedding" and str(node.attrs.get("sparse_grad", False)) in ("True", "1", "true")) \
+                    or node.op == "_contrib_SparseEmbedding":
+                if len(node.inputs) > 1 and node.inputs[1][0].op is None:
+                    sparse_grad_names.add(node.inputs[1][0].name)
         for n, a, g, req in zip(arg_names, pos_args, pos_grads, pos_req):
             if req == "null":
                 self.grad_arrays.append(None)
@@ -79,9 +86,16 @@ class Executor(object):
                 a._t.grad = g._t
             else:
                 g = NDArray(a._t.grad, a.context)
+            self._grad_pairs.append((a, g, req))
+            if n in sparse_grad_names and n not in (args_grad if isinstance(args_grad, dict) else {}) and not dup:
+                # Embedding(sparse_grad=True) / SparseEmbedding weights: the executor-owned gradient is handed out as a
+                # row_sparse array (rows = the looked-up ids), refreshed from the dense accumulator after every backward()
+                from .ndarray import sparse as _sp
+                mirror = _sp.zeros("row_sparse", a.shape, ctx=a.context, dtype=a.dtype)
+                self._sparse_mirrors[n] = (a, mirror)
+                g = mirror
             self.grad_dict[n] = g
             self.grad_arrays.append(g)
-            self._grad_pairs.append((a, g, req))
         self.arg_arrays = pos_args
         if self._grad_pairs:
             # operators without a gradient definition cannot sit on a path a requested gradient takes (nnvm gradient pass:
@@ -172,6 +186,7 @@ class Executor(object):
             with autograd.pause(train_mode=False):
                 self.outputs = self._symbol.eval_nd(feed, self._group2ctx, monitor=mon)
         self._ran_forward = True
+        self._last_is_train = bool(is_train)
         return self.outputs
 
     def _make_monitor(self):
@@ -212,6 +227,12 @@ class Executor(object):
             heads.append(o)
             hgrads.append(out_grads[i] if i < len(out_grads) else None)
         epoch = autograd._bw_epoch[0]
+        if heads and any(getattr(h._t, "_mx_graph_freed", False) for h in heads):
+            # backward() twice on one forward(): the reference's static graph allows it; the tape here was consumed by the
+            # first call, so the forward pass is replayed on the same inputs (stateful operators -- BatchNorm statistics,
+            # dropout masks -- see a second forward)
+            self.forward(is_train=getattr(self, "_last_is_train", True))
+            heads = [o for o in self.outputs if o._t.requires_grad]
         if heads:
             autograd.backward(heads, hgrads)
         # 'write' means every bound gradient array is written by every backward(): arguments no gradient reached (inputs of
@@ -238,6 +259,10 @@ class Executor(object):
                     g._t.copy_(live)
             elif live is not g._t:
                 g._t = live                       # keep the handles pointing at the live tensors
+        for n, (a, mirror) in self._sparse_mirrors.items():
+            if a._t.grad is not None:
+                from .ndarray import sparse as _sp
+                _sp.cast_storage(NDArray(a._t.grad.detach(), a.context), "row_sparse").copyto(mirror)
         # a failed operator's exception travels with everything computed from it: the gradients too
         for o in self.outputs:
             exc = getattr(o._t, "_mx_exc", None)
@@ -301,8 +326,11 @@ class Executor(object):
         names = self._symbol.list_arguments()
         self.arg_arrays = [self.arg_dict[n] for n in names]
         self.grad_arrays = [self.grad_dict.get(n) for n in names]
-        self._grad_pairs = [(self.arg_dict[n], self.grad_dict[n], self._grad_req.get(n, "null")) for n in names
-                            if n in self.grad_dict and self._grad_req.get(n, "null") != "null"]
+        keep = {id(a): (a, g, r) for a, g, r in self._grad_pairs}
+        self._grad_pairs = [keep[id(self.arg_dict[n])] if n in self._sparse_mirrors and id(self.arg_dict[n]) in keep
+                            else (self.arg_dict[n], self.grad_dict[n], self._grad_req.get(n, "null"))
+                            for n in names if n in self.grad_dict and self._grad_req.get(n, "null") != "null"]
+        self.__dict__.pop("_pair_names", None)
         self._grad_cast = {id(a): g for a, g, _r in self._grad_pairs
                            if g._t.dtype != a._t.dtype or g._t.device != a._t.device}
 

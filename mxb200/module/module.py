@@ -331,7 +331,7 @@ class Module(BaseModule):
         ex = self._exec_group.execs[0]
         for n in self._exec_group.param_names:
             a, g = ex.arg_dict.get(n), ex.grad_dict.get(n)
-            if a is None or g is None or getattr(a, "stype", "default") != "default":
+            if a is None or g is None or getattr(a, "stype", "default") != "default" or getattr(g, "stype", "default") != "default":
                 return False
             if a._t.dtype not in (torch.float32, torch.bfloat16):      # fp16 / fp64: generic per-key updaters
                 return False

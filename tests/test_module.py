@@ -290,3 +290,32 @@ def test_executor_write_request_zeroes_unreached_gradients():
     assert (out == 5.0).all()
     exe.backward(mx.nd.ones((2, 2)))
     assert (ga.asnumpy() == 1.0).all() and (gb.asnumpy() == 1.0).all()
+
+
+def test_module_sparse_grad_embedding_trains_with_row_sparse_gradients():
+    """Embedding(sparse_grad=True): the executor hands the weight gradient out as a row_sparse array (rows = looked-up ids),
+    the updater / kvstore apply it lazily; backward() may be called twice on one forward()."""
+    import numpy as np
+    import mxb200 as mx
+    rs = np.random.RandomState(0)
+    x = rs.randint(0, 50, size=(256, 4)).astype("f")
+    y = (x[:, 0] % 2).astype("f")
+    for kv in (None, "local"):
+        it = mx.io.NDArrayIter(x, y, batch_size=32, shuffle=True)
+        e = mx.sym.Embedding(mx.sym.var("data"), input_dim=50, output_dim=8, sparse_grad=True, name="emb")
+        net = mx.sym.SoftmaxOutput(mx.sym.FullyConnected(mx.sym.flatten(e), num_hidden=2, name="fc"), name="softmax")
+        mod = mx.mod.Module(net, context=[mx.cpu(0)])
+        mod.fit(it, num_epoch=25, optimizer="sgd", optimizer_params={"learning_rate": 0.5, "momentum": 0.9}, kvstore=kv,
+                initializer=mx.init.Xavier())
+        g = mod._exec_group.execs[0].grad_dict["emb_weight"]
+        assert g.stype == "row_sparse" and 0 < g.indices.shape[0] <= 50
+        assert dict(mod.score(it, "acc"))["accuracy"] > 0.95
+    ex = net.simple_bind(mx.cpu(), data=(8, 4), grad_req={"data": "null", "softmax_label": "null", "emb_weight": "write",
+                                                          "fc_weight": "write", "fc_bias": "write"})
+    ex.arg_dict["data"][:] = x[:8]
+    ex.arg_dict["emb_weight"][:] = mx.nd.array(rs.rand(50, 8))
+    ex.forward(is_train=True)
+    ex.backward()
+    first = ex.grad_dict["emb_weight"].asnumpy().copy()
+    ex.backward()
+    assert np.allclose(first, ex.grad_dict["emb_weight"].asnumpy())
