@@ -18,6 +18,7 @@ def get_model(name, **kwargs):
     for w in ("1.0", "0.75", "0.5", "0.25"):
         alias["mobilenet" + w] = "mobilenet" + w.replace(".", "_")
         alias["mobilenetv2_" + w] = "mobilenet_v2_" + w.replace(".", "_")
+    store_name = name                                   # the model store's file names use the registry spelling ('squeezenet1.1')
     name = alias.get(name, name)
     if name not in models:
         raise ValueError("Model %s is not supported. Available options are\n\t%s" % (name, "\n\t".join(sorted(models.keys()))))
@@ -27,7 +28,12 @@ def get_model(name, **kwargs):
     root = kwargs.pop("root", None)
     if pretrained:
         from ..model_store import get_model_file
-        pfile = get_model_file(name, root=root)          # raises (with the expected location) when the file is not staged
+        try:
+            pfile = get_model_file(store_name, root=root)    # raises (with the expected location) when the file is not staged
+        except Exception:  # noqa: BLE001 -- also accept the python-identifier spelling
+            if store_name == name:
+                raise
+            pfile = get_model_file(name, root=root)
     import inspect
     fn = models[name]
     try:

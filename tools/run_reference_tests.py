@@ -24,6 +24,36 @@ DEFAULT = ["test_attr", "test_autograd", "test_base", "test_contrib_autograd", "
            "test_sparse_operator", "test_symbol", "test_thread_local", "test_viz"]
 
 
+# why a test still fails (kept next to the runner so that the table explains itself); anything not listed is "unclassified"
+NETWORK = "needs the network (data set / pretrained weights / embedding download)"
+NUMPY2 = "the test's own code is rejected by numpy 2 (list-of-slices assignment, out-of-range integer, ragged array)"
+INTGRAD = "integer autograd (torch autograd is floating point only)"
+GETSYM = "autograd.get_symbol: the imperative tape is torch's, there is no NNVM graph to return"
+SPARSEPARAM = "a row_sparse Gluon Parameter keeps dense storage behind row_sparse_data views"
+KNOWN_CAUSES = {
+    "test_MNISTIter": NETWORK, "test_Cifar10Rec": NETWORK, "test_LibSVMIter": NETWORK, "test_datasets": NETWORK,
+    "test_recordimage_dataset": NETWORK, "test_recordimage_dataset_with_data_loader_multiworker": NETWORK,
+    "test_image_folder_dataset": NETWORK, "test_imageiter": NETWORK, "test_models": NETWORK, "test_symbol_block": NETWORK,
+    "test_export": NETWORK, "test_import": NETWORK, "test_save_load": NETWORK, "test_hybrid_static_memory": NETWORK,
+    "test_hybrid_static_memory_switching": NETWORK, "test_hybrid_static_memory_recording": NETWORK,
+    "test_download_embed": NETWORK, "test_get_and_pretrain_file_names": "table of the 327 published fastText file names is not carried",
+    "test_load_000800": "fixture file save_000800.json is not part of the reference checkout",
+    "test_slice_axis": NUMPY2, "test_slice_like": NUMPY2, "test_init": NUMPY2, "test_pick": NUMPY2,
+    "test_cast": INTGRAD, "test_order": INTGRAD, "test_ndarray_indexing": INTGRAD,
+    "test_get_symbol": GETSYM, "test_inline": GETSYM,
+    "test_parameter_row_sparse_data": SPARSEPARAM,
+    "test_activations": "bit-exact ELU: expm1(x) here, exp(x) - 1 in the reference",
+    "test_adam": "fp16 + row_sparse + multi_precision Adam against the python reference optimizer",
+    "test_reshape": "an executor and its reshape() child do not share output memory",
+    "test_batchnorm_fallback": "BatchNorm(fix_gamma=True) is expected to REFUSE sparse gamma; here it runs",
+    "test_sparse_mathematical_core": "d gamma(x)/dx at 0: -inf here, +inf expected (the expectation depends on the scipy version)",
+    "test_elemwise_binary_ops": "storage type of elemwise_div(row_sparse, row_sparse) corner cases",
+    "test_slice_pooling2d_slice_pooling2d": "several hundred layer combinations: slower than the per-test time limit",
+    "test_batchnorm_training": "finite differences over 4-D inputs: at the per-test time limit on a loaded host",
+    "test_multi_proposal_op": "O(n^2) NMS on the host: at the per-test time limit on a loaded host",
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("tests", nargs="*")
@@ -32,7 +62,7 @@ def main():
     a = ap.parse_args()
     ref = os.environ.get("MXB200_REFERENCE_TESTS", "/root/reference/tests/python/unittest")
     shim = os.path.join(HERE, "reftests")
-    rows = []
+    rows, failures = [], []
     work = tempfile.mkdtemp(prefix="mxb200_reftests_")
     for t in (a.tests or DEFAULT):
         path = os.path.join(ref, t + ".py")
@@ -52,6 +82,8 @@ def main():
         line = tail[-1] if tail else ""
         get = lambda k: int((re.search(r"(\d+) " + k, line) or [0, 0])[1])   # noqa: E731
         rows.append((t, "ok" if line else "collect-error", get("passed"), get("failed"), get("skipped"), get("error")))
+        for m in re.finditer(r"^FAILED \S*::(\w+)", out, flags=re.M):
+            failures.append((t, m.group(1)))
         print("%-32s passed %3d  failed %3d  skipped %3d  errors %d" % (t, rows[-1][2], rows[-1][3], rows[-1][4], rows[-1][5]), flush=True)
     tp, tf = sum(r[2] for r in rows), sum(r[3] for r in rows)
     print("TOTAL passed %d failed %d (of %d test functions run)" % (tp, tf, tp + tf))
@@ -64,6 +96,10 @@ def main():
             for r in rows:
                 f.write("| %s | %d | %d | %d | %s |\n" % (r[0], r[2], r[3], r[4], r[1] if r[5] == 0 else "%s (%d errors)" % (r[1], r[5])))
             f.write("| **total** | **%d** | **%d** | | |\n" % (tp, tf))
+            if failures:
+                f.write("\n## Failing tests and why\n\n| file | test | cause |\n|---|---|---|\n")
+                for t, name in failures:
+                    f.write("| %s | %s | %s |\n" % (t, name, KNOWN_CAUSES.get(name, "unclassified")))
 
 
 if __name__ == "__main__":
