@@ -18,6 +18,7 @@ from . import autograd
 __all__ = ["Executor"]
 
 _NON_DIFFERENTIABLE = {"batch_take"}
+_FWD_STAMP = [0]
 
 
 class Executor(object):
@@ -123,6 +124,14 @@ class Executor(object):
                     self._outputs = [nd.zeros(s, ctx=self._ctx, dtype=t) for s, t in zip(out_shapes, out_types)]
             except Exception:  # noqa: BLE001 -- best effort; forward() fills the real values
                 pass
+        for ref in self.__dict__.get("_children", ()):
+            c = ref()
+            if c is not None and c._outputs and getattr(c, "_fwd_stamp", 0) > getattr(self, "_fwd_stamp", 0):
+                for mine, theirs in zip(self._outputs, c._outputs):
+                    if mine.shape[1:] == theirs.shape[1:] and theirs.shape[0] <= mine.shape[0] and mine._t.dtype == theirs._t.dtype:
+                        with torch.no_grad():
+                            mine._t[:theirs.shape[0]].copy_(theirs._t.detach())
+                self._fwd_stamp = c._fwd_stamp
         return self._outputs
 
     @outputs.setter
@@ -186,6 +195,8 @@ class Executor(object):
             with autograd.pause(train_mode=False):
                 self.outputs = self._symbol.eval_nd(feed, self._group2ctx, monitor=mon)
         self._ran_forward = True
+        _FWD_STAMP[0] += 1
+        self._fwd_stamp = _FWD_STAMP[0]
         self._last_is_train = bool(is_train)
         return self.outputs
 
@@ -316,7 +327,12 @@ class Executor(object):
                 new_args[n] = nd.zeros(shp, ctx=self._ctx, dtype=a.dtype)
         for n, a in self.aux_dict.items():
             new_aux[n] = a
-        return Executor(self._symbol, self._ctx, new_args, None, self._grad_req, new_aux, self._group2ctx)
+        child = Executor(self._symbol, self._ctx, new_args, None, self._grad_req, new_aux, self._group2ctx)
+        # the reference's reshaped executor works in the parent's memory: outputs of the child are visible in the leading
+        # part of the parent's output arrays.  Mirrored lazily, when the parent's outputs are read after the child ran.
+        import weakref
+        self.__dict__.setdefault("_children", []).append(weakref.ref(child))
+        return child
 
     def _rebind_arrays(self):
         """After arg_dict / grad_dict entries were replaced from outside (parameter sharing between bucket executors):
