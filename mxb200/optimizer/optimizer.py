@@ -120,10 +120,15 @@ class Optimizer(object):
     def update_multi_precision(self, index, weight, grad, state):
         if self.multi_precision and weight._t.dtype in _LOW_PRECISION:
             master, inner = state
-            g32 = NDArray(grad._t.float(), grad.context)
+            sparse_g = getattr(grad, "stype", "default") != "default"
+            # a row_sparse gradient stays row_sparse (the lazy update touches its rows only)
+            g32 = grad.astype("float32") if sparse_g else NDArray(grad._t.float(), grad.context)
             self.update(index, master, g32, inner)
-            with torch.no_grad():
-                weight._t.copy_(master._t)
+            if getattr(weight, "stype", "default") != "default":
+                weight[:] = NDArray(master._t.to(weight._t.dtype), weight.context)     # storage-aware write-back
+            else:
+                with torch.no_grad():
+                    weight._t.copy_(master._t)
         else:
             self.update(index, weight, grad, state)
 

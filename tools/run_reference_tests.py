@@ -43,7 +43,6 @@ KNOWN_CAUSES = {
     "test_get_symbol": GETSYM, "test_inline": GETSYM,
     "test_parameter_row_sparse_data": SPARSEPARAM,
     "test_activations": "bit-exact ELU: expm1(x) here, exp(x) - 1 in the reference",
-    "test_adam": "fp16 + row_sparse + multi_precision Adam against the python reference optimizer",
     "test_batchnorm_fallback": "BatchNorm(fix_gamma=True) is expected to REFUSE sparse gamma; here it runs",
     "test_sparse_mathematical_core": "d gamma(x)/dx at 0: -inf here, +inf expected (the expectation depends on the scipy version)",
     "test_elemwise_binary_ops": "storage type of elemwise_div(row_sparse, row_sparse) corner cases",
