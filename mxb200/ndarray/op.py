@@ -131,9 +131,19 @@ def _mx_mod(a, b):
 
 modulo = _binary("modulo", _mx_mod)
 power = _binary("power", torch.pow)
-maximum = _binary("maximum", lambda a, b: torch.maximum(a, b) if isinstance(b, torch.Tensor) and isinstance(a, torch.Tensor)
+def _mx_maximum(a, b):
+    """Element-wise maximum of two arrays with the reference's tie rule for the gradient: at a == b the LEFT operand takes
+    all of it (mshadow_op ge / lt), where torch.maximum splits it in halves."""
+    return torch.where(a >= b, a, b)
+
+
+def _mx_minimum(a, b):
+    return torch.where(a <= b, a, b)
+
+
+maximum = _binary("maximum", lambda a, b: _mx_maximum(a, b) if isinstance(b, torch.Tensor) and isinstance(a, torch.Tensor)
                   else torch.clamp(a if isinstance(a, torch.Tensor) else b, min=b if isinstance(a, torch.Tensor) else a))
-minimum = _binary("minimum", lambda a, b: torch.minimum(a, b) if isinstance(b, torch.Tensor) and isinstance(a, torch.Tensor)
+minimum = _binary("minimum", lambda a, b: _mx_minimum(a, b) if isinstance(b, torch.Tensor) and isinstance(a, torch.Tensor)
                   else torch.clamp(a if isinstance(a, torch.Tensor) else b, max=b if isinstance(a, torch.Tensor) else a))
 hypot = _binary("hypot", torch.hypot)
 equal = _binary("equal", _cmpf(torch.eq))

@@ -119,8 +119,8 @@ _binary("_greater", _cmpf(torch.gt))
 _binary("_greater_equal", _cmpf(torch.ge))
 _binary("_lesser", _cmpf(torch.lt))
 _binary("_lesser_equal", _cmpf(torch.le))
-_binary("_maximum", torch.maximum)
-_binary("_minimum", torch.minimum)
+_binary("_maximum", _o._mx_maximum)
+_binary("_minimum", _o._mx_minimum)
 _binary("_mod", _o._mx_mod)
 _binary("_power", torch.pow)
 _binary("_hypot", torch.hypot)

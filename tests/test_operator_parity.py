@@ -213,3 +213,14 @@ def test_deferred_exception_is_delivered_once_and_reaches_executor_gradients():
     exe.backward()
     with pytest.raises(MXNetError):
         exe.grad_arrays[0].asnumpy()
+
+
+def test_maximum_minimum_gradient_goes_to_the_left_operand_at_ties():
+    a, b = mx.nd.array([1.0, 2.0, 3.0]), mx.nd.array([1.0, 5.0, 0.0])
+    a.attach_grad()
+    b.attach_grad()
+    with mx.autograd.record():
+        y = mx.nd.maximum(a, b) + mx.nd.minimum(a, b)
+    y.backward()
+    assert y.asnumpy().tolist() == [2.0, 7.0, 3.0]
+    assert a.grad.asnumpy().tolist() == [2.0, 1.0, 1.0] and b.grad.asnumpy().tolist() == [0.0, 1.0, 1.0]

@@ -45,7 +45,6 @@ KNOWN_CAUSES = {
     "test_activations": "bit-exact ELU: expm1(x) here, exp(x) - 1 in the reference",
     "test_batchnorm_fallback": "BatchNorm(fix_gamma=True) is expected to REFUSE sparse gamma; here it runs",
     "test_sparse_mathematical_core": "d gamma(x)/dx at 0: -inf here, +inf expected (the expectation depends on the scipy version)",
-    "test_elemwise_binary_ops": "storage type of elemwise_div(row_sparse, row_sparse) corner cases",
     "test_slice_pooling2d_slice_pooling2d": "16 layer combinations over a 0.5 GB input with 0.5 GB gradients compared through numpy: slower than the per-test time limit on this host",
     "test_batchnorm_training": "finite differences over 4-D inputs: at the per-test time limit on a loaded host",
     "test_multi_proposal_op": "O(n^2) NMS on the host: at the per-test time limit on a loaded host",
