@@ -135,3 +135,12 @@ def _install_fluent():
 
 
 _install_fluent()
+
+
+def __getattr__(name):
+    """``mx.nd.Custom`` before ``mx.operator`` was touched: importing the operator module registers it."""
+    if name == "Custom":
+        import importlib
+        importlib.import_module(__name__.rsplit(".", 1)[0] + ".operator")
+        return _OPS["Custom"]
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -8,6 +8,9 @@ from ..ndarray import op as _ndop
 
 
 def _lookup_op(name):
+    if name == "Custom" and _ndop.get(name) is None:
+        import importlib
+        importlib.import_module(__name__.rsplit(".", 1)[0] + ".operator")      # registers the Custom operator
     if _ndop.get(name) is None:
         return None
 
